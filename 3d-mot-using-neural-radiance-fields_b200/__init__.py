@@ -1,0 +1,31 @@
+"""star_b200 -- B200-native (sm_100a) implementation of the STaR / NeRF render hot path of
+burakcuhadar/3D-MOT-using-Neural-Radiance-Fields behind the reference's own Python API.
+
+    import star_b200                       # repo-root shim that loads this package
+    from star_b200.models.star__ import STaR
+    from star_b200.models.rendering__ import sample_pts, render_star_online
+
+`star_b200.install()` registers the mirrors as `models.rendering__`, `models.star__`, `models.nerf`,
+`models.embedder`, `models.resnet`, `models.types__` in sys.modules so that the reference's train
+scripts pick them up unmodified."""
+import sys
+
+from . import _capi, functional  # noqa: F401
+from .models import embedder, nerf, rendering__, resnet, star__, types__  # noqa: F401
+from .models.star__ import STaR  # noqa: F401
+
+__all__ = ["STaR", "functional", "install", "rendering__", "star__"]
+
+
+def install(package="models"):
+    """Make `from models.star__ import STaR` etc. resolve to the B200 path."""
+    import types
+    pkg = sys.modules.get(package)
+    if pkg is None:
+        pkg = types.ModuleType(package)
+        pkg.__path__ = []
+        sys.modules[package] = pkg
+    for name, mod in (("rendering__", rendering__), ("star__", star__), ("nerf", nerf), ("embedder", embedder),
+                      ("resnet", resnet), ("types__", types__)):
+        sys.modules[f"{package}.{name}"] = mod
+        setattr(pkg, name, mod)

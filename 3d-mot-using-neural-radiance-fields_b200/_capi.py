@@ -1,0 +1,120 @@
+"""ctypes binding of libstar_b200.so (include/star_b200.h).
+
+Fails loudly when the library is missing or a call returns a nonzero status: there is no CPU or
+PyTorch fallback for any entry point (north star: "no CPU fallback").
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstar_b200.so")
+
+PREC_F32, PREC_BF16 = 0, 1
+
+c_f = C.c_void_p      # device pointers are passed as raw addresses
+c_i64 = C.c_int64
+
+
+class StarNetDesc(C.Structure):
+    _fields_ = [("n_blocks", C.c_int32), ("L_xyz", C.c_int32), ("L_dir", C.c_int32), ("precision", C.c_int32)]
+
+
+class StarMultiOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "rgb", "disp", "acc", "depth", "weights", "rgb_static", "depth_static", "rgb_dynamic",
+        "depth_dynamic", "dynamic_transmittance", "rgb_dynamic_all", "regs")]
+
+
+_SIGS = {
+    "star_abi_version": (C.c_int, []),
+    "star_error_string": (C.c_char_p, [C.c_int]),
+    "star_last_cuda_error": (C.c_int, []),
+    "star_net_param_count": (C.c_size_t, [C.POINTER(StarNetDesc)]),
+    "star_packed_bytes": (C.c_size_t, [C.POINTER(StarNetDesc)]),
+    "star_pack_weights": (C.c_int, [C.POINTER(StarNetDesc), c_f, c_f, c_f]),
+    "star_sample_pts": (C.c_int, [c_f, c_f, c_f, c_f, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f]),
+    "star_embed": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f]),
+    "star_stash_bytes": (C.c_size_t, [C.POINTER(StarNetDesc), c_i64]),
+    "star_mlp_forward": (C.c_int, [C.POINTER(StarNetDesc), c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, c_f, c_f,
+                                   c_i64, c_f, c_f]),
+    "star_mlp_backward_workspace_bytes": (C.c_size_t, [C.POINTER(StarNetDesc), c_i64]),
+    "star_mlp_backward": (C.c_int, [C.POINTER(StarNetDesc), c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, c_f,
+                                    c_f, c_i64, c_f, c_f, c_f, c_f, c_f]),
+    "star_composite_single_forward": (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_float, C.c_int, c_f, c_f,
+                                                c_f, c_f, c_f, c_f, c_f]),
+    "star_composite_single_backward": (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_float, C.c_int, c_f, c_f,
+                                                 c_f, c_f, c_f, c_f, c_f, c_f]),
+    "star_composite_multi_ws_bytes": (C.c_size_t, [C.c_int]),
+    "star_composite_multi_forward": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_float,
+                                               C.c_int, C.c_int, C.POINTER(StarMultiOut), c_f, c_f]),
+    "star_composite_multi_backward": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_float,
+                                                C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
+                                                c_f]),
+    "star_sample_pdf": (C.c_int, [c_f, c_i64, c_f, c_i64, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f,
+                                  c_f, c_f]),
+    "star_invert_cdf": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f]),
+    "star_hierarchical": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+_lib = None
+
+
+class StarError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads libstar_b200.so once.  Missing library -> hard error (build with __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise StarError("libstar_b200.so is not built (%s); run `python -c 'import __graft_entry__ as g; "
+                            "g.build()'` -- there is no fallback path" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.star_abi_version() != 1:
+            raise StarError("libstar_b200.so ABI mismatch")
+        _lib = L
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        L = lib()
+        msg = L.star_error_string(code).decode()
+        extra = ""
+        if code == 6:
+            extra = " (cudaError %d)" % L.star_last_cuda_error()
+        raise StarError("%s failed: %s%s" % (what, msg, extra))
+
+
+def ptr(t):
+    """Device address of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise StarError("expected a CUDA tensor: the STaR B200 path has no CPU implementation")
+    if not t.is_contiguous():
+        raise StarError("expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def f32(t):
+    if t.dtype != torch.float32:
+        raise StarError("expected float32, got %s" % t.dtype)
+    return ptr(t)
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def net_desc(n_blocks, L_xyz, L_dir, precision):
+    return StarNetDesc(int(n_blocks), int(L_xyz), int(L_dir), int(precision))

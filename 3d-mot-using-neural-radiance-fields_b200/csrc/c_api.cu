@@ -1,0 +1,104 @@
+// extern "C" entry points of libstar_b200.so that are not kernel-file local (see include/star_b200.h).
+#include "star_common.cuh"
+#include "mlp_layout.h"
+
+int g_star_last_cuda_error = 0;
+
+int star_f32_pack(const MlpLayout& lay, const float* master, void* packed, cudaStream_t st);
+int star_f32_forward(const MlpLayout& lay, const void* packed, const float* pts, const float* viewdirs,
+                     const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
+                     float* raw_rgb, int64_t ray_stride, void* stash, cudaStream_t st);
+int star_f32_backward(const MlpLayout& lay, const void* packed, const float* pts, const float* viewdirs,
+                      const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S,
+                      const float* d_raw_alpha, const float* d_raw_rgb, int64_t ray_stride, const void* stash,
+                      void* workspace, float* grad_flat, float* pose_acc, cudaStream_t st);
+
+extern "C" int star_abi_version(void) { return STAR_ABI_VERSION; }
+extern "C" int star_last_cuda_error(void) { return g_star_last_cuda_error; }
+
+extern "C" const char* star_error_string(int code) {
+  switch (code) {
+    case STAR_OK: return "ok";
+    case STAR_E_BAD_SHAPE: return "size out of the supported range";
+    case STAR_E_UNSUPPORTED: return "unsupported width / depth / encoding / precision";
+    case STAR_E_NULL: return "required pointer is NULL";
+    case STAR_E_ALIGN: return "pointer alignment violated";
+    case STAR_E_WORKSPACE: return "workspace too small";
+    case STAR_E_CUDA: return "CUDA runtime error (see star_last_cuda_error)";
+    default: return "unknown error code";
+  }
+}
+
+extern "C" size_t star_net_param_count(const StarNetDesc* d) {
+  MlpLayout lay;
+  if (!d || star_make_layout(d, &lay)) return 0;
+  return (size_t)lay.n_master;
+}
+
+extern "C" size_t star_packed_bytes(const StarNetDesc* d) {
+  MlpLayout lay;
+  if (!d || star_make_layout(d, &lay)) return 0;
+  if (d->precision == STAR_PREC_F32) return sizeof(float) * (size_t)lay.n_packed;
+  return 0;
+}
+
+extern "C" int star_pack_weights(const StarNetDesc* d, const float* flat_master, void* packed, void* stream) {
+  if (!d || !flat_master || !packed) return STAR_E_NULL;
+  MlpLayout lay;
+  int rc = star_make_layout(d, &lay);
+  if (rc) return rc;
+  if (d->precision == STAR_PREC_F32) return star_f32_pack(lay, flat_master, packed, (cudaStream_t)stream);
+  return STAR_E_UNSUPPORTED;
+}
+
+extern "C" size_t star_stash_bytes(const StarNetDesc* d, int64_t n_samples) {
+  MlpLayout lay;
+  if (!d || star_make_layout(d, &lay) || n_samples < 0) return 0;
+  if (d->precision == STAR_PREC_F32) return sizeof(float) * (size_t)lay.stash_cols * (size_t)n_samples;
+  return 0;
+}
+
+extern "C" size_t star_mlp_backward_workspace_bytes(const StarNetDesc* d, int64_t n_samples) {
+  MlpLayout lay;
+  if (!d || star_make_layout(d, &lay) || n_samples < 0) return 0;
+  if (d->precision == STAR_PREC_F32) return sizeof(float) * (size_t)lay.g_cols * (size_t)n_samples;
+  return 0;
+}
+
+extern "C" int star_mlp_forward(const StarNetDesc* d, const void* packed, const float* pts, const float* viewdirs,
+                                const float* pose12, const float* enc_scale_xyz, const float* enc_scale_dir, int R,
+                                int S, float* raw_alpha, float* raw_rgb, int64_t alpha_ray_stride, void* stash,
+                                void* stream) {
+  if (!d || !packed || !pts || !viewdirs || !raw_alpha || !raw_rgb) return STAR_E_NULL;
+  if (R < 0 || S < 1 || alpha_ray_stride < S) return STAR_E_BAD_SHAPE;
+  if (R == 0) return STAR_OK;
+  MlpLayout lay;
+  int rc = star_make_layout(d, &lay);
+  if (rc) return rc;
+  if (d->precision == STAR_PREC_F32)
+    return star_f32_forward(lay, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, raw_alpha,
+                            raw_rgb, alpha_ray_stride, stash, (cudaStream_t)stream);
+  return STAR_E_UNSUPPORTED;
+}
+
+extern "C" int star_mlp_backward(const StarNetDesc* d, const void* packed, const float* flat_master,
+                                 const float* pts, const float* viewdirs, const float* pose12,
+                                 const float* enc_scale_xyz, const float* enc_scale_dir, int R, int S,
+                                 const float* d_raw_alpha, const float* d_raw_rgb, int64_t alpha_ray_stride,
+                                 const void* stash, void* workspace, float* grad_flat, float* pose_acc,
+                                 void* stream) {
+  (void)flat_master;
+  if (!d || !packed || !pts || !viewdirs || !d_raw_alpha || !d_raw_rgb || !stash || !workspace || !grad_flat)
+    return STAR_E_NULL;
+  if (pose12 && !pose_acc) return STAR_E_NULL;
+  if (R < 0 || S < 1 || alpha_ray_stride < S) return STAR_E_BAD_SHAPE;
+  if (R == 0) return STAR_OK;
+  MlpLayout lay;
+  int rc = star_make_layout(d, &lay);
+  if (rc) return rc;
+  if (d->precision == STAR_PREC_F32)
+    return star_f32_backward(lay, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, d_raw_alpha,
+                             d_raw_rgb, alpha_ray_stride, stash, workspace, grad_flat, pose_acc,
+                             (cudaStream_t)stream);
+  return STAR_E_UNSUPPORTED;
+}

@@ -1,0 +1,301 @@
+// Ray sampling kernels: stratified samples (a1), positional encoding (a3, stand-alone form),
+// inverse-CDF sampling (a9) and the coarse->fine hierarchical step (a10).
+// All arithmetic that feeds index decisions is written with explicit round-to-nearest intrinsics
+// (__fadd_rn / __fmul_rn / __fdiv_rn) so that nvcc cannot contract it into FMAs: every reference
+// op (one eager ATen kernel each) is rounded separately, and so is every op here.
+#include "star_common.cuh"
+
+// ------------------------------------------------------------------------------------------ a1
+// models/rendering__.py:87-110.  One thread per (ray, sample); pts written as 3 coalesced floats.
+__global__ void sample_pts_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                  const float* __restrict__ t_vals, const float* __restrict__ t_rand,
+                                  float near_, float far_, int R, int Nc, int lindisp,
+                                  float* __restrict__ pts, float* __restrict__ z_vals) {
+  const int64_t total = (int64_t)R * Nc;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / Nc), s = (int)(i % Nc);
+    auto zval = [&](int k) -> float {
+      const float t = t_vals[k];
+      if (!lindisp) return __fadd_rn(__fmul_rn(near_, __fsub_rn(1.f, t)), __fmul_rn(far_, t));
+      const float a = __fmul_rn(__fdiv_rn(1.f, near_), __fsub_rn(1.f, t));
+      const float b = __fmul_rn(__fdiv_rn(1.f, far_), t);
+      return __fdiv_rn(1.f, __fadd_rn(a, b));
+    };
+    float z = zval(s);
+    if (t_rand != nullptr) {  // :99-106 stratified jitter with injected noise
+      const float lo = (s == 0) ? z : __fmul_rn(0.5f, __fadd_rn(z, zval(s - 1)));
+      const float hi = (s == Nc - 1) ? z : __fmul_rn(0.5f, __fadd_rn(zval(s + 1), z));
+      z = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), t_rand[i]));
+    }
+    z_vals[i] = z;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      pts[i * 3 + c] = __fadd_rn(rays_o[r * 3 + c], __fmul_rn(rays_d[r * 3 + c], z));
+  }
+}
+
+extern "C" int star_sample_pts(const float* rays_o, const float* rays_d, const float* t_vals,
+                               const float* t_rand, float near_, float far_, int R, int Nc, int lindisp,
+                               float* pts, float* z_vals, void* stream) {
+  if (!rays_o || !rays_d || !t_vals || !pts || !z_vals) return STAR_E_NULL;
+  if (R < 0 || Nc < 1) return STAR_E_BAD_SHAPE;
+  if (R == 0) return STAR_OK;
+  const int64_t total = (int64_t)R * Nc;
+  const int threads = 256;
+  const int blocks = (int)((total + threads - 1) / threads < 148 * 16 ? (total + threads - 1) / threads : 148 * 16);
+  sample_pts_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_vals, t_rand, near_, far_, R,
+                                                                  Nc, lindisp, pts, z_vals);
+  return star_check_launch();
+}
+
+// ------------------------------------------------------------------------------------------ a3
+// models/embedder.py:81-112 -- one thread per output element so that writes are coalesced.
+__global__ void embed_kernel(const float* __restrict__ x, int64_t M, int L, const float* __restrict__ scale,
+                             float* __restrict__ out) {
+  const int D = 3 + 6 * L;
+  const int64_t total = M * D;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / D;
+    const int j = (int)(i % D);
+    float v;
+    if (j < 3) {
+      v = x[m * 3 + j];
+    } else {
+      const int q = j - 3, k = q / 6, w = q % 6, c = w % 3;
+      const float a = __fmul_rn(x[m * 3 + c], exp2f((float)k));
+      v = (w < 3) ? sinf(a) : cosf(a);
+    }
+    if (scale != nullptr) v = __fmul_rn(v, scale[j]);
+    out[i] = v;
+  }
+}
+
+extern "C" int star_embed(const float* x, int M, int L, const float* scale, float* out, void* stream) {
+  if (!x || !out) return STAR_E_NULL;
+  if (M < 0 || L < 0 || L > 16) return STAR_E_BAD_SHAPE;
+  if (M == 0) return STAR_OK;
+  const int64_t total = (int64_t)M * (3 + 6 * L);
+  const int threads = 256;
+  int64_t blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  embed_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(x, M, L, scale, out);
+  return star_check_launch();
+}
+
+// ------------------------------------------------------------------------------------------ a9
+// One warp per ray.  cdf / bins of the ray live in shared memory.
+// Defined arithmetic (DESIGN.md "sample_pdf arithmetic"):
+//   w   = weights + 1e-5f                                   (rendering__.py:722)
+//   s   = fp32( sum_k w_k accumulated in fp64 )             exactly rounded normaliser (:723)
+//   pdf = w / s                                             IEEE fp32 division
+//   cdf = fp32( prefix sums of pdf accumulated in fp64 )    == torch CPU cumsum (:733-734)
+// The fp64 sums of <= 2^10 fp32 values spanning <= 2^17 in magnitude are exact, so the warp-parallel
+// order gives the same bits as a sequential loop.
+__device__ __forceinline__ void build_cdf_warp(const float* __restrict__ w_row, int nw, float* cdf, int lane) {
+  double part = 0.0;
+  for (int k = lane; k < nw; k += 32) part += (double)__fadd_rn(w_row[k], 1e-5f);
+  const float s = (float)warp_sum_d(part);
+  double carry = 0.0;
+  if (lane == 0) cdf[0] = 0.f;
+  for (int base = 0; base < nw; base += 32) {
+    const int k = base + lane;
+    double p = 0.0;
+    if (k < nw) p = (double)__fdiv_rn(__fadd_rn(w_row[k], 1e-5f), s);
+    const double incl = warp_scan_sum_d(p, lane) + carry;
+    if (k < nw) cdf[k + 1] = (float)incl;
+    carry = __shfl_sync(STAR_FULL_MASK, incl, 31);
+  }
+}
+
+// searchsorted(cdf, u, right=True) (:745) + gather + lerp (:746-759)
+__device__ __forceinline__ float invert_one(const float* cdf, const float* bins, int nb, float u, int& inds,
+                                            int& below, int& above) {
+  int lo = 0, hi = nb;  // first index with cdf[idx] > u
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+  }
+  inds = lo;
+  below = max(0, lo - 1);
+  above = min(nb - 1, lo);
+  const float c0 = cdf[below], c1 = cdf[above];
+  float denom = __fsub_rn(c1, c0);
+  if (denom < 1e-5f) denom = 1.f;
+  const float t = __fdiv_rn(__fsub_rn(u, c0), denom);
+  const float b0 = bins[below], b1 = bins[above];
+  return __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+}
+
+template <bool HAVE_CDF>
+__global__ void sample_pdf_kernel(const float* __restrict__ bins, int64_t bins_stride,
+                                  const float* __restrict__ weights, int64_t w_stride,
+                                  const float* __restrict__ cdf_in, const float* __restrict__ u,
+                                  const float* __restrict__ u_det, int R, int nb, int Ni,
+                                  float* __restrict__ samples, int64_t* __restrict__ inds_o,
+                                  int64_t* __restrict__ below_o, int64_t* __restrict__ above_o,
+                                  float* __restrict__ cdf_o) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  float* cdf = smem + (size_t)warp * 2 * nb;
+  float* sb = cdf + nb;
+  for (int r = blockIdx.x * wpb + warp; r < R; r += gridDim.x * wpb) {
+    if (HAVE_CDF) {
+      for (int k = lane; k < nb; k += 32) cdf[k] = cdf_in[(int64_t)r * nb + k];
+    } else {
+      build_cdf_warp(weights + (int64_t)r * w_stride, nb - 1, cdf, lane);
+    }
+    for (int k = lane; k < nb; k += 32) sb[k] = bins[(int64_t)r * bins_stride + k];
+    __syncwarp();
+    if (cdf_o != nullptr)
+      for (int k = lane; k < nb; k += 32) cdf_o[(int64_t)r * nb + k] = cdf[k];
+    for (int j = lane; j < Ni; j += 32) {
+      const float uu = (u != nullptr) ? u[(int64_t)r * Ni + j] : u_det[j];
+      int i0, b0, a0;
+      const float s = invert_one(cdf, sb, nb, uu, i0, b0, a0);
+      const int64_t o = (int64_t)r * Ni + j;
+      samples[o] = s;
+      if (inds_o) inds_o[o] = i0;
+      if (below_o) below_o[o] = b0;
+      if (above_o) above_o[o] = a0;
+    }
+    __syncwarp();
+  }
+}
+
+static int launch_cfg_warp_per_ray(int R, size_t smem_per_warp, int& blocks, int& threads, size_t& smem) {
+  int wpb = 4;
+  while (wpb > 1 && smem_per_warp * wpb > 200 * 1024) wpb >>= 1;
+  if (smem_per_warp * wpb > 200 * 1024) return STAR_E_BAD_SHAPE;
+  threads = wpb * 32;
+  smem = smem_per_warp * wpb;
+  int64_t b = ((int64_t)R + wpb - 1) / wpb;
+  if (b > 148 * 32) b = 148 * 32;
+  blocks = (int)b;
+  return STAR_OK;
+}
+
+extern "C" int star_sample_pdf(const float* bins, int64_t bins_stride, const float* weights, int64_t w_stride,
+                               const float* u, const float* u_det, int R, int nb, int Ni, float* samples,
+                               int64_t* inds, int64_t* below, int64_t* above, float* cdf, void* stream) {
+  if (!bins || !weights || !samples || (!u && !u_det)) return STAR_E_NULL;
+  if (R < 0 || nb < 2 || Ni < 1) return STAR_E_BAD_SHAPE;
+  if (R == 0) return STAR_OK;
+  int blocks, threads;
+  size_t smem;
+  int rc = launch_cfg_warp_per_ray(R, sizeof(float) * 2 * nb, blocks, threads, smem);
+  if (rc) return rc;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(sample_pdf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  sample_pdf_kernel<false><<<blocks, threads, smem, (cudaStream_t)stream>>>(
+      bins, bins_stride, weights, w_stride, nullptr, u, u_det, R, nb, Ni, samples, inds, below, above, cdf);
+  return star_check_launch();
+}
+
+extern "C" int star_invert_cdf(const float* bins, const float* cdf, const float* u, int R, int nb, int Ni,
+                               float* samples, int64_t* inds, int64_t* below, int64_t* above, void* stream) {
+  if (!bins || !cdf || !u || !samples) return STAR_E_NULL;
+  if (R < 0 || nb < 1 || Ni < 1) return STAR_E_BAD_SHAPE;
+  if (R == 0) return STAR_OK;
+  int blocks, threads;
+  size_t smem;
+  int rc = launch_cfg_warp_per_ray(R, sizeof(float) * 2 * nb, blocks, threads, smem);
+  if (rc) return rc;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(sample_pdf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  sample_pdf_kernel<true><<<blocks, threads, smem, (cudaStream_t)stream>>>(
+      bins, nb, nullptr, 0, cdf, u, nullptr, R, nb, Ni, samples, inds, below, above, nullptr);
+  return star_check_launch();
+}
+
+// ------------------------------------------------------------------------------------------ a10
+// z_mid -> sample_pdf -> sort(cat(z_vals, z_samples)) -> z_std, pts.  One warp per ray.
+// smem per warp: cdf[nb] | bins[nb] | zall[P]   (P = next pow2 >= Nc+Ni, padded with +inf)
+__global__ void hierarchical_kernel(const float* __restrict__ z_vals, const float* __restrict__ weights,
+                                    const float* __restrict__ u, const float* __restrict__ u_det,
+                                    const float* __restrict__ rays_o, const float* __restrict__ rays_d, int R,
+                                    int Nc, int Ni, int P, float* __restrict__ z_samples,
+                                    float* __restrict__ z_all, float* __restrict__ z_std,
+                                    float* __restrict__ pts_fine) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int nb = Nc - 1, Nf = Nc + Ni;
+  float* cdf = smem + (size_t)warp * (2 * nb + P);
+  float* sb = cdf + nb;
+  float* za = sb + nb;
+  for (int r = blockIdx.x * wpb + warp; r < R; r += gridDim.x * wpb) {
+    const float* zr = z_vals + (int64_t)r * Nc;
+    build_cdf_warp(weights + (int64_t)r * Nc + 1, Nc - 2, cdf, lane);  // weights[..., 1:-1]  (:131,274)
+    for (int k = lane; k < nb; k += 32) sb[k] = __fmul_rn(0.5f, __fadd_rn(zr[k + 1], zr[k]));  // z_mid (:128)
+    for (int k = lane; k < Nc; k += 32) za[k] = zr[k];
+    for (int k = Nf + lane; k < P; k += 32) za[k] = __int_as_float(0x7f800000);
+    __syncwarp();
+    float sum = 0.f;
+    for (int j = lane; j < Ni; j += 32) {
+      const float uu = (u != nullptr) ? u[(int64_t)r * Ni + j] : u_det[j];
+      int i0, b0, a0;
+      const float s = invert_one(cdf, sb, nb, uu, i0, b0, a0);
+      z_samples[(int64_t)r * Ni + j] = s;
+      za[Nc + j] = s;
+      sum += s;
+    }
+    // z_std = std(z_samples, unbiased=False)   (:144,296)
+    const float mean = warp_sum(sum) / (float)Ni;
+    __syncwarp();
+    float var = 0.f;
+    for (int j = lane; j < Ni; j += 32) {
+      const float d = za[Nc + j] - mean;
+      var += d * d;
+    }
+    var = warp_sum(var) / (float)Ni;
+    if (lane == 0) z_std[r] = sqrtf(var);
+    // bitonic sort of za[0..P)   (torch.sort of the concatenation, :136,279 -- values only)
+    for (int k = 2; k <= P; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        __syncwarp();
+        for (int i = lane; i < P; i += 32) {
+          const int l = i ^ j;
+          if (l > i) {
+            const float a = za[i], b = za[l];
+            const bool up = ((i & k) == 0);
+            if ((a > b) == up) { za[i] = b; za[l] = a; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    for (int k = lane; k < Nf; k += 32) z_all[(int64_t)r * Nf + k] = za[k];
+    if (pts_fine != nullptr) {
+      const float ox = rays_o[r * 3 + 0], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
+      const float dx = rays_d[r * 3 + 0], dy = rays_d[r * 3 + 1], dz = rays_d[r * 3 + 2];
+      for (int i = lane; i < Nf * 3; i += 32) {
+        const int s = i / 3, c = i - s * 3;
+        const float o = c == 0 ? ox : (c == 1 ? oy : oz), d = c == 0 ? dx : (c == 1 ? dy : dz);
+        pts_fine[(int64_t)r * Nf * 3 + i] = __fadd_rn(o, __fmul_rn(d, za[s]));
+      }
+    }
+    __syncwarp();
+  }
+}
+
+extern "C" int star_hierarchical(const float* z_vals, const float* weights, const float* u, const float* u_det,
+                                 const float* rays_o, const float* rays_d, int R, int Nc, int Ni,
+                                 float* z_samples, float* z_all, float* z_std, float* pts_fine, void* stream) {
+  if (!z_vals || !weights || !z_samples || !z_all || !z_std || (!u && !u_det)) return STAR_E_NULL;
+  if (pts_fine && (!rays_o || !rays_d)) return STAR_E_NULL;
+  if (R < 0 || Nc < 3 || Ni < 1 || Nc + Ni > 8192) return STAR_E_BAD_SHAPE;
+  if (R == 0) return STAR_OK;
+  int P = 2;
+  while (P < Nc + Ni) P <<= 1;
+  int blocks, threads;
+  size_t smem;
+  int rc = launch_cfg_warp_per_ray(R, sizeof(float) * (2 * (Nc - 1) + P), blocks, threads, smem);
+  if (rc) return rc;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(hierarchical_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  hierarchical_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>(z_vals, weights, u, u_det, rays_o, rays_d,
+                                                                       R, Nc, Ni, P, z_samples, z_all, z_std,
+                                                                       pts_fine);
+  return star_check_launch();
+}

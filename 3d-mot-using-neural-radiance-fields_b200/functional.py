@@ -1,0 +1,413 @@
+"""torch-facing operators over the C ABI (libstar_b200.so): thin argument marshalling plus
+torch.autograd.Function wrappers.  PyTorch supplies device memory, streams and the autograd graph;
+all arithmetic happens in the CUDA kernels.  Reference citations are into /root/reference.
+"""
+import ctypes as C
+import os
+
+import torch
+from torch.autograd import Function
+
+from . import _capi
+from ._capi import check, f32, ptr, stream
+
+# Upper bound on samples handled by one MLP launch group and on bytes of saved activations kept
+# between forward and backward (beyond it the backward re-runs the forward per ray chunk).
+MAX_SAMPLES_PER_LAUNCH = int(os.environ.get("STAR_B200_MAX_SAMPLES", 1 << 19))
+STASH_BUDGET_BYTES = int(float(os.environ.get("STAR_B200_STASH_GB", "24")) * (1 << 30))
+
+# instrumentation for bench.py: number of kernel-launching C-ABI calls issued
+LAUNCH_COUNTER = {"calls": 0}
+
+
+def _count(n=1):
+    LAUNCH_COUNTER["calls"] += n
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------ a1
+_LINSPACE_CACHE = {}
+
+
+def _linspace01(n, device):
+    key = (n, str(device))
+    t = _LINSPACE_CACHE.get(key)
+    if t is None:
+        t = torch.linspace(0.0, 1.0, steps=n).to(device)   # host formula, then one H2D copy (cached)
+        _LINSPACE_CACHE[key] = t
+    return t
+
+
+def sample_pts(rays_o, rays_d, near, far, N_samples, lindisp=False, t_rand=None):
+    """models/rendering__.py:75-112 on the GPU.  t_rand: injected jitter or None."""
+    rays_o, rays_d = _c(rays_o), _c(rays_d)
+    R = rays_o.shape[0]
+    pts = torch.empty((R, N_samples, 3), device=rays_o.device, dtype=torch.float32)
+    z = torch.empty((R, N_samples), device=rays_o.device, dtype=torch.float32)
+    t_vals = _linspace01(N_samples, rays_o.device)
+    if t_rand is not None:
+        t_rand = _c(t_rand)
+    check(_capi.lib().star_sample_pts(f32(rays_o), f32(rays_d), f32(t_vals), f32(t_rand) if t_rand is not None else None,
+                                      float(near), float(far), R, N_samples, int(bool(lindisp)), f32(pts), f32(z),
+                                      stream()), "star_sample_pts")
+    _count()
+    return pts, z
+
+
+# ------------------------------------------------------------------------------------------ a3
+def embed(x, L, scale=None):
+    """models/embedder.py:81-112 (stand-alone form; the MLP kernels encode in registers)."""
+    x = _c(x)
+    M = x.shape[0]
+    out = torch.empty((M, 3 + 6 * L), device=x.device, dtype=torch.float32)
+    check(_capi.lib().star_embed(f32(x), M, L, f32(scale) if scale is not None else None, f32(out), stream()),
+          "star_embed")
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------ a5/a6
+class CompositeSingle(Function):
+    """raw2outputs (models/rendering__.py:307-379): returns rgb, disp, acc, depth, weights, dists."""
+
+    @staticmethod
+    def forward(ctx, raw_alpha, raw_rgb, z_vals, rays_d, far_dist, white_bkgd):
+        raw_alpha, raw_rgb, z_vals, rays_d = _c(raw_alpha), _c(raw_rgb), _c(z_vals), _c(rays_d)
+        R, S = raw_alpha.shape
+        dev = raw_alpha.device
+        rgb = torch.empty((R, 3), device=dev)
+        disp, acc, depth = (torch.empty((R,), device=dev) for _ in range(3))
+        weights = torch.empty((R, S), device=dev)
+        dists = torch.empty((R, S), device=dev)
+        check(_capi.lib().star_composite_single_forward(
+            f32(raw_alpha), f32(raw_rgb), f32(z_vals), f32(rays_d), R, S, float(far_dist), int(bool(white_bkgd)),
+            f32(rgb), f32(disp), f32(acc), f32(depth), f32(weights), f32(dists), stream()),
+            "star_composite_single_forward")
+        _count()
+        ctx.save_for_backward(raw_alpha, raw_rgb, z_vals, rays_d)
+        ctx.cfg = (float(far_dist), int(bool(white_bkgd)))
+        ctx.mark_non_differentiable(dists)
+        return rgb, disp, acc, depth, weights, dists
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_disp, g_acc, g_depth, g_weights, _g_dists):
+        raw_alpha, raw_rgb, z_vals, rays_d = ctx.saved_tensors
+        R, S = raw_alpha.shape
+        far_dist, white = ctx.cfg
+        d_alpha = torch.empty_like(raw_alpha)
+        d_rgb = torch.empty_like(raw_rgb)
+        g = [None if t is None else _c(t) for t in (g_rgb, g_disp, g_acc, g_depth, g_weights)]
+        check(_capi.lib().star_composite_single_backward(
+            f32(raw_alpha), f32(raw_rgb), f32(z_vals), f32(rays_d), R, S, far_dist, white,
+            *[f32(t) if t is not None else None for t in g], f32(d_alpha), f32(d_rgb), stream()),
+            "star_composite_single_backward")
+        _count()
+        return d_alpha, d_rgb, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------ a7/a8
+STAR_OUT_KEYS = ("rgb", "disp", "acc", "depth", "weights", "rgb_static", "depth_static", "rgb_dynamic",
+                 "depth_dynamic", "dynamic_transmittance", "rgb_dynamic_all", "regs")
+
+
+class CompositeStar(Function):
+    """raw2outputs_star + regularisers (models/rendering__.py:383-576, :612-715).
+    Returns the tensors of STAR_OUT_KEYS (rgb_dynamic_all is an empty tensor when test=False)."""
+
+    @staticmethod
+    def forward(ctx, ra_s, rc_s, ra_d, rc_d, z_vals, rays_d, far_dist, white_bkgd, chunk, test):
+        ra_s, rc_s, ra_d, rc_d, z_vals, rays_d = (_c(t) for t in (ra_s, rc_s, ra_d, rc_d, z_vals, rays_d))
+        R, V, S = ra_d.shape
+        dev = ra_s.device
+        e = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+        out = dict(rgb=e(R, 3), disp=e(R), acc=e(R), depth=e(R), weights=e(R, S), rgb_static=e(R, 3),
+                   depth_static=e(R), rgb_dynamic=e(R, V, 3), depth_dynamic=e(R, V), dynamic_transmittance=e(R, V),
+                   rgb_dynamic_all=e(R, 3) if test else e(0), regs=e(5))
+        L = _capi.lib()
+        ws = torch.empty((L.star_composite_multi_ws_bytes(R) // 4,), device=dev, dtype=torch.float32)
+        mo = _capi.StarMultiOut(*[ptr(out[k]) if out[k].numel() else None for k in STAR_OUT_KEYS])
+        check(L.star_composite_multi_forward(f32(ra_s), f32(rc_s), f32(ra_d), f32(rc_d), f32(z_vals), f32(rays_d),
+                                             R, V, S, float(far_dist), int(bool(white_bkgd)), int(chunk),
+                                             C.byref(mo), ptr(ws), stream()), "star_composite_multi_forward")
+        _count(2)
+        ctx.save_for_backward(ra_s, rc_s, ra_d, rc_d, z_vals, rays_d)
+        ctx.cfg = (float(far_dist), int(bool(white_bkgd)), int(chunk))
+        # per-field visualisation products: not differentiated (reference training never reads them
+        # in a loss, train_online__.py:158-273)
+        ctx.mark_non_differentiable(out["rgb_static"], out["depth_static"], out["rgb_dynamic"],
+                                    out["depth_dynamic"], out["dynamic_transmittance"], out["rgb_dynamic_all"])
+        return tuple(out[k] for k in STAR_OUT_KEYS)
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_disp, g_acc, g_depth, g_weights, _a, _b, _c2, _d, _e, _f, g_regs):
+        ra_s, rc_s, ra_d, rc_d, z_vals, rays_d = ctx.saved_tensors
+        R, V, S = ra_d.shape
+        far_dist, white, chunk = ctx.cfg
+        d = [torch.empty_like(t) for t in (ra_s, rc_s, ra_d, rc_d)]
+        g = [None if t is None else _c(t) for t in (g_rgb, g_disp, g_acc, g_depth, g_weights, g_regs)]
+        check(_capi.lib().star_composite_multi_backward(
+            f32(ra_s), f32(rc_s), f32(ra_d), f32(rc_d), f32(z_vals), f32(rays_d), R, V, S, far_dist, white, chunk,
+            *[f32(t) if t is not None else None for t in g], *[f32(t) for t in d], stream()),
+            "star_composite_multi_backward")
+        _count()
+        return d[0], d[1], d[2], d[3], None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------ a9
+def sample_pdf(bins, weights, N_samples, det=False, u=None, return_details=False):
+    """models/rendering__.py:719-761.  `weights` may be a non-contiguous last-dim-contiguous view
+    (the reference passes weights[..., 1:-1]); `u` injects the uniform draws."""
+    bins = _c(bins)
+    if weights.stride(-1) != 1:
+        weights = weights.contiguous()
+    R, nb = bins.shape
+    assert weights.shape == (R, nb - 1), "sample_pdf: weights must have one column less than bins"
+    dev = bins.device
+    u_det = None
+    if u is None:
+        if det:
+            u_det = _linspace01(N_samples, dev)
+        else:
+            u = torch.rand((R, N_samples), device=dev)
+    if u is not None:
+        u = _c(u)
+    samples = torch.empty((R, N_samples), device=dev)
+    details = {}
+    if return_details:
+        details = dict(inds=torch.empty((R, N_samples), device=dev, dtype=torch.int64),
+                       below=torch.empty((R, N_samples), device=dev, dtype=torch.int64),
+                       above=torch.empty((R, N_samples), device=dev, dtype=torch.int64),
+                       cdf=torch.empty((R, nb), device=dev))
+    wptr = weights.data_ptr()
+    check(_capi.lib().star_sample_pdf(f32(bins), nb, wptr, weights.stride(0), f32(u) if u is not None else None,
+                                      f32(u_det) if u_det is not None else None, R, nb, N_samples, f32(samples),
+                                      ptr(details.get("inds")), ptr(details.get("below")), ptr(details.get("above")),
+                                      ptr(details.get("cdf")), stream()), "star_sample_pdf")
+    _count()
+    if return_details:
+        details["u"] = u if u is not None else u_det.expand(R, N_samples)
+        return samples, details
+    return samples
+
+
+def invert_cdf(bins, cdf, u):
+    """searchsorted(right=True) + gather + lerp on a caller-supplied cdf (:744-761)."""
+    bins, cdf, u = _c(bins), _c(cdf), _c(u)
+    R, nb = cdf.shape
+    Ni = u.shape[1]
+    dev = bins.device
+    samples = torch.empty((R, Ni), device=dev)
+    inds, below, above = (torch.empty((R, Ni), device=dev, dtype=torch.int64) for _ in range(3))
+    check(_capi.lib().star_invert_cdf(f32(bins), f32(cdf), f32(u), R, nb, Ni, f32(samples), ptr(inds), ptr(below),
+                                      ptr(above), stream()), "star_invert_cdf")
+    _count()
+    return samples, inds, below, above
+
+
+def hierarchical(z_vals, weights, N_importance, det, rays_o, rays_d, u=None, want_pts=True):
+    """models/rendering__.py:128-144 / :271-296 in one kernel.  Returns z_samples, z_all, z_std, pts_fine.
+    Everything is detached, as in the reference (z_samples.detach(), :135,278)."""
+    z_vals, weights = _c(z_vals.detach()), _c(weights.detach())
+    rays_o, rays_d = _c(rays_o), _c(rays_d)
+    R, Nc = z_vals.shape
+    dev = z_vals.device
+    u_det = None
+    if u is None:
+        if det:
+            u_det = _linspace01(N_importance, dev)
+        else:
+            u = torch.rand((R, N_importance), device=dev)
+    if u is not None:
+        u = _c(u)
+    zs = torch.empty((R, N_importance), device=dev)
+    z_all = torch.empty((R, Nc + N_importance), device=dev)
+    z_std = torch.empty((R,), device=dev)
+    pts = torch.empty((R, Nc + N_importance, 3), device=dev) if want_pts else None
+    check(_capi.lib().star_hierarchical(f32(z_vals), f32(weights), f32(u) if u is not None else None,
+                                        f32(u_det) if u_det is not None else None, f32(rays_o), f32(rays_d), R, Nc,
+                                        N_importance, f32(zs), f32(z_all), f32(z_std), ptr(pts), stream()),
+          "star_hierarchical")
+    _count()
+    return zs, z_all, z_std, pts
+
+
+# ------------------------------------------------------------------------------------------ a4 + K2
+class NetRuntime:
+    """Kernel-side state of one NeRF MLP: the flat fp32 master vector (order of include/star_b200.h)
+    and the packed weight image, rebuilt when any parameter's version / storage changes."""
+
+    def __init__(self, module, n_blocks, L_xyz, L_dir):
+        self.module = module
+        self.n_blocks, self.L_xyz, self.L_dir = n_blocks, L_xyz, L_dir
+        self._key = None
+        self._flat = None
+        self._packed = {}
+
+    def ordered_params(self):
+        m = self.module
+        lins = [m.pts_net.lin_in]
+        for b in m.pts_net.blocks:
+            lins += [b.fc_0, b.fc_1]
+        lins += [m.pts_net.lin_out, m.alpha_linear, m.feature_linear, m.views_linears[0], m.rgb_linear]
+        out = []
+        for l in lins:
+            out += [l.weight, l.bias]
+        return out
+
+    def desc(self, precision):
+        return _capi.net_desc(self.n_blocks, self.L_xyz, self.L_dir, precision)
+
+    def refresh(self, precision):
+        params = self.ordered_params()
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if key != self._key:
+            self._flat = torch.cat([p.detach().reshape(-1) for p in params])
+            self._packed = {}
+            self._key = key
+        if precision not in self._packed:
+            d = self.desc(precision)
+            L = _capi.lib()
+            nbytes = L.star_packed_bytes(C.byref(d))
+            if nbytes == 0:
+                raise _capi.StarError("unsupported network shape / precision for the packed weight image")
+            assert self._flat.numel() == L.star_net_param_count(C.byref(d))
+            packed = torch.empty((nbytes,), device=self._flat.device, dtype=torch.uint8)
+            check(L.star_pack_weights(C.byref(d), f32(self._flat), ptr(packed), stream()), "star_pack_weights")
+            _count()
+            self._packed[precision] = packed
+        return self._flat, self._packed[precision]
+
+
+def _ray_chunks(R, S):
+    per = max(1, MAX_SAMPLES_PER_LAUNCH // S)
+    return [(a, min(R, a + per)) for a in range(0, R, per)]
+
+
+class NerfRaw(Function):
+    """One radiance MLP on (pts, viewdirs) with an optional rigid transform into the object frame:
+    returns RAW (raw_alpha [R,S], raw_rgb [R,S,3]) like NeRF.forward with z_vals=None
+    (models/nerf.py:112-179).  pose12 = [R(3x3) row-major | t] or None."""
+
+    @staticmethod
+    def forward(ctx, rt, precision, pts, viewdirs, pose12, sc_xyz, sc_dir, *params):
+        pts, viewdirs = _c(pts), _c(viewdirs)
+        R, S = pts.shape[0], pts.shape[1]
+        dev = pts.device
+        flat, packed = rt.refresh(precision)
+        d = rt.desc(precision)
+        L = _capi.lib()
+        raw_alpha = torch.empty((R, S), device=dev)
+        raw_rgb = torch.empty((R, S, 3), device=dev)
+        need_grad = any(ctx.needs_input_grad[7:]) or (pose12 is not None and ctx.needs_input_grad[4])
+        p12 = _c(pose12.detach()) if pose12 is not None else None
+        chunks = _ray_chunks(R, S)
+        stashes = []
+        keep = need_grad and L.star_stash_bytes(C.byref(d), R * S) <= STASH_BUDGET_BYTES
+        for (a, b) in chunks:
+            st = None
+            if keep:
+                st = torch.empty((L.star_stash_bytes(C.byref(d), (b - a) * S),), device=dev, dtype=torch.uint8)
+                stashes.append(st)
+            check(L.star_mlp_forward(C.byref(d), ptr(packed), f32(pts[a:b]), f32(viewdirs[a:b]),
+                                     f32(p12) if p12 is not None else None,
+                                     f32(sc_xyz) if sc_xyz is not None else None,
+                                     f32(sc_dir) if sc_dir is not None else None, b - a, S, f32(raw_alpha[a:b]),
+                                     f32(raw_rgb[a:b]), S, ptr(st), stream()), "star_mlp_forward")
+            _count()
+        if need_grad:
+            ctx.rt, ctx.precision, ctx.chunks, ctx.stashes = rt, precision, chunks, stashes if keep else None
+            ctx.packed, ctx.flat = packed, flat
+            ctx.scales = (sc_xyz, sc_dir)
+            ctx.save_for_backward(pts, viewdirs, p12 if p12 is not None else torch.empty(0, device=dev))
+            ctx.shapes = [p.shape for p in params]
+        return raw_alpha, raw_rgb
+
+    @staticmethod
+    def backward(ctx, g_alpha, g_rgb):
+        pts, viewdirs, p12 = ctx.saved_tensors
+        if p12.numel() == 0:
+            p12 = None
+        rt, precision = ctx.rt, ctx.precision
+        R, S = pts.shape[0], pts.shape[1]
+        dev = pts.device
+        d = rt.desc(precision)
+        L = _capi.lib()
+        sc_xyz, sc_dir = ctx.scales
+        g_alpha = torch.zeros((R, S), device=dev) if g_alpha is None else _c(g_alpha)
+        g_rgb = torch.zeros((R, S, 3), device=dev) if g_rgb is None else _c(g_rgb)
+        grad_flat = torch.zeros_like(ctx.flat)
+        pose_acc = torch.zeros((32,), device=dev) if p12 is not None else None
+        for i, (a, b) in enumerate(ctx.chunks):
+            n = (b - a) * S
+            if ctx.stashes is not None:
+                st = ctx.stashes[i]
+            else:   # recompute the forward of this ray chunk with activation stashing
+                st = torch.empty((L.star_stash_bytes(C.byref(d), n),), device=dev, dtype=torch.uint8)
+                tmp_a = torch.empty((b - a, S), device=dev)
+                tmp_c = torch.empty((b - a, S, 3), device=dev)
+                check(L.star_mlp_forward(C.byref(d), ptr(ctx.packed), f32(pts[a:b]), f32(viewdirs[a:b]),
+                                         f32(p12) if p12 is not None else None,
+                                         f32(sc_xyz) if sc_xyz is not None else None,
+                                         f32(sc_dir) if sc_dir is not None else None, b - a, S, f32(tmp_a),
+                                         f32(tmp_c), S, ptr(st), stream()), "star_mlp_forward(recompute)")
+                _count()
+            ws = torch.empty((L.star_mlp_backward_workspace_bytes(C.byref(d), n),), device=dev, dtype=torch.uint8)
+            check(L.star_mlp_backward(C.byref(d), ptr(ctx.packed), f32(ctx.flat), f32(pts[a:b]), f32(viewdirs[a:b]),
+                                      f32(p12) if p12 is not None else None,
+                                      f32(sc_xyz) if sc_xyz is not None else None,
+                                      f32(sc_dir) if sc_dir is not None else None, b - a, S, f32(g_alpha[a:b]),
+                                      f32(g_rgb[a:b]), S, ptr(st), ptr(ws), f32(grad_flat),
+                                      f32(pose_acc) if pose_acc is not None else None, stream()),
+                  "star_mlp_backward")
+            _count(3 + 2 * rt.n_blocks + 4)
+            if ctx.stashes is not None:
+                ctx.stashes[i] = None
+        grads, off = [], 0
+        for shp in ctx.shapes:
+            n = 1
+            for s_ in shp:
+                n *= s_
+            grads.append(grad_flat[off:off + n].view(shp))
+            off += n
+        g_pose = None
+        if p12 is not None and ctx.needs_input_grad[4]:
+            # Euclidean gradient w.r.t. [R | t]:  dR = sum g p^T + sum h d^T,  dt = sum g
+            g_pose = torch.cat([pose_acc[3:12] + pose_acc[15:24], pose_acc[0:3]])
+        return (None, None, None, None, g_pose, None, None, *grads)
+
+
+class Pose7ToMat12(Function):
+    """[tx,ty,tz,qx,qy,qz,qw] -> [R(q) row-major | t] with pypose's gradient convention
+    (models/star__.py:191-196 via pp.SE3.Act / pp.SO3.Act): the gradient returned for the 7-vector is
+    the LEFT tangent-space gradient padded with a zero, [dt, vee(R dR^T - dR R^T) + t x dt, 0], i.e.
+    [sum g, sum p' x g + sum d' x h, 0] -- not the Euclidean derivative of the stored numbers.
+    The quaternion is not normalised (pypose Act does not normalise either)."""
+
+    @staticmethod
+    def forward(ctx, pose7):
+        x, y, z, w = pose7[3], pose7[4], pose7[5], pose7[6]
+        K = torch.zeros((3, 3), device=pose7.device, dtype=pose7.dtype)
+        K[0, 1], K[0, 2], K[1, 0], K[1, 2], K[2, 0], K[2, 1] = -z, y, z, -x, -y, x
+        Rm = torch.eye(3, device=pose7.device, dtype=pose7.dtype) + 2.0 * w * K + 2.0 * (K @ K)
+        ctx.save_for_backward(Rm, pose7[:3].clone())
+        return torch.cat([Rm.reshape(9), pose7[:3]])
+
+    @staticmethod
+    def backward(ctx, g12):
+        Rm, t = ctx.saved_tensors
+        dR, dt = g12[:9].view(3, 3), g12[9:12]
+        A = Rm @ dR.t()
+        rot = torch.stack([A[1, 2] - A[2, 1], A[2, 0] - A[0, 2], A[0, 1] - A[1, 0]])
+        rot = rot + torch.linalg.cross(t, dt)
+        return torch.cat([dt, rot, torch.zeros(1, device=g12.device, dtype=g12.dtype)])
+
+
+def pose_to_mat12(pose_v):
+    """One object's pose -> 12-vector.  [4,4]: plain slicing (Euclidean autograd, star__.py:160-180);
+    [7]: Pose7ToMat12."""
+    if pose_v.dim() == 2:
+        return torch.cat([pose_v[:3, :3].reshape(9), pose_v[:3, 3]])
+    return Pose7ToMat12.apply(pose_v)

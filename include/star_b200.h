@@ -1,0 +1,179 @@
+/*
+ * star_b200.h -- C ABI of the B200-native (sm_100a) STaR / NeRF render hot path.
+ *
+ * The reference (burakcuhadar/3D-MOT-using-Neural-Radiance-Fields) is pure Python/PyTorch and has
+ * no FFI of its own; each entry point below replaces the reference Python function cited next to
+ * it (paths relative to the reference root).  The host side that binds this header is
+ * 3d-mot-using-neural-radiance-fields_b200/_capi.py (ctypes); INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to densely packed row-major data unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on that stream,
+ *     allocate nothing, and keep no global mutable state (re-entrant across streams / devices);
+ *   - workspaces are supplied by the caller (sizes from the *_bytes queries);
+ *   - return value: 0 = OK, otherwise a STAR_E_* code (star_error_string() gives the text).
+ *     Nothing throws or aborts.  There is no CPU fallback.
+ */
+#ifndef STAR_B200_H_
+#define STAR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STAR_ABI_VERSION 1
+
+enum {
+  STAR_OK = 0,
+  STAR_E_BAD_SHAPE = 1,    /* a size is out of the supported range                       */
+  STAR_E_UNSUPPORTED = 2,  /* W / depth / L / precision combination not compiled          */
+  STAR_E_NULL = 3,         /* a required pointer is NULL                                  */
+  STAR_E_ALIGN = 4,        /* a pointer violates the documented alignment                 */
+  STAR_E_WORKSPACE = 5,    /* workspace too small                                         */
+  STAR_E_CUDA = 6          /* a CUDA runtime call / launch failed (see star_last_cuda_error) */
+};
+
+/* precision tiers of the MLP (north star: 1e-4 abs for fp32, 2e-3 abs for the bf16 MLP) */
+enum { STAR_PREC_F32 = 0, STAR_PREC_BF16 = 1 };
+
+/* One NeRF radiance MLP (models/nerf.py:34-110, models/resnet.py:62-110).  W is fixed at 256,
+ * the view branch at 128 (all 15 reference configs agree). */
+typedef struct StarNetDesc {
+  int32_t n_blocks; /* ResnetFC blocks: netdepth/2 = 4 (static), netdepth/4 = 2 (dynamic)  */
+  int32_t L_xyz;    /* multires        (10) -> 3 + 6*L_xyz = 63 input dims                 */
+  int32_t L_dir;    /* multires_views  (4)  -> 27 dims                                     */
+  int32_t precision; /* STAR_PREC_*                                                         */
+} StarNetDesc;
+
+int star_abi_version(void);
+const char* star_error_string(int code);
+int star_last_cuda_error(void);
+
+/* Number of fp32 elements of the flat master parameter vector of one net, in this order
+ * (each nn.Linear as weight [out,in] row-major then bias [out]):
+ *   pts_net.lin_in, {pts_net.blocks.b.fc_0, pts_net.blocks.b.fc_1} b<n_blocks, pts_net.lin_out,
+ *   alpha_linear, feature_linear, views_linears.0, rgb_linear
+ * = 711300 for n_blocks=4, 448132 for n_blocks=2 (reference state_dict). */
+size_t star_net_param_count(const StarNetDesc* d);
+
+/* Packed (kernel-ready) weight image derived from the flat master vector. */
+size_t star_packed_bytes(const StarNetDesc* d);
+int star_pack_weights(const StarNetDesc* d, const float* flat_master, void* packed, void* stream);
+
+/* ---- a1: models/rendering__.py:75-112  sample_pts --------------------------------------------
+ * t_vals[Nc] = torch.linspace(0,1,Nc) from the host (its symmetric formula is not i/(n-1)).
+ * t_rand[R*Nc] or NULL: injected stratified jitter (perturb > 0 and is_train).
+ * Outputs pts[R,Nc,3], z_vals[R,Nc].  Bit-exact vs the reference ops (no FMA contraction). */
+int star_sample_pts(const float* rays_o, const float* rays_d, const float* t_vals, const float* t_rand,
+                    float near_, float far_, int R, int Nc, int lindisp, float* pts, float* z_vals,
+                    void* stream);
+
+/* ---- a3: models/embedder.py:81-112  Embedder.forward -----------------------------------------
+ * x[M,3] -> out[M,3+6L].  scale[3+6L] or NULL: per-element BARF mask (w[j mod L] quirk, :32). */
+int star_embed(const float* x, int M, int L, const float* scale, float* out, void* stream);
+
+/* ---- a4 (+K2 pose transform): models/nerf.py:112-179, models/star__.py:160-199 ---------------
+ * pts[R,S,3], viewdirs[R,3]; pose12 = NULL (static net) or 12 floats row-major [R(3x3) | t] :
+ * p' = R p + t, d' = R d (object frame).  enc_scale_xyz / enc_scale_dir: BARF masks or NULL.
+ * raw_alpha [R*S] and raw_rgb [R*S*3] are written with element strides so that the multi-field
+ * layout [R,V,S] of raw2outputs_star can be filled in place:
+ *   raw_alpha[r*alpha_ray_stride + s], raw_rgb[(r*alpha_ray_stride + s)*3 + c].
+ * stash (NULL for inference): per-GEMM input activations kept for the backward pass,
+ * star_stash_bytes(d, R*S) bytes. */
+size_t star_stash_bytes(const StarNetDesc* d, int64_t n_samples);
+int star_mlp_forward(const StarNetDesc* d, const void* packed, const float* pts, const float* viewdirs,
+                     const float* pose12, const float* enc_scale_xyz, const float* enc_scale_dir,
+                     int R, int S, float* raw_alpha, float* raw_rgb, int64_t alpha_ray_stride,
+                     void* stash, void* stream);
+
+/* Backward of star_mlp_forward.  d_raw_alpha / d_raw_rgb use the same strides as the forward.
+ * grad_flat: fp32 [star_net_param_count] in the flat master order, ACCUMULATED into (caller zeroes).
+ * pose_acc: 32 floats ACCUMULATED into (NULL when pose12 is NULL):
+ *   [0:3]  sum g            [3:12]  sum g p^T (row-major)   [12:15] sum p' x g
+ *   [15:24] sum h d^T       [24:27] sum d' x h              (g = dL/dp', h = dL/dd')
+ * from which the host forms dL/dM (4x4 pose, star__.py:160-180) or the pypose left-tangent
+ * gradient [sum g, sum p' x g + sum d' x h, 0] (7-vector pose, star__.py:182-199).
+ * workspace: star_mlp_backward_workspace_bytes(d, R*S) bytes. */
+size_t star_mlp_backward_workspace_bytes(const StarNetDesc* d, int64_t n_samples);
+int star_mlp_backward(const StarNetDesc* d, const void* packed, const float* flat_master, const float* pts,
+                      const float* viewdirs, const float* pose12, const float* enc_scale_xyz,
+                      const float* enc_scale_dir, int R, int S, const float* d_raw_alpha,
+                      const float* d_raw_rgb, int64_t alpha_ray_stride, const void* stash, void* workspace,
+                      float* grad_flat, float* pose_acc, void* stream);
+
+/* ---- a5/a6: models/rendering__.py:301-379  raw2outputs ---------------------------------------
+ * Outputs: rgb[R,3], disp[R], acc[R], depth[R], weights[R,S], dists[R,S]. */
+int star_composite_single_forward(const float* raw_alpha, const float* raw_rgb, const float* z_vals,
+                                  const float* rays_d, int R, int S, float far_dist, int white_bkgd,
+                                  float* rgb, float* disp, float* acc, float* depth, float* weights,
+                                  float* dists, void* stream);
+/* Gradients of (rgb, disp, acc, depth, weights) -> (raw_alpha, raw_rgb); any g_* may be NULL. */
+int star_composite_single_backward(const float* raw_alpha, const float* raw_rgb, const float* z_vals,
+                                   const float* rays_d, int R, int S, float far_dist, int white_bkgd,
+                                   const float* g_rgb, const float* g_disp, const float* g_acc,
+                                   const float* g_depth, const float* g_weights, float* d_raw_alpha,
+                                   float* d_raw_rgb, void* stream);
+
+/* ---- a7/a8: models/rendering__.py:383-576 raw2outputs_star + :612-715 regularisers ------------
+ * raw_alpha_d [R,V,S], raw_rgb_d [R,V,S,3] (reference layout).  `chunk` reproduces
+ * STaR.forward's "mean within a ray chunk, summed over chunks" (star__.py:84-112) for the five
+ * scalar regularisers.  reg_partial: workspace of 5*gridDim floats (star_composite_multi_ws_bytes);
+ * regs[5] = alpha_entropy, dynamic_vs_static, ray_reg, static_reg, dynamic_reg.
+ * rgb_dynamic_all may be NULL (train mode: "test" is False, star__.py:224). */
+typedef struct StarMultiOut {
+  float* rgb;                   /* [R,3]   */
+  float* disp;                  /* [R]     */
+  float* acc;                   /* [R]     */
+  float* depth;                 /* [R]     */
+  float* weights;               /* [R,S]   */
+  float* rgb_static;            /* [R,3]   */
+  float* depth_static;          /* [R]     */
+  float* rgb_dynamic;           /* [R,V,3] */
+  float* depth_dynamic;         /* [R,V]   */
+  float* dynamic_transmittance; /* [R,V]   */
+  float* rgb_dynamic_all;       /* [R,3] or NULL */
+  float* regs;                  /* [5]     */
+} StarMultiOut;
+size_t star_composite_multi_ws_bytes(int R);
+int star_composite_multi_forward(const float* raw_alpha_s, const float* raw_rgb_s, const float* raw_alpha_d,
+                                 const float* raw_rgb_d, const float* z_vals, const float* rays_d, int R,
+                                 int V, int S, float far_dist, int white_bkgd, int chunk,
+                                 const StarMultiOut* out, void* workspace, void* stream);
+/* g_regs: DEVICE pointer to 5 floats (upstream grads of the scalars) or NULL. */
+int star_composite_multi_backward(const float* raw_alpha_s, const float* raw_rgb_s, const float* raw_alpha_d,
+                                  const float* raw_rgb_d, const float* z_vals, const float* rays_d, int R,
+                                  int V, int S, float far_dist, int white_bkgd, int chunk,
+                                  const float* g_rgb, const float* g_disp, const float* g_acc,
+                                  const float* g_depth, const float* g_weights, const float* g_regs,
+                                  float* d_raw_alpha_s, float* d_raw_rgb_s, float* d_raw_alpha_d,
+                                  float* d_raw_rgb_d, void* stream);
+
+/* ---- a9: models/rendering__.py:719-761  sample_pdf -------------------------------------------
+ * bins[R,nb] (row stride bins_stride), weights[R,nb-1] (row stride w_stride; lets the caller pass
+ * the weights[...,1:-1] view without a copy).  u[R,Ni] or NULL (det: u = u_det[Ni], a host
+ * torch.linspace(0,1,Ni) copied to the device).  Outputs samples[R,Ni]; optional int64
+ * inds/below/above[R,Ni] and cdf[R,nb] (NULL to skip) for the bit-exactness tests.
+ * Arithmetic (defined): normaliser = exactly rounded fp32 sum (fp64 accumulate),
+ * cdf = fp64 prefix sum rounded per element (== torch CPU cumsum), no FMA contraction. */
+int star_sample_pdf(const float* bins, int64_t bins_stride, const float* weights, int64_t w_stride,
+                    const float* u, const float* u_det, int R, int nb, int Ni, float* samples,
+                    int64_t* inds, int64_t* below, int64_t* above, float* cdf, void* stream);
+/* cdf supplied by the caller (kernel-level parity: identical cdf,u -> identical inds, bit-exact). */
+int star_invert_cdf(const float* bins, const float* cdf, const float* u, int R, int nb, int Ni,
+                    float* samples, int64_t* inds, int64_t* below, int64_t* above, void* stream);
+
+/* ---- a10: models/rendering__.py:128-144 / :271-296  hierarchical step -------------------------
+ * z_vals[R,Nc], weights[R,Nc] -> z_mid, sample_pdf(z_mid, weights[...,1:-1]) -> z_samples[R,Ni],
+ * z_all[R,Nc+Ni] = sort(cat(z_vals, z_samples)), z_std[R] = std(z_samples, unbiased=False),
+ * pts_fine[R,Nc+Ni,3] = o + d*z_all (NULL to skip). */
+int star_hierarchical(const float* z_vals, const float* weights, const float* u, const float* u_det,
+                      const float* rays_o, const float* rays_d, int R, int Nc, int Ni, float* z_samples,
+                      float* z_all, float* z_std, float* pts_fine, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STAR_B200_H_ */

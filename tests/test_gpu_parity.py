@@ -1,0 +1,432 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs and against the golden fixtures produced by the unmodified reference.
+
+Tolerances (north star): sample indices / searchsorted bins bit-exact; rgb, depth, weights within
+1e-4 absolute for the fp32 tier (most checks are far tighter)."""
+import math
+
+import pytest
+import torch
+
+import star_b200
+from star_b200 import functional as F_
+from star_b200.models import rendering__ as R_
+from oracle import ref_harness, star_oracle as so
+from helpers import load_golden, assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+REGS = ["loss_alpha_entropy", "loss_dynamic_vs_static_reg", "loss_ray_reg", "loss_static_reg", "loss_dynamic_reg"]
+
+
+def cu(t):
+    return t.to(DEV) if torch.is_tensor(t) else t
+
+
+def make_star(V, Ni, chunk, white, seed, training, bias_std=0.02, end_barf=-1):
+    args = ref_harness.make_args(num_vehicles=V, N_importance=Ni, chunk=chunk, white_bkgd=white, end_barf=end_barf)
+    net = star_b200.STaR(args)
+    sd = so.init_star_params(V, Ni, seed=seed, bias_std=bias_std)
+    net.load_state_dict(sd, strict=True)
+    net.to(DEV).train(training)
+    params = {k: v.clone() for k, v in sd.items()}
+    return net, params
+
+
+# ------------------------------------------------------------------------------------------ a1
+def test_sample_pts_bit_exact():
+    g = load_golden("sample_pts")
+    pts, z = R_.sample_pts(cu(g["rays_o"]), cu(g["rays_d"]), g["near"], g["far"], 32)
+    assert torch.equal(z.cpu(), g["z"]) and torch.equal(pts.cpu(), g["pts"])
+    pts, z = R_.sample_pts(cu(g["rays_o"]), cu(g["rays_d"]), g["near"], g["far"], 32, lindisp=True, is_train=False)
+    assert torch.equal(z.cpu(), g["z_lindisp"]) and torch.equal(pts.cpu(), g["pts_lindisp"])
+    pts, z = R_.sample_pts(cu(g["rays_o"]), cu(g["rays_d"]), g["near"], g["far"], 32, perturb=1.0,
+                           t_rand=cu(g["t_rand"]))
+    assert torch.equal(z.cpu(), g["z_perturb"]) and torch.equal(pts.cpu(), g["pts_perturb"])
+
+
+def test_sample_pts_large_and_edge_sizes():
+    for Rr, Nc in ((1, 2), (3, 1024), (70001, 64)):
+        ro, rd = so.carla_rays(Rr, seed=1)
+        pts, z = R_.sample_pts(cu(ro), cu(rd), 0.03, 0.8, Nc)
+        p2, z2 = so.sample_pts(ro, rd, 0.03, 0.8, Nc)
+        assert torch.equal(z.cpu(), z2) and torch.equal(pts.cpu(), p2)
+
+
+# ------------------------------------------------------------------------------------------ a3
+def test_embed_vs_reference_fixture():
+    g = load_golden("embed")
+    x = cu(g["x"])
+    assert_close(F_.embed(x, 10), g["enc10"], 2e-6)
+    assert_close(F_.embed(x, 4), g["enc4"], 2e-6)
+    from star_b200.models.embedder import get_embedder
+    e10, n = get_embedder(10, 40)
+    assert n == 63
+    assert_close(e10(x, step=13), g["barf10_s13"], 2e-6)
+    assert_close(e10(x, step=0), g["barf10_s0"], 2e-6)
+    assert_close(e10(x, step=99), g["barf10_s99"], 2e-6)
+    e4, _ = get_embedder(4, 40)
+    assert_close(e4(x, step=13), g["barf4_s13"], 2e-6)
+
+
+# ------------------------------------------------------------------------------------------ a5/a6
+@pytest.mark.parametrize("white", [True, False])
+def test_raw2outputs_vs_reference_fixture(white):
+    g = load_golden("raw2outputs")
+    tag = "white." if white else "black."
+    o = R_.raw2outputs(cu(g["raw_alpha"]), cu(g["raw_rgb"]), cu(g["z_vals"]), cu(g["rays_d"]), 0.0, white, 1e10)
+    for k, v in o.items():
+        assert_close(v, g[tag + k], 2e-6, 1e-5, tag + k)
+
+
+@pytest.mark.parametrize("R,S,white", [(5, 1, False), (33, 31, True), (64, 192, True), (17, 1025, False)])
+def test_raw2outputs_forward_backward_vs_oracle(R, S, white):
+    gen = torch.Generator().manual_seed(R * 1000 + S)
+    ra = (torch.randn(R, S, generator=gen) * 3 - 1).requires_grad_(True)
+    rc = (torch.randn(R, S, 3, generator=gen) * 2).requires_grad_(True)
+    ro, rd = so.carla_rays(R, seed=2)
+    _, z = so.sample_pts(ro, rd, 0.03, 0.8, S) if S > 1 else (None, torch.full((R, 1), 0.4))
+    z = z.contiguous()
+    gw = torch.randn(R, S, generator=gen) * 0.1
+    coef = torch.randn(R, 8, generator=gen)
+
+    def loss_of(o):
+        return ((o["rgb"] * coef[:, :3].to(o["rgb"].device)).sum() + (o["depth"] * coef[:, 3].to(o["rgb"].device)).sum()
+                + (o["acc"] * coef[:, 4].to(o["rgb"].device)).sum() + (o["weights"] * gw.to(o["rgb"].device)).sum()
+                + 1e-3 * (o["disp"].clamp(max=50) * coef[:, 5].to(o["rgb"].device)).sum())
+
+    o_ref = so.raw2outputs(ra, rc, z, rd, 0.0, white, 1e10)
+    loss_of(o_ref).backward()
+    ra_g = cu(ra.detach()).requires_grad_(True)
+    rc_g = cu(rc.detach()).requires_grad_(True)
+    o = R_.raw2outputs(ra_g, rc_g, cu(z), cu(rd), 0.0, white, 1e10)
+    for k in ("rgb", "acc", "depth", "weights", "dists"):
+        assert_close(o[k], o_ref[k], 2e-6, 1e-5, k)
+    assert_close(o["disp"], o_ref["disp"], 1e-5, 1e-4, "disp")
+    loss_of(o).backward()
+    assert_close(ra_g.grad, ra.grad, 2e-5, 1e-4, "d raw_alpha")
+    assert_close(rc_g.grad, rc.grad, 2e-6, 1e-4, "d raw_rgb")
+
+
+# ------------------------------------------------------------------------------------------ a7/a8
+@pytest.mark.parametrize("test", [False, True])
+def test_raw2outputs_star_vs_reference_fixture(test):
+    g = load_golden("raw2outputs_star")
+    tag = "test." if test else "train."
+    o = R_.raw2outputs_star(cu(g["raw_alpha_s"]), cu(g["raw_rgb_s"]), cu(g["raw_alpha_d"]), cu(g["raw_rgb_d"]),
+                            cu(g["z_vals"]), cu(g["rays_d"]), 0, test, 1e10, test=test)
+    n = 0
+    for k, v in o.items():
+        if v is None:
+            assert tag + k not in g
+            continue
+        assert_close(v, g[tag + k], 3e-6, 2e-5, tag + k)
+        n += 1
+    assert n == (16 if test else 15)
+
+
+@pytest.mark.parametrize("R,V,S,chunk", [(7, 1, 40, 100), (40, 3, 48, 16), (33, 5, 130, 7), (9, 8, 33, 4)])
+def test_raw2outputs_star_forward_backward_vs_oracle(R, V, S, chunk):
+    gen = torch.Generator().manual_seed(R + 10 * V + 100 * S)
+    ras = (torch.randn(R, S, generator=gen) * 3 - 1).requires_grad_(True)
+    rcs = (torch.randn(R, S, 3, generator=gen) * 2).requires_grad_(True)
+    rad = (torch.randn(R, V, S, generator=gen) * 3 - 2).requires_grad_(True)
+    rcd = (torch.randn(R, V, S, 3, generator=gen) * 2).requires_grad_(True)
+    ro, rd = so.carla_rays(R, seed=3)
+    _, z = so.sample_pts(ro, rd, 0.03, 0.8, S)
+    z = z.contiguous()
+    gw = torch.randn(R, S, generator=gen) * 0.1
+    coef = torch.randn(R, 8, generator=gen)
+    lam = [0.7, 1.3, 0.9, 1.1, 0.5]
+
+    def loss_of(o):
+        d = o["rgb"].device
+        l = ((o["rgb"] * coef[:, :3].to(d)).sum() + (o["depth"] * coef[:, 3].to(d)).sum()
+             + (o["acc"] * coef[:, 4].to(d)).sum() + (o["weights"] * gw.to(d)).sum())
+        for w, k in zip(lam, REGS):
+            l = l + w * R * o[k]
+        return l
+
+    # oracle with the reference's chunk semantics: per-chunk means summed over chunks
+    outs = [so.raw2outputs_star(ras[i:i + chunk], rcs[i:i + chunk], rad[i:i + chunk], rcd[i:i + chunk],
+                                z[i:i + chunk], rd[i:i + chunk], False, 1e10, test=True) for i in range(0, R, chunk)]
+    o_ref = {k: (sum(o[k] for o in outs) if outs[0][k].dim() == 0 else torch.cat([o[k] for o in outs], 0))
+             for k in outs[0]}
+    loss_of(o_ref).backward()
+    leaves = [cu(t.detach()).requires_grad_(True) for t in (ras, rcs, rad, rcd)]
+    o = R_.raw2outputs_star(*leaves, cu(z), cu(rd), 0, False, 1e10, test=True, chunk=chunk)
+    for k, v in o.items():
+        tol = 2e-5 if k == "disp" else 4e-6
+        assert_close(v, o_ref[k], tol, 2e-5, k)
+    loss_of(o).backward()
+    for name, a, b in zip(("d ra_s", "d rc_s", "d ra_d", "d rc_d"), leaves, (ras, rcs, rad, rcd)):
+        assert_close(a.grad, b.grad, 3e-5, 2e-4, name)
+
+
+def test_star_equals_single_field_when_objects_are_empty():
+    """raw_alpha_dynamic -> -inf-like makes every object transparent: multi-field == single-field."""
+    gen = torch.Generator().manual_seed(5)
+    R, S = 19, 64
+    ras, rcs = torch.randn(R, S, generator=gen) * 3, torch.randn(R, S, 3, generator=gen)
+    rad, rcd = torch.full((R, 2, S), -80.0), torch.randn(R, 2, S, 3, generator=gen)
+    ro, rd = so.carla_rays(R, seed=4)
+    _, z = so.sample_pts(ro, rd, 0.03, 0.8, S)
+    a = R_.raw2outputs(cu(ras), cu(rcs), cu(z.contiguous()), cu(rd), 0.0, False, 1e10)
+    b = R_.raw2outputs_star(cu(ras), cu(rcs), cu(rad), cu(rcd), cu(z.contiguous()), cu(rd), 0, False, 1e10)
+    for k in ("rgb", "depth", "acc", "weights"):
+        assert_close(b[k], a[k], 1e-6, 1e-5, k)
+    assert_close(b["rgb_static"], a["rgb"], 1e-6, 1e-5)
+
+
+# ------------------------------------------------------------------------------------------ a9
+def test_sample_pdf_indices_bit_exact_vs_oracle_defined_arithmetic():
+    g = load_golden("sample_pdf")
+    bins, w = g["bins"], g["weights"]
+    for det, u in ((True, None), (False, g["u_rnd"])):
+        s_ref, d_ref = so.sample_pdf(bins, w, 64, det=det, u=u, exact_sum=True, return_details=True)
+        s, d = F_.sample_pdf(cu(bins), cu(w), 64, det=det, u=cu(u) if u is not None else None, return_details=True)
+        assert torch.equal(d["cdf"].cpu(), d_ref["cdf"]), "cdf bits"
+        for k in ("inds", "below", "above"):
+            assert d[k].dtype == torch.int64 and torch.equal(d[k].cpu(), d_ref[k]), k
+        assert torch.equal(s.cpu(), s_ref), "samples bits"
+
+
+def test_invert_cdf_bit_exact_on_reference_cdf():
+    """Kernel-level parity: identical cdf and u -> identical inds / samples as the unmodified reference."""
+    g = load_golden("sample_pdf")
+    s, inds, below, above = F_.invert_cdf(cu(g["bins"]), cu(g["cdf_rnd"]), cu(g["u_rnd"]))
+    assert torch.equal(inds.cpu(), g["inds_rnd"]) and torch.equal(s.cpu(), g["samples_rnd"])
+    u_det = torch.linspace(0.0, 1.0, 64).expand(g["bins"].shape[0], 64).contiguous()
+    s, inds, below, above = F_.invert_cdf(cu(g["bins"]), cu(g["cdf_det"]), cu(u_det))
+    assert torch.equal(inds.cpu(), g["inds_det"]) and torch.equal(s.cpu(), g["samples_det"])
+
+
+def test_sample_pdf_vs_reference_fixture_near_ties_only():
+    g = load_golden("sample_pdf")
+    s, d = F_.sample_pdf(cu(g["bins"]), cu(g["weights"]), 64, u=cu(g["u_rnd"]), return_details=True)
+    diff = d["inds"].cpu() != g["inds_rnd"]
+    if diff.any():
+        cdf, uu = d["cdf"].cpu(), g["u_rnd"]
+        k = torch.minimum(d["inds"].cpu(), g["inds_rnd"]).clamp(max=cdf.shape[-1] - 1)
+        assert ((uu - torch.gather(cdf, 1, k)).abs()[diff] <= 4 * 1.2e-7).all()
+    assert_close(s, g["samples_rnd"], 5e-5)
+
+
+@pytest.mark.parametrize("R,Nc,Ni", [(1, 3, 1), (5, 64, 128), (37, 256, 256), (3, 1024, 1024), (4099, 64, 128)])
+def test_sample_pdf_edge_and_large_sizes(R, Nc, Ni):
+    gen = torch.Generator().manual_seed(Nc + Ni)
+    w = torch.rand(R, Nc - 2, generator=gen) ** 6
+    w[0] = 0.0                                   # all-zero weights row (the 1e-5 floor keeps it finite)
+    bins, _ = torch.sort(torch.rand(R, Nc - 1, generator=gen) * 4 + 2, -1)
+    u = torch.rand(R, Ni, generator=gen)
+    u[:, 0], u[:, -1] = 0.0, 1.0 - 1e-7
+    s_ref, d_ref = so.sample_pdf(bins, w, Ni, u=u, exact_sum=True, return_details=True)
+    s, d = F_.sample_pdf(cu(bins), cu(w), Ni, u=cu(u), return_details=True)
+    assert torch.equal(d["inds"].cpu(), d_ref["inds"]) and torch.equal(s.cpu(), s_ref)
+
+
+def test_sample_pdf_accepts_strided_weights_view():
+    gen = torch.Generator().manual_seed(3)
+    w_full = torch.rand(11, 66, generator=gen)
+    bins, _ = torch.sort(torch.rand(11, 65, generator=gen), -1)
+    u = torch.rand(11, 32, generator=gen)
+    a = F_.sample_pdf(cu(bins), cu(w_full)[..., 1:-1], 32, u=cu(u))
+    b = F_.sample_pdf(cu(bins), cu(w_full[..., 1:-1].contiguous()), 32, u=cu(u))
+    assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------ a10
+@pytest.mark.parametrize("R,Nc,Ni,det", [(9, 16, 24, True), (33, 64, 128, False), (5, 256, 256, False), (3, 100, 77, True)])
+def test_hierarchical_vs_oracle(R, Nc, Ni, det):
+    gen = torch.Generator().manual_seed(R + Nc)
+    ro, rd = so.carla_rays(R, seed=6)
+    _, z = so.sample_pts(ro, rd, 0.03, 0.8, Nc)
+    z = z.contiguous()
+    w = torch.rand(R, Nc, generator=gen) ** 4
+    u = None if det else torch.rand(R, Ni, generator=gen)
+    mid = 0.5 * (z[..., 1:] + z[..., :-1])
+    zs_ref = so.sample_pdf(mid, w[..., 1:-1], Ni, det=det, u=u, exact_sum=True)
+    zall_ref, _ = torch.sort(torch.cat([z, zs_ref], -1), -1)
+    zs, z_all, z_std, pts = F_.hierarchical(cu(z), cu(w), Ni, det, cu(ro), cu(rd), u=cu(u) if u is not None else None)
+    assert torch.equal(zs.cpu(), zs_ref), "z_samples bits"
+    assert torch.equal(z_all.cpu(), zall_ref), "sorted merge bits"
+    assert_close(z_std, torch.std(zs_ref, dim=-1, unbiased=False), 1e-6, 1e-5)
+    pts_ref = ro[..., None, :] + rd[..., None, :] * zall_ref[..., :, None]
+    assert torch.equal(pts.cpu(), pts_ref)
+
+
+# ------------------------------------------------------------------------------------------ a4
+def test_nerf_mlp_vs_reference_fixture():
+    g = load_golden("nerf_mlp")
+    net, _ = make_star(int(g["V"]), 16, 4096, False, int(g["seed"]), training=False)
+    with torch.no_grad():
+        a, c = net.static_coarse_nerf(cu(g["pts"]), cu(g["viewdirs"]))
+        assert_close(a, g["raw_alpha_static_coarse"], 1e-4, msg="alpha static")
+        assert_close(c, g["raw_rgb_static_coarse"], 1e-4, msg="rgb static")
+        a, c = net.dynamic_fine_nerfs[0](cu(g["pts"]), cu(g["viewdirs"]))
+        assert_close(a, g["raw_alpha_dynamic_fine0"], 1e-4, msg="alpha dyn")
+        assert_close(c, g["raw_rgb_dynamic_fine0"], 1e-4, msg="rgb dyn")
+
+
+@pytest.mark.parametrize("R,S,dyn,with_pose", [(3, 5, False, False), (16, 12, True, True), (70, 33, False, True)])
+def test_nerf_mlp_forward_backward_vs_oracle(R, S, dyn, with_pose):
+    net, params = make_star(1, 8, 4096, False, seed=21, training=True)
+    prefix = "dynamic_coarse_nerfs.0." if dyn else "static_coarse_nerf."
+    module = net.dynamic_coarse_nerfs[0] if dyn else net.static_coarse_nerf
+    ro, rd = so.carla_rays(R, seed=7)
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    pts, _ = so.sample_pts(ro, rd, 0.03, 0.8, S)
+    gen = torch.Generator().manual_seed(4)
+    ga, gc = torch.randn(R, S, generator=gen), torch.randn(R, S, 3, generator=gen)
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items() if k.startswith(prefix)}
+    pose = so.pose7_to_matrix(so.random_poses7(1, seed=9))[0].requires_grad_(True) if with_pose else None
+    if with_pose:
+        ph = torch.cat([pts, torch.ones(R, S, 1)], -1).reshape(-1, 4)
+        pd = (ph @ pose.T).reshape(R, S, 4)[..., :3]
+        vdd = vd @ pose[:3, :3].T
+    else:
+        pd, vdd = pts, vd
+    a_ref, c_ref = so.nerf_mlp(p, prefix, pd, vdd)
+    ((a_ref * ga).sum() + (c_ref * gc).sum()).backward()
+
+    pose_g = cu(pose.detach()).requires_grad_(True) if with_pose else None
+    p12 = F_.pose_to_mat12(pose_g) if with_pose else None
+    a, c = module.raw(cu(pts), cu(vd), p12)
+    assert_close(a, a_ref, 1e-4, msg="raw_alpha")
+    assert_close(c, c_ref, 1e-4, msg="raw_rgb")
+    ((a * cu(ga)).sum() + (c * cu(gc)).sum()).backward()
+    for k, v in module.named_parameters():
+        ref = p[prefix + k].grad
+        scale = float(ref.abs().max()) + 1e-6
+        assert_close(v.grad, ref, 2e-4 * scale, 1e-3, "grad " + k)
+    if with_pose:
+        scale = float(pose.grad.abs().max()) + 1e-6
+        assert_close(pose_g.grad, pose.grad, 2e-4 * scale, 1e-3, "pose grad")
+
+
+def test_nerf_mlp_barf_mask_on_dynamic_net():
+    net, params = make_star(1, 8, 4096, False, seed=22, training=False, end_barf=40)
+    ro, rd = so.carla_rays(10, seed=8)
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    pts, _ = so.sample_pts(ro, rd, 0.03, 0.8, 9)
+    with torch.no_grad():
+        a, c = net.dynamic_coarse_nerfs[0].raw(cu(pts), cu(vd), None, step=13)
+    a_ref, c_ref = so.nerf_mlp(params, "dynamic_coarse_nerfs.0.", pts, vd, step=13, end_barf=40)
+    assert_close(a, a_ref, 1e-4)
+    assert_close(c, c_ref, 1e-4)
+
+
+# ------------------------------------------------------------------------------------------ end to end
+def _check_outputs(out, g, atol=1e-4):
+    n = 0
+    for k, v in out.items():
+        if v is None:
+            assert k not in g, k
+            continue
+        assert k in g, f"unexpected output key {k}"
+        tol = atol * (50 if k.startswith("disp") else 1)
+        assert_close(v, g[k], tol, 1e-4, k)
+        n += 1
+    assert n == sum(1 for k in g if k in out or False) or n >= 10
+
+
+def _digest(t):
+    f = t.detach().reshape(-1).cpu()
+    head = f[:8] if f.numel() >= 8 else torch.cat([f, torch.zeros(8 - f.numel())])
+    return torch.cat([f.norm()[None], f.sum()[None], head])
+
+
+def _check_grad_digests(net, g, rtol=2e-3):
+    for k, v in net.named_parameters():
+        ref = g["gd." + k]
+        scale = float(ref[0]) + 1e-7
+        assert_close(_digest(v.grad), ref, 1e-3 * scale + 1e-7, rtol, "grad digest " + k)
+
+
+def test_e2e_appinit_eval_fixture():
+    g = load_golden("e2e_appinit_eval")
+    net, _ = make_star(0, 24, 4096, True, int(g["seed"]), training=False)
+    ro, rd = cu(g["rays_o"]), cu(g["rays_d"])
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    with torch.no_grad():
+        pts, z = R_.sample_pts(ro, rd, g["near"], g["far"], int(g["Nc"]), is_train=False)
+        out = R_.render_star_appinit(net, pts, vd, z, ro, rd, int(g["Ni"]))
+    _check_outputs(out, g)
+    assert set(out) == {k for k in g if k not in ("seed", "rays_o", "rays_d", "near", "far", "Nc", "Ni")}
+
+
+def test_e2e_appinit_train_fixture_with_grads():
+    g = load_golden("e2e_appinit_train")
+    net, _ = make_star(0, 24, int(g["chunk"]), False, int(g["seed"]), training=True)
+    ro, rd, target = cu(g["rays_o"]), cu(g["rays_d"]), cu(g["target"])
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    pts, z = R_.sample_pts(ro, rd, g["near"], g["far"], int(g["Nc"]))
+    out = R_.render_star_appinit(net, pts, vd, z, ro, rd, int(g["Ni"]), u=cu(g["u"]))
+    _check_outputs(out, g)
+    loss = ((out["rgb0"] - target) ** 2).mean() + ((out["rgb"] - target) ** 2).mean() + 0.1 * out["depth"].mean()
+    assert_close(loss, g["loss"], 1e-5)
+    loss.backward()
+    _check_grad_digests(net, g)
+
+
+@pytest.mark.parametrize("name,training", [("e2e_online_mat_train", True), ("e2e_online_mat_eval", False),
+                                           ("e2e_online_quat_train", True)])
+def test_e2e_online_fixture(name, training):
+    g = load_golden(name)
+    net, _ = make_star(2, 24, int(g["chunk"]), False, int(g["seed"]), training=training)
+    ro, rd, target = cu(g["rays_o"]), cu(g["rays_d"]), cu(g["target"])
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    pose = cu(g["pose"]).clone().requires_grad_(training)
+    with torch.set_grad_enabled(training):
+        pts, z = R_.sample_pts(ro, rd, g["near"], g["far"], int(g["Nc"]))
+        out = R_.render_star_online(net, pts, vd, z, ro, rd, int(g["Ni"]), pose, step=None,
+                                    u=cu(g["u"]) if training else None)
+    _check_outputs(out, g)
+    if not training:
+        assert out["rgb_dynamic_all"] is not None and out["rgb_dynamic_all0"] is not None
+        return
+    loss = ((out["rgb0"] - target) ** 2).mean() + ((out["rgb"] - target) ** 2).mean()
+    for l, k in zip((1e-3, 1e-3, 1e-5, 1e-4, 1e-4), REGS):
+        loss = loss + l * 0.5 * (out[k] + out[k + "0"])
+    assert_close(loss, g["loss"], 1e-5)
+    loss.backward()
+    scale = float(g["pose_grad"].abs().max())
+    assert_close(pose.grad, g["pose_grad"], 2e-3 * scale, 2e-3, "pose grad")
+    _check_grad_digests(net, g)
+
+
+def test_error_paths():
+    net, _ = make_star(1, 0, 4096, False, seed=1, training=False)
+    ro, rd = so.carla_rays(4, seed=1)
+    pts, z = R_.sample_pts(cu(ro), cu(rd), 0.03, 0.8, 8)
+    with pytest.raises(ValueError):
+        net(pts, cu(rd), z, cu(rd), is_coarse=False)
+    with pytest.raises(NotImplementedError):
+        net(pts, cu(rd), z, cu(rd), pose=torch.zeros(1, 7, device=DEV), object_pose=torch.zeros(1))
+    with pytest.raises(NotImplementedError):
+        net(pts, cu(rd), z, cu(rd), pose=torch.zeros(7, device=DEV))
+
+
+# ------------------------------------------------------------------------------------------ properties
+def test_rays_are_independent_and_chunking_is_invisible():
+    """callbacks/check_batch_grad.py idea: per-ray outputs must not depend on the other rays in the
+    batch, nor on how rays are split over launches."""
+    net, _ = make_star(2, 24, 4096, False, seed=9, training=False)
+    ro, rd = so.carla_rays(300, seed=12)
+    ro, rd = cu(ro), cu(rd)
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    pose = cu(so.random_poses7(2, seed=3))
+    with torch.no_grad():
+        pts, z = R_.sample_pts(ro, rd, 0.03, 0.8, 16)
+        full = R_.render_star_online(net, pts, vd, z, ro, rd, 24, pose)
+        perm = torch.randperm(300, device=DEV)
+        pp = R_.render_star_online(net, pts[perm], vd[perm], z[perm], ro[perm], rd[perm], 24, pose)
+        saved = F_.MAX_SAMPLES_PER_LAUNCH
+        F_.MAX_SAMPLES_PER_LAUNCH = 16 * 37
+        try:
+            split = R_.render_star_online(net, pts, vd, z, ro, rd, 24, pose)
+        finally:
+            F_.MAX_SAMPLES_PER_LAUNCH = saved
+    for k in ("rgb", "depth", "weights", "rgb0", "rgb_dynamic", "dynamic_transmittance"):
+        assert torch.equal(full[k][perm], pp[k]), k
+        assert torch.equal(full[k], split[k]), k

@@ -1,0 +1,144 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, the module tree keeps the reference checkpoint layout, pose / BARF host helpers match the
+oracle.  No compute calls (there is no GPU here and no CPU fallback by design)."""
+import os
+import re
+
+import pytest
+import torch
+
+import star_b200
+from star_b200 import _capi, functional as F_
+from star_b200.models import embedder as emb
+from oracle import ref_harness, star_oracle as so
+from helpers import assert_close
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "star_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(star_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = _capi.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"libstar_b200.so does not export {name}"
+    assert declared == set(_capi.EXPORTED_SYMBOLS), declared ^ set(_capi.EXPORTED_SYMBOLS)
+    assert lib.star_abi_version() == 1
+
+
+def test_param_counts_and_packed_sizes():
+    import ctypes as C
+    lib = _capi.lib()
+    for nb, n in ((4, 711300), (2, 448132)):
+        d = _capi.net_desc(nb, 10, 4, _capi.PREC_F32)
+        assert lib.star_net_param_count(C.byref(d)) == n
+        assert lib.star_packed_bytes(C.byref(d)) > 4 * n
+        assert lib.star_stash_bytes(C.byref(d), 1000) > 0
+    bad = _capi.net_desc(9, 10, 4, _capi.PREC_F32)
+    assert lib.star_net_param_count(C.byref(bad)) == 0
+
+
+def test_no_cpu_fallback():
+    x = torch.zeros(4, 3)
+    with pytest.raises(_capi.StarError):
+        F_.embed(x, 4)
+
+
+def test_state_dict_layout_matches_reference_keys():
+    args = ref_harness.make_args(num_vehicles=2, N_importance=8)
+    net = star_b200.STaR(args)
+    sd = so.init_star_params(2, 8, seed=0)
+    assert set(net.state_dict().keys()) == set(sd.keys())
+    net.load_state_dict(sd, strict=True)
+    for k, v in net.state_dict().items():
+        assert v.shape == sd[k].shape
+    n_static = sum(p.numel() for p in net.static_coarse_nerf.parameters())
+    n_dyn = sum(p.numel() for p in net.dynamic_coarse_nerfs[0].parameters())
+    assert (n_static, n_dyn) == (711300, 448132)
+    if ref_harness.reference_available():
+        ref = ref_harness.load_reference()
+        rnet = ref.star.STaR(args)
+        assert list(rnet.state_dict().keys()) == list(net.state_dict().keys())
+        assert len(net.get_nerf_params()) == len(rnet.get_nerf_params())
+
+
+def test_reference_init_statistics():
+    """Same initialisers as the reference: fc_1.weight zero, biases zero, kaiming fan-in scale."""
+    torch.manual_seed(0)
+    net = star_b200.STaR(ref_harness.make_args(num_vehicles=1, N_importance=8))
+    n = net.static_coarse_nerf
+    assert float(n.pts_net.blocks[0].fc_1.weight.abs().max()) == 0.0
+    assert float(n.pts_net.lin_in.bias.abs().max()) == 0.0
+    assert abs(float(n.pts_net.blocks[1].fc_0.weight.std()) - (2.0 / 256) ** 0.5) < 2e-3
+    assert abs(float(n.pts_net.lin_in.weight.std()) - (2.0 / 63) ** 0.5) < 5e-3
+
+
+def test_flat_master_order_and_versioning():
+    net = star_b200.STaR(ref_harness.make_args(num_vehicles=0, N_importance=0))
+    rt = net.static_coarse_nerf._rt
+    ps = rt.ordered_params()
+    names = {id(p): k for k, p in net.static_coarse_nerf.named_parameters()}
+    order = [names[id(p)] for p in ps]
+    assert order[:2] == ["pts_net.lin_in.weight", "pts_net.lin_in.bias"]
+    assert order[2:6] == ["pts_net.blocks.0.fc_0.weight", "pts_net.blocks.0.fc_0.bias",
+                          "pts_net.blocks.0.fc_1.weight", "pts_net.blocks.0.fc_1.bias"]
+    assert order[-8:] == ["alpha_linear.weight", "alpha_linear.bias", "feature_linear.weight", "feature_linear.bias",
+                          "views_linears.0.weight", "views_linears.0.bias", "rgb_linear.weight", "rgb_linear.bias"]
+    assert sum(p.numel() for p in ps) == 711300
+
+
+def test_pose7_gradient_convention_matches_oracle_pypose_restatement():
+    torch.manual_seed(1)
+    p7 = so.random_poses7(1, seed=4)[0]
+    pts, dirs = torch.randn(30, 3), torch.randn(7, 3)
+    wp, wd = torch.randn(30, 3), torch.randn(7, 3)
+    a = p7.clone().requires_grad_(True)
+    ((so.se3_act(a, pts) * wp).sum() + (so.so3_act(a[3:], dirs) * wd).sum()).backward()
+    b = p7.clone().requires_grad_(True)
+    m12 = F_.pose_to_mat12(b)
+    Rm, t = m12[:9].view(3, 3), m12[9:]
+    ((((Rm @ pts.T).T + t) * wp).sum() + ((Rm @ dirs.T).T * wd).sum()).backward()
+    assert_close(b.grad, a.grad, 1e-5, 1e-5)
+    assert float(b.grad[6]) == 0.0
+
+
+def test_pose_matrix_slicing_is_euclidean():
+    M = so.pose7_to_matrix(so.random_poses7(1, seed=5))[0].requires_grad_(True)
+    m12 = F_.pose_to_mat12(M)
+    m12.sum().backward()
+    assert float(M.grad[3].abs().sum()) == 0.0 and float(M.grad[:3].sum()) == 12.0
+
+
+@pytest.mark.parametrize("L,step", [(10, 13), (4, 13), (10, 0), (10, 99)])
+def test_barf_scale_vector_matches_oracle(L, step):
+    x = (torch.rand(11, 3) * 2 - 1)
+    plain = so.embed(x, L)
+    want = so.embed(x, L, step=step, end_barf=40)
+    s = emb.barf_scale_vector(step, 40, L)
+    assert_close(plain * s, want, 1e-7)
+
+
+def test_ray_chunking_covers_all_rays():
+    for R, S in ((1, 64), (1000, 512), (640000, 192), (5, 1 << 20)):
+        ch = F_._ray_chunks(R, S)
+        assert ch[0][0] == 0 and ch[-1][1] == R
+        assert all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+        assert all((b - a) * S <= max(S, F_.MAX_SAMPLES_PER_LAUNCH) for a, b in ch)
+
+
+def test_install_registers_reference_module_names():
+    import sys
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "models" or k.startswith("models.")}
+    for k in saved:
+        sys.modules.pop(k)
+    try:
+        star_b200.install()
+        from models.star__ import STaR
+        from models.rendering__ import sample_pts, render_star_online, render_star_appinit, mse2psnr, img2mse, to8b, get_rays, get_rays_np  # noqa: F401
+        assert STaR is star_b200.STaR
+    finally:
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            sys.modules.pop(k)
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
