@@ -56,6 +56,7 @@ _SIGS = {
                                   c_f, c_f]),
     "star_invert_cdf": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f]),
     "star_hierarchical": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f]),
+    "star_merge_samples": (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -212,10 +212,13 @@ extern "C" int star_invert_cdf(const float* bins, const float* cdf, const float*
 // ------------------------------------------------------------------------------------------ a10
 // z_mid -> sample_pdf -> sort(cat(z_vals, z_samples)) -> z_std, pts.  One warp per ray.
 // smem per warp: cdf[nb] | bins[nb] | zall[P]   (P = next pow2 >= Nc+Ni, padded with +inf)
+// GIVEN = true: the fine samples are supplied in z_samples (read, not written) and only the merge,
+// z_std and pts are computed (star_merge_samples).
+template <bool GIVEN>
 __global__ void hierarchical_kernel(const float* __restrict__ z_vals, const float* __restrict__ weights,
                                     const float* __restrict__ u, const float* __restrict__ u_det,
                                     const float* __restrict__ rays_o, const float* __restrict__ rays_d, int R,
-                                    int Nc, int Ni, int P, float* __restrict__ z_samples,
+                                    int Nc, int Ni, int P, float* z_samples,
                                     float* __restrict__ z_all, float* __restrict__ z_std,
                                     float* __restrict__ pts_fine) {
   extern __shared__ float smem[];
@@ -226,17 +229,24 @@ __global__ void hierarchical_kernel(const float* __restrict__ z_vals, const floa
   float* za = sb + nb;
   for (int r = blockIdx.x * wpb + warp; r < R; r += gridDim.x * wpb) {
     const float* zr = z_vals + (int64_t)r * Nc;
-    build_cdf_warp(weights + (int64_t)r * Nc + 1, Nc - 2, cdf, lane);  // weights[..., 1:-1]  (:131,274)
-    for (int k = lane; k < nb; k += 32) sb[k] = __fmul_rn(0.5f, __fadd_rn(zr[k + 1], zr[k]));  // z_mid (:128)
+    if (!GIVEN) {
+      build_cdf_warp(weights + (int64_t)r * Nc + 1, Nc - 2, cdf, lane);  // weights[..., 1:-1]  (:131,274)
+      for (int k = lane; k < nb; k += 32) sb[k] = __fmul_rn(0.5f, __fadd_rn(zr[k + 1], zr[k]));  // z_mid (:128)
+    }
     for (int k = lane; k < Nc; k += 32) za[k] = zr[k];
     for (int k = Nf + lane; k < P; k += 32) za[k] = __int_as_float(0x7f800000);
     __syncwarp();
     float sum = 0.f;
     for (int j = lane; j < Ni; j += 32) {
-      const float uu = (u != nullptr) ? u[(int64_t)r * Ni + j] : u_det[j];
-      int i0, b0, a0;
-      const float s = invert_one(cdf, sb, nb, uu, i0, b0, a0);
-      z_samples[(int64_t)r * Ni + j] = s;
+      float s;
+      if (GIVEN) {
+        s = z_samples[(int64_t)r * Ni + j];
+      } else {
+        const float uu = (u != nullptr) ? u[(int64_t)r * Ni + j] : u_det[j];
+        int i0, b0, a0;
+        s = invert_one(cdf, sb, nb, uu, i0, b0, a0);
+        z_samples[(int64_t)r * Ni + j] = s;
+      }
       za[Nc + j] = s;
       sum += s;
     }
@@ -293,9 +303,29 @@ extern "C" int star_hierarchical(const float* z_vals, const float* weights, cons
   int rc = launch_cfg_warp_per_ray(R, sizeof(float) * (2 * (Nc - 1) + P), blocks, threads, smem);
   if (rc) return rc;
   if (smem > 48 * 1024)
-    cudaFuncSetAttribute(hierarchical_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  hierarchical_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>(z_vals, weights, u, u_det, rays_o, rays_d,
-                                                                       R, Nc, Ni, P, z_samples, z_all, z_std,
-                                                                       pts_fine);
+    cudaFuncSetAttribute(hierarchical_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  hierarchical_kernel<false><<<blocks, threads, smem, (cudaStream_t)stream>>>(
+      z_vals, weights, u, u_det, rays_o, rays_d, R, Nc, Ni, P, z_samples, z_all, z_std, pts_fine);
+  return star_check_launch();
+}
+
+extern "C" int star_merge_samples(const float* z_vals, const float* z_samples, const float* rays_o,
+                                  const float* rays_d, int R, int Nc, int Ni, float* z_all, float* z_std,
+                                  float* pts_fine, void* stream) {
+  if (!z_vals || !z_samples || !z_all || !z_std) return STAR_E_NULL;
+  if (pts_fine && (!rays_o || !rays_d)) return STAR_E_NULL;
+  if (R < 0 || Nc < 1 || Ni < 1 || Nc + Ni > 8192) return STAR_E_BAD_SHAPE;
+  if (R == 0) return STAR_OK;
+  int P = 2;
+  while (P < Nc + Ni) P <<= 1;
+  int blocks, threads;
+  size_t smem;
+  int rc = launch_cfg_warp_per_ray(R, sizeof(float) * (2 * (Nc - 1) + P), blocks, threads, smem);
+  if (rc) return rc;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(hierarchical_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  hierarchical_kernel<true><<<blocks, threads, smem, (cudaStream_t)stream>>>(
+      z_vals, nullptr, nullptr, nullptr, rays_o, rays_d, R, Nc, Ni, P, const_cast<float*>(z_samples), z_all,
+      z_std, pts_fine);
   return star_check_launch();
 }

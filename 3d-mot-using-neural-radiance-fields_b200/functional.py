@@ -24,6 +24,27 @@ def _count(n=1):
     LAUNCH_COUNTER["calls"] += n
 
 
+# bench.py sets PROFILE = {} to collect (start_event, end_event, units) per named C-ABI call on the
+# launching stream (CUDA events only; no synchronisation is added).
+PROFILE = None
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _prof_end(name, e0, units):
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    PROFILE.setdefault(name, []).append((e0, e1, units))
+
+
 def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
@@ -207,13 +228,24 @@ def invert_cdf(bins, cdf, u):
     return samples, inds, below, above
 
 
-def hierarchical(z_vals, weights, N_importance, det, rays_o, rays_d, u=None, want_pts=True):
+def hierarchical(z_vals, weights, N_importance, det, rays_o, rays_d, u=None, want_pts=True, z_samples=None):
     """models/rendering__.py:128-144 / :271-296 in one kernel.  Returns z_samples, z_all, z_std, pts_fine.
-    Everything is detached, as in the reference (z_samples.detach(), :135,278)."""
+    Everything is detached, as in the reference (z_samples.detach(), :135,278).
+    z_samples: injected fine samples (skips the inverse-CDF step; merge / std / pts only)."""
     z_vals, weights = _c(z_vals.detach()), _c(weights.detach())
     rays_o, rays_d = _c(rays_o), _c(rays_d)
     R, Nc = z_vals.shape
     dev = z_vals.device
+    if z_samples is not None:
+        zs = _c(z_samples.detach())
+        assert zs.shape == (R, N_importance)
+        z_all = torch.empty((R, Nc + N_importance), device=dev)
+        z_std = torch.empty((R,), device=dev)
+        pts = torch.empty((R, Nc + N_importance, 3), device=dev) if want_pts else None
+        check(_capi.lib().star_merge_samples(f32(z_vals), f32(zs), f32(rays_o), f32(rays_d), R, Nc, N_importance,
+                                             f32(z_all), f32(z_std), ptr(pts), stream()), "star_merge_samples")
+        _count()
+        return zs, z_all, z_std, pts
     u_det = None
     if u is None:
         if det:
@@ -311,11 +343,13 @@ class NerfRaw(Function):
             if keep:
                 st = torch.empty((L.star_stash_bytes(C.byref(d), (b - a) * S),), device=dev, dtype=torch.uint8)
                 stashes.append(st)
+            e0 = _prof_begin()
             check(L.star_mlp_forward(C.byref(d), ptr(packed), f32(pts[a:b]), f32(viewdirs[a:b]),
                                      f32(p12) if p12 is not None else None,
                                      f32(sc_xyz) if sc_xyz is not None else None,
                                      f32(sc_dir) if sc_dir is not None else None, b - a, S, f32(raw_alpha[a:b]),
                                      f32(raw_rgb[a:b]), S, ptr(st), stream()), "star_mlp_forward")
+            _prof_end("mlp_forward_stash" if st is not None else "mlp_forward", e0, (b - a) * S)
             _count()
         if need_grad:
             ctx.rt, ctx.precision, ctx.chunks, ctx.stashes = rt, precision, chunks, stashes if keep else None
@@ -355,6 +389,7 @@ class NerfRaw(Function):
                                          f32(tmp_c), S, ptr(st), stream()), "star_mlp_forward(recompute)")
                 _count()
             ws = torch.empty((L.star_mlp_backward_workspace_bytes(C.byref(d), n),), device=dev, dtype=torch.uint8)
+            e0 = _prof_begin()
             check(L.star_mlp_backward(C.byref(d), ptr(ctx.packed), f32(ctx.flat), f32(pts[a:b]), f32(viewdirs[a:b]),
                                       f32(p12) if p12 is not None else None,
                                       f32(sc_xyz) if sc_xyz is not None else None,
@@ -362,6 +397,7 @@ class NerfRaw(Function):
                                       f32(g_rgb[a:b]), S, ptr(st), ptr(ws), f32(grad_flat),
                                       f32(pose_acc) if pose_acc is not None else None, stream()),
                   "star_mlp_backward")
+            _prof_end("mlp_backward", e0, n)
             _count(3 + 2 * rt.n_blocks + 4)
             if ctx.stashes is not None:
                 ctx.stashes[i] = None

@@ -3,7 +3,8 @@ burakcuhadar/3D-MOT-using-Neural-Radiance-Fields): same function names, position
 output dictionaries; every tensor op runs in the sm_100a kernels behind include/star_b200.h.
 
 Keyword-only extras (`t_rand=`, `u=`, `noise=`) inject the random draws the reference takes from
-torch.rand / torch.randn, so that parity tests can run "with fixed noise"."""
+torch.rand / torch.randn, so that parity tests can run "with fixed noise"; `z_samples=` injects the
+fine sample positions themselves (the output of sample_pdf) for stage-wise parity of the fine pass."""
 import numpy as np
 import torch
 
@@ -94,7 +95,7 @@ def sample_pdf(bins, weights, N_samples, det=False, *, u=None):
     return F_.sample_pdf(bins, weights, N_samples, det=det, u=u)
 
 
-def _coarse_to_fine(net_call, training, pts, z_vals, rays_o, rays_d, N_importance, u):
+def _coarse_to_fine(net_call, training, pts, z_vals, rays_o, rays_d, N_importance, u, z_samples=None):
     """Shared body of render_star_appinit / render_star_online / render_nerf (:115-149, :187-298)."""
     result = {}
     coarse = net_call(pts, z_vals, True)
@@ -102,7 +103,8 @@ def _coarse_to_fine(net_call, training, pts, z_vals, rays_o, rays_d, N_importanc
         result[f"{k}0"] = v
     if N_importance > 0:
         z_samples, z_all, z_std, pts_fine = F_.hierarchical(z_vals, coarse["weights"], N_importance,
-                                                            det=not training, rays_o=rays_o, rays_d=rays_d, u=u)
+                                                            det=not training, rays_o=rays_o, rays_d=rays_d, u=u,
+                                                            z_samples=z_samples)
         fine = net_call(pts_fine, z_all, False)
         for k, v in fine.items():
             result[k] = v
@@ -110,27 +112,29 @@ def _coarse_to_fine(net_call, training, pts, z_vals, rays_o, rays_d, N_importanc
     return result
 
 
-def render_star_appinit(star_network, pts, viewdirs, z_vals, rays_o, rays_d, N_importance, *, u=None):
+def render_star_appinit(star_network, pts, viewdirs, z_vals, rays_o, rays_d, N_importance, *, u=None,
+                        z_samples=None):
     """(:115-149)."""
     def call(p, z, coarse):
         return star_network(p, viewdirs, z, rays_d, is_coarse=coarse)
-    return _coarse_to_fine(call, star_network.training, pts, z_vals, rays_o, rays_d, N_importance, u)
+    return _coarse_to_fine(call, star_network.training, pts, z_vals, rays_o, rays_d, N_importance, u, z_samples)
 
 
 def render_star_online(star_network, pts, viewdirs, z_vals, rays_o, rays_d, N_importance, pose, step=None, *,
-                       u=None):
+                       u=None, z_samples=None):
     """(:249-298)."""
     def call(p, z, coarse):
         return star_network(p, viewdirs, z, rays_d, pose, is_coarse=coarse, step=step)
-    return _coarse_to_fine(call, star_network.training, pts, z_vals, rays_o, rays_d, N_importance, u)
+    return _coarse_to_fine(call, star_network.training, pts, z_vals, rays_o, rays_d, N_importance, u, z_samples)
 
 
-def render_nerf(nerf_coarse, nerf_fine, pts, viewdirs, z_vals, rays_o, rays_d, N_importance, far_dist, *, u=None):
+def render_nerf(nerf_coarse, nerf_fine, pts, viewdirs, z_vals, rays_o, rays_d, N_importance, far_dist, *, u=None,
+                z_samples=None):
     """(:187-245) two bare NeRF modules."""
     def call(p, z, coarse):
         net = nerf_coarse if coarse else nerf_fine
         ra, rc = net(p, viewdirs, step=None)
         return raw2outputs(ra, rc, z, rays_d, net.raw_noise_std if net.training else 0, net.white_bkgd, far_dist)
-    res = _coarse_to_fine(call, nerf_coarse.training, pts, z_vals, rays_o, rays_d, N_importance, u)
+    res = _coarse_to_fine(call, nerf_coarse.training, pts, z_vals, rays_o, rays_d, N_importance, u, z_samples)
     assert all(k in res for k in NERF_KEYS)
     return res

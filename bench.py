@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the STaR / NeRF render hot path (BASELINE.json metric: rays/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode render|train] [--precision bf16|fp32]
+    python bench.py --impl reference ...      # the reference algorithm on the host cores (oracle port)
+
+Workload (BASELINE.json configs[1], "C2"): lego-shaped vanilla NeRF, coarse+fine 64+128 samples,
+random-init weights (fc_1 re-drawn), perturb=0, white background.
+  render : one "step" = one full 800x800 view (640 000 rays) through sample_pts + render_star_appinit (eval).
+  train  : one "step" = one 4096-ray training step (forward + backward to all MLP weights).
+`value` is device-timed with the rays already resident in HBM; `e2e` goes through the same public
+API from pinned HOST buffers (H2D of the rays and D2H of rgb/depth/acc inside the timed region).
+With N>1 (torchrun, one process per GPU) every rank renders its own view / batch (rays shard with no
+data-path collective; "weak" scaling); train mode all-reduces the flat gradient with NCCL.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+NC, NI = 64, 128
+NEAR, FAR = 2.0, 6.0
+F_STATIC = 1.416704e6      # MLP FLOP per sample (2*MAC), static net
+RENDER_HW = 800
+TRAIN_RAYS = 4096
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="render", choices=["render", "train"])
+    ap.add_argument("--precision", default=os.environ.get("STAR_B200_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--hw", type=int, default=RENDER_HW, help="render mode: view is hw x hw rays")
+    ap.add_argument("--train-rays", type=int, default=TRAIN_RAYS)
+    ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays of the bounded CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ inputs
+def lego_view(hw, theta=30.0):
+    from oracle import star_oracle as so
+    ro, rd = so.lego_rays(hw, hw, theta=theta)
+    return ro.reshape(-1, 3).contiguous(), rd.reshape(-1, 3).contiguous()
+
+
+def make_params(seed=0):
+    from oracle import star_oracle as so
+    return so.init_star_params(0, NI, seed=seed, bias_std=0.02)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.rows = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_render_rays_per_s(n_rays, threads, repeat=1):
+    """The reference algorithm (oracle port: same eager ATen ops as the reference's PyTorch code) on the
+    host cores: render `n_rays` rays of the C2 view, coarse+fine, eval mode."""
+    from oracle import star_oracle as so
+    torch.set_num_threads(threads)
+    p = make_params()
+    cfg = so.StarConfig(0, NI, 8192, white_bkgd=True)
+    ro, rd = lego_view(RENDER_HW)
+    g = torch.Generator().manual_seed(0)
+    idx = torch.randperm(ro.shape[0], generator=g)[:n_rays]
+    ro, rd = ro[idx].contiguous(), rd[idx].contiguous()
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    best = None
+    with torch.no_grad():
+        for _ in range(repeat):
+            t0 = time.perf_counter()
+            pts, z = so.sample_pts(ro, rd, NEAR, FAR, NC, is_train=False)
+            out = so.render_star(p, cfg, pts, vd, z, ro, rd, NI, training=False)
+            float(out["rgb"].sum())
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return n_rays / best, best
+
+
+def cpu_train_rays_per_s(n_rays, threads):
+    from oracle import star_oracle as so
+    torch.set_num_threads(threads)
+    p = {k: v.requires_grad_(True) for k, v in make_params().items()}
+    cfg = so.StarConfig(0, NI, 8192, white_bkgd=True)
+    ro, rd = lego_view(RENDER_HW)
+    g = torch.Generator().manual_seed(0)
+    idx = torch.randperm(ro.shape[0], generator=g)[:n_rays]
+    ro, rd = ro[idx].contiguous(), rd[idx].contiguous()
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    u = torch.rand(n_rays, NI, generator=g)
+    target = torch.rand(n_rays, 3, generator=g)
+    t0 = time.perf_counter()
+    pts, z = so.sample_pts(ro, rd, NEAR, FAR, NC)
+    out = so.render_star(p, cfg, pts, vd, z, ro, rd, NI, training=True, u=u)
+    loss = ((out["rgb"] - target) ** 2).mean() + ((out["rgb0"] - target) ** 2).mean()
+    loss.backward()
+    dt = time.perf_counter() - t0
+    return n_rays / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.cpu_sample_rays or (2048 if args.mode == "render" else 1024)
+    fn = cpu_render_rays_per_s if args.mode == "render" else cpu_train_rays_per_s
+    for _ in range(min(args.warmup, 1)):
+        fn(max(64, n // 8), threads)
+    times = []
+    for _ in range(args.steps):
+        times.append(fn(n, threads)[1])
+    dt = sum(times) / len(times)
+    val = n / dt
+    line = {
+        "impl": "reference", "metric": metric_name(args.mode), "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, "fp32"),
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
+                         "sample": "%d random rays of the %s workload per step" % (n, args.mode)},
+        "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def metric_name(mode):
+    return "rays/sec (render fwd)" if mode == "render" else "rays/sec (train fwd+bwd)"
+
+
+def workload_config(args, precision):
+    if args.mode == "render":
+        wl = "C2 lego vanilla NeRF coarse+fine 64+128, full %dx%d view render (%d rays/step/GPU), eval, perturb=0" % (
+            args.hw, args.hw, args.hw * args.hw)
+    else:
+        wl = "C2 lego vanilla NeRF coarse+fine 64+128, %d-ray training step (fwd+bwd, all MLP weights)" % args.train_rays
+    return {"workload": wl, "N_samples": NC, "N_importance": NI, "mlp_precision": precision,
+            "parallelism": "ray-sharded x%d" % args.gpus,
+            "l2": "inputs+activations per step exceed the 126 MB L2" if args.mode == "render" else
+                  "L2 flushed between timed iterations (256 MB write)"}
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch.distributed as dist
+    import star_b200
+    from star_b200 import functional as F_
+    from star_b200.models import rendering__ as R_
+    from oracle import ref_harness  # make_args only (argparse.Namespace builder); no compute
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    net = star_b200.STaR(ref_harness.make_args(num_vehicles=0, N_importance=NI, chunk=8192, white_bkgd=True))
+    net.load_state_dict(make_params())
+    net.to(dev)
+    net.set_precision(args.precision)
+    train = args.mode == "train"
+    net.train(train)
+
+    if train:
+        ro_h, rd_h = lego_view(RENDER_HW, theta=30.0 + 7.0 * rank)
+        g = torch.Generator().manual_seed(100 + rank)
+        idx = torch.randperm(ro_h.shape[0], generator=g)[:args.train_rays]
+        ro_h, rd_h = ro_h[idx].contiguous(), rd_h[idx].contiguous()
+        u = torch.rand(args.train_rays, NI, generator=g).to(dev)
+        target = torch.rand(args.train_rays, 3, generator=g).to(dev)
+    else:
+        ro_h, rd_h = lego_view(args.hw, theta=30.0 + 7.0 * rank)
+    R = ro_h.shape[0]
+    ro_h, rd_h = ro_h.pin_memory(), rd_h.pin_memory()
+    ro, rd = ro_h.to(dev), rd_h.to(dev)
+    params = [p for p in net.parameters()]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if train else None
+
+    def step_device(ro, rd):
+        vd = rd / rd.norm(dim=-1, keepdim=True)
+        if train:
+            for p in params:
+                p.grad = None
+            pts, z = R_.sample_pts(ro, rd, NEAR, FAR, NC, perturb=0, is_train=True)
+            out = R_.render_star_appinit(net, pts, vd, z, ro, rd, NI, u=u)
+            loss = ((out["rgb"] - target) ** 2).mean() + ((out["rgb0"] - target) ** 2).mean()
+            loss.backward()
+            if world > 1:
+                flat = torch.cat([p.grad.reshape(-1) for p in params])
+                dist.all_reduce(flat)
+            return loss
+        with torch.no_grad():
+            pts, z = R_.sample_pts(ro, rd, NEAR, FAR, NC, perturb=0, is_train=False)
+            out = R_.render_star_appinit(net, pts, vd, z, ro, rd, NI)
+        return out
+
+    def step_e2e():
+        a = ro_h.to(dev, non_blocking=True)
+        b = rd_h.to(dev, non_blocking=True)
+        out = step_device(a, b)
+        if train:
+            return out.cpu()
+        return out["rgb"].cpu(), out["depth"].cpu(), out["acc"].cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device(ro, rd)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    F_.LAUNCH_COUNTER["calls"] = 0
+    F_.PROFILE = {}
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        if flush is not None:
+            flush.fill_(i)
+        ev[2 * i].record()
+        step_device(ro, rd)
+        ev[2 * i + 1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = F_.LAUNCH_COUNTER["calls"]
+    prof = F_.PROFILE
+    F_.PROFILE = None
+    ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- timed region 2: end to end from pinned host memory through the public API
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    ms_e2e_wall = (time.perf_counter() - t0) * 1e3 / args.steps
+    ms_e2e = max(ms_e2e, ms_e2e_wall)      # the D2H read is synchronous: wall clock covers it
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        total_rays = R * world
+        # roofline of the dominant kernel (the fused MLP forward): algorithmic FLOPs / event time
+        roof = None
+        key = "mlp_forward"
+        if prof and key in prof and prof[key]:
+            tot_ms = sum(a.elapsed_time(b) for a, b, _ in prof[key])
+            tot_samples = sum(n for _, _, n in prof[key])
+            n_l = len(prof[key])
+            peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(
+                os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+            peak_tf = (peak["bf16_tflops_sustained"] if peak else 1400.0)
+            ach = tot_samples * F_STATIC / (tot_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "star_mlp_forward (%s)" % args.precision, "achieved": ach,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peak else "fallback",
+                    "launches": n_l, "avg_launch_ms": tot_ms / n_l,
+                    "share_of_step": tot_ms / (ms * args.steps)}
+        line = {
+            "metric": metric_name(args.mode), "value": total_rays / (ms * 1e-3), "unit": "rays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic", "config": workload_config(args, args.precision),
+            "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 24 * R,
+                    "d2h_bytes_per_step": (4 if train else 20 * R)},
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "wall_ms_per_step": t_wall * 1e3 / args.steps,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            n = args.cpu_sample_rays or (2048 if not train else 1024)
+            fn = cpu_train_rays_per_s if train else cpu_render_rays_per_s
+            fn(max(64, n // 8), threads)
+            v, dt = fn(n, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
+                                    "sample": "%d random rays of the same workload, %.1f s" % (n, dt)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

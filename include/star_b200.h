@@ -173,6 +173,13 @@ int star_hierarchical(const float* z_vals, const float* weights, const float* u,
                       const float* rays_o, const float* rays_d, int R, int Nc, int Ni, float* z_samples,
                       float* z_all, float* z_std, float* pts_fine, void* stream);
 
+/* The merge half of star_hierarchical on caller-supplied fine samples z_samples[R,Ni] (the
+ * reference's `sort(cat([z_vals, z_samples]))`, std and `pts = o + d*z`, :136-144): used when the
+ * caller injects the sample positions (stage-wise parity of the fine pass; sample_pdf is
+ * ill-conditioned where the coarse pdf is small). */
+int star_merge_samples(const float* z_vals, const float* z_samples, const float* rays_o, const float* rays_d,
+                       int R, int Nc, int Ni, float* z_all, float* z_std, float* pts_fine, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

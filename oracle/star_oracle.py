@@ -419,7 +419,15 @@ def star_forward(params, cfg, pts, viewdirs, z_vals, rays_d, pose=None, is_coars
 
 
 # ----------------------------------------------------------------------------- a10 orchestration
-def _hierarchical(z_vals, weights, N_importance, det, u, exact_sum):
+def _hierarchical(z_vals, weights, N_importance, det, u, exact_sum, z_samples=None):
+    """z_samples: "teacher forcing" -- use these fine samples instead of inverting the coarse pdf.
+    sample_pdf is ill-conditioned where the pdf is small (t = (u - cdf_lo) / denom with denom down to
+    1e-5 turns a 1e-7 rounding difference of the coarse weights into a 1e-3 shift of a sample), so
+    stage-wise parity of the fine pass is checked on identical sample positions."""
+    if z_samples is not None:
+        zs = z_samples.detach()
+        z_all, _ = torch.sort(torch.cat([z_vals, zs], -1), -1)
+        return zs, z_all
     mid = 0.5 * (z_vals[..., 1:] + z_vals[..., :-1])
     zs = sample_pdf(mid, weights[..., 1:-1], N_importance, det=det, u=u, exact_sum=exact_sum).detach()
     z_all, _ = torch.sort(torch.cat([z_vals, zs], -1), -1)
@@ -427,7 +435,7 @@ def _hierarchical(z_vals, weights, N_importance, det, u, exact_sum):
 
 
 def render_star(params, cfg, pts, viewdirs, z_vals, rays_o, rays_d, N_importance, pose=None, step=None,
-                training=False, u=None, exact_sum=False):
+                training=False, u=None, exact_sum=False, z_samples=None):
     """models/rendering__.py:115-149 (pose None, render_star_appinit) and :249-298
     (render_star_online).  `u` injects sample_pdf's uniform draws in training mode."""
     res = {}
@@ -435,7 +443,8 @@ def render_star(params, cfg, pts, viewdirs, z_vals, rays_o, rays_d, N_importance
     for k, v in coarse.items():
         res[f"{k}0"] = v
     if N_importance > 0:
-        zs, z_all = _hierarchical(z_vals, coarse["weights"], N_importance, not training, u, exact_sum)
+        zs, z_all = _hierarchical(z_vals, coarse["weights"], N_importance, not training, u, exact_sum,
+                                  z_samples)
         pts_f = rays_o[..., None, :] + rays_d[..., None, :] * z_all[..., :, None]
         fine = star_forward(params, cfg, pts_f, viewdirs, z_all, rays_d, pose, False, step, training)
         res.update(fine)
@@ -444,13 +453,13 @@ def render_star(params, cfg, pts, viewdirs, z_vals, rays_o, rays_d, N_importance
 
 
 def render_nerf(params, prefix_coarse, prefix_fine, cfg, pts, viewdirs, z_vals, rays_o, rays_d,
-                N_importance, far_dist, training=False, u=None, exact_sum=False):
+                N_importance, far_dist, training=False, u=None, exact_sum=False, z_samples=None):
     """models/rendering__.py:187-245 (two bare NeRF modules)."""
     kw = dict(L_xyz=cfg.multires, L_dir=cfg.multires_views, end_barf=cfg.end_barf)
     std = cfg.raw_noise_std if training else 0
     a, c = nerf_mlp(params, prefix_coarse, pts, viewdirs, **kw)
     coarse = raw2outputs(a, c, z_vals, rays_d, std, cfg.white_bkgd, far_dist)
-    zs, z_all = _hierarchical(z_vals, coarse["weights"], N_importance, not training, u, exact_sum)
+    zs, z_all = _hierarchical(z_vals, coarse["weights"], N_importance, not training, u, exact_sum, z_samples)
     pts_f = rays_o[..., None, :] + rays_d[..., None, :] * z_all[..., :, None]
     a, c = nerf_mlp(params, prefix_fine, pts_f, viewdirs, **kw)
     fine = raw2outputs(a, c, z_all, rays_d, std, cfg.white_bkgd, far_dist)

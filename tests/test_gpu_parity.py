@@ -317,17 +317,29 @@ def test_nerf_mlp_barf_mask_on_dynamic_net():
 
 
 # ------------------------------------------------------------------------------------------ end to end
-def _check_outputs(out, g, atol=1e-4):
+# Two modes (DESIGN.md "conditioning of sample_pdf"): free running (fine samples from the coarse pdf
+# computed on the GPU: coarse keys tight, fine keys loose because sample_pdf amplifies last-bit
+# differences of the coarse weights) and teacher forced (the reference's z_samples injected: all
+# outputs within the north star's 1e-4 absolute, gradients compared too).
+FINE_LOOSE = 5e-3
+META = ("seed", "rays_o", "rays_d", "near", "far", "Nc", "Ni", "z_samples", "u", "target", "pose", "chunk", "loss",
+        "pose_grad")
+
+
+def _check_outputs(out, g, atol=1e-4, fine_atol=None):
     n = 0
     for k, v in out.items():
         if v is None:
             assert k not in g, k
             continue
         assert k in g, f"unexpected output key {k}"
-        tol = atol * (50 if k.startswith("disp") else 1)
+        tol = atol if (k.endswith("0") or fine_atol is None) else fine_atol
+        if k.startswith("disp"):
+            tol *= 50
         assert_close(v, g[k], tol, 1e-4, k)
         n += 1
-    assert n == sum(1 for k in g if k in out or False) or n >= 10
+    assert n >= 10
+    assert {k for k, v in out.items() if v is not None} == {k for k in g if k not in META and not k.startswith("gd.")}
 
 
 def _digest(t):
@@ -343,35 +355,40 @@ def _check_grad_digests(net, g, rtol=2e-3):
         assert_close(_digest(v.grad), ref, 1e-3 * scale + 1e-7, rtol, "grad digest " + k)
 
 
-def test_e2e_appinit_eval_fixture():
+@pytest.mark.parametrize("forced", [False, True])
+def test_e2e_appinit_eval_fixture(forced):
     g = load_golden("e2e_appinit_eval")
     net, _ = make_star(0, 24, 4096, True, int(g["seed"]), training=False)
     ro, rd = cu(g["rays_o"]), cu(g["rays_d"])
     vd = rd / rd.norm(dim=-1, keepdim=True)
     with torch.no_grad():
         pts, z = R_.sample_pts(ro, rd, g["near"], g["far"], int(g["Nc"]), is_train=False)
-        out = R_.render_star_appinit(net, pts, vd, z, ro, rd, int(g["Ni"]))
-    _check_outputs(out, g)
-    assert set(out) == {k for k in g if k not in ("seed", "rays_o", "rays_d", "near", "far", "Nc", "Ni")}
+        out = R_.render_star_appinit(net, pts, vd, z, ro, rd, int(g["Ni"]),
+                                     z_samples=cu(g["z_samples"]) if forced else None)
+    _check_outputs(out, g, fine_atol=None if forced else FINE_LOOSE)
 
 
-def test_e2e_appinit_train_fixture_with_grads():
+@pytest.mark.parametrize("forced", [False, True])
+def test_e2e_appinit_train_fixture_with_grads(forced):
     g = load_golden("e2e_appinit_train")
     net, _ = make_star(0, 24, int(g["chunk"]), False, int(g["seed"]), training=True)
     ro, rd, target = cu(g["rays_o"]), cu(g["rays_d"]), cu(g["target"])
     vd = rd / rd.norm(dim=-1, keepdim=True)
     pts, z = R_.sample_pts(ro, rd, g["near"], g["far"], int(g["Nc"]))
-    out = R_.render_star_appinit(net, pts, vd, z, ro, rd, int(g["Ni"]), u=cu(g["u"]))
-    _check_outputs(out, g)
+    out = R_.render_star_appinit(net, pts, vd, z, ro, rd, int(g["Ni"]), u=cu(g["u"]),
+                                 z_samples=cu(g["z_samples"]) if forced else None)
+    _check_outputs(out, g, fine_atol=None if forced else FINE_LOOSE)
     loss = ((out["rgb0"] - target) ** 2).mean() + ((out["rgb"] - target) ** 2).mean() + 0.1 * out["depth"].mean()
-    assert_close(loss, g["loss"], 1e-5)
     loss.backward()
-    _check_grad_digests(net, g)
+    if forced:
+        assert_close(loss, g["loss"], 1e-5)
+        _check_grad_digests(net, g)
 
 
+@pytest.mark.parametrize("forced", [False, True])
 @pytest.mark.parametrize("name,training", [("e2e_online_mat_train", True), ("e2e_online_mat_eval", False),
                                            ("e2e_online_quat_train", True)])
-def test_e2e_online_fixture(name, training):
+def test_e2e_online_fixture(name, training, forced):
     g = load_golden(name)
     net, _ = make_star(2, 24, int(g["chunk"]), False, int(g["seed"]), training=training)
     ro, rd, target = cu(g["rays_o"]), cu(g["rays_d"]), cu(g["target"])
@@ -380,19 +397,21 @@ def test_e2e_online_fixture(name, training):
     with torch.set_grad_enabled(training):
         pts, z = R_.sample_pts(ro, rd, g["near"], g["far"], int(g["Nc"]))
         out = R_.render_star_online(net, pts, vd, z, ro, rd, int(g["Ni"]), pose, step=None,
-                                    u=cu(g["u"]) if training else None)
-    _check_outputs(out, g)
+                                    u=cu(g["u"]) if training else None,
+                                    z_samples=cu(g["z_samples"]) if forced else None)
+    _check_outputs(out, g, fine_atol=None if forced else FINE_LOOSE)
     if not training:
         assert out["rgb_dynamic_all"] is not None and out["rgb_dynamic_all0"] is not None
         return
     loss = ((out["rgb0"] - target) ** 2).mean() + ((out["rgb"] - target) ** 2).mean()
     for l, k in zip((1e-3, 1e-3, 1e-5, 1e-4, 1e-4), REGS):
         loss = loss + l * 0.5 * (out[k] + out[k + "0"])
-    assert_close(loss, g["loss"], 1e-5)
     loss.backward()
-    scale = float(g["pose_grad"].abs().max())
-    assert_close(pose.grad, g["pose_grad"], 2e-3 * scale, 2e-3, "pose grad")
-    _check_grad_digests(net, g)
+    if forced:
+        assert_close(loss, g["loss"], 1e-5)
+        scale = float(g["pose_grad"].abs().max())
+        assert_close(pose.grad, g["pose_grad"], 2e-3 * scale, 2e-3, "pose grad")
+        _check_grad_digests(net, g)
 
 
 def test_error_paths():

@@ -144,6 +144,18 @@ def main():
     npz("nerf_mlp", seed=3, V=1, pts=pts, viewdirs=vd, raw_alpha_static_coarse=a_s, raw_rgb_static_coarse=c_s,
         raw_alpha_dynamic_fine0=a_d, raw_rgb_dynamic_fine0=c_d)
 
+    # every end-to-end case also records the fine samples the reference drew (the return value of its
+    # sample_pdf), so that the fine pass can be checked on identical sample positions
+    zrec = {}
+    real_sample_pdf = R_.sample_pdf
+
+    def sample_pdf_spy(*a, **kw):
+        out = real_sample_pdf(*a, **kw)
+        zrec["z_samples"] = out.detach().clone()
+        return out
+
+    R_.sample_pdf = sample_pdf_spy
+
     # ---- end to end: app-init eval (C1-shaped, tiny), white bkgd, det sampling
     net, args = ref_star(0, 24, 4096, True, seed=4)
     net.eval()
@@ -152,7 +164,7 @@ def main():
     pts, z = R_.sample_pts(ro, rd, 2.0, 6.0, 16, perturb=0, is_train=False)
     with torch.no_grad():
         out = R_.render_star_appinit(net, pts, vd, z, ro, rd, 24)
-    npz("e2e_appinit_eval", seed=4, rays_o=ro, rays_d=rd, near=2.0, far=6.0, Nc=16, Ni=24, **flat_outputs("", out))
+    npz("e2e_appinit_eval", seed=4, rays_o=ro, rays_d=rd, near=2.0, far=6.0, Nc=16, Ni=24, z_samples=zrec["z_samples"], **flat_outputs("", out))
 
     # ---- end to end: app-init TRAIN (random u, grads to weights), chunk < R
     net, args = ref_star(0, 24, 10, False, seed=5)
@@ -169,7 +181,8 @@ def main():
     loss = ((out["rgb0"] - target) ** 2).mean() + ((out["rgb"] - target) ** 2).mean() + 0.1 * out["depth"].mean()
     loss.backward()
     npz("e2e_appinit_train", seed=5, chunk=10, rays_o=ro, rays_d=rd, near=0.03, far=0.8, Nc=16, Ni=24, u=u,
-        target=target, loss=loss, **flat_outputs("", out), **grad_digest(net.named_parameters()))
+        target=target, loss=loss, z_samples=zrec["z_samples"], **flat_outputs("", out),
+        **grad_digest(net.named_parameters()))
 
     # ---- end to end: online, V=2, 4x4 pose, train mode (regularisers + pose grads), two ray chunks
     lam = (1e-3, 1e-3, 1e-5, 1e-4, 1e-4)
@@ -197,7 +210,7 @@ def main():
             loss.backward()
             extra = dict(loss=loss, pose_grad=pose.grad, **grad_digest(net.named_parameters()))
         npz(name, seed=seed, chunk=chunk, rays_o=ro, rays_d=rd, near=0.03, far=0.8, Nc=16, Ni=24, u=u,
-            target=target, pose=pose, **flat_outputs("", out), **extra)
+            target=target, pose=pose, z_samples=zrec["z_samples"], **flat_outputs("", out), **extra)
 
     online_case("e2e_online_mat_train", so.pose7_to_matrix, True, 12, seed=6)
     with torch.no_grad():
