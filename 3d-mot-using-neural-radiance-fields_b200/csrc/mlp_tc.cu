@@ -1,0 +1,419 @@
+// bf16 tensor-core tier of the per-sample NeRF MLP (models/nerf.py:112-179, models/resnet.py:51-59,103-110)
+// for sm_100a: pose transform (star__.py:160-199) -> positional encoding (embedder.py:81-112) ->
+// ResNet-FC trunk -> heads as ONE persistent, warp-specialised kernel per launch.
+//
+// One CTA per SM walks tiles of 128 samples.  Roles (320 threads):
+//   warps 0-7  "epilogue" warps: encode the tile's inputs to bf16 into the shared-memory A operand, and after
+//              every layer move the fp32 accumulator TMEM -> registers, add bias / ReLU, convert to bf16 and
+//              write the next layer's A operand (warp w owns TMEM lanes 32*(w%4).., column half w/4);
+//              alpha / rgb heads are fp32 dot products in these registers.
+//   warp 8     weight producer: streams the pre-swizzled bf16 weight K-blocks (32 KB each) from L2 into a
+//              4-stage shared-memory ring with 1-D bulk async copies (TMA engine) + mbarrier transaction counts.
+//   warp 9     MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16, bf16 -> fp32 in TMEM).
+//
+// TMEM (512 columns): X = columns 0..255 holds the residual stream x (fp32, biases kept separately),
+// T = columns 256..511 holds the other accumulator.  fc_1 ACCUMULATES onto X, which performs the residual
+// add inside the tensor core.  Layers alternate X/T, so the epilogue of layer L (reading one region and
+// producing A K-block by K-block) overlaps the MMA of layer L+1 (writing the other region, consuming A
+// K-block by K-block through the a_ready[] barriers).
+#include "star_common.cuh"
+#include "tc_common.cuh"
+#include "mlp_tc_layout.h"
+
+#define TC_M 128
+#define TC_NS 4
+#define TC_STAGE_BYTES 32768
+#define TC_KB_BYTES 16384          // one A K-block: 128 rows x 128 B
+#define TC_EPI_WARPS 8
+#define TC_EPI_THREADS (32 * TC_EPI_WARPS)
+#define TC_THREADS (TC_EPI_THREADS + 64)
+#define TC_TMEM_COLS 512
+
+struct TcSmem {
+  uint32_t A, AD, W, small, part, bars, tmem_ptr;   // byte offsets from the 1024-aligned base
+  uint32_t total;
+};
+__host__ __device__ static inline TcSmem tc_smem_layout(uint32_t small_bytes) {
+  TcSmem s;
+  uint32_t o = 0;
+  s.A = o; o += 4 * TC_KB_BYTES;
+  s.AD = o; o += TC_KB_BYTES;
+  s.W = o; o += TC_NS * TC_STAGE_BYTES;
+  s.small = o; o += small_bytes;
+  s.part = o; o += TC_M * 4 * 4;
+  s.bars = o; o += 16 * 8;
+  s.tmem_ptr = o; o += 16;
+  s.total = o + 1024;   // slack for aligning the dynamic smem base
+  return s;
+}
+
+// barrier indices inside the bars block
+#define BAR_W_FULL(i) (i)
+#define BAR_W_EMPTY(i) (TC_NS + (i))
+#define BAR_A_READY(i) (2 * TC_NS + (i))      // 0..3: A K-blocks, 4: encoded-dirs block
+#define BAR_ACC_FULL (2 * TC_NS + 5)
+
+// ---------------------------------------------------------------------------------------------- encode
+// Positional encoding of one sample into 32 of the 64 (xyz) columns, plus the 27(+5 zero) dir columns.
+// sin/cos of the higher octaves come from the double-angle recurrence (error doubles per octave from
+// ~6e-8; 3e-5 after nine -- far below bf16 resolution).
+__device__ __forceinline__ void encode_half(int half, const float (&p)[3], const float (&dv)[3],
+                                            const float* __restrict__ sc_xyz, const float* __restrict__ sc_dir,
+                                            float (&e)[32], float (&ed)[32]) {
+  float sn[3], cs[3];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { e[j] = 0.f; ed[j] = 0.f; }
+  if (half == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { e[c] = p[c]; sincosf(p[c], &sn[c], &cs[c]); }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int j = 3 + 6 * k + c;
+        if (j < 32) e[j] = sn[c];
+        if (j + 3 < 32) e[j + 3] = cs[c];
+        const float s2 = 2.f * sn[c] * cs[c], c2 = 1.f - 2.f * sn[c] * sn[c];
+        sn[c] = s2; cs[c] = c2;
+      }
+    }
+    if (sc_xyz != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) e[j] *= sc_xyz[j];
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sincosf(16.f * p[c], &sn[c], &cs[c]);   // octave k = 4
+    e[0] = cs[2];                                                      // column 32 = cos(2^4 z)
+#pragma unroll
+    for (int k = 5; k < 10; ++k) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float s2 = 2.f * sn[c] * cs[c], c2 = 1.f - 2.f * sn[c] * sn[c];
+        sn[c] = s2; cs[c] = c2;
+        const int j = 3 + 6 * k + c - 32;
+        e[j] = sn[c];
+        e[j + 3] = cs[c];
+      }
+    }
+    if (sc_xyz != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 31; ++j) e[j] *= sc_xyz[32 + j];
+    }
+    // encoded view direction (27 values)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { ed[c] = dv[c]; sincosf(dv[c], &sn[c], &cs[c]); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int j = 3 + 6 * k + c;
+        ed[j] = sn[c];
+        ed[j + 3] = cs[c];
+        const float s2 = 2.f * sn[c] * cs[c], c2 = 1.f - 2.f * sn[c] * sn[c];
+        sn[c] = s2; cs[c] = c2;
+      }
+    }
+    if (sc_dir != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 27; ++j) ed[j] *= sc_dir[j];
+    }
+  }
+}
+
+// write 32 fp32 values as bf16 into 16-byte chunks ch0..ch0+3 of row `row` of a SW128 K-block
+__device__ __forceinline__ void store_row32_bf16(uint32_t kblock_saddr, int row, int ch0, const float (&v)[32]) {
+  const uint32_t rbase = kblock_saddr + (uint32_t)row * 128u;
+  const uint32_t x = (uint32_t)row & 7u;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t a = rbase + ((((uint32_t)(ch0 + c)) ^ x) << 4);
+    st_shared_v4(a, pack_bf16x2(v[8 * c + 0], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+                 pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+  }
+}
+
+// ============================================================================================ forward
+__global__ void __launch_bounds__(TC_THREADS, 1)
+mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const float* __restrict__ pts,
+                  const float* __restrict__ viewdirs, const float* __restrict__ pose12,
+                  const float* __restrict__ sc_xyz, const float* __restrict__ sc_dir, int S, int64_t M,
+                  float* __restrict__ raw_alpha, float* __restrict__ raw_rgb, int64_t ray_stride, int* dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw_addr);
+  const TcSmem sl = tc_smem_layout(lay.small_bytes);
+  const uint32_t sA = base + sl.A, sAD = base + sl.AD, sW = base + sl.W, sBars = base + sl.bars;
+  float* s_small = reinterpret_cast<float*>(gbase + sl.small);
+  float* s_part = reinterpret_cast<float*>(gbase + sl.part);
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(gbase + sl.tmem_ptr);
+  auto bar = [&](int i) -> uint32_t { return sBars + 8u * (uint32_t)i; };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (M + TC_M - 1) / TC_M;
+
+  // ---- one-time setup
+  if (warp == TC_EPI_WARPS && lane == 0) {
+    for (int i = 0; i < TC_NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), 1); mbar_init(bar(BAR_W_EMPTY(i)), 1); }
+    for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A_READY(i)), TC_EPI_THREADS);
+    mbar_init(bar(BAR_ACC_FULL), 1);
+    fence_mbar_init();
+  }
+  if (warp == TC_EPI_WARPS + 1) tmem_alloc(base + sl.tmem_ptr, TC_TMEM_COLS);
+  for (int i = tid; i < lay.small_floats; i += TC_THREADS) s_small[i] = reinterpret_cast<const float*>(packed)[i];
+  for (int i = tid; i < TC_KB_BYTES / 16; i += TC_THREADS)
+    reinterpret_cast<uint4*>(gbase + sl.AD)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == TC_EPI_WARPS) {
+    // ======================================================================== weight producer
+    if (lane == 0) {
+      const uint8_t* wstream = packed + lay.small_bytes;
+      uint32_t stage = 0, phase = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int l = 0; l < lay.n_layers; ++l) {
+          const uint32_t bytes = (uint32_t)lay.L[l].N * 128u;
+          for (int kb = 0; kb < lay.L[l].nkb; ++kb) {
+            mbar_wait(bar(BAR_W_EMPTY(stage)), phase ^ 1u, dbg, 1);
+            mbar_arrive_expect_tx(bar(BAR_W_FULL(stage)), bytes);
+            bulk_g2s(sW + stage * TC_STAGE_BYTES, wstream + lay.L[l].w_off + (uint32_t)kb * bytes, bytes,
+                     bar(BAR_W_FULL(stage)));
+            if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == TC_EPI_WARPS + 1) {
+    // ======================================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, a_par = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int l = 0; l < lay.n_layers; ++l) {
+          const TcLayer& L = lay.L[l];
+          const uint32_t d_tmem = tmem_base + (L.region ? 256u : 0u);
+          const uint32_t idesc = umma_idesc_bf16(TC_M, L.N);
+          for (int kb = 0; kb < L.nkb; ++kb) {
+            const int idx = (L.kind == LK_VIEWS && kb == 4) ? 4 : kb;
+            mbar_wait(bar(BAR_A_READY(idx)), (a_par >> idx) & 1u, dbg, 2);
+            a_par ^= 1u << idx;
+            mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
+            tc_fence_after();
+            const uint32_t a_addr = (idx == 4) ? sAD : sA + (uint32_t)kb * TC_KB_BYTES;
+            const uint32_t b_addr = sW + stage * TC_STAGE_BYTES;
+            const int nk = (idx == 4) ? 2 : 4;
+            for (int k = 0; k < nk; ++k)
+              tc_mma_bf16(d_tmem, umma_desc_sw128(a_addr + 32u * k), umma_desc_sw128(b_addr + 32u * k), idesc,
+                          (L.kind == LK_FC1 || kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit(bar(BAR_W_EMPTY(stage)));
+            if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
+          }
+          tc_commit(bar(BAR_ACC_FULL));
+        }
+      }
+    }
+  } else {
+    // ======================================================================== epilogue warps
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
+    uint32_t acc_par = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t gi = tile * TC_M + row;
+      const bool valid = gi < M;
+      int64_t out_idx = 0;
+      // ---- inputs: pose transform + encoding -> A K-block 0 (xyz) and the dirs block
+      {
+        float p[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+          const int64_t r = gi / S;
+          out_idx = r * ray_stride + (gi - r * S);
+          const float px = pts[gi * 3 + 0], py = pts[gi * 3 + 1], pz = pts[gi * 3 + 2];
+          const float dx = viewdirs[r * 3 + 0], dy = viewdirs[r * 3 + 1], dz = viewdirs[r * 3 + 2];
+          if (pose12 != nullptr) {   // p' = R p + t, d' = R d
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              p[i] = pose12[i * 3 + 0] * px + pose12[i * 3 + 1] * py + pose12[i * 3 + 2] * pz + pose12[9 + i];
+              dv[i] = pose12[i * 3 + 0] * dx + pose12[i * 3 + 1] * dy + pose12[i * 3 + 2] * dz;
+            }
+          } else {
+            p[0] = px; p[1] = py; p[2] = pz;
+            dv[0] = dx; dv[1] = dy; dv[2] = dz;
+          }
+        }
+        float e[32], ed[32];
+        encode_half(half, p, dv, sc_xyz, sc_dir, e, ed);
+        store_row32_bf16(sA, row, half * 4, e);
+        if (half == 1) store_row32_bf16(sAD, row, 0, ed);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar(BAR_A_READY(0)));
+        mbar_arrive(bar(BAR_A_READY(4)));
+      }
+      // ---- layers
+      for (int l = 0; l < lay.n_layers; ++l) {
+        const TcLayer& L = lay.L[l];
+        mbar_wait(bar(BAR_ACC_FULL), acc_par, dbg, 4);
+        acc_par ^= 1u;
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + lane_addr + (L.region ? 256u : 0u);
+        const float* bias = s_small + L.bias_off;
+        const int nch = L.N >> 6;
+        const bool relu = (L.kind == LK_IN || L.kind == LK_FC0 || L.kind == LK_FC1 || L.kind == LK_VIEWS);
+        float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+        for (int kb = 0; kb < nch; ++kb) {
+          const int col0 = kb * 64 + half * 32;
+          uint32_t r[32];
+          tmem_ld32(tbase + (uint32_t)col0, r);
+          tmem_wait_ld();
+          float v[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + col0 + 4 * j4);
+            v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + b.x;
+            v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + b.y;
+            v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + b.z;
+            v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + b.w;
+          }
+          if (relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (L.kind == LK_OUT) {          // alpha head (nerf.py:151) on the fp32 h
+            const float* aw = s_small + lay.off_alpha_w + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h0 = fmaf(v[j], aw[j], h0);
+          }
+          if (L.kind == LK_VIEWS) {        // rgb head (nerf.py:159) on the fp32 h2
+            const float* rw = s_small + lay.off_rgb_w + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              h0 = fmaf(v[j], rw[j], h0);
+              h1 = fmaf(v[j], rw[STAR_WV + j], h1);
+              h2 = fmaf(v[j], rw[2 * STAR_WV + j], h2);
+            }
+          } else {
+            store_row32_bf16(sA + (uint32_t)kb * TC_KB_BYTES, row, half * 4, v);
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar(BAR_A_READY(kb)));
+          }
+        }
+        if (L.kind == LK_OUT) {
+          if (half == 1) s_part[row * 4 + 0] = h0;
+          named_bar_sync(1, TC_EPI_THREADS);
+          if (half == 0 && valid) raw_alpha[out_idx] = h0 + s_part[row * 4 + 0] + s_small[lay.off_alpha_b];
+        } else if (L.kind == LK_VIEWS) {
+          if (half == 1) { s_part[row * 4 + 1] = h0; s_part[row * 4 + 2] = h1; s_part[row * 4 + 3] = h2; }
+          tc_fence_before();
+          named_bar_sync(1, TC_EPI_THREADS);
+          if (half == 0 && valid) {
+            float* o = raw_rgb + out_idx * 3;
+            o[0] = h0 + s_part[row * 4 + 1] + s_small[lay.off_rgb_b + 0];
+            o[1] = h1 + s_part[row * 4 + 2] + s_small[lay.off_rgb_b + 1];
+            o[2] = h2 + s_part[row * 4 + 3] + s_small[lay.off_rgb_b + 2];
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_EPI_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// ============================================================================================ packing
+__global__ void pack_tc_small_kernel(TcLayout tl, MlpLayout ml, const float* __restrict__ master,
+                                     float* __restrict__ small) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tl.small_floats; i += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    bool done = false;
+    for (int l = 0; l < tl.n_layers && !done; ++l) {
+      const int o = i - tl.L[l].bias_off;
+      if (o >= 0 && o < STAR_W) {
+        done = true;
+        if (o < tl.L[l].N) {
+          v = master[ml.L[l].m_b + o];
+          if (tl.L[l].kind == LK_FC1) {   // cumulative bias of the residual stream up to this block
+            v += master[ml.L[0].m_b + o];
+            for (int j = 2; j < l; j += 2) v += master[ml.L[j].m_b + o];
+          }
+        }
+      }
+    }
+    if (!done) {
+      if (i >= tl.off_alpha_w && i < tl.off_alpha_w + STAR_W) v = master[ml.m_alpha_w + (i - tl.off_alpha_w)];
+      else if (i == tl.off_alpha_b) v = master[ml.m_alpha_b];
+      else if (i >= tl.off_rgb_w && i < tl.off_rgb_w + 3 * STAR_WV) v = master[ml.m_rgb_w + (i - tl.off_rgb_w)];
+      else if (i >= tl.off_rgb_b && i < tl.off_rgb_b + 3) v = master[ml.m_rgb_b + (i - tl.off_rgb_b)];
+    }
+    small[i] = v;
+  }
+}
+
+__global__ void pack_tc_stream_kernel(TcLayout tl, MlpLayout ml, const float* __restrict__ master,
+                                      __nv_bfloat16* __restrict__ stream) {
+  const uint32_t n_elems = tl.stream_bytes / 2;
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_elems; e += gridDim.x * blockDim.x) {
+    const uint32_t byte = e * 2;
+    int l = 0;
+    while (l + 1 < tl.n_layers && byte >= tl.L[l + 1].w_off) ++l;
+    const TcLayer& L = tl.L[l];
+    const uint32_t off = byte - L.w_off, kb_bytes = (uint32_t)L.N * 128u;
+    const int kb = (int)(off / kb_bytes);
+    const uint32_t rem = off % kb_bytes;
+    const int n = (int)(rem >> 7);
+    const uint32_t inrow = rem & 127u;
+    const int chunk = (int)((inrow >> 4) ^ ((uint32_t)n & 7u));   // undo the 128-byte swizzle
+    const int kk = chunk * 8 + (int)((inrow & 15u) >> 1);
+    const int K = ml.L[l].K;                                     // true input width (63, 256, 283)
+    float v = 0.f;
+    if (L.kind == LK_VIEWS) {
+      const int k = (kb < 4) ? kb * 64 + kk : STAR_W + kk;
+      if (kb < 4 || kk < K - STAR_W) v = master[ml.L[l].m_w + (int64_t)n * K + k];
+    } else {
+      const int k = kb * 64 + kk;
+      if (k < K) v = master[ml.L[l].m_w + (int64_t)n * K + k];
+    }
+    stream[e] = __float2bfloat16_rn(v);
+  }
+}
+
+// ============================================================================================ host side
+size_t star_tc_packed_bytes(const TcLayout& tl) { return (size_t)tl.small_bytes + tl.stream_bytes; }
+
+int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, void* packed, cudaStream_t st) {
+  pack_tc_small_kernel<<<8, 256, 0, st>>>(tl, ml, master, (float*)packed);
+  int rc = star_check_launch();
+  if (rc) return rc;
+  pack_tc_stream_kernel<<<148 * 4, 256, 0, st>>>(tl, ml, master,
+                                                 (__nv_bfloat16*)((uint8_t*)packed + tl.small_bytes));
+  return star_check_launch();
+}
+
+int star_tc_forward(const TcLayout& tl, const void* packed, const float* pts, const float* viewdirs,
+                    const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
+                    float* raw_rgb, int64_t ray_stride, cudaStream_t st) {
+  const int64_t M = (int64_t)R * S;
+  const int64_t ntiles = (M + TC_M - 1) / TC_M;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  const TcSmem sl = tc_smem_layout(tl.small_bytes);
+  if (((uintptr_t)packed & 15) != 0) return STAR_E_ALIGN;
+  cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
+  if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
+  mlp_fwd_tc_kernel<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz,
+                                                         sc_dir, S, M, raw_alpha, raw_rgb, ray_stride, nullptr);
+  return star_check_launch();
+}
