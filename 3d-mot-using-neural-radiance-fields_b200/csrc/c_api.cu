@@ -6,10 +6,11 @@
 int g_star_last_cuda_error = 0;
 
 size_t star_tc_packed_bytes(const TcLayout& tl);
-int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, void* packed, cudaStream_t st);
+int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, void* packed, int fp16,
+                 cudaStream_t st);
 int star_tc_forward(const TcLayout& tl, const void* packed, const float* pts, const float* viewdirs,
                     const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
-                    float* raw_rgb, int64_t ray_stride, cudaStream_t st);
+                    float* raw_rgb, int64_t ray_stride, int fp16, cudaStream_t st);
 
 int star_f32_pack(const MlpLayout& lay, const float* master, void* packed, cudaStream_t st);
 int star_f32_forward(const MlpLayout& lay, const void* packed, const float* pts, const float* viewdirs,
@@ -46,7 +47,7 @@ extern "C" size_t star_packed_bytes(const StarNetDesc* d) {
   MlpLayout lay;
   if (!d || star_make_layout(d, &lay)) return 0;
   if (d->precision == STAR_PREC_F32) return sizeof(float) * (size_t)lay.n_packed;
-  if (d->precision == STAR_PREC_BF16) {
+  if (d->precision == STAR_PREC_BF16 || d->precision == STAR_PREC_F16) {
     TcLayout tl;
     if (star_make_tc_layout(d, &tl)) return 0;
     return star_tc_packed_bytes(tl);
@@ -60,11 +61,11 @@ extern "C" int star_pack_weights(const StarNetDesc* d, const float* flat_master,
   int rc = star_make_layout(d, &lay);
   if (rc) return rc;
   if (d->precision == STAR_PREC_F32) return star_f32_pack(lay, flat_master, packed, (cudaStream_t)stream);
-  if (d->precision == STAR_PREC_BF16) {
+  if (d->precision == STAR_PREC_BF16 || d->precision == STAR_PREC_F16) {
     TcLayout tl;
     rc = star_make_tc_layout(d, &tl);
     if (rc) return rc;
-    return star_tc_pack(tl, lay, flat_master, packed, (cudaStream_t)stream);
+    return star_tc_pack(tl, lay, flat_master, packed, d->precision == STAR_PREC_F16, (cudaStream_t)stream);
   }
   return STAR_E_UNSUPPORTED;
 }
@@ -96,13 +97,13 @@ extern "C" int star_mlp_forward(const StarNetDesc* d, const void* packed, const 
   if (d->precision == STAR_PREC_F32)
     return star_f32_forward(lay, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, raw_alpha,
                             raw_rgb, alpha_ray_stride, stash, (cudaStream_t)stream);
-  if (d->precision == STAR_PREC_BF16) {
+  if (d->precision == STAR_PREC_BF16 || d->precision == STAR_PREC_F16) {
     if (stash != nullptr) return STAR_E_UNSUPPORTED;
     TcLayout tl;
     rc = star_make_tc_layout(d, &tl);
     if (rc) return rc;
     return star_tc_forward(tl, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, raw_alpha, raw_rgb,
-                           alpha_ray_stride, (cudaStream_t)stream);
+                           alpha_ray_stride, d->precision == STAR_PREC_F16, (cudaStream_t)stream);
   }
   return STAR_E_UNSUPPORTED;
 }

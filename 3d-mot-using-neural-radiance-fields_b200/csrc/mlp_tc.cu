@@ -17,6 +17,7 @@
 // producing A K-block by K-block) overlaps the MMA of layer L+1 (writing the other region, consuming A
 // K-block by K-block through the a_ready[] barriers).
 #include "star_common.cuh"
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 #include "mlp_tc_layout.h"
 
@@ -122,18 +123,20 @@ __device__ __forceinline__ void encode_half(int half, const float (&p)[3], const
 }
 
 // write 32 fp32 values as bf16 into 16-byte chunks ch0..ch0+3 of row `row` of a SW128 K-block
-__device__ __forceinline__ void store_row32_bf16(uint32_t kblock_saddr, int row, int ch0, const float (&v)[32]) {
+template <bool FP16>
+__device__ __forceinline__ void store_row32(uint32_t kblock_saddr, int row, int ch0, const float (&v)[32]) {
   const uint32_t rbase = kblock_saddr + (uint32_t)row * 128u;
   const uint32_t x = (uint32_t)row & 7u;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const uint32_t a = rbase + ((((uint32_t)(ch0 + c)) ^ x) << 4);
-    st_shared_v4(a, pack_bf16x2(v[8 * c + 0], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
-                 pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+    st_shared_v4(a, pack_16x2<FP16>(v[8 * c + 0], v[8 * c + 1]), pack_16x2<FP16>(v[8 * c + 2], v[8 * c + 3]),
+                 pack_16x2<FP16>(v[8 * c + 4], v[8 * c + 5]), pack_16x2<FP16>(v[8 * c + 6], v[8 * c + 7]));
   }
 }
 
 // ============================================================================================ forward
+template <bool FP16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const float* __restrict__ pts,
                   const float* __restrict__ viewdirs, const float* __restrict__ pose12,
@@ -196,7 +199,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         for (int l = 0; l < lay.n_layers; ++l) {
           const TcLayer& L = lay.L[l];
           const uint32_t d_tmem = tmem_base + (L.region ? 256u : 0u);
-          const uint32_t idesc = umma_idesc_bf16(TC_M, L.N);
+          const uint32_t idesc = umma_idesc_16(TC_M, L.N, FP16 ? 0 : 1);
           for (int kb = 0; kb < L.nkb; ++kb) {
             const int idx = (L.kind == LK_VIEWS && kb == 4) ? 4 : kb;
             mbar_wait(bar(BAR_A_READY(idx)), (a_par >> idx) & 1u, dbg, 2);
@@ -247,8 +250,8 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         }
         float e[32], ed[32];
         encode_half(half, p, dv, sc_xyz, sc_dir, e, ed);
-        store_row32_bf16(sA, row, half * 4, e);
-        if (half == 1) store_row32_bf16(sAD, row, 0, ed);
+        store_row32<FP16>(sA, row, half * 4, e);
+        if (half == 1) store_row32<FP16>(sAD, row, 0, ed);
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(bar(BAR_A_READY(0)));
@@ -297,7 +300,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
               h2 = fmaf(v[j], rw[2 * STAR_WV + j], h2);
             }
           } else {
-            store_row32_bf16(sA + (uint32_t)kb * TC_KB_BYTES, row, half * 4, v);
+            store_row32<FP16>(sA + (uint32_t)kb * TC_KB_BYTES, row, half * 4, v);
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(bar(BAR_A_READY(kb)));
@@ -361,7 +364,7 @@ __global__ void pack_tc_small_kernel(TcLayout tl, MlpLayout ml, const float* __r
 }
 
 __global__ void pack_tc_stream_kernel(TcLayout tl, MlpLayout ml, const float* __restrict__ master,
-                                      __nv_bfloat16* __restrict__ stream) {
+                                      uint16_t* __restrict__ stream, int fp16) {
   const uint32_t n_elems = tl.stream_bytes / 2;
   for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_elems; e += gridDim.x * blockDim.x) {
     const uint32_t byte = e * 2;
@@ -384,25 +387,26 @@ __global__ void pack_tc_stream_kernel(TcLayout tl, MlpLayout ml, const float* __
       const int k = kb * 64 + kk;
       if (k < K) v = master[ml.L[l].m_w + (int64_t)n * K + k];
     }
-    stream[e] = __float2bfloat16_rn(v);
+    stream[e] = fp16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
   }
 }
 
 // ============================================================================================ host side
 size_t star_tc_packed_bytes(const TcLayout& tl) { return (size_t)tl.small_bytes + tl.stream_bytes; }
 
-int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, void* packed, cudaStream_t st) {
+int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, void* packed, int fp16,
+                 cudaStream_t st) {
   pack_tc_small_kernel<<<8, 256, 0, st>>>(tl, ml, master, (float*)packed);
   int rc = star_check_launch();
   if (rc) return rc;
-  pack_tc_stream_kernel<<<148 * 4, 256, 0, st>>>(tl, ml, master,
-                                                 (__nv_bfloat16*)((uint8_t*)packed + tl.small_bytes));
+  pack_tc_stream_kernel<<<148 * 4, 256, 0, st>>>(tl, ml, master, (uint16_t*)((uint8_t*)packed + tl.small_bytes),
+                                                 fp16);
   return star_check_launch();
 }
 
 int star_tc_forward(const TcLayout& tl, const void* packed, const float* pts, const float* viewdirs,
                     const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
-                    float* raw_rgb, int64_t ray_stride, cudaStream_t st) {
+                    float* raw_rgb, int64_t ray_stride, int fp16, cudaStream_t st) {
   const int64_t M = (int64_t)R * S;
   const int64_t ntiles = (M + TC_M - 1) / TC_M;
   int dev = 0, sms = 148;
@@ -411,9 +415,10 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const float* pts, co
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   const TcSmem sl = tc_smem_layout(tl.small_bytes);
   if (((uintptr_t)packed & 15) != 0) return STAR_E_ALIGN;
-  cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
+  auto kern = fp16 ? mlp_fwd_tc_kernel<true> : mlp_fwd_tc_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
   if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
-  mlp_fwd_tc_kernel<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz,
-                                                         sc_dir, S, M, raw_alpha, raw_rgb, ray_stride, nullptr);
+  kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
+                                            raw_alpha, raw_rgb, ray_stride, nullptr);
   return star_check_launch();
 }

@@ -124,9 +124,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                    // layout type SWIZZLE_128B  [61,64)
   return d;
 }
-// instruction descriptor for kind::f16: A = B = bf16 (K-major), D = fp32, shape M x N
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// instruction descriptor for kind::f16: A and B both bf16 (fmt = 1) or both fp16 (fmt = 0), K-major,
+// D = fp32, shape M x N
+__host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, int fmt) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 
 // byte offset of element (row, k) inside one [rows][64] bf16 SW128 K-block
@@ -134,9 +136,12 @@ __host__ __device__ __forceinline__ uint32_t sw128_off(int row, int k) {
   return (uint32_t)row * 128u + ((((uint32_t)k >> 3) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)k & 7u) * 2u;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+// two fp32 -> packed 16-bit pair (lo in the low half); FP16 selects IEEE half instead of bfloat16
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  if (FP16) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {

@@ -15,8 +15,8 @@ from .resnet import ResnetFC
 
 
 def default_precision():
-    """'fp32' (1e-4 tier, CUDA cores) or 'bf16' (tcgen05 tensor cores, 2e-3 tier)."""
-    return {"fp32": _capi.PREC_F32, "bf16": _capi.PREC_BF16}[os.environ.get("STAR_B200_PRECISION", "fp32")]
+    """'fp32' (1e-4 tier, CUDA cores), 'bf16' or 'fp16' (tcgen05 tensor cores, bf16 / fp16 operands)."""
+    return _capi.PRECISIONS[os.environ.get("STAR_B200_PRECISION", "fp32")]
 
 
 class NeRF(nn.Module):

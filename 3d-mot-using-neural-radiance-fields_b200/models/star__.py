@@ -30,9 +30,9 @@ class STaR(nn.Module):
                 + list(self.dynamic_coarse_nerfs.parameters()) + list(self.dynamic_fine_nerfs.parameters()))
 
     def set_precision(self, precision):
-        """'fp32' | 'bf16' for every field MLP."""
+        """'fp32' | 'bf16' | 'fp16' for every field MLP."""
         from .. import _capi
-        p = {"fp32": _capi.PREC_F32, "bf16": _capi.PREC_BF16}[precision]
+        p = _capi.PRECISIONS[precision]
         for m in self.modules():
             if isinstance(m, NeRF):
                 m.precision = p

@@ -36,8 +36,12 @@ enum {
   STAR_E_CUDA = 6          /* a CUDA runtime call / launch failed (see star_last_cuda_error) */
 };
 
-/* precision tiers of the MLP (north star: 1e-4 abs for fp32, 2e-3 abs for the bf16 MLP) */
-enum { STAR_PREC_F32 = 0, STAR_PREC_BF16 = 1 };
+/* precision tiers of the MLP (north star: 1e-4 abs for fp32, 2e-3 abs for the bf16 MLP).
+ *   F32  : CUDA-core fp32 kernels (forward, backward).
+ *   BF16 : tcgen05 tensor cores, bf16 operands, fp32 accumulation in TMEM (forward).
+ *   F16  : same kernel with IEEE fp16 operands: same speed, 8x finer operand rounding (2^-12 vs 2^-9);
+ *          for networks whose activations stay below 65504. */
+enum { STAR_PREC_F32 = 0, STAR_PREC_BF16 = 1, STAR_PREC_F16 = 2 };
 
 /* One NeRF radiance MLP (models/nerf.py:34-110, models/resnet.py:62-110).  W is fixed at 256,
  * the view branch at 128 (all 15 reference configs agree). */

@@ -91,11 +91,24 @@ def n_blocks_of(params: Dict[str, torch.Tensor], prefix: str) -> int:
     return n
 
 
-def nerf_mlp(params, prefix, pts, viewdirs, L_xyz=10, L_dir=4, step=None, end_barf=-1):
+def nerf_mlp(params, prefix, pts, viewdirs, L_xyz=10, L_dir=4, step=None, end_barf=-1, emulate_bf16=False):
     """models/nerf.py:112-179 + models/resnet.py:51-59,103-110.  Returns RAW (raw_alpha [R,S],
-    raw_rgb [R,S,3]) -- the only mode STaR uses (z_vals is None, nerf.py:178)."""
+    raw_rgb [R,S,3]) -- the only mode STaR uses (z_vals is None, nerf.py:178).
+    emulate_bf16: model of the tensor-core tier -- every GEMM operand (weights, and the activations /
+    encodings fed to a GEMM) rounded to bf16, fp32 accumulation, fp32 biases, fp32 residual stream,
+    the two heads (alpha_linear, rgb_linear) in fp32 on un-rounded activations."""
+    GEMMS = ("pts_net", "feature_linear", "views_linears")
+
+    def q(t):   # emulate_bf16: False | True / "bf16" | "fp16" (the fp16-operand variant of the same kernel)
+        if not emulate_bf16:
+            return t
+        return t.half().to(t.dtype) if emulate_bf16 == "fp16" else t.bfloat16().to(t.dtype)
+
     def lin(name, h):
-        return F.linear(h, params[f"{prefix}{name}.weight"], params[f"{prefix}{name}.bias"])
+        w, b = params[f"{prefix}{name}.weight"], params[f"{prefix}{name}.bias"]
+        if emulate_bf16 and name.startswith(GEMMS):
+            return F.linear(q(h), q(w), b)
+        return F.linear(h, w, b)
 
     R, S = pts.shape[0], pts.shape[1]
     p = pts.reshape(-1, 3)
@@ -351,7 +364,7 @@ class StarConfig:
     """The fields of `args` the path reads (star__.py:28-53, nerf.py:41-101)."""
 
     def __init__(self, num_vehicles=0, N_importance=128, chunk=8192, far_dist=1e10, white_bkgd=False,
-                 raw_noise_std=0.0, multires=10, multires_views=4, end_barf=-1):
+                 raw_noise_std=0.0, multires=10, multires_views=4, end_barf=-1, emulate_bf16=False):
         self.num_vehicles = num_vehicles
         self.N_importance = N_importance
         self.chunk = chunk
@@ -361,6 +374,7 @@ class StarConfig:
         self.multires = multires
         self.multires_views = multires_views
         self.end_barf = end_barf
+        self.emulate_bf16 = emulate_bf16       # model of the bf16 tensor-core MLP tier (see nerf_mlp)
 
 
 def _star_chunk(params, cfg, pts, viewdirs, z_vals, rays_d, pose, is_coarse, step, training):
@@ -370,7 +384,8 @@ def _star_chunk(params, cfg, pts, viewdirs, z_vals, rays_d, pose, is_coarse, ste
         raise ValueError("N_importance should be positive")
     V = cfg.num_vehicles
     R, S = pts.shape[0], pts.shape[1]
-    kw = dict(L_xyz=cfg.multires, L_dir=cfg.multires_views, end_barf=cfg.end_barf)
+    kw = dict(L_xyz=cfg.multires, L_dir=cfg.multires_views, end_barf=cfg.end_barf,
+              emulate_bf16=getattr(cfg, "emulate_bf16", False))
     ra_s, rc_s = nerf_mlp(params, f"static_{tag}_nerf.", pts, viewdirs, step=None, **kw)   # :144
     if pose is None:
         return raw2outputs(ra_s, rc_s, z_vals, rays_d, cfg.raw_noise_std if training else 0,
@@ -455,7 +470,8 @@ def render_star(params, cfg, pts, viewdirs, z_vals, rays_o, rays_d, N_importance
 def render_nerf(params, prefix_coarse, prefix_fine, cfg, pts, viewdirs, z_vals, rays_o, rays_d,
                 N_importance, far_dist, training=False, u=None, exact_sum=False, z_samples=None):
     """models/rendering__.py:187-245 (two bare NeRF modules)."""
-    kw = dict(L_xyz=cfg.multires, L_dir=cfg.multires_views, end_barf=cfg.end_barf)
+    kw = dict(L_xyz=cfg.multires, L_dir=cfg.multires_views, end_barf=cfg.end_barf,
+              emulate_bf16=getattr(cfg, "emulate_bf16", False))
     std = cfg.raw_noise_std if training else 0
     a, c = nerf_mlp(params, prefix_coarse, pts, viewdirs, **kw)
     coarse = raw2outputs(a, c, z_vals, rays_d, std, cfg.white_bkgd, far_dist)
