@@ -2,14 +2,14 @@
 // for sm_100a: pose transform (star__.py:160-199) -> positional encoding (embedder.py:81-112) ->
 // ResNet-FC trunk -> heads as ONE persistent, warp-specialised kernel per launch.
 //
-// One CTA per SM walks tiles of 128 samples.  Roles (320 threads):
-//   warps 0-7  "epilogue" warps: encode the tile's inputs to bf16 into the shared-memory A operand, and after
+// One CTA per SM walks tiles of 128 samples.  Roles (576 threads):
+//   warps 0-15 "epilogue" warps: encode the tile's inputs to bf16 into the shared-memory A operand, and after
 //              every layer move the fp32 accumulator TMEM -> registers, add bias / ReLU, convert to bf16 and
-//              write the next layer's A operand (warp w owns TMEM lanes 32*(w%4).., column half w/4);
-//              alpha / rgb heads are fp32 dot products in these registers.
-//   warp 8     weight producer: streams the pre-swizzled bf16 weight K-blocks (32 KB each) from L2 into a
+//              write the next layer's A operand (warp w owns TMEM lanes 32*(w%4).., 16 of every 64 columns:
+//              group w/4); alpha / rgb heads are fp32 dot products in these registers.
+//   warp 16    weight producer: streams the pre-swizzled bf16 weight K-blocks (32 KB each) from L2 into a
 //              4-stage shared-memory ring with 1-D bulk async copies (TMA engine) + mbarrier transaction counts.
-//   warp 9     MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16, bf16 -> fp32 in TMEM).
+//   warp 17    MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16, bf16 -> fp32 in TMEM).
 //
 // TMEM (512 columns): X = columns 0..255 holds the residual stream x (fp32, biases kept separately),
 // T = columns 256..511 holds the other accumulator.  fc_1 ACCUMULATES onto X, which performs the residual
@@ -18,6 +18,8 @@
 // K-block by K-block through the a_ready[] barriers).
 #include "star_common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
+#include <stdio.h>
 #include "tc_common.cuh"
 #include "mlp_tc_layout.h"
 
@@ -25,10 +27,11 @@
 #define TC_NS 4
 #define TC_STAGE_BYTES 32768
 #define TC_KB_BYTES 16384          // one A K-block: 128 rows x 128 B
-#define TC_EPI_WARPS 8
+#define TC_EPI_WARPS 16            // 4 per TMEM lane quadrant: each thread owns 1 row x 16 of the 64 columns of a K-block
 #define TC_EPI_THREADS (32 * TC_EPI_WARPS)
 #define TC_THREADS (TC_EPI_THREADS + 64)
 #define TC_TMEM_COLS 512
+#define TC_CPT 16                  // columns per thread per K-block
 
 struct TcSmem {
   uint32_t A, AD, W, small, part, bars, tmem_ptr;   // byte offsets from the 1024-aligned base
@@ -41,7 +44,7 @@ __host__ __device__ static inline TcSmem tc_smem_layout(uint32_t small_bytes) {
   s.AD = o; o += TC_KB_BYTES;
   s.W = o; o += TC_NS * TC_STAGE_BYTES;
   s.small = o; o += small_bytes;
-  s.part = o; o += TC_M * 4 * 4;
+  s.part = s.AD;    // head partial sums live in the never-read half (columns 32..63) of the dirs block
   s.bars = o; o += 16 * 8;
   s.tmem_ptr = o; o += 16;
   s.total = o + 1024;   // slack for aligning the dynamic smem base
@@ -55,83 +58,114 @@ __host__ __device__ static inline TcSmem tc_smem_layout(uint32_t small_bytes) {
 #define BAR_ACC_FULL (2 * TC_NS + 5)
 
 // ---------------------------------------------------------------------------------------------- encode
-// Positional encoding of one sample into 32 of the 64 (xyz) columns, plus the 27(+5 zero) dir columns.
-// sin/cos of the higher octaves come from the double-angle recurrence (error doubles per octave from
-// ~6e-8; 3e-5 after nine -- far below bf16 resolution).
-__device__ __forceinline__ void encode_half(int half, const float (&p)[3], const float (&dv)[3],
-                                            const float* __restrict__ sc_xyz, const float* __restrict__ sc_dir,
-                                            float (&e)[32], float (&ed)[32]) {
-  float sn[3], cs[3];
+// 16 consecutive columns [C0, C0+16) of the positional encoding [x, sin(2^k x), cos(2^k x)]_k (embedder.py:90-97;
+// NV = 3 + 6 L valid columns, zero beyond).  The lowest octave of the slice comes from sincosf, the following
+// ones from the double-angle recurrence (error doubles per octave from ~6e-8: < 1e-6 here, far below the
+// 16-bit operand resolution).  Everything is resolved at compile time after unrolling.
+template <int C0, int NV>
+__device__ __forceinline__ void encode_slice(const float (&p)[3], const float* __restrict__ sc, float (&e)[16]) {
+  constexpr int LAST = (C0 + 15 < NV) ? C0 + 15 : NV - 1;
+  constexpr int K_LO = (C0 < 3) ? 0 : (C0 - 3) / 6;
+  constexpr int K_HI = (LAST < 3) ? -1 : (LAST - 3) / 6;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) { e[j] = 0.f; ed[j] = 0.f; }
-  if (half == 0) {
+  for (int j = 0; j < 16; ++j) e[j] = (C0 + j < 3) ? p[(C0 + j) % 3] : 0.f;
+  if (K_HI >= K_LO) {
+    float sn[3], cs[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { e[c] = p[c]; sincosf(p[c], &sn[c], &cs[c]); }
+    for (int c = 0; c < 3; ++c) sincosf(p[c] * (float)(1 << K_LO), &sn[c], &cs[c]);
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
+    for (int k = K_LO; k <= K_HI; ++k) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int j = 3 + 6 * k + c;
-        if (j < 32) e[j] = sn[c];
-        if (j + 3 < 32) e[j + 3] = cs[c];
-        const float s2 = 2.f * sn[c] * cs[c], c2 = 1.f - 2.f * sn[c] * sn[c];
-        sn[c] = s2; cs[c] = c2;
+      for (int j = 0; j < 16; ++j) {
+        const int col = C0 + j;
+        if (col >= 3 && col < NV && (col - 3) / 6 == k) {
+          const int w = (col - 3) % 6;
+          e[j] = (w < 3) ? sn[w % 3] : cs[w % 3];
+        }
+      }
+      if (k < K_HI) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float s2 = 2.f * sn[c] * cs[c], c2 = 1.f - 2.f * sn[c] * sn[c];
+          sn[c] = s2; cs[c] = c2;
+        }
       }
     }
-    if (sc_xyz != nullptr) {
+  }
+  if (sc != nullptr) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) e[j] *= sc_xyz[j];
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) sincosf(16.f * p[c], &sn[c], &cs[c]);   // octave k = 4
-    e[0] = cs[2];                                                      // column 32 = cos(2^4 z)
-#pragma unroll
-    for (int k = 5; k < 10; ++k) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float s2 = 2.f * sn[c] * cs[c], c2 = 1.f - 2.f * sn[c] * sn[c];
-        sn[c] = s2; cs[c] = c2;
-        const int j = 3 + 6 * k + c - 32;
-        e[j] = sn[c];
-        e[j + 3] = cs[c];
-      }
-    }
-    if (sc_xyz != nullptr) {
-#pragma unroll
-      for (int j = 0; j < 31; ++j) e[j] *= sc_xyz[32 + j];
-    }
-    // encoded view direction (27 values)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { ed[c] = dv[c]; sincosf(dv[c], &sn[c], &cs[c]); }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int j = 3 + 6 * k + c;
-        ed[j] = sn[c];
-        ed[j + 3] = cs[c];
-        const float s2 = 2.f * sn[c] * cs[c], c2 = 1.f - 2.f * sn[c] * sn[c];
-        sn[c] = s2; cs[c] = c2;
-      }
-    }
-    if (sc_dir != nullptr) {
-#pragma unroll
-      for (int j = 0; j < 27; ++j) ed[j] *= sc_dir[j];
-    }
+    for (int j = 0; j < 16; ++j) e[j] *= sc[C0 + j];
   }
 }
 
-// write 32 fp32 values as bf16 into 16-byte chunks ch0..ch0+3 of row `row` of a SW128 K-block
-template <bool FP16>
-__device__ __forceinline__ void store_row32(uint32_t kblock_saddr, int row, int ch0, const float (&v)[32]) {
+// write 16 fp32 values as 16-bit operands into 16-byte chunks ch0, ch0+1 of row `row` of a SW128 K-block
+template <bool FP16, bool RELU>
+__device__ __forceinline__ void store_row16(uint32_t kblock_saddr, int row, int ch0, const float (&v)[16]) {
   const uint32_t rbase = kblock_saddr + (uint32_t)row * 128u;
   const uint32_t x = (uint32_t)row & 7u;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
     const uint32_t a = rbase + ((((uint32_t)(ch0 + c)) ^ x) << 4);
-    st_shared_v4(a, pack_16x2<FP16>(v[8 * c + 0], v[8 * c + 1]), pack_16x2<FP16>(v[8 * c + 2], v[8 * c + 3]),
-                 pack_16x2<FP16>(v[8 * c + 4], v[8 * c + 5]), pack_16x2<FP16>(v[8 * c + 6], v[8 * c + 7]));
+    st_shared_v4(a, pack_16x2<FP16, RELU>(v[8 * c + 0], v[8 * c + 1]), pack_16x2<FP16, RELU>(v[8 * c + 2], v[8 * c + 3]),
+                 pack_16x2<FP16, RELU>(v[8 * c + 4], v[8 * c + 5]), pack_16x2<FP16, RELU>(v[8 * c + 6], v[8 * c + 7]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- epilogue
+struct EpiCtx {
+  uint32_t sA, a_ready0;       // smem address of A K-block 0, of barrier a_ready[0]
+  uint32_t tcol;               // TMEM address: lane base of this warp | accumulator region | 16 * column group
+  const float* bias;           // smem, epilogue bias vector of this layer
+  const float* head_w;         // smem, alpha_linear / rgb_linear weights (OUT / VIEWS layers)
+  int row, cg, lane;
+};
+
+// One layer's accumulator -> next layer's A operand for this thread's row: per K-block kb, columns
+// [64 kb + 16 cg, +16): TMEM -> registers (double buffered) -> + bias -> (ReLU fused into the 16-bit
+// conversion) -> swizzled smem -> proxy fence -> one mbarrier arrival per warp.
+// KIND: LK_IN / LK_FC0 / LK_FC1 (ReLU), LK_OUT (affine + alpha head partial in h[0]), LK_FEAT (affine),
+// LK_VIEWS (ReLU, N = 128, rgb head partials in h[0..2], no A output).
+template <int KIND, bool FP16>
+__device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3]) {
+  constexpr int NCH = (KIND == LK_VIEWS) ? 2 : 4;
+  constexpr bool RELU = (KIND == LK_IN || KIND == LK_FC0 || KIND == LK_FC1);
+  uint32_t r[2][TC_CPT];
+  tmem_ld16(c.tcol, r[0]);
+#pragma unroll
+  for (int kb = 0; kb < NCH; ++kb) {
+    tmem_wait_ld();
+    if (kb + 1 < NCH) tmem_ld16(c.tcol + 64u * (uint32_t)(kb + 1), r[(kb + 1) & 1]);
+    const int col0 = kb * 64 + c.cg * TC_CPT;
+    float v[TC_CPT];
+#pragma unroll
+    for (int j4 = 0; j4 < TC_CPT / 4; ++j4) {
+      const float4 b = *reinterpret_cast<const float4*>(c.bias + col0 + 4 * j4);
+      v[4 * j4 + 0] = __uint_as_float(r[kb & 1][4 * j4 + 0]);
+      v[4 * j4 + 1] = __uint_as_float(r[kb & 1][4 * j4 + 1]);
+      v[4 * j4 + 2] = __uint_as_float(r[kb & 1][4 * j4 + 2]);
+      v[4 * j4 + 3] = __uint_as_float(r[kb & 1][4 * j4 + 3]);
+      add_f32x2(v[4 * j4 + 0], v[4 * j4 + 1], b.x, b.y);
+      add_f32x2(v[4 * j4 + 2], v[4 * j4 + 3], b.z, b.w);
+    }
+    if (KIND == LK_OUT) {            // alpha head (nerf.py:151) on the fp32 h
+#pragma unroll
+      for (int j = 0; j < TC_CPT; ++j) h[0] = fmaf(v[j], c.head_w[col0 + j], h[0]);
+    }
+    if (KIND == LK_VIEWS) {          // rgb head (nerf.py:159) on the rectified fp32 h2
+#pragma unroll
+      for (int j = 0; j < TC_CPT; ++j) {
+        const float x = fmaxf(v[j], 0.f);
+        h[0] = fmaf(x, c.head_w[col0 + j], h[0]);
+        h[1] = fmaf(x, c.head_w[STAR_WV + col0 + j], h[1]);
+        h[2] = fmaf(x, c.head_w[2 * STAR_WV + col0 + j], h[2]);
+      }
+    } else {
+      store_row16<FP16, RELU>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v);
+      fence_proxy_async_smem();      // this thread's A writes -> async proxy (tcgen05.mma operand reads)
+      tc_fence_before();
+      __syncwarp();
+      if (c.lane == 0) mbar_arrive(c.a_ready0 + 8u * (uint32_t)kb);
+    }
   }
 }
 
@@ -141,7 +175,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const float* __restrict__ pts,
                   const float* __restrict__ viewdirs, const float* __restrict__ pose12,
                   const float* __restrict__ sc_xyz, const float* __restrict__ sc_dir, int S, int64_t M,
-                  float* __restrict__ raw_alpha, float* __restrict__ raw_rgb, int64_t ray_stride, int* dbg) {
+                  float* __restrict__ raw_alpha, float* __restrict__ raw_rgb, int64_t ray_stride, int* dbg,
+                  int dbg_mode) {
+  // dbg_mode (bottleneck experiments only; results are garbage): bit 0 = epilogue skips TMEM load / math /
+  // A store, bit 1 = no weight streaming (MMA reads whatever is in the ring), bit 2 = MMA issuer skips the MMAs
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -149,17 +186,22 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
   const TcSmem sl = tc_smem_layout(lay.small_bytes);
   const uint32_t sA = base + sl.A, sAD = base + sl.AD, sW = base + sl.W, sBars = base + sl.bars;
   float* s_small = reinterpret_cast<float*>(gbase + sl.small);
-  float* s_part = reinterpret_cast<float*>(gbase + sl.part);
+  // partial head sums of column group g (1..3) of a row: 4 floats in 16-byte chunk (3 + g) of the row of the
+  // dirs block (logical columns 32..63, which the MMA never reads: only 2 of its 4 K-steps are issued)
+  auto part = [&](int r, int g) -> float* {
+    return reinterpret_cast<float*>(gbase + sl.part + (uint32_t)r * 128u + ((((uint32_t)(3 + g)) ^ ((uint32_t)r & 7u)) << 4));
+  };
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(gbase + sl.tmem_ptr);
   auto bar = [&](int i) -> uint32_t { return sBars + 8u * (uint32_t)i; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (M + TC_M - 1) / TC_M;
+  const long long t_start = clock64();
 
   // ---- one-time setup
   if (warp == TC_EPI_WARPS && lane == 0) {
     for (int i = 0; i < TC_NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), 1); mbar_init(bar(BAR_W_EMPTY(i)), 1); }
-    for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A_READY(i)), TC_EPI_THREADS);
+    for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A_READY(i)), TC_EPI_WARPS);
     mbar_init(bar(BAR_ACC_FULL), 1);
     fence_mbar_init();
   }
@@ -183,9 +225,13 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           const uint32_t bytes = (uint32_t)lay.L[l].N * 128u;
           for (int kb = 0; kb < lay.L[l].nkb; ++kb) {
             mbar_wait(bar(BAR_W_EMPTY(stage)), phase ^ 1u, dbg, 1);
-            mbar_arrive_expect_tx(bar(BAR_W_FULL(stage)), bytes);
-            bulk_g2s(sW + stage * TC_STAGE_BYTES, wstream + lay.L[l].w_off + (uint32_t)kb * bytes, bytes,
-                     bar(BAR_W_FULL(stage)));
+            if (dbg_mode & 2) {
+              mbar_arrive(bar(BAR_W_FULL(stage)));
+            } else {
+              mbar_arrive_expect_tx(bar(BAR_W_FULL(stage)), bytes);
+              bulk_g2s(sW + stage * TC_STAGE_BYTES, wstream + lay.L[l].w_off + (uint32_t)kb * bytes, bytes,
+                       bar(BAR_W_FULL(stage)));
+            }
             if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
           }
         }
@@ -209,7 +255,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             const uint32_t a_addr = (idx == 4) ? sAD : sA + (uint32_t)kb * TC_KB_BYTES;
             const uint32_t b_addr = sW + stage * TC_STAGE_BYTES;
             const int nk = (idx == 4) ? 2 : 4;
-            for (int k = 0; k < nk; ++k)
+            for (int k = 0; k < nk && !(dbg_mode & 4); ++k)
               tc_mma_bf16(d_tmem, umma_desc_sw128(a_addr + 32u * k), umma_desc_sw128(b_addr + 32u * k), idesc,
                           (L.kind == LK_FC1 || kb > 0 || k > 0) ? 1u : 0u);
             tc_commit(bar(BAR_W_EMPTY(stage)));
@@ -221,15 +267,17 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     }
   } else {
     // ======================================================================== epilogue warps
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, cg = warp >> 2;
     const int row = q * 32 + lane;
-    const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
     uint32_t acc_par = 0;
+    EpiCtx ctx;
+    ctx.sA = sA; ctx.a_ready0 = bar(BAR_A_READY(0));
+    ctx.row = row; ctx.cg = cg; ctx.lane = lane;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t gi = tile * TC_M + row;
       const bool valid = gi < M;
       int64_t out_idx = 0;
-      // ---- inputs: pose transform + encoding -> A K-block 0 (xyz) and the dirs block
+      // ---- inputs: pose transform + encoding -> A K-block 0 (xyz, 4 threads per row) and the dirs block
       {
         float p[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 0.f};
         if (valid) {
@@ -248,14 +296,21 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             dv[0] = dx; dv[1] = dy; dv[2] = dz;
           }
         }
-        float e[32], ed[32];
-        encode_half(half, p, dv, sc_xyz, sc_dir, e, ed);
-        store_row32<FP16>(sA, row, half * 4, e);
-        if (half == 1) store_row32<FP16>(sAD, row, 0, ed);
+        float e[16];
+        if (cg == 0) encode_slice<0, 63>(p, sc_xyz, e);
+        else if (cg == 1) encode_slice<16, 63>(p, sc_xyz, e);
+        else if (cg == 2) encode_slice<32, 63>(p, sc_xyz, e);
+        else encode_slice<48, 63>(p, sc_xyz, e);
+        store_row16<FP16, false>(sA, row, cg * 2, e);
+        if (cg == 1) { encode_slice<0, 27>(dv, sc_dir, e); store_row16<FP16, false>(sAD, row, 0, e); }
+        if (cg == 2) { encode_slice<16, 27>(dv, sc_dir, e); store_row16<FP16, false>(sAD, row, 2, e); }
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(bar(BAR_A_READY(0)));
-        mbar_arrive(bar(BAR_A_READY(4)));
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar(BAR_A_READY(0)));
+          mbar_arrive(bar(BAR_A_READY(4)));
+        }
       }
       // ---- layers
       for (int l = 0; l < lay.n_layers; ++l) {
@@ -263,62 +318,41 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         mbar_wait(bar(BAR_ACC_FULL), acc_par, dbg, 4);
         acc_par ^= 1u;
         tc_fence_after();
-        const uint32_t tbase = tmem_base + lane_addr + (L.region ? 256u : 0u);
-        const float* bias = s_small + L.bias_off;
-        const int nch = L.N >> 6;
-        const bool relu = (L.kind == LK_IN || L.kind == LK_FC0 || L.kind == LK_FC1 || L.kind == LK_VIEWS);
-        float h0 = 0.f, h1 = 0.f, h2 = 0.f;
-        for (int kb = 0; kb < nch; ++kb) {
-          const int col0 = kb * 64 + half * 32;
-          uint32_t r[32];
-          tmem_ld32(tbase + (uint32_t)col0, r);
-          tmem_wait_ld();
-          float v[32];
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = *reinterpret_cast<const float4*>(bias + col0 + 4 * j4);
-            v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + b.x;
-            v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + b.y;
-            v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + b.z;
-            v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + b.w;
+        ctx.tcol = tmem_base + (((uint32_t)(q * 32)) << 16) + (L.region ? 256u : 0u) + (uint32_t)(cg * TC_CPT);
+        ctx.bias = s_small + L.bias_off;
+        float h[3] = {0.f, 0.f, 0.f};
+        if (dbg_mode & 1) {
+          for (int kb = 0; kb < (L.N >> 6) && L.kind != LK_VIEWS; ++kb) {
+            fence_proxy_async_smem(); tc_fence_before(); __syncwarp();
+            if (lane == 0) mbar_arrive(bar(BAR_A_READY(kb)));
           }
-          if (relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (L.kind == LK_OUT) {          // alpha head (nerf.py:151) on the fp32 h
-            const float* aw = s_small + lay.off_alpha_w + col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) h0 = fmaf(v[j], aw[j], h0);
-          }
-          if (L.kind == LK_VIEWS) {        // rgb head (nerf.py:159) on the fp32 h2
-            const float* rw = s_small + lay.off_rgb_w + col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              h0 = fmaf(v[j], rw[j], h0);
-              h1 = fmaf(v[j], rw[STAR_WV + j], h1);
-              h2 = fmaf(v[j], rw[2 * STAR_WV + j], h2);
-            }
-          } else {
-            store_row32<FP16>(sA + (uint32_t)kb * TC_KB_BYTES, row, half * 4, v);
-            fence_proxy_async_smem();
-            tc_fence_before();
-            mbar_arrive(bar(BAR_A_READY(kb)));
-          }
-        }
-        if (L.kind == LK_OUT) {
-          if (half == 1) s_part[row * 4 + 0] = h0;
+        } else if (L.kind == LK_FC0 || L.kind == LK_FC1 || L.kind == LK_IN) {
+          epilogue_layer<LK_FC0, FP16>(ctx, h);
+        } else if (L.kind == LK_FEAT) {
+          epilogue_layer<LK_FEAT, FP16>(ctx, h);
+        } else if (L.kind == LK_OUT) {
+          ctx.head_w = s_small + lay.off_alpha_w;
+          epilogue_layer<LK_OUT, FP16>(ctx, h);
+          // combine the 4 column groups of each row: groups 1..3 park their partial, group 0 finishes
+          if (cg != 0) part(row, cg)[0] = h[0];
           named_bar_sync(1, TC_EPI_THREADS);
-          if (half == 0 && valid) raw_alpha[out_idx] = h0 + s_part[row * 4 + 0] + s_small[lay.off_alpha_b];
-        } else if (L.kind == LK_VIEWS) {
-          if (half == 1) { s_part[row * 4 + 1] = h0; s_part[row * 4 + 2] = h1; s_part[row * 4 + 3] = h2; }
+          if (cg == 0 && valid)
+            raw_alpha[out_idx] = h[0] + part(row, 1)[0] + part(row, 2)[0] + part(row, 3)[0] + s_small[lay.off_alpha_b];
+        } else {   // LK_VIEWS
+          ctx.head_w = s_small + lay.off_rgb_w;
+          epilogue_layer<LK_VIEWS, FP16>(ctx, h);
+          if (cg != 0) {
+            float* d = part(row, cg);
+            d[1] = h[0]; d[2] = h[1]; d[3] = h[2];
+          }
           tc_fence_before();
           named_bar_sync(1, TC_EPI_THREADS);
-          if (half == 0 && valid) {
+          if (cg == 0 && valid) {
             float* o = raw_rgb + out_idx * 3;
-            o[0] = h0 + s_part[row * 4 + 1] + s_small[lay.off_rgb_b + 0];
-            o[1] = h1 + s_part[row * 4 + 2] + s_small[lay.off_rgb_b + 1];
-            o[2] = h2 + s_part[row * 4 + 3] + s_small[lay.off_rgb_b + 2];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+              o[ch] = h[ch] + part(row, 1)[1 + ch] + part(row, 2)[1 + ch] + part(row, 3)[1 + ch] +
+                      s_small[lay.off_rgb_b + ch];
           }
         }
       }
@@ -328,6 +362,9 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
   // ---- teardown
   tc_fence_before();
   __syncthreads();
+  if (dbg != nullptr && tid == 0 && blockIdx.x == 0) {   // debug only: cycles of CTA 0 (see star_tc_forward)
+    reinterpret_cast<long long*>(dbg)[1] = clock64() - t_start;
+  }
   if (warp == TC_EPI_WARPS + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TC_TMEM_COLS);
@@ -418,7 +455,23 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const float* pts, co
   auto kern = fp16 ? mlp_fwd_tc_kernel<true> : mlp_fwd_tc_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
   if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
+  static int dbg_mode = -1;
+  if (dbg_mode < 0) { const char* e2 = getenv("STAR_TC_DEBUG_MODE"); dbg_mode = e2 ? atoi(e2) : 0; }
+  // STAR_TC_DEBUG_CYCLES=1 (bottleneck experiments only): synchronous launch that prints the SM cycles CTA 0 spent
+  static int dbg_cycles = -1;
+  static long long* d_dbg = nullptr;
+  if (dbg_cycles < 0) {
+    dbg_cycles = getenv("STAR_TC_DEBUG_CYCLES") ? 1 : 0;
+    if (dbg_cycles) { cudaMalloc(&d_dbg, 64); cudaMemset(d_dbg, 0, 64); }
+  }
   kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
-                                            raw_alpha, raw_rgb, ray_stride, nullptr);
+                                            raw_alpha, raw_rgb, ray_stride, (int*)d_dbg, dbg_mode);
+  if (dbg_cycles) {
+    long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_dbg, 64, cudaMemcpyDeviceToHost);
+    const double t0 = (double)((ntiles + grid - 1) / grid);
+    fprintf(stderr, "[star_tc] mode %d: CTA0 %.0f cycles/tile\n", dbg_mode, h[1] / t0);
+  }
   return star_check_launch();
 }

@@ -1,0 +1,71 @@
+// Micro-benchmark: issue rate of tcgen05.mma (cta_group::1, kind::f16, M=128) from shared-memory operands.
+// One CTA per SM; one thread issues NITER MMAs on (garbage) smem operands, commits, and the cycle count is
+// reported.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_rate umma_rate.cu
+#include <cstdio>
+#include <cstdlib>
+#include "../3d-mot-using-neural-radiance-fields_b200/csrc/tc_common.cuh"
+
+template <int N>
+__global__ void __launch_bounds__(128, 1) rate_kernel(int niter, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint32_t tmem_ptr;
+  __shared__ uint64_t bar;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_ptr), 512);
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t t = tmem_ptr;
+  if (warp == 0 && lane == 0) {
+    const uint32_t idesc = umma_idesc_16(128, N, 1);
+    const uint32_t a = base, b = base + 16384;
+    long long t0 = clock64();
+    for (int i = 0; i < niter; ++i) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        tc_mma_bf16(t + ((i & 1) ? 256u : 0u), umma_desc_sw128(a + 32u * k), umma_desc_sw128(b + 32u * k), idesc, 1u);
+    }
+    tc_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0, nullptr, 0);
+    long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(t, 512); }
+}
+
+template <int N>
+void run(int grid, int niter, long long* d_out) {
+  cudaFuncSetAttribute(rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  rate_kernel<N><<<grid, 128, 64 * 1024>>>(niter, d_out);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long cyc = 0;
+  cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
+  printf("N=%3d grid=%3d: %lld cycles for %d MMAs (K=16) -> %.1f cycles/MMA, %.0f MAC/clk/SM  (%s)\n", N, grid, cyc,
+         niter * 4, (double)cyc / (niter * 4), 128.0 * N * 16 * niter * 4 / cyc, cudaGetErrorString(e));
+}
+
+int main() {
+  long long* d_out;
+  cudaMalloc(&d_out, 8);
+  for (int grid : {1, 148}) {
+    run<256>(grid, 2000, d_out);
+    run<128>(grid, 2000, d_out);
+    run<64>(grid, 2000, d_out);
+  }
+  // commit -> mbarrier latency: 0, 1, 2, 4 groups of 4 MMAs (N=256: 512 cycles per group) then commit + wait
+  for (int n : {0, 1, 2, 4, 8}) {
+    cudaFuncSetAttribute(rate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    rate_kernel<256><<<148, 128, 64 * 1024>>>(n, d_out);
+    cudaDeviceSynchronize();
+    long long cyc = 0;
+    cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
+    printf("latency: %d MMA groups (ideal %d cycles) + commit + wait = %lld cycles\n", n, n * 512, cyc);
+  }
+  return 0;
+}
