@@ -10,11 +10,11 @@ burakcuhadar/3D-MOT-using-Neural-Radiance-Fields behind the reference's own Pyth
 scripts pick them up unmodified."""
 import sys
 
-from . import _capi, functional  # noqa: F401
+from . import _capi, functional, parallel  # noqa: F401
 from .models import embedder, nerf, rendering__, resnet, star__, types__  # noqa: F401
 from .models.star__ import STaR  # noqa: F401
 
-__all__ = ["STaR", "functional", "install", "rendering__", "star__"]
+__all__ = ["STaR", "functional", "install", "parallel", "rendering__", "star__"]
 
 
 def install(package="models"):

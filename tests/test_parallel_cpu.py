@@ -1,0 +1,93 @@
+"""World-size-2 gloo tests (CPU) of the ray-sharding host logic (star_b200.parallel)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import star_b200  # noqa: F401  (registers the package)
+from star_b200 import parallel as P
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 7, 8, 640000, 4097):
+        for w in (1, 2, 3, 8):
+            b = [P.shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [e - s for s, e in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        # a "model": rgb = sigmoid(d . w) per ray; every rank holds the same weights and its slice of the rays
+        w = torch.nn.Parameter(torch.randn(3, 3))
+        pose = torch.nn.Parameter(torch.randn(2, 7))
+        unused = torch.nn.Parameter(torch.zeros(4))
+        g = torch.Generator().manual_seed(1)
+        rays_o, rays_d, target = torch.randn(10, 3, generator=g), torch.randn(10, 3, generator=g), torch.rand(10, 3, generator=g)
+
+        def render(ro, rd):
+            return {"rgb": torch.sigmoid(rd @ w + pose[:, :3].sum(0)), "depth": rd.norm(dim=-1), "acc": ro[:, 0]}
+
+        ro, rd, tg = P.shard_rays(rays_o, rays_d, target)
+        loss = ((render(ro, rd)["rgb"] - tg) ** 2).mean()
+        loss.backward()
+        P.allreduce_gradients([w, pose, unused])
+        tot = P.allreduce_scalars([loss])
+        with torch.no_grad():
+            full = P.render_sharded(render, rays_o, rays_d)
+        q.put((rank, w.grad.clone(), pose.grad.clone(), unused.grad.clone(), tot.clone(),
+               {k: v.clone() for k, v in full.items()}))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_matches_single_process():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process reference
+    torch.manual_seed(0)
+    w = torch.nn.Parameter(torch.randn(3, 3))
+    pose = torch.nn.Parameter(torch.randn(2, 7))
+    g = torch.Generator().manual_seed(1)
+    rays_o, rays_d, target = torch.randn(10, 3, generator=g), torch.randn(10, 3, generator=g), torch.rand(10, 3, generator=g)
+    rgb = torch.sigmoid(rays_d @ w + pose[:, :3].sum(0))
+    loss = ((rgb - target) ** 2).mean()        # equal shards (5 + 5): mean of rank means == global mean
+    loss.backward()
+    for rank, gw, gp, gu, tot, full in res:
+        assert torch.allclose(gw, w.grad, atol=1e-6) and torch.allclose(gp, pose.grad, atol=1e-6)
+        assert float(gu.abs().max()) == 0.0
+        assert abs(float(tot[0]) - float(loss)) < 1e-6
+        assert torch.allclose(full["rgb"], rgb.detach(), atol=1e-6)
+        assert torch.equal(full["depth"], rays_d.norm(dim=-1)) and torch.equal(full["acc"], rays_o[:, 0])
+    assert torch.equal(res[0][1], res[1][1])    # ranks agree bit for bit after the all-reduce
+
+
+def test_uneven_gather():
+    assert P.shard_bounds(7, 0, 2) == (0, 4) and P.shard_bounds(7, 1, 2) == (4, 7)
+    t = torch.arange(12.0).view(4, 3)
+    assert torch.equal(P.gather_rays(t, 4), t)   # world size 1: identity
