@@ -10,7 +10,13 @@ int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, v
                  cudaStream_t st);
 int star_tc_forward(const TcLayout& tl, const void* packed, const float* pts, const float* viewdirs,
                     const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
-                    float* raw_rgb, int64_t ray_stride, int fp16, cudaStream_t st);
+                    float* raw_rgb, int64_t ray_stride, void* stash, int fp16, cudaStream_t st);
+
+size_t star_tc_gstash_bytes(const TcLayout& tl, int64_t n_samples);
+int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed, const float* pts, const float* viewdirs,
+                     const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, const float* d_raw_alpha,
+                     const float* d_raw_rgb, int64_t ray_stride, const void* stash, void* gstash, float* grad_flat,
+                     float* pose_acc, int fp16, cudaStream_t st);
 
 int star_f32_pack(const MlpLayout& lay, const float* master, void* packed, cudaStream_t st);
 int star_f32_forward(const MlpLayout& lay, const void* packed, const float* pts, const float* viewdirs,
@@ -74,6 +80,11 @@ extern "C" size_t star_stash_bytes(const StarNetDesc* d, int64_t n_samples) {
   MlpLayout lay;
   if (!d || star_make_layout(d, &lay) || n_samples < 0) return 0;
   if (d->precision == STAR_PREC_F32) return sizeof(float) * (size_t)lay.stash_cols * (size_t)n_samples;
+  if (d->precision == STAR_PREC_BF16 || d->precision == STAR_PREC_F16) {
+    TcLayout tl;
+    if (star_make_tc_layout(d, &tl)) return 0;
+    return (size_t)((n_samples + 127) / 128) * (size_t)tl.stash_blocks * TC_BLOCK_BYTES;
+  }
   return 0;
 }
 
@@ -81,6 +92,11 @@ extern "C" size_t star_mlp_backward_workspace_bytes(const StarNetDesc* d, int64_
   MlpLayout lay;
   if (!d || star_make_layout(d, &lay) || n_samples < 0) return 0;
   if (d->precision == STAR_PREC_F32) return sizeof(float) * (size_t)lay.g_cols * (size_t)n_samples;
+  if (d->precision == STAR_PREC_BF16 || d->precision == STAR_PREC_F16) {
+    TcLayout tl;
+    if (star_make_tc_layout(d, &tl)) return 0;
+    return star_tc_gstash_bytes(tl, n_samples);
+  }
   return 0;
 }
 
@@ -98,12 +114,11 @@ extern "C" int star_mlp_forward(const StarNetDesc* d, const void* packed, const 
     return star_f32_forward(lay, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, raw_alpha,
                             raw_rgb, alpha_ray_stride, stash, (cudaStream_t)stream);
   if (d->precision == STAR_PREC_BF16 || d->precision == STAR_PREC_F16) {
-    if (stash != nullptr) return STAR_E_UNSUPPORTED;
     TcLayout tl;
     rc = star_make_tc_layout(d, &tl);
     if (rc) return rc;
     return star_tc_forward(tl, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, raw_alpha, raw_rgb,
-                           alpha_ray_stride, d->precision == STAR_PREC_F16, (cudaStream_t)stream);
+                           alpha_ray_stride, stash, d->precision == STAR_PREC_F16, (cudaStream_t)stream);
   }
   return STAR_E_UNSUPPORTED;
 }
@@ -127,5 +142,13 @@ extern "C" int star_mlp_backward(const StarNetDesc* d, const void* packed, const
     return star_f32_backward(lay, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, d_raw_alpha,
                              d_raw_rgb, alpha_ray_stride, stash, workspace, grad_flat, pose_acc,
                              (cudaStream_t)stream);
+  if (d->precision == STAR_PREC_BF16 || d->precision == STAR_PREC_F16) {
+    TcLayout tl;
+    rc = star_make_tc_layout(d, &tl);
+    if (rc) return rc;
+    return star_tc_backward(tl, lay, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, d_raw_alpha,
+                            d_raw_rgb, alpha_ray_stride, stash, workspace, grad_flat, pose_acc,
+                            d->precision == STAR_PREC_F16, (cudaStream_t)stream);
+  }
   return STAR_E_UNSUPPORTED;
 }

@@ -23,93 +23,7 @@
 #include "tc_common.cuh"
 #include "mlp_tc_layout.h"
 
-#define TC_M 128
-#define TC_NS 4
-#define TC_STAGE_BYTES 32768
-#define TC_KB_BYTES 16384          // one A K-block: 128 rows x 128 B
-#define TC_EPI_WARPS 16            // 4 per TMEM lane quadrant: each thread owns 1 row x 16 of the 64 columns of a K-block
-#define TC_EPI_THREADS (32 * TC_EPI_WARPS)
-#define TC_THREADS (TC_EPI_THREADS + 64)
-#define TC_TMEM_COLS 512
-#define TC_CPT 16                  // columns per thread per K-block
-
-struct TcSmem {
-  uint32_t A, AD, W, small, part, bars, tmem_ptr;   // byte offsets from the 1024-aligned base
-  uint32_t total;
-};
-__host__ __device__ static inline TcSmem tc_smem_layout(uint32_t small_bytes) {
-  TcSmem s;
-  uint32_t o = 0;
-  s.A = o; o += 4 * TC_KB_BYTES;
-  s.AD = o; o += TC_KB_BYTES;
-  s.W = o; o += TC_NS * TC_STAGE_BYTES;
-  s.small = o; o += small_bytes;
-  s.part = s.AD;    // head partial sums live in the never-read half (columns 32..63) of the dirs block
-  s.bars = o; o += 16 * 8;
-  s.tmem_ptr = o; o += 16;
-  s.total = o + 1024;   // slack for aligning the dynamic smem base
-  return s;
-}
-
-// barrier indices inside the bars block
-#define BAR_W_FULL(i) (i)
-#define BAR_W_EMPTY(i) (TC_NS + (i))
-#define BAR_A_READY(i) (2 * TC_NS + (i))      // 0..3: A K-blocks, 4: encoded-dirs block
-#define BAR_ACC_FULL (2 * TC_NS + 5)
-
-// ---------------------------------------------------------------------------------------------- encode
-// 16 consecutive columns [C0, C0+16) of the positional encoding [x, sin(2^k x), cos(2^k x)]_k (embedder.py:90-97;
-// NV = 3 + 6 L valid columns, zero beyond).  The lowest octave of the slice comes from sincosf, the following
-// ones from the double-angle recurrence (error doubles per octave from ~6e-8: < 1e-6 here, far below the
-// 16-bit operand resolution).  Everything is resolved at compile time after unrolling.
-template <int C0, int NV>
-__device__ __forceinline__ void encode_slice(const float (&p)[3], const float* __restrict__ sc, float (&e)[16]) {
-  constexpr int LAST = (C0 + 15 < NV) ? C0 + 15 : NV - 1;
-  constexpr int K_LO = (C0 < 3) ? 0 : (C0 - 3) / 6;
-  constexpr int K_HI = (LAST < 3) ? -1 : (LAST - 3) / 6;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) e[j] = (C0 + j < 3) ? p[(C0 + j) % 3] : 0.f;
-  if (K_HI >= K_LO) {
-    float sn[3], cs[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) sincosf(p[c] * (float)(1 << K_LO), &sn[c], &cs[c]);
-#pragma unroll
-    for (int k = K_LO; k <= K_HI; ++k) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int col = C0 + j;
-        if (col >= 3 && col < NV && (col - 3) / 6 == k) {
-          const int w = (col - 3) % 6;
-          e[j] = (w < 3) ? sn[w % 3] : cs[w % 3];
-        }
-      }
-      if (k < K_HI) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float s2 = 2.f * sn[c] * cs[c], c2 = 1.f - 2.f * sn[c] * sn[c];
-          sn[c] = s2; cs[c] = c2;
-        }
-      }
-    }
-  }
-  if (sc != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) e[j] *= sc[C0 + j];
-  }
-}
-
-// write 16 fp32 values as 16-bit operands into 16-byte chunks ch0, ch0+1 of row `row` of a SW128 K-block
-template <bool FP16, bool RELU>
-__device__ __forceinline__ void store_row16(uint32_t kblock_saddr, int row, int ch0, const float (&v)[16]) {
-  const uint32_t rbase = kblock_saddr + (uint32_t)row * 128u;
-  const uint32_t x = (uint32_t)row & 7u;
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    const uint32_t a = rbase + ((((uint32_t)(ch0 + c)) ^ x) << 4);
-    st_shared_v4(a, pack_16x2<FP16, RELU>(v[8 * c + 0], v[8 * c + 1]), pack_16x2<FP16, RELU>(v[8 * c + 2], v[8 * c + 3]),
-                 pack_16x2<FP16, RELU>(v[8 * c + 4], v[8 * c + 5]), pack_16x2<FP16, RELU>(v[8 * c + 6], v[8 * c + 7]));
-  }
-}
+#include "mlp_tc_device.cuh"
 
 // ---------------------------------------------------------------------------------------------- epilogue
 struct EpiCtx {
@@ -117,6 +31,7 @@ struct EpiCtx {
   uint32_t tcol;               // TMEM address: lane base of this warp | accumulator region | 16 * column group
   const float* bias;           // smem, epilogue bias vector of this layer
   const float* head_w;         // smem, alpha_linear / rgb_linear weights (OUT / VIEWS layers)
+  uint8_t* stash_out;          // global: first stash block of this layer's epilogue output for this tile, or NULL
   int row, cg, lane;
 };
 
@@ -159,8 +74,10 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3]) {
         h[1] = fmaf(x, c.head_w[STAR_WV + col0 + j], h[1]);
         h[2] = fmaf(x, c.head_w[2 * STAR_WV + col0 + j], h[2]);
       }
+      if (c.stash_out != nullptr) store_row16<FP16, true>(0u, c.row, c.cg * 2, v, c.stash_out + kb * TC_KB_BYTES);
     } else {
-      store_row16<FP16, RELU>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v);
+      store_row16<FP16, RELU>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v,
+                              c.stash_out != nullptr ? c.stash_out + kb * TC_KB_BYTES : nullptr);
       fence_proxy_async_smem();      // this thread's A writes -> async proxy (tcgen05.mma operand reads)
       tc_fence_before();
       __syncwarp();
@@ -175,8 +92,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const float* __restrict__ pts,
                   const float* __restrict__ viewdirs, const float* __restrict__ pose12,
                   const float* __restrict__ sc_xyz, const float* __restrict__ sc_dir, int S, int64_t M,
-                  float* __restrict__ raw_alpha, float* __restrict__ raw_rgb, int64_t ray_stride, int* dbg,
-                  int dbg_mode) {
+                  float* __restrict__ raw_alpha, float* __restrict__ raw_rgb, int64_t ray_stride,
+                  uint8_t* __restrict__ stash, int* dbg, int dbg_mode) {
+  // stash (NULL for inference): [tiles][lay.stash_blocks] blocks of TC_BLOCK_BYTES (mlp_tc_layout.h).
   // dbg_mode (bottleneck experiments only; results are garbage): bit 0 = epilogue skips TMEM load / math /
   // A store, bit 1 = no weight streaming (MMA reads whatever is in the ring), bit 2 = MMA issuer skips the MMAs
   extern __shared__ uint8_t smem_raw[];
@@ -301,9 +219,15 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         else if (cg == 1) encode_slice<16, 63>(p, sc_xyz, e);
         else if (cg == 2) encode_slice<32, 63>(p, sc_xyz, e);
         else encode_slice<48, 63>(p, sc_xyz, e);
-        store_row16<FP16, false>(sA, row, cg * 2, e);
-        if (cg == 1) { encode_slice<0, 27>(dv, sc_dir, e); store_row16<FP16, false>(sAD, row, 0, e); }
-        if (cg == 2) { encode_slice<16, 27>(dv, sc_dir, e); store_row16<FP16, false>(sAD, row, 2, e); }
+        uint8_t* st_tile = stash != nullptr ? stash + (size_t)tile * (size_t)lay.stash_blocks * TC_BLOCK_BYTES : nullptr;
+        uint8_t* st_dirs = st_tile != nullptr ? st_tile + (size_t)(lay.L[lay.n_layers - 1].s_in + 4) * TC_BLOCK_BYTES : nullptr;
+        store_row16<FP16, false>(sA, row, cg * 2, e, st_tile != nullptr ? st_tile + (size_t)lay.L[0].s_in * TC_BLOCK_BYTES : nullptr);
+        if (cg == 1) { encode_slice<0, 27>(dv, sc_dir, e); store_row16<FP16, false>(sAD, row, 0, e, st_dirs); }
+        if (cg == 2) { encode_slice<16, 27>(dv, sc_dir, e); store_row16<FP16, false>(sAD, row, 2, e, st_dirs); }
+        if (st_dirs != nullptr && (cg == 0 || cg == 3)) {   // zero the unused half of the dirs block once per tile
+          const float z[16] = {0.f};
+          store_row16<FP16, false>(0u, row, cg == 0 ? 4 : 6, z, st_dirs);
+        }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
@@ -320,6 +244,9 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         tc_fence_after();
         ctx.tcol = tmem_base + (((uint32_t)(q * 32)) << 16) + (L.region ? 256u : 0u) + (uint32_t)(cg * TC_CPT);
         ctx.bias = s_small + L.bias_off;
+        ctx.stash_out = stash != nullptr
+                            ? stash + ((size_t)tile * (size_t)lay.stash_blocks + (size_t)L.s_out) * TC_BLOCK_BYTES
+                            : nullptr;
         float h[3] = {0.f, 0.f, 0.f};
         if (dbg_mode & 1) {
           for (int kb = 0; kb < (L.N >> 6) && L.kind != LK_VIEWS; ++kb) {
@@ -429,7 +356,11 @@ __global__ void pack_tc_stream_kernel(TcLayout tl, MlpLayout ml, const float* __
 }
 
 // ============================================================================================ host side
-size_t star_tc_packed_bytes(const TcLayout& tl) { return (size_t)tl.small_bytes + tl.stream_bytes; }
+int star_tc_pack_tstream(const TcLayout& tl, const MlpLayout& ml, const float* master, void* tstream, int fp16,
+                         cudaStream_t st);
+
+// packed image = [small section][forward weight stream][transposed (backward) weight stream]
+size_t star_tc_packed_bytes(const TcLayout& tl) { return (size_t)tl.small_bytes + tl.stream_bytes + tl.tstream_bytes; }
 
 int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, void* packed, int fp16,
                  cudaStream_t st) {
@@ -438,12 +369,14 @@ int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, v
   if (rc) return rc;
   pack_tc_stream_kernel<<<148 * 4, 256, 0, st>>>(tl, ml, master, (uint16_t*)((uint8_t*)packed + tl.small_bytes),
                                                  fp16);
-  return star_check_launch();
+  rc = star_check_launch();
+  if (rc) return rc;
+  return star_tc_pack_tstream(tl, ml, master, (uint8_t*)packed + tl.small_bytes + tl.stream_bytes, fp16, st);
 }
 
 int star_tc_forward(const TcLayout& tl, const void* packed, const float* pts, const float* viewdirs,
                     const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
-                    float* raw_rgb, int64_t ray_stride, int fp16, cudaStream_t st) {
+                    float* raw_rgb, int64_t ray_stride, void* stash, int fp16, cudaStream_t st) {
   const int64_t M = (int64_t)R * S;
   const int64_t ntiles = (M + TC_M - 1) / TC_M;
   int dev = 0, sms = 148;
@@ -465,7 +398,7 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const float* pts, co
     if (dbg_cycles) { cudaMalloc(&d_dbg, 64); cudaMemset(d_dbg, 0, 64); }
   }
   kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
-                                            raw_alpha, raw_rgb, ray_stride, (int*)d_dbg, dbg_mode);
+                                            raw_alpha, raw_rgb, ray_stride, (uint8_t*)stash, (int*)d_dbg, dbg_mode);
   if (dbg_cycles) {
     long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaStreamSynchronize(st);

@@ -1,0 +1,711 @@
+// Backward pass of the tensor-core MLP tier (sm_100a): gradients of (raw_alpha, raw_rgb) w.r.t. every MLP weight
+// and, for object nets, the pose accumulators (models/nerf.py:112-179, models/resnet.py:51-59, models/star__.py:160-199).
+//
+// Inputs: the activation stash written by the training forward (mlp_tc.cu; 16 KB swizzled blocks, mlp_tc_layout.h).
+//   1. mlp_bwd_tc_kernel  -- the dX chain, one persistent CTA per SM over 128-sample tiles, same roles as the
+//      forward: G_l = dL/d(output of GEMM layer l) flows backwards through tcgen05 GEMMs against the TRANSPOSED
+//      weight stream; ReLU masks come from the stash; the residual gradient dx lives in TMEM columns 0..255 (fp32)
+//      and is read-modified-written by the epilogue; every G_l is written to the gradient stash in the same block
+//      format.  Object nets also run G_in * W_in and G_views * W_views[:, dirs] and fold the result through the
+//      positional-encoding Jacobian into the 27 pose accumulators of include/star_b200.h.
+//   2. dw_tc_kernel       -- dW_l = G_l^T A_l and db_l = G_l^T 1 as tcgen05 GEMMs whose K dimension is the sample
+//      index: stash blocks are consumed directly as MN-major operands (a block is [samples][64 features]), split over
+//      CTAs by (layer, 128-row half, sample range), partial results reduced into the flat fp32 gradient with atomics.
+//   3. head_grad_tc_kernel -- alpha_linear / rgb_linear gradients on CUDA cores (tiny).
+#include <cuda_fp16.h>
+#include "mlp_tc_device.cuh"
+
+#define BK_PRE 0     // G_views from d_rgb, rgb_linear and the relu(h2) mask (no MMA before it)
+#define BK_FEAT 1    // G_feat = T                     (+ dirs part of the pose gradient)
+#define BK_OUT 2     // G_out  = X + d_alpha * w_alpha
+#define BK_X0 3      // dx = T * mask                  -> X, G_fc1(last block)
+#define BK_FC1 4     // G_fc0 = T * mask
+#define BK_FC0 5     // dx = X + T * mask              -> X, G_fc1(previous block) / G_in
+#define BK_IN 6      // pose gradient through the xyz encoding Jacobian (objects only)
+
+struct BwdStage {    // one weight K-block = one ring stage = one group of MMAs
+  uint32_t w_off, bytes;
+  int a_kb, N, tcol, accum, nk, last;   // A K-block, MMA N, TMEM column, accumulate flag of the first MMA, K-steps, last of phase
+};
+struct BwdPhase {
+  int kind, nch;       // epilogue kind, number of 64-column chunks it produces (A K-blocks)
+  int mask_blk, g_blk; // stash block of the mask source / gradient-stash block of the output (-1: none)
+  int n_wait;          // A K-blocks the following MMA group must wait for (= nch)
+};
+#define BWD_MAX_STAGES 64
+#define BWD_MAX_PHASES 24
+
+struct BwdSmem {
+  uint32_t A, W, small, tab, bars, tmem_ptr, total;
+};
+__host__ __device__ static inline BwdSmem bwd_smem_layout(uint32_t small_bytes) {
+  BwdSmem s;
+  uint32_t o = 0;
+  s.A = o; o += 4 * TC_KB_BYTES;
+  s.W = o; o += TC_NS * TC_STAGE_BYTES;
+  s.small = o; o += small_bytes;
+  s.tab = o; o += BWD_MAX_STAGES * sizeof(BwdStage) + BWD_MAX_PHASES * sizeof(BwdPhase) + 16;
+  s.bars = o; o += 16 * 8;
+  s.tmem_ptr = o; o += 16;
+  s.total = o + 1024;
+  return s;
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// d(encoding column)/d(input component) for the 16 columns [C0, C0+16): column col < 3 -> component col, 1;
+// sin(2^k x_c) -> 2^k cos; cos(2^k x_c) -> -2^k sin.  comp[j] = component index, dv[j] = derivative (0 for padding).
+template <int C0, int NV>
+__device__ __forceinline__ void encode_slice_grad(const float (&p)[3], const float* __restrict__ sc, float (&dv)[16]) {
+  constexpr int LAST = (C0 + 15 < NV) ? C0 + 15 : NV - 1;
+  constexpr int K_LO = (C0 < 3) ? 0 : (C0 - 3) / 6;
+  constexpr int K_HI = (LAST < 3) ? -1 : (LAST - 3) / 6;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) dv[j] = (C0 + j < 3) ? 1.f : 0.f;
+  if (K_HI >= K_LO) {
+    float sn[3], cs[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sincosf(p[c] * (float)(1 << K_LO), &sn[c], &cs[c]);
+#pragma unroll
+    for (int k = K_LO; k <= K_HI; ++k) {
+      const float f = (float)(1 << k);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = C0 + j;
+        if (col >= 3 && col < NV && (col - 3) / 6 == k) {
+          const int w = (col - 3) % 6;
+          dv[j] = (w < 3) ? f * cs[w % 3] : -f * sn[w % 3];
+        }
+      }
+      if (k < K_HI) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float s2 = 2.f * sn[c] * cs[c], c2 = 1.f - 2.f * sn[c] * sn[c];
+          sn[c] = s2; cs[c] = c2;
+        }
+      }
+    }
+  }
+  if (sc != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dv[j] *= sc[C0 + j];
+  }
+}
+// component (0..2) of encoding column col
+__host__ __device__ constexpr int enc_comp(int col) { return col < 3 ? col : ((col - 3) % 6) % 3; }
+
+template <int C0, int NV>
+__device__ __forceinline__ void fold_jacobian(const uint32_t (&r)[16], const float (&p)[3], const float* sc, float (&g)[3]) {
+  float dv[16];
+  encode_slice_grad<C0, NV>(p, sc, dv);
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (C0 + j < NV) g[enc_comp(C0 + j)] = fmaf(__uint_as_float(r[j]), dv[j], g[enc_comp(C0 + j)]);
+}
+
+// ============================================================================================ dX chain
+template <bool FP16>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const float* __restrict__ pts,
+                  const float* __restrict__ viewdirs, const float* __restrict__ pose12,
+                  const float* __restrict__ sc_xyz, const float* __restrict__ sc_dir, int S, int64_t M,
+                  const float* __restrict__ d_raw_alpha, const float* __restrict__ d_raw_rgb, int64_t ray_stride,
+                  const uint8_t* __restrict__ stash, uint8_t* __restrict__ gstash, float* __restrict__ pose_acc,
+                  int* dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw_addr);
+  const BwdSmem sl = bwd_smem_layout(lay.small_bytes);
+  const uint32_t sA = base + sl.A, sW = base + sl.W, sBars = base + sl.bars;
+  float* s_small = reinterpret_cast<float*>(gbase + sl.small);
+  BwdStage* stages = reinterpret_cast<BwdStage*>(gbase + sl.tab);
+  BwdPhase* phases = reinterpret_cast<BwdPhase*>(gbase + sl.tab + BWD_MAX_STAGES * sizeof(BwdStage));
+  int* counts = reinterpret_cast<int*>(gbase + sl.tab + BWD_MAX_STAGES * sizeof(BwdStage) + BWD_MAX_PHASES * sizeof(BwdPhase));
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(gbase + sl.tmem_ptr);
+  auto bar = [&](int i) -> uint32_t { return sBars + 8u * (uint32_t)i; };
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (M + TC_M - 1) / TC_M;
+  const bool has_pose = pose12 != nullptr;
+
+  // ---- the per-tile program (identical for every tile): built once by one thread
+  if (tid == 0) {
+    const int nl = lay.n_layers, V = nl - 1, F = nl - 2, O = nl - 3;
+    int ns = 0, np = 0;
+    auto stage = [&](uint32_t w_off, uint32_t bytes, int a_kb, int N, int tcol, int accum, int nk, int last) {
+      BwdStage& s = stages[ns++];
+      s.w_off = w_off; s.bytes = bytes; s.a_kb = a_kb; s.N = N; s.tcol = tcol; s.accum = accum; s.nk = nk; s.last = last;
+    };
+    auto phase = [&](int kind, int nch, int mask_blk, int g_blk) {
+      BwdPhase& p = phases[np++];
+      p.kind = kind; p.nch = nch; p.mask_blk = mask_blk; p.g_blk = g_blk; p.n_wait = nch;
+    };
+    // full layer: N = 256 input features, K = n_out / 64 blocks of the transposed stream
+    auto gemm = [&](int l, int tcol) {
+      const int nkb = lay.L[l].N / 64;
+      for (int kb = 0; kb < nkb; ++kb)
+        stage(lay.stream_bytes + lay.L[l].wt_off + (uint32_t)kb * 32768u, 32768u, kb, 256, tcol, kb > 0, 4, kb == nkb - 1);
+    };
+    phase(BK_PRE, 2, lay.L[V].s_out, lay.L[V].g_out);
+    // views: T <- G_v * Wv[:, :256]^T (+ X[0:32] <- G_v * Wv[:, 256:288]^T for objects)
+    for (int kb = 0; kb < 2; ++kb)
+      stage(lay.stream_bytes + lay.L[V].wt_off + (uint32_t)kb * 32768u, 32768u, kb, 256, 256, kb > 0, 4, !has_pose && kb == 1);
+    if (has_pose)
+      for (int kb = 0; kb < 2; ++kb)
+        stage(lay.stream_bytes + lay.wt_dirs_off + (uint32_t)kb * 8192u, 8192u, kb, 32, 0, kb > 0, 4, kb == 1);
+    phase(BK_FEAT, 4, -1, lay.L[F].g_out);
+    gemm(F, 0);
+    phase(BK_OUT, 4, -1, lay.L[O].g_out);
+    gemm(O, 256);
+    phase(BK_X0, 4, lay.L[O].s_in, lay.L[O - 1].g_out);       // mask relu(x_B) > 0; G of the last fc_1 (or lin_in)
+    for (int b = lay.n_blocks - 1; b >= 0; --b) {
+      const int l0 = 1 + 2 * b, l1 = 2 + 2 * b;
+      gemm(l1, 256);
+      phase(BK_FC1, 4, lay.L[l1].s_in, lay.L[l0].g_out);      // mask relu(net_b) > 0
+      gemm(l0, 256);
+      phase(BK_FC0, 4, lay.L[l0].s_in, lay.L[l0 - 1].g_out);  // mask relu(x_b) > 0; G of fc_1(b-1) or lin_in
+    }
+    if (has_pose) {   // d enc_xyz = G_in * W_in: N = 64 input features, K = 256
+      for (int kb = 0; kb < 4; ++kb)
+        stage(lay.stream_bytes + lay.L[0].wt_off + (uint32_t)kb * 8192u, 8192u, kb, 64, 256, kb > 0, 4, kb == 3);
+      phase(BK_IN, 0, -1, -1);
+    }
+    counts[0] = ns; counts[1] = np;
+  }
+  if (warp == TC_EPI_WARPS && lane == 0) {
+    for (int i = 0; i < TC_NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), 1); mbar_init(bar(BAR_W_EMPTY(i)), 1); }
+    for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A_READY(i)), TC_EPI_WARPS);
+    mbar_init(bar(BAR_ACC_FULL), 1);
+    fence_mbar_init();
+  }
+  if (warp == TC_EPI_WARPS + 1) tmem_alloc(base + sl.tmem_ptr, TC_TMEM_COLS);
+  for (int i = tid; i < lay.small_floats; i += TC_THREADS) s_small[i] = reinterpret_cast<const float*>(packed)[i];
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const int n_stages = counts[0], n_phases = counts[1];
+
+  if (warp == TC_EPI_WARPS) {
+    // ======================================================================== weight producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int i = 0; i < n_stages; ++i) {
+          const BwdStage& s = stages[i];
+          mbar_wait(bar(BAR_W_EMPTY(stage)), phase ^ 1u, dbg, 1);
+          mbar_arrive_expect_tx(bar(BAR_W_FULL(stage)), s.bytes);
+          bulk_g2s(sW + stage * TC_STAGE_BYTES, packed + lay.small_bytes + s.w_off, s.bytes, bar(BAR_W_FULL(stage)));
+          if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == TC_EPI_WARPS + 1) {
+    // ======================================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, a_par = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int ph = 0;              // index of the epilogue phase that produced the A operand of the current group
+        bool group_start = true;
+        for (int i = 0; i < n_stages; ++i) {
+          const BwdStage& s = stages[i];
+          if (group_start) {
+            // the A operand (and the free accumulator) of this group need ALL chunks of the previous epilogue
+            for (int kb = 0; kb < phases[ph].n_wait; ++kb) {
+              mbar_wait(bar(BAR_A_READY(kb)), (a_par >> kb) & 1u, dbg, 2);
+              a_par ^= 1u << kb;
+            }
+            group_start = false;
+          }
+          mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
+          tc_fence_after();
+          const uint32_t idesc = umma_idesc_16(TC_M, s.N, FP16 ? 0 : 1);
+          const uint32_t a_addr = sA + (uint32_t)s.a_kb * TC_KB_BYTES, b_addr = sW + stage * TC_STAGE_BYTES;
+          for (int k = 0; k < s.nk; ++k)
+            tc_mma_bf16(tmem_base + (uint32_t)s.tcol, umma_desc_sw128(a_addr + 32u * k), umma_desc_sw128(b_addr + 32u * k),
+                        idesc, (s.accum || k > 0) ? 1u : 0u);
+          tc_commit(bar(BAR_W_EMPTY(stage)));
+          if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
+          if (s.last) {
+            tc_commit(bar(BAR_ACC_FULL));
+            ++ph;
+            group_start = true;
+          }
+        }
+      }
+    }
+  } else {
+    // ======================================================================== epilogue warps
+    const int q = warp & 3, cg = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
+    uint32_t acc_par = 0;
+    float pacc[27];
+#pragma unroll
+    for (int i = 0; i < 27; ++i) pacc[i] = 0.f;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t gi = tile * TC_M + row;
+      const bool valid = gi < M;
+      float da = 0.f, dc0 = 0.f, dc1 = 0.f, dc2 = 0.f;
+      float pw[3] = {0.f, 0.f, 0.f}, po[3] = {0.f, 0.f, 0.f}, dw[3] = {0.f, 0.f, 0.f}, dob[3] = {0.f, 0.f, 0.f};
+      if (valid) {
+        const int64_t r = gi / S;
+        const int64_t o = r * ray_stride + (gi - r * S);
+        da = d_raw_alpha[o];
+        dc0 = d_raw_rgb[o * 3 + 0]; dc1 = d_raw_rgb[o * 3 + 1]; dc2 = d_raw_rgb[o * 3 + 2];
+        if (has_pose) {
+          pw[0] = pts[gi * 3 + 0]; pw[1] = pts[gi * 3 + 1]; pw[2] = pts[gi * 3 + 2];
+          dw[0] = viewdirs[r * 3 + 0]; dw[1] = viewdirs[r * 3 + 1]; dw[2] = viewdirs[r * 3 + 2];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            po[i] = pose12[i * 3 + 0] * pw[0] + pose12[i * 3 + 1] * pw[1] + pose12[i * 3 + 2] * pw[2] + pose12[9 + i];
+            dob[i] = pose12[i * 3 + 0] * dw[0] + pose12[i * 3 + 1] * dw[1] + pose12[i * 3 + 2] * dw[2];
+          }
+        }
+      }
+      const uint8_t* st_tile = stash + (size_t)tile * (size_t)lay.stash_blocks * TC_BLOCK_BYTES;
+      uint8_t* gs_tile = gstash + (size_t)tile * (size_t)lay.gstash_blocks * TC_BLOCK_BYTES;
+      const uint32_t x_sw = (uint32_t)row & 7u;
+
+      for (int pi = 0; pi < n_phases; ++pi) {
+        const BwdPhase P = phases[pi];
+        if (P.kind != BK_PRE) {
+          mbar_wait(bar(BAR_ACC_FULL), acc_par, dbg, 4);
+          acc_par ^= 1u;
+          tc_fence_after();
+        }
+        const uint32_t tX = tmem_base + lane_addr + (uint32_t)(cg * TC_CPT);
+        const uint32_t tT = tX + 256u;
+        if (P.kind == BK_IN) {       // d enc_xyz in T[0:64]: 16 columns per thread
+          uint32_t r[16];
+          tmem_ld16(tT, r);
+          tmem_wait_ld();
+          float g[3] = {0.f, 0.f, 0.f};
+          if (cg == 0) fold_jacobian<0, 63>(r, po, sc_xyz, g);
+          else if (cg == 1) fold_jacobian<16, 63>(r, po, sc_xyz, g);
+          else if (cg == 2) fold_jacobian<32, 63>(r, po, sc_xyz, g);
+          else fold_jacobian<48, 63>(r, po, sc_xyz, g);
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              pacc[i] += g[i];
+#pragma unroll
+              for (int j = 0; j < 3; ++j) pacc[3 + i * 3 + j] += g[i] * pw[j];
+            }
+            pacc[12] += po[1] * g[2] - po[2] * g[1];
+            pacc[13] += po[2] * g[0] - po[0] * g[2];
+            pacc[14] += po[0] * g[1] - po[1] * g[0];
+          }
+          tc_fence_before();
+          continue;
+        }
+        if (P.kind == BK_FEAT && has_pose && cg < 2) {   // d enc_dir in X[0:32]
+          uint32_t r[16];
+          tmem_ld16(tX, r);
+          tmem_wait_ld();
+          float h[3] = {0.f, 0.f, 0.f};
+          if (cg == 0) fold_jacobian<0, 27>(r, dob, sc_dir, h);
+          else fold_jacobian<16, 27>(r, dob, sc_dir, h);
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j) pacc[15 + i * 3 + j] += h[i] * dw[j];
+            pacc[24] += dob[1] * h[2] - dob[2] * h[1];
+            pacc[25] += dob[2] * h[0] - dob[0] * h[2];
+            pacc[26] += dob[0] * h[1] - dob[1] * h[0];
+          }
+        }
+        for (int kb = 0; kb < P.nch; ++kb) {
+          const int col0 = kb * 64 + cg * TC_CPT;
+          const uint32_t off0 = (uint32_t)row * 128u + ((((uint32_t)(cg * 2)) ^ x_sw) << 4);
+          const uint32_t off1 = (uint32_t)row * 128u + ((((uint32_t)(cg * 2 + 1)) ^ x_sw) << 4);
+          // mask source: 16 stashed 16-bit activations (> 0 <=> bits != 0 for a ReLU output)
+          uint4 m0 = make_uint4(~0u, ~0u, ~0u, ~0u), m1 = m0;
+          if (P.mask_blk >= 0) {
+            const uint8_t* mb = st_tile + (size_t)(P.mask_blk + kb) * TC_BLOCK_BYTES;
+            m0 = *reinterpret_cast<const uint4*>(mb + off0);
+            m1 = *reinterpret_cast<const uint4*>(mb + off1);
+          }
+          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          float v[16];
+          if (P.kind == BK_PRE) {
+            const float* rw = s_small + lay.off_rgb_w + col0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = dc0 * rw[j] + dc1 * rw[STAR_WV + j] + dc2 * rw[2 * STAR_WV + j];
+          } else {
+            uint32_t r[16];
+            tmem_ld16(((P.kind == BK_OUT) ? tX : tT) + 64u * (uint32_t)kb, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          }
+          if (P.kind == BK_OUT) {
+            const float* aw = s_small + lay.off_alpha_w + col0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaf(da, aw[j], v[j]);
+          }
+          if (P.mask_blk >= 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t bits = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xffffu);
+              if (bits == 0u) v[j] = 0.f;
+            }
+          }
+          if (P.kind == BK_FC0) {      // dx += masked product
+            uint32_t rx[16];
+            tmem_ld16(tX + 64u * (uint32_t)kb, rx);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(rx[j]);
+          }
+          if (P.kind == BK_FC0 || P.kind == BK_X0) {
+            uint32_t rx[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rx[j] = __float_as_uint(v[j]);
+            tmem_st16(tX + 64u * (uint32_t)kb, rx);
+            tmem_wait_st();
+          }
+          if (!valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+          }
+          store_row16<FP16, false>(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, v,
+                                   gs_tile + (size_t)(P.g_blk + kb) * TC_BLOCK_BYTES);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_A_READY(kb)));
+        }
+      }
+    }
+    if (has_pose) {
+#pragma unroll
+      for (int i = 0; i < 27; ++i) {
+        const float s = warp_sum(pacc[i]);
+        if (lane == 0) atomicAdd(&pose_acc[i], s);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_EPI_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// ============================================================================================ dW / db
+// One CTA = (layer l, 128-row half of its outputs, sample-tile range).  Per tile: 2 gradient blocks (A operand,
+// MN-major: M = output features) and up to 4 activation blocks (B operand, MN-major: N = input features), K = 128
+// samples = 8 MMAs of K = 16; a constant "ones" block gives db as 16 extra accumulator columns.
+#define DW_THREADS 192          // warp 0: producer, warp 1: MMA, warps 2..5: epilogue (TMEM lane quadrants 2,3,0,1)
+#define DW_STAGE_BLOCKS 6
+#define DW_NSTAGE 2
+
+struct DwItem {
+  int g_blk, a_blk, n_a;     // first gradient-stash block (2 blocks), first stash block, number of stash blocks
+  int64_t w_off, b_off;      // flat-gradient offsets of W[half*128][0] (+k0) and b[half*128] (-1: no bias here)
+  int K, k0, k_valid;        // row length of W, first column written, valid columns of this item
+};
+#define DW_MAX_ITEMS 40
+struct DwPlan {
+  int n_items, splits;
+  DwItem it[DW_MAX_ITEMS];
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;   // between 64-element groups along M / N
+  d |= (uint64_t)(1024 >> 4) << 32;                    // between 8-row groups along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(DW_THREADS, 1)
+dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8_t* __restrict__ stash,
+             const uint8_t* __restrict__ gstash, int64_t ntiles, float* __restrict__ grad_flat, int* dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw_addr);
+  const uint32_t sStage = base, sOnes = base + DW_NSTAGE * DW_STAGE_BLOCKS * TC_BLOCK_BYTES;
+  const uint32_t sBars = sOnes + TC_BLOCK_BYTES;
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(gbase + (sBars - base) + 64);
+  auto bar = [&](int i) -> uint32_t { return sBars + 8u * (uint32_t)i; };   // 0,1 full; 2,3 empty; 4 done
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int item_id = blockIdx.x / plan.splits, split = blockIdx.x % plan.splits;
+  const DwItem it = plan.it[item_id];
+  const int64_t per = (ntiles + plan.splits - 1) / plan.splits;
+  const int64_t t0 = (int64_t)split * per, t1 = (t0 + per < ntiles) ? t0 + per : ntiles;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2 * DW_NSTAGE; ++i) mbar_init(bar(i), 1);
+    mbar_init(bar(4), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(sBars + 64, 512);
+  // ones block: logical column 0 of every row = 1.0 (16-byte chunk 0 ^ (row & 7), element 0), zero elsewhere
+  for (int i = tid; i < TC_BLOCK_BYTES / 16; i += DW_THREADS) {
+    const int r = i >> 3, c = i & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (c == (r & 7)) v.x = FP16 ? 0x3C00u : 0x3F80u;
+    reinterpret_cast<uint4*>(gbase + (sOnes - base))[i] = v;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t stage_bytes = (uint32_t)(2 + it.n_a) * TC_BLOCK_BYTES;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      for (int64_t t = t0; t < t1; ++t) {
+        mbar_wait(bar(2 + st), ph ^ 1u, dbg, 1);
+        mbar_arrive_expect_tx(bar(st), stage_bytes);
+        const uint32_t dst = sStage + st * DW_STAGE_BLOCKS * TC_BLOCK_BYTES;
+        bulk_g2s(dst, gstash + ((size_t)t * gstash_blocks + it.g_blk) * TC_BLOCK_BYTES, 2 * TC_BLOCK_BYTES, bar(st));
+        bulk_g2s(dst + 2 * TC_BLOCK_BYTES, stash + ((size_t)t * stash_blocks + it.a_blk) * TC_BLOCK_BYTES,
+                 (uint32_t)it.n_a * TC_BLOCK_BYTES, bar(st));
+        if (++st == DW_NSTAGE) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const int N = 64 * it.n_a;
+      const uint32_t fmt = FP16 ? 0u : 1u;
+      const uint32_t idesc = umma_idesc_16(128, N, (int)fmt) | (1u << 15) | (1u << 16);      // both operands MN-major
+      const uint32_t idesc1 = umma_idesc_16(128, 16, (int)fmt) | (1u << 15) | (1u << 16);
+      uint32_t st = 0, ph = 0;
+      bool first = true;
+      for (int64_t t = t0; t < t1; ++t) {
+        mbar_wait(bar(st), ph, dbg, 2);
+        tc_fence_after();
+        const uint32_t g_addr = sStage + st * DW_STAGE_BLOCKS * TC_BLOCK_BYTES, a_addr = g_addr + 2 * TC_BLOCK_BYTES;
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t da = umma_desc_mn_sw128(g_addr + 2048u * ks, TC_BLOCK_BYTES);
+          tc_mma_bf16(tmem_base, da, umma_desc_mn_sw128(a_addr + 2048u * ks, TC_BLOCK_BYTES), idesc, first ? 0u : 1u);
+          if (it.b_off >= 0)
+            tc_mma_bf16(tmem_base + 256u, da, umma_desc_mn_sw128(sOnes + 2048u * ks, TC_BLOCK_BYTES), idesc1,
+                        first ? 0u : 1u);
+          first = false;
+        }
+        tc_commit(bar(2 + st));
+        if (++st == DW_NSTAGE) { st = 0; ph ^= 1u; }
+      }
+      tc_commit(bar(4));
+    }
+  } else {
+    // epilogue: TMEM -> registers -> atomics into the flat gradient
+    const int q = warp & 3;
+    const int n = q * 32 + lane;                      // output feature within the half
+    if (t1 > t0) {
+      mbar_wait(bar(4), 0, dbg, 3);
+      tc_fence_after();
+      const uint32_t tl = tmem_base + (((uint32_t)(q * 32)) << 16);
+      float* wrow = grad_flat + it.w_off + (int64_t)n * it.K + it.k0;
+      for (int c0 = 0; c0 < 64 * it.n_a; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tl + (uint32_t)c0, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c0 + j < it.k_valid) atomicAdd(wrow + c0 + j, __uint_as_float(r[j]));
+      }
+      if (it.b_off >= 0) {
+        uint32_t r[16];
+        tmem_ld16(tl + 256u, r);
+        tmem_wait_ld();
+        atomicAdd(grad_flat + it.b_off + n, __uint_as_float(r[0]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ============================================================================================ head gradients
+// d alpha_w[k] = sum_m d_alpha[m] h[m][k]  (h = stashed input of feature_linear), d rgb_w[c][n] = sum_m d_rgb[m][c] relu(h2)[m][n]
+__device__ __forceinline__ float stash_elem(const uint8_t* blk, int row, int col, bool fp16) {
+  const uint16_t bits = *reinterpret_cast<const uint16_t*>(blk + sw128_off(row, col));
+  return fp16 ? __half2float(__ushort_as_half(bits)) : __uint_as_float((uint32_t)bits << 16);
+}
+
+__global__ void __launch_bounds__(256)
+head_grad_tc_kernel(const TcLayout lay, MlpLayout ml, const uint8_t* __restrict__ stash, const float* __restrict__ d_raw_alpha,
+                    const float* __restrict__ d_raw_rgb, int64_t ray_stride, int S, int64_t M, int fp16,
+                    float* __restrict__ grad_flat) {
+  const int tid = threadIdx.x;
+  const int64_t ntiles = (M + 127) / 128;
+  const int F = lay.n_layers - 2, V = lay.n_layers - 1;
+  float aw = 0.f, ab = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+  __shared__ float s_d[128][4];
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    __syncthreads();
+    if (tid < 128) {
+      const int64_t gi = t * 128 + tid;
+      float a = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+      if (gi < M) {
+        const int64_t r = gi / S, o = r * ray_stride + (gi - r * S);
+        a = d_raw_alpha[o]; c0 = d_raw_rgb[o * 3]; c1 = d_raw_rgb[o * 3 + 1]; c2 = d_raw_rgb[o * 3 + 2];
+      }
+      s_d[tid][0] = a; s_d[tid][1] = c0; s_d[tid][2] = c1; s_d[tid][3] = c2;
+    }
+    __syncthreads();
+    const uint8_t* tile = stash + (size_t)t * lay.stash_blocks * TC_BLOCK_BYTES;
+    const uint8_t* hb = tile + (size_t)(lay.L[F].s_in + (tid >> 6)) * TC_BLOCK_BYTES;      // column tid of h
+    const uint8_t* h2b = tile + (size_t)(lay.L[V].s_out + ((tid & 127) >> 6)) * TC_BLOCK_BYTES;
+    for (int m = 0; m < 128; ++m) {
+      const float a = s_d[m][0];
+      aw = fmaf(a, stash_elem(hb, m, tid & 63, fp16), aw);
+      if (tid < 128) {
+        const float x = stash_elem(h2b, m, tid & 63, fp16);
+        r0 = fmaf(s_d[m][1], x, r0); r1 = fmaf(s_d[m][2], x, r1); r2 = fmaf(s_d[m][3], x, r2);
+      }
+      if (tid == 0) { ab += a; b0 += s_d[m][1]; b1 += s_d[m][2]; b2 += s_d[m][3]; }
+    }
+  }
+  atomicAdd(&grad_flat[ml.m_alpha_w + tid], aw);
+  if (tid < 128) {
+    atomicAdd(&grad_flat[ml.m_rgb_w + 0 * STAR_WV + tid], r0);
+    atomicAdd(&grad_flat[ml.m_rgb_w + 1 * STAR_WV + tid], r1);
+    atomicAdd(&grad_flat[ml.m_rgb_w + 2 * STAR_WV + tid], r2);
+  }
+  if (tid == 0) {
+    atomicAdd(&grad_flat[ml.m_alpha_b], ab);
+    atomicAdd(&grad_flat[ml.m_rgb_b + 0], b0);
+    atomicAdd(&grad_flat[ml.m_rgb_b + 1], b1);
+    atomicAdd(&grad_flat[ml.m_rgb_b + 2], b2);
+  }
+}
+
+// ============================================================================================ transposed weight stream
+// dX GEMM of layer l: out[m][j] = sum_n G[m][n] W[n][j]: B operand rows j (input features, padded to 64 / 256),
+// K-blocks over the output features n, swizzled like every other block.
+__global__ void pack_tc_tstream_kernel(TcLayout tl, MlpLayout ml, const float* __restrict__ master,
+                                       uint16_t* __restrict__ tstream, int fp16) {
+  const uint32_t n_elems = tl.tstream_bytes / 2;
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_elems; e += gridDim.x * blockDim.x) {
+    const uint32_t byte = e * 2;
+    float v = 0.f;
+    int rows, l, kb, j, nn;
+    uint32_t off;
+    if (byte >= tl.wt_dirs_off) {                 // view layer, encoded-dirs rows: [64 rows j][64 n] x 2
+      l = tl.n_layers - 1; rows = 64; off = byte - tl.wt_dirs_off;
+    } else {
+      l = 0;
+      while (l + 1 < tl.n_layers && byte >= tl.L[l + 1].wt_off) ++l;
+      rows = (tl.L[l].nkb < 4 ? tl.L[l].nkb : 4) * 64; off = byte - tl.L[l].wt_off;
+    }
+    const uint32_t kb_bytes = (uint32_t)rows * 128u;
+    kb = (int)(off / kb_bytes);
+    const uint32_t rem = off % kb_bytes;
+    j = (int)(rem >> 7);
+    const uint32_t inrow = rem & 127u;
+    const int chunk = (int)((inrow >> 4) ^ ((uint32_t)j & 7u));
+    nn = kb * 64 + chunk * 8 + (int)((inrow & 15u) >> 1);      // output feature
+    const int K = ml.L[l].K;
+    const int jj = (byte >= tl.wt_dirs_off) ? STAR_W + j : j;    // input feature
+    if (nn < tl.L[l].N && jj < K && (byte >= tl.wt_dirs_off ? j < K - STAR_W : true))
+      v = master[ml.L[l].m_w + (int64_t)nn * K + jj];
+    tstream[e] = fp16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  }
+}
+
+// ============================================================================================ host side
+int star_tc_pack_tstream(const TcLayout& tl, const MlpLayout& ml, const float* master, void* tstream, int fp16,
+                         cudaStream_t st) {
+  pack_tc_tstream_kernel<<<148 * 4, 256, 0, st>>>(tl, ml, master, (uint16_t*)tstream, fp16);
+  return star_check_launch();
+}
+
+size_t star_tc_gstash_bytes(const TcLayout& tl, int64_t n_samples) {
+  return (size_t)((n_samples + 127) / 128) * (size_t)tl.gstash_blocks * TC_BLOCK_BYTES;
+}
+
+int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed, const float* pts, const float* viewdirs,
+                     const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, const float* d_raw_alpha,
+                     const float* d_raw_rgb, int64_t ray_stride, const void* stash, void* gstash, float* grad_flat,
+                     float* pose_acc, int fp16, cudaStream_t st) {
+  const int64_t M = (int64_t)R * S;
+  const int64_t ntiles = (M + TC_M - 1) / TC_M;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // ---- 1. dX chain
+  {
+    const int grid = (int)(ntiles < sms ? ntiles : sms);
+    const BwdSmem sl = bwd_smem_layout(tl.small_bytes);
+    auto kern = fp16 ? mlp_bwd_tc_kernel<true> : mlp_bwd_tc_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
+    if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
+    kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
+                                              d_raw_alpha, d_raw_rgb, ray_stride, (const uint8_t*)stash, (uint8_t*)gstash,
+                                              pose_acc, nullptr);
+    int rc = star_check_launch();
+    if (rc) return rc;
+  }
+  // ---- 2. dW / db
+  {
+    DwPlan plan;
+    int n = 0;
+    for (int l = 0; l < tl.n_layers; ++l) {
+      const TcLayer& L = tl.L[l];
+      const int halves = L.N / 128, K = ml.L[l].K;
+      for (int h = 0; h < halves; ++h) {
+        DwItem& it = plan.it[n++];
+        it.g_blk = L.g_out + 2 * h;
+        it.a_blk = L.s_in;
+        it.n_a = L.nkb < 4 ? L.nkb : 4;
+        it.K = K; it.k0 = 0;
+        it.k_valid = K < 64 * it.n_a ? K : 64 * it.n_a;
+        it.w_off = ml.L[l].m_w + (int64_t)h * 128 * K;
+        it.b_off = ml.L[l].m_b + h * 128;
+        if (L.kind == LK_VIEWS) {          // encoded-dirs columns of the view layer: separate item, no bias
+          DwItem& d2 = plan.it[n++];
+          d2 = it;
+          d2.a_blk = L.s_in + 4; d2.n_a = 1; d2.k0 = STAR_W; d2.k_valid = K - STAR_W; d2.b_off = -1;
+        }
+      }
+    }
+    plan.n_items = n;
+    int splits = sms / n;
+    if (splits < 1) splits = 1;
+    if ((int64_t)splits > ntiles) splits = (int)ntiles;
+    plan.splits = splits;
+    const size_t smem = (size_t)(DW_NSTAGE * DW_STAGE_BLOCKS + 1) * TC_BLOCK_BYTES + 256 + 1024;
+    auto kern = fp16 ? dw_tc_kernel<true> : dw_tc_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
+    kern<<<n * splits, DW_THREADS, smem, st>>>(plan, tl.stash_blocks, tl.gstash_blocks, (const uint8_t*)stash,
+                                               (const uint8_t*)gstash, ntiles, grad_flat, nullptr);
+    int rc = star_check_launch();
+    if (rc) return rc;
+  }
+  // ---- 3. heads
+  {
+    int blocks = (int)(ntiles < 2 * sms ? ntiles : 2 * sms);
+    head_grad_tc_kernel<<<blocks, 256, 0, st>>>(tl, ml, (const uint8_t*)stash, d_raw_alpha, d_raw_rgb, ray_stride, S, M,
+                                                fp16, grad_flat);
+    return star_check_launch();
+  }
+}

@@ -337,10 +337,9 @@ class NerfRaw(Function):
         p12 = _c(pose12.detach()) if pose12 is not None else None
         chunks = _ray_chunks(R, S)
         stashes = []
-        # activations are stashed by the fp32 forward only; the bf16 (tcgen05) forward keeps nothing and its
-        # backward re-runs the fp32 forward per ray chunk (gradient of the fp32 function at the same weights)
-        keep = need_grad and precision == _capi.PREC_F32 and \
-            L.star_stash_bytes(C.byref(d), R * S) <= STASH_BUDGET_BYTES
+        # activations needed by the backward are stashed by the forward of the same tier (fp32: per-GEMM inputs in
+        # fp32; tensor-core tiers: 16-bit swizzled blocks); over budget, the backward re-runs the forward per chunk
+        keep = need_grad and L.star_stash_bytes(C.byref(d), R * S) <= STASH_BUDGET_BYTES
         for (a, b) in chunks:
             st = None
             if keep:
@@ -355,8 +354,8 @@ class NerfRaw(Function):
             _prof_end("mlp_forward_stash" if st is not None else "mlp_forward", e0, (b - a) * S)
             _count()
         if need_grad:
-            ctx.rt, ctx.precision, ctx.chunks, ctx.stashes = rt, _capi.PREC_F32, chunks, stashes if keep else None
-            ctx.flat, ctx.packed = rt.refresh(_capi.PREC_F32)
+            ctx.rt, ctx.precision, ctx.chunks, ctx.stashes = rt, precision, chunks, stashes if keep else None
+            ctx.flat, ctx.packed = flat, packed
             ctx.scales = (sc_xyz, sc_dir)
             ctx.save_for_backward(pts, viewdirs, p12 if p12 is not None else torch.empty(0, device=dev))
             ctx.shapes = [p.shape for p in params]

@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="render", choices=["render", "train"])
-    ap.add_argument("--precision", default=os.environ.get("STAR_B200_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("STAR_B200_PRECISION", "bf16"), choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--hw", type=int, default=RENDER_HW, help="render mode: view is hw x hw rays")
     ap.add_argument("--train-rays", type=int, default=TRAIN_RAYS)
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays of the bounded CPU sample (0 = auto)")
@@ -159,7 +159,8 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n = args.cpu_sample_rays or (2048 if args.mode == "render" else 1024)
+    # each step is a bounded sample; the whole --steps K run is sized to stay within a few minutes
+    n = args.cpu_sample_rays or max(256, cpu_sample_default(args.mode, threads) * 3 // max(3, args.steps) // 256 * 256)
     fn = cpu_render_rays_per_s if args.mode == "render" else cpu_train_rays_per_s
     for _ in range(min(args.warmup, 1)):
         fn(max(64, n // 8), threads)
@@ -178,6 +179,12 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_sample_default(mode, threads):
+    """Bounded CPU sample sized for roughly 10-20 s of host work (about 120 rays/s/core render, 40 train)."""
+    per_core = 120 if mode == "render" else 40
+    return int(max(512, min(65536, 12 * per_core * threads)) // 256 * 256)
 
 
 def metric_name(mode):
@@ -246,8 +253,7 @@ def run_b200(args):
             loss = ((out["rgb"] - target) ** 2).mean() + ((out["rgb0"] - target) ** 2).mean()
             loss.backward()
             if world > 1:
-                flat = torch.cat([p.grad.reshape(-1) for p in params])
-                dist.all_reduce(flat)
+                star_b200.parallel.allreduce_gradients(params)     # one NCCL all-reduce of the flat gradient
             return loss
         with torch.no_grad():
             pts, z = R_.sample_pts(ro, rd, NEAR, FAR, NC, perturb=0, is_train=False)
@@ -326,15 +332,18 @@ def run_b200(args):
                 os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
             peak_tf = (peak["bf16_tflops_sustained"] if peak else 1400.0)
             ach = tot_samples * F_STATIC / (tot_ms * 1e-3) / 1e12
+            # dram__bytes_read+write per launch from the committed ncu capture (profiles/r1c_mlp_fwd_tc.md:
+            # 7.83 MB per 524288-sample launch = 14.9 B/sample), scaled to this run's average launch
+            traffic = 14.93 * tot_samples / n_l if args.precision != "fp32" else None
             roof = {"bound": "tensor", "kernel": "star_mlp_forward (%s)" % args.precision, "achieved": ach,
-                    "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                    "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peak else "fallback",
                     "launches": n_l, "avg_launch_ms": tot_ms / n_l,
                     "share_of_step": tot_ms / (ms * args.steps)}
         line = {
             "metric": metric_name(args.mode), "value": total_rays / (ms * 1e-3), "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision],
             "data": "synthetic", "config": workload_config(args, args.precision),
             "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 24 * R,
                     "d2h_bytes_per_step": (4 if train else 20 * R)},
@@ -342,7 +351,7 @@ def run_b200(args):
         }
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            n = args.cpu_sample_rays or (2048 if not train else 1024)
+            n = args.cpu_sample_rays or cpu_sample_default(args.mode, threads)
             fn = cpu_train_rays_per_s if train else cpu_render_rays_per_s
             fn(max(64, n // 8), threads)
             v, dt = fn(n, threads)
@@ -355,6 +364,11 @@ def run_b200(args):
 
 def main():
     args = parse()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl != "reference":
+        # plain `python bench.py --gpus N`: re-launch as one process per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args)
     else:
