@@ -241,6 +241,12 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             group_start = true;
           }
         }
+        // the tile's last epilogue phase (G_in for static nets) also arrives on a_ready[]: consume those phases so
+        // that the parity bookkeeping stays in step with the barriers across tiles
+        for (int kb = 0; ph < n_phases && kb < phases[ph].n_wait; ++kb) {
+          mbar_wait(bar(BAR_A_READY(kb)), (a_par >> kb) & 1u, dbg, 5);
+          a_par ^= 1u << kb;
+        }
       }
     }
   } else {
@@ -544,21 +550,35 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
 }
 
 // ============================================================================================ head gradients
-// d alpha_w[k] = sum_m d_alpha[m] h[m][k]  (h = stashed input of feature_linear), d rgb_w[c][n] = sum_m d_rgb[m][c] relu(h2)[m][n]
-__device__ __forceinline__ float stash_elem(const uint8_t* blk, int row, int col, bool fp16) {
-  const uint16_t bits = *reinterpret_cast<const uint16_t*>(blk + sw128_off(row, col));
-  return fp16 ? __half2float(__ushort_as_half(bits)) : __uint_as_float((uint32_t)bits << 16);
+// d alpha_w[k] = sum_m d_alpha[m] h[m][k]  (h = stashed input of feature_linear), d rgb_w[c][n] = sum_m d_rgb[m][c] relu(h2)[m][n].
+// 256 threads = 8 row groups x 32 sixteen-byte chunks: thread (rg, ch) owns 8 consecutive columns of h (and of
+// relu(h2) when ch < 16) for rows rg*16..rg*16+15 of every tile; partial sums stay in registers across tiles.
+__device__ __forceinline__ void unpack8(const uint4& v, bool fp16, float (&x)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (fp16) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      x[2 * i] = f.x; x[2 * i + 1] = f.y;
+    } else {
+      x[2 * i] = __uint_as_float(w[i] << 16);
+      x[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256)
 head_grad_tc_kernel(const TcLayout lay, MlpLayout ml, const uint8_t* __restrict__ stash, const float* __restrict__ d_raw_alpha,
                     const float* __restrict__ d_raw_rgb, int64_t ray_stride, int S, int64_t M, int fp16,
                     float* __restrict__ grad_flat) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, rg = tid >> 5, ch = tid & 31;
   const int64_t ntiles = (M + 127) / 128;
   const int F = lay.n_layers - 2, V = lay.n_layers - 1;
-  float aw = 0.f, ab = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+  float aw[8], rw[3][8], ab = 0.f, rb[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { aw[j] = 0.f; rw[0][j] = 0.f; rw[1][j] = 0.f; rw[2][j] = 0.f; }
   __shared__ float s_d[128][4];
+  __shared__ float s_red[8][32][33];
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     __syncthreads();
     if (tid < 128) {
@@ -572,29 +592,60 @@ head_grad_tc_kernel(const TcLayout lay, MlpLayout ml, const uint8_t* __restrict_
     }
     __syncthreads();
     const uint8_t* tile = stash + (size_t)t * lay.stash_blocks * TC_BLOCK_BYTES;
-    const uint8_t* hb = tile + (size_t)(lay.L[F].s_in + (tid >> 6)) * TC_BLOCK_BYTES;      // column tid of h
-    const uint8_t* h2b = tile + (size_t)(lay.L[V].s_out + ((tid & 127) >> 6)) * TC_BLOCK_BYTES;
-    for (int m = 0; m < 128; ++m) {
-      const float a = s_d[m][0];
-      aw = fmaf(a, stash_elem(hb, m, tid & 63, fp16), aw);
-      if (tid < 128) {
-        const float x = stash_elem(h2b, m, tid & 63, fp16);
-        r0 = fmaf(s_d[m][1], x, r0); r1 = fmaf(s_d[m][2], x, r1); r2 = fmaf(s_d[m][3], x, r2);
+    const uint8_t* hb = tile + (size_t)(lay.L[F].s_in + (ch >> 3)) * TC_BLOCK_BYTES;
+    const uint8_t* h2b = tile + (size_t)(lay.L[V].s_out + ((ch & 15) >> 3)) * TC_BLOCK_BYTES;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int m = rg * 16 + i;
+      const uint32_t off = (uint32_t)m * 128u + ((((uint32_t)ch & 7u) ^ ((uint32_t)m & 7u)) << 4);
+      const float4 d = *reinterpret_cast<const float4*>(&s_d[m][0]);
+      float x[8];
+      unpack8(*reinterpret_cast<const uint4*>(hb + off), fp16 != 0, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) aw[j] = fmaf(d.x, x[j], aw[j]);
+      if (ch < 16) {
+        unpack8(*reinterpret_cast<const uint4*>(h2b + off), fp16 != 0, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          rw[0][j] = fmaf(d.y, x[j], rw[0][j]);
+          rw[1][j] = fmaf(d.z, x[j], rw[1][j]);
+          rw[2][j] = fmaf(d.w, x[j], rw[2][j]);
+        }
       }
-      if (tid == 0) { ab += a; b0 += s_d[m][1]; b1 += s_d[m][2]; b2 += s_d[m][3]; }
+      if (ch == 31) { ab += d.x; rb[0] += d.y; rb[1] += d.z; rb[2] += d.w; }
     }
   }
-  atomicAdd(&grad_flat[ml.m_alpha_w + tid], aw);
-  if (tid < 128) {
-    atomicAdd(&grad_flat[ml.m_rgb_w + 0 * STAR_WV + tid], r0);
-    atomicAdd(&grad_flat[ml.m_rgb_w + 1 * STAR_WV + tid], r1);
-    atomicAdd(&grad_flat[ml.m_rgb_w + 2 * STAR_WV + tid], r2);
+  // reduce the 8 row groups through shared memory, then one atomic per output element and CTA
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s_red[rg][ch][j] = aw[j];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_red[rg][ch][8 + c * 8 + j] = rw[c][j];
+  s_red[rg][ch][32] = (ch == 31) ? ab : 0.f;
+  __syncthreads();
+  for (int e = tid; e < 32 * 32; e += 256) {
+    const int c2 = e >> 5, k = e & 31;     // chunk, slot
+    float v = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) v += s_red[g][c2][k];
+    if (k < 8) atomicAdd(&grad_flat[ml.m_alpha_w + c2 * 8 + k], v);
+    else if (c2 < 16) atomicAdd(&grad_flat[ml.m_rgb_w + ((k - 8) >> 3) * STAR_WV + c2 * 8 + ((k - 8) & 7)], v);
   }
   if (tid == 0) {
-    atomicAdd(&grad_flat[ml.m_alpha_b], ab);
-    atomicAdd(&grad_flat[ml.m_rgb_b + 0], b0);
-    atomicAdd(&grad_flat[ml.m_rgb_b + 1], b1);
-    atomicAdd(&grad_flat[ml.m_rgb_b + 2], b2);
+    float v = 0.f;
+    for (int g = 0; g < 8; ++g) v += s_red[g][31][32];
+    atomicAdd(&grad_flat[ml.m_alpha_b], v);
+  }
+  // rgb bias: sum of d_rgb
+  __syncthreads();
+  if (ch == 31) { s_red[rg][0][0] = rb[0]; s_red[rg][0][1] = rb[1]; s_red[rg][0][2] = rb[2]; }
+  __syncthreads();
+  if (tid < 3) {
+    float v = 0.f;
+    for (int g = 0; g < 8; ++g) v += s_red[g][0][tid];
+    atomicAdd(&grad_flat[ml.m_rgb_b + tid], v);
   }
 }
 

@@ -323,23 +323,29 @@ def run_b200(args):
         total_rays = R * world
         # roofline of the dominant kernel (the fused MLP forward): algorithmic FLOPs / event time
         roof = None
-        key = "mlp_forward"
-        if prof and key in prof and prof[key]:
-            tot_ms = sum(a.elapsed_time(b) for a, b, _ in prof[key])
-            tot_samples = sum(n for _, _, n in prof[key])
-            n_l = len(prof[key])
+        parts = {}
+        for k, evs in (prof or {}).items():
+            if evs:
+                parts[k] = {"ms": sum(a.elapsed_time(b) for a, b, _ in evs), "samples": sum(n for _, _, n in evs),
+                            "launches": len(evs)}
+        if parts:
+            # dominant C-ABI call of the step: its algorithmic FLOPs (MLP 2*MAC per sample; backward = dX + dW = 2x)
+            key = max(parts, key=lambda k: parts[k]["ms"])
+            flop_per_sample = F_STATIC * (2.0 if key == "mlp_backward" else 1.0)
+            tot_ms, tot_samples, n_l = parts[key]["ms"], parts[key]["samples"], parts[key]["launches"]
             peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(
                 os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
             peak_tf = (peak["bf16_tflops_sustained"] if peak else 1400.0)
-            ach = tot_samples * F_STATIC / (tot_ms * 1e-3) / 1e12
+            ach = tot_samples * flop_per_sample / (tot_ms * 1e-3) / 1e12
             # dram__bytes_read+write per launch from the committed ncu capture (profiles/r1c_mlp_fwd_tc.md:
             # 7.83 MB per 524288-sample launch = 14.9 B/sample), scaled to this run's average launch
-            traffic = 14.93 * tot_samples / n_l if args.precision != "fp32" else None
-            roof = {"bound": "tensor", "kernel": "star_mlp_forward (%s)" % args.precision, "achieved": ach,
+            traffic = 14.93 * tot_samples / n_l if (args.precision != "fp32" and key == "mlp_forward") else None
+            roof = {"bound": "tensor", "kernel": "star_%s (%s)" % (key, args.precision), "achieved": ach,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peak else "fallback",
                     "launches": n_l, "avg_launch_ms": tot_ms / n_l,
-                    "share_of_step": tot_ms / (ms * args.steps)}
+                    "share_of_step": tot_ms / (ms * args.steps),
+                    "calls_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in parts.items()}}
         line = {
             "metric": metric_name(args.mode), "value": total_rays / (ms * 1e-3), "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,

@@ -162,7 +162,7 @@ def test_tc_training_step_runs_and_grads_match_fp32_path():
 
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
 @pytest.mark.parametrize("R,S,dyn,with_pose", [(8, 32, False, False), (70, 33, False, False), (40, 48, True, True),
-                                               (300, 64, True, True)])
+                                               (300, 64, True, True), (1250, 64, True, True)])   # last: 625 tiles, > 4 per CTA
 def test_tc_backward_matches_rounding_model_and_fp64(R, S, dyn, with_pose, prec):
     """Tensor-core backward (dX chain + dW GEMMs over the 16-bit stash).  Two references, both fp64 autograd:
       * the oracle's operand-rounding model of the forward with straight-through gradients -- the kernel must
