@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--train-rays", type=int, default=TRAIN_RAYS)
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-extra", action="store_true",
+                    help="render mode: skip the extra 4096-ray training-step measurement reported under \"train\"")
     return ap.parse_args()
 
 
@@ -206,6 +208,32 @@ def workload_config(args, precision):
 # ------------------------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
     import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = measure(args)
+    if args.mode == "render" and not args.no_train_extra:
+        # the metric also names the training step: measure it on the same box and attach it to the line
+        a2 = argparse.Namespace(**vars(args))
+        a2.mode, a2.no_cpu_baseline = "train", True
+        t = measure(a2)
+        if rank == 0:
+            line["train"] = {k: t[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline", "gpu_launches")}
+            line["train"]["config"] = t["config"]["workload"]
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure(args):
+    """One timed measurement (render or train per args.mode); returns the JSON line as a dict on rank 0."""
+    import torch.distributed as dist
     import star_b200
     from star_b200 import functional as F_
     from star_b200.models import rendering__ as R_
@@ -214,12 +242,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
 
     net = star_b200.STaR(ref_harness.make_args(num_vehicles=0, N_importance=NI, chunk=8192, white_bkgd=True))
     net.load_state_dict(make_params())
@@ -363,9 +386,8 @@ def run_b200(args):
             v, dt = fn(n, threads)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
                                     "sample": "%d random rays of the same workload, %.1f s" % (n, dt)}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        return line
+    return None
 
 
 def main():
