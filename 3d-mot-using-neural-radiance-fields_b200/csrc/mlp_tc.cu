@@ -40,12 +40,16 @@ struct EpiCtx {
 // conversion) -> swizzled smem -> proxy fence -> one mbarrier arrival per warp.
 // KIND: LK_IN / LK_FC0 / LK_FC1 (ReLU), LK_OUT (affine + alpha head partial in h[0]), LK_FEAT (affine),
 // LK_VIEWS (ReLU, N = 128, rgb head partials in h[0..2], no A output).
-template <int KIND, bool FP16>
+template <int KIND, bool FP16, bool STASH>
 __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3]) {
   constexpr int NCH = (KIND == LK_VIEWS) ? 2 : 4;
   constexpr bool RELU = (KIND == LK_IN || KIND == LK_FC0 || KIND == LK_FC1);
   uint32_t r[2][TC_CPT];
   tmem_ld16(c.tcol, r[0]);
+  // bias of chunk kb+1 is fetched (shared memory, broadcast) while chunk kb's stores / proxy fence drain
+  float4 bq[TC_CPT / 4];
+#pragma unroll
+  for (int j4 = 0; j4 < TC_CPT / 4; ++j4) bq[j4] = *reinterpret_cast<const float4*>(c.bias + c.cg * TC_CPT + 4 * j4);
 #pragma unroll
   for (int kb = 0; kb < NCH; ++kb) {
     tmem_wait_ld();
@@ -54,13 +58,16 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3]) {
     float v[TC_CPT];
 #pragma unroll
     for (int j4 = 0; j4 < TC_CPT / 4; ++j4) {
-      const float4 b = *reinterpret_cast<const float4*>(c.bias + col0 + 4 * j4);
       v[4 * j4 + 0] = __uint_as_float(r[kb & 1][4 * j4 + 0]);
       v[4 * j4 + 1] = __uint_as_float(r[kb & 1][4 * j4 + 1]);
       v[4 * j4 + 2] = __uint_as_float(r[kb & 1][4 * j4 + 2]);
       v[4 * j4 + 3] = __uint_as_float(r[kb & 1][4 * j4 + 3]);
-      add_f32x2(v[4 * j4 + 0], v[4 * j4 + 1], b.x, b.y);
-      add_f32x2(v[4 * j4 + 2], v[4 * j4 + 3], b.z, b.w);
+      add_f32x2(v[4 * j4 + 0], v[4 * j4 + 1], bq[j4].x, bq[j4].y);
+      add_f32x2(v[4 * j4 + 2], v[4 * j4 + 3], bq[j4].z, bq[j4].w);
+    }
+    if (kb + 1 < NCH) {   // next chunk's bias: in flight during this chunk's convert / store / fence
+#pragma unroll
+      for (int j4 = 0; j4 < TC_CPT / 4; ++j4) bq[j4] = *reinterpret_cast<const float4*>(c.bias + col0 + 64 + 4 * j4);
     }
     if (KIND == LK_OUT) {            // alpha head (nerf.py:151) on the fp32 h
 #pragma unroll
@@ -74,10 +81,10 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3]) {
         h[1] = fmaf(x, c.head_w[STAR_WV + col0 + j], h[1]);
         h[2] = fmaf(x, c.head_w[2 * STAR_WV + col0 + j], h[2]);
       }
-      if (c.stash_out != nullptr) store_row16<FP16, true>(0u, c.row, c.cg * 2, v, c.stash_out + kb * TC_KB_BYTES);
+      if (STASH) store_row16<FP16, true>(0u, c.row, c.cg * 2, v, c.stash_out + kb * TC_KB_BYTES);
     } else {
-      store_row16<FP16, RELU>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v,
-                              c.stash_out != nullptr ? c.stash_out + kb * TC_KB_BYTES : nullptr);
+      if (STASH) store_row16<FP16, RELU>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v, c.stash_out + kb * TC_KB_BYTES);
+      else store_row16<FP16, RELU>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v);
       fence_proxy_async_smem();      // this thread's A writes -> async proxy (tcgen05.mma operand reads)
       tc_fence_before();
       __syncwarp();
@@ -87,7 +94,7 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3]) {
 }
 
 // ============================================================================================ forward
-template <bool FP16>
+template <bool FP16, bool STASH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const float* __restrict__ pts,
                   const float* __restrict__ viewdirs, const float* __restrict__ pose12,
@@ -191,6 +198,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     EpiCtx ctx;
     ctx.sA = sA; ctx.a_ready0 = bar(BAR_A_READY(0));
     ctx.row = row; ctx.cg = cg; ctx.lane = lane;
+    ctx.stash_out = nullptr;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t gi = tile * TC_M + row;
       const bool valid = gi < M;
@@ -219,12 +227,12 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         else if (cg == 1) encode_slice<16, 63>(p, sc_xyz, e);
         else if (cg == 2) encode_slice<32, 63>(p, sc_xyz, e);
         else encode_slice<48, 63>(p, sc_xyz, e);
-        uint8_t* st_tile = stash != nullptr ? stash + (size_t)tile * (size_t)lay.stash_blocks * TC_BLOCK_BYTES : nullptr;
-        uint8_t* st_dirs = st_tile != nullptr ? st_tile + (size_t)(lay.L[lay.n_layers - 1].s_in + 4) * TC_BLOCK_BYTES : nullptr;
-        store_row16<FP16, false>(sA, row, cg * 2, e, st_tile != nullptr ? st_tile + (size_t)lay.L[0].s_in * TC_BLOCK_BYTES : nullptr);
+        uint8_t* st_tile = STASH ? stash + (size_t)tile * (size_t)lay.stash_blocks * TC_BLOCK_BYTES : nullptr;
+        uint8_t* st_dirs = STASH ? st_tile + (size_t)(lay.L[lay.n_layers - 1].s_in + 4) * TC_BLOCK_BYTES : nullptr;
+        store_row16<FP16, false>(sA, row, cg * 2, e, STASH ? st_tile + (size_t)lay.L[0].s_in * TC_BLOCK_BYTES : nullptr);
         if (cg == 1) { encode_slice<0, 27>(dv, sc_dir, e); store_row16<FP16, false>(sAD, row, 0, e, st_dirs); }
         if (cg == 2) { encode_slice<16, 27>(dv, sc_dir, e); store_row16<FP16, false>(sAD, row, 2, e, st_dirs); }
-        if (st_dirs != nullptr && (cg == 0 || cg == 3)) {   // zero the unused half of the dirs block once per tile
+        if (STASH && (cg == 0 || cg == 3)) {   // zero the unused half of the dirs block once per tile
           const float z[16] = {0.f};
           store_row16<FP16, false>(0u, row, cg == 0 ? 4 : 6, z, st_dirs);
         }
@@ -244,9 +252,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         tc_fence_after();
         ctx.tcol = tmem_base + (((uint32_t)(q * 32)) << 16) + (L.region ? 256u : 0u) + (uint32_t)(cg * TC_CPT);
         ctx.bias = s_small + L.bias_off;
-        ctx.stash_out = stash != nullptr
-                            ? stash + ((size_t)tile * (size_t)lay.stash_blocks + (size_t)L.s_out) * TC_BLOCK_BYTES
-                            : nullptr;
+        if (STASH) ctx.stash_out = stash + ((size_t)tile * (size_t)lay.stash_blocks + (size_t)L.s_out) * TC_BLOCK_BYTES;
         float h[3] = {0.f, 0.f, 0.f};
         if (dbg_mode & 1) {
           for (int kb = 0; kb < (L.N >> 6) && L.kind != LK_VIEWS; ++kb) {
@@ -254,12 +260,12 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             if (lane == 0) mbar_arrive(bar(BAR_A_READY(kb)));
           }
         } else if (L.kind == LK_FC0 || L.kind == LK_FC1 || L.kind == LK_IN) {
-          epilogue_layer<LK_FC0, FP16>(ctx, h);
+          epilogue_layer<LK_FC0, FP16, STASH>(ctx, h);
         } else if (L.kind == LK_FEAT) {
-          epilogue_layer<LK_FEAT, FP16>(ctx, h);
+          epilogue_layer<LK_FEAT, FP16, STASH>(ctx, h);
         } else if (L.kind == LK_OUT) {
           ctx.head_w = s_small + lay.off_alpha_w;
-          epilogue_layer<LK_OUT, FP16>(ctx, h);
+          epilogue_layer<LK_OUT, FP16, STASH>(ctx, h);
           // combine the 4 column groups of each row: groups 1..3 park their partial, group 0 finishes
           if (cg != 0) part(row, cg)[0] = h[0];
           named_bar_sync(1, TC_EPI_THREADS);
@@ -267,7 +273,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             raw_alpha[out_idx] = h[0] + part(row, 1)[0] + part(row, 2)[0] + part(row, 3)[0] + s_small[lay.off_alpha_b];
         } else {   // LK_VIEWS
           ctx.head_w = s_small + lay.off_rgb_w;
-          epilogue_layer<LK_VIEWS, FP16>(ctx, h);
+          epilogue_layer<LK_VIEWS, FP16, STASH>(ctx, h);
           if (cg != 0) {
             float* d = part(row, cg);
             d[1] = h[0]; d[2] = h[1]; d[3] = h[2];
@@ -385,7 +391,8 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const float* pts, co
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   const TcSmem sl = tc_smem_layout(tl.small_bytes);
   if (((uintptr_t)packed & 15) != 0) return STAR_E_ALIGN;
-  auto kern = fp16 ? mlp_fwd_tc_kernel<true> : mlp_fwd_tc_kernel<false>;
+  auto kern = stash != nullptr ? (fp16 ? mlp_fwd_tc_kernel<true, true> : mlp_fwd_tc_kernel<false, true>)
+                               : (fp16 ? mlp_fwd_tc_kernel<true, false> : mlp_fwd_tc_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
   if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
   static int dbg_mode = -1;

@@ -324,7 +324,7 @@ class NerfRaw(Function):
     (models/nerf.py:112-179).  pose12 = [R(3x3) row-major | t] or None."""
 
     @staticmethod
-    def forward(ctx, rt, precision, pts, viewdirs, pose12, sc_xyz, sc_dir, *params):
+    def forward(ctx, rt, precision, grad_mode, pts, viewdirs, pose12, sc_xyz, sc_dir, *params):
         pts, viewdirs = _c(pts), _c(viewdirs)
         R, S = pts.shape[0], pts.shape[1]
         dev = pts.device
@@ -333,7 +333,9 @@ class NerfRaw(Function):
         L = _capi.lib()
         raw_alpha = torch.empty((R, S), device=dev)
         raw_rgb = torch.empty((R, S, 3), device=dev)
-        need_grad = any(ctx.needs_input_grad[7:]) or (pose12 is not None and ctx.needs_input_grad[4])
+        # ctx.needs_input_grad ignores torch.no_grad(): `grad_mode` (torch.is_grad_enabled() at the call site) decides
+        # whether anything is kept for a backward pass at all
+        need_grad = grad_mode and (any(ctx.needs_input_grad[8:]) or (pose12 is not None and ctx.needs_input_grad[5]))
         p12 = _c(pose12.detach()) if pose12 is not None else None
         chunks = _ray_chunks(R, S)
         stashes = []
@@ -411,10 +413,10 @@ class NerfRaw(Function):
             grads.append(grad_flat[off:off + n].view(shp))
             off += n
         g_pose = None
-        if p12 is not None and ctx.needs_input_grad[4]:
+        if p12 is not None and ctx.needs_input_grad[5]:
             # Euclidean gradient w.r.t. [R | t]:  dR = sum g p^T + sum h d^T,  dt = sum g
             g_pose = torch.cat([pose_acc[3:12] + pose_acc[15:24], pose_acc[0:3]])
-        return (None, None, None, None, g_pose, None, None, *grads)
+        return (None, None, None, None, None, g_pose, None, None, *grads)
 
 
 class Pose7ToMat12(Function):

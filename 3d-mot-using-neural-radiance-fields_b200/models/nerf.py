@@ -52,7 +52,7 @@ class NeRF(nn.Module):
         """RAW outputs; pose12 moves samples into the object frame inside the kernel (K2)."""
         sc_xyz = self.embedder.scale(step, pts.device, pad_to=64)
         sc_dir = self.embedder_dirs.scale(step, pts.device, pad_to=32)
-        return F_.NerfRaw.apply(self._rt, self._prec(), pts, viewdirs, pose12, sc_xyz, sc_dir,
+        return F_.NerfRaw.apply(self._rt, self._prec(), torch.is_grad_enabled(), pts, viewdirs, pose12, sc_xyz, sc_dir,
                                 *self._rt.ordered_params())
 
     def forward(self, pts, viewdirs, z_vals=None, rays_d=None, step=None, time=None):
