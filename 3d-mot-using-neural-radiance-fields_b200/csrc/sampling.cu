@@ -211,9 +211,24 @@ extern "C" int star_invert_cdf(const float* bins, const float* cdf, const float*
 
 // ------------------------------------------------------------------------------------------ a10
 // z_mid -> sample_pdf -> sort(cat(z_vals, z_samples)) -> z_std, pts.  One warp per ray.
-// smem per warp: cdf[nb] | bins[nb] | zall[P]   (P = next pow2 >= Nc+Ni, padded with +inf)
+// smem per warp: cdf[nb] | bins[nb] | zc[Nc] | zs[P] | zall[Nf]   (P = next pow2 >= Ni, padded with +inf)
+// The concatenation is sorted as a MERGE: the coarse samples are sorted by construction, the fine samples are
+// sorted whenever u is (always in eval mode: inverse-CDF sampling is monotone); only otherwise (random u in
+// training) are the Ni fine samples bitonic-sorted first.  Every element then finds its output slot with one
+// binary search in the other list (coarse before fine on ties; torch.sort returns values only, :136,279).
 // GIVEN = true: the fine samples are supplied in z_samples (read, not written) and only the merge,
 // z_std and pts are computed (star_merge_samples).
+__device__ __forceinline__ int count_less(const float* a, int n, float x) {      // # a[i] <  x, a sorted
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < x) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+__device__ __forceinline__ int count_less_equal(const float* a, int n, float x) {  // # a[i] <= x, a sorted
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] <= x) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
 template <bool GIVEN>
 __global__ void hierarchical_kernel(const float* __restrict__ z_vals, const float* __restrict__ weights,
                                     const float* __restrict__ u, const float* __restrict__ u_det,
@@ -224,17 +239,19 @@ __global__ void hierarchical_kernel(const float* __restrict__ z_vals, const floa
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int nb = Nc - 1, Nf = Nc + Ni;
-  float* cdf = smem + (size_t)warp * (2 * nb + P);
+  float* cdf = smem + (size_t)warp * (2 * nb + Nc + P + Nf);
   float* sb = cdf + nb;
-  float* za = sb + nb;
+  float* zc = sb + nb;
+  float* zs = zc + Nc;
+  float* za = zs + P;
   for (int r = blockIdx.x * wpb + warp; r < R; r += gridDim.x * wpb) {
     const float* zr = z_vals + (int64_t)r * Nc;
     if (!GIVEN) {
       build_cdf_warp(weights + (int64_t)r * Nc + 1, Nc - 2, cdf, lane);  // weights[..., 1:-1]  (:131,274)
       for (int k = lane; k < nb; k += 32) sb[k] = __fmul_rn(0.5f, __fadd_rn(zr[k + 1], zr[k]));  // z_mid (:128)
     }
-    for (int k = lane; k < Nc; k += 32) za[k] = zr[k];
-    for (int k = Nf + lane; k < P; k += 32) za[k] = __int_as_float(0x7f800000);
+    for (int k = lane; k < Nc; k += 32) zc[k] = zr[k];
+    for (int k = Ni + lane; k < P; k += 32) zs[k] = __int_as_float(0x7f800000);
     __syncwarp();
     float sum = 0.f;
     for (int j = lane; j < Ni; j += 32) {
@@ -247,32 +264,46 @@ __global__ void hierarchical_kernel(const float* __restrict__ z_vals, const floa
         s = invert_one(cdf, sb, nb, uu, i0, b0, a0);
         z_samples[(int64_t)r * Ni + j] = s;
       }
-      za[Nc + j] = s;
+      zs[j] = s;
       sum += s;
     }
     // z_std = std(z_samples, unbiased=False)   (:144,296)
     const float mean = warp_sum(sum) / (float)Ni;
     __syncwarp();
     float var = 0.f;
+    bool sorted = true;
     for (int j = lane; j < Ni; j += 32) {
-      const float d = za[Nc + j] - mean;
+      const float d = zs[j] - mean;
       var += d * d;
+      if (j + 1 < Ni && zs[j] > zs[j + 1]) sorted = false;
     }
     var = warp_sum(var) / (float)Ni;
     if (lane == 0) z_std[r] = sqrtf(var);
-    // bitonic sort of za[0..P)   (torch.sort of the concatenation, :136,279 -- values only)
-    for (int k = 2; k <= P; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        __syncwarp();
-        for (int i = lane; i < P; i += 32) {
-          const int l = i ^ j;
-          if (l > i) {
-            const float a = za[i], b = za[l];
-            const bool up = ((i & k) == 0);
-            if ((a > b) == up) { za[i] = b; za[l] = a; }
+    if (!__all_sync(STAR_FULL_MASK, sorted)) {
+      // bitonic sort of zs[0..P)
+      for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          __syncwarp();
+          for (int i = lane; i < P; i += 32) {
+            const int l = i ^ j;
+            if (l > i) {
+              const float a = zs[i], b = zs[l];
+              const bool up = ((i & k) == 0);
+              if ((a > b) == up) { zs[i] = b; zs[l] = a; }
+            }
           }
         }
       }
+      __syncwarp();
+    }
+    // merge by rank
+    for (int i = lane; i < Nc; i += 32) {
+      const float v = zc[i];
+      za[i + count_less(zs, Ni, v)] = v;
+    }
+    for (int j = lane; j < Ni; j += 32) {
+      const float v = zs[j];
+      za[j + count_less_equal(zc, Nc, v)] = v;
     }
     __syncwarp();
     for (int k = lane; k < Nf; k += 32) z_all[(int64_t)r * Nf + k] = za[k];
@@ -297,10 +328,10 @@ extern "C" int star_hierarchical(const float* z_vals, const float* weights, cons
   if (R < 0 || Nc < 3 || Ni < 1 || Nc + Ni > 8192) return STAR_E_BAD_SHAPE;
   if (R == 0) return STAR_OK;
   int P = 2;
-  while (P < Nc + Ni) P <<= 1;
+  while (P < Ni) P <<= 1;
   int blocks, threads;
   size_t smem;
-  int rc = launch_cfg_warp_per_ray(R, sizeof(float) * (2 * (Nc - 1) + P), blocks, threads, smem);
+  int rc = launch_cfg_warp_per_ray(R, sizeof(float) * (2 * (Nc - 1) + Nc + P + Nc + Ni), blocks, threads, smem);
   if (rc) return rc;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(hierarchical_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -317,10 +348,10 @@ extern "C" int star_merge_samples(const float* z_vals, const float* z_samples, c
   if (R < 0 || Nc < 1 || Ni < 1 || Nc + Ni > 8192) return STAR_E_BAD_SHAPE;
   if (R == 0) return STAR_OK;
   int P = 2;
-  while (P < Nc + Ni) P <<= 1;
+  while (P < Ni) P <<= 1;
   int blocks, threads;
   size_t smem;
-  int rc = launch_cfg_warp_per_ray(R, sizeof(float) * (2 * (Nc - 1) + P), blocks, threads, smem);
+  int rc = launch_cfg_warp_per_ray(R, sizeof(float) * (2 * (Nc - 1) + Nc + P + Nc + Ni), blocks, threads, smem);
   if (rc) return rc;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(hierarchical_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
