@@ -22,10 +22,10 @@ __device__ __forceinline__ float sample_dist(const float* __restrict__ zr, int s
 }
 
 // alpha = 1 - exp(-softplus(raw) * dist)   (:301-303)
-__device__ __forceinline__ float alpha_of(float raw, float dist) { return 1.f - expf(-softplus_f(raw) * dist); }
+__device__ __forceinline__ float alpha_of(float raw, float dist) { return 1.f - fexp(-softplus_f(raw) * dist); }
 // d alpha / d raw
 __device__ __forceinline__ float dalpha_draw(float raw, float dist) {
-  return dist * expf(-softplus_f(raw) * dist) * softplus_grad_f(raw);
+  return dist * fexp(-softplus_f(raw) * dist) * softplus_grad_f(raw);
 }
 
 // exclusive prefix product of m over the warp given the running carry; updates carry
@@ -84,6 +84,69 @@ __global__ void composite_single_fwd_kernel(const float* __restrict__ raw_alpha,
       rgb_o[r * 3 + 0] = sr + bg;
       rgb_o[r * 3 + 1] = sg + bg;
       rgb_o[r * 3 + 2] = sb + bg;
+    }
+  }
+}
+
+// Even S: every lane owns two consecutive samples (8-byte loads / stores, one transmittance scan and one trip of
+// the loop per 64 samples) and the five per-ray sums share 11 shuffles (warp_sum4).
+__global__ void composite_single_fwd_x2_kernel(const float* __restrict__ raw_alpha, const float* __restrict__ raw_rgb,
+                                               const float* __restrict__ z_vals, const float* __restrict__ rays_d,
+                                               int R, int S, float far_dist, int white_bkgd,
+                                               float* __restrict__ rgb_o, float* __restrict__ disp_o,
+                                               float* __restrict__ acc_o, float* __restrict__ depth_o,
+                                               float* __restrict__ weights_o, float* __restrict__ dists_o) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < R; r += gridDim.x * wpb) {
+    const float norm = ray_norm(rays_d, r);
+    const int64_t row = (int64_t)r * S;
+    const float* zr = z_vals + row;
+    float carry = 1.f, sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
+    for (int base = 0; base < S; base += 64) {
+      const int s0 = base + 2 * lane;
+      const bool ok = s0 < S;   // S even: both samples of the pair are valid together
+      float2 z = make_float2(0.f, 0.f), ra = make_float2(0.f, 0.f);
+      float2 c01 = make_float2(0.f, 0.f), c23 = c01, c45 = c01;
+      if (ok) {
+        z = *reinterpret_cast<const float2*>(zr + s0);
+        ra = *reinterpret_cast<const float2*>(raw_alpha + row + s0);
+        const float2* cp = reinterpret_cast<const float2*>(raw_rgb + (row + s0) * 3);
+        c01 = cp[0]; c23 = cp[1]; c45 = cp[2];
+      }
+      float znext = __shfl_down_sync(STAR_FULL_MASK, z.x, 1);
+      if (lane == 31 && base + 64 < S) znext = zr[base + 64];
+      float2 dist = make_float2(0.f, 0.f), alpha = make_float2(0.f, 0.f);
+      if (ok) {
+        dist.x = (z.y - z.x) * norm;
+        dist.y = ((s0 + 1 == S - 1) ? far_dist : (znext - z.y)) * norm;
+        alpha.x = alpha_of(ra.x, dist.x);
+        alpha.y = alpha_of(ra.y, dist.y);
+      }
+      const float m0 = 1.f - alpha.x + 1e-10f, m1 = 1.f - alpha.y + 1e-10f;   // (alpha = 0 -> m = 1 when !ok)
+      const float T0 = excl_transmittance(ok ? m0 * m1 : 1.f, carry, lane);
+      if (ok) {
+        const float w0 = alpha.x * T0, w1 = alpha.y * (T0 * m0);
+        *reinterpret_cast<float2*>(weights_o + row + s0) = make_float2(w0, w1);
+        if (dists_o) *reinterpret_cast<float2*>(dists_o + row + s0) = dist;
+        sr += w0 * sigmoid_f(c01.x) + w1 * sigmoid_f(c23.y);
+        sg += w0 * sigmoid_f(c01.y) + w1 * sigmoid_f(c45.x);
+        sb += w0 * sigmoid_f(c23.x) + w1 * sigmoid_f(c45.y);
+        sd += w0 * z.x + w1 * z.y;
+        sa += w0 + w1;
+      }
+    }
+    sa = warp_sum(sa);
+    const float v = warp_sum4(sr, sg, sb, sd, lane);   // lanes 0-7: r, 8-15: g, 16-23: b, 24-31: depth
+    const float bg = white_bkgd ? (1.f - sa) : 0.f;                   // :360-361
+    if ((lane & 7) == 0) {
+      if (lane < 24) {
+        rgb_o[r * 3 + (lane >> 3)] = v + bg;
+      } else {
+        const float wsum = (sa >= 0.f) ? sa : 1e-7f;                  // :353-354
+        disp_o[r] = 1.f / fmaxf(1e-10f, v / wsum);                    // :355-357
+        depth_o[r] = v;
+        acc_o[r] = sa;
+      }
     }
   }
 }
@@ -160,7 +223,7 @@ __global__ void composite_single_bwd_kernel(const float* __restrict__ raw_alpha,
       suffix += __shfl_sync(STAR_FULL_MASK, incl, 0);
       if (ok) {
         const float m = 1.f - alpha + 1e-10f;
-        const float d_alpha = T * G - after / m;
+        const float d_alpha = T * G - fdiv(after, m);
         const float raw = ar[s];
         d_raw_alpha[(int64_t)r * S + s] = d_alpha * dalpha_draw(raw, sample_dist(zr, s, S, far_dist, norm));
         const float w = alpha * T;
@@ -183,7 +246,7 @@ struct RegRayAcc {
 
 __device__ __forceinline__ float bin_entropy_term(float a) {  // alpha*log(clamp) + (1-alpha)*log1p(-clamp) (:620-628)
   const float c = fminf(fmaxf(a, STAR_EPS_F32), 1.f - STAR_EPS_F32);
-  return a * logf(c) + (1.f - a) * log1pf(-c);
+  return a * flog(c) + (1.f - a) * flog1m(c);
 }
 
 // Layout helpers for the reference [R,V,S] / [R,V,S,3] dynamic tensors
@@ -197,7 +260,8 @@ __device__ __forceinline__ float chunk_inv_count(int r, int R, int chunk) {
   return 1.f / (float)n;
 }
 
-__global__ void composite_multi_fwd_kernel(const float* __restrict__ raw_alpha_s, const float* __restrict__ raw_rgb_s,
+template <int VT>
+__global__ void __launch_bounds__(128) composite_multi_fwd_kernel(const float* __restrict__ raw_alpha_s, const float* __restrict__ raw_rgb_s,
                                            const float* __restrict__ raw_alpha_d, const float* __restrict__ raw_rgb_d,
                                            const float* __restrict__ z_vals, const float* __restrict__ rays_d, int R,
                                            int V, int S, float far_dist, int white_bkgd, int chunk, StarMultiOut out,
@@ -208,12 +272,12 @@ __global__ void composite_multi_fwd_kernel(const float* __restrict__ raw_alpha_s
     const float norm = ray_norm(rays_d, r);
     const float* zr = z_vals + (int64_t)r * S;
     float cT = 1.f, cTs = 1.f, cTall = 1.f;
-    float cTd[STAR_MAX_V];
+    float cTd[VT];
     float s_rgb[3] = {0, 0, 0}, s_rgbs[3] = {0, 0, 0}, s_all[3] = {0, 0, 0};
     float s_depth = 0.f, s_acc = 0.f, s_depth_s = 0.f;
-    float s_rgbd[STAR_MAX_V][3], s_depth_d[STAR_MAX_V], mx[STAR_MAX_V];
+    float s_rgbd[VT][3], s_depth_d[VT], mx[VT];
 #pragma unroll
-    for (int v = 0; v < STAR_MAX_V; ++v) {
+    for (int v = 0; v < VT; ++v) {
       cTd[v] = 1.f; s_depth_d[v] = 0.f; mx[v] = -1.f;
       s_rgbd[v][0] = s_rgbd[v][1] = s_rgbd[v][2] = 0.f;
     }
@@ -235,9 +299,9 @@ __global__ void composite_multi_fwd_kernel(const float* __restrict__ raw_alpha_s
       // dynamic fields
       float mixd[3] = {0, 0, 0};
       float a_dsum = 0.f, sig_dsum = 0.f, ent_d = 0.f;
-      float a_dv[STAR_MAX_V], sig_dv[STAR_MAX_V];
+      float a_dv[VT], sig_dv[VT];
 #pragma unroll
-      for (int v = 0; v < STAR_MAX_V; ++v) {
+      for (int v = 0; v < VT; ++v) {
         if (v < V) {
           float a_d = 0.f, sg = 0.f, cd[3] = {0, 0, 0};
           if (ok) {
@@ -292,22 +356,22 @@ __global__ void composite_multi_fwd_kernel(const float* __restrict__ raw_alpha_s
         const float tc = fmaxf(tot, STAR_EPS_F32);
         float E;
         {
-          const float p = fmaxf(a_s / tc, STAR_EPS_F32);
-          E = p * logf(p);
+          const float p = fmaxf(fdiv(a_s, tc), STAR_EPS_F32);
+          E = p * flog(p);
         }
         const float sc = fmaxf(sig_s + sig_dsum, STAR_EPS_F32);
 #pragma unroll
-        for (int v = 0; v < STAR_MAX_V; ++v) {
+        for (int v = 0; v < VT; ++v) {
           if (v < V) {
-            const float p = fmaxf(a_dv[v] / tc, STAR_EPS_F32);
-            E += p * logf(p);
-            mx[v] = fmaxf(mx[v], sig_dv[v] / sc);
+            const float p = fmaxf(fdiv(a_dv[v], tc), STAR_EPS_F32);
+            E += p * flog(p);
+            mx[v] = fmaxf(mx[v], fdiv(sig_dv[v], sc));
           }
         }
         dvs += tot * E;
         const float cc = fminf(fmaxf(a_s, STAR_EPS_F32), 1.f - STAR_EPS_F32);
         Z += cc;
-        clogc += cc * logf(cc);
+        clogc += cc * flog(cc);
         sig_s_sum += sig_s;
       }
     }
@@ -319,7 +383,7 @@ __global__ void composite_multi_fwd_kernel(const float* __restrict__ raw_alpha_s
     Z = warp_sum(Z); clogc = warp_sum(clogc); sig_s_sum = warp_sum(sig_s_sum);
     float rayreg = 0.f;
 #pragma unroll
-    for (int v = 0; v < STAR_MAX_V; ++v) {
+    for (int v = 0; v < VT; ++v) {
       if (v < V) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) s_rgbd[v][c] = warp_sum(s_rgbd[v][c]);
@@ -342,7 +406,7 @@ __global__ void composite_multi_fwd_kernel(const float* __restrict__ raw_alpha_s
       }
       out.depth_static[r] = s_depth_s;
 #pragma unroll
-      for (int v = 0; v < STAR_MAX_V; ++v) {
+      for (int v = 0; v < VT; ++v) {
         if (v < V) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) out.rgb_dynamic[((int64_t)r * V + v) * 3 + c] = s_rgbd[v][c];
@@ -354,7 +418,7 @@ __global__ void composite_multi_fwd_kernel(const float* __restrict__ raw_alpha_s
       reg_acc[0] += -ent * inc * invS / (float)(V + 1);                 // :620-629
       reg_acc[1] += -dvs * inc * invS;                                  // :645-651
       reg_acc[2] += rayreg * inc / (float)V;                            // :690-693
-      const float pl = clogc / Z - logf(Z);                             // sum_s p log p, p = c/Z
+      const float pl = clogc / Z - flog(Z);                             // sum_s p log p, p = c/Z
       reg_acc[3] += (sig_s_sum < 0.1f ? 0.f : 1.f) * (-pl * invS) * inc;  // :707-709
       reg_acc[4] += dyn * inc * invS / (float)V;                        // :715
     }
@@ -437,13 +501,13 @@ __global__ void composite_multi_bwd_kernel(const float* __restrict__ raw_alpha_s
           const float a_s = alpha_of(ra_s, dist);
           const float cc = fminf(fmaxf(a_s, STAR_EPS_F32), 1.f - STAR_EPS_F32);
           Z += cc;
-          clogc += cc * logf(cc);
+          clogc += cc * flog(cc);
           sig_s_sum += softplus_f(ra_s);
           const float sc = fmaxf(sig_sum, STAR_EPS_F32);
 #pragma unroll
           for (int v = 0; v < STAR_MAX_V; ++v)
             if (v < V) {
-              const float n = sig_dv[v] / sc;
+              const float n = fdiv(sig_dv[v], sc);
               if (n > mx[v]) { mx[v] = n; amx[v] = s; }
             }
         }
@@ -460,7 +524,7 @@ __global__ void composite_multi_bwd_kernel(const float* __restrict__ raw_alpha_s
     float PL = 0.f, mask = 0.f;
     if (need_regs) {
       Z = warp_sum(Z); clogc = warp_sum(clogc); sig_s_sum = warp_sum(sig_s_sum);
-      PL = clogc / Z - logf(Z);
+      PL = clogc / Z - flog(Z);
       mask = sig_s_sum < 0.1f ? 0.f : 1.f;
 #pragma unroll
       for (int v = 0; v < STAR_MAX_V; ++v)
@@ -528,7 +592,7 @@ __global__ void composite_multi_bwd_kernel(const float* __restrict__ raw_alpha_s
       suffix += __shfl_sync(STAR_FULL_MASK, incl, 0);
       if (ok) {
         const float m_t = 1.f - a_t + 1e-10f;
-        const float d_at = T * Gw - after / m_t;
+        const float d_at = T * Gw - fdiv(after, m_t);
         const float shared_raw = d_at * dalpha_draw(raw_tot, dist);  // flows to every field's raw (:416-418)
         // direct alpha / sigma gradients
         float d_as = T * (gr * cs[0] + gg * cs[1] + gb * cs[2]);
@@ -542,28 +606,28 @@ __global__ void composite_multi_bwd_kernel(const float* __restrict__ raw_alpha_s
           // dynamic-vs-static (:634-651)
           float E = 0.f, Csum = 0.f;
           {
-            const float q = a_s / tc, p = fmaxf(q, STAR_EPS_F32);
-            E += p * logf(p);
-            if (q >= STAR_EPS_F32) Csum += (logf(p) + 1.f) * a_s;
+            const float q = fdiv(a_s, tc), p = fmaxf(q, STAR_EPS_F32);
+            E += p * flog(p);
+            if (q >= STAR_EPS_F32) Csum += (flog(p) + 1.f) * a_s;
           }
 #pragma unroll
           for (int v = 0; v < STAR_MAX_V; ++v)
             if (v < V) {
-              const float q = a_dv[v] / tc, p = fmaxf(q, STAR_EPS_F32);
-              E += p * logf(p);
-              if (q >= STAR_EPS_F32) Csum += (logf(p) + 1.f) * a_dv[v];
+              const float q = fdiv(a_dv[v], tc), p = fmaxf(q, STAR_EPS_F32);
+              E += p * flog(p);
+              if (q >= STAR_EPS_F32) Csum += (flog(p) + 1.f) * a_dv[v];
             }
-          reg_common = E - tot * tot_ok * Csum / (tc * tc);
+          reg_common = E - tot * tot_ok * fdiv(Csum, tc * tc);
           {
-            const float q = a_s / tc, p = fmaxf(q, STAR_EPS_F32);
-            d_as += k_dvs * (reg_common + (q >= STAR_EPS_F32 ? tot * (logf(p) + 1.f) / tc : 0.f));
+            const float q = fdiv(a_s, tc), p = fmaxf(q, STAR_EPS_F32);
+            d_as += k_dvs * (reg_common + (q >= STAR_EPS_F32 ? fdiv(tot * (flog(p) + 1.f), tc) : 0.f));
           }
           // alpha entropy (:612-631)
           {
             const float c = fminf(fmaxf(a_s, STAR_EPS_F32), 1.f - STAR_EPS_F32);
-            d_as += k_ent * (logf(c) - log1pf(-c));
+            d_as += k_ent * (flog(c) - flog1m(c));
             // static reg (:698-711)
-            if (a_s >= STAR_EPS_F32 && a_s <= 1.f - STAR_EPS_F32) d_as += k_sta * (logf(c / Z) - PL);
+            if (a_s >= STAR_EPS_F32 && a_s <= 1.f - STAR_EPS_F32) d_as += k_sta * (flog(fdiv(c, Z)) - PL);
           }
           // ray reg (:682-695): gradient lands on the arg-max sample of each object
           const float ssum = sig_s + sig_dsum;
@@ -594,10 +658,10 @@ __global__ void composite_multi_bwd_kernel(const float* __restrict__ raw_alpha_s
             float d_ad = T * (gr * c0 + gg * c1 + gb * c2);
             float d_sig = 0.f;
             if (need_regs) {
-              const float q = a_d / tc, p = fmaxf(q, STAR_EPS_F32);
-              d_ad += k_dvs * (reg_common + (q >= STAR_EPS_F32 ? tot * (logf(p) + 1.f) / tc : 0.f));
+              const float q = fdiv(a_d, tc), p = fmaxf(q, STAR_EPS_F32);
+              d_ad += k_dvs * (reg_common + (q >= STAR_EPS_F32 ? fdiv(tot * (flog(p) + 1.f), tc) : 0.f));
               const float c = fminf(fmaxf(a_d, STAR_EPS_F32), 1.f - STAR_EPS_F32);
-              d_ad += k_ent * (logf(c) - log1pf(-c));
+              d_ad += k_ent * (flog(c) - flog1m(c));
               d_sig = d_sig_all + k_dyn;
               if (amx[v] == s) {
                 const float sc = fmaxf(softplus_f(ra_s) + sig_dsum, STAR_EPS_F32);
@@ -638,8 +702,14 @@ extern "C" int star_composite_single_forward(const float* raw_alpha, const float
   int blocks, threads;
   size_t smem;
   warp_per_ray_cfg(R, 0, blocks, threads, smem);
-  composite_single_fwd_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
-      raw_alpha, raw_rgb, z_vals, rays_d, R, S, far_dist, white_bkgd, rgb, disp, acc, depth, weights, dists);
+  const bool aligned8 = (((uintptr_t)raw_alpha | (uintptr_t)raw_rgb | (uintptr_t)z_vals | (uintptr_t)weights |
+                          (uintptr_t)dists) & 7) == 0;
+  if ((S & 1) == 0 && aligned8)
+    composite_single_fwd_x2_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+        raw_alpha, raw_rgb, z_vals, rays_d, R, S, far_dist, white_bkgd, rgb, disp, acc, depth, weights, dists);
+  else
+    composite_single_fwd_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+        raw_alpha, raw_rgb, z_vals, rays_d, R, S, far_dist, white_bkgd, rgb, disp, acc, depth, weights, dists);
   return star_check_launch();
 }
 
@@ -682,9 +752,17 @@ extern "C" int star_composite_multi_forward(const float* raw_alpha_s, const floa
     return STAR_E_NULL;
   if (R < 1 || S < 1 || V < 1 || V > STAR_MAX_V || chunk < 1) return STAR_E_BAD_SHAPE;
   const int blocks = multi_fwd_blocks(R);
-  composite_multi_fwd_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(
-      raw_alpha_s, raw_rgb_s, raw_alpha_d, raw_rgb_d, z_vals, rays_d, R, V, S, far_dist, white_bkgd, chunk, *out,
-      (float*)workspace);
+#define STAR_MULTI_FWD(VT)                                                                                       \
+  case VT:                                                                                                       \
+    composite_multi_fwd_kernel<VT><<<blocks, 128, 0, (cudaStream_t)stream>>>(                                    \
+        raw_alpha_s, raw_rgb_s, raw_alpha_d, raw_rgb_d, z_vals, rays_d, R, V, S, far_dist, white_bkgd, chunk,    \
+        *out, (float*)workspace);                                                                                \
+    break;
+  switch (V) {   // per-object accumulators live in registers: one instantiation per object count
+    STAR_MULTI_FWD(1) STAR_MULTI_FWD(2) STAR_MULTI_FWD(3) STAR_MULTI_FWD(4)
+    STAR_MULTI_FWD(5) STAR_MULTI_FWD(6) STAR_MULTI_FWD(7) STAR_MULTI_FWD(8)
+  }
+#undef STAR_MULTI_FWD
   int rc = star_check_launch();
   if (rc) return rc;
   reg_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const float*)workspace, blocks, out->regs);

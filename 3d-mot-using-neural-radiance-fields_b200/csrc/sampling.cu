@@ -35,6 +35,59 @@ __global__ void sample_pts_kernel(const float* __restrict__ rays_o, const float*
   }
 }
 
+// Nc % 4 == 0: one thread per four consecutive samples of a ray -- 16-byte stores of z and of the 12 pts floats,
+// 32-bit index arithmetic.  Same per-element arithmetic as above.
+__global__ void sample_pts_x4_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                     const float* __restrict__ t_vals, const float* __restrict__ t_rand,
+                                     float near_, float far_, int R, int Nc, int lindisp,
+                                     float* __restrict__ pts, float* __restrict__ z_vals) {
+  const uint32_t Q = (uint32_t)Nc >> 2;
+  const uint32_t total = (uint32_t)R * Q;
+  auto zval = [&](int k) -> float {
+    const float t = t_vals[k];
+    if (!lindisp) return __fadd_rn(__fmul_rn(near_, __fsub_rn(1.f, t)), __fmul_rn(far_, t));
+    const float a = __fmul_rn(__fdiv_rn(1.f, near_), __fsub_rn(1.f, t));
+    const float b = __fmul_rn(__fdiv_rn(1.f, far_), t);
+    return __fdiv_rn(1.f, __fadd_rn(a, b));
+  };
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+    const uint32_t r = q / Q, s0 = (q - r * Q) * 4u;
+    float z[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) z[j] = zval((int)s0 + j);
+    if (t_rand != nullptr) {  // :99-106 stratified jitter with injected noise
+      const float4 tr = *reinterpret_cast<const float4*>(t_rand + (size_t)q * 4);
+      const float trv[4] = {tr.x, tr.y, tr.z, tr.w};
+      const float zm = (s0 == 0) ? 0.f : zval((int)s0 - 1), zp = ((int)s0 + 4 >= Nc) ? 0.f : zval((int)s0 + 4);
+      float zj[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int s = (int)s0 + j;
+        const float prev = (j == 0) ? zm : z[j - 1], next = (j == 3) ? zp : z[j + 1];
+        const float lo = (s == 0) ? z[j] : __fmul_rn(0.5f, __fadd_rn(z[j], prev));
+        const float hi = (s == Nc - 1) ? z[j] : __fmul_rn(0.5f, __fadd_rn(next, z[j]));
+        zj[j] = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), trv[j]));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) z[j] = zj[j];
+    }
+    const float ox = rays_o[r * 3 + 0], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
+    const float dx = rays_d[r * 3 + 0], dy = rays_d[r * 3 + 1], dz = rays_d[r * 3 + 2];
+    float p[12];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      p[3 * j + 0] = __fadd_rn(ox, __fmul_rn(dx, z[j]));
+      p[3 * j + 1] = __fadd_rn(oy, __fmul_rn(dy, z[j]));
+      p[3 * j + 2] = __fadd_rn(oz, __fmul_rn(dz, z[j]));
+    }
+    __stcs(reinterpret_cast<float4*>(z_vals + (size_t)q * 4), make_float4(z[0], z[1], z[2], z[3]));
+    float4* po = reinterpret_cast<float4*>(pts + (size_t)q * 12);
+    __stcs(po + 0, make_float4(p[0], p[1], p[2], p[3]));
+    __stcs(po + 1, make_float4(p[4], p[5], p[6], p[7]));
+    __stcs(po + 2, make_float4(p[8], p[9], p[10], p[11]));
+  }
+}
+
 extern "C" int star_sample_pts(const float* rays_o, const float* rays_d, const float* t_vals,
                                const float* t_rand, float near_, float far_, int R, int Nc, int lindisp,
                                float* pts, float* z_vals, void* stream) {
@@ -43,6 +96,14 @@ extern "C" int star_sample_pts(const float* rays_o, const float* rays_d, const f
   if (R == 0) return STAR_OK;
   const int64_t total = (int64_t)R * Nc;
   const int threads = 256;
+  if ((Nc & 3) == 0 && total / 4 < (int64_t)0x7fffffff &&
+      (((uintptr_t)pts | (uintptr_t)z_vals | (uintptr_t)t_rand) & 15) == 0) {
+    const int64_t nq = total / 4;
+    const int blocks = (int)((nq + threads - 1) / threads < 148 * 8 ? (nq + threads - 1) / threads : 148 * 8);
+    sample_pts_x4_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_vals, t_rand, near_, far_,
+                                                                        R, Nc, lindisp, pts, z_vals);
+    return star_check_launch();
+  }
   const int blocks = (int)((total + threads - 1) / threads < 148 * 16 ? (total + threads - 1) / threads : 148 * 16);
   sample_pts_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_vals, t_rand, near_, far_, R,
                                                                   Nc, lindisp, pts, z_vals);
@@ -211,7 +272,7 @@ extern "C" int star_invert_cdf(const float* bins, const float* cdf, const float*
 
 // ------------------------------------------------------------------------------------------ a10
 // z_mid -> sample_pdf -> sort(cat(z_vals, z_samples)) -> z_std, pts.  One warp per ray.
-// smem per warp: cdf[nb] | bins[nb] | zc[Nc] | zs[P] | zall[Nf]   (P = next pow2 >= Ni, padded with +inf)
+// smem per warp: see hier_smem_floats (P = next pow2 >= Ni; zs is padded with +inf up to P)
 // The concatenation is sorted as a MERGE: the coarse samples are sorted by construction, the fine samples are
 // sorted whenever u is (always in eval mode: inverse-CDF sampling is monotone); only otherwise (random u in
 // training) are the Ni fine samples bitonic-sorted first.  Every element then finds its output slot with one
@@ -229,6 +290,11 @@ __device__ __forceinline__ int count_less_equal(const float* a, int n, float x) 
   return lo;
 }
 
+// floats of shared memory per warp: zall[Nf, padded to 4] | zs[P] | zc[Nc] | cdf[nb] | bins[nb] | guess[Ni]
+__host__ __device__ __forceinline__ int hier_smem_floats(int Nc, int Ni, int P) {
+  return ((((Nc + Ni + 3) & ~3) + P + Nc + 2 * (Nc - 1) + Ni) + 3) & ~3;
+}
+
 template <bool GIVEN>
 __global__ void hierarchical_kernel(const float* __restrict__ z_vals, const float* __restrict__ weights,
                                     const float* __restrict__ u, const float* __restrict__ u_det,
@@ -236,14 +302,16 @@ __global__ void hierarchical_kernel(const float* __restrict__ z_vals, const floa
                                     int Nc, int Ni, int P, float* z_samples,
                                     float* __restrict__ z_all, float* __restrict__ z_std,
                                     float* __restrict__ pts_fine) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int nb = Nc - 1, Nf = Nc + Ni;
-  float* cdf = smem + (size_t)warp * (2 * nb + Nc + P + Nf);
+  float* za = smem + (size_t)warp * hier_smem_floats(Nc, Ni, P);   // 16-byte aligned (region is a multiple of 4)
+  float* zs = za + ((Nf + 3) & ~3);
+  float* zc = zs + P;
+  float* cdf = zc + Nc;
   float* sb = cdf + nb;
-  float* zc = sb + nb;
-  float* zs = zc + Nc;
-  float* za = zs + P;
+  int* gs = reinterpret_cast<int*>(sb + nb);   // per fine sample: below + 1 = first guess of its rank among zc
+  const bool vec4 = ((Nf & 3) == 0) && (((uintptr_t)z_all | (uintptr_t)pts_fine) & 15) == 0;
   for (int r = blockIdx.x * wpb + warp; r < R; r += gridDim.x * wpb) {
     const float* zr = z_vals + (int64_t)r * Nc;
     if (!GIVEN) {
@@ -263,6 +331,7 @@ __global__ void hierarchical_kernel(const float* __restrict__ z_vals, const floa
         int i0, b0, a0;
         s = invert_one(cdf, sb, nb, uu, i0, b0, a0);
         z_samples[(int64_t)r * Ni + j] = s;
+        gs[j] = b0 + 1;
       }
       zs[j] = s;
       sum += s;
@@ -279,7 +348,8 @@ __global__ void hierarchical_kernel(const float* __restrict__ z_vals, const floa
     }
     var = warp_sum(var) / (float)Ni;
     if (lane == 0) z_std[r] = sqrtf(var);
-    if (!__all_sync(STAR_FULL_MASK, sorted)) {
+    const bool all_sorted = __all_sync(STAR_FULL_MASK, sorted);
+    if (!all_sorted) {
       // bitonic sort of zs[0..P)
       for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -303,17 +373,43 @@ __global__ void hierarchical_kernel(const float* __restrict__ z_vals, const floa
     }
     for (int j = lane; j < Ni; j += 32) {
       const float v = zs[j];
-      za[j + count_less_equal(zc, Nc, v)] = v;
+      int k;
+      if (!GIVEN && all_sorted) {
+        // a sample drawn from bin [z_mid[b], z_mid[b+1]] has b+1 or b+2 coarse samples at or below it: start from
+        // the guess and walk (exact for any input, O(1) here)
+        k = gs[j];
+        while (k < Nc && zc[k] <= v) ++k;
+        while (k > 0 && zc[k - 1] > v) --k;
+      } else {
+        k = count_less_equal(zc, Nc, v);
+      }
+      za[j + k] = v;
     }
     __syncwarp();
-    for (int k = lane; k < Nf; k += 32) z_all[(int64_t)r * Nf + k] = za[k];
-    if (pts_fine != nullptr) {
-      const float ox = rays_o[r * 3 + 0], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
-      const float dx = rays_d[r * 3 + 0], dy = rays_d[r * 3 + 1], dz = rays_d[r * 3 + 2];
-      for (int i = lane; i < Nf * 3; i += 32) {
-        const int s = i / 3, c = i - s * 3;
-        const float o = c == 0 ? ox : (c == 1 ? oy : oz), d = c == 0 ? dx : (c == 1 ? dy : dz);
-        pts_fine[(int64_t)r * Nf * 3 + i] = __fadd_rn(o, __fmul_rn(d, za[s]));
+    const float ox = rays_o ? rays_o[r * 3 + 0] : 0.f, oy = rays_o ? rays_o[r * 3 + 1] : 0.f, oz = rays_o ? rays_o[r * 3 + 2] : 0.f;
+    const float dx = rays_d ? rays_d[r * 3 + 0] : 0.f, dy = rays_d ? rays_d[r * 3 + 1] : 0.f, dz = rays_d ? rays_d[r * 3 + 2] : 0.f;
+    if (vec4) {
+      for (int q = lane; q < (Nf >> 2); q += 32) {
+        const float4 z = *reinterpret_cast<const float4*>(za + 4 * q);
+        __stcs(reinterpret_cast<float4*>(z_all + (int64_t)r * Nf) + q, z);
+        if (pts_fine != nullptr) {
+          float4* po = reinterpret_cast<float4*>(pts_fine + ((int64_t)r * Nf + 4 * q) * 3);
+          __stcs(po + 0, make_float4(__fadd_rn(ox, __fmul_rn(dx, z.x)), __fadd_rn(oy, __fmul_rn(dy, z.x)),
+                                     __fadd_rn(oz, __fmul_rn(dz, z.x)), __fadd_rn(ox, __fmul_rn(dx, z.y))));
+          __stcs(po + 1, make_float4(__fadd_rn(oy, __fmul_rn(dy, z.y)), __fadd_rn(oz, __fmul_rn(dz, z.y)),
+                                     __fadd_rn(ox, __fmul_rn(dx, z.z)), __fadd_rn(oy, __fmul_rn(dy, z.z))));
+          __stcs(po + 2, make_float4(__fadd_rn(oz, __fmul_rn(dz, z.z)), __fadd_rn(ox, __fmul_rn(dx, z.w)),
+                                     __fadd_rn(oy, __fmul_rn(dy, z.w)), __fadd_rn(oz, __fmul_rn(dz, z.w))));
+        }
+      }
+    } else {
+      for (int k = lane; k < Nf; k += 32) z_all[(int64_t)r * Nf + k] = za[k];
+      if (pts_fine != nullptr) {
+        for (int i = lane; i < Nf * 3; i += 32) {
+          const int s = i / 3, c = i - s * 3;
+          const float o = c == 0 ? ox : (c == 1 ? oy : oz), d = c == 0 ? dx : (c == 1 ? dy : dz);
+          pts_fine[(int64_t)r * Nf * 3 + i] = __fadd_rn(o, __fmul_rn(d, za[s]));
+        }
       }
     }
     __syncwarp();
@@ -331,7 +427,7 @@ extern "C" int star_hierarchical(const float* z_vals, const float* weights, cons
   while (P < Ni) P <<= 1;
   int blocks, threads;
   size_t smem;
-  int rc = launch_cfg_warp_per_ray(R, sizeof(float) * (2 * (Nc - 1) + Nc + P + Nc + Ni), blocks, threads, smem);
+  int rc = launch_cfg_warp_per_ray(R, sizeof(float) * (size_t)hier_smem_floats(Nc, Ni, P), blocks, threads, smem);
   if (rc) return rc;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(hierarchical_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -351,7 +447,7 @@ extern "C" int star_merge_samples(const float* z_vals, const float* z_samples, c
   while (P < Ni) P <<= 1;
   int blocks, threads;
   size_t smem;
-  int rc = launch_cfg_warp_per_ray(R, sizeof(float) * (2 * (Nc - 1) + Nc + P + Nc + Ni), blocks, threads, smem);
+  int rc = launch_cfg_warp_per_ray(R, sizeof(float) * (size_t)hier_smem_floats(Nc, Ni, P), blocks, threads, smem);
   if (rc) return rc;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(hierarchical_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
