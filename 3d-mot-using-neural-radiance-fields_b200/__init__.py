@@ -6,12 +6,14 @@ burakcuhadar/3D-MOT-using-Neural-Radiance-Fields behind the reference's own Pyth
     from star_b200.models.rendering__ import sample_pts, render_star_online
 
 `star_b200.install()` registers the mirrors as `models.rendering__`, `models.star__`, `models.nerf`,
-`models.embedder`, `models.resnet`, `models.types__` in sys.modules so that the reference's train
+`models.embedder`, `models.resnet`, `models.types__`, `models.star_mipnerf`, `models.mipnerf`,
+`models.rendering_starmip` in sys.modules so that the reference's train
 scripts pick them up unmodified."""
 import sys
 
 from . import _capi, functional, parallel  # noqa: F401
-from .models import embedder, nerf, rendering__, resnet, star__, types__  # noqa: F401
+from . import mip_functional  # noqa: F401
+from .models import embedder, mipnerf, nerf, rendering__, rendering_starmip, resnet, star__, star_mipnerf, types__  # noqa: F401
 from .models.star__ import STaR  # noqa: F401
 
 __all__ = ["STaR", "functional", "install", "parallel", "rendering__", "star__"]
@@ -26,6 +28,7 @@ def install(package="models"):
         pkg.__path__ = []
         sys.modules[package] = pkg
     for name, mod in (("rendering__", rendering__), ("star__", star__), ("nerf", nerf), ("embedder", embedder),
-                      ("resnet", resnet), ("types__", types__)):
+                      ("resnet", resnet), ("types__", types__), ("star_mipnerf", star_mipnerf), ("mipnerf", mipnerf),
+                      ("rendering_starmip", rendering_starmip)):
         sys.modules[f"{package}.{name}"] = mod
         setattr(pkg, name, mod)

@@ -22,6 +22,12 @@ class StarNetDesc(C.Structure):
     _fields_ = [("n_blocks", C.c_int32), ("L_xyz", C.c_int32), ("L_dir", C.c_int32), ("precision", C.c_int32)]
 
 
+class StarMipMultiOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "rgb", "acc", "depth", "weights", "rgb_static", "depth_static", "rgb_dynamic", "depth_dynamic",
+        "dynamic_transmittance", "regs")]
+
+
 class StarMultiOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "rgb", "disp", "acc", "depth", "weights", "rgb_static", "depth_static", "rgb_dynamic",
@@ -58,6 +64,26 @@ _SIGS = {
     "star_invert_cdf": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f]),
     "star_hierarchical": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f]),
     "star_merge_samples": (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f]),
+    # a12: mip-NeRF variant
+    "star_mip_uniform_bins": (C.c_int, [c_f, c_f, C.c_float, C.c_float, C.c_int, C.c_int, c_f, c_f, c_f]),
+    "star_mip_pdf_sample": (C.c_int, [c_f, c_f, c_i64, c_f, c_f, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
+                                      c_f, c_f, c_f, c_f, c_f]),
+    "star_mip_param_count": (C.c_size_t, []),
+    "star_mip_packed_bytes": (C.c_size_t, [C.c_int]),
+    "star_mip_pack_weights": (C.c_int, [C.c_int, c_f, c_f, c_f]),
+    "star_mip_stash_bytes": (C.c_size_t, [C.c_int, c_i64]),
+    "star_mip_backward_workspace_bytes": (C.c_size_t, [C.c_int, c_i64]),
+    "star_mip_field_forward": (C.c_int, [C.c_int, c_f, c_f, c_f, c_f, c_f, c_f, C.c_float, C.c_int, C.c_int, c_f, c_f,
+                                         c_i64, c_f, c_f]),
+    "star_mip_field_backward": (C.c_int, [C.c_int, c_f, c_f, c_f, c_f, c_f, c_f, C.c_float, C.c_int, C.c_int, c_f,
+                                          c_f, c_i64, c_f, c_f, c_f, c_f, c_f]),
+    "star_mip_composite_single_forward": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f]),
+    "star_mip_composite_single_backward": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f, c_f]),
+    "star_mip_composite_multi_ws_bytes": (C.c_size_t, [C.c_int]),
+    "star_mip_composite_multi_forward": (C.c_int, [c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                   C.POINTER(StarMipMultiOut), c_f, c_f]),
+    "star_mip_composite_multi_backward": (C.c_int, [c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                    c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -2,6 +2,7 @@
 #include "star_common.cuh"
 #include "mlp_layout.h"
 #include "mlp_tc_layout.h"
+#include "mip_layout.h"
 
 int g_star_last_cuda_error = 0;
 
@@ -150,5 +151,84 @@ extern "C" int star_mlp_backward(const StarNetDesc* d, const void* packed, const
                             d_raw_rgb, alpha_ray_stride, stash, workspace, grad_flat, pose_acc,
                             d->precision == STAR_PREC_F16, (cudaStream_t)stream);
   }
+  return STAR_E_UNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------- a12 mip field
+int star_mip_f32_pack(const MipLayout& lay, const float* master, void* packed, cudaStream_t st);
+int star_mip_f32_forward(const MipLayout& lay, const void* packed, const float* origins, const float* dirs,
+                         const float* pose12, const float* bins, const float* freqs, float radius, int R, int S,
+                         float* raw_sigma, float* raw_rgb, int64_t ray_stride, void* stash, cudaStream_t st);
+int star_mip_f32_backward(const MipLayout& lay, const void* packed, const float* origins, const float* dirs,
+                          const float* pose12, const float* bins, const float* freqs, float radius, int R, int S,
+                          const float* d_raw_sigma, const float* d_raw_rgb, int64_t ray_stride, const void* stash,
+                          void* workspace, float* grad_flat, float* pose_acc, cudaStream_t st);
+
+extern "C" size_t star_mip_param_count(void) {
+  MipLayout lay;
+  star_make_mip_layout(&lay);
+  return (size_t)lay.n_master;
+}
+
+extern "C" size_t star_mip_packed_bytes(int precision) {
+  MipLayout lay;
+  star_make_mip_layout(&lay);
+  if (precision == STAR_PREC_F32) return sizeof(float) * (size_t)lay.n_packed;
+  return 0;
+}
+
+extern "C" int star_mip_pack_weights(int precision, const float* flat_master, void* packed, void* stream) {
+  if (!flat_master || !packed) return STAR_E_NULL;
+  MipLayout lay;
+  star_make_mip_layout(&lay);
+  if (precision == STAR_PREC_F32) return star_mip_f32_pack(lay, flat_master, packed, (cudaStream_t)stream);
+  return STAR_E_UNSUPPORTED;
+}
+
+extern "C" size_t star_mip_stash_bytes(int precision, int64_t n_samples) {
+  MipLayout lay;
+  star_make_mip_layout(&lay);
+  if (precision != STAR_PREC_F32 || n_samples < 0) return 0;
+  return sizeof(float) * (size_t)lay.stash_cols * (size_t)n_samples;
+}
+
+extern "C" size_t star_mip_backward_workspace_bytes(int precision, int64_t n_samples) {
+  MipLayout lay;
+  star_make_mip_layout(&lay);
+  if (precision != STAR_PREC_F32 || n_samples < 0) return 0;
+  return sizeof(float) * (size_t)lay.g_cols * (size_t)n_samples;
+}
+
+extern "C" int star_mip_field_forward(int precision, const void* packed, const float* origins, const float* dirs,
+                                      const float* pose12, const float* bins, const float* freqs, float radius, int R,
+                                      int S, float* raw_sigma, float* raw_rgb, int64_t ray_stride, void* stash,
+                                      void* stream) {
+  if (!packed || !origins || !dirs || !bins || !freqs || !raw_sigma || !raw_rgb) return STAR_E_NULL;
+  if (R < 0 || S < 1 || ray_stride < S) return STAR_E_BAD_SHAPE;
+  if (R == 0) return STAR_OK;
+  MipLayout lay;
+  star_make_mip_layout(&lay);
+  if (precision == STAR_PREC_F32)
+    return star_mip_f32_forward(lay, packed, origins, dirs, pose12, bins, freqs, radius, R, S, raw_sigma, raw_rgb,
+                                ray_stride, stash, (cudaStream_t)stream);
+  return STAR_E_UNSUPPORTED;
+}
+
+extern "C" int star_mip_field_backward(int precision, const void* packed, const float* origins, const float* dirs,
+                                       const float* pose12, const float* bins, const float* freqs, float radius, int R,
+                                       int S, const float* d_raw_sigma, const float* d_raw_rgb, int64_t ray_stride,
+                                       const void* stash, void* workspace, float* grad_flat, float* pose_acc,
+                                       void* stream) {
+  if (!packed || !origins || !dirs || !bins || !freqs || !d_raw_sigma || !d_raw_rgb || !stash || !workspace ||
+      !grad_flat)
+    return STAR_E_NULL;
+  if (pose12 && !pose_acc) return STAR_E_NULL;
+  if (R < 0 || S < 1 || ray_stride < S) return STAR_E_BAD_SHAPE;
+  if (R == 0) return STAR_OK;
+  MipLayout lay;
+  star_make_mip_layout(&lay);
+  if (precision == STAR_PREC_F32)
+    return star_mip_f32_backward(lay, packed, origins, dirs, pose12, bins, freqs, radius, R, S, d_raw_sigma, d_raw_rgb,
+                                 ray_stride, stash, workspace, grad_flat, pose_acc, (cudaStream_t)stream);
   return STAR_E_UNSUPPORTED;
 }

@@ -10,71 +10,7 @@
 #include "star_common.cuh"
 #include "mlp_layout.h"
 
-#define TM 64
-#define AS 68
-#define KS 16
-#define A_ROWS 288
-#define NTHREADS 256
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-// Column owned by register slot nj of this lane: lane*4 + (nj&3) + 128*(nj>>2)
-__device__ __forceinline__ int col_of(int lane, int nj) { return lane * 4 + (nj & 3) + 128 * (nj >> 2); }
-
-// acc[8][4*NJ] += As^T[64 x K] * Wg[K x 128*NJ]   (As: smem [K][AS], Wg: global row-major, ld = ldw)
-template <int NJ>
-__device__ __forceinline__ void gemm_tile(const float* __restrict__ As, const float* __restrict__ Wg, int ldw,
-                                          int K, float (&acc)[8][4 * NJ], float* __restrict__ Wbuf, int tid) {
-  constexpr int NCOL = 128 * NJ;
-  constexpr int CHUNKS = KS * NCOL / 4;          // float4 chunks per slab
-  const int warp = tid >> 5, lane = tid & 31;
-  const int nslab = K / KS;
-  auto load_slab = [&](int s, int buf) {
-    float* dst = Wbuf + buf * (KS * 256);
-    const float* src = Wg + (int64_t)s * KS * ldw;
-#pragma unroll
-    for (int c = tid; c < CHUNKS; c += NTHREADS) {
-      const int row = c / (NCOL / 4), col4 = c % (NCOL / 4);
-      cp_async16(dst + row * NCOL + col4 * 4, src + (int64_t)row * ldw + col4 * 4);
-    }
-    cp_async_commit();
-  };
-  load_slab(0, 0);
-  for (int s = 0; s < nslab; ++s) {
-    if (s + 1 < nslab) {
-      load_slab(s + 1, (s + 1) & 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    const float* Wb = Wbuf + (s & 1) * (KS * 256);
-    const float* Ab = As + (s * KS) * AS + warp * 8;
-#pragma unroll
-    for (int kk = 0; kk < KS; ++kk) {
-      const float4 a0 = *reinterpret_cast<const float4*>(Ab + kk * AS);
-      const float4 a1 = *reinterpret_cast<const float4*>(Ab + kk * AS + 4);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      float b[4 * NJ];
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const float4 bv = *reinterpret_cast<const float4*>(Wb + kk * NCOL + lane * 4 + 128 * j);
-        b[4 * j + 0] = bv.x; b[4 * j + 1] = bv.y; b[4 * j + 2] = bv.z; b[4 * j + 3] = bv.w;
-      }
-#pragma unroll
-      for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-        for (int nj = 0; nj < 4 * NJ; ++nj) acc[mi][nj] = fmaf(a[mi], b[nj], acc[mi][nj]);
-    }
-    __syncthreads();
-  }
-}
+#include "mlp_f32_device.cuh"
 
 // ------------------------------------------------------------------------------ encoding helpers
 struct SampleGeom {
@@ -595,7 +531,7 @@ mlp_bwd_f32_kernel(MlpLayout lay, const float* __restrict__ packed, const float*
 // Grid: (Kpad/64, N/64, splits).  64x64 output tile, 256 threads, 4x4 per thread, 32-sample slabs.
 __global__ void __launch_bounds__(256)
 dw_f32_kernel(const float* __restrict__ G, int N, const float* __restrict__ In, int Kpad, int K, int64_t M,
-              float* __restrict__ dW, float* __restrict__ db) {
+              float* __restrict__ dW, int ldw, float* __restrict__ db) {
   __shared__ float Gs[32][64 + 4];
   __shared__ float Xs[32][64 + 4];
   const int tid = threadIdx.x;
@@ -632,7 +568,7 @@ dw_f32_kernel(const float* __restrict__ G, int N, const float* __restrict__ In, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(gv[i], xx[j], acc[i][j]);
     }
-    if (blockIdx.x == 0 && tid < 64) {
+    if (db != nullptr && blockIdx.x == 0 && tid < 64) {
 #pragma unroll 8
       for (int mm = 0; mm < 32; ++mm) bsum += Gs[mm][tid];
     }
@@ -643,9 +579,20 @@ dw_f32_kernel(const float* __restrict__ G, int N, const float* __restrict__ In, 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tn + i, k = k0 + tk + j;
-      if (k < K) atomicAdd(&dW[(int64_t)n * K + k], acc[i][j]);
+      if (k < K) atomicAdd(&dW[(int64_t)n * ldw + k], acc[i][j]);
     }
-  if (blockIdx.x == 0 && tid < 64) atomicAdd(&db[n0 + tid], bsum);
+  if (db != nullptr && blockIdx.x == 0 && tid < 64) atomicAdd(&db[n0 + tid], bsum);
+}
+
+// dW[n][k] (row stride ldw) += G^T In for one GEMM layer (or one K-segment of it); db (may be NULL) += column sums of G
+int star_f32_dw(const float* G, int N, const float* In, int Kpad, int K, int64_t M, float* dW, int ldw, float* db,
+                cudaStream_t st) {
+  int splits = (int)((M + 8191) / 8192);
+  if (splits < 1) splits = 1;
+  if (splits > 64) splits = 64;
+  dim3 grid(Kpad / 64 + (Kpad % 64 ? 1 : 0), N / 64, splits);
+  dw_f32_kernel<<<grid, 256, 0, st>>>(G, N, In, Kpad, K, M, dW, ldw, db);
+  return star_check_launch();
 }
 
 // Head gradients: d alpha_w[k] = sum_m d_alpha[m] h[m][k]; d rgb_w[c][n] = sum_m d_rgb[m][c] h2[m][n]; biases.
@@ -769,15 +716,10 @@ int star_f32_backward(const MlpLayout& lay, const void* packed, const float* pts
       (const float*)stash, gst, pose_acc);
   int rc = star_check_launch();
   if (rc) return rc;
-  int splits = (int)((M + 8191) / 8192);
-  if (splits < 1) splits = 1;
-  if (splits > 64) splits = 64;
   for (int l = 0; l < lay.n_layers; ++l) {
     const MlpLayer& ly = lay.L[l];
-    dim3 grid(ly.Kpad / 64 + (ly.Kpad % 64 ? 1 : 0), ly.N / 64, splits);
-    dw_f32_kernel<<<grid, 256, 0, st>>>(gst + ly.g_out * M, ly.N, (const float*)stash + ly.s_in * M, ly.Kpad, ly.K, M,
-                                        grad_flat + ly.m_w, grad_flat + ly.m_b);
-    rc = star_check_launch();
+    rc = star_f32_dw(gst + ly.g_out * M, ly.N, (const float*)stash + ly.s_in * M, ly.Kpad, ly.K, M,
+                     grad_flat + ly.m_w, ly.K, grad_flat + ly.m_b, st);
     if (rc) return rc;
   }
   int hb = (int)((M + 2047) / 2048);

@@ -184,6 +184,84 @@ int star_hierarchical(const float* z_vals, const float* weights, const float* u,
 int star_merge_samples(const float* z_vals, const float* z_samples, const float* rays_o, const float* rays_d,
                        int R, int Nc, int Ni, float* z_all, float* z_std, float* pts_fine, void* stream);
 
+/* ================================================================================================
+ * a12: the mip-NeRF / integrated-positional-encoding variant
+ * (models/star_mipnerf.py:99-357, models/rendering_starmip.py:32-175, models/mipnerf.py:53-100; the arithmetic
+ * is nerfstudio's -- un-vendored and un-pinned by the reference: "parity unpinned", see oracle/mip_oracle.py).
+ * ================================================================================================ */
+
+/* ---- nerfstudio UniformSampler (star_mipnerf.py:75-77,271): Nc+1 frustum edges per ray --------
+ * lin[Nc+1] = torch.linspace(0,1,Nc+1) from the host; t_rand[R,Nc+1] or NULL (training-mode stratified jitter).
+ * Outputs spacing[R,Nc+1] (in [0,1]) and euclid[R,Nc+1] = spacing*far + (1-spacing)*near. */
+int star_mip_uniform_bins(const float* lin, const float* t_rand, float near_, float far_, int R, int Nc,
+                          float* spacing, float* euclid, void* stream);
+
+/* ---- nerfstudio PDFSampler(include_original=False, histogram_padding=0.01) (star_mipnerf.py:286-288) ----
+ * spacing_bins[R,Nc+1], weights[R,Nc] (row stride w_stride) -> Ni+1 new edges per ray.
+ * u_base[Ni+1]: host-side linspace(0, 1-1/nb, nb) (+ 1/(2 nb) in eval mode); u_rand[R,Ni+1] or NULL: training jitter
+ * (u = u_base + u_rand/nb).  Optional inds[R,Ni+1] (int64, searchsorted side="right") and cdf[R,Nc+1] for the
+ * bit-exactness tests.  Same defined arithmetic as star_sample_pdf. */
+int star_mip_pdf_sample(const float* spacing_bins, const float* weights, int64_t w_stride, const float* u_base,
+                        const float* u_rand, float near_, float far_, int R, int Nc, int Ni, float* spacing_out,
+                        float* euclid_out, int64_t* inds, float* cdf, void* stream);
+
+/* ---- the field: models/mipnerf.py:89-100 -> nerfstudio NeRFField(use_integrated_encoding=True) ---------
+ * Flat master order (each nn.Linear as weight [out,in] then bias [out]): field.mlp_base.layers.0..7,
+ * field.field_output_density.net, field.mlp_head.layers.0, .1, field.field_heads.0.net  (589 572 floats).
+ * origins[R,3], dirs[R,3] (normalised view directions), bins[R,S+1] euclidean frustum edges; pose12 = NULL (static
+ * field) or [R(3x3) | t]: o' = R o + t, d' = R d (star_mipnerf.py:206-214).  freqs[64]: host table
+ * [2**linspace(0,24,24) | its square | 2**linspace(0,4,4) | pad].  radius = sqrt(pixel_area)/sqrt(pi) (= 0.5642:
+ * the reference passes pixel_area = 1, star_mipnerf.py:267).
+ * Outputs are RAW (pre-softplus density, pre-sigmoid rgb), written with the strides of star_mlp_forward. */
+size_t star_mip_param_count(void);
+size_t star_mip_packed_bytes(int precision);
+int star_mip_pack_weights(int precision, const float* flat_master, void* packed, void* stream);
+size_t star_mip_stash_bytes(int precision, int64_t n_samples);
+size_t star_mip_backward_workspace_bytes(int precision, int64_t n_samples);
+int star_mip_field_forward(int precision, const void* packed, const float* origins, const float* dirs,
+                           const float* pose12, const float* bins, const float* freqs, float radius, int R, int S,
+                           float* raw_sigma, float* raw_rgb, int64_t ray_stride, void* stash, void* stream);
+/* grad_flat: ACCUMULATED into; pose_acc[32] as in star_mlp_backward with p = the ray origin
+ * ([0:3] sum g, [3:12] sum g o^T, [12:15] sum o' x g, [15:24] sum h d^T, [24:27] sum d' x h). */
+int star_mip_field_backward(int precision, const void* packed, const float* origins, const float* dirs,
+                            const float* pose12, const float* bins, const float* freqs, float radius, int R, int S,
+                            const float* d_raw_sigma, const float* d_raw_rgb, int64_t ray_stride, const void* stash,
+                            void* workspace, float* grad_flat, float* pose_acc, void* stream);
+
+/* ---- density-space compositing: models/rendering_starmip.py:32-91 (single field) -----------------------
+ * sigma = softplus(raw), colour = sigmoid(raw); depth = nerfstudio median DepthRenderer.
+ * Outputs rgb[R,3], acc[R], depth[R], weights[R,S]. */
+int star_mip_composite_single_forward(const float* raw_sigma, const float* raw_rgb, const float* bins, int R, int S,
+                                      float* rgb, float* acc, float* depth, float* weights, void* stream);
+int star_mip_composite_single_backward(const float* raw_sigma, const float* raw_rgb, const float* bins, int R, int S,
+                                       const float* g_rgb, const float* g_acc, const float* g_weights,
+                                       float* d_raw_sigma, float* d_raw_rgb, void* stream);
+
+/* ---- models/rendering_starmip.py:112-175 (static + V dynamic fields, regularisers) ----------------------
+ * regs[5] = alpha_entropy, dynamic_vs_static, ray_reg, static_reg, dynamic_reg with the mip shapes' quirks
+ * (ray_reg has no max over samples; static_reg is identically 0 -- oracle/mip_oracle.py online_outputs). */
+typedef struct StarMipMultiOut {
+  float* rgb;                   /* [R,3]   */
+  float* acc;                   /* [R]     */
+  float* depth;                 /* [R]     */
+  float* weights;               /* [R,S]   */
+  float* rgb_static;            /* [R,3]   */
+  float* depth_static;          /* [R]     */
+  float* rgb_dynamic;           /* [R,V,3] */
+  float* depth_dynamic;         /* [R,V]   */
+  float* dynamic_transmittance; /* [R,V]   */
+  float* regs;                  /* [5]     */
+} StarMipMultiOut;
+size_t star_mip_composite_multi_ws_bytes(int R);
+int star_mip_composite_multi_forward(const float* raw_sigma_s, const float* raw_rgb_s, const float* raw_sigma_d,
+                                     const float* raw_rgb_d, const float* bins, int R, int V, int S, int chunk,
+                                     const StarMipMultiOut* out, void* workspace, void* stream);
+int star_mip_composite_multi_backward(const float* raw_sigma_s, const float* raw_rgb_s, const float* raw_sigma_d,
+                                      const float* raw_rgb_d, const float* bins, int R, int V, int S, int chunk,
+                                      const float* g_rgb, const float* g_acc, const float* g_weights,
+                                      const float* g_regs, float* d_raw_sigma_s, float* d_raw_rgb_s,
+                                      float* d_raw_sigma_d, float* d_raw_rgb_d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
