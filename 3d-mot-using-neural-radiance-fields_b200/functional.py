@@ -24,8 +24,10 @@ def _count(n=1):
     LAUNCH_COUNTER["calls"] += n
 
 
-# bench.py sets PROFILE = {} to collect (start_event, end_event, units) per named C-ABI call on the
+# bench.py sets PROFILE = {} to collect (start_event, end_event, samples, algorithmic FLOPs) per named C-ABI call on the
 # launching stream (CUDA events only; no synchronisation is added).
+MLP_MAC_PER_SAMPLE = {4: 708352, 2: 446208}    # static / dynamic net; 2 FLOP per MAC
+MIP_MAC_PER_SAMPLE = 587264
 PROFILE = None
 
 
@@ -37,12 +39,12 @@ def _prof_begin():
     return e
 
 
-def _prof_end(name, e0, units):
+def _prof_end(name, e0, samples, flops):
     if e0 is None:
         return
     e1 = torch.cuda.Event(enable_timing=True)
     e1.record()
-    PROFILE.setdefault(name, []).append((e0, e1, units))
+    PROFILE.setdefault(name, []).append((e0, e1, samples, flops))
 
 
 def _c(t):
@@ -353,7 +355,8 @@ class NerfRaw(Function):
                                      f32(sc_xyz) if sc_xyz is not None else None,
                                      f32(sc_dir) if sc_dir is not None else None, b - a, S, f32(raw_alpha[a:b]),
                                      f32(raw_rgb[a:b]), S, ptr(st), stream()), "star_mlp_forward")
-            _prof_end("mlp_forward_stash" if st is not None else "mlp_forward", e0, (b - a) * S)
+            _prof_end("mlp_forward_stash" if st is not None else "mlp_forward", e0, (b - a) * S,
+                      2.0 * MLP_MAC_PER_SAMPLE.get(rt.n_blocks, 0) * (b - a) * S)
             _count()
         if need_grad:
             ctx.rt, ctx.precision, ctx.chunks, ctx.stashes = rt, precision, chunks, stashes if keep else None
@@ -401,7 +404,7 @@ class NerfRaw(Function):
                                       f32(g_rgb[a:b]), S, ptr(st), ptr(ws), f32(grad_flat),
                                       f32(pose_acc) if pose_acc is not None else None, stream()),
                   "star_mlp_backward")
-            _prof_end("mlp_backward", e0, n)
+            _prof_end("mlp_backward", e0, n, 4.0 * MLP_MAC_PER_SAMPLE.get(rt.n_blocks, 0) * n)   # dX + dW
             _count(3 + 2 * rt.n_blocks + 4)
             if ctx.stashes is not None:
                 ctx.stashes[i] = None

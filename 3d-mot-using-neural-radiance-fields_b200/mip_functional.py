@@ -10,7 +10,7 @@ from torch.autograd import Function
 
 from . import _capi
 from ._capi import check, f32, ptr, stream
-from .functional import _c, _count, _prof_begin, _prof_end, _ray_chunks, STASH_BUDGET_BYTES
+from .functional import _c, _count, _prof_begin, _prof_end, _ray_chunks, STASH_BUDGET_BYTES, MIP_MAC_PER_SAMPLE
 
 N_FREQ_XYZ, MAX_EXP_XYZ = 24, 24.0     # models/mipnerf.py:58-64
 N_FREQ_DIR, MAX_EXP_DIR = 4, 4.0       # models/mipnerf.py:65-71
@@ -158,7 +158,8 @@ class MipFieldRaw(Function):
                                            f32(p12) if p12 is not None else None, f32(bins[a:b]), f32(freqs),
                                            CONE_RADIUS, b - a, S, f32(raw_sigma[a:b]), f32(raw_rgb[a:b]), S, ptr(st),
                                            stream()), "star_mip_field_forward")
-            _prof_end("mip_field_forward_stash" if st is not None else "mip_field_forward", e0, (b - a) * S)
+            _prof_end("mip_field_forward_stash" if st is not None else "mip_field_forward", e0, (b - a) * S,
+                      2.0 * MIP_MAC_PER_SAMPLE * (b - a) * S)
             _count()
         if need_grad:
             ctx.rt, ctx.precision, ctx.chunks, ctx.stashes = rt, precision, chunks, stashes if keep else None
@@ -201,7 +202,7 @@ class MipFieldRaw(Function):
                                             CONE_RADIUS, b - a, S, f32(g_sigma[a:b]), f32(g_rgb[a:b]), S, ptr(st),
                                             ptr(ws), f32(grad_flat), f32(pose_acc) if pose_acc is not None else None,
                                             stream()), "star_mip_field_backward")
-            _prof_end("mip_field_backward", e0, n)
+            _prof_end("mip_field_backward", e0, n, 4.0 * MIP_MAC_PER_SAMPLE * n)
             _count(15)
             if ctx.stashes is not None:
                 ctx.stashes[i] = None

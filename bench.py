@@ -41,6 +41,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="render", choices=["render", "train"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
+                    help="c2: lego vanilla NeRF (the headline, BASELINE.json configs[1]); c4: carla_star_online_multi "
+                         "(static + 5 objects, 256+256 samples, 7-vector poses); c5: carla_star_app_init_mip (mip-NeRF "
+                         "fields, 256+512 frustums).  c4 / c5 are extra measurements; the driver runs c2.")
+    ap.add_argument("--rays", type=int, default=0, help="c4 / c5: rays per step per GPU (0 = default of the workload)")
     ap.add_argument("--precision", default=os.environ.get("STAR_B200_PRECISION", "bf16"), choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--hw", type=int, default=RENDER_HW, help="render mode: view is hw x hw rays")
     ap.add_argument("--train-rays", type=int, default=TRAIN_RAYS)
@@ -194,6 +199,20 @@ def metric_name(mode):
 
 
 def workload_config(args, precision):
+    wk = getattr(args, "workload", "c2")
+    if wk == "c4":
+        R = args.rays or (8192 if args.mode == "train" else 65536)
+        wl = ("C4 carla_star_online_multi: static + 5 rigid objects (7-vector poses), coarse+fine 256+256, %d CARLA-shaped "
+              "rays/step/GPU, %s" % (R, "training step (fwd+bwd to all MLP weights and the poses, 3 regularisers)"
+                                     if args.mode == "train" else "eval render"))
+        return {"workload": wl, "N_samples": 256, "N_importance": 256, "num_vehicles": 5, "mlp_precision": precision,
+                "parallelism": "ray-sharded x%d" % args.gpus, "l2": "L2 flushed between timed iterations (256 MB write)"}
+    if wk == "c5":
+        R = args.rays or 16384
+        wl = ("C5 carla_star_app_init_mip: mip-NeRF field (IPE), 256+512 frustums, %d CARLA-shaped rays/step/GPU, %s" % (
+            R, "training step" if args.mode == "train" else "eval render"))
+        return {"workload": wl, "N_samples": 256, "N_importance": 512, "mlp_precision": precision,
+                "parallelism": "ray-sharded x%d" % args.gpus, "l2": "L2 flushed between timed iterations (256 MB write)"}
     if args.mode == "render":
         wl = "C2 lego vanilla NeRF coarse+fine 64+128, full %dx%d view render (%d rays/step/GPU), eval, perturb=0" % (
             args.hw, args.hw, args.hw * args.hw)
@@ -203,6 +222,122 @@ def workload_config(args, precision):
             "parallelism": "ray-sharded x%d" % args.gpus,
             "l2": "inputs+activations per step exceed the 126 MB L2" if args.mode == "render" else
                   "L2 flushed between timed iterations (256 MB write)"}
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+def build_workload(args, dev, rank, world):
+    """Returns (net, ro_h, rd_h, step_device, params, d2h) for args.workload / args.mode.
+    step_device(ro, rd) runs one pass from device-resident rays; d2h(out) reads the step's result back to the host."""
+    import star_b200
+    from star_b200.models import rendering__ as R_
+    from oracle import ref_harness, star_oracle as so  # argument / synthetic-input builders only; no compute
+    train = args.mode == "train"
+    wk = args.workload
+    if wk == "c2":
+        net = star_b200.STaR(ref_harness.make_args(num_vehicles=0, N_importance=NI, chunk=8192, white_bkgd=True))
+        net.load_state_dict(make_params())
+        net.to(dev)
+        net.set_precision(args.precision)
+        net.train(train)
+        if train:
+            ro_h, rd_h = lego_view(RENDER_HW, theta=30.0 + 7.0 * rank)
+            g = torch.Generator().manual_seed(100 + rank)
+            idx = torch.randperm(ro_h.shape[0], generator=g)[:args.train_rays]
+            ro_h, rd_h = ro_h[idx].contiguous(), rd_h[idx].contiguous()
+            u = torch.rand(args.train_rays, NI, generator=g).to(dev)
+            target = torch.rand(args.train_rays, 3, generator=g).to(dev)
+        else:
+            ro_h, rd_h = lego_view(args.hw, theta=30.0 + 7.0 * rank)
+        params = [p for p in net.parameters()]
+
+        def step_device(ro, rd):
+            vd = rd / rd.norm(dim=-1, keepdim=True)
+            if train:
+                for p in params:
+                    p.grad = None
+                pts, z = R_.sample_pts(ro, rd, NEAR, FAR, NC, perturb=0, is_train=True)
+                out = R_.render_star_appinit(net, pts, vd, z, ro, rd, NI, u=u)
+                loss = ((out["rgb"] - target) ** 2).mean() + ((out["rgb0"] - target) ** 2).mean()
+                loss.backward()
+                if world > 1:
+                    star_b200.parallel.allreduce_gradients(params)     # one NCCL all-reduce of the flat gradient
+                return loss
+            with torch.no_grad():
+                pts, z = R_.sample_pts(ro, rd, NEAR, FAR, NC, perturb=0, is_train=False)
+                out = R_.render_star_appinit(net, pts, vd, z, ro, rd, NI)
+            return out
+        return net, ro_h, rd_h, step_device, params
+
+    V = 5
+    R = args.rays or ((8192 if train else 65536) if wk == "c4" else 16384)
+    ro_h, rd_h = so.carla_rays(R, seed=10 + rank)
+    g = torch.Generator().manual_seed(200 + rank)
+    target = torch.rand(R, 3, generator=g).to(dev)
+    if wk == "c4":
+        Nc = Ni = 256
+        net = star_b200.STaR(ref_harness.make_args(num_vehicles=V, N_importance=Ni, chunk=8192, white_bkgd=False))
+        net.load_state_dict(so.init_star_params(V, Ni, seed=0, bias_std=0.02))
+        net.to(dev)
+        net.set_precision(args.precision)
+        net.train(train)
+        pose = torch.nn.Parameter(so.random_poses7(V, seed=3).to(dev))
+        params = [p for p in net.parameters()] + [pose]
+        u = torch.rand(R, Ni, generator=g).to(dev) if train else None
+
+        def step_device(ro, rd):
+            vd = rd / rd.norm(dim=-1, keepdim=True)
+            if train:
+                for p in params:
+                    p.grad = None
+                pts, z = R_.sample_pts(ro, rd, 0.03, 0.8, Nc, perturb=0, is_train=True)
+                out = R_.render_star_online(net, pts, vd, z, ro, rd, Ni, pose, u=u)
+                loss = ((out["rgb"] - target) ** 2).mean() + ((out["rgb0"] - target) ** 2).mean()
+                for sfx in ("", "0"):        # configs/carla_star_online_multi.txt:72-74
+                    loss = loss + 0.5 * (1e-3 * out["loss_alpha_entropy" + sfx] + 1e-3 * out["loss_dynamic_vs_static_reg" + sfx]
+                                         + 1e-5 * out["loss_ray_reg" + sfx])
+                loss.backward()
+                if world > 1:
+                    star_b200.parallel.allreduce_gradients(params)
+                return loss
+            with torch.no_grad():
+                pts, z = R_.sample_pts(ro, rd, 0.03, 0.8, Nc, perturb=0, is_train=False)
+                out = R_.render_star_online(net, pts, vd, z, ro, rd, Ni, pose)
+            return out
+        return net, ro_h, rd_h, step_device, params
+
+    # c5: mip variant (static field only in app-init mode, star_mipnerf.py:262-300)
+    import argparse as _ap
+    from star_b200.models.star_mipnerf import STaR as MipSTaR
+    from oracle import mip_oracle as mo
+    margs = _ap.Namespace(num_vehicles=0, chunk=8192, far_dist=1e10, N_importance=512, N_samples=256, scale_factor=0.01,
+                          near=3.0, far=80.0)
+    net = MipSTaR(margs)
+    net.load_state_dict(mo.init_mip_params(0, seed=0, gain=1.4, bias_std=0.02))
+    net.to(dev)
+    net.set_precision(args.precision if args.precision in MIP_TIERS else "fp32")
+    net.train(train)
+    params = [p for p in net.parameters()]
+    t_rand = torch.rand(R, 257, generator=g).to(dev) if train else None
+    u_rand = torch.rand(R, 513, generator=g).to(dev) if train else None
+
+    def step_device(ro, rd):
+        vd = rd / rd.norm(dim=-1, keepdim=True)
+        if train:
+            for p in params:
+                p.grad = None
+            out = net(ro, vd, None, t_rand=t_rand, u_rand=u_rand)
+            loss = ((out["rgb"] - target) ** 2).mean() + 0.1 * ((out["rgb0"] - target) ** 2).mean()   # train_app_init_mip.py:60
+            loss.backward()
+            if world > 1:
+                star_b200.parallel.allreduce_gradients(params)
+            return loss
+        with torch.no_grad():
+            out = net(ro, vd, None)
+        return out
+    return net, ro_h, rd_h, step_device, params
+
+
+MIP_TIERS = ("fp32",)      # precision tiers compiled for the mip field
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -217,7 +352,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     line = measure(args)
-    if args.mode == "render" and not args.no_train_extra:
+    if args.mode == "render" and not args.no_train_extra and args.workload == "c2":
         # the metric also names the training step: measure it on the same box and attach it to the line
         a2 = argparse.Namespace(**vars(args))
         a2.mode, a2.no_cpu_baseline = "train", True
@@ -244,44 +379,12 @@ def measure(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", local)
 
-    net = star_b200.STaR(ref_harness.make_args(num_vehicles=0, N_importance=NI, chunk=8192, white_bkgd=True))
-    net.load_state_dict(make_params())
-    net.to(dev)
-    net.set_precision(args.precision)
     train = args.mode == "train"
-    net.train(train)
-
-    if train:
-        ro_h, rd_h = lego_view(RENDER_HW, theta=30.0 + 7.0 * rank)
-        g = torch.Generator().manual_seed(100 + rank)
-        idx = torch.randperm(ro_h.shape[0], generator=g)[:args.train_rays]
-        ro_h, rd_h = ro_h[idx].contiguous(), rd_h[idx].contiguous()
-        u = torch.rand(args.train_rays, NI, generator=g).to(dev)
-        target = torch.rand(args.train_rays, 3, generator=g).to(dev)
-    else:
-        ro_h, rd_h = lego_view(args.hw, theta=30.0 + 7.0 * rank)
+    net, ro_h, rd_h, step_device, params = build_workload(args, dev, rank, world)
     R = ro_h.shape[0]
     ro_h, rd_h = ro_h.pin_memory(), rd_h.pin_memory()
     ro, rd = ro_h.to(dev), rd_h.to(dev)
-    params = [p for p in net.parameters()]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if train else None
-
-    def step_device(ro, rd):
-        vd = rd / rd.norm(dim=-1, keepdim=True)
-        if train:
-            for p in params:
-                p.grad = None
-            pts, z = R_.sample_pts(ro, rd, NEAR, FAR, NC, perturb=0, is_train=True)
-            out = R_.render_star_appinit(net, pts, vd, z, ro, rd, NI, u=u)
-            loss = ((out["rgb"] - target) ** 2).mean() + ((out["rgb0"] - target) ** 2).mean()
-            loss.backward()
-            if world > 1:
-                star_b200.parallel.allreduce_gradients(params)     # one NCCL all-reduce of the flat gradient
-            return loss
-        with torch.no_grad():
-            pts, z = R_.sample_pts(ro, rd, NEAR, FAR, NC, perturb=0, is_train=False)
-            out = R_.render_star_appinit(net, pts, vd, z, ro, rd, NI)
-        return out
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if (train or args.workload != "c2") else None
 
     def step_e2e():
         a = ro_h.to(dev, non_blocking=True)
@@ -289,7 +392,7 @@ def measure(args):
         out = step_device(a, b)
         if train:
             return out.cpu()
-        return out["rgb"].cpu(), out["depth"].cpu(), out["acc"].cpu()
+        return out["rgb"].cpu(), out["depth"].cpu(), out["acc"].cpu()     # 20 B per ray
 
     def barrier():
         if world > 1:
@@ -349,21 +452,22 @@ def measure(args):
         parts = {}
         for k, evs in (prof or {}).items():
             if evs:
-                parts[k] = {"ms": sum(a.elapsed_time(b) for a, b, _ in evs), "samples": sum(n for _, _, n in evs),
-                            "launches": len(evs)}
+                parts[k] = {"ms": sum(a.elapsed_time(b) for a, b, _, _ in evs), "samples": sum(n for _, _, n, _ in evs),
+                            "flops": sum(f for _, _, _, f in evs), "launches": len(evs)}
         if parts:
-            # dominant C-ABI call of the step: its algorithmic FLOPs (MLP 2*MAC per sample; backward = dX + dW = 2x)
+            # dominant C-ABI call of the step and its algorithmic FLOPs (2 FLOP per MAC of the MLP layers, padding
+            # excluded; backward = dX + dW = 2x forward), summed over the launches of the timed region
             key = max(parts, key=lambda k: parts[k]["ms"])
-            flop_per_sample = F_STATIC * (2.0 if key == "mlp_backward" else 1.0)
             tot_ms, tot_samples, n_l = parts[key]["ms"], parts[key]["samples"], parts[key]["launches"]
             peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(
                 os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
             peak_tf = (peak["bf16_tflops_sustained"] if peak else 1400.0)
-            ach = tot_samples * flop_per_sample / (tot_ms * 1e-3) / 1e12
+            ach = parts[key]["flops"] / (tot_ms * 1e-3) / 1e12
             # dram__bytes_read+write per launch from the committed ncu capture (profiles/r1c_mlp_fwd_tc.md:
             # 7.83 MB per 524288-sample launch = 14.9 B/sample), scaled to this run's average launch
             traffic = 14.93 * tot_samples / n_l if (args.precision != "fp32" and key == "mlp_forward") else None
-            roof = {"bound": "tensor", "kernel": "star_%s (%s)" % (key, args.precision), "achieved": ach,
+            tier = args.precision if not key.startswith("mip") else (args.precision if args.precision in MIP_TIERS else "fp32")
+            roof = {"bound": "tensor", "kernel": "star_%s (%s)" % (key, tier), "achieved": ach,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peak else "fallback",
                     "launches": n_l, "avg_launch_ms": tot_ms / n_l,
@@ -372,13 +476,15 @@ def measure(args):
         line = {
             "metric": metric_name(args.mode), "value": total_rays / (ms * 1e-3), "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision],
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[
+                args.precision if (args.workload != "c5" or (args.precision in MIP_TIERS and not train)) else "fp32"],
             "data": "synthetic", "config": workload_config(args, args.precision),
             "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 24 * R,
                     "d2h_bytes_per_step": (4 if train else 20 * R)},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "wall_ms_per_step": t_wall * 1e3 / args.steps,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and args.workload == "c2":
             threads = os.cpu_count() or 1
             n = args.cpu_sample_rays or cpu_sample_default(args.mode, threads)
             fn = cpu_train_rays_per_s if train else cpu_render_rays_per_s
