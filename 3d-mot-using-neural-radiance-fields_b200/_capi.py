@@ -70,7 +70,7 @@ _SIGS = {
                                       c_f, c_f, c_f, c_f, c_f]),
     "star_mip_param_count": (C.c_size_t, []),
     "star_mip_packed_bytes": (C.c_size_t, [C.c_int]),
-    "star_mip_pack_weights": (C.c_int, [C.c_int, c_f, c_f, c_f]),
+    "star_mip_pack_weights": (C.c_int, [C.c_int, c_f, c_f, c_f, c_f]),
     "star_mip_stash_bytes": (C.c_size_t, [C.c_int, c_i64]),
     "star_mip_backward_workspace_bytes": (C.c_size_t, [C.c_int, c_i64]),
     "star_mip_field_forward": (C.c_int, [C.c_int, c_f, c_f, c_f, c_f, c_f, c_f, C.c_float, C.c_int, C.c_int, c_f, c_f,

@@ -164,6 +164,12 @@ int star_mip_f32_backward(const MipLayout& lay, const void* packed, const float*
                           const float* d_raw_sigma, const float* d_raw_rgb, int64_t ray_stride, const void* stash,
                           void* workspace, float* grad_flat, float* pose_acc, cudaStream_t st);
 
+size_t star_mip_tc_packed_bytes();
+int star_mip_tc_pack(const float* master, const float* freqs, void* packed, int fp16, cudaStream_t st);
+int star_mip_tc_forward(const void* packed, const float* origins, const float* dirs, const float* pose12,
+                        const float* bins, float radius, int R, int S, float* raw_sigma, float* raw_rgb,
+                        int64_t ray_stride, int fp16, cudaStream_t st);
+
 extern "C" size_t star_mip_param_count(void) {
   MipLayout lay;
   star_make_mip_layout(&lay);
@@ -174,14 +180,20 @@ extern "C" size_t star_mip_packed_bytes(int precision) {
   MipLayout lay;
   star_make_mip_layout(&lay);
   if (precision == STAR_PREC_F32) return sizeof(float) * (size_t)lay.n_packed;
+  if (precision == STAR_PREC_BF16 || precision == STAR_PREC_F16) return star_mip_tc_packed_bytes();
   return 0;
 }
 
-extern "C" int star_mip_pack_weights(int precision, const float* flat_master, void* packed, void* stream) {
+extern "C" int star_mip_pack_weights(int precision, const float* flat_master, const float* freqs, void* packed,
+                                     void* stream) {
   if (!flat_master || !packed) return STAR_E_NULL;
   MipLayout lay;
   star_make_mip_layout(&lay);
   if (precision == STAR_PREC_F32) return star_mip_f32_pack(lay, flat_master, packed, (cudaStream_t)stream);
+  if (precision == STAR_PREC_BF16 || precision == STAR_PREC_F16) {
+    if (!freqs) return STAR_E_NULL;
+    return star_mip_tc_pack(flat_master, freqs, packed, precision == STAR_PREC_F16, (cudaStream_t)stream);
+  }
   return STAR_E_UNSUPPORTED;
 }
 
@@ -211,6 +223,11 @@ extern "C" int star_mip_field_forward(int precision, const void* packed, const f
   if (precision == STAR_PREC_F32)
     return star_mip_f32_forward(lay, packed, origins, dirs, pose12, bins, freqs, radius, R, S, raw_sigma, raw_rgb,
                                 ray_stride, stash, (cudaStream_t)stream);
+  if (precision == STAR_PREC_BF16 || precision == STAR_PREC_F16) {
+    if (stash != nullptr) return STAR_E_UNSUPPORTED;   // tensor-core tier of the mip field: inference only
+    return star_mip_tc_forward(packed, origins, dirs, pose12, bins, radius, R, S, raw_sigma, raw_rgb, ray_stride,
+                               precision == STAR_PREC_F16, (cudaStream_t)stream);
+  }
   return STAR_E_UNSUPPORTED;
 }
 

@@ -1,0 +1,512 @@
+// Tensor-core tier (tcgen05 / TMEM, bf16 or fp16 operands) of the mip-NeRF field forward pass (SURVEY.md row a12:
+// models/mipnerf.py:53-100 -> nerfstudio NeRFField with integrated positional encoding).  Same machine as
+// mlp_tc.cu: one persistent CTA per SM walks tiles of 128 samples with 16 epilogue warps, one weight-producer warp
+// (1-D bulk copies of pre-swizzled K-blocks into a 4-stage ring) and one MMA-issuer thread; accumulators alternate
+// between two 256-column TMEM regions so the epilogue of layer L overlaps the MMAs of layer L+1 K-block by K-block.
+//
+// Layer program per tile (K-blocks of 64 features; N = output width):
+//   encode IPE (147 -> 192) into A[0..2], encoded dirs (27 -> 32) into AD
+//   L0 : A[0..2]            N=256 ReLU                         L1..L3 : A[0..3] N=256 ReLU
+//   L4 : A[0..3] (x part), then -- once those MMAs are done (x_done) -- the epilogue warps RE-ENCODE the IPE into
+//        A[0..2] and 3 more K-blocks accumulate the skip connection's encoding part (nerfstudio MLP: cat[enc, x]);
+//        re-encoding costs ~2 % of a tile and saves 48 KB of shared memory that the weight ring needs
+//   L5..L7 : A[0..3] N=256 ReLU; L7's epilogue also takes the density head (fp32 dot on the rectified base_out)
+//   H0 : A[0..3] + AD       N=128 ReLU -> A[0..1]              H1 : A[0..1] N=128 ReLU + rgb head (fp32 dot)
+// Biases are fp32 and added in the epilogue; the two heads run in fp32 on un-rounded activations (as in mlp_tc.cu).
+// Forward / inference only: training uses the fp32 tier (mip_f32.cu).
+#include "star_common.cuh"
+#include <cuda_fp16.h>
+#include "tc_common.cuh"
+#include "mip_layout.h"
+#include "mlp_tc_device.cuh"
+
+#define MIP_TC_NL 10
+#define BAR_X_DONE (2 * TC_NS + 6)
+
+enum MipTcKind { MK_HID = 0, MK_BASE_OUT = 1, MK_H0 = 2, MK_H1 = 3 };
+
+struct MipTcLayer {
+  int nkb;          // K-blocks issued before the (optional) mid-layer barrier
+  int nkb_extra;    // layer 4: 3 K-blocks of the re-encoded input; H0: 1 K-block of encoded dirs
+  int N, region, kind;
+  int bias_off;     // float offset in the small section
+  uint32_t w_off;   // byte offset of the first K-block in the weight stream
+};
+
+struct MipTcLayout {
+  MipTcLayer L[MIP_TC_NL];
+  int off_dw, off_db, off_rw, off_rb, off_freq;   // float offsets: density head, rgb head, frequency table
+  int small_floats;
+  uint32_t small_bytes, stream_bytes;
+};
+
+static inline void star_make_mip_tc_layout(MipTcLayout* o) {
+  int fo = 0;
+  uint32_t wo = 0;
+  auto add = [&](int i, int nkb, int extra, int N, int region, int kind) {
+    MipTcLayer& l = o->L[i];
+    l.nkb = nkb; l.nkb_extra = extra; l.N = N; l.region = region; l.kind = kind;
+    l.bias_off = fo; fo += MIP_W;
+    l.w_off = wo; wo += (uint32_t)(nkb + extra) * (uint32_t)N * 128u;
+  };
+  add(0, 3, 0, MIP_W, 0, MK_HID);
+  for (int l = 1; l < MIP_NBASE; ++l)
+    add(l, 4, l == MIP_SKIP ? 3 : 0, MIP_W, l & 1, l == MIP_NBASE - 1 ? MK_BASE_OUT : MK_HID);
+  add(8, 4, 1, MIP_WH, 0, MK_H0);
+  add(9, 2, 0, MIP_WH, 1, MK_H1);
+  o->off_dw = fo; fo += MIP_W;
+  o->off_db = fo; fo += 4;
+  o->off_rw = fo; fo += 3 * MIP_WH;
+  o->off_rb = fo; fo += 4;
+  o->off_freq = fo; fo += MIP_FREQ_FLOATS;
+  o->small_floats = fo;
+  o->small_bytes = ((uint32_t)fo * 4u + TC_SMALL_ALIGN - 1) / TC_SMALL_ALIGN * TC_SMALL_ALIGN;
+  o->stream_bytes = wo;
+}
+
+#define MIP_TWO_PI 6.2831854820251465f
+#define MIP_PIO2 1.5707963705062866f
+
+// sin for arguments up to ~1e5 at 16-bit-operand accuracy: two-term Cody-Waite reduction by 2 pi, then the SFU
+__device__ __forceinline__ float sin_reduced(float a) {
+  const float n = rintf(a * 0.15915494309189535f);
+  float r = fmaf(-n, 6.28318548202514648f, a);
+  r = fmaf(-n, -1.74845553146951715e-7f, r);
+  return __sinf(r);
+}
+
+struct MipTcGeom {
+  float mean[3], diag[3], d[3];
+};
+
+__device__ __forceinline__ MipTcGeom mip_tc_geom(const float* __restrict__ origins, const float* __restrict__ dirs,
+                                                 const float* __restrict__ pose12, const float* __restrict__ bins,
+                                                 int64_t gi, int S, float radius) {
+  MipTcGeom g;
+  const int64_t r = gi / S;
+  const int s = (int)(gi - r * S);
+  const float ox = origins[r * 3 + 0], oy = origins[r * 3 + 1], oz = origins[r * 3 + 2];
+  const float dx = dirs[r * 3 + 0], dy = dirs[r * 3 + 1], dz = dirs[r * 3 + 2];
+  float o[3];
+  if (pose12 != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      o[i] = pose12[i * 3 + 0] * ox + pose12[i * 3 + 1] * oy + pose12[i * 3 + 2] * oz + pose12[9 + i];
+      g.d[i] = pose12[i * 3 + 0] * dx + pose12[i * 3 + 1] * dy + pose12[i * 3 + 2] * dz;
+    }
+  } else {
+    o[0] = ox; o[1] = oy; o[2] = oz;
+    g.d[0] = dx; g.d[1] = dy; g.d[2] = dz;
+  }
+  // conical_frustum_to_gaussian with the reference's rounding sequence (see mip_f32.cu)
+  const float st = bins[r * (S + 1) + s], en = bins[r * (S + 1) + s + 1];
+  const float mu = __fdiv_rn(__fadd_rn(st, en), 2.f), hw = __fdiv_rn(__fsub_rn(en, st), 2.f);
+  const float mu2 = __fmul_rn(mu, mu), hw2 = __fmul_rn(hw, hw), hw4 = __fmul_rn(hw2, hw2);
+  const float den = __fadd_rn(__fmul_rn(3.f, mu2), hw2);
+  const float tmean = __fadd_rn(mu, __fdiv_rn(__fmul_rn(__fmul_rn(2.f, mu), hw2), den));
+  const float dvar = __fsub_rn(__fdiv_rn(hw2, 3.f),
+                               __fmul_rn(4.f / 15.f, __fdiv_rn(__fmul_rn(hw4, __fsub_rn(__fmul_rn(12.f, mu2), hw2)), __fmul_rn(den, den))));
+  const float rvar = __fmul_rn(radius * radius,
+                               __fsub_rn(__fadd_rn(__fdiv_rn(mu2, 4.f), __fmul_rn(5.f / 12.f, hw2)), __fdiv_rn(__fmul_rn(4.f / 15.f, hw4), den)));
+  const float mag = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(g.d[0], g.d[0]), __fmul_rn(g.d[1], g.d[1])), __fmul_rn(g.d[2], g.d[2])), 1e-10f);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    g.mean[c] = __fadd_rn(o[c], __fmul_rn(g.d[c], tmean));
+    g.diag[c] = __fadd_rn(__fmul_rn(dvar, __fmul_rn(g.d[c], g.d[c])),
+                          __fmul_rn(rvar, __fsub_rn(1.f, __fmul_rn(g.d[c], __fdiv_rn(g.d[c], mag)))));
+  }
+  return g;
+}
+
+// feature j (0..191) of the integrated positional encoding: [e sin(a) (72) | e sin(a + pi/2) (72) | mean (3) | 0]
+__device__ __forceinline__ float ipe_feature(const MipTcGeom& g, const float* __restrict__ s_f, int j) {
+  if (j >= MIP_KX) return 0.f;
+  if (j >= 6 * MIP_NF) return j == 6 * MIP_NF ? g.mean[0] : (j == 6 * MIP_NF + 1 ? g.mean[1] : g.mean[2]);
+  const int jj = j < 3 * MIP_NF ? j : j - 3 * MIP_NF;
+  const int c = jj / MIP_NF, k = jj - c * MIP_NF;
+  const float mc = c == 0 ? g.mean[0] : (c == 1 ? g.mean[1] : g.mean[2]);
+  const float dc = c == 0 ? g.diag[0] : (c == 1 ? g.diag[1] : g.diag[2]);
+  const float hv = -0.5f * __fmul_rn(dc, s_f[MIP_NF + k]);
+  if (hv < -104.f) return 0.f;           // exp underflows to 0 in fp32: the reference's feature is exactly 0
+  float a = __fmul_rn(__fmul_rn(MIP_TWO_PI, mc), s_f[k]);
+  if (j >= 3 * MIP_NF) a = __fadd_rn(a, MIP_PIO2);
+  return __expf(hv) * sin_reduced(a);
+}
+
+template <bool FP16>
+__device__ __forceinline__ void encode_ipe_blocks(const MipTcGeom& g, const float* __restrict__ s_f, uint32_t sA, int row,
+                                                  int cg) {
+#pragma unroll 1
+  for (int kb = 0; kb < 3; ++kb) {
+    float e[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) e[j] = ipe_feature(g, s_f, kb * 64 + cg * 16 + j);
+    store_row16<FP16, false>(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, e);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- epilogue
+struct MipEpi {
+  uint32_t sA, a_ready0, tcol;
+  const float* bias;
+  const float* head_w;
+  int row, cg, lane;
+};
+
+template <int KIND, bool FP16>
+__device__ __forceinline__ void mip_epilogue(const MipEpi& c, float (&h)[3]) {
+  constexpr int NCH = (KIND == MK_H0 || KIND == MK_H1) ? 2 : 4;
+  uint32_t r[2][TC_CPT];
+  tmem_ld16(c.tcol, r[0]);
+  float4 bq[TC_CPT / 4];
+#pragma unroll
+  for (int j4 = 0; j4 < TC_CPT / 4; ++j4) bq[j4] = *reinterpret_cast<const float4*>(c.bias + c.cg * TC_CPT + 4 * j4);
+#pragma unroll
+  for (int kb = 0; kb < NCH; ++kb) {
+    tmem_wait_ld();
+    if (kb + 1 < NCH) tmem_ld16(c.tcol + 64u * (uint32_t)(kb + 1), r[(kb + 1) & 1]);
+    const int col0 = kb * 64 + c.cg * TC_CPT;
+    float v[TC_CPT];
+#pragma unroll
+    for (int j4 = 0; j4 < TC_CPT / 4; ++j4) {
+      v[4 * j4 + 0] = __uint_as_float(r[kb & 1][4 * j4 + 0]);
+      v[4 * j4 + 1] = __uint_as_float(r[kb & 1][4 * j4 + 1]);
+      v[4 * j4 + 2] = __uint_as_float(r[kb & 1][4 * j4 + 2]);
+      v[4 * j4 + 3] = __uint_as_float(r[kb & 1][4 * j4 + 3]);
+      add_f32x2(v[4 * j4 + 0], v[4 * j4 + 1], bq[j4].x, bq[j4].y);
+      add_f32x2(v[4 * j4 + 2], v[4 * j4 + 3], bq[j4].z, bq[j4].w);
+    }
+    if (kb + 1 < NCH) {
+#pragma unroll
+      for (int j4 = 0; j4 < TC_CPT / 4; ++j4) bq[j4] = *reinterpret_cast<const float4*>(c.bias + col0 + 64 + 4 * j4);
+    }
+    if (KIND == MK_BASE_OUT) {       // density head on the rectified base_out (fp32)
+#pragma unroll
+      for (int j = 0; j < TC_CPT; ++j) h[0] = fmaf(fmaxf(v[j], 0.f), c.head_w[col0 + j], h[0]);
+    }
+    if (KIND == MK_H1) {             // rgb head on the rectified head output (fp32)
+#pragma unroll
+      for (int j = 0; j < TC_CPT; ++j) {
+        const float x = fmaxf(v[j], 0.f);
+        h[0] = fmaf(x, c.head_w[col0 + j], h[0]);
+        h[1] = fmaf(x, c.head_w[MIP_WH + col0 + j], h[1]);
+        h[2] = fmaf(x, c.head_w[2 * MIP_WH + col0 + j], h[2]);
+      }
+    } else {
+      store_row16<FP16, true>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (c.lane == 0) mbar_arrive(c.a_ready0 + 8u * (uint32_t)kb);
+    }
+  }
+}
+
+// ============================================================================================ forward
+template <bool FP16>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+mip_fwd_tc_kernel(const MipTcLayout lay, const uint8_t* __restrict__ packed, const float* __restrict__ origins,
+                  const float* __restrict__ dirs, const float* __restrict__ pose12, const float* __restrict__ bins,
+                  float radius, int S, int64_t M, float* __restrict__ raw_sigma, float* __restrict__ raw_rgb,
+                  int64_t ray_stride, int* dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw_addr);
+  const TcSmem sl = tc_smem_layout(lay.small_bytes);
+  const uint32_t sA = base + sl.A, sAD = base + sl.AD, sW = base + sl.W, sBars = base + sl.bars;
+  float* s_small = reinterpret_cast<float*>(gbase + sl.small);
+  const float* s_f = s_small + lay.off_freq;
+  auto part = [&](int r, int g) -> float* {   // head partial sums of column group g: unused half of the dirs block
+    return reinterpret_cast<float*>(gbase + sl.part + (uint32_t)r * 128u + ((((uint32_t)(3 + g)) ^ ((uint32_t)r & 7u)) << 4));
+  };
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(gbase + sl.tmem_ptr);
+  auto bar = [&](int i) -> uint32_t { return sBars + 8u * (uint32_t)i; };
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (M + TC_M - 1) / TC_M;
+
+  if (warp == TC_EPI_WARPS && lane == 0) {
+    for (int i = 0; i < TC_NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), 1); mbar_init(bar(BAR_W_EMPTY(i)), 1); }
+    for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A_READY(i)), TC_EPI_WARPS);
+    mbar_init(bar(BAR_ACC_FULL), 1);
+    mbar_init(bar(BAR_X_DONE), 1);
+    fence_mbar_init();
+  }
+  if (warp == TC_EPI_WARPS + 1) tmem_alloc(base + sl.tmem_ptr, TC_TMEM_COLS);
+  for (int i = tid; i < lay.small_floats; i += TC_THREADS) s_small[i] = reinterpret_cast<const float*>(packed)[i];
+  for (int i = tid; i < TC_KB_BYTES / 16; i += TC_THREADS)
+    reinterpret_cast<uint4*>(gbase + sl.AD)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == TC_EPI_WARPS) {
+    // ======================================================================== weight producer
+    if (lane == 0) {
+      const uint8_t* wstream = packed + lay.small_bytes;
+      uint32_t stage = 0, phase = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int l = 0; l < MIP_TC_NL; ++l) {
+          const uint32_t bytes = (uint32_t)lay.L[l].N * 128u;
+          const int n = lay.L[l].nkb + lay.L[l].nkb_extra;
+          for (int kb = 0; kb < n; ++kb) {
+            mbar_wait(bar(BAR_W_EMPTY(stage)), phase ^ 1u, dbg, 1);
+            mbar_arrive_expect_tx(bar(BAR_W_FULL(stage)), bytes);
+            bulk_g2s(sW + stage * TC_STAGE_BYTES, wstream + lay.L[l].w_off + (uint32_t)kb * bytes, bytes,
+                     bar(BAR_W_FULL(stage)));
+            if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == TC_EPI_WARPS + 1) {
+    // ======================================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, a_par = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int l = 0; l < MIP_TC_NL; ++l) {
+          const MipTcLayer& L = lay.L[l];
+          const uint32_t d_tmem = tmem_base + (L.region ? 256u : 0u);
+          const uint32_t idesc = umma_idesc_16(TC_M, L.N, FP16 ? 0 : 1);
+          const int n = L.nkb + L.nkb_extra;
+          for (int kb = 0; kb < n; ++kb) {
+            // operand block: A[kb] for the main K-blocks; the skip layer's extra blocks re-use A[0..2]; H0's extra
+            // block is the encoded-dirs block (2 of its 4 K-steps are used)
+            const bool extra = kb >= L.nkb;
+            const bool is_dirs = extra && L.kind == MK_H0;
+            const int idx = is_dirs ? 4 : (extra ? kb - L.nkb : kb);
+            if (extra && kb == L.nkb && !is_dirs) tc_commit(bar(BAR_X_DONE));   // x-part MMAs done -> A may be re-encoded
+            mbar_wait(bar(BAR_A_READY(idx)), (a_par >> idx) & 1u, dbg, 2);
+            a_par ^= 1u << idx;
+            mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
+            tc_fence_after();
+            const uint32_t a_addr = is_dirs ? sAD : sA + (uint32_t)idx * TC_KB_BYTES;
+            const uint32_t b_addr = sW + stage * TC_STAGE_BYTES;
+            const int nk = is_dirs ? 2 : 4;
+            for (int k = 0; k < nk; ++k)
+              tc_mma_bf16(d_tmem, umma_desc_sw128(a_addr + 32u * k), umma_desc_sw128(b_addr + 32u * k), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit(bar(BAR_W_EMPTY(stage)));
+            if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
+          }
+          tc_commit(bar(BAR_ACC_FULL));
+        }
+      }
+    }
+  } else {
+    // ======================================================================== epilogue warps
+    const int q = warp & 3, cg = warp >> 2;
+    const int row = q * 32 + lane;
+    uint32_t acc_par = 0, x_par = 0;
+    MipEpi ctx;
+    ctx.sA = sA; ctx.a_ready0 = bar(BAR_A_READY(0));
+    ctx.row = row; ctx.cg = cg; ctx.lane = lane;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t gi = tile * TC_M + row;
+      const bool valid = gi < M;
+      int64_t out_idx = 0;
+      MipTcGeom g;
+      if (valid) {
+        const int64_t r = gi / S;
+        out_idx = r * ray_stride + (gi - r * S);
+        g = mip_tc_geom(origins, dirs, pose12, bins, gi, S, radius);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { g.mean[c] = 0.f; g.diag[c] = 1e30f; g.d[c] = 0.f; }
+      }
+      // ---- inputs: IPE -> A[0..2]; encoded dirs -> AD (columns 0..31: groups 0 and 1)
+      encode_ipe_blocks<FP16>(g, s_f, sA, row, cg);
+      if (cg < 2) {
+        float e[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = cg * 16 + j;
+          float v = 0.f;
+          if (col < 6 * MIP_NFD) {
+            const int jj = col < 3 * MIP_NFD ? col : col - 3 * MIP_NFD;
+            const int c = jj / MIP_NFD, k = jj - c * MIP_NFD;
+            const float dc = c == 0 ? g.d[0] : (c == 1 ? g.d[1] : g.d[2]);
+            float a = __fmul_rn(__fmul_rn(MIP_TWO_PI, dc), s_f[2 * MIP_NF + k]);
+            if (col >= 3 * MIP_NFD) a = __fadd_rn(a, MIP_PIO2);
+            v = sin_reduced(a);
+          } else if (col < MIP_KD) {
+            v = col == 6 * MIP_NFD ? g.d[0] : (col == 6 * MIP_NFD + 1 ? g.d[1] : g.d[2]);
+          }
+          e[j] = valid ? v : 0.f;
+        }
+        store_row16<FP16, false>(sAD, row, cg * 2, e);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(BAR_A_READY(0)));
+        mbar_arrive(bar(BAR_A_READY(1)));
+        mbar_arrive(bar(BAR_A_READY(2)));
+        mbar_arrive(bar(BAR_A_READY(4)));
+      }
+      // ---- layers
+      for (int l = 0; l < MIP_TC_NL; ++l) {
+        const MipTcLayer& L = lay.L[l];
+        if (L.kind != MK_H0 && L.nkb_extra > 0) {
+          // skip layer: once its x-part MMAs are complete the A blocks are free -> re-encode the input into A[0..2]
+          mbar_wait(bar(BAR_X_DONE), x_par, dbg, 6);
+          x_par ^= 1u;
+          tc_fence_after();
+          encode_ipe_blocks<FP16>(g, s_f, sA, row, cg);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(bar(BAR_A_READY(0)));
+            mbar_arrive(bar(BAR_A_READY(1)));
+            mbar_arrive(bar(BAR_A_READY(2)));
+          }
+        }
+        mbar_wait(bar(BAR_ACC_FULL), acc_par, dbg, 4);
+        acc_par ^= 1u;
+        tc_fence_after();
+        ctx.tcol = tmem_base + (((uint32_t)(q * 32)) << 16) + (L.region ? 256u : 0u) + (uint32_t)(cg * TC_CPT);
+        ctx.bias = s_small + L.bias_off;
+        float h[3] = {0.f, 0.f, 0.f};
+        if (L.kind == MK_HID) {
+          mip_epilogue<MK_HID, FP16>(ctx, h);
+        } else if (L.kind == MK_BASE_OUT) {
+          ctx.head_w = s_small + lay.off_dw;
+          mip_epilogue<MK_BASE_OUT, FP16>(ctx, h);
+          if (cg != 0) part(row, cg)[0] = h[0];
+          named_bar_sync(1, TC_EPI_THREADS);
+          if (cg == 0 && valid)
+            raw_sigma[out_idx] = h[0] + part(row, 1)[0] + part(row, 2)[0] + part(row, 3)[0] + s_small[lay.off_db];
+        } else if (L.kind == MK_H0) {
+          mip_epilogue<MK_H0, FP16>(ctx, h);
+        } else {
+          ctx.head_w = s_small + lay.off_rw;
+          mip_epilogue<MK_H1, FP16>(ctx, h);
+          if (cg != 0) {
+            float* d = part(row, cg);
+            d[1] = h[0]; d[2] = h[1]; d[3] = h[2];
+          }
+          tc_fence_before();
+          named_bar_sync(1, TC_EPI_THREADS);
+          if (cg == 0 && valid) {
+            float* o = raw_rgb + out_idx * 3;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+              o[ch] = h[ch] + part(row, 1)[1 + ch] + part(row, 2)[1 + ch] + part(row, 3)[1 + ch] + s_small[lay.off_rb + ch];
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_EPI_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// ============================================================================================ packing
+__global__ void mip_pack_tc_small_kernel(MipTcLayout tl, MipLayout ml, const float* __restrict__ master,
+                                         const float* __restrict__ freqs, float* __restrict__ small) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tl.small_floats; i += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    bool done = false;
+    for (int l = 0; l < MIP_TC_NL && !done; ++l) {
+      const int o = i - tl.L[l].bias_off;
+      if (o >= 0 && o < MIP_W) {
+        done = true;
+        const int ml_idx = l < MIP_NBASE ? l : (l == 8 ? MIP_L_H0 : MIP_L_H1);
+        if (o < tl.L[l].N) v = master[ml.m_b[ml_idx] + o];
+      }
+    }
+    if (!done) {
+      if (i >= tl.off_dw && i < tl.off_dw + MIP_W) v = master[ml.m_w[MIP_L_DENS] + (i - tl.off_dw)];
+      else if (i == tl.off_db) v = master[ml.m_b[MIP_L_DENS]];
+      else if (i >= tl.off_rw && i < tl.off_rw + 3 * MIP_WH) v = master[ml.m_w[MIP_L_RGB] + (i - tl.off_rw)];
+      else if (i >= tl.off_rb && i < tl.off_rb + 3) v = master[ml.m_b[MIP_L_RGB] + (i - tl.off_rb)];
+      else if (i >= tl.off_freq && i < tl.off_freq + MIP_FREQ_FLOATS) v = freqs[i - tl.off_freq];
+    }
+    small[i] = v;
+  }
+}
+
+__global__ void mip_pack_tc_stream_kernel(MipTcLayout tl, MipLayout ml, const float* __restrict__ master,
+                                          uint16_t* __restrict__ stream, int fp16) {
+  const uint32_t n_elems = tl.stream_bytes / 2;
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_elems; e += gridDim.x * blockDim.x) {
+    const uint32_t byte = e * 2;
+    int l = 0;
+    while (l + 1 < MIP_TC_NL && byte >= tl.L[l + 1].w_off) ++l;
+    const MipTcLayer& L = tl.L[l];
+    const uint32_t off = byte - L.w_off, kb_bytes = (uint32_t)L.N * 128u;
+    const int kb = (int)(off / kb_bytes);
+    const uint32_t rem = off % kb_bytes;
+    const int n = (int)(rem >> 7);
+    const uint32_t inrow = rem & 127u;
+    const int chunk = (int)((inrow >> 4) ^ ((uint32_t)n & 7u));   // undo the 128-byte swizzle
+    const int kk = chunk * 8 + (int)((inrow & 15u) >> 1);
+    const int ml_idx = l < MIP_NBASE ? l : (l == 8 ? MIP_L_H0 : MIP_L_H1);
+    const int K = ml.K[ml_idx];
+    int k = -1;   // master column of this element, -1 = zero padding
+    if (l == 0) {
+      k = kb * 64 + kk;
+      if (k >= MIP_KX) k = -1;
+    } else if (l == MIP_SKIP) {
+      if (kb < 4) k = MIP_KX + kb * 64 + kk;            // x part first (issue order), encoding part after x_done
+      else { k = (kb - 4) * 64 + kk; if (k >= MIP_KX) k = -1; }
+    } else if (l == 8) {
+      if (kb < 4) k = MIP_KD + kb * 64 + kk;            // base_out part, then the encoded-dirs block
+      else { k = kk; if (k >= MIP_KD) k = -1; }
+    } else {
+      k = kb * 64 + kk;
+    }
+    const float v = (k >= 0 && k < K) ? master[ml.m_w[ml_idx] + (int64_t)n * K + k] : 0.f;
+    stream[e] = fp16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  }
+}
+
+// ============================================================================================ host side
+size_t star_mip_tc_packed_bytes() {
+  MipTcLayout tl;
+  star_make_mip_tc_layout(&tl);
+  return (size_t)tl.small_bytes + tl.stream_bytes;
+}
+
+int star_mip_tc_pack(const float* master, const float* freqs, void* packed, int fp16, cudaStream_t st) {
+  MipTcLayout tl;
+  MipLayout ml;
+  star_make_mip_tc_layout(&tl);
+  star_make_mip_layout(&ml);
+  mip_pack_tc_small_kernel<<<8, 256, 0, st>>>(tl, ml, master, freqs, (float*)packed);
+  int rc = star_check_launch();
+  if (rc) return rc;
+  mip_pack_tc_stream_kernel<<<148 * 4, 256, 0, st>>>(tl, ml, master, (uint16_t*)((uint8_t*)packed + tl.small_bytes), fp16);
+  return star_check_launch();
+}
+
+int star_mip_tc_forward(const void* packed, const float* origins, const float* dirs, const float* pose12,
+                        const float* bins, float radius, int R, int S, float* raw_sigma, float* raw_rgb,
+                        int64_t ray_stride, int fp16, cudaStream_t st) {
+  MipTcLayout tl;
+  star_make_mip_tc_layout(&tl);
+  const int64_t M = (int64_t)R * S;
+  const int64_t ntiles = (M + TC_M - 1) / TC_M;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  const TcSmem sl = tc_smem_layout(tl.small_bytes);
+  if (((uintptr_t)packed & 15) != 0) return STAR_E_ALIGN;
+  auto kern = fp16 ? mip_fwd_tc_kernel<true> : mip_fwd_tc_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
+  if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
+  kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, origins, dirs, pose12, bins, radius, S, M,
+                                            raw_sigma, raw_rgb, ray_stride, nullptr);
+  return star_check_launch();
+}

@@ -122,7 +122,8 @@ class MipRuntime:
                 raise _capi.StarError("mip field: precision tier not available")
             assert self._flat.numel() == L.star_mip_param_count()
             packed = torch.empty((nbytes,), device=self._flat.device, dtype=torch.uint8)
-            check(L.star_mip_pack_weights(precision, f32(self._flat), ptr(packed), stream()), "star_mip_pack_weights")
+            check(L.star_mip_pack_weights(precision, f32(self._flat), f32(freq_table(self._flat.device)), ptr(packed),
+                                          stream()), "star_mip_pack_weights")
             _count()
             self._packed[precision] = packed
         return self._flat, self._packed[precision]
@@ -138,12 +139,14 @@ class MipFieldRaw(Function):
         origins, dirs, bins = _c(origins), _c(dirs), _c(bins.detach())
         R, S = bins.shape[0], bins.shape[1] - 1
         dev = origins.device
+        need_grad = grad_mode and (any(ctx.needs_input_grad[7:]) or (pose12 is not None and ctx.needs_input_grad[6]))
+        if need_grad:
+            precision = _capi.PREC_F32     # the tensor-core tier of the mip field is forward-only: training runs in fp32
         flat, packed = rt.refresh(precision)
         L = _capi.lib()
         freqs = freq_table(dev)
         raw_sigma = torch.empty((R, S), device=dev)
         raw_rgb = torch.empty((R, S, 3), device=dev)
-        need_grad = grad_mode and (any(ctx.needs_input_grad[7:]) or (pose12 is not None and ctx.needs_input_grad[6]))
         p12 = _c(pose12.detach()) if pose12 is not None else None
         chunks = _ray_chunks(R, S)
         keep = need_grad and L.star_mip_stash_bytes(precision, R * S) <= STASH_BUDGET_BYTES

@@ -337,7 +337,7 @@ def build_workload(args, dev, rank, world):
     return net, ro_h, rd_h, step_device, params
 
 
-MIP_TIERS = ("fp32",)      # precision tiers compiled for the mip field
+MIP_TIERS = ("fp32", "bf16", "fp16")      # precision tiers of the mip field (16-bit tiers: forward only)
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm

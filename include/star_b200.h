@@ -212,10 +212,12 @@ int star_mip_pdf_sample(const float* spacing_bins, const float* weights, int64_t
  * field) or [R(3x3) | t]: o' = R o + t, d' = R d (star_mipnerf.py:206-214).  freqs[64]: host table
  * [2**linspace(0,24,24) | its square | 2**linspace(0,4,4) | pad].  radius = sqrt(pixel_area)/sqrt(pi) (= 0.5642:
  * the reference passes pixel_area = 1, star_mipnerf.py:267).
- * Outputs are RAW (pre-softplus density, pre-sigmoid rgb), written with the strides of star_mlp_forward. */
+ * Outputs are RAW (pre-softplus density, pre-sigmoid rgb), written with the strides of star_mlp_forward.
+ * Precision tiers: STAR_PREC_F32 (CUDA cores, forward + backward) and STAR_PREC_BF16 / STAR_PREC_F16 (tcgen05
+ * tensor cores, forward / inference only: stash must be NULL; the frequency table is baked into the packed image). */
 size_t star_mip_param_count(void);
 size_t star_mip_packed_bytes(int precision);
-int star_mip_pack_weights(int precision, const float* flat_master, void* packed, void* stream);
+int star_mip_pack_weights(int precision, const float* flat_master, const float* freqs, void* packed, void* stream);
 size_t star_mip_stash_bytes(int precision, int64_t n_samples);
 size_t star_mip_backward_workspace_bytes(int precision, int64_t n_samples);
 int star_mip_field_forward(int precision, const void* packed, const float* origins, const float* dirs,

@@ -296,3 +296,74 @@ def test_mip_error_paths():
         net(cu(ro), cu(vd), torch.eye(4, device=DEV)[None])
     with pytest.raises(star_b200._capi.StarError):
         net(ro, vd)          # CPU tensors: there is no CPU path
+
+
+# ------------------------------------------------------------------------------------------ tensor-core tier
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("R,S,with_pose", [(4, 32, False), (70, 33, False), (16, 12, True), (301, 191, False), (1, 1, True)])
+def test_mip_tc_field_matches_rounding_model(R, S, with_pose, prec):
+    """tcgen05 tier of the mip field against (1) the oracle's operand-rounding model of the kernel (GEMM operands --
+    encodings, activations, weights -- rounded to 16 bits, fp32 accumulate / bias / heads) and (2) the fp32 oracle."""
+    net, sd = make_net(1, 4, 4, 64, seed=3, training=False, gain=1.4)
+    net.set_precision(prec)
+    ro, vd, eu = _field_inputs(R, S, 10)
+    model = net.dynamic_nerfs[0] if with_pose else net.static_nerf
+    prefix = "dynamic_nerfs.0." if with_pose else "static_nerf."
+    pose7 = so.random_poses7(1, seed=4)[0]
+    p = {k: v for k, v in sd.items() if k.startswith(prefix)}
+    o, d = (so.se3_act(pose7, ro), so.so3_act(pose7[3:], vd)) if with_pose else (ro, vd)
+    a_m, c_m = mo.mip_field(p, prefix, o, d, eu[:, :-1], eu[:, 1:], emulate=prec, return_raw=True)
+    a_f, c_f = mo.mip_field(p, prefix, o, d, eu[:, :-1], eu[:, 1:], return_raw=True)
+    with torch.no_grad():
+        p12 = star_b200.functional.pose_to_mat12(cu(pose7)) if with_pose else None
+        a, c = model.raw(cu(ro), cu(vd), cu(eu), p12)
+    scale = float(a_f.abs().max()) + float(c_f.abs().max()) + 1e-3
+    ea, ec = (a.cpu() - a_m).abs() / scale, (c.cpu() - c_m).abs() / scale
+    assert float(ea.mean()) < 1e-3 and float(ec.mean()) < 1e-3, (float(ea.mean()), float(ec.mean()))
+    assert float(ea.max()) < 6e-2 and float(ec.max()) < 6e-2, (float(ea.max()), float(ec.max()))
+    med = 1e-4 if prec == "bf16" else 1e-3
+    assert float(ea.median()) < med and float(ec.median()) < med, (float(ea.median()), float(ec.median()))
+    assert float((a.cpu() - a_f).abs().mean()) < 2e-2 * scale
+    assert float((c.cpu() - c_f).abs().mean()) < 2e-2 * scale
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_mip_tc_end_to_end_render_close_to_fp32(prec):
+    R, Nc, Ni, V = 64, 32, 48, 2
+    net, sd = make_net(V, Nc, Ni, chunk=1 << 20, seed=7, training=False, gain=1.4)
+    ro, vd = rays(R, 50)
+    pose = so.random_poses7(V, seed=8)
+    with torch.no_grad():
+        ref = net(cu(ro), cu(vd), cu(pose))
+        net.set_precision(prec)
+        out = net(cu(ro), cu(vd), cu(pose))
+    # 16-bit operands: rgb within the north star's 2e-3 in the mean (bf16) / in the max norm (fp16)
+    err = (out["rgb0"] - ref["rgb0"]).abs()
+    assert float(err.mean()) < 2e-3 and float(err.max()) < (2e-3 if prec == "fp16" else 2e-2), (float(err.mean()), float(err.max()))
+    assert float((out["rgb"] - ref["rgb"]).abs().mean()) < 4e-3
+    assert psnr_shift(out["rgb0"], ref["rgb0"]) < 0.05
+
+
+def psnr_shift(a, b):
+    """|PSNR(a, t) - PSNR(b, t)| against a fixed random target t."""
+    t = torch.rand(a.shape, generator=gen(99)).to(a.device)
+    pa = -10 * torch.log10(((a - t) ** 2).mean())
+    pb = -10 * torch.log10(((b - t) ** 2).mean())
+    return float((pa - pb).abs())
+
+
+def test_mip_tc_training_falls_back_to_fp32_kernels_not_to_cpu():
+    """The 16-bit tiers of the mip field are forward-only: under autograd the fp32 CUDA kernels run (same gradients
+    as an fp32-tier module)."""
+    net, _ = make_net(0, 8, 8, 64, seed=11, training=True, gain=1.4)
+    ro, vd = rays(8, 3)
+    t = torch.rand(8, 9, generator=gen(1))
+    u = torch.rand(8, 9, generator=gen(2))
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        net.set_precision(prec)
+        net.zero_grad()
+        o = net(cu(ro), cu(vd), None, t_rand=cu(t), u_rand=cu(u))
+        o["rgb"].sum().backward()
+        outs[prec] = net.static_nerf.field.mlp_base.layers[0].weight.grad.clone()
+    assert torch.equal(outs["fp32"], outs["bf16"])
