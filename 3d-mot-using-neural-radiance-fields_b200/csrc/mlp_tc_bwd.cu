@@ -112,7 +112,7 @@ __device__ __forceinline__ void fold_jacobian(const uint32_t (&r)[16], const flo
 }
 
 // ============================================================================================ dX chain
-template <bool FP16>
+template <bool FP16, bool POSE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const float* __restrict__ pts,
                   const float* __restrict__ viewdirs, const float* __restrict__ pose12,
@@ -134,7 +134,7 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
   auto bar = [&](int i) -> uint32_t { return sBars + 8u * (uint32_t)i; };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (M + TC_M - 1) / TC_M;
-  const bool has_pose = pose12 != nullptr;
+  constexpr bool has_pose = POSE;   // object nets: pose accumulators and two extra GEMMs (compiled out for the static net)
 
   // ---- the per-tile program (identical for every tile): built once by one thread
   if (tid == 0) {
@@ -255,9 +255,9 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     const int row = q * 32 + lane;
     const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
     uint32_t acc_par = 0;
-    float pacc[27];
+    float pacc[POSE ? 27 : 1];
 #pragma unroll
-    for (int i = 0; i < 27; ++i) pacc[i] = 0.f;
+    for (int i = 0; i < (POSE ? 27 : 1); ++i) pacc[i] = 0.f;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t gi = tile * TC_M + row;
       const bool valid = gi < M;
@@ -284,6 +284,19 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
 
       for (int pi = 0; pi < n_phases; ++pi) {
         const BwdPhase P = phases[pi];
+        // mask sources of the whole phase (16 stashed 16-bit activations per chunk; > 0 <=> bits != 0 for a ReLU output)
+        // are fetched BEFORE waiting for the accumulator: the global-memory latency hides behind the MMAs
+        uint4 mq[4][2];
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          mq[kb][0] = make_uint4(~0u, ~0u, ~0u, ~0u);
+          mq[kb][1] = mq[kb][0];
+          if (P.mask_blk >= 0 && kb < P.nch) {
+            const uint8_t* mb = st_tile + (size_t)(P.mask_blk + kb) * TC_BLOCK_BYTES;
+            mq[kb][0] = __ldg(reinterpret_cast<const uint4*>(mb + (uint32_t)row * 128u + ((((uint32_t)(cg * 2)) ^ x_sw) << 4)));
+            mq[kb][1] = __ldg(reinterpret_cast<const uint4*>(mb + (uint32_t)row * 128u + ((((uint32_t)(cg * 2 + 1)) ^ x_sw) << 4)));
+          }
+        }
         if (P.kind != BK_PRE) {
           mbar_wait(bar(BAR_ACC_FULL), acc_par, dbg, 4);
           acc_par ^= 1u;
@@ -331,17 +344,11 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             pacc[26] += dob[0] * h[1] - dob[1] * h[0];
           }
         }
-        for (int kb = 0; kb < P.nch; ++kb) {
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          if (kb >= P.nch) break;
           const int col0 = kb * 64 + cg * TC_CPT;
-          const uint32_t off0 = (uint32_t)row * 128u + ((((uint32_t)(cg * 2)) ^ x_sw) << 4);
-          const uint32_t off1 = (uint32_t)row * 128u + ((((uint32_t)(cg * 2 + 1)) ^ x_sw) << 4);
-          // mask source: 16 stashed 16-bit activations (> 0 <=> bits != 0 for a ReLU output)
-          uint4 m0 = make_uint4(~0u, ~0u, ~0u, ~0u), m1 = m0;
-          if (P.mask_blk >= 0) {
-            const uint8_t* mb = st_tile + (size_t)(P.mask_blk + kb) * TC_BLOCK_BYTES;
-            m0 = *reinterpret_cast<const uint4*>(mb + off0);
-            m1 = *reinterpret_cast<const uint4*>(mb + off1);
-          }
+          const uint4 m0 = mq[kb][0], m1 = mq[kb][1];
           const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
           float v[16];
           if (P.kind == BK_PRE) {
@@ -706,7 +713,8 @@ int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed
   {
     const int grid = (int)(ntiles < sms ? ntiles : sms);
     const BwdSmem sl = bwd_smem_layout(tl.small_bytes);
-    auto kern = fp16 ? mlp_bwd_tc_kernel<true> : mlp_bwd_tc_kernel<false>;
+    auto kern = pose12 != nullptr ? (fp16 ? mlp_bwd_tc_kernel<true, true> : mlp_bwd_tc_kernel<false, true>)
+                                  : (fp16 ? mlp_bwd_tc_kernel<true, false> : mlp_bwd_tc_kernel<false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
     if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
     kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
