@@ -164,29 +164,36 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     }
   } else if (warp == TC_EPI_WARPS + 1) {
     // ======================================================================== MMA issuer
-    if (lane == 0) {
+    // warp-uniform control flow (all lanes wait on the barriers), one elected lane issues the tcgen05 instructions
+    {
       uint32_t stage = 0, phase = 0, a_par = 0;
+      const bool no_mma = (dbg_mode & 4) != 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int l = 0; l < lay.n_layers; ++l) {
-          const TcLayer& L = lay.L[l];
-          const uint32_t d_tmem = tmem_base + (L.region ? 256u : 0u);
-          const uint32_t idesc = umma_idesc_16(TC_M, L.N, FP16 ? 0 : 1);
-          for (int kb = 0; kb < L.nkb; ++kb) {
-            const int idx = (L.kind == LK_VIEWS && kb == 4) ? 4 : kb;
+          const int kind = lay.L[l].kind, nkb = lay.L[l].nkb;
+          const uint32_t d_tmem = tmem_base + (lay.L[l].region ? 256u : 0u);
+          const uint32_t idesc = umma_idesc_16(TC_M, lay.L[l].N, FP16 ? 0 : 1);
+          for (int kb = 0; kb < nkb; ++kb) {
+            const bool dirs = (kind == LK_VIEWS && kb == 4);
+            const int idx = dirs ? 4 : kb;
             mbar_wait(bar(BAR_A_READY(idx)), (a_par >> idx) & 1u, dbg, 2);
             a_par ^= 1u << idx;
             mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
             tc_fence_after();
-            const uint32_t a_addr = (idx == 4) ? sAD : sA + (uint32_t)kb * TC_KB_BYTES;
-            const uint32_t b_addr = sW + stage * TC_STAGE_BYTES;
-            const int nk = (idx == 4) ? 2 : 4;
-            for (int k = 0; k < nk && !(dbg_mode & 4); ++k)
-              tc_mma_bf16(d_tmem, umma_desc_sw128(a_addr + 32u * k), umma_desc_sw128(b_addr + 32u * k), idesc,
-                          (L.kind == LK_FC1 || kb > 0 || k > 0) ? 1u : 0u);
-            tc_commit(bar(BAR_W_EMPTY(stage)));
+            const uint64_t a0 = umma_desc_sw128(dirs ? sAD : sA + (uint32_t)kb * TC_KB_BYTES);
+            const uint64_t b0 = umma_desc_sw128(sW + stage * TC_STAGE_BYTES);
+            const uint32_t acc0 = (kind == LK_FC1 || kb > 0) ? 1u : 0u;
+            if (elect_one_sync()) {
+              if (!no_mma) {
+                if (dirs) tc_mma_kblock<2>(d_tmem, a0, b0, idesc, acc0);
+                else tc_mma_kblock<4>(d_tmem, a0, b0, idesc, acc0);
+              }
+              tc_commit(bar(BAR_W_EMPTY(stage)));
+              if (kb == nkb - 1) tc_commit(bar(BAR_ACC_FULL));
+            }
+            __syncwarp();
             if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
           }
-          tc_commit(bar(BAR_ACC_FULL));
         }
       }
     }

@@ -98,6 +98,31 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
+// One lane of a fully active warp (elect.sync).  The MMA-issuing warp runs its control flow on all 32 lanes and guards
+// only the tcgen05 instructions with this predicate: behind a plain `lane == 0` branch the compiler has to treat the
+// uniform-datapath operands of UTCHMMA / UTCBAR as divergent and wraps every one of them in a vote / elect / branch loop
+// plus vector->uniform register moves, which made the issuer thread (~120 dependent instructions per K-block) slower
+// than the tensor core it feeds.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// 4 (or NK) K-steps of one K-block: descriptors advance by 32 bytes (+2 in the 16-byte address field) per K-step.
+// ACC0: accumulate flag of the first K-step (the others always accumulate).
+template <int NK>
+__device__ __forceinline__ void tc_mma_kblock(uint32_t d_tmem, uint64_t a_desc0, uint64_t b_desc0, uint32_t idesc,
+                                              uint32_t acc0) {
+#pragma unroll
+  for (int k = 0; k < NK; ++k)
+    tc_mma_bf16(d_tmem, a_desc0 + (uint64_t)(2 * k), b_desc0 + (uint64_t)(2 * k), idesc, k == 0 ? acc0 : 1u);
+}
+
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives lane (base + t), columns [c, c+32)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

@@ -39,6 +39,113 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int niter, long long* out)
   if (warp == 1) { tc_fence_after(); tmem_dealloc(t, 512); }
 }
 
+// Same issue loop, but the operands walk through distinct shared-memory blocks the way the MLP kernel does:
+// A = 4 K-blocks of 16 KB, B = a ring of 4 stages of 32 KB, 4 K-steps (+32 B) inside each block.
+template <int N>
+__global__ void __launch_bounds__(128, 1) stream_kernel(int niter, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint32_t tmem_ptr;
+  __shared__ uint64_t bar;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_ptr), 512);
+  for (int i = threadIdx.x; i < 192 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t t = tmem_ptr;
+  if (warp == 0 && lane == 0) {
+    const uint32_t idesc = umma_idesc_16(128, N, 1);
+    long long t0 = clock64();
+    for (int i = 0; i < niter; ++i) {
+      const uint32_t a = base + (uint32_t)(i & 3) * 16384u, b = base + 65536u + (uint32_t)(i & 3) * 32768u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        tc_mma_bf16(t + ((i & 4) ? 256u : 0u), umma_desc_sw128(a + 32u * k), umma_desc_sw128(b + 32u * k), idesc, 1u);
+    }
+    tc_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0, nullptr, 0);
+    long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(t, 512); }
+}
+
+// The MLP kernel's issuer loop, piece by piece: per K-block [VAR & 1: two try_waits on already-completed barriers]
+// [VAR & 2: tcgen05.fence::after_thread_sync] 4 MMAs [VAR & 4: tcgen05.commit to a per-stage barrier]
+template <int VAR>
+__global__ void __launch_bounds__(128, 1) loop_kernel(int niter, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint32_t tmem_ptr;
+  __shared__ uint64_t bar, done_bar[2], stage_bar[4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    mbar_init(smem_u32(&done_bar[0]), 1); mbar_init(smem_u32(&done_bar[1]), 1);
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&stage_bar[i]), 1);
+    fence_mbar_init();
+    mbar_arrive(smem_u32(&done_bar[0]));   // phase 0 of both complete: try_wait(parity 0) succeeds immediately
+    mbar_arrive(smem_u32(&done_bar[1]));
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_ptr), 512);
+  for (int i = threadIdx.x; i < 192 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t t = tmem_ptr;
+  if (warp == 0 && lane == 0) {
+    const uint32_t idesc = umma_idesc_16(128, 256, 1);
+    long long t0 = clock64();
+    for (int i = 0; i < niter; ++i) {
+      const uint32_t a = base + (uint32_t)(i & 3) * 16384u, b = base + 65536u + (uint32_t)(i & 3) * 32768u;
+      if (VAR & 1) {
+        mbar_wait(smem_u32(&done_bar[0]), 0, nullptr, 0);
+        mbar_wait(smem_u32(&done_bar[1]), 0, nullptr, 0);
+      }
+      if (VAR & 2) tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        tc_mma_bf16(t + ((i & 4) ? 256u : 0u), umma_desc_sw128(a + 32u * k), umma_desc_sw128(b + 32u * k), idesc, 1u);
+      if (VAR & 4) tc_commit(smem_u32(&stage_bar[i & 3]));
+    }
+    tc_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0, nullptr, 0);
+    long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(t, 512); }
+}
+
+template <int VAR>
+void run_loop(int niter, long long* d_out) {
+  cudaFuncSetAttribute(loop_kernel<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  loop_kernel<VAR><<<148, 128, 200 * 1024>>>(niter, d_out);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long cyc = 0;
+  cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
+  printf("issuer loop variant %d (1: 2 try_waits, 2: fence, 4: commit per K-block): %.1f cycles per K-block of 4 MMAs (ideal 512)  (%s)\n",
+         VAR, (double)cyc / niter, cudaGetErrorString(e));
+}
+
+template <int N>
+void run_stream(int grid, int niter, long long* d_out) {
+  cudaFuncSetAttribute(stream_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  stream_kernel<N><<<grid, 128, 200 * 1024>>>(niter, d_out);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long cyc = 0;
+  cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
+  printf("streaming operands N=%3d grid=%3d: %.1f cycles/MMA, %.0f MAC/clk/SM  (%s)\n", N, grid,
+         (double)cyc / (niter * 4), 128.0 * N * 16 * niter * 4 / cyc, cudaGetErrorString(e));
+}
+
 template <int N>
 void run(int grid, int niter, long long* d_out) {
   cudaFuncSetAttribute(rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -58,6 +165,12 @@ int main() {
     run<128>(grid, 2000, d_out);
     run<64>(grid, 2000, d_out);
   }
+  for (int grid : {1, 148}) {
+    run_stream<256>(grid, 2000, d_out);
+    run_stream<128>(grid, 2000, d_out);
+  }
+  run_loop<0>(2000, d_out); run_loop<1>(2000, d_out); run_loop<2>(2000, d_out); run_loop<4>(2000, d_out);
+  run_loop<3>(2000, d_out); run_loop<7>(2000, d_out);
   // commit -> mbarrier latency: 0, 1, 2, 4 groups of 4 MMAs (N=256: 512 cycles per group) then commit + wait
   for (int n : {0, 1, 2, 4, 8}) {
     cudaFuncSetAttribute(rate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
