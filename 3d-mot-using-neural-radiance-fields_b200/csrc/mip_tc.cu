@@ -264,35 +264,40 @@ mip_fwd_tc_kernel(const MipTcLayout lay, const uint8_t* __restrict__ packed, con
     }
   } else if (warp == TC_EPI_WARPS + 1) {
     // ======================================================================== MMA issuer
-    if (lane == 0) {
+    // warp-uniform control flow (all lanes wait on the barriers), one elected lane issues the tcgen05 instructions
+    {
       uint32_t stage = 0, phase = 0, a_par = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int l = 0; l < MIP_TC_NL; ++l) {
-          const MipTcLayer& L = lay.L[l];
-          const uint32_t d_tmem = tmem_base + (L.region ? 256u : 0u);
-          const uint32_t idesc = umma_idesc_16(TC_M, L.N, FP16 ? 0 : 1);
-          const int n = L.nkb + L.nkb_extra;
+          const int kind = lay.L[l].kind, nkb = lay.L[l].nkb, n = nkb + lay.L[l].nkb_extra;
+          const uint32_t d_tmem = tmem_base + (lay.L[l].region ? 256u : 0u);
+          const uint32_t idesc = umma_idesc_16(TC_M, lay.L[l].N, FP16 ? 0 : 1);
           for (int kb = 0; kb < n; ++kb) {
             // operand block: A[kb] for the main K-blocks; the skip layer's extra blocks re-use A[0..2]; H0's extra
             // block is the encoded-dirs block (2 of its 4 K-steps are used)
-            const bool extra = kb >= L.nkb;
-            const bool is_dirs = extra && L.kind == MK_H0;
-            const int idx = is_dirs ? 4 : (extra ? kb - L.nkb : kb);
-            if (extra && kb == L.nkb && !is_dirs) tc_commit(bar(BAR_X_DONE));   // x-part MMAs done -> A may be re-encoded
+            const bool extra = kb >= nkb;
+            const bool is_dirs = extra && kind == MK_H0;
+            const int idx = is_dirs ? 4 : (extra ? kb - nkb : kb);
+            if (extra && kb == nkb && !is_dirs) {      // x-part MMAs done -> A may be re-encoded
+              if (elect_one_sync()) tc_commit(bar(BAR_X_DONE));
+              __syncwarp();
+            }
             mbar_wait(bar(BAR_A_READY(idx)), (a_par >> idx) & 1u, dbg, 2);
             a_par ^= 1u << idx;
             mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
             tc_fence_after();
-            const uint32_t a_addr = is_dirs ? sAD : sA + (uint32_t)idx * TC_KB_BYTES;
-            const uint32_t b_addr = sW + stage * TC_STAGE_BYTES;
-            const int nk = is_dirs ? 2 : 4;
-            for (int k = 0; k < nk; ++k)
-              tc_mma_bf16(d_tmem, umma_desc_sw128(a_addr + 32u * k), umma_desc_sw128(b_addr + 32u * k), idesc,
-                          (kb > 0 || k > 0) ? 1u : 0u);
-            tc_commit(bar(BAR_W_EMPTY(stage)));
+            const uint64_t a0 = umma_desc_sw128(is_dirs ? sAD : sA + (uint32_t)idx * TC_KB_BYTES);
+            const uint64_t b0 = umma_desc_sw128(sW + stage * TC_STAGE_BYTES);
+            const uint32_t acc0 = kb > 0 ? 1u : 0u;
+            if (elect_one_sync()) {
+              if (is_dirs) tc_mma_kblock<2>(d_tmem, a0, b0, idesc, acc0);
+              else tc_mma_kblock<4>(d_tmem, a0, b0, idesc, acc0);
+              tc_commit(bar(BAR_W_EMPTY(stage)));
+              if (kb == n - 1) tc_commit(bar(BAR_ACC_FULL));
+            }
+            __syncwarp();
             if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
           }
-          tc_commit(bar(BAR_ACC_FULL));
         }
       }
     }

@@ -211,13 +211,14 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     }
   } else if (warp == TC_EPI_WARPS + 1) {
     // ======================================================================== MMA issuer
-    if (lane == 0) {
+    // warp-uniform control flow (all lanes wait on the barriers), one elected lane issues the tcgen05 instructions
+    {
       uint32_t stage = 0, phase = 0, a_par = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int ph = 0;              // index of the epilogue phase that produced the A operand of the current group
         bool group_start = true;
         for (int i = 0; i < n_stages; ++i) {
-          const BwdStage& s = stages[i];
+          const BwdStage s = stages[i];
           if (group_start) {
             // the A operand (and the free accumulator) of this group need ALL chunks of the previous epilogue
             for (int kb = 0; kb < phases[ph].n_wait; ++kb) {
@@ -229,14 +230,16 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
           tc_fence_after();
           const uint32_t idesc = umma_idesc_16(TC_M, s.N, FP16 ? 0 : 1);
-          const uint32_t a_addr = sA + (uint32_t)s.a_kb * TC_KB_BYTES, b_addr = sW + stage * TC_STAGE_BYTES;
-          for (int k = 0; k < s.nk; ++k)
-            tc_mma_bf16(tmem_base + (uint32_t)s.tcol, umma_desc_sw128(a_addr + 32u * k), umma_desc_sw128(b_addr + 32u * k),
-                        idesc, (s.accum || k > 0) ? 1u : 0u);
-          tc_commit(bar(BAR_W_EMPTY(stage)));
+          const uint64_t a0 = umma_desc_sw128(sA + (uint32_t)s.a_kb * TC_KB_BYTES);
+          const uint64_t b0 = umma_desc_sw128(sW + stage * TC_STAGE_BYTES);
+          if (elect_one_sync()) {
+            tc_mma_kblock<4>(tmem_base + (uint32_t)s.tcol, a0, b0, idesc, s.accum ? 1u : 0u);   // every stage has 4 K-steps
+            tc_commit(bar(BAR_W_EMPTY(stage)));
+            if (s.last) tc_commit(bar(BAR_ACC_FULL));
+          }
+          __syncwarp();
           if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
           if (s.last) {
-            tc_commit(bar(BAR_ACC_FULL));
             ++ph;
             group_start = true;
           }
@@ -499,29 +502,39 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // warp-uniform control flow, one elected lane issues the tcgen05 instructions (see elect_one_sync)
+    {
       const int N = 64 * it.n_a;
       const uint32_t fmt = FP16 ? 0u : 1u;
       const uint32_t idesc = umma_idesc_16(128, N, (int)fmt) | (1u << 15) | (1u << 16);      // both operands MN-major
       const uint32_t idesc1 = umma_idesc_16(128, 16, (int)fmt) | (1u << 15) | (1u << 16);
+      const bool with_bias = it.b_off >= 0;
+      const uint64_t d1 = umma_desc_mn_sw128(sOnes, TC_BLOCK_BYTES);
       uint32_t st = 0, ph = 0;
-      bool first = true;
+      uint32_t acc = 0u;
       for (int64_t t = t0; t < t1; ++t) {
         mbar_wait(bar(st), ph, dbg, 2);
         tc_fence_after();
         const uint32_t g_addr = sStage + st * DW_STAGE_BLOCKS * TC_BLOCK_BYTES, a_addr = g_addr + 2 * TC_BLOCK_BYTES;
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t da = umma_desc_mn_sw128(g_addr + 2048u * ks, TC_BLOCK_BYTES);
-          tc_mma_bf16(tmem_base, da, umma_desc_mn_sw128(a_addr + 2048u * ks, TC_BLOCK_BYTES), idesc, first ? 0u : 1u);
-          if (it.b_off >= 0)
-            tc_mma_bf16(tmem_base + 256u, da, umma_desc_mn_sw128(sOnes + 2048u * ks, TC_BLOCK_BYTES), idesc1,
-                        first ? 0u : 1u);
-          first = false;
+        const uint64_t dg = umma_desc_mn_sw128(g_addr, TC_BLOCK_BYTES), da = umma_desc_mn_sw128(a_addr, TC_BLOCK_BYTES);
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {     // +2048 bytes per K-step of 16 samples = +128 in the 16-byte address field
+            const uint32_t a_ = (ks == 0) ? acc : 1u;
+            tc_mma_bf16(tmem_base, dg + (uint64_t)(128 * ks), da + (uint64_t)(128 * ks), idesc, a_);
+            if (with_bias) tc_mma_bf16(tmem_base + 256u, dg + (uint64_t)(128 * ks), d1 + (uint64_t)(128 * ks), idesc1, a_);
+          }
+          tc_commit(bar(2 + st));
+          if (t == t1 - 1) tc_commit(bar(4));
         }
-        tc_commit(bar(2 + st));
+        __syncwarp();
+        acc = 1u;
         if (++st == DW_NSTAGE) { st = 0; ph ^= 1u; }
       }
-      tc_commit(bar(4));
+      if (t1 <= t0) {
+        if (elect_one_sync()) tc_commit(bar(4));
+        __syncwarp();
+      }
     }
   } else {
     // epilogue: TMEM -> registers -> atomics into the flat gradient
