@@ -122,6 +122,17 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (M + TC_M - 1) / TC_M;
   const long long t_start = clock64();
+#ifdef STAR_TC_TIMELINE
+  // -DSTAR_TC_TIMELINE (debug build only, see tools/tc_timeline.sh): CTA 0 records clock64() stamps of its second tile
+  // into dbg[8..]:  issuer, slot 16 + 4 l: {a_ready[0] seen, last K-block issued + committed}; slots 240 + 3 kb: layer 2
+  // per K-block {a_ready seen, w_full seen, issued};  epilogue warp 0, slot 80 + 8 l: {wait start, accumulator seen,
+  // layer done}; slots 200 + w: layer-1 epilogue done per warp; slots 8 / 9: encode start / done
+  long long* tl = (dbg != nullptr && blockIdx.x == 0) ? reinterpret_cast<long long*>(dbg) : nullptr;
+  const int64_t tl_tile = (int64_t)blockIdx.x + gridDim.x;
+#define TL_STAMP(cond, slot) do { if (tl != nullptr && (cond)) tl[slot] = clock64(); } while (0)
+#else
+#define TL_STAMP(cond, slot) do { } while (0)
+#endif
 
   // ---- one-time setup
   if (warp == TC_EPI_WARPS && lane == 0) {
@@ -178,8 +189,11 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             const int idx = dirs ? 4 : kb;
             mbar_wait(bar(BAR_A_READY(idx)), (a_par >> idx) & 1u, dbg, 2);
             a_par ^= 1u << idx;
+            TL_STAMP(tile == tl_tile && lane == 0 && kb == 0, 16 + 4 * l);
+            TL_STAMP(tile == tl_tile && lane == 0 && l == 2, 240 + 3 * kb);
             mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
             tc_fence_after();
+            TL_STAMP(tile == tl_tile && lane == 0 && l == 2, 241 + 3 * kb);
             const uint64_t a0 = umma_desc_sw128(dirs ? sAD : sA + (uint32_t)kb * TC_KB_BYTES);
             const uint64_t b0 = umma_desc_sw128(sW + stage * TC_STAGE_BYTES);
             const uint32_t acc0 = (kind == LK_FC1 || kb > 0) ? 1u : 0u;
@@ -192,6 +206,8 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
               if (kb == nkb - 1) tc_commit(bar(BAR_ACC_FULL));
             }
             __syncwarp();
+            TL_STAMP(tile == tl_tile && lane == 0 && kb == nkb - 1, 17 + 4 * l);
+            TL_STAMP(tile == tl_tile && lane == 0 && l == 2, 242 + 3 * kb);
             if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
           }
         }
@@ -210,6 +226,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
       const int64_t gi = tile * TC_M + row;
       const bool valid = gi < M;
       int64_t out_idx = 0;
+      TL_STAMP(tile == tl_tile && tid == 0, 8);
       // ---- inputs: pose transform + encoding -> A K-block 0 (xyz, 4 threads per row) and the dirs block
       {
         float p[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 0.f};
@@ -250,13 +267,16 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           mbar_arrive(bar(BAR_A_READY(0)));
           mbar_arrive(bar(BAR_A_READY(4)));
         }
+        TL_STAMP(tile == tl_tile && tid == 0, 9);
       }
       // ---- layers
       for (int l = 0; l < lay.n_layers; ++l) {
         const TcLayer& L = lay.L[l];
+        TL_STAMP(tile == tl_tile && tid == 0, 80 + 8 * l);
         mbar_wait(bar(BAR_ACC_FULL), acc_par, dbg, 4);
         acc_par ^= 1u;
         tc_fence_after();
+        TL_STAMP(tile == tl_tile && tid == 0, 81 + 8 * l);
         ctx.tcol = tmem_base + (((uint32_t)(q * 32)) << 16) + (L.region ? 256u : 0u) + (uint32_t)(cg * TC_CPT);
         ctx.bias = s_small + L.bias_off;
         if (STASH) ctx.stash_out = stash + ((size_t)tile * (size_t)lay.stash_blocks + (size_t)L.s_out) * TC_BLOCK_BYTES;
@@ -295,6 +315,8 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
                       s_small[lay.off_rgb_b + ch];
           }
         }
+        TL_STAMP(tile == tl_tile && tid == 0, 82 + 8 * l);
+        TL_STAMP(tile == tl_tile && lane == 0 && l == 1, 200 + warp);
       }
     }
   }
@@ -409,16 +431,32 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const float* pts, co
   static long long* d_dbg = nullptr;
   if (dbg_cycles < 0) {
     dbg_cycles = getenv("STAR_TC_DEBUG_CYCLES") ? 1 : 0;
-    if (dbg_cycles) { cudaMalloc(&d_dbg, 64); cudaMemset(d_dbg, 0, 64); }
+    if (dbg_cycles) { cudaMalloc(&d_dbg, 4096); cudaMemset(d_dbg, 0, 4096); }
   }
   kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
                                             raw_alpha, raw_rgb, ray_stride, (uint8_t*)stash, (int*)d_dbg, dbg_mode);
   if (dbg_cycles) {
-    long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    static long long h[512];
     cudaStreamSynchronize(st);
-    cudaMemcpy(h, d_dbg, 64, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h, d_dbg, 4096, cudaMemcpyDeviceToHost);
     const double t0 = (double)((ntiles + grid - 1) / grid);
     fprintf(stderr, "[star_tc] mode %d: CTA0 %.0f cycles/tile\n", dbg_mode, h[1] / t0);
+#ifdef STAR_TC_TIMELINE
+    if (ntiles > 2 * (int64_t)grid && h[8] != 0) {
+      const long long z = h[8];
+      fprintf(stderr, "[star_tc] timeline of CTA 0, tile 2 (cycles from encode start): encode done %lld\n", h[9] - z);
+      for (int l = 0; l < tl.n_layers; ++l)
+        fprintf(stderr, "[star_tc]  L%-2d kind %d  issuer: a_ready0 %6lld  last kb issued %6lld | epilogue: wait-start %6lld  "
+                        "acc seen %6lld  done %6lld\n", l, tl.L[l].kind, h[16 + 4 * l] - z, h[17 + 4 * l] - z,
+                h[80 + 8 * l] - z, h[81 + 8 * l] - z, h[82 + 8 * l] - z);
+      fprintf(stderr, "[star_tc]  L1 epilogue done per warp:");
+      for (int w = 0; w < 16; ++w) fprintf(stderr, " %lld", h[200 + w] - z);
+      fprintf(stderr, "\n[star_tc]  L2 issuer per K-block (a_ready seen, w_full seen, issued):");
+      for (int kb = 0; kb < 4; ++kb) fprintf(stderr, "  kb%d %lld %lld %lld", kb, h[240 + 3 * kb] - z, h[241 + 3 * kb] - z, h[242 + 3 * kb] - z);
+      fprintf(stderr, "\n");
+      cudaMemset(d_dbg, 0, 4096);
+    }
+#endif
   }
   return star_check_launch();
 }

@@ -135,6 +135,117 @@ void run_loop(int niter, long long* d_out) {
          VAR, (double)cyc / niter, cudaGetErrorString(e));
 }
 
+// MMA rate under interference: one issuing thread streams N=256 MMAs (as stream_kernel) while 16 other warps run
+// (VAR & 1) tcgen05.ld x16 loops on the OTHER accumulator region, (VAR & 2) 16-byte st.shared loops into a scratch
+// block, (VAR & 4) ld.shared loops -- the epilogue's traffic classes.  Reports cycles per MMA.
+template <int VAR>
+__global__ void __launch_bounds__(576, 1) interf_kernel(int niter, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint32_t tmem_ptr;
+  __shared__ uint64_t bar;
+  __shared__ volatile int stop;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); stop = 0; }
+  if (warp == 17) tmem_alloc(smem_u32(&tmem_ptr), 512);
+  for (int i = threadIdx.x; i < 208 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t t = tmem_ptr;
+  if (warp == 17) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_16(128, 256, 1);
+      long long t0 = clock64();
+      for (int i = 0; i < niter; ++i) {
+        const uint32_t a = base + (uint32_t)(i & 3) * 16384u, b = base + 65536u + (uint32_t)(i & 3) * 32768u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_bf16(t, umma_desc_sw128(a + 32u * k), umma_desc_sw128(b + 32u * k), idesc, 1u);
+      }
+      tc_commit(smem_u32(&bar));
+      mbar_wait(smem_u32(&bar), 0, nullptr, 0);
+      long long t1 = clock64();
+      if (blockIdx.x == 0) out[0] = t1 - t0;
+      stop = 1;
+    }
+  } else if (warp < 16) {
+    const uint32_t taddr = t + 256u + (((uint32_t)((warp & 3) * 32)) << 16) + (uint32_t)((warp >> 2) * 16);
+    const uint32_t saddr = base + 196608u + (uint32_t)threadIdx.x * 16u;   // scratch: 8 KB past the operand blocks
+    uint32_t acc = 0;
+    while (!stop) {
+      if (VAR & 1) {
+        uint32_t r[16];
+        tmem_ld16(taddr, r);
+        tmem_wait_ld();
+        acc += r[0] + r[15];
+      }
+      if (VAR & 2) {
+        st_shared_v4(saddr, acc, acc, acc, acc);
+        st_shared_v4(saddr + 8192u < base + 208u * 1024u ? saddr : saddr, acc, acc, acc, acc);
+      }
+      if (VAR & 4) {
+        uint32_t v;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr));
+        acc += v;
+      }
+      if (VAR & 8) { fence_proxy_async_smem(); }
+    }
+    if (acc == 0x12345678u) out[1] = acc;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) { tc_fence_after(); tmem_dealloc(t, 512); }
+}
+
+template <int VAR>
+void run_interf(int niter, long long* d_out) {
+  cudaFuncSetAttribute(interf_kernel<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+  interf_kernel<VAR><<<148, 576, 212 * 1024>>>(niter, d_out);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long cyc = 0;
+  cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
+  printf("interference %2d (1: LDTM, 2: st.shared, 4: ld.shared, 8: proxy fence; 16 warps): %.1f cycles/MMA (ideal 128)  (%s)\n",
+         VAR, (double)cyc / (niter * 4), cudaGetErrorString(e));
+}
+
+// How far can the issuing thread run ahead?  Cycles spent INSIDE the issue loop of n MMAs (N=256) starting from an
+// idle tensor pipe, before any completion wait.
+__global__ void __launch_bounds__(128, 1) depth_kernel(int n, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint32_t tmem_ptr;
+  __shared__ uint64_t bar;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_ptr), 512);
+  for (int i = threadIdx.x; i < 192 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t t = tmem_ptr;
+  if (warp == 0) {
+    const uint32_t idesc = umma_idesc_16(128, 256, 1);
+    const uint64_t a0 = umma_desc_sw128(base), b0 = umma_desc_sw128(base + 65536u);
+    long long t0 = 0, t1 = 0, t2 = 0;
+    if (elect_one_sync()) {
+      t0 = clock64();
+      for (int i = 0; i < n; ++i) tc_mma_bf16(t, a0 + (uint64_t)(2 * (i & 3)), b0 + (uint64_t)(2 * (i & 3)), idesc, 1u);
+      t1 = clock64();
+      tc_commit(smem_u32(&bar));
+      mbar_wait(smem_u32(&bar), 0, nullptr, 0);
+      t2 = clock64();
+      if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(t, 512); }
+}
+
 template <int N>
 void run_stream(int grid, int niter, long long* d_out) {
   cudaFuncSetAttribute(stream_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -159,7 +270,7 @@ void run(int grid, int niter, long long* d_out) {
 
 int main() {
   long long* d_out;
-  cudaMalloc(&d_out, 8);
+  cudaMalloc(&d_out, 64);
   for (int grid : {1, 148}) {
     run<256>(grid, 2000, d_out);
     run<128>(grid, 2000, d_out);
@@ -171,6 +282,16 @@ int main() {
   }
   run_loop<0>(2000, d_out); run_loop<1>(2000, d_out); run_loop<2>(2000, d_out); run_loop<4>(2000, d_out);
   run_loop<3>(2000, d_out); run_loop<7>(2000, d_out);
+  run_interf<0>(1000, d_out); run_interf<1>(1000, d_out); run_interf<2>(1000, d_out); run_interf<4>(1000, d_out);
+  run_interf<8>(1000, d_out); run_interf<3>(1000, d_out); run_interf<15>(1000, d_out);
+  for (int n : {1, 2, 3, 4, 6, 8, 12, 16, 32}) {
+    cudaFuncSetAttribute(depth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    depth_kernel<<<148, 128, 200 * 1024>>>(n, d_out);
+    cudaDeviceSynchronize();
+    long long c2[2] = {0, 0};
+    cudaMemcpy(c2, d_out, 16, cudaMemcpyDeviceToHost);
+    printf("issue depth: %2d MMAs issued in %5lld cycles, all complete after %5lld cycles (ideal %d)\n", n, c2[0], c2[1], n * 128);
+  }
   // commit -> mbarrier latency: 0, 1, 2, 4 groups of 4 MMAs (N=256: 512 cycles per group) then commit + wait
   for (int n : {0, 1, 2, 4, 8}) {
     cudaFuncSetAttribute(rate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
