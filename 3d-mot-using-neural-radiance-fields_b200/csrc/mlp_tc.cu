@@ -25,6 +25,10 @@
 
 #include "mlp_tc_device.cuh"
 
+#ifndef TC_LD_DEPTH
+#define TC_LD_DEPTH 2        // TMEM chunk loads in flight per epilogue thread (measured: 2 beats 1 and 4)
+#endif
+
 // ---------------------------------------------------------------------------------------------- epilogue
 struct EpiCtx {
   uint32_t sA, a_ready0;       // smem address of A K-block 0, of barrier a_ready[0]
@@ -44,30 +48,35 @@ template <int KIND, bool FP16, bool STASH>
 __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3]) {
   constexpr int NCH = (KIND == LK_VIEWS) ? 2 : 4;
   constexpr bool RELU = (KIND == LK_IN || KIND == LK_FC0 || KIND == LK_FC1);
-  uint32_t r[2][TC_CPT];
-  tmem_ld16(c.tcol, r[0]);
-  // bias of chunk kb+1 is fetched (shared memory, broadcast) while chunk kb's stores / proxy fence drain
-  float4 bq[TC_CPT / 4];
+  // All TMEM loads of the layer are issued up front (TC_LD_DEPTH chunks in flight): a tcgen05.ld takes several hundred
+  // cycles to return, which with one chunk of look-ahead made every chunk of the serial epilogue chain as long as
+  // that latency.
+  uint32_t r[NCH][TC_CPT];
 #pragma unroll
-  for (int j4 = 0; j4 < TC_CPT / 4; ++j4) bq[j4] = *reinterpret_cast<const float4*>(c.bias + c.cg * TC_CPT + 4 * j4);
+  for (int kb = 0; kb < NCH && kb < TC_LD_DEPTH; ++kb) tmem_ld16(c.tcol + 64u * (uint32_t)kb, r[kb]);
 #pragma unroll
   for (int kb = 0; kb < NCH; ++kb) {
-    tmem_wait_ld();
-    if (kb + 1 < NCH) tmem_ld16(c.tcol + 64u * (uint32_t)(kb + 1), r[(kb + 1) & 1]);
     const int col0 = kb * 64 + c.cg * TC_CPT;
+    float4 bq[TC_CPT / 4];
+#pragma unroll
+    for (int j4 = 0; j4 < TC_CPT / 4; ++j4) bq[j4] = *reinterpret_cast<const float4*>(c.bias + col0 + 4 * j4);
+    // tcgen05.wait::ld waits for every outstanding load of the thread: with the whole layer in flight there is one
+    // wait (before chunk 0); with a shallower depth the next load is issued after each wait
+    if (TC_LD_DEPTH >= NCH) {
+      if (kb == 0) tmem_wait_ld();
+    } else {
+      tmem_wait_ld();
+      if (kb + TC_LD_DEPTH < NCH) tmem_ld16(c.tcol + 64u * (uint32_t)(kb + TC_LD_DEPTH), r[kb + TC_LD_DEPTH]);
+    }
     float v[TC_CPT];
 #pragma unroll
     for (int j4 = 0; j4 < TC_CPT / 4; ++j4) {
-      v[4 * j4 + 0] = __uint_as_float(r[kb & 1][4 * j4 + 0]);
-      v[4 * j4 + 1] = __uint_as_float(r[kb & 1][4 * j4 + 1]);
-      v[4 * j4 + 2] = __uint_as_float(r[kb & 1][4 * j4 + 2]);
-      v[4 * j4 + 3] = __uint_as_float(r[kb & 1][4 * j4 + 3]);
+      v[4 * j4 + 0] = __uint_as_float(r[kb][4 * j4 + 0]);
+      v[4 * j4 + 1] = __uint_as_float(r[kb][4 * j4 + 1]);
+      v[4 * j4 + 2] = __uint_as_float(r[kb][4 * j4 + 2]);
+      v[4 * j4 + 3] = __uint_as_float(r[kb][4 * j4 + 3]);
       add_f32x2(v[4 * j4 + 0], v[4 * j4 + 1], bq[j4].x, bq[j4].y);
       add_f32x2(v[4 * j4 + 2], v[4 * j4 + 3], bq[j4].z, bq[j4].w);
-    }
-    if (kb + 1 < NCH) {   // next chunk's bias: in flight during this chunk's convert / store / fence
-#pragma unroll
-      for (int j4 = 0; j4 < TC_CPT / 4; ++j4) bq[j4] = *reinterpret_cast<const float4*>(c.bias + col0 + 64 + 4 * j4);
     }
     if (KIND == LK_OUT) {            // alpha head (nerf.py:151) on the fp32 h
 #pragma unroll
@@ -179,13 +188,14 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     {
       uint32_t stage = 0, phase = 0, a_par = 0;
       const bool no_mma = (dbg_mode & 4) != 0;
+      const uint64_t desc_a0 = umma_desc_sw128(sA), desc_ad = umma_desc_sw128(sAD), desc_w0 = umma_desc_sw128(sW);
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int l = 0; l < lay.n_layers; ++l) {
           const int kind = lay.L[l].kind, nkb = lay.L[l].nkb;
           const uint32_t d_tmem = tmem_base + (lay.L[l].region ? 256u : 0u);
           const uint32_t idesc = umma_idesc_16(TC_M, lay.L[l].N, FP16 ? 0 : 1);
-          for (int kb = 0; kb < nkb; ++kb) {
-            const bool dirs = (kind == LK_VIEWS && kb == 4);
+          // one K-block: wait for its operand blocks, issue 4 (2 for the dirs block) MMAs, release the weight stage
+          auto kblock = [&](const int kb, const bool dirs) {
             const int idx = dirs ? 4 : kb;
             mbar_wait(bar(BAR_A_READY(idx)), (a_par >> idx) & 1u, dbg, 2);
             a_par ^= 1u << idx;
@@ -194,8 +204,8 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
             tc_fence_after();
             TL_STAMP(tile == tl_tile && lane == 0 && l == 2, 241 + 3 * kb);
-            const uint64_t a0 = umma_desc_sw128(dirs ? sAD : sA + (uint32_t)kb * TC_KB_BYTES);
-            const uint64_t b0 = umma_desc_sw128(sW + stage * TC_STAGE_BYTES);
+            const uint64_t a0 = dirs ? desc_ad : desc_a0 + (uint64_t)(kb * (TC_KB_BYTES >> 4));
+            const uint64_t b0 = desc_w0 + (uint64_t)(stage * (TC_STAGE_BYTES >> 4));
             const uint32_t acc0 = (kind == LK_FC1 || kb > 0) ? 1u : 0u;
             if (elect_one_sync()) {
               if (!no_mma) {
@@ -209,6 +219,11 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             TL_STAMP(tile == tl_tile && lane == 0 && kb == nkb - 1, 17 + 4 * l);
             TL_STAMP(tile == tl_tile && lane == 0 && l == 2, 242 + 3 * kb);
             if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
+          };
+          if (nkb == 4) {            // the common case, unrolled: K-block indices become immediates
+            kblock(0, false); kblock(1, false); kblock(2, false); kblock(3, false);
+          } else {
+            for (int kb = 0; kb < nkb; ++kb) kblock(kb, kind == LK_VIEWS && kb == 4);
           }
         }
       }
