@@ -156,29 +156,27 @@ struct MipEpi {
 template <int KIND, bool FP16>
 __device__ __forceinline__ void mip_epilogue(const MipEpi& c, float (&h)[3]) {
   constexpr int NCH = (KIND == MK_H0 || KIND == MK_H1) ? 2 : 4;
-  uint32_t r[2][TC_CPT];
-  tmem_ld16(c.tcol, r[0]);
-  float4 bq[TC_CPT / 4];
+  // two TMEM chunk loads in flight (measured best in mlp_tc.cu: 1 and NCH are slower)
+  uint32_t r[NCH][TC_CPT];
 #pragma unroll
-  for (int j4 = 0; j4 < TC_CPT / 4; ++j4) bq[j4] = *reinterpret_cast<const float4*>(c.bias + c.cg * TC_CPT + 4 * j4);
+  for (int kb = 0; kb < NCH && kb < 2; ++kb) tmem_ld16(c.tcol + 64u * (uint32_t)kb, r[kb]);
 #pragma unroll
   for (int kb = 0; kb < NCH; ++kb) {
-    tmem_wait_ld();
-    if (kb + 1 < NCH) tmem_ld16(c.tcol + 64u * (uint32_t)(kb + 1), r[(kb + 1) & 1]);
     const int col0 = kb * 64 + c.cg * TC_CPT;
+    float4 bq[TC_CPT / 4];
+#pragma unroll
+    for (int j4 = 0; j4 < TC_CPT / 4; ++j4) bq[j4] = *reinterpret_cast<const float4*>(c.bias + col0 + 4 * j4);
+    tmem_wait_ld();
+    if (kb + 2 < NCH) tmem_ld16(c.tcol + 64u * (uint32_t)(kb + 2), r[kb + 2]);
     float v[TC_CPT];
 #pragma unroll
     for (int j4 = 0; j4 < TC_CPT / 4; ++j4) {
-      v[4 * j4 + 0] = __uint_as_float(r[kb & 1][4 * j4 + 0]);
-      v[4 * j4 + 1] = __uint_as_float(r[kb & 1][4 * j4 + 1]);
-      v[4 * j4 + 2] = __uint_as_float(r[kb & 1][4 * j4 + 2]);
-      v[4 * j4 + 3] = __uint_as_float(r[kb & 1][4 * j4 + 3]);
+      v[4 * j4 + 0] = __uint_as_float(r[kb][4 * j4 + 0]);
+      v[4 * j4 + 1] = __uint_as_float(r[kb][4 * j4 + 1]);
+      v[4 * j4 + 2] = __uint_as_float(r[kb][4 * j4 + 2]);
+      v[4 * j4 + 3] = __uint_as_float(r[kb][4 * j4 + 3]);
       add_f32x2(v[4 * j4 + 0], v[4 * j4 + 1], bq[j4].x, bq[j4].y);
       add_f32x2(v[4 * j4 + 2], v[4 * j4 + 3], bq[j4].z, bq[j4].w);
-    }
-    if (kb + 1 < NCH) {
-#pragma unroll
-      for (int j4 = 0; j4 < TC_CPT / 4; ++j4) bq[j4] = *reinterpret_cast<const float4*>(c.bias + col0 + 64 + 4 * j4);
     }
     if (KIND == MK_BASE_OUT) {       // density head on the rectified base_out (fp32)
 #pragma unroll
@@ -267,36 +265,43 @@ mip_fwd_tc_kernel(const MipTcLayout lay, const uint8_t* __restrict__ packed, con
     // warp-uniform control flow (all lanes wait on the barriers), one elected lane issues the tcgen05 instructions
     {
       uint32_t stage = 0, phase = 0, a_par = 0;
+      const uint64_t desc_a0 = umma_desc_sw128(sA), desc_ad = umma_desc_sw128(sAD), desc_w0 = umma_desc_sw128(sW);
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int l = 0; l < MIP_TC_NL; ++l) {
           const int kind = lay.L[l].kind, nkb = lay.L[l].nkb, n = nkb + lay.L[l].nkb_extra;
           const uint32_t d_tmem = tmem_base + (lay.L[l].region ? 256u : 0u);
           const uint32_t idesc = umma_idesc_16(TC_M, lay.L[l].N, FP16 ? 0 : 1);
-          for (int kb = 0; kb < n; ++kb) {
-            // operand block: A[kb] for the main K-blocks; the skip layer's extra blocks re-use A[0..2]; H0's extra
-            // block is the encoded-dirs block (2 of its 4 K-steps are used)
-            const bool extra = kb >= nkb;
-            const bool is_dirs = extra && kind == MK_H0;
-            const int idx = is_dirs ? 4 : (extra ? kb - nkb : kb);
-            if (extra && kb == nkb && !is_dirs) {      // x-part MMAs done -> A may be re-encoded
-              if (elect_one_sync()) tc_commit(bar(BAR_X_DONE));
-              __syncwarp();
-            }
+          // one K-block kb of the layer reading operand block idx (4 = encoded dirs, 2 of its 4 K-steps)
+          auto kblock = [&](const int kb, const int idx) {
             mbar_wait(bar(BAR_A_READY(idx)), (a_par >> idx) & 1u, dbg, 2);
             a_par ^= 1u << idx;
             mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
             tc_fence_after();
-            const uint64_t a0 = umma_desc_sw128(is_dirs ? sAD : sA + (uint32_t)idx * TC_KB_BYTES);
-            const uint64_t b0 = umma_desc_sw128(sW + stage * TC_STAGE_BYTES);
+            const uint64_t a0 = idx == 4 ? desc_ad : desc_a0 + (uint64_t)(idx * (TC_KB_BYTES >> 4));
+            const uint64_t b0 = desc_w0 + (uint64_t)(stage * (TC_STAGE_BYTES >> 4));
             const uint32_t acc0 = kb > 0 ? 1u : 0u;
             if (elect_one_sync()) {
-              if (is_dirs) tc_mma_kblock<2>(d_tmem, a0, b0, idesc, acc0);
+              if (idx == 4) tc_mma_kblock<2>(d_tmem, a0, b0, idesc, acc0);
               else tc_mma_kblock<4>(d_tmem, a0, b0, idesc, acc0);
               tc_commit(bar(BAR_W_EMPTY(stage)));
               if (kb == n - 1) tc_commit(bar(BAR_ACC_FULL));
             }
             __syncwarp();
             if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
+          };
+          if (n == 4) {              // plain hidden layer, unrolled: K-block indices become immediates
+            kblock(0, 0); kblock(1, 1); kblock(2, 2); kblock(3, 3);
+          } else {
+            for (int kb = 0; kb < nkb; ++kb) kblock(kb, kb);
+            if (n > nkb) {
+              if (kind == MK_H0) {
+                kblock(nkb, 4);                         // encoded-dirs block
+              } else {                                  // skip layer: x-part MMAs done -> A may be re-encoded
+                if (elect_one_sync()) tc_commit(bar(BAR_X_DONE));
+                __syncwarp();
+                for (int e = 0; e < n - nkb; ++e) kblock(nkb + e, e);
+              }
+            }
           }
         }
       }

@@ -214,6 +214,7 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     // warp-uniform control flow (all lanes wait on the barriers), one elected lane issues the tcgen05 instructions
     {
       uint32_t stage = 0, phase = 0, a_par = 0;
+      const uint64_t desc_a0 = umma_desc_sw128(sA), desc_w0 = umma_desc_sw128(sW);
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int ph = 0;              // index of the epilogue phase that produced the A operand of the current group
         bool group_start = true;
@@ -230,8 +231,8 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
           tc_fence_after();
           const uint32_t idesc = umma_idesc_16(TC_M, s.N, FP16 ? 0 : 1);
-          const uint64_t a0 = umma_desc_sw128(sA + (uint32_t)s.a_kb * TC_KB_BYTES);
-          const uint64_t b0 = umma_desc_sw128(sW + stage * TC_STAGE_BYTES);
+          const uint64_t a0 = desc_a0 + (uint64_t)(s.a_kb * (TC_KB_BYTES >> 4));
+          const uint64_t b0 = desc_w0 + (uint64_t)(stage * (TC_STAGE_BYTES >> 4));
           if (elect_one_sync()) {
             tc_mma_kblock<4>(tmem_base + (uint32_t)s.tcol, a0, b0, idesc, s.accum ? 1u : 0u);   // every stage has 4 K-steps
             tc_commit(bar(BAR_W_EMPTY(stage)));
