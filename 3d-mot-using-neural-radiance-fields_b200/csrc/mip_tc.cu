@@ -7,9 +7,9 @@
 // Layer program per tile (K-blocks of 64 features; N = output width):
 //   encode IPE (147 -> 192) into A[0..2], encoded dirs (27 -> 32) into AD
 //   L0 : A[0..2]            N=256 ReLU                         L1..L3 : A[0..3] N=256 ReLU
-//   L4 : A[0..3] (x part), then -- once those MMAs are done (x_done) -- the epilogue warps RE-ENCODE the IPE into
-//        A[0..2] and 3 more K-blocks accumulate the skip connection's encoding part (nerfstudio MLP: cat[enc, x]);
-//        re-encoding costs ~2 % of a tile and saves 48 KB of shared memory that the weight ring needs
+//   L4 : A[0..3] (x part), then -- once those MMAs are done (x_done) -- the epilogue warps put the IPE back into
+//        A[0..2] (each thread kept its 24 packed words) and 3 more K-blocks accumulate the skip connection's
+//        encoding part (nerfstudio MLP: cat[enc, x]); this saves the 48 KB of shared memory the weight ring needs
 //   L5..L7 : A[0..3] N=256 ReLU; L7's epilogue also takes the density head (fp32 dot on the rectified base_out)
 //   H0 : A[0..3] + AD       N=128 ReLU -> A[0..1]              H1 : A[0..1] N=128 ReLU + rgb head (fp32 dot)
 // Biases are fp32 and added in the epilogue; the two heads run in fp32 on un-rounded activations (as in mlp_tc.cu).
@@ -118,30 +118,72 @@ __device__ __forceinline__ MipTcGeom mip_tc_geom(const float* __restrict__ origi
   return g;
 }
 
-// feature j (0..191) of the integrated positional encoding: [e sin(a) (72) | e sin(a + pi/2) (72) | mean (3) | 0]
-__device__ __forceinline__ float ipe_feature(const MipTcGeom& g, const float* __restrict__ s_f, int j) {
-  if (j >= MIP_KX) return 0.f;
-  if (j >= 6 * MIP_NF) return j == 6 * MIP_NF ? g.mean[0] : (j == 6 * MIP_NF + 1 ? g.mean[1] : g.mean[2]);
-  const int jj = j < 3 * MIP_NF ? j : j - 3 * MIP_NF;
-  const int c = jj / MIP_NF, k = jj - c * MIP_NF;
+// Kernel-internal K order of the integrated positional encoding (the packed weights are permuted to match,
+// mip_pack_tc_stream_kernel): column 2 p + t, p = c * 24 + k the (axis, frequency) pair, t = 0: e sin(a), t = 1:
+// e sin(a + pi/2); columns 144..146 the raw mean; zero padding up to 192.  A thread's 16 columns are 8 whole pairs, so
+// the damping factor and the range reduction are shared by the two features of a pair (the reference evaluates
+// sin(fl(a + pi/2)); cos of the reduced argument differs by < ulp(a)/2, far below the 16-bit operand resolution).
+__host__ __device__ __forceinline__ int ipe_master_col(int col) {   // kernel column -> reference feature index, -1 = padding
+  if (col < 6 * MIP_NF) return (col & 1) * 3 * MIP_NF + (col >> 1);
+  return col < MIP_KX ? col : -1;
+}
+
+__device__ __forceinline__ void ipe_pair(const MipTcGeom& g, const float* __restrict__ s_f, int p, float& f0, float& f1) {
+  const int c = p / MIP_NF, k = p - c * MIP_NF;
   const float mc = c == 0 ? g.mean[0] : (c == 1 ? g.mean[1] : g.mean[2]);
   const float dc = c == 0 ? g.diag[0] : (c == 1 ? g.diag[1] : g.diag[2]);
   const float hv = -0.5f * __fmul_rn(dc, s_f[MIP_NF + k]);
-  if (hv < -104.f) return 0.f;           // exp underflows to 0 in fp32: the reference's feature is exactly 0
-  float a = __fmul_rn(__fmul_rn(MIP_TWO_PI, mc), s_f[k]);
-  if (j >= 3 * MIP_NF) a = __fadd_rn(a, MIP_PIO2);
-  return __expf(hv) * sin_reduced(a);
+  f0 = 0.f; f1 = 0.f;
+  if (hv >= -104.f) {                    // below: exp underflows to 0 in fp32, the reference's features are exactly 0
+    const float a = __fmul_rn(__fmul_rn(MIP_TWO_PI, mc), s_f[k]);
+    const float n = rintf(a * 0.15915494309189535f);
+    float r = fmaf(-n, 6.28318548202514648f, a);
+    r = fmaf(-n, -1.74845553146951715e-7f, r);
+    float sn, cs;
+    __sincosf(r, &sn, &cs);
+    const float e = __expf(hv);
+    f0 = e * sn;
+    f1 = e * cs;
+  }
 }
 
+// 16 fp32 values -> 8 packed 16-bit pairs
+template <bool FP16>
+__device__ __forceinline__ void pack_row16(const float (&v)[16], uint32_t (&w)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = pack_16x2<FP16, false>(v[2 * i], v[2 * i + 1]);
+}
+__device__ __forceinline__ void store_words16(uint32_t kblock_saddr, int row, int ch0, const uint32_t (&w)[8]) {
+  const uint32_t x = (uint32_t)row & 7u;
+  st_shared_v4(kblock_saddr + (uint32_t)row * 128u + ((((uint32_t)ch0) ^ x) << 4), w[0], w[1], w[2], w[3]);
+  st_shared_v4(kblock_saddr + (uint32_t)row * 128u + ((((uint32_t)(ch0 + 1)) ^ x) << 4), w[4], w[5], w[6], w[7]);
+}
+
+// Encodes this thread's 3 x 16 columns, stores them into A[0..2] and keeps the packed words for the skip layer
 template <bool FP16>
 __device__ __forceinline__ void encode_ipe_blocks(const MipTcGeom& g, const float* __restrict__ s_f, uint32_t sA, int row,
-                                                  int cg) {
-#pragma unroll 1
+                                                  int cg, uint32_t (&cache)[3][8]) {
+#pragma unroll
   for (int kb = 0; kb < 3; ++kb) {
     float e[16];
+    const int col0 = kb * 64 + cg * 16;
+    if (col0 + 16 <= 6 * MIP_NF) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) e[j] = ipe_feature(g, s_f, kb * 64 + cg * 16 + j);
-    store_row16<FP16, false>(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, e);
+      for (int j = 0; j < 8; ++j) ipe_pair(g, s_f, (col0 >> 1) + j, e[2 * j], e[2 * j + 1]);
+    } else {                             // the block that holds the last pairs, the raw mean and the padding
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = col0 + 2 * j;
+        e[2 * j] = 0.f; e[2 * j + 1] = 0.f;
+        if (col + 1 < 6 * MIP_NF) ipe_pair(g, s_f, col >> 1, e[2 * j], e[2 * j + 1]);
+        else {
+          if (col == 6 * MIP_NF) { e[2 * j] = g.mean[0]; e[2 * j + 1] = g.mean[1]; }
+          if (col == 6 * MIP_NF + 2) e[2 * j] = g.mean[2];
+        }
+      }
+    }
+    pack_row16<FP16>(e, cache[kb]);
+    store_words16(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, cache[kb]);
   }
 }
 
@@ -328,7 +370,8 @@ mip_fwd_tc_kernel(const MipTcLayout lay, const uint8_t* __restrict__ packed, con
         for (int c = 0; c < 3; ++c) { g.mean[c] = 0.f; g.diag[c] = 1e30f; g.d[c] = 0.f; }
       }
       // ---- inputs: IPE -> A[0..2]; encoded dirs -> AD (columns 0..31: groups 0 and 1)
-      encode_ipe_blocks<FP16>(g, s_f, sA, row, cg);
+      uint32_t enc_cache[3][8];
+      encode_ipe_blocks<FP16>(g, s_f, sA, row, cg, enc_cache);
       if (cg < 2) {
         float e[16];
 #pragma unroll
@@ -362,11 +405,13 @@ mip_fwd_tc_kernel(const MipTcLayout lay, const uint8_t* __restrict__ packed, con
       for (int l = 0; l < MIP_TC_NL; ++l) {
         const MipTcLayer& L = lay.L[l];
         if (L.kind != MK_H0 && L.nkb_extra > 0) {
-          // skip layer: once its x-part MMAs are complete the A blocks are free -> re-encode the input into A[0..2]
+          // skip layer: once its x-part MMAs are complete the A blocks are free -> the encoding (kept as 24 packed
+          // words per thread since the tile's first encode) goes back into A[0..2]
           mbar_wait(bar(BAR_X_DONE), x_par, dbg, 6);
           x_par ^= 1u;
           tc_fence_after();
-          encode_ipe_blocks<FP16>(g, s_f, sA, row, cg);
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) store_words16(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, enc_cache[kb]);
           fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
@@ -465,11 +510,10 @@ __global__ void mip_pack_tc_stream_kernel(MipTcLayout tl, MipLayout ml, const fl
     const int K = ml.K[ml_idx];
     int k = -1;   // master column of this element, -1 = zero padding
     if (l == 0) {
-      k = kb * 64 + kk;
-      if (k >= MIP_KX) k = -1;
+      k = ipe_master_col(kb * 64 + kk);                 // kernel-internal K order of the encoding
     } else if (l == MIP_SKIP) {
       if (kb < 4) k = MIP_KX + kb * 64 + kk;            // x part first (issue order), encoding part after x_done
-      else { k = (kb - 4) * 64 + kk; if (k >= MIP_KX) k = -1; }
+      else k = ipe_master_col((kb - 4) * 64 + kk);
     } else if (l == 8) {
       if (kb < 4) k = MIP_KD + kb * 64 + kk;            // base_out part, then the encoded-dirs block
       else { k = kk; if (k >= MIP_KD) k = -1; }
