@@ -287,25 +287,28 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
       // ---- layers
       for (int l = 0; l < lay.n_layers; ++l) {
         const TcLayer& L = lay.L[l];
+        // everything that does not depend on the accumulator is set up BEFORE the wait: the stretch from "accumulator
+        // complete" to "first operand block of the next layer published" is tensor-idle time of every layer
+        const int kind = L.kind;
+        ctx.tcol = tmem_base + (((uint32_t)(q * 32)) << 16) + (L.region ? 256u : 0u) + (uint32_t)(cg * TC_CPT);
+        ctx.bias = s_small + L.bias_off;
+        if (STASH) ctx.stash_out = stash + ((size_t)tile * (size_t)lay.stash_blocks + (size_t)L.s_out) * TC_BLOCK_BYTES;
+        float h[3] = {0.f, 0.f, 0.f};
         TL_STAMP(tile == tl_tile && tid == 0, 80 + 8 * l);
         mbar_wait(bar(BAR_ACC_FULL), acc_par, dbg, 4);
         acc_par ^= 1u;
         tc_fence_after();
         TL_STAMP(tile == tl_tile && tid == 0, 81 + 8 * l);
-        ctx.tcol = tmem_base + (((uint32_t)(q * 32)) << 16) + (L.region ? 256u : 0u) + (uint32_t)(cg * TC_CPT);
-        ctx.bias = s_small + L.bias_off;
-        if (STASH) ctx.stash_out = stash + ((size_t)tile * (size_t)lay.stash_blocks + (size_t)L.s_out) * TC_BLOCK_BYTES;
-        float h[3] = {0.f, 0.f, 0.f};
         if (dbg_mode & 1) {
-          for (int kb = 0; kb < (L.N >> 6) && L.kind != LK_VIEWS; ++kb) {
+          for (int kb = 0; kb < (L.N >> 6) && kind != LK_VIEWS; ++kb) {
             fence_proxy_async_smem(); tc_fence_before(); __syncwarp();
             if (lane == 0) mbar_arrive(bar(BAR_A_READY(kb)));
           }
-        } else if (L.kind == LK_FC0 || L.kind == LK_FC1 || L.kind == LK_IN) {
+        } else if (kind == LK_FC0 || kind == LK_FC1 || kind == LK_IN) {
           epilogue_layer<LK_FC0, FP16, STASH>(ctx, h);
-        } else if (L.kind == LK_FEAT) {
+        } else if (kind == LK_FEAT) {
           epilogue_layer<LK_FEAT, FP16, STASH>(ctx, h);
-        } else if (L.kind == LK_OUT) {
+        } else if (kind == LK_OUT) {
           ctx.head_w = s_small + lay.off_alpha_w;
           epilogue_layer<LK_OUT, FP16, STASH>(ctx, h);
           // combine the 4 column groups of each row: groups 1..3 park their partial, group 0 finishes
