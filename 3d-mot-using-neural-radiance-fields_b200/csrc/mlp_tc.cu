@@ -92,8 +92,8 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3]) {
       }
       if (STASH) store_row16<FP16, true>(0u, c.row, c.cg * 2, v, c.stash_out + kb * TC_KB_BYTES);
     } else {
-      if (STASH) store_row16<FP16, RELU>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v, c.stash_out + kb * TC_KB_BYTES);
-      else store_row16<FP16, RELU>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v);
+      // (training: the stash copy of this block is a bulk store issued by the producer warp once the block is complete)
+      store_row16<FP16, RELU>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v);
       fence_proxy_async_smem();      // this thread's A writes -> async proxy (tcgen05.mma operand reads)
       tc_fence_before();
       __syncwarp();
@@ -148,6 +148,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     for (int i = 0; i < TC_NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), 1); mbar_init(bar(BAR_W_EMPTY(i)), 1); }
     for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A_READY(i)), TC_EPI_WARPS);
     mbar_init(bar(BAR_ACC_FULL), 1);
+    mbar_init(bar(BAR_STASH_DONE), 1);
     fence_mbar_init();
   }
   if (warp == TC_EPI_WARPS + 1) tmem_alloc(base + sl.tmem_ptr, TC_TMEM_COLS);
@@ -162,13 +163,35 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
 
   if (warp == TC_EPI_WARPS) {
     // ======================================================================== weight producer
+    // Training (STASH): the same thread also writes the activation stash.  A shared-memory A block IS the 16 KB stash
+    // block (same swizzled image), so once all 16 epilogue warps have published output block kb of layer ls
+    // (a_ready[kb]) one bulk store moves it to global memory -- instead of two 16-byte stores per thread and chunk.
+    // The store of (ls, kb) is issued just before the weights of (ls + 2, kb) are requested (it cannot be needed
+    // earlier than that: the weight stage frees only after MMA (ls + 1, kb), which itself waits for a_ready[kb]);
+    // stash_done tells the epilogue of layer ls + 1 that the A blocks have been read and may be overwritten.
     if (lane == 0) {
       const uint8_t* wstream = packed + lay.small_bytes;
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, phase = 0, s_par = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        uint8_t* st_tile = STASH ? stash + (size_t)tile * (size_t)lay.stash_blocks * TC_BLOCK_BYTES : nullptr;
+        auto stash_chunk = [&](int ls, int kb) {
+          mbar_wait(bar(BAR_A_READY(kb)), (s_par >> kb) & 1u, dbg, 6);
+          s_par ^= 1u << kb;
+          bulk_s2g(st_tile + (size_t)(lay.L[ls].s_out + kb) * TC_BLOCK_BYTES, sA + (uint32_t)kb * TC_KB_BYTES, TC_KB_BYTES);
+          bulk_commit_group();
+          if (kb == 3) {
+            bulk_wait_group_read0();
+            mbar_arrive(bar(BAR_STASH_DONE));
+          }
+        };
+        if (STASH) {   // a_ready[0] also carries the encoder's arrival at the start of a tile: consume that phase
+          mbar_wait(bar(BAR_A_READY(0)), s_par & 1u, dbg, 6);
+          s_par ^= 1u;
+        }
         for (int l = 0; l < lay.n_layers; ++l) {
           const uint32_t bytes = (uint32_t)lay.L[l].N * 128u;
           for (int kb = 0; kb < lay.L[l].nkb; ++kb) {
+            if (STASH && l >= 2 && kb < 4) stash_chunk(l - 2, kb);
             mbar_wait(bar(BAR_W_EMPTY(stage)), phase ^ 1u, dbg, 1);
             if (dbg_mode & 2) {
               mbar_arrive(bar(BAR_W_FULL(stage)));
@@ -180,7 +203,10 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
           }
         }
+        if (STASH)
+          for (int kb = 0; kb < 4; ++kb) stash_chunk(lay.n_layers - 2, kb);   // feature_linear's output blocks
       }
+      if (STASH) bulk_wait_group0();
     }
   } else if (warp == TC_EPI_WARPS + 1) {
     // ======================================================================== MMA issuer
@@ -232,7 +258,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     // ======================================================================== epilogue warps
     const int q = warp & 3, cg = warp >> 2;
     const int row = q * 32 + lane;
-    uint32_t acc_par = 0;
+    uint32_t acc_par = 0, stash_par = 0;
     EpiCtx ctx;
     ctx.sA = sA; ctx.a_ready0 = bar(BAR_A_READY(0));
     ctx.row = row; ctx.cg = cg; ctx.lane = lane;
@@ -241,6 +267,10 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
       const int64_t gi = tile * TC_M + row;
       const bool valid = gi < M;
       int64_t out_idx = 0;
+      if (STASH && tile != (int64_t)blockIdx.x) {   // feature_linear's blocks of the previous tile have been read
+        mbar_wait(bar(BAR_STASH_DONE), stash_par, dbg, 7);
+        stash_par ^= 1u;
+      }
       TL_STAMP(tile == tl_tile && tid == 0, 8);
       // ---- inputs: pose transform + encoding -> A K-block 0 (xyz, 4 threads per row) and the dirs block
       {
@@ -298,6 +328,10 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         mbar_wait(bar(BAR_ACC_FULL), acc_par, dbg, 4);
         acc_par ^= 1u;
         tc_fence_after();
+        if (STASH && l >= 1 && L.kind != LK_VIEWS) {   // the previous layer's A blocks are in the stash: free to overwrite
+          mbar_wait(bar(BAR_STASH_DONE), stash_par, dbg, 7);
+          stash_par ^= 1u;
+        }
         TL_STAMP(tile == tl_tile && tid == 0, 81 + 8 * l);
         if (dbg_mode & 1) {
           for (int kb = 0; kb < (L.N >> 6) && kind != LK_VIEWS; ++kb) {

@@ -38,6 +38,7 @@ __host__ __device__ static inline TcSmem tc_smem_layout(uint32_t small_bytes) {
 #define BAR_W_EMPTY(i) (TC_NS + (i))
 #define BAR_A_READY(i) (2 * TC_NS + (i))      // 0..3: A K-blocks, 4: encoded-dirs block
 #define BAR_ACC_FULL (2 * TC_NS + 5)
+#define BAR_STASH_DONE (2 * TC_NS + 6)   // training forward: the bulk stores of a layer's A blocks have read shared memory
 
 // ---------------------------------------------------------------------------------------------- encode
 // 16 consecutive columns [C0, C0+16) of the positional encoding [x, sin(2^k x), cos(2^k x)]_k (embedder.py:90-97;
