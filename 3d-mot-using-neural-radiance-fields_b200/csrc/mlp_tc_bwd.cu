@@ -184,6 +184,7 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     for (int i = 0; i < TC_NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), 1); mbar_init(bar(BAR_W_EMPTY(i)), 1); }
     for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A_READY(i)), TC_EPI_WARPS);
     mbar_init(bar(BAR_ACC_FULL), 1);
+    mbar_init(bar(BAR_STASH_DONE), 1);
     fence_mbar_init();
   }
   if (warp == TC_EPI_WARPS + 1) tmem_alloc(base + sl.tmem_ptr, TC_TMEM_COLS);
@@ -197,17 +198,44 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
 
   if (warp == TC_EPI_WARPS) {
     // ======================================================================== weight producer
+    // The same thread writes the gradient stash: an A block in shared memory IS the 16 KB gstash block, so once all
+    // 16 epilogue warps have published block kb of phase g (a_ready[kb]) one bulk store moves it to global memory.
+    // The stores of phase g are issued before the weights of MMA group g + 1 are requested (its first ring stage frees
+    // only after an MMA of group g, which itself waits for every a_ready of phase g); stash_done then tells the
+    // epilogue of phase g + 1 that the A blocks have been read and may be overwritten.
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, phase = 0, s_par = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        uint8_t* gs_tile = gstash + (size_t)tile * (size_t)lay.gstash_blocks * TC_BLOCK_BYTES;
+        auto stash_phase = [&](int g) {
+          const int nch = phases[g].nch, g_blk = phases[g].g_blk;
+          if (nch == 0) return;
+          for (int kb = 0; kb < nch; ++kb) {
+            mbar_wait(bar(BAR_A_READY(kb)), (s_par >> kb) & 1u, dbg, 6);
+            s_par ^= 1u << kb;
+            if (g_blk >= 0) {
+              bulk_s2g(gs_tile + (size_t)(g_blk + kb) * TC_BLOCK_BYTES, sA + (uint32_t)kb * TC_KB_BYTES, TC_KB_BYTES);
+              bulk_commit_group();
+            }
+          }
+          bulk_wait_group_read0();
+          mbar_arrive(bar(BAR_STASH_DONE));
+        };
+        int grp = 0;
+        bool group_start = true;
         for (int i = 0; i < n_stages; ++i) {
           const BwdStage& s = stages[i];
+          if (group_start && grp >= 1) stash_phase(grp - 1);
+          group_start = false;
           mbar_wait(bar(BAR_W_EMPTY(stage)), phase ^ 1u, dbg, 1);
           mbar_arrive_expect_tx(bar(BAR_W_FULL(stage)), s.bytes);
           bulk_g2s(sW + stage * TC_STAGE_BYTES, packed + lay.small_bytes + s.w_off, s.bytes, bar(BAR_W_FULL(stage)));
           if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
+          if (s.last) { ++grp; group_start = true; }
         }
+        for (int g = grp - 1; g < n_phases; ++g) stash_phase(g);   // the phases after the last MMA group of the tile
       }
+      bulk_wait_group0();
     }
   } else if (warp == TC_EPI_WARPS + 1) {
     // ======================================================================== MMA issuer
@@ -258,7 +286,7 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     const int q = warp & 3, cg = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
-    uint32_t acc_par = 0;
+    uint32_t acc_par = 0, stash_par = 0;
     float pacc[POSE ? 27 : 1];
 #pragma unroll
     for (int i = 0; i < (POSE ? 27 : 1); ++i) pacc[i] = 0.f;
@@ -305,6 +333,10 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           mbar_wait(bar(BAR_ACC_FULL), acc_par, dbg, 4);
           acc_par ^= 1u;
           tc_fence_after();
+        }
+        if (P.nch > 0 && !(pi == 0 && tile == (int64_t)blockIdx.x)) {   // the previous phase's A blocks are in the gstash
+          mbar_wait(bar(BAR_STASH_DONE), stash_par, dbg, 7);
+          stash_par ^= 1u;
         }
         const uint32_t tX = tmem_base + lane_addr + (uint32_t)(cg * TC_CPT);
         const uint32_t tT = tX + 256u;
@@ -396,8 +428,8 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = 0.f;
           }
-          store_row16<FP16, false>(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, v,
-                                   gs_tile + (size_t)(P.g_blk + kb) * TC_BLOCK_BYTES);
+          // (the gstash copy of this block is a bulk store issued by the producer warp once the block is complete)
+          store_row16<FP16, false>(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, v);
           fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
