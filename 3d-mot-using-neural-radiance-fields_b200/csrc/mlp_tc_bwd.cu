@@ -647,17 +647,25 @@ head_grad_tc_kernel(const TcLayout lay, MlpLayout ml, const uint8_t* __restrict_
     const uint8_t* tile = stash + (size_t)t * lay.stash_blocks * TC_BLOCK_BYTES;
     const uint8_t* hb = tile + (size_t)(lay.L[F].s_in + (ch >> 3)) * TC_BLOCK_BYTES;
     const uint8_t* h2b = tile + (size_t)(lay.L[V].s_out + ((ch & 15) >> 3)) * TC_BLOCK_BYTES;
-#pragma unroll 4
+    // all 16 (+16) 16-byte loads of the tile are issued before the first use: the kernel is a pure HBM reader
+    uint4 qh[16], q2[16];
+#pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int m = rg * 16 + i;
       const uint32_t off = (uint32_t)m * 128u + ((((uint32_t)ch & 7u) ^ ((uint32_t)m & 7u)) << 4);
+      qh[i] = __ldg(reinterpret_cast<const uint4*>(hb + off));
+      if (ch < 16) q2[i] = __ldg(reinterpret_cast<const uint4*>(h2b + off));
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int m = rg * 16 + i;
       const float4 d = *reinterpret_cast<const float4*>(&s_d[m][0]);
       float x[8];
-      unpack8(*reinterpret_cast<const uint4*>(hb + off), fp16 != 0, x);
+      unpack8(qh[i], fp16 != 0, x);
 #pragma unroll
       for (int j = 0; j < 8; ++j) aw[j] = fmaf(d.x, x[j], aw[j]);
       if (ch < 16) {
-        unpack8(*reinterpret_cast<const uint4*>(h2b + off), fp16 != 0, x);
+        unpack8(q2[i], fp16 != 0, x);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           rw[0][j] = fmaf(d.y, x[j], rw[0][j]);
@@ -808,7 +816,7 @@ int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed
   }
   // ---- 3. heads
   {
-    int blocks = (int)(ntiles < 2 * sms ? ntiles : 2 * sms);
+    int blocks = (int)(ntiles < 4 * sms ? ntiles : 4 * sms);
     head_grad_tc_kernel<<<blocks, 256, 0, st>>>(tl, ml, (const uint8_t*)stash, d_raw_alpha, d_raw_rgb, ray_stride, S, M,
                                                 fp16, grad_flat);
     return star_check_launch();
