@@ -42,6 +42,8 @@ _SIGS = {
     "star_packed_bytes": (C.c_size_t, [C.POINTER(StarNetDesc)]),
     "star_pack_weights": (C.c_int, [C.POINTER(StarNetDesc), c_f, c_f, c_f]),
     "star_sample_pts": (C.c_int, [c_f, c_f, c_f, c_f, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f]),
+    "star_get_rays": (C.c_int, [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, c_f, C.c_int, C.c_int,
+                                c_f, c_f, c_f, c_f]),
     "star_embed": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f]),
     "star_stash_bytes": (C.c_size_t, [C.POINTER(StarNetDesc), c_i64]),
     "star_mlp_forward": (C.c_int, [C.POINTER(StarNetDesc), c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, c_f, c_f,

@@ -110,6 +110,50 @@ extern "C" int star_sample_pts(const float* rays_o, const float* rays_d, const f
   return star_check_launch();
 }
 
+// ------------------------------------------------------------------------------------------ a2
+// models/rendering__.py:41-55 get_rays: pinhole rays of an H x W view (or of the pixel rows [row0, row0 + nrows)):
+// dirs = [(i - cx) / fx, -(j - cy) / fy, -1]; rays_d = sum_k dirs[k] * c2w[c][k]; rays_o = c2w[:, 3].
+// One rounding per reference op (no FMA contraction); optional fused viewdirs = rays_d / ||rays_d||.
+__global__ void get_rays_kernel(int W, float fx, float fy, float cx, float cy, const float* __restrict__ c2w, int row0,
+                                int64_t n, float* __restrict__ rays_o, float* __restrict__ rays_d,
+                                float* __restrict__ viewdirs) {
+  __shared__ float m[12];
+  if (threadIdx.x < 12) m[threadIdx.x] = c2w[threadIdx.x];
+  __syncthreads();
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int j = row0 + (int)(p / W), i = (int)(p % W);
+    const float d0 = __fdiv_rn(__fsub_rn((float)i, cx), fx);
+    const float d1 = -__fdiv_rn(__fsub_rn((float)j, cy), fy);
+    const float d2 = -1.f;
+    float r[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      r[c] = __fadd_rn(__fadd_rn(__fmul_rn(d0, m[c * 4 + 0]), __fmul_rn(d1, m[c * 4 + 1])), __fmul_rn(d2, m[c * 4 + 2]));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      rays_d[p * 3 + c] = r[c];
+      rays_o[p * 3 + c] = m[c * 4 + 3];
+    }
+    if (viewdirs != nullptr) {
+      const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(r[0], r[0]), __fmul_rn(r[1], r[1])), __fmul_rn(r[2], r[2])));
+#pragma unroll
+      for (int c = 0; c < 3; ++c) viewdirs[p * 3 + c] = __fdiv_rn(r[c], nrm);
+    }
+  }
+}
+
+extern "C" int star_get_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, int row0, int nrows,
+                             float* rays_o, float* rays_d, float* viewdirs, void* stream) {
+  if (!c2w || !rays_o || !rays_d) return STAR_E_NULL;
+  if (H < 1 || W < 1 || row0 < 0 || nrows < 0 || row0 + nrows > H) return STAR_E_BAD_SHAPE;
+  if (nrows == 0) return STAR_OK;
+  const int64_t n = (int64_t)nrows * W;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  get_rays_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(W, fx, fy, cx, cy, c2w, row0, n, rays_o, rays_d, viewdirs);
+  return star_check_launch();
+}
+
 // ------------------------------------------------------------------------------------------ a3
 // models/embedder.py:81-112 -- one thread per output element so that writes are coalesced.
 __global__ void embed_kernel(const float* __restrict__ x, int64_t M, int L, const float* __restrict__ scale,

@@ -80,6 +80,22 @@ def sample_pts(rays_o, rays_d, near, far, N_samples, lindisp=False, t_rand=None)
     return pts, z
 
 
+# ------------------------------------------------------------------------------------------ a2
+def get_rays(H, W, K, c2w, rows=None, want_viewdirs=False):
+    """models/rendering__.py:41-55 on the GPU: rays of the pixel rows `rows` = (row0, nrows) (default: the whole view)
+    from the 3x4 camera-to-world matrix `c2w` (CUDA tensor).  Returns rays_o, rays_d [nrows, W, 3] (+ viewdirs)."""
+    c2w = _c(c2w[:3, :4].to(torch.float32))
+    row0, nrows = (0, H) if rows is None else rows
+    dev = c2w.device
+    ro = torch.empty((nrows, W, 3), device=dev)
+    rd = torch.empty((nrows, W, 3), device=dev)
+    vd = torch.empty((nrows, W, 3), device=dev) if want_viewdirs else None
+    check(_capi.lib().star_get_rays(int(H), int(W), float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]),
+                                    f32(c2w), int(row0), int(nrows), f32(ro), f32(rd), ptr(vd), stream()), "star_get_rays")
+    _count()
+    return (ro, rd, vd) if want_viewdirs else (ro, rd)
+
+
 # ------------------------------------------------------------------------------------------ a3
 def embed(x, L, scale=None):
     """models/embedder.py:81-112 (stand-alone form; the MLP kernels encode in registers)."""

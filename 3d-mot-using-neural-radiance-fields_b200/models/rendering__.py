@@ -25,7 +25,11 @@ def to8b(img, debug_type=None):
 
 
 def get_rays(H, W, K, c2w):
-    """Pinhole rays (:41-55): dirs = [(i-cx)/fx, -(j-cy)/fy, -1] rotated by c2w; rays_d un-normalised."""
+    """Pinhole rays (:41-55): dirs = [(i-cx)/fx, -(j-cy)/fy, -1] rotated by c2w; rays_d un-normalised.
+    A CUDA `c2w` runs the star_get_rays kernel (bit-identical); host tensors (dataset preparation, as in the reference's
+    datasets/*.py) stay on the host."""
+    if torch.is_tensor(c2w) and c2w.is_cuda:
+        return F_.get_rays(H, W, K, c2w)
     dev = c2w.device if torch.is_tensor(c2w) else None
     i, j = torch.meshgrid(torch.linspace(0, W - 1, W, device=dev), torch.linspace(0, H - 1, H, device=dev),
                           indexing="xy")

@@ -75,6 +75,14 @@ int star_sample_pts(const float* rays_o, const float* rays_d, const float* t_val
                     float near_, float far_, int R, int Nc, int lindisp, float* pts, float* z_vals,
                     void* stream);
 
+/* ---- a2: models/rendering__.py:41-55  get_rays ---------------------------------
+ * Pinhole rays of the pixel rows [row0, row0 + nrows) of an H x W view: intrinsics (fx, fy, cx, cy) = (K[0][0], K[1][1],
+ * K[0][2], K[1][2]), c2w = DEVICE pointer to the [3,4] camera-to-world matrix (row-major).  Outputs rays_o, rays_d
+ * [nrows*W, 3] (rays_d un-normalised, bit-exact vs the reference ops) and, if viewdirs != NULL, rays_d / ||rays_d||.
+ * Lets a full-view render start from 12 floats instead of 24 B/ray of host-generated rays. */
+int star_get_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w, int row0, int nrows,
+                  float* rays_o, float* rays_d, float* viewdirs, void* stream);
+
 /* ---- a3: models/embedder.py:81-112  Embedder.forward -----------------------------------------
  * x[M,3] -> out[M,3+6L].  scale[3+6L] or NULL: per-element BARF mask (w[j mod L] quirk, :32). */
 int star_embed(const float* x, int M, int L, const float* scale, float* out, void* stream);

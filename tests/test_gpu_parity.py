@@ -475,3 +475,19 @@ def test_rays_are_independent_and_chunking_is_invisible():
     for k in ("rgb", "depth", "weights", "rgb0", "rgb_dynamic", "dynamic_transmittance"):
         assert torch.equal(full[k][perm], pp[k]), k
         assert torch.equal(full[k], split[k]), k
+
+
+# ------------------------------------------------------------------------------------------ a2 (8f-1)
+@pytest.mark.parametrize("H,W", [(100, 100), (37, 53), (720, 1280)])
+def test_get_rays_kernel_bit_exact(H, W):
+    focal = 0.5 * W / math.tan(0.5 * 0.6911112)
+    K = torch.tensor([[focal, 0, 0.5 * W], [0, focal * 1.01, 0.5 * H - 0.25], [0, 0, 1.0]])
+    g = torch.Generator().manual_seed(5)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+    c2w = torch.cat([q, torch.randn(3, 1, generator=g)], 1)
+    ro_ref, rd_ref = so.get_rays(H, W, K, c2w)
+    ro, rd = R_.get_rays(H, W, K, cu(c2w))
+    assert torch.equal(ro.cpu(), ro_ref) and torch.equal(rd.cpu(), rd_ref)
+    ro2, rd2, vd2 = F_.get_rays(H, W, K, cu(c2w), rows=(H // 3, H // 2), want_viewdirs=True)
+    assert torch.equal(rd2.cpu(), rd_ref[H // 3:H // 3 + H // 2])
+    assert_close(vd2, rd_ref[H // 3:H // 3 + H // 2] / rd_ref[H // 3:H // 3 + H // 2].norm(dim=-1, keepdim=True), 2e-7)
