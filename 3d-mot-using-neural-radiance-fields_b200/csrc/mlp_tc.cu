@@ -15,7 +15,11 @@
 // T = columns 256..511 holds the other accumulator.  fc_1 ACCUMULATES onto X, which performs the residual
 // add inside the tensor core.  Layers alternate X/T, so the epilogue of layer L (reading one region and
 // producing A K-block by K-block) overlaps the MMA of layer L+1 (writing the other region, consuming A
-// K-block by K-block through the a_ready[] barriers).
+// K-block by K-block).  An operand block of layer L+1 is announced on the SAME barrier as the weight K-block it will
+// be multiplied with: w_full[stage] expects 1 arrival + the copy's bytes from the producer and 16 arrivals from the
+// epilogue warps (count 17), so the issuer -- whose loop must stay under the 512 tensor cycles of a K-block -- waits
+// on one barrier per K-block instead of two.  (The encoded-dirs block is written a whole tile ahead of its use and
+// keeps its own a_ready[4]; training additionally arrives on a_ready[kb] for the stash writer.)
 #include "star_common.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -36,6 +40,8 @@ struct EpiCtx {
   const float* bias;           // smem, epilogue bias vector of this layer
   const float* head_w;         // smem, alpha_linear / rgb_linear weights (OUT / VIEWS layers)
   uint8_t* stash_out;          // global: first stash block of this layer's epilogue output for this tile, or NULL
+  uint32_t w_full0;            // smem address of barrier w_full[0]
+  uint32_t next_stage0;        // ring stage of the NEXT layer's K-block 0 (its K-block kb uses (next_stage0 + kb) % 4)
   int row, cg, lane;
 };
 
@@ -97,7 +103,10 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3]) {
       fence_proxy_async_smem();      // this thread's A writes -> async proxy (tcgen05.mma operand reads)
       tc_fence_before();
       __syncwarp();
-      if (c.lane == 0) mbar_arrive(c.a_ready0 + 8u * (uint32_t)kb);
+      if (c.lane == 0) {
+        mbar_arrive(c.w_full0 + 8u * ((c.next_stage0 + (uint32_t)kb) & (TC_NS - 1)));
+        if (STASH) mbar_arrive(c.a_ready0 + 8u * (uint32_t)kb);
+      }
     }
   }
 }
@@ -145,7 +154,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
 
   // ---- one-time setup
   if (warp == TC_EPI_WARPS && lane == 0) {
-    for (int i = 0; i < TC_NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), 1); mbar_init(bar(BAR_W_EMPTY(i)), 1); }
+    for (int i = 0; i < TC_NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), 1 + TC_EPI_WARPS); mbar_init(bar(BAR_W_EMPTY(i)), 1); }
     for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A_READY(i)), TC_EPI_WARPS);
     mbar_init(bar(BAR_ACC_FULL), 1);
     mbar_init(bar(BAR_STASH_DONE), 1);
@@ -193,6 +202,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           for (int kb = 0; kb < lay.L[l].nkb; ++kb) {
             if (STASH && l >= 2 && kb < 4) stash_chunk(l - 2, kb);
             mbar_wait(bar(BAR_W_EMPTY(stage)), phase ^ 1u, dbg, 1);
+            if (lay.L[l].kind == LK_VIEWS && kb == 4) mbar_arrive_n(bar(BAR_W_FULL(stage)), TC_EPI_WARPS);
             if (dbg_mode & 2) {
               mbar_arrive(bar(BAR_W_FULL(stage)));
             } else {
@@ -222,9 +232,10 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           const uint32_t idesc = umma_idesc_16(TC_M, lay.L[l].N, FP16 ? 0 : 1);
           // one K-block: wait for its operand blocks, issue 4 (2 for the dirs block) MMAs, release the weight stage
           auto kblock = [&](const int kb, const bool dirs) {
-            const int idx = dirs ? 4 : kb;
-            mbar_wait(bar(BAR_A_READY(idx)), (a_par >> idx) & 1u, dbg, 2);
-            a_par ^= 1u << idx;
+            if (dirs) {
+              mbar_wait(bar(BAR_A_READY(4)), a_par & 1u, dbg, 2);
+              a_par ^= 1u;
+            }
             TL_STAMP(tile == tl_tile && lane == 0 && kb == 0, 16 + 4 * l);
             TL_STAMP(tile == tl_tile && lane == 0 && l == 2, 240 + 3 * kb);
             mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
@@ -259,8 +270,9 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     const int q = warp & 3, cg = warp >> 2;
     const int row = q * 32 + lane;
     uint32_t acc_par = 0, stash_par = 0;
+    uint32_t kstage = 0;          // ring stage of the current layer's K-block 0 (same sequence as producer / issuer)
     EpiCtx ctx;
-    ctx.sA = sA; ctx.a_ready0 = bar(BAR_A_READY(0));
+    ctx.sA = sA; ctx.a_ready0 = bar(BAR_A_READY(0)); ctx.w_full0 = bar(BAR_W_FULL(0));
     ctx.row = row; ctx.cg = cg; ctx.lane = lane;
     ctx.stash_out = nullptr;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -309,7 +321,8 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(bar(BAR_A_READY(0)));
+          mbar_arrive(bar(BAR_W_FULL(kstage & (TC_NS - 1))));   // operand of (layer 0, K-block 0)
+          if (STASH) mbar_arrive(bar(BAR_A_READY(0)));
           mbar_arrive(bar(BAR_A_READY(4)));
         }
         TL_STAMP(tile == tl_tile && tid == 0, 9);
@@ -325,6 +338,8 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         if (STASH) ctx.stash_out = stash + ((size_t)tile * (size_t)lay.stash_blocks + (size_t)L.s_out) * TC_BLOCK_BYTES;
         float h[3] = {0.f, 0.f, 0.f};
         TL_STAMP(tile == tl_tile && tid == 0, 80 + 8 * l);
+        kstage = (kstage + (uint32_t)L.nkb) & (TC_NS - 1);     // now the stage of the NEXT layer's K-block 0
+        ctx.next_stage0 = kstage;
         mbar_wait(bar(BAR_ACC_FULL), acc_par, dbg, 4);
         acc_par ^= 1u;
         tc_fence_after();
@@ -336,7 +351,10 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         if (dbg_mode & 1) {
           for (int kb = 0; kb < (L.N >> 6) && kind != LK_VIEWS; ++kb) {
             fence_proxy_async_smem(); tc_fence_before(); __syncwarp();
-            if (lane == 0) mbar_arrive(bar(BAR_A_READY(kb)));
+            if (lane == 0) {
+              mbar_arrive(bar(BAR_W_FULL((kstage + (uint32_t)kb) & (TC_NS - 1))));
+              if (STASH) mbar_arrive(bar(BAR_A_READY(kb)));
+            }
           }
         } else if (kind == LK_FC0 || kind == LK_FC1 || kind == LK_IN) {
           epilogue_layer<LK_FC0, FP16, STASH>(ctx, h);
