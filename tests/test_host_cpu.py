@@ -142,3 +142,45 @@ def test_install_registers_reference_module_names():
         for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
             sys.modules.pop(k)
         sys.modules.update({k: v for k, v in saved.items() if v is not None})
+
+
+# ------------------------------------------------------------------------------------------ mip variant (row a12), host side
+def test_mip_module_tree_param_count_and_install():
+    import argparse
+    from oracle import mip_oracle as mo
+    from star_b200.models.star_mipnerf import STaR as MipSTaR
+    args = argparse.Namespace(num_vehicles=2, chunk=64, far_dist=1e10, N_importance=8, N_samples=4, scale_factor=0.01,
+                              near=3.0, far=80.0)
+    net = MipSTaR(args)
+    sd = mo.init_mip_params(2, seed=0)
+    assert set(net.state_dict().keys()) == set(sd.keys())
+    net.load_state_dict(sd, strict=True)
+    lib = _capi.lib()
+    n = sum(p.numel() for p in net.static_nerf.parameters())
+    assert n == lib.star_mip_param_count() == 589572
+    assert sum(o * i for (o, i) in mo.mip_param_shapes().values()) == F_.MIP_MAC_PER_SAMPLE
+    assert net.near_plane == pytest.approx(0.03) and net.far_plane == pytest.approx(0.8)
+    assert len(net.get_nerf_params()) == 3 * 2 * len(mo.mip_param_shapes())
+    for prec in (_capi.PREC_F32, _capi.PREC_BF16, _capi.PREC_F16):
+        assert lib.star_mip_packed_bytes(prec) > 2 * n
+    assert lib.star_mip_stash_bytes(_capi.PREC_F32, 128) > 0 and lib.star_mip_stash_bytes(_capi.PREC_BF16, 128) == 0
+    star_b200.install("models_under_test")
+    import importlib
+    assert importlib.import_module("models_under_test.star_mipnerf").STaR is MipSTaR
+    assert importlib.import_module("models_under_test.rendering__").sample_pts is star_b200.rendering__.sample_pts
+
+
+def test_c_abi_argument_checks_need_no_gpu():
+    """Every entry point validates pointers / shapes before touching the device: status codes, never a crash."""
+    import ctypes as C
+    lib = _capi.lib()
+    assert lib.star_sample_pts(None, None, None, None, 0.0, 1.0, 4, 8, 0, None, None, None) == 3          # STAR_E_NULL
+    assert lib.star_get_rays(4, 4, 1.0, 1.0, 2.0, 2.0, None, 0, 4, None, None, None, None) == 3
+    assert lib.star_mip_uniform_bins(None, None, 0.0, 1.0, 4, 8, None, None, None) == 3
+    assert lib.star_mip_pdf_sample(None, None, 0, None, None, 0.0, 1.0, 4, 8, 8, None, None, None, None, None) == 3
+    assert lib.star_mip_field_forward(0, None, None, None, None, None, None, 0.5, 4, 8, None, None, 8, None, None) == 3
+    assert lib.star_mip_composite_single_forward(None, None, None, 4, 8, None, None, None, None, None) == 3
+    assert lib.star_mip_pack_weights(7, C.c_void_p(16), None, C.c_void_p(16), None) == 2                    # STAR_E_UNSUPPORTED
+    assert lib.star_error_string(2).decode().startswith("unsupported")
+    d = _capi.net_desc(4, 10, 4, _capi.PREC_F32)
+    assert lib.star_mlp_forward(C.byref(d), None, None, None, None, None, None, 4, 8, None, None, 8, None, None) == 3
