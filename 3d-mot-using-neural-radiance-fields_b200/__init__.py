@@ -7,16 +7,17 @@ burakcuhadar/3D-MOT-using-Neural-Radiance-Fields behind the reference's own Pyth
 
 `star_b200.install()` registers the mirrors as `models.rendering__`, `models.star__`, `models.nerf`,
 `models.embedder`, `models.resnet`, `models.types__`, `models.star_mipnerf`, `models.mipnerf`,
-`models.rendering_starmip` in sys.modules so that the reference's train
-scripts pick them up unmodified."""
+`models.rendering_starmip`, `models.loss` in sys.modules so that the reference's train
+scripts pick them up unmodified.  `star_b200.optim` holds the fused clip + Adam step."""
 import sys
 
 from . import _capi, functional, parallel  # noqa: F401
-from . import mip_functional  # noqa: F401
+from . import mip_functional, optim  # noqa: F401
+from .models import loss  # noqa: F401
 from .models import embedder, mipnerf, nerf, rendering__, rendering_starmip, resnet, star__, star_mipnerf, types__  # noqa: F401
 from .models.star__ import STaR  # noqa: F401
 
-__all__ = ["STaR", "functional", "install", "parallel", "rendering__", "star__"]
+__all__ = ["STaR", "functional", "install", "optim", "parallel", "rendering__", "star__"]
 
 
 def install(package="models"):
@@ -29,6 +30,6 @@ def install(package="models"):
         sys.modules[package] = pkg
     for name, mod in (("rendering__", rendering__), ("star__", star__), ("nerf", nerf), ("embedder", embedder),
                       ("resnet", resnet), ("types__", types__), ("star_mipnerf", star_mipnerf), ("mipnerf", mipnerf),
-                      ("rendering_starmip", rendering_starmip)):
+                      ("rendering_starmip", rendering_starmip), ("loss", loss)):
         sys.modules[f"{package}.{name}"] = mod
         setattr(pkg, name, mod)

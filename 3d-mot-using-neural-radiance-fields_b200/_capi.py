@@ -34,6 +34,11 @@ class StarMultiOut(C.Structure):
         "depth_dynamic", "dynamic_transmittance", "rgb_dynamic_all", "regs")]
 
 
+class StarAdamSeg(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("n", C.c_int64), ("step_size", C.c_float), ("bc2_sqrt", C.c_float)]
+
+
 _SIGS = {
     "star_abi_version": (C.c_int, []),
     "star_error_string": (C.c_char_p, [C.c_int]),
@@ -86,6 +91,20 @@ _SIGS = {
                                                    C.POINTER(StarMipMultiOut), c_f, c_f]),
     "star_mip_composite_multi_backward": (C.c_int, [c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_int,
                                                     c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f]),
+    # losses and the optimiser step
+    "star_train_ws_bytes": (C.c_size_t, []),
+    "star_photometric_loss": (C.c_int, [c_f, c_f, c_f, c_i64, c_f, c_f, c_f, c_f, c_f]),
+    "star_depth_loss_forward": (C.c_int, [c_f, c_f, c_i64, C.c_float, C.c_float, c_f, c_f, c_f]),
+    "star_depth_loss_backward": (C.c_int, [c_f, c_f, c_i64, C.c_float, C.c_float, c_f, c_f, c_f, c_f]),
+    "star_sigma_loss_forward": (C.c_int, [c_f, c_f, c_f, c_f, c_i64, C.c_int, C.c_float, C.c_float, C.c_float, c_f, c_f,
+                                          c_f, c_f]),
+    "star_sigma_loss_backward": (C.c_int, [c_f, c_f, c_f, c_f, c_i64, C.c_int, C.c_float, C.c_float, C.c_float, c_f,
+                                           c_f, C.c_int, c_f, c_f]),
+    "star_grad_sqnorm": (C.c_int, [C.POINTER(StarAdamSeg), C.c_int, c_f, c_f]),
+    "star_grad_sqnorm_result": (C.c_void_p, [c_f]),
+    "star_grad_scale": (C.c_int, [C.POINTER(StarAdamSeg), C.c_int, c_f, C.c_float, c_f]),
+    "star_adam_step": (C.c_int, [C.POINTER(StarAdamSeg), C.c_int, C.c_double, C.c_double, C.c_double, c_f, C.c_float,
+                                 C.c_int, c_f]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -285,6 +285,21 @@ def hierarchical(z_vals, weights, N_importance, det, rays_o, rays_d, u=None, wan
 
 
 # ------------------------------------------------------------------------------------------ a4 + K2
+def flat_master(params):
+    """Flat fp32 master vector of a net: a zero-copy view when its parameters already sit back to back in one storage
+    in master order (optim.flatten_parameters re-homes them that way), else a concatenated copy."""
+    p0 = params[0]
+    addr = p0.data_ptr()
+    for p in params:
+        if p.data_ptr() != addr or not p.is_contiguous() or p.dtype != torch.float32:
+            return torch.cat([q.detach().reshape(-1).float() for q in params])
+        addr += 4 * p.numel()
+    total = (addr - p0.data_ptr()) // 4
+    if (p0.storage_offset() + total) * 4 > p0.untyped_storage().nbytes():
+        return torch.cat([q.detach().reshape(-1) for q in params])
+    return torch.as_strided(p0.detach(), (total,), (1,))
+
+
 class NetRuntime:
     """Kernel-side state of one NeRF MLP: the flat fp32 master vector (order of include/star_b200.h)
     and the packed weight image, rebuilt when any parameter's version / storage changes."""
@@ -314,7 +329,7 @@ class NetRuntime:
         params = self.ordered_params()
         key = tuple((p.data_ptr(), p._version) for p in params)
         if key != self._key:
-            self._flat = torch.cat([p.detach().reshape(-1) for p in params])
+            self._flat = flat_master(params)
             self._packed = {}
             self._key = key
         if precision not in self._packed:

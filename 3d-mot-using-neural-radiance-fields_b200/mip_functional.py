@@ -10,7 +10,8 @@ from torch.autograd import Function
 
 from . import _capi
 from ._capi import check, f32, ptr, stream
-from .functional import _c, _count, _prof_begin, _prof_end, _ray_chunks, STASH_BUDGET_BYTES, MIP_MAC_PER_SAMPLE
+from .functional import (_c, _count, _prof_begin, _prof_end, _ray_chunks, STASH_BUDGET_BYTES, MIP_MAC_PER_SAMPLE,
+                         flat_master as _flat_master)
 
 N_FREQ_XYZ, MAX_EXP_XYZ = 24, 24.0     # models/mipnerf.py:58-64
 N_FREQ_DIR, MAX_EXP_DIR = 4, 4.0       # models/mipnerf.py:65-71
@@ -112,7 +113,7 @@ class MipRuntime:
         params = self.ordered_params()
         key = tuple((p.data_ptr(), p._version) for p in params)
         if key != self._key:
-            self._flat = torch.cat([p.detach().reshape(-1) for p in params])
+            self._flat = _flat_master(params)
             self._packed = {}
             self._key = key
         if precision not in self._packed:

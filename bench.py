@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--train-rays", type=int, default=TRAIN_RAYS)
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt-step", action="store_true",
+                    help="train mode: include gradient clipping + the fused Adam step (and the weight re-pack) in the step")
     ap.add_argument("--no-train-extra", action="store_true",
                     help="render mode: skip the extra 4096-ray training-step measurement reported under \"train\"")
     return ap.parse_args()
@@ -229,7 +231,7 @@ def build_workload(args, dev, rank, world):
     """Returns (net, ro_h, rd_h, step_device, params, d2h) for args.workload / args.mode.
     step_device(ro, rd) runs one pass from device-resident rays; d2h(out) reads the step's result back to the host."""
     import star_b200
-    from star_b200.models import rendering__ as R_
+    from star_b200.models import rendering__ as R_, loss as L_
     from oracle import ref_harness, star_oracle as so  # argument / synthetic-input builders only; no compute
     train = args.mode == "train"
     wk = args.workload
@@ -257,7 +259,7 @@ def build_workload(args, dev, rank, world):
                     p.grad = None
                 pts, z = R_.sample_pts(ro, rd, NEAR, FAR, NC, perturb=0, is_train=True)
                 out = R_.render_star_appinit(net, pts, vd, z, ro, rd, NI, u=u)
-                loss = ((out["rgb"] - target) ** 2).mean() + ((out["rgb0"] - target) ** 2).mean()
+                loss = L_.photometric_loss(out["rgb0"], out["rgb"], target)[0]      # train_online__.py:158-166, fused
                 loss.backward()
                 if world > 1:
                     star_b200.parallel.allreduce_gradients(params)     # one NCCL all-reduce of the flat gradient
@@ -291,7 +293,7 @@ def build_workload(args, dev, rank, world):
                     p.grad = None
                 pts, z = R_.sample_pts(ro, rd, 0.03, 0.8, Nc, perturb=0, is_train=True)
                 out = R_.render_star_online(net, pts, vd, z, ro, rd, Ni, pose, u=u)
-                loss = ((out["rgb"] - target) ** 2).mean() + ((out["rgb0"] - target) ** 2).mean()
+                loss = L_.photometric_loss(out["rgb0"], out["rgb"], target)[0]
                 for sfx in ("", "0"):        # configs/carla_star_online_multi.txt:72-74
                     loss = loss + 0.5 * (1e-3 * out["loss_alpha_entropy" + sfx] + 1e-3 * out["loss_dynamic_vs_static_reg" + sfx]
                                          + 1e-5 * out["loss_ray_reg" + sfx])
@@ -326,7 +328,8 @@ def build_workload(args, dev, rank, world):
             for p in params:
                 p.grad = None
             out = net(ro, vd, None, t_rand=t_rand, u_rand=u_rand)
-            loss = ((out["rgb"] - target) ** 2).mean() + 0.1 * ((out["rgb0"] - target) ** 2).mean()   # train_app_init_mip.py:60
+            _l, mse0, mse, _p0, _p1 = L_.photometric_loss(out["rgb0"], out["rgb"], target)
+            loss = mse + 0.1 * mse0   # train_app_init_mip.py:60
             loss.backward()
             if world > 1:
                 star_b200.parallel.allreduce_gradients(params)
@@ -360,6 +363,12 @@ def run_b200(args):
         if rank == 0:
             line["train"] = {k: t[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline", "gpu_launches")}
             line["train"]["config"] = t["config"]["workload"]
+        a2.opt_step = True
+        t = measure(a2)
+        if rank == 0:
+            line["train"]["with_optimizer"] = {
+                "metric": "rays/sec (train fwd+bwd + clip + Adam + weight re-pack)", "value": t["value"], "unit": "rays/s",
+                "ms_per_step": t["ms_per_step"], "gpu_launches": t["gpu_launches"]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -381,6 +390,18 @@ def measure(args):
 
     train = args.mode == "train"
     net, ro_h, rd_h, step_device, params = build_workload(args, dev, rank, world)
+    if train and args.opt_step:
+        # the whole optimisation step of the reference: + clip_grad_norm_(1.0) + Adam, fused, over
+        # parameters re-homed into one flat buffer; the packed 16-bit weight images are rebuilt every step
+        from star_b200 import optim as O_
+        O_.flatten_parameters(net)
+        opt = O_.FusedAdam(params, lr=5e-4, betas=(0.9, 0.999), max_grad_norm=1.0)
+        fwd_bwd = step_device
+
+        def step_device(ro, rd):
+            loss = fwd_bwd(ro, rd)
+            opt.step()
+            return loss
     R = ro_h.shape[0]
     ro_h, rd_h = ro_h.pin_memory(), rd_h.pin_memory()
     ro, rd = ro_h.to(dev), rd_h.to(dev)

@@ -272,6 +272,61 @@ int star_mip_composite_multi_backward(const float* raw_sigma_s, const float* raw
                                       const float* g_regs, float* d_raw_sigma_s, float* d_raw_rgb_s,
                                       float* d_raw_sigma_d, float* d_raw_rgb_d, void* stream);
 
+/* ==== SURVEY.md 8(f) rows 2-3: loss and optimiser step either side of the render path =========
+ * All reductions accumulate in fp64 and are deterministic (per-block partials added in block order).
+ * `ws` = caller workspace of star_train_ws_bytes() bytes, 16-byte aligned; a call may overwrite it. */
+size_t star_train_ws_bytes(void);
+
+/* train_online__.py:158-166 / train_app_init__.py: loss = MSELoss(rgb0, target) + MSELoss(rgb, target) and
+ * models/rendering__.py:22-23 mse2psnr.  n = number of elements (R*3).  out5 = [mse0, mse, psnr0, psnr, mse0 + mse];
+ * g_rgb0 / g_rgb (nullable) receive d(mse0 + mse)/d(rgb0 | rgb) = 2 (x - target) / n.  rgb0 may be NULL
+ * (N_importance == 0): mse0 = psnr0 = 0. */
+int star_photometric_loss(const float* rgb0, const float* rgb, const float* target, int64_t n, float* out5,
+                          float* g_rgb0, float* g_rgb, void* ws, void* stream);
+
+/* models/loss.py:4-10 compute_depth_loss.  out2 = [loss, number of rays with near < gt < far] (loss is NaN when no
+ * ray qualifies, like torch.mean of an empty tensor).  backward: g_depth[R] = g_out[0] * d loss / d depth. */
+int star_depth_loss_forward(const float* depth, const float* gt_depth, int64_t R, float near_, float far_, float* out2,
+                            void* ws, void* stream);
+int star_depth_loss_backward(const float* depth, const float* gt_depth, int64_t R, float near_, float far_,
+                             const float* out2, const float* g_out, float* g_depth, void* stream);
+
+/* models/loss.py:13-66 compute_sigma_loss (weights, z_vals, dists [R,S]; depths [R]); per_ray (nullable, [R]) receives
+ * the un-masked per-ray sums of compute_sigma_loss_per_ray (:70-87).  backward: gradient w.r.t. weights only (z_vals
+ * and dists carry no gradient on the render path: z_samples are detached, rendering__.py:135); g_out = the scalar
+ * upstream gradient, or with g_per_ray != 0 one upstream gradient per ray for the per-ray variant (mask ignored). */
+int star_sigma_loss_forward(const float* weights, const float* z_vals, const float* dists, const float* depths, int64_t R,
+                            int S, float near_, float far_, float err, float* out2, float* per_ray, void* ws,
+                            void* stream);
+int star_sigma_loss_backward(const float* weights, const float* z_vals, const float* dists, const float* depths,
+                             int64_t R, int S, float near_, float far_, float err, const float* out2, const float* g_out,
+                             int g_per_ray, float* g_weights, void* stream);
+
+/* One contiguous run of fp32 parameters with its gradient and Adam moments (all DEVICE pointers, 4-byte aligned; the
+ * 16-byte path is taken where the four share their alignment).  step_size = lr / (1 - beta1^t) and
+ * bc2_sqrt = sqrt(1 - beta2^t) are formed by the host in double, as torch.optim.Adam does. */
+typedef struct StarAdamSeg {
+  float* param;
+  float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+  float step_size;
+  float bc2_sqrt;
+} StarAdamSeg;
+
+/* `segs` is a HOST array.  star_grad_sqnorm leaves sum(grad^2) over all segments as a double at
+ * star_grad_sqnorm_result(ws) (a device address inside ws).  star_grad_scale = torch.nn.utils.clip_grad_norm_
+ * (Trainer(gradient_clip_val=1.0), train_online__.py:1170): grad *= min(1, max_norm / (sqrt(sqnorm) + 1e-6)).
+ * star_adam_step = torch.optim.Adam(betas, eps, amsgrad=False, weight_decay=0) (train_online__.py:333-353) on every
+ * segment, with the clip coefficient applied to the gradient on the fly when sqnorm != NULL (write_back_grads != 0
+ * also stores the clipped gradient, as the reference's in-place clip leaves it). */
+int star_grad_sqnorm(const StarAdamSeg* segs, int n_segs, void* ws, void* stream);
+const double* star_grad_sqnorm_result(const void* ws);
+int star_grad_scale(const StarAdamSeg* segs, int n_segs, const double* sqnorm, float max_norm, void* stream);
+int star_adam_step(const StarAdamSeg* segs, int n_segs, double beta1, double beta2, double eps, const double* sqnorm,
+                   float max_norm, int write_back_grads, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
