@@ -184,3 +184,64 @@ def test_c_abi_argument_checks_need_no_gpu():
     assert lib.star_error_string(2).decode().startswith("unsupported")
     d = _capi.net_desc(4, 10, 4, _capi.PREC_F32)
     assert lib.star_mlp_forward(C.byref(d), None, None, None, None, None, None, 4, 8, None, None, 8, None, None) == 3
+
+
+def test_train_step_abi_argument_checks_and_host_logic():
+    """status codes of the loss / optimiser entry points without a GPU, the run-merging and
+    parameter re-homing logic of optim.py (pure host code), and the no-fallback rule."""
+    import ctypes as C
+    from star_b200 import optim as O_
+    from star_b200.models import loss as L_
+    lib = _capi.lib()
+    assert lib.star_train_ws_bytes() >= 16
+    assert lib.star_photometric_loss(None, None, None, 12, None, None, None, None, None) == 3               # STAR_E_NULL
+    assert lib.star_photometric_loss(None, C.c_void_p(16), C.c_void_p(16), 0, C.c_void_p(16), None, None,
+                                     C.c_void_p(16), None) == 1                                             # STAR_E_BAD_SHAPE
+    assert lib.star_photometric_loss(None, C.c_void_p(16), C.c_void_p(16), 3, C.c_void_p(16), None, None,
+                                     C.c_void_p(8), None) == 4                                              # STAR_E_ALIGN
+    assert lib.star_depth_loss_forward(None, None, 4, 0.0, 1.0, None, None, None) == 3
+    assert lib.star_sigma_loss_forward(None, None, None, None, 4, 8, 0.0, 1.0, 1.0, None, None, None, None) == 3
+    assert lib.star_sigma_loss_backward(None, None, None, None, 4, 8, 0.0, 1.0, 1.0, None, None, 0, None, None) == 3
+    segs = (_capi.StarAdamSeg * 1)()
+    assert lib.star_adam_step(segs, 0, 0.9, 0.999, 1e-8, None, 0.0, 0, None) == 0          # nothing to do
+    assert lib.star_adam_step(segs, 1, 1.5, 0.999, 1e-8, None, 0.0, 0, None) == 1          # beta1 out of range
+    segs[0].n = 8
+    assert lib.star_adam_step(segs, 1, 0.9, 0.999, 1e-8, None, 0.0, 0, None) == 3          # NULL run pointers
+    segs[0].n = -1
+    assert lib.star_adam_step(segs, 1, 0.9, 0.999, 1e-8, None, 0.0, 0, None) == 1
+    assert lib.star_grad_scale(segs, 0, None, 1.0, None) == 3
+    assert lib.star_grad_sqnorm(segs, 0, None, None) == 3
+    # run merging: records whose every address continues the previous one's collapse into one run
+    recs = [((1000, 5000), 10, "a"), ((1040, 5040), 6, "a"), ((1064, 5064), 2, "b"), ((2000, 5072), 4, "b")]
+    assert O_._runs(recs) == [((1000, 5000), 16, "a"), ((1064, 5064), 2, "b"), ((2000, 5072), 4, "b")]
+    # flatten_parameters: values, shapes and state_dict keys survive; each net becomes one zero-copy master vector
+    net = star_b200.STaR(ref_harness.make_args(num_vehicles=1, N_importance=8))
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    flat = O_.flatten_parameters(net)
+    assert flat.numel() == sum(p.numel() for p in net.parameters())
+    after = net.state_dict()
+    assert list(after.keys()) == list(before.keys())
+    assert all(torch.equal(after[k], before[k]) for k in before)
+    for m in (net.static_coarse_nerf, net.static_fine_nerf, net.dynamic_coarse_nerfs[0], net.dynamic_fine_nerfs[0]):
+        ps = m._rt.ordered_params()
+        master = F_.flat_master(ps)
+        assert master.data_ptr() == ps[0].data_ptr() and master.numel() == sum(p.numel() for p in ps)
+        assert master.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr()
+    flat.mul_(2.0)                                      # the modules see writes to the flat buffer
+    assert torch.equal(net.static_coarse_nerf.rgb_linear.bias, 2.0 * before["static_coarse_nerf.rgb_linear.bias"])
+    # a net whose parameters are separate tensors still gets a (copied) master vector in the same order
+    other = star_b200.STaR(ref_harness.make_args(num_vehicles=0, N_importance=8))
+    ps = other.static_coarse_nerf._rt.ordered_params()
+    assert torch.equal(F_.flat_master(ps), torch.cat([p.detach().reshape(-1) for p in ps]))
+    # no CPU fallback anywhere on this side either
+    with pytest.raises(ValueError):
+        O_.FusedAdam(list(other.parameters()), weight_decay=1e-2)
+    opt = O_.FusedAdam(list(other.parameters()), lr=5e-4, max_grad_norm=1.0)
+    for p in other.parameters():
+        p.grad = torch.zeros_like(p)
+    with pytest.raises(_capi.StarError):
+        opt.step()
+    with pytest.raises(_capi.StarError):
+        L_.photometric_loss(torch.rand(4, 3), torch.rand(4, 3), torch.rand(4, 3))
+    with pytest.raises(ValueError):
+        L_.photometric_loss(torch.rand(4, 3), torch.rand(5, 3), torch.rand(4, 3))
