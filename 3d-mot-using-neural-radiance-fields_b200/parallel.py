@@ -33,14 +33,51 @@ def shard_rays(*tensors, rank=None, world_size=None):
     return out if len(out) > 1 else out[0]
 
 
+def _grad_runs(params, max_runs=32):
+    """Gradients that already sit back to back in memory (a net's flat gradient, parameters re-homed by
+    optim.flatten_parameters) as flat zero-copy views, one per run; None when a gradient is missing, not dense
+    contiguous fp32, or the gradients are scattered over more than `max_runs` pieces."""
+    gs = []
+    for p in params:
+        g = p.grad
+        if g is None or g.dtype != torch.float32 or g.is_sparse or not g.is_contiguous():
+            return None
+        gs.append(g)
+    # Runs are formed in LIST order and only inside one storage, so that every rank derives the same run structure
+    # (address order and accidental adjacency of separate allocations differ between processes).
+    runs = []          # [first tensor, element count, end address]
+    for g in gs:
+        if g.numel() == 0:
+            continue
+        if runs and g.data_ptr() == runs[-1][2] and \
+                g.untyped_storage().data_ptr() == runs[-1][0].untyped_storage().data_ptr():
+            runs[-1][1] += g.numel()
+            runs[-1][2] += 4 * g.numel()
+            continue
+        runs.append([g, g.numel(), g.data_ptr() + 4 * g.numel()])
+        if len(runs) > max_runs:
+            return None
+    return [torch.as_strided(first, (n,), (1,)) for first, n, _ in runs]
+
+
 def allreduce_gradients(params, average=True, group=None):
-    """One all-reduce(sum) over a flat fp32 buffer of every .grad (parameters without a gradient contribute
-    zeros, so all ranks agree on the layout), scattered back in place.  average=True divides by the world
-    size: with equal ray shards the mean of per-rank mean losses is the global mean loss."""
+    """All-reduce(sum) of every .grad across ranks, in place.  Gradients that form a few contiguous runs are reduced
+    where they lie (one collective per run, no staging copy); otherwise one all-reduce over a concatenated fp32
+    buffer (parameters without a gradient contribute zeros, so all ranks agree on the layout), scattered back.
+    average=True divides by the world size: with equal ray shards the mean of per-rank mean losses is the global
+    mean loss.  Every rank must hold the same parameter list with the same gradient layout."""
     params = [p for p in params if p.requires_grad]
     if not params:
         return None
     _, w = world()
+    runs = _grad_runs(params)
+    if runs is not None:
+        if w > 1:
+            for r in runs:
+                dist.all_reduce(r, op=dist.ReduceOp.SUM, group=group)
+                if average:
+                    r.div_(w)
+        return runs
     flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params])
     if w > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)

@@ -91,3 +91,48 @@ def test_uneven_gather():
     assert P.shard_bounds(7, 0, 2) == (0, 4) and P.shard_bounds(7, 1, 2) == (4, 7)
     t = torch.arange(12.0).view(4, 3)
     assert torch.equal(P.gather_rays(t, 4), t)   # world size 1: identity
+
+
+def _worker_flat(rank, world, port, q):
+    """Gradients lying back to back (a net's flat gradient): reduced in place, one collective per run."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from star_b200 import optim as O_
+        torch.manual_seed(0)
+        holder = torch.nn.ParameterList([torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(5)),
+                                         torch.nn.Parameter(torch.randn(3, 5)), torch.nn.Parameter(torch.randn(3))])
+        O_.flatten_parameters(holder)
+        ps = list(holder)
+        n = sum(p.numel() for p in ps)
+        gbuf = torch.arange(n, dtype=torch.float32) * (rank + 1)          # rank 0: k, rank 1: 2k  -> mean 1.5 k
+        lone = torch.nn.Parameter(torch.zeros(2))
+        lone.grad = torch.full((2,), float(rank))
+        off = 0
+        for p in ps:
+            p.grad = gbuf[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        runs = P.allreduce_gradients(ps + [lone])
+        q.put((rank, len(runs), gbuf.clone(), lone.grad.clone(), ps[2].grad.clone()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_flat_gradient_runs_are_reduced_in_place():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_flat, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = 15 + 5 + 15 + 3
+    for rank, n_runs, gbuf, lone, g2 in res:
+        assert n_runs == 2                                               # the flat run + the lone parameter
+        assert torch.equal(gbuf, 1.5 * torch.arange(n, dtype=torch.float32))   # reduced where it lies
+        assert torch.equal(lone, torch.full((2,), 0.5))
+        assert torch.equal(g2, 1.5 * torch.arange(20, 35, dtype=torch.float32).view(3, 5))
