@@ -40,6 +40,7 @@ struct EpiCtx {
   const float* bias;           // smem, epilogue bias vector of this layer
   const float* head_w;         // smem, alpha_linear / rgb_linear weights (OUT / VIEWS layers)
   uint8_t* stash_out;          // global: first stash block of this layer's epilogue output for this tile, or NULL
+  uint8_t* mask_out;           // global: this layer's ReLU bit masks for this tile (training), or NULL
   uint32_t w_full0;            // smem address of barrier w_full[0]
   uint32_t next_stage0;        // ring stage of the NEXT layer's K-block 0 (its K-block kb uses (next_stage0 + kb) % 4)
   int row, cg, lane;
@@ -58,6 +59,7 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3]) {
   // cycles to return, which with one chunk of look-ahead made every chunk of the serial epilogue chain as long as
   // that latency.
   uint32_t r[NCH][TC_CPT];
+  uint32_t mlo = 0u, mhi = 0u;   // training: one bit per rectified output of this row (dX pass of the backward)
 #pragma unroll
   for (int kb = 0; kb < NCH && kb < TC_LD_DEPTH; ++kb) tmem_ld16(c.tcol + 64u * (uint32_t)kb, r[kb]);
 #pragma unroll
@@ -100,6 +102,13 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3]) {
     } else {
       // (training: the stash copy of this block is a bulk store issued by the producer warp once the block is complete)
       store_row16<FP16, RELU>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v);
+      if (STASH && RELU) {
+        uint32_t b = 0u;
+#pragma unroll
+        for (int j = 0; j < TC_CPT; ++j) b |= (v[j] > 0.f ? 1u : 0u) << j;
+        if (kb & 1) b <<= 16;
+        if (kb < 2) mlo |= b; else mhi |= b;
+      }
       fence_proxy_async_smem();      // this thread's A writes -> async proxy (tcgen05.mma operand reads)
       tc_fence_before();
       __syncwarp();
@@ -109,6 +118,8 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3]) {
       }
     }
   }
+  if (STASH && RELU)
+    *reinterpret_cast<uint2*>(c.mask_out + ((uint32_t)(c.cg * TC_M + c.row) << 3)) = make_uint2(mlo, mhi);
 }
 
 // ============================================================================================ forward
@@ -275,6 +286,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     ctx.sA = sA; ctx.a_ready0 = bar(BAR_A_READY(0)); ctx.w_full0 = bar(BAR_W_FULL(0));
     ctx.row = row; ctx.cg = cg; ctx.lane = lane;
     ctx.stash_out = nullptr;
+    ctx.mask_out = nullptr;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t gi = tile * TC_M + row;
       const bool valid = gi < M;
@@ -335,7 +347,11 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         const int kind = L.kind;
         ctx.tcol = tmem_base + (((uint32_t)(q * 32)) << 16) + (L.region ? 256u : 0u) + (uint32_t)(cg * TC_CPT);
         ctx.bias = s_small + L.bias_off;
-        if (STASH) ctx.stash_out = stash + ((size_t)tile * (size_t)lay.stash_blocks + (size_t)L.s_out) * TC_BLOCK_BYTES;
+        if (STASH) {
+          ctx.stash_out = stash + ((size_t)tile * (size_t)lay.stash_blocks + (size_t)L.s_out) * TC_BLOCK_BYTES;
+          ctx.mask_out = stash + ((size_t)tile * (size_t)lay.stash_blocks + (size_t)lay.mask_blk0) * TC_BLOCK_BYTES +
+                         (size_t)l * TC_MASK_BYTES;
+        }
         float h[3] = {0.f, 0.f, 0.f};
         TL_STAMP(tile == tl_tile && tid == 0, 80 + 8 * l);
         kstage = (kstage + (uint32_t)L.nkb) & (TC_NS - 1);     // now the stage of the NEXT layer's K-block 0

@@ -30,6 +30,7 @@ struct BwdStage {    // one weight K-block = one ring stage = one group of MMAs
 struct BwdPhase {
   int kind, nch;       // epilogue kind, number of 64-column chunks it produces (A K-blocks)
   int mask_blk, g_blk; // stash block of the mask source / gradient-stash block of the output (-1: none)
+  int mask_layer;      // >= 0: the mask comes from the bit masks of this forward layer (TC_MASK_BYTES each) instead
   int n_wait;          // A K-blocks the following MMA group must wait for (= nch)
 };
 #define BWD_MAX_STAGES 64
@@ -144,9 +145,9 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
       BwdStage& s = stages[ns++];
       s.w_off = w_off; s.bytes = bytes; s.a_kb = a_kb; s.N = N; s.tcol = tcol; s.accum = accum; s.nk = nk; s.last = last;
     };
-    auto phase = [&](int kind, int nch, int mask_blk, int g_blk) {
+    auto phase = [&](int kind, int nch, int mask_blk, int g_blk, int mask_layer = -1) {
       BwdPhase& p = phases[np++];
-      p.kind = kind; p.nch = nch; p.mask_blk = mask_blk; p.g_blk = g_blk; p.n_wait = nch;
+      p.kind = kind; p.nch = nch; p.mask_blk = mask_blk; p.g_blk = g_blk; p.n_wait = nch; p.mask_layer = mask_layer;
     };
     // full layer: N = 256 input features, K = n_out / 64 blocks of the transposed stream
     auto gemm = [&](int l, int tcol) {
@@ -165,13 +166,14 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     gemm(F, 0);
     phase(BK_OUT, 4, -1, lay.L[O].g_out);
     gemm(O, 256);
-    phase(BK_X0, 4, lay.L[O].s_in, lay.L[O - 1].g_out);       // mask relu(x_B) > 0; G of the last fc_1 (or lin_in)
+    // the rectified operand of layer x was written by the epilogue of layer x - 1: its bit masks are slot x - 1
+    phase(BK_X0, 4, -1, lay.L[O - 1].g_out, O - 1);           // mask relu(x_B) > 0; G of the last fc_1 (or lin_in)
     for (int b = lay.n_blocks - 1; b >= 0; --b) {
       const int l0 = 1 + 2 * b, l1 = 2 + 2 * b;
       gemm(l1, 256);
-      phase(BK_FC1, 4, lay.L[l1].s_in, lay.L[l0].g_out);      // mask relu(net_b) > 0
+      phase(BK_FC1, 4, -1, lay.L[l0].g_out, l1 - 1);          // mask relu(net_b) > 0
       gemm(l0, 256);
-      phase(BK_FC0, 4, lay.L[l0].s_in, lay.L[l0 - 1].g_out);  // mask relu(x_b) > 0; G of fc_1(b-1) or lin_in
+      phase(BK_FC0, 4, -1, lay.L[l0 - 1].g_out, l0 - 1);      // mask relu(x_b) > 0; G of fc_1(b-1) or lin_in
     }
     if (has_pose) {   // d enc_xyz = G_in * W_in: N = 64 input features, K = 256
       for (int kb = 0; kb < 4; ++kb)
@@ -316,11 +318,14 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
 
       for (int pi = 0; pi < n_phases; ++pi) {
         const BwdPhase P = phases[pi];
-        // mask sources of the whole phase (16 stashed 16-bit activations per chunk; > 0 <=> bits != 0 for a ReLU output)
-        // are fetched BEFORE waiting for the accumulator: the global-memory latency hides behind the MMAs
-        uint4 mq[4][2];
+        // mask sources of the whole phase are fetched BEFORE waiting for the accumulator (the global-memory latency
+        // hides behind the MMAs): the hidden layers' ReLU masks are one 64-bit word per thread (bit 16 kb + j), written
+        // by the forward epilogue; relu(h2) of the view layer is tested on its stashed 16-bit activations
+        // (> 0 <=> bits != 0 for a ReLU output)
+        uint4 mq[2][2];
+        uint2 mbits = make_uint2(~0u, ~0u);
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
+        for (int kb = 0; kb < 2; ++kb) {
           mq[kb][0] = make_uint4(~0u, ~0u, ~0u, ~0u);
           mq[kb][1] = mq[kb][0];
           if (P.mask_blk >= 0 && kb < P.nch) {
@@ -329,6 +334,9 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             mq[kb][1] = __ldg(reinterpret_cast<const uint4*>(mb + (uint32_t)row * 128u + ((((uint32_t)(cg * 2 + 1)) ^ x_sw) << 4)));
           }
         }
+        if (P.mask_layer >= 0)
+          mbits = __ldg(reinterpret_cast<const uint2*>(st_tile + (size_t)lay.mask_blk0 * TC_BLOCK_BYTES +
+                                                       (size_t)P.mask_layer * TC_MASK_BYTES) + (cg * TC_M + row));
         if (P.kind != BK_PRE) {
           mbar_wait(bar(BAR_ACC_FULL), acc_par, dbg, 4);
           acc_par ^= 1u;
@@ -384,8 +392,9 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         for (int kb = 0; kb < 4; ++kb) {
           if (kb >= P.nch) break;
           const int col0 = kb * 64 + cg * TC_CPT;
-          const uint4 m0 = mq[kb][0], m1 = mq[kb][1];
+          const uint4 m0 = mq[kb & 1][0], m1 = mq[kb & 1][1];      // (only the 2-chunk view phase has mask_blk >= 0)
           const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          const uint32_t mb16 = ((kb < 2 ? mbits.x : mbits.y) >> ((kb & 1) * 16)) & 0xffffu;
           float v[16];
           if (P.kind == BK_PRE) {
             const float* rw = s_small + lay.off_rgb_w + col0;
@@ -409,6 +418,11 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
               const uint32_t bits = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xffffu);
               if (bits == 0u) v[j] = 0.f;
             }
+          }
+          if (P.mask_layer >= 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (!((mb16 >> j) & 1u)) v[j] = 0.f;
           }
           if (P.kind == BK_FC0) {      // dx += masked product
             uint32_t rx[16];

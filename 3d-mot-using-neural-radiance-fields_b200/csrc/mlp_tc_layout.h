@@ -40,6 +40,7 @@ struct TcLayout {
   // training: blocks per 128-sample tile of the activation stash and of the gradient stash, and the size of
   // the backward (transposed) weight stream that follows the forward one in the packed image
   int stash_blocks, gstash_blocks;
+  int mask_blk0;            // first block of the tile's ReLU bit masks (TC_MASK_BYTES per layer, see below)
   uint32_t wt_dirs_off;     // transposed view-layer rows of the encoded dirs (objects only): 2 K-blocks x [64 rows][128 B]
   uint32_t tstream_bytes;
 };
@@ -49,6 +50,11 @@ struct TcLayout {
 // 16-byte chunk c at position c ^ (r & 7)).  A block is therefore at once a K-major operand (K = features)
 // for the forward / dX GEMMs and an MN-major operand (K = samples) for the dW GEMMs, and moves with one bulk copy.
 #define TC_BLOCK_BYTES 16384
+// ReLU masks for the dX pass: for every layer l whose epilogue output is rectified (lin_in, fc_0, fc_1) the forward also
+// leaves one bit per output feature, [4 column groups][128 rows] 64-bit words (bit 16 kb + j of word (cg, row) =
+// feature 64 kb + 16 cg + j is positive), at byte l * TC_MASK_BYTES of the tile's mask blocks: the dX pass then reads
+// 4 KB instead of 64 KB of 16-bit activations per layer and tile.
+#define TC_MASK_BYTES 4096
 
 static inline int star_make_tc_layout(const StarNetDesc* d, TcLayout* o) {
   if (d->n_blocks < 1 || 2 * d->n_blocks + 4 > STAR_MAX_LAYERS) return STAR_E_UNSUPPORTED;
@@ -79,6 +85,8 @@ static inline int star_make_tc_layout(const StarNetDesc* d, TcLayout* o) {
   o->n_layers = n;
   for (int i = 0; i + 1 < n; ++i) o->L[i].s_out = o->L[i + 1].s_in;   // epilogue output = next layer's input
   o->L[n - 1].s_out = sb; sb += 2;                                     // relu(h2), 128 columns
+  o->mask_blk0 = sb;
+  sb += (n * TC_MASK_BYTES + TC_BLOCK_BYTES - 1) / TC_BLOCK_BYTES;
   o->stash_blocks = sb;
   o->gstash_blocks = gb;
   o->wt_dirs_off = wto; wto += 2u * 64u * 128u;

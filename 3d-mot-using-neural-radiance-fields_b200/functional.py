@@ -346,6 +346,20 @@ class NetRuntime:
         return self._flat, self._packed[precision]
 
 
+STASH_RESERVE_BYTES = 6 << 30      # head room kept free for the backward's workspaces and the caller's tensors
+
+
+def stash_fits(nbytes, device):
+    """Keep the activations of a forward for its backward?  Yes when they fit the per-call budget AND the memory that
+    is actually free right now (driver-free + blocks cached by the allocator); otherwise the backward re-runs the
+    forward chunk by chunk."""
+    if nbytes > STASH_BUDGET_BYTES:
+        return False
+    free, _total = torch.cuda.mem_get_info(device)
+    cached = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    return nbytes + STASH_RESERVE_BYTES <= free + cached
+
+
 def _ray_chunks(R, S):
     per = max(1, MAX_SAMPLES_PER_LAUNCH // S)
     return [(a, min(R, a + per)) for a in range(0, R, per)]
@@ -374,7 +388,7 @@ class NerfRaw(Function):
         stashes = []
         # activations needed by the backward are stashed by the forward of the same tier (fp32: per-GEMM inputs in
         # fp32; tensor-core tiers: 16-bit swizzled blocks); over budget, the backward re-runs the forward per chunk
-        keep = need_grad and L.star_stash_bytes(C.byref(d), R * S) <= STASH_BUDGET_BYTES
+        keep = need_grad and stash_fits(L.star_stash_bytes(C.byref(d), R * S), dev)
         for (a, b) in chunks:
             st = None
             if keep:

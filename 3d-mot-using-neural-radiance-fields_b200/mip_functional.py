@@ -10,7 +10,7 @@ from torch.autograd import Function
 
 from . import _capi
 from ._capi import check, f32, ptr, stream
-from .functional import (_c, _count, _prof_begin, _prof_end, _ray_chunks, STASH_BUDGET_BYTES, MIP_MAC_PER_SAMPLE,
+from .functional import (_c, _count, _prof_begin, _prof_end, _ray_chunks, stash_fits, MIP_MAC_PER_SAMPLE,
                          flat_master as _flat_master)
 
 N_FREQ_XYZ, MAX_EXP_XYZ = 24, 24.0     # models/mipnerf.py:58-64
@@ -150,7 +150,7 @@ class MipFieldRaw(Function):
         raw_rgb = torch.empty((R, S, 3), device=dev)
         p12 = _c(pose12.detach()) if pose12 is not None else None
         chunks = _ray_chunks(R, S)
-        keep = need_grad and L.star_mip_stash_bytes(precision, R * S) <= STASH_BUDGET_BYTES
+        keep = need_grad and stash_fits(L.star_mip_stash_bytes(precision, R * S), dev)
         stashes = []
         for (a, b) in chunks:
             st = None
