@@ -4,6 +4,7 @@ all arithmetic happens in the CUDA kernels.  Reference citations are into /root/
 """
 import ctypes as C
 import os
+import weakref
 
 import torch
 from torch.autograd import Function
@@ -346,18 +347,40 @@ class NetRuntime:
         return self._flat, self._packed[precision]
 
 
-STASH_RESERVE_BYTES = 6 << 30      # head room kept free for the backward's workspaces and the caller's tensors
+STASH_RESERVE_BYTES = int(float(os.environ.get("STAR_B200_STASH_RESERVE_GB", "14")) * (1 << 30))
+_STASH_LIVE = {}       # device index -> bytes of activation stashes currently alive
+_DEVICE_BYTES = {}     # device index -> total memory (queried once; cudaMemGetInfo costs ~2 ms per call)
+
+
+def _dev_index(device):
+    return device.index if device.index is not None else torch.cuda.current_device()
+
+
+def _stash_release(idx, nbytes):
+    _STASH_LIVE[idx] -= nbytes
 
 
 def stash_fits(nbytes, device):
-    """Keep the activations of a forward for its backward?  Yes when they fit the per-call budget AND the memory that
-    is actually free right now (driver-free + blocks cached by the allocator); otherwise the backward re-runs the
-    forward chunk by chunk."""
+    """Keep the activations of a forward for its backward?  Yes when they fit the per-call budget AND, together with
+    the stashes that are still alive (earlier nets of the same step), leave STASH_RESERVE_BYTES of the device free
+    for everything else; otherwise the backward re-runs the forward chunk by chunk.  Pure host bookkeeping."""
     if nbytes > STASH_BUDGET_BYTES:
         return False
-    free, _total = torch.cuda.mem_get_info(device)
-    cached = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
-    return nbytes + STASH_RESERVE_BYTES <= free + cached
+    idx = _dev_index(device)
+    total = _DEVICE_BYTES.get(idx)
+    if total is None:
+        total = _DEVICE_BYTES[idx] = torch.cuda.get_device_properties(idx).total_memory
+    return _STASH_LIVE.get(idx, 0) + nbytes + STASH_RESERVE_BYTES <= total
+
+
+def stash_alloc(nbytes, device):
+    """A stash buffer whose bytes count as alive until the tensor is garbage-collected (the backward drops it as soon
+    as the chunk is done; a graph that is never back-propagated drops it with the graph)."""
+    t = torch.empty((nbytes,), device=device, dtype=torch.uint8)
+    idx = _dev_index(device)
+    _STASH_LIVE[idx] = _STASH_LIVE.get(idx, 0) + nbytes
+    weakref.finalize(t, _stash_release, idx, nbytes)
+    return t
 
 
 def _ray_chunks(R, S):
@@ -392,7 +415,7 @@ class NerfRaw(Function):
         for (a, b) in chunks:
             st = None
             if keep:
-                st = torch.empty((L.star_stash_bytes(C.byref(d), (b - a) * S),), device=dev, dtype=torch.uint8)
+                st = stash_alloc(L.star_stash_bytes(C.byref(d), (b - a) * S), dev)
                 stashes.append(st)
             e0 = _prof_begin()
             check(L.star_mlp_forward(C.byref(d), ptr(packed), f32(pts[a:b]), f32(viewdirs[a:b]),

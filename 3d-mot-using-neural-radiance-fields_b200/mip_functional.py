@@ -10,7 +10,7 @@ from torch.autograd import Function
 
 from . import _capi
 from ._capi import check, f32, ptr, stream
-from .functional import (_c, _count, _prof_begin, _prof_end, _ray_chunks, stash_fits, MIP_MAC_PER_SAMPLE,
+from .functional import (_c, _count, _prof_begin, _prof_end, _ray_chunks, stash_alloc, stash_fits, MIP_MAC_PER_SAMPLE,
                          flat_master as _flat_master)
 
 N_FREQ_XYZ, MAX_EXP_XYZ = 24, 24.0     # models/mipnerf.py:58-64
@@ -155,7 +155,7 @@ class MipFieldRaw(Function):
         for (a, b) in chunks:
             st = None
             if keep:
-                st = torch.empty((L.star_mip_stash_bytes(precision, (b - a) * S),), device=dev, dtype=torch.uint8)
+                st = stash_alloc(L.star_mip_stash_bytes(precision, (b - a) * S), dev)
                 stashes.append(st)
             e0 = _prof_begin()
             check(L.star_mip_field_forward(precision, ptr(packed), f32(origins[a:b]), f32(dirs[a:b]),
