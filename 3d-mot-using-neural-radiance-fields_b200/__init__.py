@@ -12,7 +12,7 @@ scripts pick them up unmodified.  `star_b200.optim` holds the f
 import sys
 
 from . import _capi, functional, parallel  # noqa: F401
-from . import mip_functional, optim  # noqa: F401
+from . import metrics, mip_functional, optim  # noqa: F401
 from .models import loss  # noqa: F401
 from .models import embedder, mipnerf, nerf, rendering__, rendering_starmip, resnet, star__, star_mipnerf, types__  # noqa: F401
 from .models.star__ import STaR  # noqa: F401

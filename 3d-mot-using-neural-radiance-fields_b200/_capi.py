@@ -103,6 +103,7 @@ _SIGS = {
     "star_grad_sqnorm": (C.c_int, [C.POINTER(StarAdamSeg), C.c_int, c_f, c_f]),
     "star_grad_sqnorm_result": (C.c_void_p, [c_f]),
     "star_grad_scale": (C.c_int, [C.POINTER(StarAdamSeg), C.c_int, c_f, C.c_float, c_f]),
+    "star_iou2d": (C.c_int, [c_f, c_f, c_i64, C.c_int, C.c_float, c_f, c_f, c_f]),
     "star_adam_step": (C.c_int, [C.POINTER(StarAdamSeg), C.c_int, C.c_double, C.c_double, C.c_double, c_f, C.c_float,
                                  C.c_int, c_f]),
 }

@@ -327,6 +327,13 @@ int star_grad_scale(const StarAdamSeg* segs, int n_segs, const double* sqnorm, f
 int star_adam_step(const StarAdamSeg* segs, int n_segs, double beta1, double beta2, double eps, const double* sqnorm,
                    float max_norm, int write_back_grads, void* stream);
 
+/* ==== SURVEY.md 8(f) row 4, device side: utils/metrics.py:527-550 compute_2d_iou ================
+ * dyn_t [R, V] = dynamic_transmittance of render_star_online; sem [R] bytes (non-zero = vehicle pixel of the semantic
+ * mask).  pred (nullable) [V, R] bytes <- (dyn_t[:, v] < thres); counts[2] (int64) <- {|sem AND any_v pred|,
+ * |sem OR any_v pred|}; the host forms iou = counts[0] / counts[1] (0 when the union is empty).  Bit-exact. */
+int star_iou2d(const float* dyn_t, const uint8_t* sem, int64_t R, int V, float thres, uint8_t* pred, int64_t* counts,
+               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,8 @@ rows 2-3), each function citing the reference lines it follows (paths relative t
   clip_and_adam         train_online__.py:333-353 (torch.optim.Adam, betas (0.9, 0.999)) and the Trainer's
                         gradient_clip_val=1.0 (:1170, i.e. torch.nn.utils.clip_grad_norm_)
 
+  compute_2d_iou        utils/metrics.py:527-550
+
 PINNED: tools/make_golden_train.py runs the unmodified reference `models/loss.py` and `models/rendering__.py`
 (imported from /root/reference) and the installed torch.optim.Adam / clip_grad_norm_ -- the very code the reference
 calls -- on seeded inputs and commits tests/golden/train_*.npz; tests/test_train_oracle.py checks this file against
@@ -85,3 +87,18 @@ def adam_restated(p, grads, lr, betas=(0.9, 0.999), eps=1e-8, clip_coefs=None):
         denom = v.sqrt() / math.sqrt(1 - b2 ** t) + eps
         p = p - (lr / (1 - b1 ** t)) * (m / denom)
     return p, m, v
+
+
+def compute_2d_iou(dynamic_transmittance, semantic_mask, thres=0.1):
+    """utils/metrics.py:527-550 (numpy loops over the objects, as there)."""
+    import numpy as np
+    num_rays, num_vehicles = dynamic_transmittance.shape
+    sem = semantic_mask.detach().cpu().numpy().astype(bool)
+    union_pred = np.zeros((num_rays,), dtype=bool)
+    masks = np.zeros((num_vehicles, num_rays), dtype=bool)
+    for i in range(num_vehicles):
+        masks[i] = (dynamic_transmittance[:, i] < thres).cpu().numpy()
+        union_pred = np.logical_or(union_pred, masks[i])
+    union = np.count_nonzero(np.logical_or(sem, union_pred))
+    inter = np.count_nonzero(np.logical_and(sem, union_pred))
+    return (0 if union == 0 else inter / union), masks

@@ -209,3 +209,32 @@ def test_tc_backward_matches_rounding_model_and_fp64(R, S, dyn, with_pose, prec)
     if with_pose:
         assert rel(pose_g.grad, posem.grad) < 2 * tol_model, ("pose", rel(pose_g.grad, posem.grad))
         assert rel(pose_g.grad, pose64.grad) < tol_exact, ("pose", rel(pose_g.grad, pose64.grad))
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_recompute_path_matches_stash_path_and_stash_accounting(prec, monkeypatch):
+    """Over the stash budget the backward re-runs the forward chunk by chunk: same kernels, same gradients (the dW
+    reduction uses atomics, so equality is to rounding, not bitwise).  The host-side accounting of live stash bytes
+    returns to zero once the graph is gone."""
+    import gc
+    g = load_golden("e2e_online_quat_train")
+    grads = {}
+    for mode in ("stash", "recompute"):
+        monkeypatch.setattr(F_, "STASH_BUDGET_BYTES", (24 << 30) if mode == "stash" else 0)
+        net, _ = make_star(2, 24, int(g["chunk"]), False, int(g["seed"]), training=True, precision=prec)
+        ro, rd, target = cu(g["rays_o"]), cu(g["rays_d"]), cu(g["target"])
+        vd = rd / rd.norm(dim=-1, keepdim=True)
+        pose = cu(g["pose"]).clone().requires_grad_(True)
+        pts, z = R_.sample_pts(ro, rd, g["near"], g["far"], int(g["Nc"]))
+        out = R_.render_star_online(net, pts, vd, z, ro, rd, int(g["Ni"]), pose, u=cu(g["u"]),
+                                    z_samples=cu(g["z_samples"]))
+        live = F_._STASH_LIVE.get(torch.cuda.current_device(), 0)
+        assert (live > 0) == (mode == "stash")
+        loss = ((out["rgb0"] - target) ** 2).mean() + ((out["rgb"] - target) ** 2).mean()
+        loss.backward()
+        grads[mode] = [pose.grad.clone()] + [p.grad.clone() for p in net.parameters()]
+        del out, loss
+        gc.collect()
+        assert F_._STASH_LIVE.get(torch.cuda.current_device(), 0) == 0
+    for a, b in zip(grads["stash"], grads["recompute"]):
+        assert float((a - b).norm()) <= 1e-4 * float(b.norm()) + 1e-9

@@ -298,3 +298,32 @@ def test_fused_adam_at_c4_parameter_count_against_torch_cuda_adam():
         assert F_.LAUNCH_COUNTER["calls"] - n0 == 2
     assert_close(pb, pa, 2e-8, 2e-6)
     assert_close(ob.state[pb]["exp_avg_sq"], oa.state[pa]["exp_avg_sq"], 1e-16, 2e-6)
+
+
+# ------------------------------------------------------------------------------------------ evaluation (8f-4)
+@pytest.mark.parametrize("tag", ["a", "b", "empty"])
+def test_compute_2d_iou_matches_the_reference_fixture(tag):
+    """utils/metrics.py:527-550 on the device: bit-exact masks and counts (NaN and the threshold itself are not below)."""
+    from star_b200 import metrics as M_
+    g = load_golden("train_iou2d")
+    iou, masks = M_.compute_2d_iou(c(g[tag + ".T"]), c(g[tag + ".sem"]), 0.1)
+    assert iou == float(g[tag + ".iou"])
+    assert masks.dtype == bool and (torch.from_numpy(masks) == g[tag + ".masks"]).all()
+    # the semantic mask may live on the host (the reference's batches do): same result
+    iou2, _ = M_.compute_2d_iou(c(g[tag + ".T"]), g[tag + ".sem"], 0.1)
+    assert iou2 == iou
+
+
+def test_compute_2d_iou_full_view_against_the_oracle():
+    from star_b200 import metrics as M_
+    gen = torch.Generator().manual_seed(31)
+    R, V = 1280 * 720, 5
+    T = torch.rand(R, V, generator=gen) ** 4
+    sem = torch.rand(R, generator=gen) < 0.1
+    ref_iou, ref_masks = to.compute_2d_iou(T, sem, 0.1)
+    iou, masks = M_.compute_2d_iou(c(T), c(sem), 0.1)
+    assert iou == ref_iou and (masks == ref_masks).all()
+    with pytest.raises(ValueError):
+        M_.compute_2d_iou(c(T), c(sem)[:-1])
+    with pytest.raises(star_b200._capi.StarError):
+        M_.compute_2d_iou(T, sem)            # CPU tensors: no fallback

@@ -89,3 +89,13 @@ def test_adam_recurrence_restated():
             assert_close(v, g["clip.v%d" % k], 1e-14, 2e-6, "v%d" % k)
             k += 1
     assert math.isclose(coefs[3], 1.0)      # a step whose norm is below the threshold is not scaled
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "empty"])
+def test_compute_2d_iou(tag):
+    g = load_golden("train_iou2d")
+    iou, masks = to.compute_2d_iou(g[tag + ".T"], g[tag + ".sem"], 0.1)
+    assert iou == float(g[tag + ".iou"])
+    assert (torch.from_numpy(masks) == g[tag + ".masks"]).all()
+    if tag == "empty":
+        assert not masks.any()

@@ -26,6 +26,18 @@ def load_ref_loss():
     return mod
 
 
+def load_ref_function(relpath, name):
+    """One function of a reference module whose other imports are not installed (utils/metrics.py needs pytorch3d):
+    its source is cut out of the file by the parser and executed unmodified."""
+    import ast
+    path = os.path.join(ref_harness.REFERENCE_ROOT, relpath)
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"np": np, "torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
 def save(name, **kw):
     arrs = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in kw.items()}
     path = os.path.join(OUT, name + ".npz")
@@ -81,6 +93,21 @@ def main():
         save("train_dsnerf_" + tag, near=near, far=far, weights=w, z_vals=z, dists=dists, depths=depths, depth=depth,
              depth_loss=dl, g_depth=depth.grad, sigma_loss=sl, g_weights=g_w, per_ray=pr, per_ray_coef=coef,
              g_weights_per_ray=w.grad, sigma_loss_err025=sl2)
+
+    # ---- 2-D IoU of the online-tracking evaluation (utils/metrics.py:527-550)
+    iou_fn = load_ref_function(os.path.join("utils", "metrics.py"), "compute_2d_iou")
+    out = {}
+    for tag, (R, V, p_vehicle) in (("a", (1000, 2, 0.2)), ("b", (4099, 5, 0.05)), ("empty", (300, 3, 0.0))):
+        T = torch.rand(R, V, generator=gen)
+        T[torch.rand(R, V, generator=gen) < (0.15 if tag != "empty" else 0.0)] *= 0.05       # some pixels covered by an object
+        if tag == "empty":
+            T = 0.5 + 0.5 * T
+        T[0, 0] = float("nan")
+        T[1, 0] = 0.1                                                                 # the threshold itself: not below
+        sem = torch.rand(R, generator=gen) < p_vehicle
+        iou, masks = iou_fn(T, sem, 0.1)
+        out.update({tag + ".T": T, tag + ".sem": sem, tag + ".iou": np.float64(iou), tag + ".masks": masks})
+    save("train_iou2d", **out)
 
     # ---- clip_grad_norm_ + Adam: 3 groups (static nets, dynamic nets, poses) with the reference's learning rates
     shapes = [[(64, 63), (64,), (3, 128), (3,)], [(96, 33), (1, 64), (1,)], [(5, 7)]]
