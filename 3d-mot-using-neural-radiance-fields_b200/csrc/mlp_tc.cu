@@ -41,6 +41,7 @@ struct EpiCtx {
   const float* head_w;         // smem, alpha_linear / rgb_linear weights (OUT / VIEWS layers)
   uint8_t* stash_out;          // global: first stash block of this layer's epilogue output for this tile, or NULL
   uint8_t* mask_out;           // global: this layer's ReLU bit masks for this tile (training), or NULL
+  bool no_mask;                // debug (timing experiments only)
   uint32_t w_full0;            // smem address of barrier w_full[0]
   uint32_t next_stage0;        // ring stage of the NEXT layer's K-block 0 (its K-block kb uses (next_stage0 + kb) % 4)
   int row, cg, lane;
@@ -102,7 +103,7 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3]) {
     } else {
       // (training: the stash copy of this block is a bulk store issued by the producer warp once the block is complete)
       store_row16<FP16, RELU>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v);
-      if (STASH && RELU) {
+      if (STASH && RELU && !c.no_mask) {
         uint32_t b = 0u;
 #pragma unroll
         for (int j = 0; j < TC_CPT; ++j) b |= (v[j] > 0.f ? 1u : 0u) << j;
@@ -118,7 +119,7 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3]) {
       }
     }
   }
-  if (STASH && RELU)
+  if (STASH && RELU && !c.no_mask)
     *reinterpret_cast<uint2*>(c.mask_out + ((uint32_t)(c.cg * TC_M + c.row) << 3)) = make_uint2(mlo, mhi);
 }
 
@@ -132,7 +133,8 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
                   uint8_t* __restrict__ stash, int* dbg, int dbg_mode) {
   // stash (NULL for inference): [tiles][lay.stash_blocks] blocks of TC_BLOCK_BYTES (mlp_tc_layout.h).
   // dbg_mode (bottleneck experiments only; results are garbage): bit 0 = epilogue skips TMEM load / math /
-  // A store, bit 1 = no weight streaming (MMA reads whatever is in the ring), bit 2 = MMA issuer skips the MMAs
+  // A store, bit 1 = no weight streaming (MMA reads whatever is in the ring), bit 2 = MMA issuer skips the MMAs,
+  // training variant: bit 3 = no stash bulk stores, bit 4 = no ReLU bit masks, bit 5 = no stash_done waits
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -197,8 +199,10 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         auto stash_chunk = [&](int ls, int kb) {
           mbar_wait(bar(BAR_A_READY(kb)), (s_par >> kb) & 1u, dbg, 6);
           s_par ^= 1u << kb;
-          bulk_s2g(st_tile + (size_t)(lay.L[ls].s_out + kb) * TC_BLOCK_BYTES, sA + (uint32_t)kb * TC_KB_BYTES, TC_KB_BYTES);
-          bulk_commit_group();
+          if (!(dbg_mode & 8)) {
+            bulk_s2g(st_tile + (size_t)(lay.L[ls].s_out + kb) * TC_BLOCK_BYTES, sA + (uint32_t)kb * TC_KB_BYTES, TC_KB_BYTES);
+            bulk_commit_group();
+          }
           if (kb == 3) {
             bulk_wait_group_read0();
             mbar_arrive(bar(BAR_STASH_DONE));
@@ -287,6 +291,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     ctx.row = row; ctx.cg = cg; ctx.lane = lane;
     ctx.stash_out = nullptr;
     ctx.mask_out = nullptr;
+    ctx.no_mask = (dbg_mode & 16) != 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t gi = tile * TC_M + row;
       const bool valid = gi < M;
@@ -360,7 +365,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         acc_par ^= 1u;
         tc_fence_after();
         if (STASH && l >= 1 && L.kind != LK_VIEWS) {   // the previous layer's A blocks are in the stash: free to overwrite
-          mbar_wait(bar(BAR_STASH_DONE), stash_par, dbg, 7);
+          if (!(dbg_mode & 32)) mbar_wait(bar(BAR_STASH_DONE), stash_par, dbg, 7);
           stash_par ^= 1u;
         }
         TL_STAMP(tile == tl_tile && tid == 0, 81 + 8 * l);
