@@ -101,6 +101,14 @@ class FusedAdam(torch.optim.Optimizer):
         self._plan_key = None
         self._plan_cache = None
 
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._plan_key = None          # the loaded moments live in new tensors
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        self._plan_key = None
+
     def _init_state(self, params):
         """Moment buffers are allocated per run of adjacent parameters, so that they are adjacent too.  `step` is kept
         as a Python int (torch.optim.Adam accepts a number when such a state_dict is loaded into it)."""

@@ -164,6 +164,23 @@ def test_fused_adam_matches_torch_adam_fixture(tag, max_norm, layout):
     check_adam_state(opt, flat, g, tag)
     sd = opt.state_dict()
     assert len(sd["state"]) == total and len(sd["param_groups"]) == 3
+    # the state dict loads into torch.optim.Adam (and back): one more identical step on both sides
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in flat]
+    groups_ref, i = [], 0
+    for n, lr in zip(n_groups, lrs):
+        groups_ref.append({"params": ref[i:i + n], "lr": lr})
+        i += n
+    topt = torch.optim.Adam(groups_ref, betas=(0.9, 0.999))
+    import copy                              # (load_state_dict aliases same-device tensors: copy them)
+    topt.load_state_dict(copy.deepcopy(sd))
+    opt.load_state_dict(copy.deepcopy(topt.state_dict()))
+    opt.max_grad_norm = None
+    for p, q, x in zip(flat, ref, grads[0]):
+        p.grad, q.grad = c(x), c(x)
+    opt.step()
+    topt.step()
+    for p, q in zip(flat, ref):
+        assert_close(p, q, 2e-8, 2e-6)
 
 
 def test_clip_grad_norm_matches_torch():
@@ -261,11 +278,19 @@ def test_flatten_parameters_training_step_against_torch_adam():
                 torch.nn.utils.clip_grad_norm_([p for gr in opt.param_groups for p in gr["params"]], 1.0)
             opt.step()
             losses.append(float(loss))
-        assert abs(losses[0] - losses[1]) <= 2e-5 * abs(losses[0])
-    for (ka, pa), (kb, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert abs(losses[0] - losses[1]) <= 1e-4 * abs(losses[0])
+    # Adam's first steps move every element by ~lr * sign(g): an element whose gradient is rounding noise (the fp32 dW
+    # reduction uses atomics, so its last bits differ from run to run) may move the other way.  Those are rare and
+    # bounded by 2 * lr * steps; everything else agrees to fp32 rounding.
+    n_bad = n_all = 0
+    for (ka, pa), (kb, pb) in zip(list(a.named_parameters()) + [("pose", pose_a)],
+                                  list(b.named_parameters()) + [("pose", pose_b)]):
         assert ka == kb
-        assert_close(pb, pa, 2e-5, 1e-4, ka)       # update size ~ lr * steps = 1.5e-3; sign flips of ~0 gradients
-    assert_close(pose_b, pose_a, 2e-5, 1e-4)
+        d = (pb.detach() - pa.detach()).abs()
+        assert float(d.max()) <= 2 * 1e-3 * 3 + 1e-6, ka
+        n_bad += int((d > 2e-5 + 1e-4 * pa.detach().abs()).sum())
+        n_all += d.numel()
+    assert n_bad <= 2e-3 * n_all, (n_bad, n_all)
     # the packed weights follow the update: a fresh model loaded from b's state dict renders the same image
     fresh = star_net(V, "fp32")
     fresh.load_state_dict(b.state_dict())
