@@ -88,46 +88,6 @@ __global__ void sample_pts_x4_kernel(const float* __restrict__ rays_o, const flo
   }
 }
 
-// Eval path (no jitter), Nc % 4 == 0: every warp store covers 512 contiguous bytes.  A thread of the x4 kernel above
-// writes its 12 pts floats as three 16-byte pieces 48 bytes apart from its neighbour's, so one warp instruction touches
-// twelve 128-byte lines a third full; here a thread owns one float4 of the FLAT pts array (elements 4u .. 4u+3 =
-// components of at most two consecutive samples) and, in a second grid-stride loop, one float4 of z_vals.
-__global__ void sample_pts_flat_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                                       const float* __restrict__ t_vals, float near_, float far_, int R, int Nc,
-                                       int lindisp, float* __restrict__ pts, float* __restrict__ z_vals) {
-  auto zval = [&](int k) -> float {
-    const float t = t_vals[k];
-    if (!lindisp) return __fadd_rn(__fmul_rn(near_, __fsub_rn(1.f, t)), __fmul_rn(far_, t));
-    const float a = __fmul_rn(__fdiv_rn(1.f, near_), __fsub_rn(1.f, t));
-    const float b = __fmul_rn(__fdiv_rn(1.f, far_), t);
-    return __fdiv_rn(1.f, __fadd_rn(a, b));
-  };
-  const uint32_t Q = (uint32_t)Nc >> 2;
-  const uint32_t nq = (uint32_t)R * Q, stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
-  for (uint32_t q = tid; q < nq; q += stride) {
-    const uint32_t s0 = (q % Q) * 4u;
-    __stcs(reinterpret_cast<float4*>(z_vals) + q, make_float4(zval(s0), zval(s0 + 1), zval(s0 + 2), zval(s0 + 3)));
-  }
-  const uint32_t npq = 3u * nq;
-  for (uint32_t u = tid; u < npq; u += stride) {
-    const uint32_t e0 = 4u * u;
-    uint32_t sg = e0 / 3u, c = e0 - 3u * sg;       // flat sample index (ray * Nc + s) and component of element e0
-    uint32_t r = sg / (uint32_t)Nc, sidx = sg - r * (uint32_t)Nc;
-    float z = zval((int)sidx);
-    float v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      v[k] = __fadd_rn(rays_o[r * 3u + c], __fmul_rn(rays_d[r * 3u + c], z));
-      if (++c == 3u) {
-        c = 0u;
-        if (++sidx == (uint32_t)Nc) { sidx = 0u; ++r; }
-        if (k < 3) z = zval((int)sidx);
-      }
-    }
-    __stcs(reinterpret_cast<float4*>(pts) + u, make_float4(v[0], v[1], v[2], v[3]));
-  }
-}
-
 extern "C" int star_sample_pts(const float* rays_o, const float* rays_d, const float* t_vals,
                                const float* t_rand, float near_, float far_, int R, int Nc, int lindisp,
                                float* pts, float* z_vals, void* stream) {
@@ -139,13 +99,6 @@ extern "C" int star_sample_pts(const float* rays_o, const float* rays_d, const f
   if ((Nc & 3) == 0 && total / 4 < (int64_t)0x7fffffff &&
       (((uintptr_t)pts | (uintptr_t)z_vals | (uintptr_t)t_rand) & 15) == 0) {
     const int64_t nq = total / 4;
-    if (t_rand == nullptr && 3 * nq < (int64_t)0x3fffffff) {
-      const int64_t want = (3 * nq + threads - 1) / threads;
-      const int blocks = (int)(want < 148 * 16 ? want : 148 * 16);
-      sample_pts_flat_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_vals, near_, far_, R, Nc,
-                                                                          lindisp, pts, z_vals);
-      return star_check_launch();
-    }
     const int blocks = (int)((nq + threads - 1) / threads < 148 * 8 ? (nq + threads - 1) / threads : 148 * 8);
     sample_pts_x4_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_vals, t_rand, near_, far_,
                                                                         R, Nc, lindisp, pts, z_vals);
