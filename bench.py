@@ -486,7 +486,11 @@ def measure(args):
             ach = parts[key]["flops"] / (tot_ms * 1e-3) / 1e12
             # dram__bytes_read+write per launch from the committed ncu capture (profiles/r1c_mlp_fwd_tc.md:
             # 7.83 MB per 524288-sample launch = 14.9 B/sample), scaled to this run's average launch
-            traffic = 14.93 * tot_samples / n_l if (args.precision != "fp32" and key == "mlp_forward") else None
+            # (training kernels, profiles/r1q_launches_train.md, static net: stash forward 1.657 GB and dX + dW
+            #  4.806 GB per 262144-sample launch)
+            per_sample = {"mlp_forward": 14.93, "mlp_forward_stash": 6321.0, "mlp_backward": 18333.0}.get(key)
+            traffic = per_sample * tot_samples / n_l if (args.precision != "fp32" and per_sample is not None
+                                                         and args.workload == "c2") else None
             tier = args.precision if not key.startswith("mip") else (args.precision if args.precision in MIP_TIERS else "fp32")
             roof = {"bound": "tensor", "kernel": "star_%s (%s)" % (key, tier), "achieved": ach,
                     "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
