@@ -42,6 +42,9 @@ struct EpiCtx {
   uint8_t* stash_out;          // global: first stash block of this layer's epilogue output for this tile, or NULL
   uint8_t* mask_out;           // global: this layer's ReLU bit masks for this tile (training), or NULL
   bool no_mask;                // debug (timing experiments only)
+  uint32_t stash_done0;        // smem address of barrier stash_done[0]
+  bool wait_stash;             // training: this layer's A blocks still feed the stash stores of the previous layer
+  bool no_stash_wait;          // debug (timing experiments only)
   uint32_t w_full0;            // smem address of barrier w_full[0]
   uint32_t next_stage0;        // ring stage of the NEXT layer's K-block 0 (its K-block kb uses (next_stage0 + kb) % 4)
   int row, cg, lane;
@@ -53,7 +56,7 @@ struct EpiCtx {
 // KIND: LK_IN / LK_FC0 / LK_FC1 (ReLU), LK_OUT (affine + alpha head partial in h[0]), LK_FEAT (affine),
 // LK_VIEWS (ReLU, N = 128, rgb head partials in h[0..2], no A output).
 template <int KIND, bool FP16, bool STASH>
-__device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3]) {
+__device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3], uint32_t& stash_par) {
   constexpr int NCH = (KIND == LK_VIEWS) ? 2 : 4;
   constexpr bool RELU = (KIND == LK_IN || KIND == LK_FC0 || KIND == LK_FC1);
   // All TMEM loads of the layer are issued up front (TC_LD_DEPTH chunks in flight): a tcgen05.ld takes several hundred
@@ -101,7 +104,12 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3]) {
       }
       if (STASH) store_row16<FP16, true>(0u, c.row, c.cg * 2, v, c.stash_out + kb * TC_KB_BYTES);
     } else {
-      // (training: the stash copy of this block is a bulk store issued by the producer warp once the block is complete)
+      // (training: the stash copy of this block is a bulk store issued by the producer warp once the block is complete;
+      //  the previous layer's copy of block kb must have left shared memory before it is overwritten)
+      if (STASH && c.wait_stash) {
+        if (!c.no_stash_wait) mbar_wait(c.stash_done0 + 8u * (uint32_t)kb, (stash_par >> kb) & 1u, nullptr, 7);
+        stash_par ^= 1u << kb;
+      }
       store_row16<FP16, RELU>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v);
       if (STASH && RELU && !c.no_mask) {
         uint32_t b = 0u;
@@ -170,7 +178,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     for (int i = 0; i < TC_NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), 1 + TC_EPI_WARPS); mbar_init(bar(BAR_W_EMPTY(i)), 1); }
     for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A_READY(i)), TC_EPI_WARPS);
     mbar_init(bar(BAR_ACC_FULL), 1);
-    mbar_init(bar(BAR_STASH_DONE), 1);
+    for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_STASH_DONE_KB(i)), 1);
     fence_mbar_init();
   }
   if (warp == TC_EPI_WARPS + 1) tmem_alloc(base + sl.tmem_ptr, TC_TMEM_COLS);
@@ -203,9 +211,15 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             bulk_s2g(st_tile + (size_t)(lay.L[ls].s_out + kb) * TC_BLOCK_BYTES, sA + (uint32_t)kb * TC_KB_BYTES, TC_KB_BYTES);
             bulk_commit_group();
           }
+          // block kb - 1 may be overwritten once its own store has read it (groups complete in order): the epilogue of
+          // the next layer waits per block, so only the last block's store is still in flight when that epilogue starts
+          if (kb >= 1) {
+            bulk_wait_group_read1();
+            mbar_arrive(bar(BAR_STASH_DONE_KB(kb - 1)));
+          }
           if (kb == 3) {
             bulk_wait_group_read0();
-            mbar_arrive(bar(BAR_STASH_DONE));
+            mbar_arrive(bar(BAR_STASH_DONE_KB(3)));
           }
         };
         if (STASH) {   // a_ready[0] also carries the encoder's arrival at the start of a tile: consume that phase
@@ -292,13 +306,16 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     ctx.stash_out = nullptr;
     ctx.mask_out = nullptr;
     ctx.no_mask = (dbg_mode & 16) != 0;
+    ctx.stash_done0 = bar(BAR_STASH_DONE_KB(0));
+    ctx.wait_stash = false;
+    ctx.no_stash_wait = (dbg_mode & 32) != 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t gi = tile * TC_M + row;
       const bool valid = gi < M;
       int64_t out_idx = 0;
       if (STASH && tile != (int64_t)blockIdx.x) {   // feature_linear's blocks of the previous tile have been read
-        mbar_wait(bar(BAR_STASH_DONE), stash_par, dbg, 7);
-        stash_par ^= 1u;
+        for (int kb = 0; kb < 4; ++kb) mbar_wait(bar(BAR_STASH_DONE_KB(kb)), (stash_par >> kb) & 1u, dbg, 7);
+        stash_par ^= 0xfu;
       }
       TL_STAMP(tile == tl_tile && tid == 0, 8);
       // ---- inputs: pose transform + encoding -> A K-block 0 (xyz, 4 threads per row) and the dirs block
@@ -364,10 +381,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         mbar_wait(bar(BAR_ACC_FULL), acc_par, dbg, 4);
         acc_par ^= 1u;
         tc_fence_after();
-        if (STASH && l >= 1 && L.kind != LK_VIEWS) {   // the previous layer's A blocks are in the stash: free to overwrite
-          if (!(dbg_mode & 32)) mbar_wait(bar(BAR_STASH_DONE), stash_par, dbg, 7);
-          stash_par ^= 1u;
-        }
+        ctx.wait_stash = STASH && l >= 1;   // (per block, inside the epilogue: see epilogue_layer)
         TL_STAMP(tile == tl_tile && tid == 0, 81 + 8 * l);
         if (dbg_mode & 1) {
           for (int kb = 0; kb < (L.N >> 6) && kind != LK_VIEWS; ++kb) {
@@ -378,12 +392,12 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             }
           }
         } else if (kind == LK_FC0 || kind == LK_FC1 || kind == LK_IN) {
-          epilogue_layer<LK_FC0, FP16, STASH>(ctx, h);
+          epilogue_layer<LK_FC0, FP16, STASH>(ctx, h, stash_par);
         } else if (kind == LK_FEAT) {
-          epilogue_layer<LK_FEAT, FP16, STASH>(ctx, h);
+          epilogue_layer<LK_FEAT, FP16, STASH>(ctx, h, stash_par);
         } else if (kind == LK_OUT) {
           ctx.head_w = s_small + lay.off_alpha_w;
-          epilogue_layer<LK_OUT, FP16, STASH>(ctx, h);
+          epilogue_layer<LK_OUT, FP16, STASH>(ctx, h, stash_par);
           // combine the 4 column groups of each row: groups 1..3 park their partial, group 0 finishes
           if (cg != 0) part(row, cg)[0] = h[0];
           named_bar_sync(1, TC_EPI_THREADS);
@@ -391,7 +405,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             raw_alpha[out_idx] = h[0] + part(row, 1)[0] + part(row, 2)[0] + part(row, 3)[0] + s_small[lay.off_alpha_b];
         } else {   // LK_VIEWS
           ctx.head_w = s_small + lay.off_rgb_w;
-          epilogue_layer<LK_VIEWS, FP16, STASH>(ctx, h);
+          epilogue_layer<LK_VIEWS, FP16, STASH>(ctx, h, stash_par);
           if (cg != 0) {
             float* d = part(row, cg);
             d[1] = h[0]; d[2] = h[1]; d[3] = h[2];

@@ -27,7 +27,7 @@ __host__ __device__ static inline TcSmem tc_smem_layout(uint32_t small_bytes) {
   s.W = o; o += TC_NS * TC_STAGE_BYTES;
   s.small = o; o += small_bytes;
   s.part = s.AD;    // head partial sums live in the never-read half (columns 32..63) of the dirs block
-  s.bars = o; o += 16 * 8;
+  s.bars = o; o += 24 * 8;
   s.tmem_ptr = o; o += 16;
   s.total = o + 1024;   // slack for aligning the dynamic smem base
   return s;
@@ -38,7 +38,8 @@ __host__ __device__ static inline TcSmem tc_smem_layout(uint32_t small_bytes) {
 #define BAR_W_EMPTY(i) (TC_NS + (i))
 #define BAR_A_READY(i) (2 * TC_NS + (i))      // 0..3: A K-blocks, 4: encoded-dirs block
 #define BAR_ACC_FULL (2 * TC_NS + 5)
-#define BAR_STASH_DONE (2 * TC_NS + 6)   // training forward: the bulk stores of a layer's A blocks have read shared memory
+#define BAR_STASH_DONE (2 * TC_NS + 6)   // training: the bulk store of A block kb has read shared memory (one barrier per block)
+#define BAR_STASH_DONE_KB(kb) (BAR_STASH_DONE + (kb))
 
 // ---------------------------------------------------------------------------------------------- encode
 // 16 consecutive columns [C0, C0+16) of the positional encoding [x, sin(2^k x), cos(2^k x)]_k (embedder.py:90-97;

@@ -76,6 +76,8 @@ __device__ __forceinline__ void bulk_s2g(void* dst_global, uint32_t src_smem, ui
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed groups have finished READING their shared-memory source (it may be overwritten)
 __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the most recently committed group have read their source (groups complete in order)
+__device__ __forceinline__ void bulk_wait_group_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 // all committed groups are complete (global writes performed)
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
