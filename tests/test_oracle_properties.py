@@ -7,7 +7,7 @@ from hypothesis import given, settings, strategies as st
 
 from oracle import star_oracle as so, train_oracle as to
 
-SET = dict(max_examples=20, deadline=None)
+SET = dict(max_examples=20, deadline=None, derandomize=True, database=None)   # same examples on every run
 
 
 def gen(seed):
@@ -76,7 +76,7 @@ def test_multi_field_compositing_invariants(seed, R, S, V):
     assert float(dead["acc"].abs().max()) == 0.0
 
 
-@settings(max_examples=10, deadline=None)
+@settings(max_examples=10, deadline=None, derandomize=True, database=None)
 @given(seed=st.integers(0, 10_000), n=st.integers(1, 50), steps=st.integers(1, 5),
        lr=st.sampled_from([1e-4, 5e-4, 1e-2]), scale=st.sampled_from([1e-6, 1.0, 30.0]))
 def test_adam_recurrence_tracks_torch_adam(seed, n, steps, lr, scale):
