@@ -28,6 +28,21 @@ def build(force=False, verbose=False):
     """nvcc -shared of every kernel file; cross-compiles without a GPU."""
     if not force and not _stale():
         return LIB
+    # one builder at a time (torchrun ranks import the package concurrently): the others wait on the lock and then
+    # find the library fresh
+    import fcntl
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []
@@ -45,10 +60,12 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, out))
         if verbose and out:
             print(out)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    tmp = LIB + ".tmp.%d" % os.getpid()    # link beside, then rename: a reader never maps a half-written library
+    cmd = [nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
+    os.replace(tmp, LIB)
     return LIB
 
 

@@ -11,6 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstar_b200.so")
 
+ABI_VERSION = 2
 PREC_F32, PREC_BF16, PREC_F16 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_F32, "bf16": PREC_BF16, "fp16": PREC_F16}
 
@@ -51,11 +52,11 @@ _SIGS = {
                                 c_f, c_f, c_f, c_f]),
     "star_embed": (C.c_int, [c_f, C.c_int, C.c_int, c_f, c_f, c_f]),
     "star_stash_bytes": (C.c_size_t, [C.POINTER(StarNetDesc), c_i64]),
-    "star_mlp_forward": (C.c_int, [C.POINTER(StarNetDesc), c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, c_f, c_f,
-                                   c_i64, c_f, c_f]),
+    "star_mlp_forward": (C.c_int, [C.POINTER(StarNetDesc), c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int,
+                                   C.c_int, c_f, c_f, c_i64, c_f, c_f, c_f]),
     "star_mlp_backward_workspace_bytes": (C.c_size_t, [C.POINTER(StarNetDesc), c_i64]),
-    "star_mlp_backward": (C.c_int, [C.POINTER(StarNetDesc), c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, c_f,
-                                    c_f, c_i64, c_f, c_f, c_f, c_f, c_f]),
+    "star_mlp_backward": (C.c_int, [C.POINTER(StarNetDesc), c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, C.c_int,
+                                    C.c_int, c_f, c_f, c_i64, c_f, c_f, c_f, c_f, c_f]),
     "star_composite_single_forward": (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_float, C.c_int, c_f, c_f,
                                                 c_f, c_f, c_f, c_f, c_f]),
     "star_composite_single_backward": (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_float, C.c_int, c_f, c_f,
@@ -129,7 +130,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.star_abi_version() != 1:
+        if L.star_abi_version() != ABI_VERSION:
             raise StarError("libstar_b200.so ABI mismatch")
         _lib = L
     return _lib

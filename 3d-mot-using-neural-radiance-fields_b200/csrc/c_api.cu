@@ -9,21 +9,21 @@ int g_star_last_cuda_error = 0;
 size_t star_tc_packed_bytes(const TcLayout& tl);
 int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, void* packed, int fp16,
                  cudaStream_t st);
-int star_tc_forward(const TcLayout& tl, const void* packed, const float* pts, const float* viewdirs,
+int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                     const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
-                    float* raw_rgb, int64_t ray_stride, void* stash, int fp16, cudaStream_t st);
+                    float* raw_rgb, int64_t ray_stride, void* stash, int* status, int fp16, cudaStream_t st);
 
 size_t star_tc_gstash_bytes(const TcLayout& tl, int64_t n_samples);
-int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed, const float* pts, const float* viewdirs,
+int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                      const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, const float* d_raw_alpha,
                      const float* d_raw_rgb, int64_t ray_stride, const void* stash, void* gstash, float* grad_flat,
                      float* pose_acc, int fp16, cudaStream_t st);
 
 int star_f32_pack(const MlpLayout& lay, const float* master, void* packed, cudaStream_t st);
-int star_f32_forward(const MlpLayout& lay, const void* packed, const float* pts, const float* viewdirs,
+int star_f32_forward(const MlpLayout& lay, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                      const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
                      float* raw_rgb, int64_t ray_stride, void* stash, cudaStream_t st);
-int star_f32_backward(const MlpLayout& lay, const void* packed, const float* pts, const float* viewdirs,
+int star_f32_backward(const MlpLayout& lay, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                       const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S,
                       const float* d_raw_alpha, const float* d_raw_rgb, int64_t ray_stride, const void* stash,
                       void* workspace, float* grad_flat, float* pose_acc, cudaStream_t st);
@@ -101,11 +101,14 @@ extern "C" size_t star_mlp_backward_workspace_bytes(const StarNetDesc* d, int64_
   return 0;
 }
 
-extern "C" int star_mlp_forward(const StarNetDesc* d, const void* packed, const float* pts, const float* viewdirs,
+extern "C" int star_mlp_forward(const StarNetDesc* d, const void* packed, const float* pts_or_null,
+                                const float* rays_o, const float* rays_d, const float* z_vals, const float* viewdirs,
                                 const float* pose12, const float* enc_scale_xyz, const float* enc_scale_dir, int R,
                                 int S, float* raw_alpha, float* raw_rgb, int64_t alpha_ray_stride, void* stash,
-                                void* stream) {
-  if (!d || !packed || !pts || !viewdirs || !raw_alpha || !raw_rgb) return STAR_E_NULL;
+                                int32_t* status, void* stream) {
+  if (!d || !packed || !viewdirs || !raw_alpha || !raw_rgb) return STAR_E_NULL;
+  if (!pts_or_null && (!rays_o || !rays_d || !z_vals)) return STAR_E_NULL;
+  const StarPtsSrc pts{pts_or_null, rays_o, rays_d, z_vals};
   if (R < 0 || S < 1 || alpha_ray_stride < S) return STAR_E_BAD_SHAPE;
   if (R == 0) return STAR_OK;
   MlpLayout lay;
@@ -119,20 +122,23 @@ extern "C" int star_mlp_forward(const StarNetDesc* d, const void* packed, const 
     rc = star_make_tc_layout(d, &tl);
     if (rc) return rc;
     return star_tc_forward(tl, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, raw_alpha, raw_rgb,
-                           alpha_ray_stride, stash, d->precision == STAR_PREC_F16, (cudaStream_t)stream);
+                           alpha_ray_stride, stash, status, d->precision == STAR_PREC_F16, (cudaStream_t)stream);
   }
   return STAR_E_UNSUPPORTED;
 }
 
 extern "C" int star_mlp_backward(const StarNetDesc* d, const void* packed, const float* flat_master,
-                                 const float* pts, const float* viewdirs, const float* pose12,
+                                 const float* pts_or_null, const float* rays_o, const float* rays_d,
+                                 const float* z_vals, const float* viewdirs, const float* pose12,
                                  const float* enc_scale_xyz, const float* enc_scale_dir, int R, int S,
                                  const float* d_raw_alpha, const float* d_raw_rgb, int64_t alpha_ray_stride,
                                  const void* stash, void* workspace, float* grad_flat, float* pose_acc,
                                  void* stream) {
   (void)flat_master;
-  if (!d || !packed || !pts || !viewdirs || !d_raw_alpha || !d_raw_rgb || !stash || !workspace || !grad_flat)
+  if (!d || !packed || !viewdirs || !d_raw_alpha || !d_raw_rgb || !stash || !workspace || !grad_flat)
     return STAR_E_NULL;
+  if (!pts_or_null && (!rays_o || !rays_d || !z_vals)) return STAR_E_NULL;
+  const StarPtsSrc pts{pts_or_null, rays_o, rays_d, z_vals};
   if (pose12 && !pose_acc) return STAR_E_NULL;
   if (R < 0 || S < 1 || alpha_ray_stride < S) return STAR_E_BAD_SHAPE;
   if (R == 0) return STAR_OK;

@@ -17,11 +17,12 @@ struct SampleGeom {
   float p[3], d[3];   // object-frame point and view direction
 };
 
-__device__ __forceinline__ SampleGeom load_geom(const float* __restrict__ pts, const float* __restrict__ viewdirs,
+__device__ __forceinline__ SampleGeom load_geom(const StarPtsSrc& pts, const float* __restrict__ viewdirs,
                                                 const float* __restrict__ pose12, int64_t gi, int S) {
   SampleGeom g;
   const int64_t r = gi / S;
-  const float px = pts[gi * 3 + 0], py = pts[gi * 3 + 1], pz = pts[gi * 3 + 2];
+  float px, py, pz;
+  star_load_pt(pts, gi, r, px, py, pz);
   const float dx = viewdirs[r * 3 + 0], dy = viewdirs[r * 3 + 1], dz = viewdirs[r * 3 + 2];
   if (pose12 != nullptr) {   // p' = R p + t, d' = R d   (star__.py:165-180 / pypose Act :191-196)
 #pragma unroll
@@ -39,7 +40,7 @@ __device__ __forceinline__ SampleGeom load_geom(const float* __restrict__ pts, c
 // ================================================================================ forward kernel
 template <bool STASH>
 __global__ void __launch_bounds__(NTHREADS, 1)
-mlp_fwd_f32_kernel(MlpLayout lay, const float* __restrict__ packed, const float* __restrict__ pts,
+mlp_fwd_f32_kernel(MlpLayout lay, const float* __restrict__ packed, const StarPtsSrc pts,
                    const float* __restrict__ viewdirs, const float* __restrict__ pose12,
                    const float* __restrict__ sc_xyz, const float* __restrict__ sc_dir, int S, int64_t M,
                    float* __restrict__ raw_alpha, float* __restrict__ raw_rgb, int64_t ray_stride,
@@ -247,7 +248,7 @@ mlp_fwd_f32_kernel(MlpLayout lay, const float* __restrict__ packed, const float*
 // for every GEMM layer into `gst` ([layer][M][N]) -- consumed by the dW kernel -- and, for dynamic
 // objects, the pose accumulators (see star_b200.h).  ReLU masks come from the stashed activations.
 __global__ void __launch_bounds__(NTHREADS, 1)
-mlp_bwd_f32_kernel(MlpLayout lay, const float* __restrict__ packed, const float* __restrict__ pts,
+mlp_bwd_f32_kernel(MlpLayout lay, const float* __restrict__ packed, const StarPtsSrc pts,
                    const float* __restrict__ viewdirs, const float* __restrict__ pose12,
                    const float* __restrict__ sc_xyz, const float* __restrict__ sc_dir, int S, int64_t M,
                    const float* __restrict__ d_raw_alpha, const float* __restrict__ d_raw_rgb, int64_t ray_stride,
@@ -485,7 +486,8 @@ mlp_bwd_f32_kernel(MlpLayout lay, const float* __restrict__ packed, const float*
             }
             h[c] = bq;
           }
-          const float p0 = pts[gi * 3 + 0], p1 = pts[gi * 3 + 1], p2 = pts[gi * 3 + 2];
+          float p0, p1, p2;
+          star_load_pt(pts, gi, gi / S, p0, p1, p2);
           const float pw[3] = {p0, p1, p2};
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
@@ -683,7 +685,7 @@ static int grid_for_tiles(int64_t ntiles) {
   return (int)(ntiles < sms ? ntiles : sms);
 }
 
-int star_f32_forward(const MlpLayout& lay, const void* packed, const float* pts, const float* viewdirs,
+int star_f32_forward(const MlpLayout& lay, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                      const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
                      float* raw_rgb, int64_t ray_stride, void* stash, cudaStream_t st) {
   const int64_t M = (int64_t)R * S;
@@ -703,7 +705,7 @@ int star_f32_forward(const MlpLayout& lay, const void* packed, const float* pts,
   return star_check_launch();
 }
 
-int star_f32_backward(const MlpLayout& lay, const void* packed, const float* pts, const float* viewdirs,
+int star_f32_backward(const MlpLayout& lay, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                       const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S,
                       const float* d_raw_alpha, const float* d_raw_rgb, int64_t ray_stride, const void* stash,
                       void* workspace, float* grad_flat, float* pose_acc, cudaStream_t st) {

@@ -134,11 +134,20 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3], u
 // ============================================================================================ forward
 template <bool FP16, bool STASH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const float* __restrict__ pts,
+mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const StarPtsSrc pts,
                   const float* __restrict__ viewdirs, const float* __restrict__ pose12,
                   const float* __restrict__ sc_xyz, const float* __restrict__ sc_dir, int S, int64_t M,
                   float* __restrict__ raw_alpha, float* __restrict__ raw_rgb, int64_t ray_stride,
-                  uint8_t* __restrict__ stash, int* dbg, int dbg_mode) {
+                  uint8_t* __restrict__ stash, int* __restrict__ status, int* dbg, int dbg_mode_arg) {
+  // status (nullable): word set to 1 when a raw output is not finite -- the range guard of the fp16-operand tier (an
+  // activation beyond 65504 becomes +inf in the 16-bit operand and reaches the heads as inf / NaN) and, for any tier,
+  // the sign of non-finite inputs or weights.
+#ifdef STAR_TC_DEBUG
+  const int dbg_mode = dbg_mode_arg;
+#else
+  constexpr int dbg_mode = 0;    // the bottleneck-experiment switches below exist in -DSTAR_TC_DEBUG builds only
+  (void)dbg_mode_arg;
+#endif
   // stash (NULL for inference): [tiles][lay.stash_blocks] blocks of TC_BLOCK_BYTES (mlp_tc_layout.h).
   // dbg_mode (bottleneck experiments only; results are garbage): bit 0 = epilogue skips TMEM load / math /
   // A store, bit 1 = no weight streaming (MMA reads whatever is in the ring), bit 2 = MMA issuer skips the MMAs,
@@ -299,6 +308,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     const int q = warp & 3, cg = warp >> 2;
     const int row = q * 32 + lane;
     uint32_t acc_par = 0, stash_par = 0;
+    bool nonfinite = false;
     uint32_t kstage = 0;          // ring stage of the current layer's K-block 0 (same sequence as producer / issuer)
     EpiCtx ctx;
     ctx.sA = sA; ctx.a_ready0 = bar(BAR_A_READY(0)); ctx.w_full0 = bar(BAR_W_FULL(0));
@@ -324,7 +334,8 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         if (valid) {
           const int64_t r = gi / S;
           out_idx = r * ray_stride + (gi - r * S);
-          const float px = pts[gi * 3 + 0], py = pts[gi * 3 + 1], pz = pts[gi * 3 + 2];
+          float px, py, pz;
+          star_load_pt(pts, gi, r, px, py, pz);
           const float dx = viewdirs[r * 3 + 0], dy = viewdirs[r * 3 + 1], dz = viewdirs[r * 3 + 2];
           if (pose12 != nullptr) {   // p' = R p + t, d' = R d
 #pragma unroll
@@ -401,8 +412,11 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           // combine the 4 column groups of each row: groups 1..3 park their partial, group 0 finishes
           if (cg != 0) part(row, cg)[0] = h[0];
           named_bar_sync(1, TC_EPI_THREADS);
-          if (cg == 0 && valid)
-            raw_alpha[out_idx] = h[0] + part(row, 1)[0] + part(row, 2)[0] + part(row, 3)[0] + s_small[lay.off_alpha_b];
+          if (cg == 0 && valid) {
+            const float ra = h[0] + part(row, 1)[0] + part(row, 2)[0] + part(row, 3)[0] + s_small[lay.off_alpha_b];
+            raw_alpha[out_idx] = ra;
+            nonfinite |= !(fabsf(ra) <= 3.4028235e38f);
+          }
         } else {   // LK_VIEWS
           ctx.head_w = s_small + lay.off_rgb_w;
           epilogue_layer<LK_VIEWS, FP16, STASH>(ctx, h, stash_par);
@@ -415,15 +429,19 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           if (cg == 0 && valid) {
             float* o = raw_rgb + out_idx * 3;
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch)
-              o[ch] = h[ch] + part(row, 1)[1 + ch] + part(row, 2)[1 + ch] + part(row, 3)[1 + ch] +
-                      s_small[lay.off_rgb_b + ch];
+            for (int ch = 0; ch < 3; ++ch) {
+              const float rc = h[ch] + part(row, 1)[1 + ch] + part(row, 2)[1 + ch] + part(row, 3)[1 + ch] +
+                               s_small[lay.off_rgb_b + ch];
+              o[ch] = rc;
+              nonfinite |= !(fabsf(rc) <= 3.4028235e38f);
+            }
           }
         }
         TL_STAMP(tile == tl_tile && tid == 0, 82 + 8 * l);
         TL_STAMP(tile == tl_tile && lane == 0 && l == 1, 200 + warp);
       }
     }
+    if (status != nullptr && nonfinite) *reinterpret_cast<volatile int*>(status) = 1;
   }
 
   // ---- teardown
@@ -514,9 +532,9 @@ int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, v
   return star_tc_pack_tstream(tl, ml, master, (uint8_t*)packed + tl.small_bytes + tl.stream_bytes, fp16, st);
 }
 
-int star_tc_forward(const TcLayout& tl, const void* packed, const float* pts, const float* viewdirs,
+int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                     const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
-                    float* raw_rgb, int64_t ray_stride, void* stash, int fp16, cudaStream_t st) {
+                    float* raw_rgb, int64_t ray_stride, void* stash, int* status, int fp16, cudaStream_t st) {
   const int64_t M = (int64_t)R * S;
   const int64_t ntiles = (M + TC_M - 1) / TC_M;
   int dev = 0, sms = 148;
@@ -529,6 +547,12 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const float* pts, co
                                : (fp16 ? mlp_fwd_tc_kernel<true, false> : mlp_fwd_tc_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
   if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
+#ifndef STAR_TC_DEBUG
+  kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
+                                            raw_alpha, raw_rgb, ray_stride, (uint8_t*)stash, status, nullptr, 0);
+#else
+  // -DSTAR_TC_DEBUG builds only (tools/tc_debug_modes.sh, tools/tc_timeline.sh): STAR_TC_DEBUG_MODE switches parts of the
+  // kernel off (results are garbage), STAR_TC_DEBUG_CYCLES=1 makes the launch synchronous and prints CTA 0's cycles
   static int dbg_mode = -1;
   if (dbg_mode < 0) { const char* e2 = getenv("STAR_TC_DEBUG_MODE"); dbg_mode = e2 ? atoi(e2) : 0; }
   // STAR_TC_DEBUG_CYCLES=1 (bottleneck experiments only): synchronous launch that prints the SM cycles CTA 0 spent
@@ -539,7 +563,7 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const float* pts, co
     if (dbg_cycles) { cudaMalloc(&d_dbg, 4096); cudaMemset(d_dbg, 0, 4096); }
   }
   kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
-                                            raw_alpha, raw_rgb, ray_stride, (uint8_t*)stash, (int*)d_dbg, dbg_mode);
+                                            raw_alpha, raw_rgb, ray_stride, (uint8_t*)stash, status, (int*)d_dbg, dbg_mode);
   if (dbg_cycles) {
     static long long h[512];
     cudaStreamSynchronize(st);
@@ -563,5 +587,6 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const float* pts, co
     }
 #endif
   }
+#endif
   return star_check_launch();
 }

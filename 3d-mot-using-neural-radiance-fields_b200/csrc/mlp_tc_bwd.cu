@@ -113,9 +113,12 @@ __device__ __forceinline__ void fold_jacobian(const uint32_t (&r)[16], const flo
 }
 
 // ============================================================================================ dX chain
-template <bool FP16, bool POSE>
+// GF16: format of the back-propagated gradients G_l (A operand here and in dW; false = bf16 -- the production choice for
+// both tiers: dL/d(activation) of a 4096-ray batch reaches 1e-8, below fp16's subnormal range); WF16: format of the
+// weights (B operand), the forward tier's.
+template <bool GF16, bool WF16, bool POSE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const float* __restrict__ pts,
+mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const StarPtsSrc pts,
                   const float* __restrict__ viewdirs, const float* __restrict__ pose12,
                   const float* __restrict__ sc_xyz, const float* __restrict__ sc_dir, int S, int64_t M,
                   const float* __restrict__ d_raw_alpha, const float* __restrict__ d_raw_rgb, int64_t ray_stride,
@@ -260,7 +263,7 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           }
           mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
           tc_fence_after();
-          const uint32_t idesc = umma_idesc_16(TC_M, s.N, FP16 ? 0 : 1);
+          const uint32_t idesc = umma_idesc_ab(TC_M, s.N, GF16 ? 0 : 1, WF16 ? 0 : 1);
           const uint64_t a0 = desc_a0 + (uint64_t)(s.a_kb * (TC_KB_BYTES >> 4));
           const uint64_t b0 = desc_w0 + (uint64_t)(stage * (TC_STAGE_BYTES >> 4));
           if (elect_one_sync()) {
@@ -303,7 +306,7 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         da = d_raw_alpha[o];
         dc0 = d_raw_rgb[o * 3 + 0]; dc1 = d_raw_rgb[o * 3 + 1]; dc2 = d_raw_rgb[o * 3 + 2];
         if (has_pose) {
-          pw[0] = pts[gi * 3 + 0]; pw[1] = pts[gi * 3 + 1]; pw[2] = pts[gi * 3 + 2];
+          star_load_pt(pts, gi, r, pw[0], pw[1], pw[2]);
           dw[0] = viewdirs[r * 3 + 0]; dw[1] = viewdirs[r * 3 + 1]; dw[2] = viewdirs[r * 3 + 2];
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
@@ -443,7 +446,7 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             for (int j = 0; j < 16; ++j) v[j] = 0.f;
           }
           // (the gstash copy of this block is a bulk store issued by the producer warp once the block is complete)
-          store_row16<FP16, false>(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, v);
+          store_row16<GF16, false>(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, v);
           fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
@@ -497,7 +500,8 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t 
   return d;
 }
 
-template <bool FP16>
+// GF16 / AF16: formats of the gradient blocks (A operand) and of the activation blocks (B operand; the forward tier's)
+template <bool GF16, bool AF16>
 __global__ void __launch_bounds__(DW_THREADS, 1)
 dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8_t* __restrict__ stash,
              const uint8_t* __restrict__ gstash, int64_t ntiles, float* __restrict__ grad_flat, int* dbg) {
@@ -525,7 +529,7 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
   for (int i = tid; i < TC_BLOCK_BYTES / 16; i += DW_THREADS) {
     const int r = i >> 3, c = i & 7;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (c == (r & 7)) v.x = FP16 ? 0x3C00u : 0x3F80u;
+    if (c == (r & 7)) v.x = AF16 ? 0x3C00u : 0x3F80u;
     reinterpret_cast<uint4*>(gbase + (sOnes - base))[i] = v;
   }
   fence_proxy_async_smem();
@@ -552,9 +556,9 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
     // warp-uniform control flow, one elected lane issues the tcgen05 instructions (see elect_one_sync)
     {
       const int N = 64 * it.n_a;
-      const uint32_t fmt = FP16 ? 0u : 1u;
-      const uint32_t idesc = umma_idesc_16(128, N, (int)fmt) | (1u << 15) | (1u << 16);      // both operands MN-major
-      const uint32_t idesc1 = umma_idesc_16(128, 16, (int)fmt) | (1u << 15) | (1u << 16);
+      const int gf = GF16 ? 0 : 1, af = AF16 ? 0 : 1;
+      const uint32_t idesc = umma_idesc_ab(128, N, gf, af) | (1u << 15) | (1u << 16);      // both operands MN-major
+      const uint32_t idesc1 = umma_idesc_ab(128, 16, gf, af) | (1u << 15) | (1u << 16);
       const bool with_bias = it.b_off >= 0;
       const uint64_t d1 = umma_desc_mn_sw128(sOnes, TC_BLOCK_BYTES);
       uint32_t st = 0, ph = 0;
@@ -768,7 +772,7 @@ size_t star_tc_gstash_bytes(const TcLayout& tl, int64_t n_samples) {
   return (size_t)((n_samples + 127) / 128) * (size_t)tl.gstash_blocks * TC_BLOCK_BYTES;
 }
 
-int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed, const float* pts, const float* viewdirs,
+int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                      const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, const float* d_raw_alpha,
                      const float* d_raw_rgb, int64_t ray_stride, const void* stash, void* gstash, float* grad_flat,
                      float* pose_acc, int fp16, cudaStream_t st) {
@@ -781,8 +785,8 @@ int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed
   {
     const int grid = (int)(ntiles < sms ? ntiles : sms);
     const BwdSmem sl = bwd_smem_layout(tl.small_bytes);
-    auto kern = pose12 != nullptr ? (fp16 ? mlp_bwd_tc_kernel<true, true> : mlp_bwd_tc_kernel<false, true>)
-                                  : (fp16 ? mlp_bwd_tc_kernel<true, false> : mlp_bwd_tc_kernel<false, false>);
+    auto kern = pose12 != nullptr ? (fp16 ? mlp_bwd_tc_kernel<false, true, true> : mlp_bwd_tc_kernel<false, false, true>)
+                                  : (fp16 ? mlp_bwd_tc_kernel<false, true, false> : mlp_bwd_tc_kernel<false, false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
     if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
     kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
@@ -820,7 +824,7 @@ int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed
     if ((int64_t)splits > ntiles) splits = (int)ntiles;
     plan.splits = splits;
     const size_t smem = (size_t)(DW_NSTAGE * DW_STAGE_BLOCKS + 1) * TC_BLOCK_BYTES + 256 + 1024;
-    auto kern = fp16 ? dw_tc_kernel<true> : dw_tc_kernel<false>;
+    auto kern = fp16 ? dw_tc_kernel<false, true> : dw_tc_kernel<false, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
     kern<<<n * splits, DW_THREADS, smem, st>>>(plan, tl.stash_blocks, tl.gstash_blocks, (const uint8_t*)stash,

@@ -19,6 +19,27 @@ static inline int star_check_launch() {
   return STAR_OK;
 }
 
+// Where a kernel finds the sample positions: either a materialised pts [M,3] array (the tensor that crosses the
+// reference API between sample_pts and render_*, models/rendering__.py:108-110) or, when pts == NULL, the ray and its
+// depths -- p = rays_o[r] + rays_d[r] * z_vals[r, s] with the reference's two roundings (no FMA contraction), so both
+// forms are bit-identical and the fused render path never writes or reads 12 B/sample of positions.
+struct StarPtsSrc {
+  const float* pts;
+  const float* rays_o;
+  const float* rays_d;
+  const float* z_vals;     // [R, S]
+};
+__device__ __forceinline__ void star_load_pt(const StarPtsSrc& s, int64_t gi, int64_t r, float& px, float& py, float& pz) {
+  if (s.pts != nullptr) {
+    px = s.pts[gi * 3 + 0]; py = s.pts[gi * 3 + 1]; pz = s.pts[gi * 3 + 2];
+  } else {
+    const float z = s.z_vals[gi];
+    px = __fadd_rn(s.rays_o[r * 3 + 0], __fmul_rn(s.rays_d[r * 3 + 0], z));
+    py = __fadd_rn(s.rays_o[r * 3 + 1], __fmul_rn(s.rays_d[r * 3 + 1], z));
+    pz = __fadd_rn(s.rays_o[r * 3 + 2], __fmul_rn(s.rays_d[r * 3 + 2], z));
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(STAR_FULL_MASK, v, o);

@@ -383,6 +383,41 @@ def stash_alloc(nbytes, device):
     return t
 
 
+# ---- range guard of the 16-bit tiers: one int32 per device in mapped pinned host memory.  The MLP kernels set it to 1 when
+# a raw output is not finite (an fp16 operand overflowed, or the inputs / weights were not finite); the host looks at it
+# WITHOUT synchronising at the next MLP call (an overflow therefore raises one call late at the latest) and on demand.
+_RANGE_FLAGS = {}
+
+
+def _range_flag(device):
+    idx = _dev_index(device)
+    t = _RANGE_FLAGS.get(idx)
+    if t is None:
+        t = _RANGE_FLAGS[idx] = torch.zeros(1, dtype=torch.int32).pin_memory()
+    return t
+
+
+def check_range(sync=True):
+    """Raises StarError if any tensor-core MLP launch so far produced a non-finite raw output (fp16 activations beyond
+    65504: switch that net to set_precision('bf16') or 'fp32').  sync=True waits for the device first."""
+    if sync and _RANGE_FLAGS:
+        torch.cuda.synchronize()
+    for idx, t in _RANGE_FLAGS.items():
+        if int(t[0]) != 0:
+            t[0] = 0
+            raise _capi.StarError("cuda:%d: a tensor-core MLP launch produced non-finite raw outputs (fp16 operand range "
+                                  "exceeded, or non-finite inputs / weights); use set_precision('bf16') or 'fp32'" % idx)
+
+
+def _geom_ptrs(geom, a, b):
+    """geom = pts [R,S,3]  or  (rays_o [R,3], rays_d [R,3], z_vals [R,S])  ->  the four pointer arguments of
+    star_mlp_forward / star_mlp_backward for the ray range [a, b)."""
+    if torch.is_tensor(geom):
+        return f32(geom[a:b]), None, None, None
+    ro, rd, z = geom
+    return None, f32(ro[a:b]), f32(rd[a:b]), f32(z[a:b])
+
+
 def _ray_chunks(R, S):
     per = max(1, MAX_SAMPLES_PER_LAUNCH // S)
     return [(a, min(R, a + per)) for a in range(0, R, per)]
@@ -395,12 +430,24 @@ class NerfRaw(Function):
 
     @staticmethod
     def forward(ctx, rt, precision, grad_mode, pts, viewdirs, pose12, sc_xyz, sc_dir, *params):
-        pts, viewdirs = _c(pts), _c(viewdirs)
-        R, S = pts.shape[0], pts.shape[1]
-        dev = pts.device
+        # pts: the materialised positions [R,S,3], or the tuple (rays_o, rays_d, z_vals) -- the kernel then forms
+        # rays_o + rays_d * z itself (bit-identical; nothing of size [R,S,3] is read)
+        if torch.is_tensor(pts):
+            geom = _c(pts)
+            R, S = geom.shape[0], geom.shape[1]
+        else:
+            geom = tuple(_c(t.detach()) for t in pts)
+            R, S = geom[2].shape
+        viewdirs = _c(viewdirs)
+        dev = viewdirs.device
         flat, packed = rt.refresh(precision)
         d = rt.desc(precision)
         L = _capi.lib()
+        flag = None
+        if precision != _capi.PREC_F32:
+            flag = _range_flag(dev)
+            if int(flag[0]) != 0:
+                check_range(sync=False)
         raw_alpha = torch.empty((R, S), device=dev)
         raw_rgb = torch.empty((R, S, 3), device=dev)
         # ctx.needs_input_grad ignores torch.no_grad(): `grad_mode` (torch.is_grad_enabled() at the call site) decides
@@ -416,32 +463,36 @@ class NerfRaw(Function):
             st = None
             if keep:
                 st = stash_alloc(L.star_stash_bytes(C.byref(d), (b - a) * S), dev)
-                stashes.append(st)
+            stashes.append(st)
             e0 = _prof_begin()
-            check(L.star_mlp_forward(C.byref(d), ptr(packed), f32(pts[a:b]), f32(viewdirs[a:b]),
+            check(L.star_mlp_forward(C.byref(d), ptr(packed), *_geom_ptrs(geom, a, b), f32(viewdirs[a:b]),
                                      f32(p12) if p12 is not None else None,
                                      f32(sc_xyz) if sc_xyz is not None else None,
                                      f32(sc_dir) if sc_dir is not None else None, b - a, S, f32(raw_alpha[a:b]),
-                                     f32(raw_rgb[a:b]), S, ptr(st), stream()), "star_mlp_forward")
+                                     f32(raw_rgb[a:b]), S, ptr(st), flag.data_ptr() if flag is not None else None,
+                                     stream()), "star_mlp_forward")
             _prof_end("mlp_forward_stash" if st is not None else "mlp_forward", e0, (b - a) * S,
                       2.0 * MLP_MAC_PER_SAMPLE.get(rt.n_blocks, 0) * (b - a) * S)
             _count()
         if need_grad:
-            ctx.rt, ctx.precision, ctx.chunks, ctx.stashes = rt, precision, chunks, stashes if keep else None
+            ctx.rt, ctx.precision, ctx.chunks, ctx.stashes = rt, precision, chunks, stashes
             ctx.flat, ctx.packed = flat, packed
             ctx.scales = (sc_xyz, sc_dir)
-            ctx.save_for_backward(pts, viewdirs, p12 if p12 is not None else torch.empty(0, device=dev))
+            ctx.geom_is_pts = torch.is_tensor(geom)
+            saved = (geom,) if ctx.geom_is_pts else geom
+            ctx.save_for_backward(viewdirs, p12 if p12 is not None else torch.empty(0, device=dev), *saved)
             ctx.shapes = [p.shape for p in params]
         return raw_alpha, raw_rgb
 
     @staticmethod
     def backward(ctx, g_alpha, g_rgb):
-        pts, viewdirs, p12 = ctx.saved_tensors
+        viewdirs, p12, *saved = ctx.saved_tensors
+        geom = saved[0] if ctx.geom_is_pts else tuple(saved)
         if p12.numel() == 0:
             p12 = None
         rt, precision = ctx.rt, ctx.precision
-        R, S = pts.shape[0], pts.shape[1]
-        dev = pts.device
+        R, S = g_alpha.shape if g_alpha is not None else g_rgb.shape[:2]
+        dev = viewdirs.device
         d = rt.desc(precision)
         L = _capi.lib()
         sc_xyz, sc_dir = ctx.scales
@@ -451,22 +502,23 @@ class NerfRaw(Function):
         pose_acc = torch.zeros((32,), device=dev) if p12 is not None else None
         for i, (a, b) in enumerate(ctx.chunks):
             n = (b - a) * S
-            if ctx.stashes is not None:
-                st = ctx.stashes[i]
-            else:   # recompute the forward of this ray chunk with activation stashing
+            st = ctx.stashes[i]
+            if st is None:
+                # over the stash budget, or a second backward through a retained graph (the stash of a chunk is dropped
+                # as soon as it has been used): recompute the forward of this ray chunk with activation stashing
                 st = torch.empty((L.star_stash_bytes(C.byref(d), n),), device=dev, dtype=torch.uint8)
                 tmp_a = torch.empty((b - a, S), device=dev)
                 tmp_c = torch.empty((b - a, S, 3), device=dev)
-                check(L.star_mlp_forward(C.byref(d), ptr(ctx.packed), f32(pts[a:b]), f32(viewdirs[a:b]),
+                check(L.star_mlp_forward(C.byref(d), ptr(ctx.packed), *_geom_ptrs(geom, a, b), f32(viewdirs[a:b]),
                                          f32(p12) if p12 is not None else None,
                                          f32(sc_xyz) if sc_xyz is not None else None,
                                          f32(sc_dir) if sc_dir is not None else None, b - a, S, f32(tmp_a),
-                                         f32(tmp_c), S, ptr(st), stream()), "star_mlp_forward(recompute)")
+                                         f32(tmp_c), S, ptr(st), None, stream()), "star_mlp_forward(recompute)")
                 _count()
             ws = torch.empty((L.star_mlp_backward_workspace_bytes(C.byref(d), n),), device=dev, dtype=torch.uint8)
             e0 = _prof_begin()
-            check(L.star_mlp_backward(C.byref(d), ptr(ctx.packed), f32(ctx.flat), f32(pts[a:b]), f32(viewdirs[a:b]),
-                                      f32(p12) if p12 is not None else None,
+            check(L.star_mlp_backward(C.byref(d), ptr(ctx.packed), f32(ctx.flat), *_geom_ptrs(geom, a, b),
+                                      f32(viewdirs[a:b]), f32(p12) if p12 is not None else None,
                                       f32(sc_xyz) if sc_xyz is not None else None,
                                       f32(sc_dir) if sc_dir is not None else None, b - a, S, f32(g_alpha[a:b]),
                                       f32(g_rgb[a:b]), S, ptr(st), ptr(ws), f32(grad_flat),
@@ -474,8 +526,7 @@ class NerfRaw(Function):
                   "star_mlp_backward")
             _prof_end("mlp_backward", e0, n, 4.0 * MLP_MAC_PER_SAMPLE.get(rt.n_blocks, 0) * n)   # dX + dW
             _count(3 + 2 * rt.n_blocks + 4)
-            if ctx.stashes is not None:
-                ctx.stashes[i] = None
+            ctx.stashes[i] = None
         grads, off = [], 0
         for shp in ctx.shapes:
             n = 1

@@ -16,8 +16,8 @@ def compute_2d_iou(dynamic_transmittance, semantic_mask, thres=0.1):
         raise ValueError("dynamic_transmittance must be [N_rays, num_vehicles] and semantic_mask [N_rays]")
     T = _c(dynamic_transmittance.detach())
     R, V = T.shape
-    sem = _c(semantic_mask.detach().to(device=T.device)).to(torch.uint8) if semantic_mask.dtype != torch.uint8 else \
-        _c(semantic_mask.detach().to(device=T.device))
+    # any non-zero value is True, as in np.logical_or / np.logical_and of the reference (a float mask of 0.5 counts)
+    sem = _c((semantic_mask.detach().to(device=T.device) != 0).to(torch.uint8))
     pred = torch.empty((V, R), device=T.device, dtype=torch.uint8)
     counts = torch.empty((2,), device=T.device, dtype=torch.int64)
     check(_capi.lib().star_iou2d(f32(T), ptr(sem), R, V, float(thres), ptr(pred), ptr(counts), stream()), "star_iou2d")

@@ -15,7 +15,8 @@ from .resnet import ResnetFC
 
 
 def default_precision():
-    """'fp32' (1e-4 tier, CUDA cores), 'bf16' or 'fp16' (tcgen05 tensor cores, bf16 / fp16 operands)."""
+    """'fp32' (1e-4 tier, CUDA cores), 'fp16' (tcgen05 tensor cores, fp16 operands: the 2e-3 tier) or 'bf16' (same
+    kernels, bf16 operands: wider range, 9e-3 worst case on random-init nets)."""
     return _capi.PRECISIONS[os.environ.get("STAR_B200_PRECISION", "fp32")]
 
 
@@ -49,9 +50,10 @@ class NeRF(nn.Module):
         return default_precision() if self.precision is None else self.precision
 
     def raw(self, pts, viewdirs, pose12=None, step=None):
-        """RAW outputs; pose12 moves samples into the object frame inside the kernel (K2)."""
-        sc_xyz = self.embedder.scale(step, pts.device, pad_to=64)
-        sc_dir = self.embedder_dirs.scale(step, pts.device, pad_to=32)
+        """RAW outputs; pose12 moves samples into the object frame inside the kernel (K2).
+        pts: [R,S,3], or the tuple (rays_o, rays_d, z_vals): positions formed inside the kernel."""
+        sc_xyz = self.embedder.scale(step, viewdirs.device, pad_to=64)
+        sc_dir = self.embedder_dirs.scale(step, viewdirs.device, pad_to=32)
         return F_.NerfRaw.apply(self._rt, self._prec(), torch.is_grad_enabled(), pts, viewdirs, pose12, sc_xyz, sc_dir,
                                 *self._rt.ordered_params())
 

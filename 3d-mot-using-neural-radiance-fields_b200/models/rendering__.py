@@ -106,10 +106,12 @@ def _coarse_to_fine(net_call, training, pts, z_vals, rays_o, rays_d, N_importanc
     for k, v in coarse.items():
         result[f"{k}0"] = v
     if N_importance > 0:
-        z_samples, z_all, z_std, pts_fine = F_.hierarchical(z_vals, coarse["weights"], N_importance,
-                                                            det=not training, rays_o=rays_o, rays_d=rays_d, u=u,
-                                                            z_samples=z_samples)
-        fine = net_call(pts_fine, z_all, False)
+        # the fine positions rays_o + rays_d * z (:137-139, :283-291) are never materialised: the MLP kernels form them
+        # from (rays_o, rays_d, z_all) with the reference's roundings
+        z_samples, z_all, z_std, _ = F_.hierarchical(z_vals, coarse["weights"], N_importance, det=not training,
+                                                     rays_o=rays_o, rays_d=rays_d, u=u, z_samples=z_samples,
+                                                     want_pts=False)
+        fine = net_call((rays_o, rays_d, z_all), z_all, False)
         for k, v in fine.items():
             result[k] = v
         result["z_std"] = z_std

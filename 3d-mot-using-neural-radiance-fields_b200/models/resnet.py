@@ -25,7 +25,10 @@ class ResnetBlockFC(nn.Module):
         self.shortcut = None
 
     def forward(self, x):
-        raise RuntimeError("ResnetBlockFC is evaluated inside the fused NeRF MLP kernel; call NeRF.forward")
+        # reference: models/resnet.py:51-59.  No stand-alone kernel exists for one block: the block only ever runs
+        # inside NeRF.forward (models/nerf.py:150), which is the fused kernel here.
+        raise NotImplementedError("ResnetBlockFC.forward (reference models/resnet.py:51-59) has no stand-alone B200 "
+                                  "kernel: the block is evaluated inside the fused NeRF MLP kernel; call NeRF.forward")
 
 
 class ResnetFC(nn.Module):
@@ -45,4 +48,6 @@ class ResnetFC(nn.Module):
         self.blocks = nn.ModuleList([ResnetBlockFC(d_hidden, beta=beta) for _ in range(n_blocks)])
 
     def forward(self, x):
-        raise RuntimeError("ResnetFC is evaluated inside the fused NeRF MLP kernel; call NeRF.forward")
+        # reference: models/resnet.py:103-110; only caller is NeRF.forward (models/nerf.py:150) = the fused kernel
+        raise NotImplementedError("ResnetFC.forward (reference models/resnet.py:103-110) has no stand-alone B200 "
+                                  "kernel: the trunk is evaluated inside the fused NeRF MLP kernel; call NeRF.forward")

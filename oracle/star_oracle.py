@@ -99,16 +99,29 @@ def nerf_mlp(params, prefix, pts, viewdirs, L_xyz=10, L_dir=4, step=None, end_ba
     the two heads (alpha_linear, rgb_linear) in fp32 on un-rounded activations."""
     GEMMS = ("pts_net", "feature_linear", "views_linears")
 
-    def q(t):   # emulate_bf16: False | True / "bf16" | "fp16" (the fp16-operand variant of the same kernel)
-        if not emulate_bf16:
-            return t
-        return t.half().to(t.dtype) if emulate_bf16 == "fp16" else t.bfloat16().to(t.dtype)
+    def mode_of(name):
+        # emulate_bf16: False | True / "bf16" | "fp16" (one mode for every GEMM), or a dict keyed by the layer's
+        # short name ("lin_in", "fc_0", "fc_1", "lin_out", "feature_linear", "views_linears"; missing = exact) --
+        # the per-layer form is what tools/error_budget.py uses.  Modes "bf16x2" / "fp16x2" model a split operand
+        # (hi + lo, the lo * lo product dropped: three MMAs per K-step).
+        if isinstance(emulate_bf16, dict):
+            parts = name.split(".")
+            return emulate_bf16.get(parts[-2] if parts[-1].isdigit() else parts[-1], False)
+        return "bf16" if emulate_bf16 is True else emulate_bf16
+
+    def q(t, mode):
+        return t.half().to(t.dtype) if mode.startswith("fp16") else t.bfloat16().to(t.dtype)
 
     def lin(name, h):
         w, b = params[f"{prefix}{name}.weight"], params[f"{prefix}{name}.bias"]
-        if emulate_bf16 and name.startswith(GEMMS):
-            return F.linear(q(h), q(w), b)
-        return F.linear(h, w, b)
+        mode = mode_of(name) if name.startswith(GEMMS) else False
+        if not mode:
+            return F.linear(h, w, b)
+        h1, w1 = q(h, mode), q(w, mode)
+        if mode.endswith("x2"):
+            h2, w2 = q(h - h1, mode), q(w - w1, mode)
+            return F.linear(h1, w1, b) + F.linear(h2, w1) + F.linear(h1, w2)
+        return F.linear(h1, w1, b)
 
     R, S = pts.shape[0], pts.shape[1]
     p = pts.reshape(-1, 3)

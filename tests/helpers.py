@@ -22,8 +22,17 @@ def assert_close(a, b, atol, rtol=0.0, msg=""):
     assert a.shape == b.shape, f"{msg}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
     err = (a - b).abs()
     tol = atol + rtol * b.abs()
-    bad = err > tol
-    assert not bad.any(), f"{msg}: max err {err.max().item():.3e} (tol {atol:g}+{rtol:g}*|b|), {int(bad.sum())} bad of {bad.numel()}"
+    # NaN-aware: a NaN error compares False against any tolerance, so "bad" is "not within", and a NaN / inf on one
+    # side only is always an error (identical non-finite values on both sides -- e.g. the NaN mean of an empty mask,
+    # which the reference produces too -- are equal)
+    same_nonfinite = (a == b) | (torch.isnan(a) & torch.isnan(b))
+    bad = ~((err <= tol) | same_nonfinite)
+    if bad.any():
+        fin = err[torch.isfinite(err)]
+        mx = fin.max().item() if fin.numel() else float("nan")
+        nn_ = int((~torch.isfinite(a) & ~same_nonfinite).sum())
+        raise AssertionError(f"{msg}: max err {mx:.3e} (tol {atol:g}+{rtol:g}*|b|), {int(bad.sum())} bad of "
+                             f"{bad.numel()}, {nn_} non-finite in the result")
 
 
 def psnr_db(a, b):

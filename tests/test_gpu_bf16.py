@@ -102,9 +102,12 @@ def _dev_stats(out, ref, keys):
     return res
 
 
-# (mean, 99th percentile, max) bounds on |rgb - ref| and |weights - ref|.  fp16 operands meet the north
-# star's 2e-3 in the max norm; bf16 operands meet it in the mean (measured 1.7e-3 .. 2.2e-3 on these
-# random-init fixtures, max 9e-3).
+# (mean, 99th percentile, max) bounds on |rgb - ref| and |weights - ref| against the reference fixtures.
+# "fp16" is the QUALIFIED 16-bit tier (the one bench.py reports): the north star's 2e-3 absolute in the max norm (and
+# <= 0.05 dB PSNR, below).  "bf16" keeps the same kernels with bf16 operands for networks whose activations leave
+# fp16's range; tools/error_budget.py shows that each of its 11 GEMMs alone costs 2-3e-3 on these random-init fixtures, so
+# no selective fix exists and it does NOT meet the bound (measured mean 1.7e-3 .. 2.2e-3, max 9e-3): its numbers below are
+# a regression guard, not a parity claim.
 BOUNDS = {"bf16": (3e-3, 1.2e-2, 2e-2), "fp16": (4e-4, 1.5e-3, 2e-3)}
 
 
@@ -126,10 +129,13 @@ def test_tc_e2e_eval_within_bounds(name, V, prec):
     b_mean, b_p99, b_max = BOUNDS[prec]
     for k, (mean, p99, mx) in st.items():
         assert mean < b_mean and p99 < b_p99 and mx < b_max, (k, mean, p99, mx)
+    # depth is in scene units: judged relative to the far plane (the lego-shaped fixture has far = 6 and only 16 + 24
+    # samples per ray; at C2's 64 + 128 samples the absolute error is < 1e-3, tests/test_gpu_configs.py)
     far = float(g["far"])
     for k in ("depth0", "depth"):
         e = (out[k].cpu() - g[k]).abs() / far
         assert float(e.mean()) < b_mean and float(e.max()) < b_max, (k, float(e.mean()), float(e.max()))
+    F_.check_range()
     # PSNR of the bf16 render vs the fp32 reference render itself, and the PSNR shift w.r.t. a target image
     target = torch.rand(out["rgb"].shape, generator=torch.Generator().manual_seed(1))
     shift = abs(psnr_db(out["rgb"].cpu(), target) - psnr_db(g["rgb"], target))
@@ -238,3 +244,44 @@ def test_recompute_path_matches_stash_path_and_stash_accounting(prec, monkeypatc
         assert F_._STASH_LIVE.get(torch.cuda.current_device(), 0) == 0
     for a, b in zip(grads["stash"], grads["recompute"]):
         assert float((a - b).norm()) <= 1e-4 * float(b.norm()) + 1e-9
+
+
+def test_fp16_range_guard_reports_overflow():
+    """fp16 operands overflow beyond 65504: the kernel flags non-finite raw outputs through its status word and the
+    host raises (at the next MLP call at the latest, or on demand) instead of returning garbage silently."""
+    net, _ = make_star(0, 8, 4096, False, seed=3, training=False, precision="fp16")
+    ro, rd = so.carla_rays(64, seed=1)
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    pts, _ = so.sample_pts(ro, rd, 0.03, 0.8, 16)
+    with torch.no_grad():
+        a, _ = net.static_coarse_nerf.raw(cu(pts), cu(vd), None)
+        F_.check_range()                                       # sane weights: nothing flagged
+        assert bool(torch.isfinite(a).all())
+        net.static_coarse_nerf.pts_net.lin_in.weight.mul_(3.0e4)
+        net.static_coarse_nerf.pts_net.lin_in.weight._version  # (mul_ bumped the version -> the packed image is rebuilt)
+        a, _ = net.static_coarse_nerf.raw(cu(pts), cu(vd), None)
+        with pytest.raises(_capi.StarError):
+            F_.check_range()
+        F_.check_range()                                       # the flag is cleared once reported
+        # the same weights on the bf16 tier stay finite (8-bit exponent)
+        net.set_precision("bf16")
+        a, _ = net.static_coarse_nerf.raw(cu(pts), cu(vd), None)
+        F_.check_range()
+        assert bool(torch.isfinite(a).all())
+
+
+def test_second_backward_through_a_retained_graph():
+    """backward(retain_graph=True) followed by a second backward: the stash of a chunk is dropped after its first use, the
+    second pass recomputes it -- same gradients (dW reductions use atomics: equal to rounding)."""
+    net, _ = make_star(0, 8, 4096, False, seed=3, training=True, precision="fp16")
+    ro, rd = so.carla_rays(96, seed=1)
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    pts, _ = so.sample_pts(ro, rd, 0.03, 0.8, 24)
+    a, c = net.static_coarse_nerf.raw(cu(pts), cu(vd), None)
+    loss = (a ** 2).mean() + (c ** 2).mean()
+    loss.backward(retain_graph=True)
+    g1 = [p.grad.clone() for p in net.static_coarse_nerf.parameters()]
+    net.zero_grad()
+    loss.backward()
+    for x, y in zip(g1, (p.grad for p in net.static_coarse_nerf.parameters())):
+        assert float((x - y).norm()) <= 1e-4 * float(x.norm()) + 1e-12

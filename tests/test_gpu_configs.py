@@ -54,16 +54,22 @@ def test_c1_lego_100x100_view_against_the_cpu_oracle():
     assert abs(psnr_db(out["rgb"].cpu(), ref["rgb"]) ) > 40.0
 
 
-def test_c2_full_size_render_properties_bf16():
-    net, _ = lego_net("bf16")
-    ro, rd = so.lego_rays(800, 800)
-    ro, rd = ro.reshape(-1, 3).contiguous().to(DEV), rd.reshape(-1, 3).contiguous().to(DEV)
+def test_c2_full_size_render_fp16_tier_properties_and_oracle_parity():
+    """C2 = lego 800x800, 64+128, the 16-bit tensor-core tier that the bench reports (fp16 operands).  Whole view:
+    size-independent properties.  4096 random rays of the view: against the fp32 CPU ORACLE, teacher forced with the
+    oracle's own fine samples -- the north star's bound for the 16-bit MLP: 2e-3 absolute on rgb / weights / depth
+    and <= 0.05 dB PSNR."""
+    net, sd = lego_net("fp16")
+    ro_h, rd_h = so.lego_rays(800, 800)
+    ro_h, rd_h = ro_h.reshape(-1, 3).contiguous(), rd_h.reshape(-1, 3).contiguous()
+    ro, rd = ro_h.to(DEV), rd_h.to(DEV)
     vd = rd / rd.norm(dim=-1, keepdim=True)
     R = ro.shape[0]
     assert R == 640000
     with torch.no_grad():
         pts, z = R_.sample_pts(ro, rd, NEAR, FAR, NC, is_train=False)
         out = R_.render_star_appinit(net, pts, vd, z, ro, rd, NI)
+        F_.check_range()                      # no fp16 operand overflowed anywhere in the view
         for k in ("rgb", "rgb0", "depth", "acc", "weights", "weights0", "z_std"):
             assert bool(torch.isfinite(out[k]).all()), k
         assert out["rgb"].shape == (R, 3) and out["weights"].shape == (R, NC + NI) and out["weights0"].shape == (R, NC)
@@ -79,10 +85,19 @@ def test_c2_full_size_render_properties_bf16():
         sub = R_.render_star_appinit(net, pts[idx], vd[idx], z[idx], ro[idx], rd[idx], NI)
         for k in ("rgb", "depth", "weights", "rgb0"):
             assert torch.equal(sub[k], out[k][idx]), k
-        # the same rays on the fp32 tier: the bf16 tier's deviation (north star: 2e-3 in the mean, PSNR shift <= 0.05 dB)
-        net.set_precision("fp32")
-        ref = R_.render_star_appinit(net, pts[idx], vd[idx], z[idx], ro[idx], rd[idx], NI)
-        err = (sub["rgb0"] - ref["rgb0"]).abs()
-        assert float(err.mean()) < 2e-3, float(err.mean())
-        target = torch.rand(4096, 3, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
-        assert abs(psnr_db(sub["rgb0"].cpu(), target.cpu()) - psnr_db(ref["rgb0"].cpu(), target.cpu())) < 0.05
+        # ---- the oracle (fp32, CPU) on the same 4096 rays
+        ih = idx.cpu()
+        cfg = so.StarConfig(0, NI, 8192, white_bkgd=True)
+        vd_h = rd_h[ih] / rd_h[ih].norm(dim=-1, keepdim=True)
+        pts_h, z_h = so.sample_pts(ro_h[ih], rd_h[ih], NEAR, FAR, NC, is_train=False)
+        ref = so.render_star(sd, cfg, pts_h, vd_h, z_h, ro_h[ih], rd_h[ih], NI, training=False, exact_sum=True)
+        mid = 0.5 * (z_h[..., 1:] + z_h[..., :-1])
+        zs_ref = so.sample_pdf(mid, ref["weights0"][..., 1:-1], NI, det=True, exact_sum=True)
+        forced = R_.render_star_appinit(net, pts[idx], vd[idx], z[idx], ro[idx], rd[idx], NI, z_samples=zs_ref.to(DEV))
+    for k in ("rgb0", "rgb", "weights0", "weights", "depth0", "depth", "acc"):
+        e = (forced[k].cpu() - ref[k]).abs()
+        assert float(e.max()) <= 2e-3, (k, float(e.max()), float(e.mean()))
+    target = torch.rand(4096, 3, generator=torch.Generator().manual_seed(1))
+    for k in ("rgb0", "rgb"):
+        assert abs(psnr_db(forced[k].cpu(), target) - psnr_db(ref[k], target)) <= 0.05, k
+    assert psnr_db(forced["rgb"].cpu(), ref["rgb"]) > 60.0

@@ -478,6 +478,14 @@ def test_rays_are_independent_and_chunking_is_invisible():
 
 
 # ------------------------------------------------------------------------------------------ a2 (8f-1)
+def test_get_rays_kernel_matches_reference_fixture():
+    """star_get_rays against the reference's own get_rays output (tests/golden/get_rays.npz), bit for bit."""
+    g = load_golden("get_rays")
+    H, W = int(g["H"]), int(g["W"])
+    ro, rd = R_.get_rays(H, W, g["K"], cu(g["c2w"]))
+    assert torch.equal(ro.cpu(), g["rays_o"]) and torch.equal(rd.cpu(), g["rays_d"])
+
+
 @pytest.mark.parametrize("H,W", [(100, 100), (37, 53), (720, 1280)])
 def test_get_rays_kernel_bit_exact(H, W):
     focal = 0.5 * W / math.tan(0.5 * 0.6911112)

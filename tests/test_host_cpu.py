@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libstar_b200.so does not export {name}"
     assert declared == set(_capi.EXPORTED_SYMBOLS), declared ^ set(_capi.EXPORTED_SYMBOLS)
-    assert lib.star_abi_version() == 1
+    assert lib.star_abi_version() == _capi.ABI_VERSION
 
 
 def test_param_counts_and_packed_sizes():
@@ -183,7 +183,7 @@ def test_c_abi_argument_checks_need_no_gpu():
     assert lib.star_mip_pack_weights(7, C.c_void_p(16), None, C.c_void_p(16), None) == 2                    # STAR_E_UNSUPPORTED
     assert lib.star_error_string(2).decode().startswith("unsupported")
     d = _capi.net_desc(4, 10, 4, _capi.PREC_F32)
-    assert lib.star_mlp_forward(C.byref(d), None, None, None, None, None, None, 4, 8, None, None, 8, None, None) == 3
+    assert lib.star_mlp_forward(C.byref(d), None, None, None, None, None, None, None, None, None, 4, 8, None, None, 8, None, None, None) == 3
 
 
 def test_train_step_abi_argument_checks_and_host_logic():

@@ -29,6 +29,20 @@ def test_sample_pts():
     assert torch.equal(z, g["z_perturb"]) and torch.equal(pts, g["pts_perturb"])
 
 
+def test_get_rays():
+    """oracle.get_rays and the host mirrors against the reference's get_rays / get_rays_np (rendering__.py:41-71)."""
+    import star_b200
+    from star_b200.models import rendering__ as R_
+    g = load_golden("get_rays")
+    H, W = int(g["H"]), int(g["W"])
+    ro, rd = so.get_rays(H, W, g["K"], g["c2w"])
+    assert torch.equal(ro, g["rays_o"]) and torch.equal(rd, g["rays_d"])
+    ro, rd = R_.get_rays(H, W, g["K"], g["c2w"])           # host branch of the mirror (dataset preparation)
+    assert torch.equal(ro, g["rays_o"]) and torch.equal(rd, g["rays_d"])
+    ro_np, rd_np = R_.get_rays_np(H, W, g["K"].numpy(), g["c2w"].numpy())
+    assert (ro_np == g["rays_o_np"].numpy()).all() and (rd_np == g["rays_d_np"].numpy()).all()
+
+
 def test_raw2outputs():
     g = load_golden("raw2outputs")
     for tag, white in (("white.", True), ("black.", False)):

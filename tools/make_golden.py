@@ -53,8 +53,25 @@ def grad_digest(named_params):
     return out
 
 
+def rays_fixture(ref):
+    """get_rays / get_rays_np (rendering__.py:41-71) on a non-square view with an off-centre principal point."""
+    import math
+    H, W = 37, 53
+    focal = 0.5 * W / math.tan(0.5 * 0.6911112)
+    K = torch.tensor([[focal, 0, 0.5 * W], [0, focal * 1.01, 0.5 * H - 0.25], [0, 0, 1.0]])
+    g = torch.Generator().manual_seed(5)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+    c2w = torch.cat([q, torch.randn(3, 1, generator=g)], 1)
+    ro, rd = ref.rendering.get_rays(H, W, K, c2w)
+    ro_np, rd_np = ref.rendering.get_rays_np(H, W, K.numpy(), c2w.numpy())
+    npz("get_rays", H=H, W=W, K=K, c2w=c2w, rays_o=ro, rays_d=rd, rays_o_np=np.ascontiguousarray(ro_np), rays_d_np=rd_np)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--only-rays" in sys.argv:      # added after the other fixtures were committed: leaves them untouched
+        rays_fixture(ref_harness.load_reference())
+        return
     torch.set_num_threads(8)
     torch.set_float32_matmul_precision("highest")
     ref = ref_harness.load_reference()
@@ -217,6 +234,7 @@ def main():
         online_case("e2e_online_mat_eval", so.pose7_to_matrix, False, 4096, seed=6)
     # 7-vector pose: goes through the pypose STUB (third-party semantics restated; parity unpinned)
     online_case("e2e_online_quat_train", lambda p: p, True, 4096, seed=6)
+    rays_fixture(ref)
 
 
 if __name__ == "__main__":
