@@ -113,10 +113,11 @@ __device__ __forceinline__ void fold_jacobian(const uint32_t (&r)[16], const flo
 }
 
 // ============================================================================================ dX chain
-// GF16: format of the back-propagated gradients G_l (A operand here and in dW; false = bf16 -- the production choice for
-// both tiers: dL/d(activation) of a 4096-ray batch reaches 1e-8, below fp16's subnormal range); WF16: format of the
-// weights (B operand), the forward tier's.
-template <bool GF16, bool WF16, bool POSE>
+// The backward pass computes in bf16 on BOTH 16-bit tiers: dL/d(activation) of a 4096-ray batch reaches 1e-8, far below
+// fp16's range, and kind::f16 does not take mixed operand formats (bf16 x fp16 raises an illegal-instruction fault on
+// B200: tools/umma_probe.cu).  So the gradients G_l and the transposed weight stream are bf16 here, and the dW kernel
+// converts the fp16 tier's stashed activations to bf16 in shared memory (dw_tc_kernel<CVT>).
+template <bool POSE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const StarPtsSrc pts,
                   const float* __restrict__ viewdirs, const float* __restrict__ pose12,
@@ -263,7 +264,7 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           }
           mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
           tc_fence_after();
-          const uint32_t idesc = umma_idesc_ab(TC_M, s.N, GF16 ? 0 : 1, WF16 ? 0 : 1);
+          const uint32_t idesc = umma_idesc_16(TC_M, s.N, 1);
           const uint64_t a0 = desc_a0 + (uint64_t)(s.a_kb * (TC_KB_BYTES >> 4));
           const uint64_t b0 = desc_w0 + (uint64_t)(stage * (TC_STAGE_BYTES >> 4));
           if (elect_one_sync()) {
@@ -446,7 +447,7 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             for (int j = 0; j < 16; ++j) v[j] = 0.f;
           }
           // (the gstash copy of this block is a bulk store issued by the producer warp once the block is complete)
-          store_row16<GF16, false>(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, v);
+          store_row16<false, false>(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, v);
           fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
@@ -500,8 +501,10 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t 
   return d;
 }
 
-// GF16 / AF16: formats of the gradient blocks (A operand) and of the activation blocks (B operand; the forward tier's)
-template <bool GF16, bool AF16>
+// CVT (fp16 tier): the activation blocks arrive as fp16 (what the forward multiplied) and are converted to bf16 in place
+// by the four epilogue warps, which are otherwise idle until the last tile, before the MMAs read them: the kernel is
+// HBM-bound (a stage of up to 96 KB lands every ~4000 cycles; the conversion is ~450 issue cycles per scheduler).
+template <bool CVT>
 __global__ void __launch_bounds__(DW_THREADS, 1)
 dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8_t* __restrict__ stash,
              const uint8_t* __restrict__ gstash, int64_t ntiles, float* __restrict__ grad_flat, int* dbg) {
@@ -512,7 +515,7 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
   const uint32_t sStage = base, sOnes = base + DW_NSTAGE * DW_STAGE_BLOCKS * TC_BLOCK_BYTES;
   const uint32_t sBars = sOnes + TC_BLOCK_BYTES;
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(gbase + (sBars - base) + 64);
-  auto bar = [&](int i) -> uint32_t { return sBars + 8u * (uint32_t)i; };   // 0,1 full; 2,3 empty; 4 done
+  auto bar = [&](int i) -> uint32_t { return sBars + 8u * (uint32_t)i; };   // 0,1 full; 2,3 empty; 4 done; 5,6 converted
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int item_id = blockIdx.x / plan.splits, split = blockIdx.x % plan.splits;
   const DwItem it = plan.it[item_id];
@@ -522,6 +525,7 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
   if (tid == 0) {
     for (int i = 0; i < 2 * DW_NSTAGE; ++i) mbar_init(bar(i), 1);
     mbar_init(bar(4), 1);
+    for (int i = 0; i < DW_NSTAGE; ++i) mbar_init(bar(5 + i), 4);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(sBars + 64, 512);
@@ -529,7 +533,7 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
   for (int i = tid; i < TC_BLOCK_BYTES / 16; i += DW_THREADS) {
     const int r = i >> 3, c = i & 7;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (c == (r & 7)) v.x = AF16 ? 0x3C00u : 0x3F80u;
+    if (c == (r & 7)) v.x = 0x3F80u;     // bf16 1.0
     reinterpret_cast<uint4*>(gbase + (sOnes - base))[i] = v;
   }
   fence_proxy_async_smem();
@@ -556,15 +560,14 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
     // warp-uniform control flow, one elected lane issues the tcgen05 instructions (see elect_one_sync)
     {
       const int N = 64 * it.n_a;
-      const int gf = GF16 ? 0 : 1, af = AF16 ? 0 : 1;
-      const uint32_t idesc = umma_idesc_ab(128, N, gf, af) | (1u << 15) | (1u << 16);      // both operands MN-major
-      const uint32_t idesc1 = umma_idesc_ab(128, 16, gf, af) | (1u << 15) | (1u << 16);
+      const uint32_t idesc = umma_idesc_16(128, N, 1) | (1u << 15) | (1u << 16);      // bf16, both operands MN-major
+      const uint32_t idesc1 = umma_idesc_16(128, 16, 1) | (1u << 15) | (1u << 16);
       const bool with_bias = it.b_off >= 0;
       const uint64_t d1 = umma_desc_mn_sw128(sOnes, TC_BLOCK_BYTES);
       uint32_t st = 0, ph = 0;
       uint32_t acc = 0u;
       for (int64_t t = t0; t < t1; ++t) {
-        mbar_wait(bar(st), ph, dbg, 2);
+        mbar_wait(bar(CVT ? 5 + st : st), ph, dbg, 2);
         tc_fence_after();
         const uint32_t g_addr = sStage + st * DW_STAGE_BLOCKS * TC_BLOCK_BYTES, a_addr = g_addr + 2 * TC_BLOCK_BYTES;
         const uint64_t dg = umma_desc_mn_sw128(g_addr, TC_BLOCK_BYTES), da = umma_desc_mn_sw128(a_addr, TC_BLOCK_BYTES);
@@ -588,6 +591,28 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
       }
     }
   } else {
+    if (CVT) {   // fp16 -> bf16 of the stage's activation blocks, in step with the producer
+      uint32_t st = 0, ph = 0;
+      const int nvec = it.n_a * (TC_BLOCK_BYTES / 16);
+      for (int64_t t = t0; t < t1; ++t) {
+        mbar_wait(bar(st), ph, dbg, 5);
+        uint4* a = reinterpret_cast<uint4*>(gbase + (size_t)st * DW_STAGE_BLOCKS * TC_BLOCK_BYTES + 2 * TC_BLOCK_BYTES);
+        for (int i = tid - 64; i < nvec; i += DW_THREADS - 64) {
+          uint4 v = a[i];
+          uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+            w[j] = pack_16x2<false, false>(f.x, f.y);
+          }
+          a[i] = v;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(5 + st));
+        if (++st == DW_NSTAGE) { st = 0; ph ^= 1u; }
+      }
+    }
     // epilogue: TMEM -> registers -> atomics into the flat gradient
     const int q = warp & 3;
     const int n = q * 32 + lane;                      // output feature within the half
@@ -785,8 +810,7 @@ int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed
   {
     const int grid = (int)(ntiles < sms ? ntiles : sms);
     const BwdSmem sl = bwd_smem_layout(tl.small_bytes);
-    auto kern = pose12 != nullptr ? (fp16 ? mlp_bwd_tc_kernel<false, true, true> : mlp_bwd_tc_kernel<false, false, true>)
-                                  : (fp16 ? mlp_bwd_tc_kernel<false, true, false> : mlp_bwd_tc_kernel<false, false, false>);
+    auto kern = pose12 != nullptr ? mlp_bwd_tc_kernel<true> : mlp_bwd_tc_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
     if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
     kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
@@ -824,7 +848,7 @@ int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed
     if ((int64_t)splits > ntiles) splits = (int)ntiles;
     plan.splits = splits;
     const size_t smem = (size_t)(DW_NSTAGE * DW_STAGE_BLOCKS + 1) * TC_BLOCK_BYTES + 256 + 1024;
-    auto kern = fp16 ? dw_tc_kernel<false, true> : dw_tc_kernel<false, false>;
+    auto kern = fp16 ? dw_tc_kernel<true> : dw_tc_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
     kern<<<n * splits, DW_THREADS, smem, st>>>(plan, tl.stash_blocks, tl.gstash_blocks, (const uint8_t*)stash,

@@ -182,13 +182,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_16(int M, int N, int fmt) {
          ((uint32_t)(M >> 4) << 24);
 }
 
-// same with separate operand formats (0 = fp16, 1 = bf16): kind::f16 takes any combination (tools/umma_probe.cu checks
-// bf16 x fp16 on the hardware) -- the gradient GEMMs of the fp16 tier multiply bf16 gradients (range) with fp16 weights
-// and activations (precision)
-__host__ __device__ constexpr uint32_t umma_idesc_ab(int M, int N, int afmt, int bfmt) {
-  return (1u << 4) | ((uint32_t)afmt << 7) | ((uint32_t)bfmt << 10) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
-}
+// (A and B must share the format: kind::f16 with a_format != b_format -- bf16 x fp16 -- raises an illegal-instruction
+//  fault on B200, tools/umma_probe.cu)
 
 // byte offset of element (row, k) inside one [rows][64] bf16 SW128 K-block
 __host__ __device__ __forceinline__ uint32_t sw128_off(int row, int k) {

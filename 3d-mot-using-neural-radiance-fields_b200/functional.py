@@ -311,6 +311,10 @@ class NetRuntime:
         self._key = None
         self._flat = None
         self._packed = {}
+        # parallel.GradSync: flat gradient range of this net (the backward kernels accumulate straight into it) and the
+        # object told when a forward starts / a backward has been launched
+        self.grad_sink = None
+        self.sink_owner = None
 
     def ordered_params(self):
         m = self.module
@@ -475,6 +479,8 @@ class NerfRaw(Function):
                       2.0 * MLP_MAC_PER_SAMPLE.get(rt.n_blocks, 0) * (b - a) * S)
             _count()
         if need_grad:
+            if rt.sink_owner is not None:
+                rt.sink_owner.on_forward(rt)
             ctx.rt, ctx.precision, ctx.chunks, ctx.stashes = rt, precision, chunks, stashes
             ctx.flat, ctx.packed = flat, packed
             ctx.scales = (sc_xyz, sc_dir)
@@ -498,7 +504,8 @@ class NerfRaw(Function):
         sc_xyz, sc_dir = ctx.scales
         g_alpha = torch.zeros((R, S), device=dev) if g_alpha is None else _c(g_alpha)
         g_rgb = torch.zeros((R, S, 3), device=dev) if g_rgb is None else _c(g_rgb)
-        grad_flat = torch.zeros_like(ctx.flat)
+        sink = rt.grad_sink if (rt.grad_sink is not None and rt.grad_sink.numel() == ctx.flat.numel()) else None
+        grad_flat = sink if sink is not None else torch.zeros_like(ctx.flat)
         pose_acc = torch.zeros((32,), device=dev) if p12 is not None else None
         for i, (a, b) in enumerate(ctx.chunks):
             n = (b - a) * S
@@ -528,12 +535,16 @@ class NerfRaw(Function):
             _count(3 + 2 * rt.n_blocks + 4)
             ctx.stashes[i] = None
         grads, off = [], 0
-        for shp in ctx.shapes:
-            n = 1
-            for s_ in shp:
-                n *= s_
-            grads.append(grad_flat[off:off + n].view(shp))
-            off += n
+        if sink is not None:     # the parameters' .grad are views of the sink: nothing to hand to autograd
+            grads = [None] * len(ctx.shapes)
+            rt.sink_owner.on_backward_launched(rt)
+        else:
+            for shp in ctx.shapes:
+                n = 1
+                for s_ in shp:
+                    n *= s_
+                grads.append(grad_flat[off:off + n].view(shp))
+                off += n
         g_pose = None
         if p12 is not None and ctx.needs_input_grad[5]:
             # Euclidean gradient w.r.t. [R | t]:  dR = sum g p^T + sum h d^T,  dt = sum g

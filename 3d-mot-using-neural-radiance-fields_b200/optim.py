@@ -236,4 +236,5 @@ def flatten_parameters(module):
             flat[off:off + n].copy_(p.detach().reshape(-1))
             p.data = flat[off:off + n].view(p.shape)
             off += n
+    module._star_flat = (flat, uniq)       # parallel.GradSync lays the gradients out the same way
     return flat

@@ -67,9 +67,9 @@ def allreduce_gradients(params, average=True, group=None):
     average=True divides by the world size: with equal ray shards the mean of per-rank mean losses is the global
     mean loss.  Every rank must hold the same parameter list with the same gradient layout."""
     params = [p for p in params if p.requires_grad]
-    if not params:
-        return None
     _, w = world()
+    if not params or w == 1:
+        return None                # single process: nothing to exchange, and no .grad is materialised
     runs = _grad_runs(params)
     if runs is not None:
         if w > 1:
@@ -78,21 +78,169 @@ def allreduce_gradients(params, average=True, group=None):
                 if average:
                     r.div_(w)
         return runs
-    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params])
-    if w > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        if average:
-            flat.div_(w)
+    # Parameters without a gradient contribute zeros so that all ranks agree on the layout; a presence count travels
+    # with the buffer, and a parameter that NO rank has a gradient for keeps .grad = None -- the single-process
+    # reference skips such parameters in Adam (no step count, no momentum decay), and so must every rank here.
+    have = torch.tensor([0.0 if p.grad is None else 1.0 for p in params], device=params[0].device)
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params]
+                     + [have])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    present = flat[-len(params):] > 0
+    present = present.tolist()
+    if average:
+        flat.div_(w)
     off = 0
-    for p in params:
+    for p, any_rank in zip(params, present):
         n = p.numel()
-        g = flat[off:off + n].view_as(p).to(p.dtype)
-        if p.grad is None:
-            p.grad = g.clone()
-        else:
-            p.grad.copy_(g)
+        if any_rank:
+            g = flat[off:off + n].view_as(p).to(p.dtype)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
         off += n
-    return flat
+    return flat[:-len(params)]
+
+
+class GradSync:
+    """Gradient exchange of a ray-sharded training step, overlapped with the backward pass (one
+    all-reduce(sum) over the flat fp32 gradient per optimiser step, before gradient clipping, train_online__.py:1170).
+
+        sync = GradSync(net, extra_params=[pose])        # after .cuda(), BEFORE the optimiser is built
+        loss = sync.scale_loss(loss); loss.backward(); sync.finish(); optimiser.step()
+
+    * parameters are re-homed into one flat buffer (optim.flatten_parameters) and every .grad becomes a view into ONE
+      flat gradient buffer of the same layout, so a net's gradient is one contiguous range and the whole model one run
+      for FusedAdam / clip_grad_norm_;
+    * the MLP backward kernels accumulate straight into that buffer (functional.NerfRaw: the net's `grad_sink`), and as
+      soon as a net's backward has been launched its range is all-reduced on a side stream: the fine net's collective
+      runs under the coarse net's backward, only the last one is exposed;
+    * averaging costs nothing: scale_loss() multiplies the loss by 1 / world_size, so the summed gradients are the mean;
+    * finish() reduces what is left (nets whose backward did not run, other parameters, `extra_params` such as the
+      pose vector) in one more collective and makes the current stream wait for all of them.  No host synchronisation.
+    The buffer is zeroed by the first forward after finish(), i.e. gradient accumulation over several backward passes
+    per optimiser step works; zero_grad(set_to_none=True) by a trainer is tolerated (views are re-attached in finish)."""
+
+    def __init__(self, module, extra_params=(), group=None, overlap=True):
+        from . import optim
+        self.overlap = overlap           # False: reduce everything in finish() (several backward passes per step)
+        if getattr(module, "_star_flat", None) is None:
+            optim.flatten_parameters(module)
+        self.flat, self.order = module._star_flat
+        self.group = group
+        self.extra = [p for p in extra_params if p.requires_grad]
+        self.flat_grad = torch.zeros_like(self.flat)
+        self.views, off = [], 0
+        index = {}
+        for p in self.order:
+            n = p.numel()
+            v = self.flat_grad[off:off + n].view(p.shape)
+            self.views.append(v)
+            index[id(p)] = (off, off + n)
+            if p.requires_grad:
+                p.grad = v
+            off += n
+        self.n_flat = off
+        # nets: contiguous ranges in the kernels' master order -> gradient sinks
+        self.sinks = []
+        for m in module.modules():
+            rt = getattr(m, "_rt", None)
+            if rt is None or not hasattr(rt, "ordered_params"):
+                continue
+            ps = rt.ordered_params()
+            a, b = index[id(ps[0])][0], index[id(ps[-1])][1]
+            if b - a != sum(q.numel() for q in ps) or not all(q.requires_grad for q in ps):
+                continue
+            rt.grad_sink, rt.sink_owner = self.flat_grad[a:b], self
+            self.sinks.append((rt, a, b))
+        self.stream = torch.cuda.Stream(self.flat.device) if self.flat.is_cuda else None
+        self._works, self._done, self._dirty = [], set(), False
+
+    # ---- hooks called by functional.NerfRaw
+    def on_forward(self, rt):
+        if self._dirty:                      # first forward of a new optimiser step
+            self.flat_grad.zero_()
+            for p in self.extra:
+                p.grad = None
+            self._dirty = False
+            self._done = set()
+        elif rt is not None and id(rt) in self._done:
+            raise RuntimeError("GradSync: a net runs forward again while its gradient of this step is already being "
+                               "all-reduced; with several backward passes per optimiser step use GradSync(overlap=False)")
+
+    def on_backward_launched(self, rt):
+        """All kernels that write rt.grad_sink are queued on the current stream: reduce it behind them, on the side."""
+        _, w = world()
+        if w == 1 or not self.overlap or id(rt) in self._done:
+            return
+        self._done.add(id(rt))
+        self._reduce_async(rt.grad_sink)
+
+    def _reduce_async(self, t):
+        if self.stream is None:
+            self._works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            self._works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    # ---- user side
+    def scale_loss(self, loss):
+        _, w = world()
+        return loss if w == 1 else loss * (1.0 / w)
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+        for p in self.extra:
+            p.grad = None
+        self._dirty, self._done = False, set()
+        for p, v in zip(self.order, self.views):
+            if p.requires_grad:
+                p.grad = v
+
+    def finish(self):
+        _, w = world()
+        # a trainer may have dropped the views (zero_grad(set_to_none=True)): fold what autograd allocated back in
+        for p, v in zip(self.order, self.views):
+            if not p.requires_grad:
+                continue
+            g = p.grad
+            if g is None or g.data_ptr() != v.data_ptr():
+                if g is not None:
+                    v.add_(g)
+                p.grad = v
+        if w > 1:
+            # everything outside the ranges already in flight, as contiguous pieces of the flat buffer
+            pieces, pos = [], 0
+            for rt, a, b in sorted(self.sinks, key=lambda r: r[1]):
+                if id(rt) in self._done:
+                    if a > pos:
+                        pieces.append((pos, a))
+                    pos = max(pos, b)
+            if pos < self.n_flat:
+                pieces.append((pos, self.n_flat))
+            for a, b in pieces:
+                self._reduce_async(self.flat_grad[a:b])
+            ex = [p for p in self.extra]
+            if ex:
+                buf = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in ex])
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+                off = 0
+                for p in ex:
+                    n = p.numel()
+                    g = buf[off:off + n].view_as(p)
+                    if p.grad is None:
+                        p.grad = g.clone()
+                    else:
+                        p.grad.copy_(g)
+                    off += n
+            for wk in self._works:
+                wk.wait()                    # current stream waits for the collective; the host does not
+        self._works = []
+        self._dirty = True
+        return self.flat_grad
 
 
 def allreduce_scalars(values, average=True, group=None):

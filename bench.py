@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the STaR / NeRF render hot path (BASELINE.json metric: rays/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode render|train] [--precision bf16|fp32]
-    python bench.py --impl reference ...      # the reference algorithm on the host cores (oracle port)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode render|train] [--precision fp16|bf16|fp32]
+    python bench.py --impl reference ...      # the reference itself (oracle/_ref) on the host cores; oracle port if absent
 
 Workload (BASELINE.json configs[1], "C2"): lego-shaped vanilla NeRF, coarse+fine 64+128 samples,
 random-init weights (fc_1 re-drawn), perturb=0, white background.
@@ -11,7 +11,11 @@ random-init weights (fc_1 re-drawn), perturb=0, white background.
 `value` is device-timed with the rays already resident in HBM; `e2e` goes through the same public
 API from pinned HOST buffers (H2D of the rays and D2H of rgb/depth/acc inside the timed region).
 With N>1 (torchrun, one process per GPU) every rank renders its own view / batch (rays shard with no
-data-path collective; "weak" scaling); train mode all-reduces the flat gradient with NCCL.
+data-path collective; "weak" scaling); train mode all-reduces the flat gradient with NCCL, overlapped with the
+backward of the other net.  The default line (C2 render) also carries sub-records: "train" (C2 4096-ray step, with
+and without the optimiser), "c4_train" / "c4_render" (static + 5 objects), "c5_render" (mip field), "strong" (N > 1: one
+view and one batch SPLIT over the ranks), "accuracy" (max error of the benched tier against the fp32 oracle) and, at N = 1,
+"gpu_eager_baseline" (the reference's eager PyTorch code on the same GPU).
 """
 import argparse
 import json
@@ -46,7 +50,9 @@ def parse():
                          "(static + 5 objects, 256+256 samples, 7-vector poses); c5: carla_star_app_init_mip (mip-NeRF "
                          "fields, 256+512 frustums).  c4 / c5 are extra measurements; the driver runs c2.")
     ap.add_argument("--rays", type=int, default=0, help="c4 / c5: rays per step per GPU (0 = default of the workload)")
-    ap.add_argument("--precision", default=os.environ.get("STAR_B200_PRECISION", "bf16"), choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("STAR_B200_PRECISION", "fp16"), choices=["bf16", "fp16", "fp32"],
+                    help="MLP tier: fp16 = tcgen05, fp16 operands / fp32 accumulate (the tier that meets the 2e-3 bound; "
+                         "default), bf16 = same kernels with bf16 operands, fp32 = CUDA-core 1e-4 tier")
     ap.add_argument("--hw", type=int, default=RENDER_HW, help="render mode: view is hw x hw rays")
     ap.add_argument("--train-rays", type=int, default=TRAIN_RAYS)
     ap.add_argument("--cpu-sample-rays", type=int, default=0, help="rays of the bounded CPU sample (0 = auto)")
@@ -55,6 +61,8 @@ def parse():
                     help="train mode: include gradient clipping + the fused Adam step (and the weight re-pack) in the step")
     ap.add_argument("--no-train-extra", action="store_true",
                     help="render mode: skip the extra 4096-ray training-step measurement reported under \"train\"")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the c4 / c5 / strong-scaling / accuracy / eager-GPU sub-records of the default line")
     return ap.parse_args()
 
 
@@ -118,49 +126,122 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def cpu_render_rays_per_s(n_rays, threads, repeat=1):
-    """The reference algorithm (oracle port: same eager ATen ops as the reference's PyTorch code) on the
-    host cores: render `n_rays` rays of the C2 view, coarse+fine, eval mode."""
-    from oracle import star_oracle as so
-    torch.set_num_threads(threads)
-    p = make_params()
-    cfg = so.StarConfig(0, NI, 8192, white_bkgd=True)
+def _reference_modules():
+    """The reference's own code (oracle/_ref: its hot-path files, unmodified) when present, else None (-> oracle port)."""
+    from oracle import ref_harness
+    if not ref_harness.reference_available():
+        return None
+    return ref_harness.load_reference()
+
+
+def _c2_sample(n_rays, seed=0):
     ro, rd = lego_view(RENDER_HW)
-    g = torch.Generator().manual_seed(0)
+    g = torch.Generator().manual_seed(seed)
     idx = torch.randperm(ro.shape[0], generator=g)[:n_rays]
     ro, rd = ro[idx].contiguous(), rd[idx].contiguous()
-    vd = rd / rd.norm(dim=-1, keepdim=True)
+    return ro, rd, rd / rd.norm(dim=-1, keepdim=True), g
+
+
+def reference_render_fn(device="cpu"):
+    """-> (kind, fn): fn(ro, rd, vd) renders C2 rays (coarse+fine 64+128, eval) with the reference's eager PyTorch code
+    (kind "reference": models/rendering__.py::render_star_appinit on models/star__.py::STaR, unmodified) or, when
+    oracle/_ref is absent, with the oracle port (same ATen ops)."""
+    from oracle import ref_harness, star_oracle as so
+    ref = _reference_modules()
+    if ref is not None:
+        net = ref.star.STaR(ref_harness.make_args(num_vehicles=0, N_importance=NI, chunk=8192, white_bkgd=True))
+        net.load_state_dict(make_params())
+        net.to(device).eval()
+
+        def fn(ro, rd, vd):
+            pts, z = ref.rendering.sample_pts(ro, rd, NEAR, FAR, NC, perturb=0, is_train=False)
+            return ref.rendering.render_star_appinit(net, pts, vd, z, ro, rd, NI)
+        return "reference", fn
+    p = {k: v.to(device) for k, v in make_params().items()}
+    cfg = so.StarConfig(0, NI, 8192, white_bkgd=True)
+
+    def fn(ro, rd, vd):
+        pts, z = so.sample_pts(ro, rd, NEAR, FAR, NC, is_train=False)
+        return so.render_star(p, cfg, pts, vd, z, ro, rd, NI, training=False)
+    return "port", fn
+
+
+def cpu_render_rays_per_s(n_rays, threads, repeat=1):
+    """The reference on the host cores: render `n_rays` rays of the C2 view, coarse+fine, eval mode."""
+    torch.set_num_threads(threads)
+    kind, fn = reference_render_fn("cpu")
+    ro, rd, vd, _ = _c2_sample(n_rays)
     best = None
     with torch.no_grad():
         for _ in range(repeat):
             t0 = time.perf_counter()
-            pts, z = so.sample_pts(ro, rd, NEAR, FAR, NC, is_train=False)
-            out = so.render_star(p, cfg, pts, vd, z, ro, rd, NI, training=False)
+            out = fn(ro, rd, vd)
             float(out["rgb"].sum())
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
-    return n_rays / best, best
+    return n_rays / best, best, kind
 
 
 def cpu_train_rays_per_s(n_rays, threads):
-    from oracle import star_oracle as so
+    from oracle import ref_harness, star_oracle as so
     torch.set_num_threads(threads)
-    p = {k: v.requires_grad_(True) for k, v in make_params().items()}
-    cfg = so.StarConfig(0, NI, 8192, white_bkgd=True)
-    ro, rd = lego_view(RENDER_HW)
-    g = torch.Generator().manual_seed(0)
-    idx = torch.randperm(ro.shape[0], generator=g)[:n_rays]
-    ro, rd = ro[idx].contiguous(), rd[idx].contiguous()
-    vd = rd / rd.norm(dim=-1, keepdim=True)
-    u = torch.rand(n_rays, NI, generator=g)
+    ro, rd, vd, g = _c2_sample(n_rays)
     target = torch.rand(n_rays, 3, generator=g)
+    ref = _reference_modules()
     t0 = time.perf_counter()
-    pts, z = so.sample_pts(ro, rd, NEAR, FAR, NC)
-    out = so.render_star(p, cfg, pts, vd, z, ro, rd, NI, training=True, u=u)
+    if ref is not None:      # the reference draws sample_pdf's u itself in train mode (rendering__.py:741)
+        kind = "reference"
+        net = ref.star.STaR(ref_harness.make_args(num_vehicles=0, N_importance=NI, chunk=8192, white_bkgd=True))
+        net.load_state_dict(make_params())
+        net.train()
+        t0 = time.perf_counter()
+        pts, z = ref.rendering.sample_pts(ro, rd, NEAR, FAR, NC, perturb=0, is_train=True)
+        out = ref.rendering.render_star_appinit(net, pts, vd, z, ro, rd, NI)
+    else:
+        kind = "port"
+        p = {k: v.requires_grad_(True) for k, v in make_params().items()}
+        cfg = so.StarConfig(0, NI, 8192, white_bkgd=True)
+        u = torch.rand(n_rays, NI, generator=g)
+        t0 = time.perf_counter()
+        pts, z = so.sample_pts(ro, rd, NEAR, FAR, NC)
+        out = so.render_star(p, cfg, pts, vd, z, ro, rd, NI, training=True, u=u)
     loss = ((out["rgb"] - target) ** 2).mean() + ((out["rgb0"] - target) ** 2).mean()
     loss.backward()
     dt = time.perf_counter() - t0
-    return n_rays / dt, dt
+    return n_rays / dt, dt, kind
+
+
+def gpu_eager_baseline(dev, n_rays=65536):
+    """The reference's eager PyTorch path ON THE SAME GPU ("the real bar"): C2 render of `n_rays` rays at
+    float32 matmul precision "highest" (what its fp32 results mean) and "medium" (utils/io.py:487-494 lets the user
+    pick; TF32 tensor cores).  Device-timed, 1 warm-up + 2 runs each."""
+    res = {}
+    saved = torch.get_float32_matmul_precision()
+    try:
+        with torch.device(dev):          # the reference creates a few constants without device= (rendering__.py:321,335)
+            kind, fn = reference_render_fn(dev)
+            ro, rd, vd, _ = _c2_sample(n_rays)
+            ro, rd, vd = ro.to(dev), rd.to(dev), vd.to(dev)
+            for prec in ("highest", "medium"):
+                torch.set_float32_matmul_precision(prec)
+                best = None
+                with torch.no_grad():
+                    for i in range(3):
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        out = fn(ro, rd, vd)
+                        e1.record()
+                        torch.cuda.synchronize()
+                        if i:
+                            t = e0.elapsed_time(e1)
+                            best = t if best is None else min(best, t)
+                res[prec] = {"value": n_rays / (best * 1e-3), "unit": "rays/s", "ms": best}
+        res.update({"kind": kind, "sample": "%d random rays of the C2 view, eager PyTorch on cuda" % n_rays})
+    except Exception as e:       # reported, never fatal: this is context, not the product
+        res = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    finally:
+        torch.set_float32_matmul_precision(saved)
+    return res
 
 
 def run_reference(args):
@@ -173,9 +254,11 @@ def run_reference(args):
     fn = cpu_render_rays_per_s if args.mode == "render" else cpu_train_rays_per_s
     for _ in range(min(args.warmup, 1)):
         fn(max(64, n // 8), threads)
-    times = []
+    times, kind = [], "port"
     for _ in range(args.steps):
-        times.append(fn(n, threads)[1])
+        r = fn(n, threads)
+        times.append(r[1])
+        kind = r[2]
     dt = sum(times) / len(times)
     val = n / dt
     line = {
@@ -183,7 +266,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, "fp32"),
-        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": kind,
                          "sample": "%d random rays of the %s workload per step" % (n, args.mode)},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -514,8 +597,8 @@ def measure(args):
             n = args.cpu_sample_rays or cpu_sample_default(args.mode, threads)
             fn = cpu_train_rays_per_s if train else cpu_render_rays_per_s
             fn(max(64, n // 8), threads)
-            v, dt = fn(n, threads)
-            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": "port",
+            v, dt, kind = fn(n, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": threads, "kind": kind,
                                     "sample": "%d random rays of the same workload, %.1f s" % (n, dt)}
         return line
     return None

@@ -31,7 +31,18 @@ import argparse
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("STAR_REFERENCE_ROOT", "/root/reference")
+def _find_reference_root():
+    """The mounted reference tree (build container), else oracle/_ref/ -- the reference's own hot-path files placed there
+    unmodified by oracle/make_ref.py (git-ignored; travels to the GPU box with the snapshot)."""
+    cands = [os.environ.get("STAR_REFERENCE_ROOT"), "/root/reference",
+             os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "models", "rendering__.py")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:
