@@ -334,18 +334,24 @@ def build_workload(args, dev, rank, world):
         else:
             ro_h, rd_h = lego_view(args.hw, theta=30.0 + 7.0 * rank)
         params = [p for p in net.parameters()]
+        # N > 1: flat gradient buffer, the kernels accumulate into it, each net's range is all-reduced on a side stream
+        # as soon as its backward is queued (the fine net's collective runs under the coarse net's backward)
+        sync = star_b200.parallel.GradSync(net) if (train and world > 1) else None
 
         def step_device(ro, rd):
             vd = rd / rd.norm(dim=-1, keepdim=True)
             if train:
-                for p in params:
-                    p.grad = None
+                if sync is None:
+                    for p in params:
+                        p.grad = None
                 pts, z = R_.sample_pts(ro, rd, NEAR, FAR, NC, perturb=0, is_train=True)
                 out = R_.render_star_appinit(net, pts, vd, z, ro, rd, NI, u=u)
                 loss = L_.photometric_loss(out["rgb0"], out["rgb"], target)[0]      # train_online__.py:158-166, fused
-                loss.backward()
-                if world > 1:
-                    star_b200.parallel.allreduce_gradients(params)     # one NCCL all-reduce of the flat gradient
+                if sync is not None:
+                    sync.scale_loss(loss).backward()
+                    sync.finish()
+                else:
+                    loss.backward()
                 return loss
             with torch.no_grad():
                 pts, z = R_.sample_pts(ro, rd, NEAR, FAR, NC, perturb=0, is_train=False)
@@ -368,21 +374,25 @@ def build_workload(args, dev, rank, world):
         pose = torch.nn.Parameter(so.random_poses7(V, seed=3).to(dev))
         params = [p for p in net.parameters()] + [pose]
         u = torch.rand(R, Ni, generator=g).to(dev) if train else None
+        sync = star_b200.parallel.GradSync(net, extra_params=[pose]) if (train and world > 1) else None
 
         def step_device(ro, rd):
             vd = rd / rd.norm(dim=-1, keepdim=True)
             if train:
-                for p in params:
-                    p.grad = None
+                if sync is None:
+                    for p in params:
+                        p.grad = None
                 pts, z = R_.sample_pts(ro, rd, 0.03, 0.8, Nc, perturb=0, is_train=True)
                 out = R_.render_star_online(net, pts, vd, z, ro, rd, Ni, pose, u=u)
                 loss = L_.photometric_loss(out["rgb0"], out["rgb"], target)[0]
                 for sfx in ("", "0"):        # configs/carla_star_online_multi.txt:72-74
                     loss = loss + 0.5 * (1e-3 * out["loss_alpha_entropy" + sfx] + 1e-3 * out["loss_dynamic_vs_static_reg" + sfx]
                                          + 1e-5 * out["loss_ray_reg" + sfx])
-                loss.backward()
-                if world > 1:
-                    star_b200.parallel.allreduce_gradients(params)
+                if sync is not None:
+                    sync.scale_loss(loss).backward()
+                    sync.finish()
+                else:
+                    loss.backward()
                 return loss
             with torch.no_grad():
                 pts, z = R_.sample_pts(ro, rd, 0.03, 0.8, Nc, perturb=0, is_train=False)
@@ -452,10 +462,117 @@ def run_b200(args):
             line["train"]["with_optimizer"] = {
                 "metric": "rays/sec (train fwd+bwd + clip + Adam + weight re-pack)", "value": t["value"], "unit": "rays/s",
                 "ms_per_step": t["ms_per_step"], "gpu_launches": t["gpu_launches"]}
+    if args.mode == "render" and args.workload == "c2" and not args.no_extras and not args.no_train_extra:
+        # the other configurations BASELINE.json names, as sub-records of the same line (weak scaling like the headline:
+        # every rank its own rays): C4 = static + 5 objects with pose gradients, C5 = mip field
+        for name, wk, mode, rays in (("c4_train", "c4", "train", 8192), ("c4_train_r1000", "c4", "train", 1000),
+                                     ("c4_render", "c4", "render", 65536), ("c5_render", "c5", "render", 16384)):
+            a3 = argparse.Namespace(**vars(args))
+            a3.workload, a3.mode, a3.rays, a3.no_cpu_baseline, a3.opt_step = wk, mode, rays, True, False
+            a3.steps, a3.warmup = min(args.steps, 5), 3
+            t = measure(a3)
+            if rank == 0:
+                line[name] = {k: t[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline", "gpu_launches",
+                                                "dtype", "steps")}
+                line[name]["config"] = t["config"]["workload"]
+        if world > 1:
+            st = measure_strong(args)
+            if rank == 0:
+                line["strong"] = st
+        if rank == 0:
+            line["accuracy"] = accuracy_vs_oracle(args, torch.device("cuda", local))
+            if world == 1:
+                line["gpu_eager_baseline"] = gpu_eager_baseline(torch.device("cuda", local))
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def accuracy_vs_oracle(args, dev, n_rays=512):
+    """Max deviation of the benched MLP tier from the fp32 CPU oracle on `n_rays` random rays of the C2 view (fine pass
+    teacher-forced with the oracle's own fine samples): the numbers the north star bounds (2e-3 absolute on rgb / depth /
+    weights and 0.05 dB PSNR for the 16-bit MLP, 1e-4 for fp32).  Checker use of oracle/, outside every timed region."""
+    import star_b200
+    from star_b200 import functional as F_
+    from star_b200.models import rendering__ as R_
+    from oracle import ref_harness, star_oracle as so
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = make_params()
+    ro, rd, vd, _ = _c2_sample(n_rays, seed=3)
+    cfg = so.StarConfig(0, NI, 8192, white_bkgd=True)
+    with torch.no_grad():
+        pts, z = so.sample_pts(ro, rd, NEAR, FAR, NC, is_train=False)
+        ref = so.render_star(sd, cfg, pts, vd, z, ro, rd, NI, training=False, exact_sum=True)
+        mid = 0.5 * (z[..., 1:] + z[..., :-1])
+        zs = so.sample_pdf(mid, ref["weights0"][..., 1:-1], NI, det=True, exact_sum=True)
+        net = star_b200.STaR(ref_harness.make_args(num_vehicles=0, N_importance=NI, chunk=8192, white_bkgd=True))
+        net.load_state_dict(sd)
+        net.to(dev).eval()
+        net.set_precision(args.precision)
+        c = lambda t: t.to(dev)
+        pts_g, z_g = R_.sample_pts(c(ro), c(rd), NEAR, FAR, NC, perturb=0, is_train=False)
+        out = R_.render_star_appinit(net, pts_g, c(vd), z_g, c(ro), c(rd), NI, z_samples=c(zs))
+        F_.check_range()
+    res = {"tier": args.precision, "rays": n_rays, "against": "oracle/star_oracle.py fp32 on the host (pinned to the reference)"}
+    for k in ("rgb0", "rgb", "weights", "depth"):
+        res["max_abs_" + k] = float((out[k].cpu() - ref[k]).abs().max())
+    tgt = torch.rand(n_rays, 3, generator=torch.Generator().manual_seed(1))
+    psnr = lambda a: float(-10.0 * torch.log10(((a.double() - tgt.double()) ** 2).mean()))
+    res["psnr_shift_db"] = abs(psnr(out["rgb"].cpu()) - psnr(ref["rgb"]))
+    res["bound"] = {"fp32": 1e-4}.get(args.precision, 2e-3)
+    return res
+
+
+def measure_strong(args):
+    """Strong scaling at N ranks: (1) ONE 800x800 view split over the ranks by contiguous ray ranges, per-ray outputs
+    all-gathered on every rank (parallel.render_sharded); (2) ONE 4096-ray training batch split over the ranks, gradients
+    all-reduced (GradSync).  Device-timed, max over ranks; value = rays of the whole view / batch per second."""
+    import torch.distributed as dist
+    import star_b200
+    from star_b200 import parallel as P
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    res = {}
+    steps = min(args.steps, 5)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # (1) one view
+    a = argparse.Namespace(**vars(args))
+    a.mode, a.workload = "render", "c2"
+    _net, ro_h, rd_h, step_device, _ = build_workload(a, dev, 0, 1)      # rank 0's view on every rank
+    ro, rd = ro_h.to(dev), rd_h.to(dev)
+    ms = timed(lambda: P.render_sharded(step_device, ro, rd))
+    R = ro.shape[0]
+    res["render_view_split"] = {"metric": "rays/sec (render fwd, one %dx%d view split over %d GPUs, outputs all-gathered)" % (
+        args.hw, args.hw, world), "value": R / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "scaling": "strong"}
+    # (2) one batch
+    a = argparse.Namespace(**vars(args))
+    a.mode, a.workload, a.train_rays = "train", "c2", args.train_rays // world
+    _net, ro_h, rd_h, step_device, _ = build_workload(a, dev, rank, world)
+    ro, rd = ro_h.to(dev), rd_h.to(dev)
+    ms = timed(lambda: step_device(ro, rd))
+    res["train_batch_split"] = {"metric": "rays/sec (train fwd+bwd, one %d-ray batch split over %d GPUs, gradients all-reduced)" % (
+        a.train_rays * world, world), "value": a.train_rays * world / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms,
+        "scaling": "strong"}
+    return res
 
 
 def measure(args):
@@ -477,7 +594,8 @@ def measure(args):
         # the whole optimisation step of the reference: + clip_grad_norm_(1.0) + Adam, fused, over
         # parameters re-homed into one flat buffer; the packed 16-bit weight images are rebuilt every step
         from star_b200 import optim as O_
-        O_.flatten_parameters(net)
+        if getattr(net, "_star_flat", None) is None:      # (N > 1: GradSync already re-homed them)
+            O_.flatten_parameters(net)
         opt = O_.FusedAdam(params, lr=5e-4, betas=(0.9, 0.999), max_grad_norm=1.0)
         fwd_bwd = step_device
 
@@ -567,11 +685,11 @@ def measure(args):
                 os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
             peak_tf = (peak["bf16_tflops_sustained"] if peak else 1400.0)
             ach = parts[key]["flops"] / (tot_ms * 1e-3) / 1e12
-            # dram__bytes_read+write per launch from the committed ncu capture (profiles/r1c_mlp_fwd_tc.md:
-            # 7.83 MB per 524288-sample launch = 14.9 B/sample), scaled to this run's average launch
-            # (training kernels, profiles/r1q_launches_train.md, static net: stash forward 1.657 GB and dX + dW
-            #  4.806 GB per 262144-sample launch)
-            per_sample = {"mlp_forward": 14.93, "mlp_forward_stash": 6321.0, "mlp_backward": 18333.0}.get(key)
+            # dram__bytes_read + dram__bytes_write per launch: bench.py cannot read DRAM counters, so the per-sample figure
+            # of the committed `ncu --set full` capture of this kernel (profiles/traffic.json, written by
+            # tools/ncu_traffic.py from profiles/*_raw.csv; static net) is scaled to this run's average launch
+            tj = os.path.join(ROOT, "profiles", "traffic.json")
+            per_sample = (json.load(open(tj)) if os.path.isfile(tj) else {}).get(key, {}).get("dram_bytes_per_sample")
             traffic = per_sample * tot_samples / n_l if (args.precision != "fp32" and per_sample is not None
                                                          and args.workload == "c2") else None
             tier = args.precision if not key.startswith("mip") else (args.precision if args.precision in MIP_TIERS else "fp32")

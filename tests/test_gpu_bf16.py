@@ -204,7 +204,9 @@ def test_tc_backward_matches_rounding_model_and_fp64(R, S, dyn, with_pose, prec)
     p12 = F_.pose_to_mat12(pose_g) if with_pose else None
     a, c = module.raw(cu(pts), cu(vd), p12)
     ((a * cu(ga)).sum() + (c * cu(gc)).sum()).backward()
-    tol_model, tol_exact = (0.03, 0.2) if prec == "bf16" else (0.025, 0.08)
+    # (the fp16 tier back-propagates in bf16 -- mixed operand formats do not exist in kind::f16 -- on ReLU masks taken
+    #  from its fp16 forward: its distance to the exact network sits between the all-fp16 and the all-bf16 figures)
+    tol_model, tol_exact = (0.03, 0.2) if prec == "bf16" else (0.03, 0.12)
 
     def rel(x, ref):
         return float((x.cpu().double() - ref).norm() / (ref.norm() + 1e-30))

@@ -1,0 +1,39 @@
+"""Builds profiles/traffic.json -- DRAM bytes per sample of the MLP kernels, from the committed `ncu --set full` raw pages
+(profiles/*_raw.csv: metric,unit,value as written by `ncu -i X.ncu-rep --page raw --csv` after transposition).  bench.py
+scales these to the average launch of its own run for `roofline.traffic` (it cannot read DRAM counters itself); re-run
+after every new capture:
+
+    python tools/ncu_traffic.py mlp_forward=profiles/r2a_tc_raw.csv:524288 mlp_forward_stash=...:262144 ...
+"""
+import csv
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+UNITS = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def dram_bytes(path):
+    tot = 0.0
+    for row in csv.reader(open(path)):
+        if len(row) >= 3 and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(row[2]) * UNITS[row[1]]
+    return tot
+
+
+def main():
+    out_path = os.path.join(ROOT, "profiles", "traffic.json")
+    out = json.load(open(out_path)) if os.path.isfile(out_path) else {}
+    for arg in sys.argv[1:]:
+        key, rest = arg.split("=")
+        paths, samples = rest.rsplit(":", 1)
+        b = sum(dram_bytes(os.path.join(ROOT, p)) for p in paths.split("+"))
+        out[key] = {"dram_bytes_per_sample": b / int(samples), "samples_per_captured_launch": int(samples),
+                    "source": paths}
+    json.dump(out, open(out_path, "w"), indent=1, sort_keys=True)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
