@@ -218,10 +218,10 @@ def gpu_eager_baseline(dev, n_rays=65536):
     res = {}
     saved = torch.get_float32_matmul_precision()
     try:
+        ro, rd, vd, _ = _c2_sample(n_rays)
+        ro, rd, vd = ro.to(dev), rd.to(dev), vd.to(dev)
+        kind, fn = reference_render_fn(dev)
         with torch.device(dev):          # the reference creates a few constants without device= (rendering__.py:321,335)
-            kind, fn = reference_render_fn(dev)
-            ro, rd, vd, _ = _c2_sample(n_rays)
-            ro, rd, vd = ro.to(dev), rd.to(dev), vd.to(dev)
             for prec in ("highest", "medium"):
                 torch.set_float32_matmul_precision(prec)
                 best = None

@@ -15,8 +15,16 @@ UNITS = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
 def dram_bytes(path):
+    """Both shapes of a raw page: transposed (metric,unit,value per line) or ncu's own (names / units / values rows)."""
+    rows = list(csv.reader(open(path)))
     tot = 0.0
-    for row in csv.reader(open(path)):
+    if rows and rows[0] and rows[0][0] == "ID":
+        names, units, vals = rows[0], rows[1], rows[2]
+        for n, u, v in zip(names, units, vals):
+            if n in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(v.replace(",", "")) * UNITS[u]
+        return tot
+    for row in rows:
         if len(row) >= 3 and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(row[2]) * UNITS[row[1]]
     return tot
