@@ -6,12 +6,15 @@
 
 int g_star_last_cuda_error = 0;
 
+static inline int star_prec(const StarNetDesc* d) { return d->precision & 0xff; }   // (upper bits: STAR_PREC_FLAG_*)
+
 size_t star_tc_packed_bytes(const TcLayout& tl);
 int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, void* packed, int fp16,
                  cudaStream_t st);
 int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                     const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
-                    float* raw_rgb, int64_t ray_stride, void* stash, int* status, int fp16, cudaStream_t st);
+                    float* raw_rgb, int64_t ray_stride, void* stash, int* status, int fp16, int single_cta,
+                    cudaStream_t st);
 
 size_t star_tc_gstash_bytes(const TcLayout& tl, int64_t n_samples);
 int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
@@ -53,8 +56,8 @@ extern "C" size_t star_net_param_count(const StarNetDesc* d) {
 extern "C" size_t star_packed_bytes(const StarNetDesc* d) {
   MlpLayout lay;
   if (!d || star_make_layout(d, &lay)) return 0;
-  if (d->precision == STAR_PREC_F32) return sizeof(float) * (size_t)lay.n_packed;
-  if (d->precision == STAR_PREC_BF16 || d->precision == STAR_PREC_F16) {
+  if (star_prec(d) == STAR_PREC_F32) return sizeof(float) * (size_t)lay.n_packed;
+  if (star_prec(d) == STAR_PREC_BF16 || star_prec(d) == STAR_PREC_F16) {
     TcLayout tl;
     if (star_make_tc_layout(d, &tl)) return 0;
     return star_tc_packed_bytes(tl);
@@ -67,12 +70,12 @@ extern "C" int star_pack_weights(const StarNetDesc* d, const float* flat_master,
   MlpLayout lay;
   int rc = star_make_layout(d, &lay);
   if (rc) return rc;
-  if (d->precision == STAR_PREC_F32) return star_f32_pack(lay, flat_master, packed, (cudaStream_t)stream);
-  if (d->precision == STAR_PREC_BF16 || d->precision == STAR_PREC_F16) {
+  if (star_prec(d) == STAR_PREC_F32) return star_f32_pack(lay, flat_master, packed, (cudaStream_t)stream);
+  if (star_prec(d) == STAR_PREC_BF16 || star_prec(d) == STAR_PREC_F16) {
     TcLayout tl;
     rc = star_make_tc_layout(d, &tl);
     if (rc) return rc;
-    return star_tc_pack(tl, lay, flat_master, packed, d->precision == STAR_PREC_F16, (cudaStream_t)stream);
+    return star_tc_pack(tl, lay, flat_master, packed, star_prec(d) == STAR_PREC_F16, (cudaStream_t)stream);
   }
   return STAR_E_UNSUPPORTED;
 }
@@ -80,11 +83,12 @@ extern "C" int star_pack_weights(const StarNetDesc* d, const float* flat_master,
 extern "C" size_t star_stash_bytes(const StarNetDesc* d, int64_t n_samples) {
   MlpLayout lay;
   if (!d || star_make_layout(d, &lay) || n_samples < 0) return 0;
-  if (d->precision == STAR_PREC_F32) return sizeof(float) * (size_t)lay.stash_cols * (size_t)n_samples;
-  if (d->precision == STAR_PREC_BF16 || d->precision == STAR_PREC_F16) {
+  if (star_prec(d) == STAR_PREC_F32) return sizeof(float) * (size_t)lay.stash_cols * (size_t)n_samples;
+  if (star_prec(d) == STAR_PREC_BF16 || star_prec(d) == STAR_PREC_F16) {
     TcLayout tl;
     if (star_make_tc_layout(d, &tl)) return 0;
-    return (size_t)((n_samples + 127) / 128) * (size_t)tl.stash_blocks * TC_BLOCK_BYTES;
+    // (an even number of tiles: the CTA-pair kernels walk pairs of tiles and may write a phantom last tile)
+    return (size_t)(((n_samples + 127) / 128 + 1) / 2 * 2) * (size_t)tl.stash_blocks * TC_BLOCK_BYTES;
   }
   return 0;
 }
@@ -92,8 +96,8 @@ extern "C" size_t star_stash_bytes(const StarNetDesc* d, int64_t n_samples) {
 extern "C" size_t star_mlp_backward_workspace_bytes(const StarNetDesc* d, int64_t n_samples) {
   MlpLayout lay;
   if (!d || star_make_layout(d, &lay) || n_samples < 0) return 0;
-  if (d->precision == STAR_PREC_F32) return sizeof(float) * (size_t)lay.g_cols * (size_t)n_samples;
-  if (d->precision == STAR_PREC_BF16 || d->precision == STAR_PREC_F16) {
+  if (star_prec(d) == STAR_PREC_F32) return sizeof(float) * (size_t)lay.g_cols * (size_t)n_samples;
+  if (star_prec(d) == STAR_PREC_BF16 || star_prec(d) == STAR_PREC_F16) {
     TcLayout tl;
     if (star_make_tc_layout(d, &tl)) return 0;
     return star_tc_gstash_bytes(tl, n_samples);
@@ -114,15 +118,16 @@ extern "C" int star_mlp_forward(const StarNetDesc* d, const void* packed, const 
   MlpLayout lay;
   int rc = star_make_layout(d, &lay);
   if (rc) return rc;
-  if (d->precision == STAR_PREC_F32)
+  if (star_prec(d) == STAR_PREC_F32)
     return star_f32_forward(lay, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, raw_alpha,
                             raw_rgb, alpha_ray_stride, stash, (cudaStream_t)stream);
-  if (d->precision == STAR_PREC_BF16 || d->precision == STAR_PREC_F16) {
+  if (star_prec(d) == STAR_PREC_BF16 || star_prec(d) == STAR_PREC_F16) {
     TcLayout tl;
     rc = star_make_tc_layout(d, &tl);
     if (rc) return rc;
     return star_tc_forward(tl, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, raw_alpha, raw_rgb,
-                           alpha_ray_stride, stash, status, d->precision == STAR_PREC_F16, (cudaStream_t)stream);
+                           alpha_ray_stride, stash, status, star_prec(d) == STAR_PREC_F16,
+                           (d->precision & STAR_PREC_FLAG_SINGLE_CTA) != 0, (cudaStream_t)stream);
   }
   return STAR_E_UNSUPPORTED;
 }
@@ -145,17 +150,17 @@ extern "C" int star_mlp_backward(const StarNetDesc* d, const void* packed, const
   MlpLayout lay;
   int rc = star_make_layout(d, &lay);
   if (rc) return rc;
-  if (d->precision == STAR_PREC_F32)
+  if (star_prec(d) == STAR_PREC_F32)
     return star_f32_backward(lay, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, d_raw_alpha,
                              d_raw_rgb, alpha_ray_stride, stash, workspace, grad_flat, pose_acc,
                              (cudaStream_t)stream);
-  if (d->precision == STAR_PREC_BF16 || d->precision == STAR_PREC_F16) {
+  if (star_prec(d) == STAR_PREC_BF16 || star_prec(d) == STAR_PREC_F16) {
     TcLayout tl;
     rc = star_make_tc_layout(d, &tl);
     if (rc) return rc;
     return star_tc_backward(tl, lay, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, d_raw_alpha,
                             d_raw_rgb, alpha_ray_stride, stash, workspace, grad_flat, pose_acc,
-                            d->precision == STAR_PREC_F16, (cudaStream_t)stream);
+                            star_prec(d) == STAR_PREC_F16, (cudaStream_t)stream);
   }
   return STAR_E_UNSUPPORTED;
 }

@@ -21,7 +21,7 @@
 #include "mlp_tc_device.cuh"
 
 #define MIP_TC_NL 10
-#define BAR_X_DONE (2 * TC_NS + 6)
+#define BAR_X_DONE (2 * TC_MAX_NS + 14)
 
 enum MipTcKind { MK_HID = 0, MK_BASE_OUT = 1, MK_H0 = 2, MK_H1 = 3 };
 

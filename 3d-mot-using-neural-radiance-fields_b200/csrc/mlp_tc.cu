@@ -42,11 +42,13 @@ struct EpiCtx {
   uint8_t* stash_out;          // global: first stash block of this layer's epilogue output for this tile, or NULL
   uint8_t* mask_out;           // global: this layer's ReLU bit masks for this tile (training), or NULL
   bool no_mask;                // debug (timing experiments only)
-  uint32_t stash_done0;        // smem address of barrier stash_done[0]
-  bool wait_stash;             // training: this layer's A blocks still feed the stash stores of the previous layer
+  uint32_t stash_done0;        // smem address of barrier stash_done[0] of the A set this layer writes
+  int set;                     // A set this layer writes (0 unless the training pair kernel alternates two sets)
+  bool publishes;              // training: this layer's output blocks are bulk-stored to the stash afterwards
   bool no_stash_wait;          // debug (timing experiments only)
   uint32_t w_full0;            // smem address of barrier w_full[0]
-  uint32_t next_stage0;        // ring stage of the NEXT layer's K-block 0 (its K-block kb uses (next_stage0 + kb) % 4)
+  uint32_t next_stage0;        // ring stage of the NEXT layer's K-block 0 (its K-block kb uses (next_stage0 + kb) % NS)
+  uint32_t ns_mask;            // NS - 1
   int row, cg, lane;
 };
 
@@ -55,8 +57,12 @@ struct EpiCtx {
 // conversion) -> swizzled smem -> proxy fence -> one mbarrier arrival per warp.
 // KIND: LK_IN / LK_FC0 / LK_FC1 (ReLU), LK_OUT (affine + alpha head partial in h[0]), LK_FEAT (affine),
 // LK_VIEWS (ReLU, N = 128, rgb head partials in h[0..2], no A output).
+// Stash bookkeeping (training): bit (4 * set + kb) of `pend` = a bulk store that READS A block (set, kb) has been issued
+// by the producer warp since this thread last waited for that block (every block strictly alternates "written and
+// published" -> "stored" -> "waited for" -> "overwritten"; the layer program is static, so the flag needs no
+// communication); `par` holds the parity of the next wait per block.
 template <int KIND, bool FP16, bool STASH>
-__device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3], uint32_t& stash_par) {
+__device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3], uint32_t& stash_par, uint32_t& stash_pend) {
   constexpr int NCH = (KIND == LK_VIEWS) ? 2 : 4;
   constexpr bool RELU = (KIND == LK_IN || KIND == LK_FC0 || KIND == LK_FC1);
   // All TMEM loads of the layer are issued up front (TC_LD_DEPTH chunks in flight): a tcgen05.ld takes several hundred
@@ -106,9 +112,14 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3], u
     } else {
       // (training: the stash copy of this block is a bulk store issued by the producer warp once the block is complete;
       //  the previous layer's copy of block kb must have left shared memory before it is overwritten)
-      if (STASH && c.wait_stash) {
-        if (!c.no_stash_wait) mbar_wait(c.stash_done0 + 8u * (uint32_t)kb, (stash_par >> kb) & 1u, nullptr, 7);
-        stash_par ^= 1u << kb;
+      if (STASH) {
+        const uint32_t bit = 1u << (4 * c.set + kb);
+        if (stash_pend & bit) {
+          if (!c.no_stash_wait) mbar_wait(c.stash_done0 + 8u * (uint32_t)kb, (stash_par & bit) ? 1u : 0u, nullptr, 7);
+          stash_par ^= bit;
+          stash_pend &= ~bit;
+        }
+        if (c.publishes) stash_pend |= bit;
       }
       store_row16<FP16, RELU>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v);
       if (STASH && RELU && !c.no_mask) {
@@ -122,7 +133,7 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3], u
       tc_fence_before();
       __syncwarp();
       if (c.lane == 0) {
-        mbar_arrive(c.w_full0 + 8u * ((c.next_stage0 + (uint32_t)kb) & (TC_NS - 1)));
+        mbar_arrive(c.w_full0 + 8u * ((c.next_stage0 + (uint32_t)kb) & c.ns_mask));
         if (STASH) mbar_arrive(c.a_ready0 + 8u * (uint32_t)kb);
       }
     }
@@ -132,7 +143,11 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3], u
 }
 
 // ============================================================================================ forward
-template <bool FP16, bool STASH>
+// PAIR: two CTAs (a cluster of 2 = two SMs of one TPC) walk PAIRS of tiles in lock step.  The leader's warp 17 issues
+// cta_group::2 MMAs (M = 256: both tiles at once; each CTA stages only its HALF of every weight K-block), the peer's warp 17
+// relays "my operand block + my weight half are ready" to the leader's w_full barrier, and tcgen05.commit multicasts
+// stage-free / accumulator-complete to both CTAs.  Everything else (producer, 16 epilogue warps, TMEM plan) is per CTA.
+template <bool FP16, bool STASH, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const StarPtsSrc pts,
                   const float* __restrict__ viewdirs, const float* __restrict__ pose12,
@@ -156,9 +171,13 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw_addr);
-  const TcSmem sl = tc_smem_layout(lay.small_bytes);
+  constexpr int NS = tc_ns(PAIR, STASH);
+  constexpr uint32_t STAGE_BYTES = tc_stage_bytes(PAIR);
+  constexpr int NSETS = tc_a_sets(PAIR, STASH);
+  const TcSmem sl = tc_smem_layout(lay.small_bytes, PAIR, STASH);
   const uint32_t sA = base + sl.A, sAD = base + sl.AD, sW = base + sl.W, sBars = base + sl.bars;
   float* s_small = reinterpret_cast<float*>(gbase + sl.small);
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   // partial head sums of column group g (1..3) of a row: 4 floats in 16-byte chunk (3 + g) of the row of the
   // dirs block (logical columns 32..63, which the MMA never reads: only 2 of its 4 K-steps are issued)
   auto part = [&](int r, int g) -> float* {
@@ -169,6 +188,12 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (M + TC_M - 1) / TC_M;
+  // work units: tiles, or pairs of tiles (this CTA takes tile 2 u + rank; a tile beyond the last one has no valid row,
+  // and the stash is allocated for an even number of tiles)
+  const int64_t n_units = PAIR ? (ntiles + 1) / 2 : ntiles;
+  const int64_t unit0 = PAIR ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+  const int64_t unit_step = PAIR ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+  auto tile_of = [&](int64_t u) -> int64_t { return PAIR ? 2 * u + (int64_t)rank : u; };
   const long long t_start = clock64();
 #ifdef STAR_TC_TIMELINE
   // -DSTAR_TC_TIMELINE (debug build only, see tools/tc_timeline.sh): CTA 0 records clock64() stamps of its second tile
@@ -176,7 +201,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
   // per K-block {a_ready seen, w_full seen, issued};  epilogue warp 0, slot 80 + 8 l: {wait start, accumulator seen,
   // layer done}; slots 200 + w: layer-1 epilogue done per warp; slots 8 / 9: encode start / done
   long long* tl = (dbg != nullptr && blockIdx.x == 0) ? reinterpret_cast<long long*>(dbg) : nullptr;
-  const int64_t tl_tile = (int64_t)blockIdx.x + gridDim.x;
+  const int64_t tl_tile = tile_of(unit0 + unit_step);
 #define TL_STAMP(cond, slot) do { if (tl != nullptr && (cond)) tl[slot] = clock64(); } while (0)
 #else
 #define TL_STAMP(cond, slot) do { } while (0)
@@ -184,13 +209,19 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
 
   // ---- one-time setup
   if (warp == TC_EPI_WARPS && lane == 0) {
-    for (int i = 0; i < TC_NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), 1 + TC_EPI_WARPS); mbar_init(bar(BAR_W_EMPTY(i)), 1); }
+    // w_full: the producer (+ its bytes), the 16 epilogue warps and, in the leader of a pair, the peer's relay
+    const uint32_t full_count = 1 + TC_EPI_WARPS + ((PAIR && rank == 0) ? 1 : 0);
+    for (int i = 0; i < NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), full_count); mbar_init(bar(BAR_W_EMPTY(i)), 1); }
     for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A_READY(i)), TC_EPI_WARPS);
     mbar_init(bar(BAR_ACC_FULL), 1);
-    for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_STASH_DONE_KB(i)), 1);
+    for (int i = 0; i < 8; ++i) mbar_init(bar(BAR_STASH_DONE_KB(i)), 1);
     fence_mbar_init();
   }
-  if (warp == TC_EPI_WARPS + 1) tmem_alloc(base + sl.tmem_ptr, TC_TMEM_COLS);
+  if (PAIR) cluster_sync_all();     // both CTAs' barriers exist before anything arrives on them from the other side
+  if (warp == TC_EPI_WARPS + 1) {
+    if (PAIR) tmem_alloc2(base + sl.tmem_ptr, TC_TMEM_COLS);
+    else tmem_alloc(base + sl.tmem_ptr, TC_TMEM_COLS);
+  }
   for (int i = tid; i < lay.small_floats; i += TC_THREADS) s_small[i] = reinterpret_cast<const float*>(packed)[i];
   for (int i = tid; i < TC_KB_BYTES / 16; i += TC_THREADS)
     reinterpret_cast<uint4*>(gbase + sl.AD)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -211,24 +242,27 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     if (lane == 0) {
       const uint8_t* wstream = packed + lay.small_bytes;
       uint32_t stage = 0, phase = 0, s_par = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
+        const int64_t tile = tile_of(unit);
         uint8_t* st_tile = STASH ? stash + (size_t)tile * (size_t)lay.stash_blocks * TC_BLOCK_BYTES : nullptr;
         auto stash_chunk = [&](int ls, int kb) {
+          const int set = (ls + 1) & (NSETS - 1);       // the A set that holds layer ls's output
           mbar_wait(bar(BAR_A_READY(kb)), (s_par >> kb) & 1u, dbg, 6);
           s_par ^= 1u << kb;
           if (!(dbg_mode & 8)) {
-            bulk_s2g(st_tile + (size_t)(lay.L[ls].s_out + kb) * TC_BLOCK_BYTES, sA + (uint32_t)kb * TC_KB_BYTES, TC_KB_BYTES);
+            bulk_s2g(st_tile + (size_t)(lay.L[ls].s_out + kb) * TC_BLOCK_BYTES,
+                     sA + (uint32_t)(4 * set + kb) * TC_KB_BYTES, TC_KB_BYTES);
             bulk_commit_group();
           }
-          // block kb - 1 may be overwritten once its own store has read it (groups complete in order): the epilogue of
-          // the next layer waits per block, so only the last block's store is still in flight when that epilogue starts
+          // block kb - 1 may be overwritten once its own store has read it (groups complete in order): the epilogue that
+          // next writes this set waits per block, so only the last block's store can still be in flight by then
           if (kb >= 1) {
             bulk_wait_group_read1();
-            mbar_arrive(bar(BAR_STASH_DONE_KB(kb - 1)));
+            mbar_arrive(bar(BAR_STASH_DONE_KB(4 * set + kb - 1)));
           }
           if (kb == 3) {
             bulk_wait_group_read0();
-            mbar_arrive(bar(BAR_STASH_DONE_KB(3)));
+            mbar_arrive(bar(BAR_STASH_DONE_KB(4 * set + 3)));
           }
         };
         if (STASH) {   // a_ready[0] also carries the encoder's arrival at the start of a tile: consume that phase
@@ -236,7 +270,9 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           s_par ^= 1u;
         }
         for (int l = 0; l < lay.n_layers; ++l) {
-          const uint32_t bytes = (uint32_t)lay.L[l].N * 128u;
+          // (pair: this CTA's half of the K-block = rows [rank N/2, (rank + 1) N/2) = a contiguous half of its image)
+          const uint32_t kb_bytes = (uint32_t)lay.L[l].N * 128u;
+          const uint32_t bytes = PAIR ? kb_bytes / 2 : kb_bytes;
           for (int kb = 0; kb < lay.L[l].nkb; ++kb) {
             if (STASH && l >= 2 && kb < 4) stash_chunk(l - 2, kb);
             mbar_wait(bar(BAR_W_EMPTY(stage)), phase ^ 1u, dbg, 1);
@@ -245,10 +281,10 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
               mbar_arrive(bar(BAR_W_FULL(stage)));
             } else {
               mbar_arrive_expect_tx(bar(BAR_W_FULL(stage)), bytes);
-              bulk_g2s(sW + stage * TC_STAGE_BYTES, wstream + lay.L[l].w_off + (uint32_t)kb * bytes, bytes,
+              bulk_g2s(sW + stage * STAGE_BYTES, wstream + lay.L[l].w_off + (uint32_t)kb * kb_bytes + rank * bytes, bytes,
                        bar(BAR_W_FULL(stage)));
             }
-            if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
+            if (++stage == NS) { stage = 0; phase ^= 1u; }
           }
         }
         if (STASH)
@@ -257,17 +293,20 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
       if (STASH) bulk_wait_group0();
     }
   } else if (warp == TC_EPI_WARPS + 1) {
-    // ======================================================================== MMA issuer
+    // ======================================================================== MMA issuer (pair: leader) / relay (pair: peer)
     // warp-uniform control flow (all lanes wait on the barriers), one elected lane issues the tcgen05 instructions
-    {
+    if (!PAIR || rank == 0) {
       uint32_t stage = 0, phase = 0, a_par = 0;
       const bool no_mma = (dbg_mode & 4) != 0;
       const uint64_t desc_a0 = umma_desc_sw128(sA), desc_ad = umma_desc_sw128(sAD), desc_w0 = umma_desc_sw128(sW);
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
+        const int64_t tile = tile_of(unit);
+        (void)tile;
         for (int l = 0; l < lay.n_layers; ++l) {
           const int kind = lay.L[l].kind, nkb = lay.L[l].nkb;
           const uint32_t d_tmem = tmem_base + (lay.L[l].region ? 256u : 0u);
-          const uint32_t idesc = umma_idesc_16(TC_M, lay.L[l].N, FP16 ? 0 : 1);
+          const uint32_t idesc = umma_idesc_16(PAIR ? 2 * TC_M : TC_M, lay.L[l].N, FP16 ? 0 : 1);
+          const uint64_t desc_al = desc_a0 + (uint64_t)((l & (NSETS - 1)) * 4 * (TC_KB_BYTES >> 4));   // this layer's A set
           // one K-block: wait for its operand blocks, issue 4 (2 for the dirs block) MMAs, release the weight stage
           auto kblock = [&](const int kb, const bool dirs) {
             if (dirs) {
@@ -276,24 +315,35 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             }
             TL_STAMP(tile == tl_tile && lane == 0 && kb == 0, 16 + 4 * l);
             TL_STAMP(tile == tl_tile && lane == 0 && l == 2, 240 + 3 * kb);
-            mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
+            if (PAIR) mbar_wait_cluster(bar(BAR_W_FULL(stage)), phase, dbg, 3);   // (acquires the peer's relay arrival)
+            else mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
             tc_fence_after();
             TL_STAMP(tile == tl_tile && lane == 0 && l == 2, 241 + 3 * kb);
-            const uint64_t a0 = dirs ? desc_ad : desc_a0 + (uint64_t)(kb * (TC_KB_BYTES >> 4));
-            const uint64_t b0 = desc_w0 + (uint64_t)(stage * (TC_STAGE_BYTES >> 4));
+            const uint64_t a0 = dirs ? desc_ad : desc_al + (uint64_t)(kb * (TC_KB_BYTES >> 4));
+            const uint64_t b0 = desc_w0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
             const uint32_t acc0 = (kind == LK_FC1 || kb > 0) ? 1u : 0u;
             if (elect_one_sync()) {
               if (!no_mma) {
-                if (dirs) tc_mma_kblock<2>(d_tmem, a0, b0, idesc, acc0);
-                else tc_mma_kblock<4>(d_tmem, a0, b0, idesc, acc0);
+                if (PAIR) {
+                  if (dirs) tc_mma2_kblock<2>(d_tmem, a0, b0, idesc, acc0);
+                  else tc_mma2_kblock<4>(d_tmem, a0, b0, idesc, acc0);
+                } else {
+                  if (dirs) tc_mma_kblock<2>(d_tmem, a0, b0, idesc, acc0);
+                  else tc_mma_kblock<4>(d_tmem, a0, b0, idesc, acc0);
+                }
               }
-              tc_commit(bar(BAR_W_EMPTY(stage)));
-              if (kb == nkb - 1) tc_commit(bar(BAR_ACC_FULL));
+              if (PAIR) {
+                tc_commit2(bar(BAR_W_EMPTY(stage)));
+                if (kb == nkb - 1) tc_commit2(bar(BAR_ACC_FULL));
+              } else {
+                tc_commit(bar(BAR_W_EMPTY(stage)));
+                if (kb == nkb - 1) tc_commit(bar(BAR_ACC_FULL));
+              }
             }
             __syncwarp();
             TL_STAMP(tile == tl_tile && lane == 0 && kb == nkb - 1, 17 + 4 * l);
             TL_STAMP(tile == tl_tile && lane == 0 && l == 2, 242 + 3 * kb);
-            if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
+            if (++stage == NS) { stage = 0; phase ^= 1u; }
           };
           if (nkb == 4) {            // the common case, unrolled: K-block indices become immediates
             kblock(0, false); kblock(1, false); kblock(2, false); kblock(3, false);
@@ -302,12 +352,31 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           }
         }
       }
+    } else {
+      // peer of a pair: the same walk over (tile pair, layer, K-block); once THIS CTA's operand block and weight half of a
+      // K-block are in shared memory (its own w_full: producer bytes + 16 epilogue warps), tell the leader's w_full
+      uint32_t stage = 0, phase = 0, a_par = 0;
+      for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
+        for (int l = 0; l < lay.n_layers; ++l) {
+          const int nkb = lay.L[l].nkb;
+          for (int kb = 0; kb < nkb; ++kb) {
+            if (lay.L[l].kind == LK_VIEWS && kb == 4) {
+              mbar_wait(bar(BAR_A_READY(4)), a_par & 1u, dbg, 2);
+              a_par ^= 1u;
+            }
+            mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 8);
+            if (lane == 0) mbar_arrive_remote(bar(BAR_W_FULL(stage)), 0u);
+            __syncwarp();
+            if (++stage == NS) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
     }
   } else {
     // ======================================================================== epilogue warps
     const int q = warp & 3, cg = warp >> 2;
     const int row = q * 32 + lane;
-    uint32_t acc_par = 0, stash_par = 0;
+    uint32_t acc_par = 0, stash_par = 0, stash_pend = 0;
     bool nonfinite = false;
     uint32_t kstage = 0;          // ring stage of the current layer's K-block 0 (same sequence as producer / issuer)
     EpiCtx ctx;
@@ -317,15 +386,19 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     ctx.mask_out = nullptr;
     ctx.no_mask = (dbg_mode & 16) != 0;
     ctx.stash_done0 = bar(BAR_STASH_DONE_KB(0));
-    ctx.wait_stash = false;
+    ctx.set = 0;
+    ctx.publishes = false;
+    ctx.ns_mask = NS - 1;
     ctx.no_stash_wait = (dbg_mode & 32) != 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
+      const int64_t tile = tile_of(unit);
       const int64_t gi = tile * TC_M + row;
       const bool valid = gi < M;
       int64_t out_idx = 0;
-      if (STASH && tile != (int64_t)blockIdx.x) {   // feature_linear's blocks of the previous tile have been read
-        for (int kb = 0; kb < 4; ++kb) mbar_wait(bar(BAR_STASH_DONE_KB(kb)), (stash_par >> kb) & 1u, dbg, 7);
-        stash_par ^= 0xfu;
+      if (STASH && (stash_pend & 1u)) {   // block 0 of set 0 (the encoder's) still feeds a stash store of the previous tile
+        if (!ctx.no_stash_wait) mbar_wait(bar(BAR_STASH_DONE_KB(0)), stash_par & 1u, dbg, 7);
+        stash_par ^= 1u;
+        stash_pend &= ~1u;
       }
       TL_STAMP(tile == tl_tile && tid == 0, 8);
       // ---- inputs: pose transform + encoding -> A K-block 0 (xyz, 4 threads per row) and the dirs block
@@ -366,7 +439,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(bar(BAR_W_FULL(kstage & (TC_NS - 1))));   // operand of (layer 0, K-block 0)
+          mbar_arrive(bar(BAR_W_FULL(kstage & (NS - 1))));   // operand of (layer 0, K-block 0)
           if (STASH) mbar_arrive(bar(BAR_A_READY(0)));
           mbar_arrive(bar(BAR_A_READY(4)));
         }
@@ -387,28 +460,33 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         }
         float h[3] = {0.f, 0.f, 0.f};
         TL_STAMP(tile == tl_tile && tid == 0, 80 + 8 * l);
-        kstage = (kstage + (uint32_t)L.nkb) & (TC_NS - 1);     // now the stage of the NEXT layer's K-block 0
+        kstage = (kstage + (uint32_t)L.nkb) & (NS - 1);     // now the stage of the NEXT layer's K-block 0
         ctx.next_stage0 = kstage;
+        // this layer's output = the next layer's operand: A set (l + 1) mod NSETS; bulk-stored to the stash afterwards
+        // unless it is the view layer's (whose relu(h2) goes to the stash directly)
+        ctx.set = (l + 1) & (NSETS - 1);
+        ctx.sA = sA + (uint32_t)ctx.set * 4u * TC_KB_BYTES;
+        ctx.stash_done0 = bar(BAR_STASH_DONE_KB(4 * ctx.set));
+        ctx.publishes = STASH && l + 1 < lay.n_layers;
         mbar_wait(bar(BAR_ACC_FULL), acc_par, dbg, 4);
         acc_par ^= 1u;
         tc_fence_after();
-        ctx.wait_stash = STASH && l >= 1;   // (per block, inside the epilogue: see epilogue_layer)
         TL_STAMP(tile == tl_tile && tid == 0, 81 + 8 * l);
         if (dbg_mode & 1) {
           for (int kb = 0; kb < (L.N >> 6) && kind != LK_VIEWS; ++kb) {
             fence_proxy_async_smem(); tc_fence_before(); __syncwarp();
             if (lane == 0) {
-              mbar_arrive(bar(BAR_W_FULL((kstage + (uint32_t)kb) & (TC_NS - 1))));
+              mbar_arrive(bar(BAR_W_FULL((kstage + (uint32_t)kb) & (NS - 1))));
               if (STASH) mbar_arrive(bar(BAR_A_READY(kb)));
             }
           }
         } else if (kind == LK_FC0 || kind == LK_FC1 || kind == LK_IN) {
-          epilogue_layer<LK_FC0, FP16, STASH>(ctx, h, stash_par);
+          epilogue_layer<LK_FC0, FP16, STASH>(ctx, h, stash_par, stash_pend);
         } else if (kind == LK_FEAT) {
-          epilogue_layer<LK_FEAT, FP16, STASH>(ctx, h, stash_par);
+          epilogue_layer<LK_FEAT, FP16, STASH>(ctx, h, stash_par, stash_pend);
         } else if (kind == LK_OUT) {
           ctx.head_w = s_small + lay.off_alpha_w;
-          epilogue_layer<LK_OUT, FP16, STASH>(ctx, h, stash_par);
+          epilogue_layer<LK_OUT, FP16, STASH>(ctx, h, stash_par, stash_pend);
           // combine the 4 column groups of each row: groups 1..3 park their partial, group 0 finishes
           if (cg != 0) part(row, cg)[0] = h[0];
           named_bar_sync(1, TC_EPI_THREADS);
@@ -419,7 +497,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           }
         } else {   // LK_VIEWS
           ctx.head_w = s_small + lay.off_rgb_w;
-          epilogue_layer<LK_VIEWS, FP16, STASH>(ctx, h, stash_par);
+          epilogue_layer<LK_VIEWS, FP16, STASH>(ctx, h, stash_par, stash_pend);
           if (cg != 0) {
             float* d = part(row, cg);
             d[1] = h[0]; d[2] = h[1]; d[3] = h[2];
@@ -444,15 +522,17 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     if (status != nullptr && nonfinite) *reinterpret_cast<volatile int*>(status) = 1;
   }
 
-  // ---- teardown
+  // ---- teardown (pair: neither CTA may leave while the other's MMAs / commits can still touch its shared memory)
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   if (dbg != nullptr && tid == 0 && blockIdx.x == 0) {   // debug only: cycles of CTA 0 (see star_tc_forward)
     reinterpret_cast<long long*>(dbg)[1] = clock64() - t_start;
   }
   if (warp == TC_EPI_WARPS + 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    if (PAIR) tmem_dealloc2(tmem_base, TC_TMEM_COLS);
+    else tmem_dealloc(tmem_base, TC_TMEM_COLS);
   }
 }
 
@@ -535,22 +615,52 @@ int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, v
 
 int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                     const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
-                    float* raw_rgb, int64_t ray_stride, void* stash, int* status, int fp16, cudaStream_t st) {
+                    float* raw_rgb, int64_t ray_stride, void* stash, int* status, int fp16, int single_cta,
+                    cudaStream_t st) {
   const int64_t M = (int64_t)R * S;
   const int64_t ntiles = (M + TC_M - 1) / TC_M;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = (int)(ntiles < sms ? ntiles : sms);
-  const TcSmem sl = tc_smem_layout(tl.small_bytes);
   if (((uintptr_t)packed & 15) != 0) return STAR_E_ALIGN;
-  auto kern = stash != nullptr ? (fp16 ? mlp_fwd_tc_kernel<true, true> : mlp_fwd_tc_kernel<false, true>)
-                               : (fp16 ? mlp_fwd_tc_kernel<true, false> : mlp_fwd_tc_kernel<false, false>);
+  const bool pair = !single_cta;
+  const bool with_stash = stash != nullptr;
+  const TcSmem sl = tc_smem_layout(tl.small_bytes, pair, with_stash);
+  // grid: one CTA per SM over the tiles, or one CTA pair per two SMs over pairs of tiles
+  const int64_t units = pair ? (ntiles + 1) / 2 : ntiles;
+  const int max_units = pair ? sms / 2 : sms;
+  const int grid = (int)(units < max_units ? units : max_units) * (pair ? 2 : 1);
+  using Kern = void (*)(const TcLayout, const uint8_t*, const StarPtsSrc, const float*, const float*, const float*,
+                        const float*, int, int64_t, float*, float*, int64_t, uint8_t*, int*, int*, int);
+  Kern kern;
+  if (pair)
+    kern = with_stash ? (fp16 ? mlp_fwd_tc_kernel<true, true, true> : mlp_fwd_tc_kernel<false, true, true>)
+                      : (fp16 ? mlp_fwd_tc_kernel<true, false, true> : mlp_fwd_tc_kernel<false, false, true>);
+  else
+    kern = with_stash ? (fp16 ? mlp_fwd_tc_kernel<true, true, false> : mlp_fwd_tc_kernel<false, true, false>)
+                      : (fp16 ? mlp_fwd_tc_kernel<true, false, false> : mlp_fwd_tc_kernel<false, false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
   if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = sl.total;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  auto launch = [&](int* dbg, int dbg_mode) -> int {
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
+                                        raw_alpha, raw_rgb, ray_stride, (uint8_t*)stash, status, dbg, dbg_mode);
+    if (le != cudaSuccess) { g_star_last_cuda_error = (int)le; return STAR_E_CUDA; }
+    return STAR_OK;
+  };
 #ifndef STAR_TC_DEBUG
-  kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
-                                            raw_alpha, raw_rgb, ray_stride, (uint8_t*)stash, status, nullptr, 0);
+  { const int lrc = launch(nullptr, 0); if (lrc) return lrc; }
 #else
   // -DSTAR_TC_DEBUG builds only (tools/tc_debug_modes.sh, tools/tc_timeline.sh): STAR_TC_DEBUG_MODE switches parts of the
   // kernel off (results are garbage), STAR_TC_DEBUG_CYCLES=1 makes the launch synchronous and prints CTA 0's cycles
@@ -563,13 +673,12 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pt
     dbg_cycles = getenv("STAR_TC_DEBUG_CYCLES") ? 1 : 0;
     if (dbg_cycles) { cudaMalloc(&d_dbg, 4096); cudaMemset(d_dbg, 0, 4096); }
   }
-  kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
-                                            raw_alpha, raw_rgb, ray_stride, (uint8_t*)stash, status, (int*)d_dbg, dbg_mode);
+  { const int lrc = launch((int*)d_dbg, dbg_mode); if (lrc) return lrc; }
   if (dbg_cycles) {
     static long long h[512];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, d_dbg, 4096, cudaMemcpyDeviceToHost);
-    const double t0 = (double)((ntiles + grid - 1) / grid);
+    const double t0 = (double)((units * (pair ? 2 : 1) + grid - 1) / grid);
     fprintf(stderr, "[star_tc] mode %d: CTA0 %.0f cycles/tile\n", dbg_mode, h[1] / t0);
 #ifdef STAR_TC_TIMELINE
     if (ntiles > 2 * (int64_t)grid && h[8] != 0) {

@@ -46,7 +46,7 @@ __host__ __device__ static inline BwdSmem bwd_smem_layout(uint32_t small_bytes) 
   s.W = o; o += TC_NS * TC_STAGE_BYTES;
   s.small = o; o += small_bytes;
   s.tab = o; o += BWD_MAX_STAGES * sizeof(BwdStage) + BWD_MAX_PHASES * sizeof(BwdPhase) + 16;
-  s.bars = o; o += 16 * 8;
+  s.bars = o; o += 40 * 8;
   s.tmem_ptr = o; o += 16;
   s.total = o + 1024;
   return s;
@@ -794,7 +794,7 @@ int star_tc_pack_tstream(const TcLayout& tl, const MlpLayout& ml, const float* m
 }
 
 size_t star_tc_gstash_bytes(const TcLayout& tl, int64_t n_samples) {
-  return (size_t)((n_samples + 127) / 128) * (size_t)tl.gstash_blocks * TC_BLOCK_BYTES;
+  return (size_t)(((n_samples + 127) / 128 + 1) / 2 * 2) * (size_t)tl.gstash_blocks * TC_BLOCK_BYTES;
 }
 
 int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed, const StarPtsSrc& pts, const float* viewdirs,

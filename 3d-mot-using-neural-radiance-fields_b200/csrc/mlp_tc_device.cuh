@@ -19,15 +19,22 @@ struct TcSmem {
   uint32_t A, AD, W, small, part, bars, tmem_ptr;   // byte offsets from the 1024-aligned base
   uint32_t total;
 };
-__host__ __device__ static inline TcSmem tc_smem_layout(uint32_t small_bytes) {
+// CTA-pair variants (cta_group::2): a weight stage holds this CTA's HALF of a K-block (16 KB), which frees 64 KB: the
+// inference kernel spends them on a ring of 8 stages, the training kernel on a SECOND set of 4 A blocks, so that the bulk
+// stores of one layer's operand blocks to the stash overlap the next epilogue, which writes the other set.
+#define TC_MAX_NS 8
+__host__ __device__ constexpr int tc_ns(bool pair, bool stash) { return pair ? (stash ? 4 : 8) : TC_NS; }
+__host__ __device__ constexpr uint32_t tc_stage_bytes(bool pair) { return pair ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES; }
+__host__ __device__ constexpr int tc_a_sets(bool pair, bool stash) { return (pair && stash) ? 2 : 1; }
+__host__ __device__ static inline TcSmem tc_smem_layout(uint32_t small_bytes, bool pair = false, bool stash = false) {
   TcSmem s;
   uint32_t o = 0;
-  s.A = o; o += 4 * TC_KB_BYTES;
+  s.A = o; o += (uint32_t)tc_a_sets(pair, stash) * 4 * TC_KB_BYTES;
   s.AD = o; o += TC_KB_BYTES;
-  s.W = o; o += TC_NS * TC_STAGE_BYTES;
+  s.W = o; o += (uint32_t)tc_ns(pair, stash) * tc_stage_bytes(pair);
   s.small = o; o += small_bytes;
   s.part = s.AD;    // head partial sums live in the never-read half (columns 32..63) of the dirs block
-  s.bars = o; o += 24 * 8;
+  s.bars = o; o += 40 * 8;
   s.tmem_ptr = o; o += 16;
   s.total = o + 1024;   // slack for aligning the dynamic smem base
   return s;
@@ -35,11 +42,11 @@ __host__ __device__ static inline TcSmem tc_smem_layout(uint32_t small_bytes) {
 
 // barrier indices inside the bars block
 #define BAR_W_FULL(i) (i)
-#define BAR_W_EMPTY(i) (TC_NS + (i))
-#define BAR_A_READY(i) (2 * TC_NS + (i))      // 0..3: A K-blocks, 4: encoded-dirs block
-#define BAR_ACC_FULL (2 * TC_NS + 5)
-#define BAR_STASH_DONE (2 * TC_NS + 6)   // training: the bulk store of A block kb has read shared memory (one barrier per block)
-#define BAR_STASH_DONE_KB(kb) (BAR_STASH_DONE + (kb))
+#define BAR_W_EMPTY(i) (TC_MAX_NS + (i))
+#define BAR_A_READY(i) (2 * TC_MAX_NS + (i))      // 0..3: A K-blocks, 4: encoded-dirs block
+#define BAR_ACC_FULL (2 * TC_MAX_NS + 5)
+#define BAR_STASH_DONE (2 * TC_MAX_NS + 6)   // training: the bulk store of A block kb has read shared memory (one barrier per block)
+#define BAR_STASH_DONE_KB(kb) (BAR_STASH_DONE + (kb))       // kb + 4 * set: 8 barriers
 
 // ---------------------------------------------------------------------------------------------- encode
 // 16 consecutive columns [C0, C0+16) of the positional encoding [x, sin(2^k x), cos(2^k x)]_k (embedder.py:90-97;

@@ -114,6 +114,78 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
+// ---- CTA pairs (cluster of 2, cta_group::2): ONE tcgen05.mma of the leader CTA drives both SMs' tensor cores: M = 256
+// (each CTA's own 128 rows of A from its own shared memory, results in its own TMEM), B split by rows -- the leader holds
+// rows [0, N/2), the peer rows [N/2, N) of the [N][64] K-block at the same shared-memory offset (tools/umma_probe.cu
+// checks this on the hardware: 128 cycles per 256 x 256 x 16 MMA).  Per SM this halves the weight bytes fetched from
+// L2, written to and read from shared memory.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {  // one full warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs of the pair once the leader's MMAs have completed
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// arrive (release, cluster scope) on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// wait with cluster-scope acquire: pairs with mbar_arrive_remote (the peer's shared-memory writes become visible)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int* dbg, int code) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > STAR_TC_WATCHDOG_CYCLES) {
+      if (dbg != nullptr) atomicExch(dbg, (code << 16) | (int)(blockIdx.x & 0xffff));
+      __trap();
+    }
+  }
+}
+template <int NK>
+__device__ __forceinline__ void tc_mma2_kblock(uint32_t d_tmem, uint64_t a_desc0, uint64_t b_desc0, uint32_t idesc,
+                                               uint32_t acc0) {
+#pragma unroll
+  for (int k = 0; k < NK; ++k)
+    tc_mma2_bf16(d_tmem, a_desc0 + (uint64_t)(2 * k), b_desc0 + (uint64_t)(2 * k), idesc, k == 0 ? acc0 : 1u);
+}
+
 // One lane of a fully active warp (elect.sync).  The MMA-issuing warp runs its control flow on all 32 lanes and guards
 // only the tcgen05 instructions with this predicate: behind a plain `lane == 0` branch the compiler has to treat the
 // uniform-datapath operands of UTCHMMA / UTCBAR as divergent and wraps every one of them in a vote / elect / branch loop

@@ -47,6 +47,9 @@ enum {
  *          activations by mixed-format tcgen05.mma.  Range guard: activations beyond 65504 overflow to inf and surface
  *          as non-finite raw outputs, which star_mlp_forward reports through its `status` word. */
 enum { STAR_PREC_F32 = 0, STAR_PREC_BF16 = 1, STAR_PREC_F16 = 2 };
+/* OR-ed into StarNetDesc.precision (tensor-core tiers): run the one-CTA-per-SM kernels instead of the CTA-pair
+ * (cta_group::2) kernels -- same results bit for bit; kept for A/B measurements. */
+#define STAR_PREC_FLAG_SINGLE_CTA 0x100
 
 /* One NeRF radiance MLP (models/nerf.py:34-110, models/resnet.py:62-110).  W is fixed at 256,
  * the view branch at 128 (all 15 reference configs agree). */
