@@ -127,7 +127,7 @@ extern "C" int star_mlp_forward(const StarNetDesc* d, const void* packed, const 
     if (rc) return rc;
     return star_tc_forward(tl, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, raw_alpha, raw_rgb,
                            alpha_ray_stride, stash, status, star_prec(d) == STAR_PREC_F16,
-                           (d->precision & STAR_PREC_FLAG_SINGLE_CTA) != 0, (cudaStream_t)stream);
+                           (d->precision & STAR_PREC_FLAG_CTA_PAIR) == 0, (cudaStream_t)stream);
   }
   return STAR_E_UNSUPPORTED;
 }

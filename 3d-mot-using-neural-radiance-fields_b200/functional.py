@@ -17,8 +17,9 @@ from ._capi import check, f32, ptr, stream
 MAX_SAMPLES_PER_LAUNCH = int(os.environ.get("STAR_B200_MAX_SAMPLES", 1 << 19))
 STASH_BUDGET_BYTES = int(float(os.environ.get("STAR_B200_STASH_GB", "24")) * (1 << 30))
 
-# A/B switch: run the one-CTA-per-SM tensor-core kernels instead of the CTA-pair (cta_group::2) ones (same results)
-TC_SINGLE_CTA = os.environ.get("STAR_B200_TC_SINGLE", "0") == "1"
+# A/B switch: run the tensor-core forward on the CTA-pair (cta_group::2) kernels instead of the one-CTA-per-SM ones (same
+# results, measured slower: see include/star_b200.h)
+TC_CTA_PAIR = os.environ.get("STAR_B200_TC_PAIR", "0") == "1"
 
 # instrumentation for bench.py: number of kernel-launching C-ABI calls issued
 LAUNCH_COUNTER = {"calls": 0}
@@ -331,8 +332,8 @@ class NetRuntime:
         return out
 
     def desc(self, precision):
-        if TC_SINGLE_CTA and precision != _capi.PREC_F32:
-            precision = precision | _capi.PREC_FLAG_SINGLE_CTA
+        if TC_CTA_PAIR and precision != _capi.PREC_F32:
+            precision = precision | _capi.PREC_FLAG_CTA_PAIR
         return _capi.net_desc(self.n_blocks, self.L_xyz, self.L_dir, precision)
 
     def refresh(self, precision):

@@ -47,9 +47,11 @@ enum {
  *          activations by mixed-format tcgen05.mma.  Range guard: activations beyond 65504 overflow to inf and surface
  *          as non-finite raw outputs, which star_mlp_forward reports through its `status` word. */
 enum { STAR_PREC_F32 = 0, STAR_PREC_BF16 = 1, STAR_PREC_F16 = 2 };
-/* OR-ed into StarNetDesc.precision (tensor-core tiers): run the one-CTA-per-SM kernels instead of the CTA-pair
- * (cta_group::2) kernels -- same results bit for bit; kept for A/B measurements. */
-#define STAR_PREC_FLAG_SINGLE_CTA 0x100
+/* OR-ed into StarNetDesc.precision (tensor-core tiers): run the forward on the CTA-pair (cta_group::2) kernels instead of
+ * the one-CTA-per-SM kernels.  Same results bit for bit; measured SLOWER on B200 (C2 render 2.05 M against 2.66 M rays/s,
+ * profiles/r2b_*: the layer chain of a tile is latency-bound and the pair adds a cross-CTA hop to every operand hand-off),
+ * so it is opt-in and kept for A/B measurements. */
+#define STAR_PREC_FLAG_CTA_PAIR 0x100
 
 /* One NeRF radiance MLP (models/nerf.py:34-110, models/resnet.py:62-110).  W is fixed at 256,
  * the view branch at 128 (all 15 reference configs agree). */

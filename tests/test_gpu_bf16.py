@@ -287,3 +287,32 @@ def test_second_backward_through_a_retained_graph():
     loss.backward()
     for x, y in zip(g1, (p.grad for p in net.static_coarse_nerf.parameters())):
         assert float((x - y).norm()) <= 1e-4 * float(x.norm()) + 1e-12
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_cta_pair_kernels_are_bit_identical_to_the_single_cta_kernels(prec, monkeypatch):
+    """The opt-in cta_group::2 forward (two CTAs, one M = 256 MMA, half the weight K-block per CTA; inference: 8-stage
+    ring, training: second A-block set) computes the same dot products in the same K order: raw outputs and stashes
+    (hence gradients, up to the dW atomics) must not differ from the one-CTA-per-SM kernels.  Odd tile counts exercise
+    the phantom last tile of a pair."""
+    net, _ = make_star(1, 8, 4096, False, seed=21, training=True, precision=prec)
+    for R, S, dyn in ((301, 191, False), (129, 5, True), (1, 1, False), (640, 64, True)):
+        module = net.dynamic_coarse_nerfs[0] if dyn else net.static_coarse_nerf
+        ro, rd = so.carla_rays(R, seed=7)
+        vd = rd / rd.norm(dim=-1, keepdim=True)
+        pts, _ = so.sample_pts(ro, rd, 0.03, 0.8, S)
+        p12 = F_.pose_to_mat12(cu(so.pose7_to_matrix(so.random_poses7(1, seed=9))[0])) if dyn else None
+        res = {}
+        for pair in (False, True):
+            monkeypatch.setattr(F_, "TC_CTA_PAIR", pair)
+            with torch.no_grad():
+                a0, c0 = module.raw(cu(pts), cu(vd), p12)             # inference variant
+            module.zero_grad()
+            a, c = module.raw(cu(pts), cu(vd), p12)                   # training (stash) variant
+            ((a ** 2).mean() + (c ** 2).mean()).backward()
+            res[pair] = (a0, c0, a.detach(), c.detach(), [p.grad.clone() for p in module.parameters()])
+        for i in range(4):
+            assert torch.equal(res[False][i], res[True][i]), (R, S, i)
+        for x, y in zip(res[False][4], res[True][4]):
+            assert float((x - y).norm()) <= 1e-4 * float(x.norm()) + 1e-12
+    F_.check_range()
