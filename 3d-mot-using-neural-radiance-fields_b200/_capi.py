@@ -36,6 +36,29 @@ class StarMultiOut(C.Structure):
         "depth_dynamic", "dynamic_transmittance", "rgb_dynamic_all", "regs")]
 
 
+class StarRenderCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("R", "Nc", "Ni", "V", "precision", "n_blocks_static", "n_blocks_dynamic", "L_xyz",
+                                         "L_dir", "white_bkgd", "lindisp", "test", "chunk")] + \
+               [(n, C.c_float) for n in ("near_", "far_", "far_dist")]
+
+
+class StarRenderIn(C.Structure):
+    _fields_ = [("rays_o", C.c_void_p), ("rays_d", C.c_void_p), ("viewdirs", C.c_void_p),
+                ("H", C.c_int32), ("W", C.c_int32), ("row0", C.c_int32), ("nrows", C.c_int32),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("c2w", C.c_void_p),
+                ("z_vals", C.c_void_p), ("pts", C.c_void_p), ("t_vals", C.c_void_p), ("t_rand", C.c_void_p),
+                ("u", C.c_void_p), ("u_det", C.c_void_p), ("z_samples", C.c_void_p),
+                ("pose12", C.c_void_p), ("enc_scale_xyz", C.c_void_p), ("enc_scale_dir", C.c_void_p),
+                ("packed_static_coarse", C.c_void_p), ("packed_static_fine", C.c_void_p),
+                ("packed_dynamic_coarse", C.POINTER(C.c_void_p)), ("packed_dynamic_fine", C.POINTER(C.c_void_p))]
+
+
+class StarRenderOut(C.Structure):
+    _fields_ = [("coarse", StarMultiOut), ("fine", StarMultiOut)] + \
+               [(n, C.c_void_p) for n in ("dists0", "dists", "z_vals0", "z_vals", "z_samples", "z_std", "rays_o", "rays_d",
+                                          "viewdirs")]
+
+
 class StarAdamSeg(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
                 ("n", C.c_int64), ("step_size", C.c_float), ("bc2_sqrt", C.c_float)]
@@ -73,6 +96,9 @@ _SIGS = {
     "star_invert_cdf": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f]),
     "star_hierarchical": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f]),
     "star_merge_samples": (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f]),
+    "star_render_workspace_bytes": (C.c_size_t, [C.POINTER(StarRenderCfg)]),
+    "star_render_forward": (C.c_int, [C.POINTER(StarRenderCfg), C.POINTER(StarRenderIn), C.POINTER(StarRenderOut), c_f,
+                                      C.c_size_t, c_f, c_f]),
     # a12: mip-NeRF variant
     "star_mip_uniform_bins": (C.c_int, [c_f, c_f, C.c_float, C.c_float, C.c_int, C.c_int, c_f, c_f, c_f]),
     "star_mip_pdf_sample": (C.c_int, [c_f, c_f, c_i64, c_f, c_f, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,

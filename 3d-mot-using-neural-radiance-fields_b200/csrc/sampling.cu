@@ -29,9 +29,11 @@ __global__ void sample_pts_kernel(const float* __restrict__ rays_o, const float*
       z = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), t_rand[i]));
     }
     z_vals[i] = z;
+    if (pts != nullptr) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-      pts[i * 3 + c] = __fadd_rn(rays_o[r * 3 + c], __fmul_rn(rays_d[r * 3 + c], z));
+      for (int c = 0; c < 3; ++c)
+        pts[i * 3 + c] = __fadd_rn(rays_o[r * 3 + c], __fmul_rn(rays_d[r * 3 + c], z));
+    }
   }
 }
 
@@ -71,6 +73,8 @@ __global__ void sample_pts_x4_kernel(const float* __restrict__ rays_o, const flo
 #pragma unroll
       for (int j = 0; j < 4; ++j) z[j] = zj[j];
     }
+    __stcs(reinterpret_cast<float4*>(z_vals + (size_t)q * 4), make_float4(z[0], z[1], z[2], z[3]));
+    if (pts == nullptr) continue;      // depths only: the MLP kernels form the positions themselves (StarPtsSrc)
     const float ox = rays_o[r * 3 + 0], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
     const float dx = rays_d[r * 3 + 0], dy = rays_d[r * 3 + 1], dz = rays_d[r * 3 + 2];
     float p[12];
@@ -80,7 +84,6 @@ __global__ void sample_pts_x4_kernel(const float* __restrict__ rays_o, const flo
       p[3 * j + 1] = __fadd_rn(oy, __fmul_rn(dy, z[j]));
       p[3 * j + 2] = __fadd_rn(oz, __fmul_rn(dz, z[j]));
     }
-    __stcs(reinterpret_cast<float4*>(z_vals + (size_t)q * 4), make_float4(z[0], z[1], z[2], z[3]));
     float4* po = reinterpret_cast<float4*>(pts + (size_t)q * 12);
     __stcs(po + 0, make_float4(p[0], p[1], p[2], p[3]));
     __stcs(po + 1, make_float4(p[4], p[5], p[6], p[7]));
@@ -91,7 +94,7 @@ __global__ void sample_pts_x4_kernel(const float* __restrict__ rays_o, const flo
 extern "C" int star_sample_pts(const float* rays_o, const float* rays_d, const float* t_vals,
                                const float* t_rand, float near_, float far_, int R, int Nc, int lindisp,
                                float* pts, float* z_vals, void* stream) {
-  if (!rays_o || !rays_d || !t_vals || !pts || !z_vals) return STAR_E_NULL;
+  if (!t_vals || !z_vals || (pts && (!rays_o || !rays_d))) return STAR_E_NULL;     // pts == NULL: depths only
   if (R < 0 || Nc < 1) return STAR_E_BAD_SHAPE;
   if (R == 0) return STAR_OK;
   const int64_t total = (int64_t)R * Nc;

@@ -558,6 +558,134 @@ class NerfRaw(Function):
         return (None, None, None, None, None, g_pose, None, None, *grads)
 
 
+# ------------------------------------------------------------------------------------------ a10 + a11 in one call
+def render_forward(static_nets, dynamic_nets, precision, rays_o, rays_d, viewdirs, N_importance, *, z_vals=None, pts=None,
+                   near=None, far=None, N_samples=None, lindisp=False, t_rand=None, pose12=None, det=True, u=None,
+                   z_samples=None, white_bkgd=False, far_dist=1e10, chunk=None, test=True, enc_scales=(None, None),
+                   camera=None):
+    """The whole coarse -> fine render (models/rendering__.py:115-149, :249-298 on models/star__.py:119-225) as ONE
+    C-ABI call, star_render_forward: every kernel is queued on the current stream without returning to Python.
+    Inference only (nothing is kept for a backward pass).
+
+    static_nets = (coarse NeRF module, fine NeRF module or None); dynamic_nets = (list of coarse, list of fine) object
+    modules; pose12 [V,12].  Coarse depths: `z_vals` [R,Nc] (optionally with the caller's `pts`), or near / far /
+    N_samples (sampled inside).  Rays: rays_o / rays_d / viewdirs [R,3], or camera = (H, W, K, c2w, (row0, nrows)) --
+    rays generated inside.  Returns the reference's output dictionary (StarRenderOutput / NerfNetworkOutput keys)."""
+    L = _capi.lib()
+    sc_net, sf_net = static_nets
+    dyn_c, dyn_f = dynamic_nets
+    V = len(dyn_c)
+    Ni = int(N_importance) if sf_net is not None else 0
+    if camera is not None:
+        H, W, K, c2w, (row0, nrows) = camera
+        c2w = _c(c2w[:3, :4].to(torch.float32))
+        dev, R = c2w.device, nrows * W
+    else:
+        rays_o, rays_d = _c(rays_o), _c(rays_d)
+        viewdirs = _c(viewdirs) if viewdirs is not None else None
+        dev, R = rays_o.device, rays_o.shape[0]
+    if z_vals is not None:
+        z_vals = _c(z_vals)
+        Nc = z_vals.shape[1]
+        pts = _c(pts) if pts is not None else None
+    else:
+        Nc = int(N_samples)
+    Nf = Nc + Ni
+    cfg = _capi.StarRenderCfg(R, Nc, Ni, V, int(precision), sc_net._rt.n_blocks, dyn_c[0]._rt.n_blocks if V else 2,
+                              sc_net._rt.L_xyz, sc_net._rt.L_dir, int(bool(white_bkgd)), int(bool(lindisp)),
+                              int(bool(test)), int(chunk or max(R, 1)), float(near or 0.0), float(far or 0.0),
+                              float(far_dist))
+    flag = None
+    if precision != _capi.PREC_F32:
+        flag = _range_flag(dev)
+        if int(flag[0]) != 0:
+            check_range(sync=False)
+    e = lambda *s_: torch.empty(s_, device=dev, dtype=torch.float32)
+
+    def pass_out(S):
+        o = dict(rgb=e(R, 3), disp=e(R), acc=e(R), depth=e(R), weights=e(R, S))
+        if V:
+            o.update(rgb_static=e(R, 3), depth_static=e(R), rgb_dynamic=e(R, V, 3), depth_dynamic=e(R, V),
+                     dynamic_transmittance=e(R, V), rgb_dynamic_all=e(R, 3) if test else None, regs=e(5))
+        return o
+    oc, of = pass_out(Nc), (pass_out(Nf) if Ni > 0 else {})
+    mo = lambda o: _capi.StarMultiOut(*[ptr(o.get(k)) for k in STAR_OUT_KEYS])
+    extra = {}
+    if V == 0:
+        extra["dists0"] = e(R, Nc)
+        if Ni > 0:
+            extra["dists"] = e(R, Nf)
+    if z_vals is None:
+        extra["z_vals0"] = e(R, Nc)
+    if Ni > 0:
+        extra["z_vals"], extra["z_std"] = e(R, Nf), e(R)
+        if z_samples is None:
+            extra["z_samples"] = e(R, Ni)
+    if camera is not None:
+        extra["rays_o"], extra["rays_d"], extra["viewdirs"] = e(R, 3), e(R, 3), e(R, 3)
+    out = _capi.StarRenderOut(mo(oc), mo(of), *[ptr(extra.get(k)) for k in
+                                                ("dists0", "dists", "z_vals0", "z_vals", "z_samples", "z_std", "rays_o",
+                                                 "rays_d", "viewdirs")])
+    # packed weight images (rebuilt when a parameter changed)
+    pk = lambda m: ptr(m._rt.refresh(precision)[1])
+    keep = [sc_net._rt.refresh(precision)[1]]
+    arr_c = (C.c_void_p * max(V, 1))(*[pk(m) for m in dyn_c])
+    arr_f = (C.c_void_p * max(V, 1))(*[pk(m) for m in dyn_f]) if (V and Ni > 0) else (C.c_void_p * 1)()
+    u_det = None
+    if Ni > 0 and z_samples is None and u is None:
+        if det:
+            u_det = _linspace01(Ni, dev)
+        else:
+            u = torch.rand((R, Ni), device=dev)
+    t_vals = _linspace01(Nc, dev) if z_vals is None else None
+    fp = lambda t: f32(_c(t)) if t is not None else None
+    sin = _capi.StarRenderIn(
+        fp(rays_o) if camera is None else None, fp(rays_d) if camera is None else None, fp(viewdirs),
+        *( (int(camera[0]), int(camera[1]), int(row0), int(nrows), float(K[0][0]), float(K[1][1]), float(K[0][2]),
+            float(K[1][2]), f32(c2w)) if camera is not None else (0, 0, 0, 0, 0.0, 0.0, 0.0, 0.0, None)),
+        fp(z_vals), fp(pts), fp(t_vals), fp(t_rand), fp(u), fp(u_det), fp(z_samples), fp(pose12),
+        fp(enc_scales[0]), fp(enc_scales[1]), pk(sc_net), pk(sf_net) if Ni > 0 else None, arr_c, arr_f)
+    ws_bytes = L.star_render_workspace_bytes(C.byref(cfg))
+    ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
+    e0 = _prof_begin()
+    check(L.star_render_forward(C.byref(cfg), C.byref(sin), C.byref(out), ptr(ws), ws_bytes,
+                                flag.data_ptr() if flag is not None else None, stream()), "star_render_forward")
+    mac = MLP_MAC_PER_SAMPLE.get(sc_net._rt.n_blocks, 0) + V * (MLP_MAC_PER_SAMPLE.get(dyn_c[0]._rt.n_blocks, 0) if V else 0)
+    n_samp = R * (Nc + (Nf if Ni > 0 else 0))
+    _prof_end("render_forward", e0, n_samp, 2.0 * mac * n_samp)
+    passes = 2 if Ni > 0 else 1
+    _count(passes * (1 + V + (2 if V else 1)) + (1 if Ni > 0 else 0) + (1 if z_vals is None else 0)
+           + (1 if (camera is not None or viewdirs is None) else 0))
+    del keep
+
+    def to_dict(o, z, dists, sfx):
+        d = {}
+        for k in ("rgb", "disp", "acc", "weights", "depth"):
+            d[k + sfx] = o[k]
+        if V:
+            for k in ("rgb_static", "depth_static", "rgb_dynamic", "depth_dynamic", "dynamic_transmittance"):
+                d[k + sfx] = o[k]
+            d["rgb_dynamic_all" + sfx] = o["rgb_dynamic_all"]
+            r = o["regs"]
+            for i, k in enumerate(("loss_alpha_entropy", "loss_dynamic_vs_static_reg", "loss_ray_reg", "loss_static_reg",
+                                   "loss_dynamic_reg")):
+                d[k + sfx] = r[i]
+        else:
+            d["dists" + sfx] = dists
+            d["z_vals" + sfx] = z
+        return d
+    z0 = z_vals if z_vals is not None else extra["z_vals0"]
+    res = to_dict(oc, z0, extra.get("dists0"), "0")
+    if Ni > 0:
+        res.update(to_dict(of, extra["z_vals"], extra.get("dists"), ""))
+        res["z_std"] = extra["z_std"]
+    res["_z_vals0"], res["_z_all"] = z0, extra.get("z_vals")
+    res["_z_samples"] = extra.get("z_samples", z_samples)
+    if camera is not None:
+        res["_rays"] = (extra["rays_o"], extra["rays_d"], extra["viewdirs"])
+    return res
+
+
 class Pose7ToMat12(Function):
     """[tx,ty,tz,qx,qy,qz,qw] -> [R(q) row-major | t] with pypose's gradient convention
     (models/star__.py:191-196 via pp.SE3.Act / pp.SO3.Act): the gradient returned for the 7-vector is

@@ -118,9 +118,47 @@ def _coarse_to_fine(net_call, training, pts, z_vals, rays_o, rays_d, N_importanc
     return result
 
 
+# Inference (no autograd graph wanted): the whole coarse -> fine render is ONE C-ABI call (star_render_forward: every
+# kernel of the V + 1 coarse nets, compositing, inverse-CDF sampling / merge, the V + 1 fine nets and compositing queued
+# without returning to Python).  Training keeps the staged path below, whose stages have backward twins.
+FUSED_INFERENCE = True
+
+
+def _fused(star_network, pts, viewdirs, z_vals, rays_o, rays_d, N_importance, pose, step, u, z_samples):
+    if not FUSED_INFERENCE or torch.is_grad_enabled() or not hasattr(star_network, "static_coarse_nerf"):
+        return None
+    sc = star_network.static_coarse_nerf
+    if star_network.training and sc.raw_noise_std > 0.0 and pose is None:
+        return None                                    # density noise (:335): staged path
+    Ni = N_importance if star_network.N_importance > 0 else 0
+    if N_importance > 0 and star_network.N_importance <= 0:
+        raise ValueError("N_importance should be positive")
+    sf = star_network.static_fine_nerf if Ni > 0 else None
+    dyn_c, dyn_f, pose12, scales = [], [], None, (None, None)
+    if pose is not None:
+        if pose.dim() not in (2, 3):
+            raise NotImplementedError
+        dyn_c = list(star_network.dynamic_coarse_nerfs)
+        dyn_f = list(star_network.dynamic_fine_nerfs) if Ni > 0 else []
+        if not dyn_c:
+            return None
+        pose12 = torch.stack([F_.pose_to_mat12(pose[i]) for i in range(len(dyn_c))])
+        m = dyn_c[0]
+        scales = (m.embedder.scale(step, viewdirs.device, pad_to=64), m.embedder_dirs.scale(step, viewdirs.device, pad_to=32))
+    res = F_.render_forward((sc, sf), (dyn_c, dyn_f), sc._prec(), rays_o, rays_d, viewdirs, Ni, z_vals=z_vals, pts=pts,
+                            pose12=pose12, det=not star_network.training, u=u, z_samples=z_samples,
+                            white_bkgd=sc.white_bkgd, far_dist=star_network.far_dist, chunk=star_network.chunk,
+                            test=not star_network.training, enc_scales=scales)
+    return {k: v for k, v in res.items() if not k.startswith("_")}
+
+
 def render_star_appinit(star_network, pts, viewdirs, z_vals, rays_o, rays_d, N_importance, *, u=None,
                         z_samples=None):
     """(:115-149)."""
+    fused = _fused(star_network, pts, viewdirs, z_vals, rays_o, rays_d, N_importance, None, None, u, z_samples)
+    if fused is not None:
+        return fused
+
     def call(p, z, coarse):
         return star_network(p, viewdirs, z, rays_d, is_coarse=coarse)
     return _coarse_to_fine(call, star_network.training, pts, z_vals, rays_o, rays_d, N_importance, u, z_samples)
@@ -129,6 +167,10 @@ def render_star_appinit(star_network, pts, viewdirs, z_vals, rays_o, rays_d, N_i
 def render_star_online(star_network, pts, viewdirs, z_vals, rays_o, rays_d, N_importance, pose, step=None, *,
                        u=None, z_samples=None):
     """(:249-298)."""
+    fused = _fused(star_network, pts, viewdirs, z_vals, rays_o, rays_d, N_importance, pose, step, u, z_samples)
+    if fused is not None:
+        return fused
+
     def call(p, z, coarse):
         return star_network(p, viewdirs, z, rays_d, pose, is_coarse=coarse, step=step)
     return _coarse_to_fine(call, star_network.training, pts, z_vals, rays_o, rays_d, N_importance, u, z_samples)

@@ -80,7 +80,8 @@ int star_pack_weights(const StarNetDesc* d, const float* flat_master, void* pack
 /* ---- a1: models/rendering__.py:75-112  sample_pts --------------------------------------------
  * t_vals[Nc] = torch.linspace(0,1,Nc) from the host (its symmetric formula is not i/(n-1)).
  * t_rand[R*Nc] or NULL: injected stratified jitter (perturb > 0 and is_train).
- * Outputs pts[R,Nc,3], z_vals[R,Nc].  Bit-exact vs the reference ops (no FMA contraction). */
+ * Outputs pts[R,Nc,3] (NULL: depths only -- the MLP kernels can form the positions themselves), z_vals[R,Nc].
+ * Bit-exact vs the reference ops (no FMA contraction). */
 int star_sample_pts(const float* rays_o, const float* rays_d, const float* t_vals, const float* t_rand,
                     float near_, float far_, int R, int Nc, int lindisp, float* pts, float* z_vals,
                     void* stream);
@@ -208,6 +209,58 @@ int star_hierarchical(const float* z_vals, const float* weights, const float* u,
  * ill-conditioned where the coarse pdf is small). */
 int star_merge_samples(const float* z_vals, const float* z_samples, const float* rays_o, const float* rays_d,
                        int R, int Nc, int Ni, float* z_all, float* z_std, float* pts_fine, void* stream);
+
+/* ---- a10 + a11 in ONE call: models/rendering__.py:115-149 (render_star_appinit), :249-298 (render_star_online),
+ *      models/star__.py:119-225 (STaR.forward_chunk) -----------------------------------------------------------
+ * star_render_forward runs the whole coarse -> fine render of R rays on `stream` with no host round trip:
+ *   [ray generation from a pinhole camera (get_rays, :41-55)] -> [stratified depths (sample_pts, :87-106)] ->
+ *   coarse MLPs of the static field and of the V object fields (positions formed in-kernel from rays + depths, or read
+ *   from a caller-supplied pts; samples moved into each object frame by pose12[v]; raw outputs written in place into the
+ *   [R,V,S] layout) -> compositing + regularisers -> inverse-CDF sampling, merge, z_std -> fine MLPs on all Nc + Ni
+ *   samples -> compositing.  2 V + 6 (+2) launches for the vanilla path, e.g. 18 for V = 5.
+ * Inference only (no activations are kept); training goes through the per-stage entries and their backward twins.
+ * Pointers are device pointers unless noted; any output pointer may be NULL except rgb / disp / acc / depth / weights.
+ * With V == 0 only the first five StarMultiOut fields are used (+ dists). */
+typedef struct StarRenderCfg {
+  int32_t R, Nc, Ni, V;
+  int32_t precision;                 /* STAR_PREC_* (| STAR_PREC_FLAG_*) of every field MLP                         */
+  int32_t n_blocks_static, n_blocks_dynamic, L_xyz, L_dir;
+  int32_t white_bkgd, lindisp, test; /* test: eval extras of raw2outputs_star (rgb_dynamic_all), star__.py:224      */
+  int32_t chunk;                     /* ray-chunk length of the regulariser means (star__.py:84-112)                 */
+  float near_, far_, far_dist;
+} StarRenderCfg;
+
+typedef struct StarRenderIn {
+  /* rays: explicit [R,3] arrays, or rays_o == NULL and a camera: rays of pixel rows [row0, row0 + nrows) of an H x W
+   * view (R == nrows * W) are generated into the workspace (star_get_rays arithmetic)                               */
+  const float* rays_o; const float* rays_d; const float* viewdirs;
+  int32_t H, W, row0, nrows; float fx, fy, cx, cy; const float* c2w;
+  /* coarse depths: z_vals [R,Nc] given by the caller (optionally with pts [R,Nc,3]), or z_vals == NULL and
+   * t_vals [Nc] (= torch.linspace(0,1,Nc)) + optional t_rand [R,Nc] jitter: sampled here                          */
+  const float* z_vals; const float* pts; const float* t_vals; const float* t_rand;
+  /* inverse-CDF draws: u [R,Ni], or u_det [Ni] (= torch.linspace(0,1,Ni), deterministic / eval); z_samples [R,Ni]
+   * injects the fine samples themselves (skips the inversion)                                                      */
+  const float* u; const float* u_det; const float* z_samples;
+  const float* pose12;               /* [V,12] row-major [R | t] per object (V > 0)                                  */
+  const float* enc_scale_xyz; const float* enc_scale_dir;   /* BARF masks of the object nets, or NULL              */
+  const void* packed_static_coarse; const void* packed_static_fine;
+  const void* const* packed_dynamic_coarse;  /* HOST arrays of V device pointers (star_pack_weights images)        */
+  const void* const* packed_dynamic_fine;
+} StarRenderIn;
+
+typedef struct StarRenderOut {
+  StarMultiOut coarse, fine;         /* per-pass outputs ("...0" keys / plain keys of the reference dict)            */
+  float* dists0; float* dists;       /* [R,Nc] / [R,Nc+Ni], V == 0 only (raw2outputs' `dists`), may be NULL         */
+  float* z_vals0;                    /* [R,Nc]: the coarse depths when sampled here (NULL if the caller gave z_vals) */
+  float* z_vals;                     /* [R,Nc+Ni] merged depths of the fine pass                                     */
+  float* z_samples;                  /* [R,Ni] (NULL when injected) */
+  float* z_std;                      /* [R] */
+  float* rays_o; float* rays_d; float* viewdirs;   /* camera mode: where the generated rays go ([R,3] each, or NULL) */
+} StarRenderOut;
+
+size_t star_render_workspace_bytes(const StarRenderCfg* cfg);
+int star_render_forward(const StarRenderCfg* cfg, const StarRenderIn* in, const StarRenderOut* out, void* workspace,
+                        size_t workspace_bytes, int32_t* status, void* stream);
 
 /* ================================================================================================
  * a12: the mip-NeRF / integrated-positional-encoding variant

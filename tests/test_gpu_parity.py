@@ -499,3 +499,55 @@ def test_get_rays_kernel_bit_exact(H, W):
     ro2, rd2, vd2 = F_.get_rays(H, W, K, cu(c2w), rows=(H // 3, H // 2), want_viewdirs=True)
     assert torch.equal(rd2.cpu(), rd_ref[H // 3:H // 3 + H // 2])
     assert_close(vd2, rd_ref[H // 3:H // 3 + H // 2] / rd_ref[H // 3:H // 3 + H // 2].norm(dim=-1, keepdim=True), 2e-7)
+
+
+# ------------------------------------------------------------------------------------------ a10 + a11 in one C-ABI call
+@pytest.mark.parametrize("V,prec", [(0, "fp32"), (2, "fp32"), (0, "fp16"), (3, "fp16")])
+def test_single_call_render_equals_the_staged_path(V, prec, monkeypatch):
+    """star_render_forward (one call: V + 1 coarse nets -> compositing -> sample_pdf / merge -> V + 1 fine nets ->
+    compositing, positions formed in-kernel) returns bit for bit what the staged per-function path returns, for every
+    key of the reference's output dictionary; also from a camera (ray generation inside the call)."""
+    net, _ = make_star(V, 24, 64, V == 0, seed=13, training=False)
+    net.set_precision(prec)
+    ro, rd = so.carla_rays(333, seed=2)
+    ro, rd = cu(ro), cu(rd)
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    pose = cu(so.random_poses7(V, seed=5)) if V else None
+    with torch.no_grad():
+        pts, z = R_.sample_pts(ro, rd, 0.03, 0.8, 20, is_train=False)
+        outs = {}
+        for fused in (True, False):
+            monkeypatch.setattr(R_, "FUSED_INFERENCE", fused)
+            n0 = F_.LAUNCH_COUNTER["calls"]
+            outs[fused] = (R_.render_star_online(net, pts, vd, z, ro, rd, 24, pose) if V else
+                           R_.render_star_appinit(net, pts, vd, z, ro, rd, 24))
+            outs[fused]["_calls"] = F_.LAUNCH_COUNTER["calls"] - n0
+    a, b = outs[True], outs[False]
+    a.pop("_calls"), b.pop("_calls")
+    assert set(a.keys()) == set(b.keys())
+    for k in b:
+        if b[k] is None:
+            assert a[k] is None, k
+        else:
+            assert torch.equal(a[k], b[k]), k
+    # the same render starting from the camera: rays, depths and everything else made inside the one call
+    if V == 0:
+        H, W = 12, 16
+        K = torch.tensor([[20.0, 0, 8.0], [0, 20.0, 6.0], [0, 0, 1.0]])
+        g = torch.Generator().manual_seed(3)
+        q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+        c2w = cu(torch.cat([q, torch.randn(3, 1, generator=g) * 0.1], 1))
+        with torch.no_grad():
+            res = F_.render_forward((net.static_coarse_nerf, net.static_fine_nerf), ([], []), net.static_coarse_nerf._prec(),
+                                    None, None, None, 24, near=0.03, far=0.8, N_samples=20, white_bkgd=True,
+                                    camera=(H, W, K, c2w, (0, H)))
+            ro2, rd2 = R_.get_rays(H, W, K, c2w)
+            ro2, rd2 = ro2.reshape(-1, 3), rd2.reshape(-1, 3)
+            vd2 = rd2 / rd2.norm(dim=-1, keepdim=True)
+            pts2, z2 = R_.sample_pts(ro2, rd2, 0.03, 0.8, 20, is_train=False)
+            monkeypatch.setattr(R_, "FUSED_INFERENCE", False)
+            ref = R_.render_star_appinit(net, pts2, vd2, z2, ro2, rd2, 24)
+        assert torch.equal(res["_rays"][1], rd2) and torch.equal(res["_z_vals0"], z2)
+        assert_close(res["_rays"][2], vd2, 2e-7)
+        for k in ("rgb0", "weights0"):
+            assert_close(res[k], ref[k], 1e-5, msg=k)      # (viewdirs differ in the last bit: sqrt + division order)
