@@ -8,11 +8,12 @@ burakcuhadar/3D-MOT-using-Neural-Radiance-Fields behind the reference's own Pyth
 `star_b200.install()` registers the mirrors as `models.rendering__`, `models.star__`, `models.nerf`,
 `models.embedder`, `models.resnet`, `models.types__`, `models.star_mipnerf`, `models.mipnerf`,
 `models.rendering_starmip`, `models.loss` in sys.modules so that the reference's train
-scripts pick them up unmodified.  `star_b200.optim` holds the fused clip + Adam step."""
+scripts pick them up unmodified.  `star_b200.optim` holds the fused clip + Adam step,
+`star_b200.evaluation` the multi-frame / multi-view test loop of online tracking, `star_b200.parallel` the ray sharding."""
 import sys
 
 from . import _capi, functional, parallel  # noqa: F401
-from . import metrics, mip_functional, optim  # noqa: F401
+from . import evaluation, metrics, mip_functional, optim  # noqa: F401
 from .models import loss  # noqa: F401
 from .models import embedder, mipnerf, nerf, rendering__, rendering_starmip, resnet, star__, star_mipnerf, types__  # noqa: F401
 from .models.star__ import STaR  # noqa: F401

@@ -352,3 +352,58 @@ def test_compute_2d_iou_full_view_against_the_oracle():
         M_.compute_2d_iou(c(T), c(sem)[:-1])
     with pytest.raises(star_b200._capi.StarError):
         M_.compute_2d_iou(T, sem)            # CPU tensors: no fallback
+
+
+# ------------------------------------------------------------------------------------------ 8(f) row 4: evaluation driver
+def test_evaluate_sequence_matches_per_item_staged_renders():
+    """evaluation.evaluate_sequence (views x frames, each item one star_render_forward call from the camera) against the
+    same items rendered through the staged reference-API path and measured with plain torch / metrics.compute_2d_iou."""
+    import math
+    from star_b200 import evaluation as E_, metrics as M_
+    from star_b200.models import rendering__ as R_
+    from oracle import ref_harness, star_oracle as so
+    V, Nc, Ni, H, W, F = 2, 16, 16, 10, 14, 3
+    net = star_b200.STaR(ref_harness.make_args(num_vehicles=V, N_importance=Ni, chunk=64, white_bkgd=False))
+    net.load_state_dict(so.init_star_params(V, Ni, seed=8, bias_std=0.02))
+    net.to(DEV).train()                       # the driver switches to eval and back
+    focal = 0.5 * W
+    K = torch.tensor([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1.0]])
+    g = torch.Generator().manual_seed(2)
+    cams = []
+    for _ in range(2):
+        q, _r = torch.linalg.qr(torch.randn(3, 3, generator=g))
+        cams.append(torch.cat([q, torch.randn(3, 1, generator=g) * 0.05], 1))
+    cams = torch.stack(cams)
+    poses = torch.stack([so.random_poses7(V, seed=20 + f) for f in range(F - 1)]).to(DEV)
+    targets = torch.rand(2, F, H * W, 3, generator=g)
+    masks = torch.rand(2, F, H * W, generator=g) < 0.3
+    masks[1, 2] = False                       # a frame without dynamic pixels: excluded from the IoU mean
+    out = E_.evaluate_sequence(net, cams, poses, H, W, K, 0.03, 0.8, Nc, Ni, F, targets=targets, semantic_masks=masks,
+                               keep_images=True)
+    assert net.training and out["table"].shape == (2, F, len(E_.METRIC_KEYS)) and len(out["images"]) == 2 * F
+    net.eval()
+    ious = []
+    with torch.no_grad():
+        for v in range(2):
+            for f in range(F):
+                ro, rd = R_.get_rays(H, W, K, cams[v].to(DEV))
+                ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+                vd = rd / rd.norm(dim=-1, keepdim=True)
+                pts, z = R_.sample_pts(ro, rd, 0.03, 0.8, Nc, is_train=False)
+                pose = E_.frame_poses(poses, f, V, DEV)
+                ref = R_.render_star_online(net, pts, vd, z, ro, rd, Ni, pose)
+                tgt, m = targets[v, f].to(DEV), masks[v, f].to(DEV)
+                assert_close(out["images"][(v, f)]["rgb"], ref["rgb"], 2e-5, msg="rgb")     # (viewdirs: last-bit differences)
+                mse = ((ref["rgb"] - tgt) ** 2).mean()
+                row = out["table"][v, f]
+                assert_close(row[0], mse, 1e-6, msg="mse")
+                assert_close(row[1], -10.0 * torch.log10(mse), 1e-4, msg="psnr")
+                if bool(m.any()):
+                    assert_close(row[2], -10.0 * torch.log10(((ref["rgb"] - tgt)[m] ** 2).mean()), 1e-3, msg="psnr_dynamic")
+                iou, _ = M_.compute_2d_iou(ref["dynamic_transmittance"], m)
+                assert abs(float(row[4]) - iou) < 1e-6 + 0.02 * (iou > 0)     # (a transmittance within rounding of 0.1 may flip)
+                assert int(row[5]) == int(m.sum())
+                if int(m.sum()) > 0:
+                    ious.append(float(row[4]))
+    assert abs(out["mean"]["iou_2d"] - sum(ious) / len(ious)) < 1e-6
+    assert math.isfinite(out["mean"]["psnr"]) and math.isfinite(out["mean"]["psnr_static"])

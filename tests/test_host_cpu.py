@@ -245,3 +245,23 @@ def test_train_step_abi_argument_checks_and_host_logic():
         L_.photometric_loss(torch.rand(4, 3), torch.rand(4, 3), torch.rand(4, 3))
     with pytest.raises(ValueError):
         L_.photometric_loss(torch.rand(4, 3), torch.rand(5, 3), torch.rand(4, 3))
+
+
+def test_online_frame_scheduler_follows_the_reference_callback():
+    """callbacks/online_training_callback.py:91-162: first admission when the loss reaches online_thres (threshold then
+    95e-5), later ones need > 70 epochs since the last admission AND the loss under the threshold; stop beyond num_frames."""
+    from star_b200.evaluation import OnlineFrameScheduler, frame_poses
+    s = OnlineFrameScheduler(online_thres=1e-3, initial_num_frames=5, num_frames=7, precrop_iters=2)
+    assert not s.epoch_end(0, 1e-9) and not s.epoch_end(1, 1e-9)          # precrop epochs are skipped
+    assert not s.epoch_end(2, 2e-3) and s.current_frame_num == 5
+    assert s.epoch_end(3, 1e-3) and s.current_frame_num == 6 and s.online_thres == 95e-5
+    for e in range(70):
+        assert not s.epoch_end(4 + e, 1e-9)                               # count 1..70: not yet
+    assert not s.epoch_end(74, 96e-5)                                     # count 71 but loss above the new threshold
+    assert s.epoch_end(75, 95e-5) and s.current_frame_num == 7 and not s.should_stop
+    for e in range(70):
+        s.epoch_end(76 + e, 1e-9)
+    assert s.epoch_end(146, 1e-9) and s.current_frame_num == 8 and s.should_stop
+    poses = torch.arange(2 * 3 * 7, dtype=torch.float32).view(2, 3, 7)
+    p0 = frame_poses(poses, 0, 3, "cpu")
+    assert torch.equal(p0, torch.tensor([[0, 0, 0, 0, 0, 0, 1.0]] * 3)) and torch.equal(frame_poses(poses, 2, 3, "cpu"), poses[1])
