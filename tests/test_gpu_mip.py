@@ -231,6 +231,8 @@ def test_mip_star_forward_end_to_end(V, training):
                               exact_sum=True)
     out = net(cu(ro), cu(vd), cu(pose) if V else None, t_rand=cu(t_rand), u_rand=cu(u_rand))
     assert set(out.keys()) == set(ref.keys())
+    from star_b200.models import types__ as T_      # the reference's TypedDicts (models/types__.py:36-87)
+    assert set(out.keys()) == set(T_.MIP_ONLINE_KEYS if V else T_.MIP_APPINIT_KEYS)
     for k, v in ref.items():
         assert out[k].shape == v.shape, (k, out[k].shape, v.shape)
     # coarse pass: identical frustums -> tight; fine pass: the PDF sampler amplifies 1e-7 weight differences
