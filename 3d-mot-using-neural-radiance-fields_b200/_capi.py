@@ -145,6 +145,29 @@ class StarError(RuntimeError):
     pass
 
 
+class _NvtxLib:
+    """STAR_B200_NVTX=1: every kernel-launching C-ABI call (those that take a stream) runs inside an NVTX range named
+    after the entry point, so that nsys / ncu timelines show the render path stage by stage."""
+
+    def __init__(self, L):
+        self._L = L
+
+    def __getattr__(self, name):
+        fn = getattr(self._L, name)
+        sig = _SIGS.get(name)
+        if sig is None or not sig[1] or sig[1][-1] is not c_f or sig[0] is not C.c_int:
+            return fn
+
+        def wrapped(*a):
+            torch.cuda.nvtx.range_push(name)
+            try:
+                return fn(*a)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        object.__setattr__(self, name, wrapped)
+        return wrapped
+
+
 def lib():
     """Loads libstar_b200.so once.  Missing library -> hard error (build with __graft_entry__.build())."""
     global _lib
@@ -159,6 +182,8 @@ def lib():
             fn.argtypes = args
         if L.star_abi_version() != ABI_VERSION:
             raise StarError("libstar_b200.so ABI mismatch")
+        if os.environ.get("STAR_B200_NVTX", "0") == "1":
+            L = _NvtxLib(L)
         _lib = L
     return _lib
 
