@@ -130,6 +130,10 @@ class MipRuntime:
         return self._flat, self._packed[precision]
 
 
+_WARNED_FP32_TRAINING = False
+EFFECTIVE_TRAIN_PRECISION = "fp32"      # what a training pass of the mip field computes in, whatever tier is selected
+
+
 class MipFieldRaw(Function):
     """One mip-NeRF field on (origins, directions, frustum edges) with an optional rigid transform of the ray into
     the object frame: RAW (pre-softplus density [R,S], pre-sigmoid rgb [R,S,3])
@@ -141,8 +145,16 @@ class MipFieldRaw(Function):
         R, S = bins.shape[0], bins.shape[1] - 1
         dev = origins.device
         need_grad = grad_mode and (any(ctx.needs_input_grad[7:]) or (pose12 is not None and ctx.needs_input_grad[6]))
-        if need_grad:
-            precision = _capi.PREC_F32     # the tensor-core tier of the mip field is forward-only: training runs in fp32
+        if need_grad and precision != _capi.PREC_F32:
+            # the tensor-core tier of the mip field is forward-only: a training pass runs the fp32 kernels -- said out
+            # loud once, and visible to callers (bench.py reports it) through EFFECTIVE_TRAIN_PRECISION
+            global _WARNED_FP32_TRAINING
+            if not _WARNED_FP32_TRAINING:
+                import warnings
+                warnings.warn("star_b200 mip field: the 16-bit tensor-core tier has no backward pass; this training pass "
+                              "(and every later one) runs on the fp32 CUDA-core kernels", RuntimeWarning, stacklevel=2)
+                _WARNED_FP32_TRAINING = True
+            precision = _capi.PREC_F32
         flat, packed = rt.refresh(precision)
         L = _capi.lib()
         freqs = freq_table(dev)
