@@ -477,6 +477,7 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
 // MN-major: M = output features) and up to 4 activation blocks (B operand, MN-major: N = input features), K = 128
 // samples = 8 MMAs of K = 16; a constant "ones" block gives db as 16 extra accumulator columns.
 #define DW_THREADS 192          // warp 0: producer, warp 1: MMA, warps 2..5: epilogue (TMEM lane quadrants 2,3,0,1)
+#define DW_THREADS_CVT 320      // fp16 tier: warps 2..9 convert the activation blocks (warps 2..5 also run the epilogue)
 #define DW_STAGE_BLOCKS 6
 #define DW_NSTAGE 2
 
@@ -505,7 +506,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t 
 // by the four epilogue warps, which are otherwise idle until the last tile, before the MMAs read them: the kernel is
 // HBM-bound (a stage of up to 96 KB lands every ~4000 cycles; the conversion is ~450 issue cycles per scheduler).
 template <bool CVT>
-__global__ void __launch_bounds__(DW_THREADS, 1)
+__global__ void __launch_bounds__(DW_THREADS_CVT, 1)
 dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8_t* __restrict__ stash,
              const uint8_t* __restrict__ gstash, int64_t ntiles, float* __restrict__ grad_flat, int* dbg) {
   extern __shared__ uint8_t smem_raw[];
@@ -525,12 +526,12 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
   if (tid == 0) {
     for (int i = 0; i < 2 * DW_NSTAGE; ++i) mbar_init(bar(i), 1);
     mbar_init(bar(4), 1);
-    for (int i = 0; i < DW_NSTAGE; ++i) mbar_init(bar(5 + i), 4);
+    for (int i = 0; i < DW_NSTAGE; ++i) mbar_init(bar(5 + i), (DW_THREADS_CVT - 64) / 32);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(sBars + 64, 512);
   // ones block: logical column 0 of every row = 1.0 (16-byte chunk 0 ^ (row & 7), element 0), zero elsewhere
-  for (int i = tid; i < TC_BLOCK_BYTES / 16; i += DW_THREADS) {
+  for (int i = tid; i < TC_BLOCK_BYTES / 16; i += (int)blockDim.x) {
     const int r = i >> 3, c = i & 7;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (c == (r & 7)) v.x = 0x3F80u;     // bf16 1.0
@@ -597,15 +598,21 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
       for (int64_t t = t0; t < t1; ++t) {
         mbar_wait(bar(st), ph, dbg, 5);
         uint4* a = reinterpret_cast<uint4*>(gbase + (size_t)st * DW_STAGE_BLOCKS * TC_BLOCK_BYTES + 2 * TC_BLOCK_BYTES);
-        for (int i = tid - 64; i < nvec; i += DW_THREADS - 64) {
-          uint4 v = a[i];
-          uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+        // 4 vectors per thread and trip, all loads first (nvec is a multiple of 4 * 256)
+        for (int i = tid - 64; i < nvec; i += 4 * (DW_THREADS_CVT - 64)) {
+          uint4 v[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-            w[j] = pack_16x2<false, false>(f.x, f.y);
+          for (int q4 = 0; q4 < 4; ++q4) v[q4] = a[i + q4 * (DW_THREADS_CVT - 64)];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(&v[q4]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+              w[j] = pack_16x2<false, false>(f.x, f.y);
+            }
+            a[i + q4 * (DW_THREADS_CVT - 64)] = v[q4];
           }
-          a[i] = v;
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -613,10 +620,10 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
         if (++st == DW_NSTAGE) { st = 0; ph ^= 1u; }
       }
     }
-    // epilogue: TMEM -> registers -> atomics into the flat gradient
+    // epilogue: TMEM -> registers -> atomics into the flat gradient (warps 2..5)
     const int q = warp & 3;
     const int n = q * 32 + lane;                      // output feature within the half
-    if (t1 > t0) {
+    if (t1 > t0 && warp < 6) {
       mbar_wait(bar(4), 0, dbg, 3);
       tc_fence_after();
       const uint32_t tl = tmem_base + (((uint32_t)(q * 32)) << 16);
@@ -851,7 +858,7 @@ int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed
     auto kern = fp16 ? dw_tc_kernel<true> : dw_tc_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
-    kern<<<n * splits, DW_THREADS, smem, st>>>(plan, tl.stash_blocks, tl.gstash_blocks, (const uint8_t*)stash,
+    kern<<<n * splits, fp16 ? DW_THREADS_CVT : DW_THREADS, smem, st>>>(plan, tl.stash_blocks, tl.gstash_blocks, (const uint8_t*)stash,
                                                (const uint8_t*)gstash, ntiles, grad_flat, nullptr);
     int rc = star_check_launch();
     if (rc) return rc;
