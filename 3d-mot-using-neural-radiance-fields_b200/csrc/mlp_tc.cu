@@ -609,8 +609,7 @@ int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, v
                                                  fp16);
   rc = star_check_launch();
   if (rc) return rc;
-  // the backward computes in bf16 on both tiers (mlp_tc_bwd.cu): its transposed weight stream is always bf16
-  return star_tc_pack_tstream(tl, ml, master, (uint8_t*)packed + tl.small_bytes + tl.stream_bytes, 0, st);
+  return star_tc_pack_tstream(tl, ml, master, (uint8_t*)packed + tl.small_bytes + tl.stream_bytes, fp16, st);
 }
 
 int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pts, const float* viewdirs,

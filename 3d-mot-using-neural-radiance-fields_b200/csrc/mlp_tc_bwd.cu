@@ -113,18 +113,42 @@ __device__ __forceinline__ void fold_jacobian(const uint32_t (&r)[16], const flo
 }
 
 // ============================================================================================ dX chain
-// The backward pass computes in bf16 on BOTH 16-bit tiers: dL/d(activation) of a 4096-ray batch reaches 1e-8, far below
-// fp16's range, and kind::f16 does not take mixed operand formats (bf16 x fp16 raises an illegal-instruction fault on
-// B200: tools/umma_probe.cu).  So the gradients G_l and the transposed weight stream are bf16 here, and the dW kernel
-// converts the fp16 tier's stashed activations to bf16 in shared memory (dw_tc_kernel<CVT>).
-template <bool POSE>
+// Operand formats of the backward pass.  kind::f16 does not take mixed formats (bf16 x fp16 raises an illegal-instruction
+// fault on B200: tools/umma_probe.cu), so the gradients G_l share the format of the weights / stashed activations they are
+// multiplied with: bf16 on the bf16 tier; fp16 on the fp16 tier.  dL/d(activation) of a 4096-ray batch reaches 1e-8,
+// below fp16's range, so the fp16 tier back-propagates SCALED gradients: scale = 2^k (exact) with k chosen per call from
+// the largest |upstream gradient| (grad_absmax_kernel; no host round trip) such that the scaled maximum lies in [64, 128) --
+// 2^9 of headroom to fp16's 65504 for growth along the chain (conversions saturate instead of producing inf), and every
+// value down to 2^-20 of the maximum stays a normal fp16 number with 11 significant bits (bf16 keeps 8 everywhere).  The dW
+// and pose epilogues multiply by 2^-k.  F16 = false: bf16, scale 1.
+__device__ __forceinline__ float grad_scale_of(const float* __restrict__ absmax) {
+  const uint32_t bits = __float_as_uint(*absmax);
+  const int e = (int)((bits >> 23) & 0xffu);            // biased exponent of max |g| (floor(log2) + 127)
+  if (e == 0 || e == 255) return 1.f;                   // zero / subnormal / non-finite upstream gradient: leave it alone
+  int k = 6 + 127 - e;                                  // 2^k * max in [64, 128)
+  k = k > 96 ? 96 : (k < -96 ? -96 : k);
+  return __uint_as_float((uint32_t)(127 + k) << 23);
+}
+
+__global__ void grad_absmax_kernel(const float* __restrict__ d_alpha, const float* __restrict__ d_rgb, int S, int64_t M,
+                                   int64_t ray_stride, float* __restrict__ absmax) {
+  float m = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / S, o = r * ray_stride + (i - r * S);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(d_alpha[o]), fabsf(d_rgb[o * 3])), fmaxf(fabsf(d_rgb[o * 3 + 1]), fabsf(d_rgb[o * 3 + 2]))));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(absmax), __float_as_uint(m));
+}
+
+template <bool F16, bool POSE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const StarPtsSrc pts,
                   const float* __restrict__ viewdirs, const float* __restrict__ pose12,
                   const float* __restrict__ sc_xyz, const float* __restrict__ sc_dir, int S, int64_t M,
                   const float* __restrict__ d_raw_alpha, const float* __restrict__ d_raw_rgb, int64_t ray_stride,
                   const uint8_t* __restrict__ stash, uint8_t* __restrict__ gstash, float* __restrict__ pose_acc,
-                  int* dbg) {
+                  const float* __restrict__ absmax, int* dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -264,7 +288,7 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           }
           mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
           tc_fence_after();
-          const uint32_t idesc = umma_idesc_16(TC_M, s.N, 1);
+          const uint32_t idesc = umma_idesc_16(TC_M, s.N, F16 ? 0 : 1);
           const uint64_t a0 = desc_a0 + (uint64_t)(s.a_kb * (TC_KB_BYTES >> 4));
           const uint64_t b0 = desc_w0 + (uint64_t)(stage * (TC_STAGE_BYTES >> 4));
           if (elect_one_sync()) {
@@ -296,6 +320,7 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     float pacc[POSE ? 27 : 1];
 #pragma unroll
     for (int i = 0; i < (POSE ? 27 : 1); ++i) pacc[i] = 0.f;
+    const float gscale = F16 ? grad_scale_of(absmax) : 1.f;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t gi = tile * TC_M + row;
       const bool valid = gi < M;
@@ -304,8 +329,8 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
       if (valid) {
         const int64_t r = gi / S;
         const int64_t o = r * ray_stride + (gi - r * S);
-        da = d_raw_alpha[o];
-        dc0 = d_raw_rgb[o * 3 + 0]; dc1 = d_raw_rgb[o * 3 + 1]; dc2 = d_raw_rgb[o * 3 + 2];
+        da = d_raw_alpha[o] * gscale;         // (exact: a power of two)
+        dc0 = d_raw_rgb[o * 3 + 0] * gscale; dc1 = d_raw_rgb[o * 3 + 1] * gscale; dc2 = d_raw_rgb[o * 3 + 2] * gscale;
         if (has_pose) {
           star_load_pt(pts, gi, r, pw[0], pw[1], pw[2]);
           dw[0] = viewdirs[r * 3 + 0]; dw[1] = viewdirs[r * 3 + 1]; dw[2] = viewdirs[r * 3 + 2];
@@ -447,7 +472,11 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             for (int j = 0; j < 16; ++j) v[j] = 0.f;
           }
           // (the gstash copy of this block is a bulk store issued by the producer warp once the block is complete)
-          store_row16<false, false>(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, v);
+          if (F16) {    // saturating conversion: a gradient that outgrows the headroom clamps to 65504 instead of inf
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], -65504.f), 65504.f);
+          }
+          store_row16<F16, false>(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, v);
           fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
@@ -456,10 +485,11 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
       }
     }
     if (has_pose) {
+      const float inv = 1.f / gscale;
 #pragma unroll
       for (int i = 0; i < 27; ++i) {
         const float s = warp_sum(pacc[i]);
-        if (lane == 0) atomicAdd(&pose_acc[i], s);
+        if (lane == 0) atomicAdd(&pose_acc[i], s * inv);
       }
     }
   }
@@ -477,7 +507,6 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
 // MN-major: M = output features) and up to 4 activation blocks (B operand, MN-major: N = input features), K = 128
 // samples = 8 MMAs of K = 16; a constant "ones" block gives db as 16 extra accumulator columns.
 #define DW_THREADS 192          // warp 0: producer, warp 1: MMA, warps 2..5: epilogue (TMEM lane quadrants 2,3,0,1)
-#define DW_THREADS_CVT 320      // fp16 tier: warps 2..9 convert the activation blocks (warps 2..5 also run the epilogue)
 #define DW_STAGE_BLOCKS 6
 #define DW_NSTAGE 2
 
@@ -502,13 +531,13 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t 
   return d;
 }
 
-// CVT (fp16 tier): the activation blocks arrive as fp16 (what the forward multiplied) and are converted to bf16 in place
-// by the four epilogue warps, which are otherwise idle until the last tile, before the MMAs read them: the kernel is
-// HBM-bound (a stage of up to 96 KB lands every ~4000 cycles; the conversion is ~450 issue cycles per scheduler).
-template <bool CVT>
-__global__ void __launch_bounds__(DW_THREADS_CVT, 1)
+// F16: operand format (both the gradient and the activation blocks; see the note on formats above).  The fp16 tier's
+// gradients are scaled by 2^k: the epilogue multiplies the accumulators by 2^-k.
+template <bool F16>
+__global__ void __launch_bounds__(DW_THREADS, 1)
 dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8_t* __restrict__ stash,
-             const uint8_t* __restrict__ gstash, int64_t ntiles, float* __restrict__ grad_flat, int* dbg) {
+             const uint8_t* __restrict__ gstash, int64_t ntiles, float* __restrict__ grad_flat,
+             const float* __restrict__ absmax, int* dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -526,15 +555,14 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
   if (tid == 0) {
     for (int i = 0; i < 2 * DW_NSTAGE; ++i) mbar_init(bar(i), 1);
     mbar_init(bar(4), 1);
-    for (int i = 0; i < DW_NSTAGE; ++i) mbar_init(bar(5 + i), (DW_THREADS_CVT - 64) / 32);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(sBars + 64, 512);
   // ones block: logical column 0 of every row = 1.0 (16-byte chunk 0 ^ (row & 7), element 0), zero elsewhere
-  for (int i = tid; i < TC_BLOCK_BYTES / 16; i += (int)blockDim.x) {
+  for (int i = tid; i < TC_BLOCK_BYTES / 16; i += DW_THREADS) {
     const int r = i >> 3, c = i & 7;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (c == (r & 7)) v.x = 0x3F80u;     // bf16 1.0
+    if (c == (r & 7)) v.x = F16 ? 0x3C00u : 0x3F80u;     // 1.0
     reinterpret_cast<uint4*>(gbase + (sOnes - base))[i] = v;
   }
   fence_proxy_async_smem();
@@ -561,14 +589,14 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
     // warp-uniform control flow, one elected lane issues the tcgen05 instructions (see elect_one_sync)
     {
       const int N = 64 * it.n_a;
-      const uint32_t idesc = umma_idesc_16(128, N, 1) | (1u << 15) | (1u << 16);      // bf16, both operands MN-major
-      const uint32_t idesc1 = umma_idesc_16(128, 16, 1) | (1u << 15) | (1u << 16);
+      const uint32_t idesc = umma_idesc_16(128, N, F16 ? 0 : 1) | (1u << 15) | (1u << 16);      // both operands MN-major
+      const uint32_t idesc1 = umma_idesc_16(128, 16, F16 ? 0 : 1) | (1u << 15) | (1u << 16);
       const bool with_bias = it.b_off >= 0;
       const uint64_t d1 = umma_desc_mn_sw128(sOnes, TC_BLOCK_BYTES);
       uint32_t st = 0, ph = 0;
       uint32_t acc = 0u;
       for (int64_t t = t0; t < t1; ++t) {
-        mbar_wait(bar(CVT ? 5 + st : st), ph, dbg, 2);
+        mbar_wait(bar(st), ph, dbg, 2);
         tc_fence_after();
         const uint32_t g_addr = sStage + st * DW_STAGE_BLOCKS * TC_BLOCK_BYTES, a_addr = g_addr + 2 * TC_BLOCK_BYTES;
         const uint64_t dg = umma_desc_mn_sw128(g_addr, TC_BLOCK_BYTES), da = umma_desc_mn_sw128(a_addr, TC_BLOCK_BYTES);
@@ -592,38 +620,11 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
       }
     }
   } else {
-    if (CVT) {   // fp16 -> bf16 of the stage's activation blocks, in step with the producer
-      uint32_t st = 0, ph = 0;
-      const int nvec = it.n_a * (TC_BLOCK_BYTES / 16);
-      for (int64_t t = t0; t < t1; ++t) {
-        mbar_wait(bar(st), ph, dbg, 5);
-        uint4* a = reinterpret_cast<uint4*>(gbase + (size_t)st * DW_STAGE_BLOCKS * TC_BLOCK_BYTES + 2 * TC_BLOCK_BYTES);
-        // 4 vectors per thread and trip, all loads first (nvec is a multiple of 4 * 256)
-        for (int i = tid - 64; i < nvec; i += 4 * (DW_THREADS_CVT - 64)) {
-          uint4 v[4];
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) v[q4] = a[i + q4 * (DW_THREADS_CVT - 64)];
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint32_t* w = reinterpret_cast<uint32_t*>(&v[q4]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-              w[j] = pack_16x2<false, false>(f.x, f.y);
-            }
-            a[i + q4 * (DW_THREADS_CVT - 64)] = v[q4];
-          }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(5 + st));
-        if (++st == DW_NSTAGE) { st = 0; ph ^= 1u; }
-      }
-    }
-    // epilogue: TMEM -> registers -> atomics into the flat gradient (warps 2..5)
+    // epilogue: TMEM -> registers -> atomics into the flat gradient
     const int q = warp & 3;
     const int n = q * 32 + lane;                      // output feature within the half
-    if (t1 > t0 && warp < 6) {
+    const float unscale = F16 ? 1.f / grad_scale_of(absmax) : 1.f;
+    if (t1 > t0) {
       mbar_wait(bar(4), 0, dbg, 3);
       tc_fence_after();
       const uint32_t tl = tmem_base + (((uint32_t)(q * 32)) << 16);
@@ -634,13 +635,13 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (c0 + j < it.k_valid) atomicAdd(wrow + c0 + j, __uint_as_float(r[j]));
+          if (c0 + j < it.k_valid) atomicAdd(wrow + c0 + j, __uint_as_float(r[j]) * unscale);
       }
       if (it.b_off >= 0) {
         uint32_t r[16];
         tmem_ld16(tl + 256u, r);
         tmem_wait_ld();
-        atomicAdd(grad_flat + it.b_off + n, __uint_as_float(r[0]));
+        atomicAdd(grad_flat + it.b_off + n, __uint_as_float(r[0]) * unscale);
       }
     }
   }
@@ -801,7 +802,8 @@ int star_tc_pack_tstream(const TcLayout& tl, const MlpLayout& ml, const float* m
 }
 
 size_t star_tc_gstash_bytes(const TcLayout& tl, int64_t n_samples) {
-  return (size_t)(((n_samples + 127) / 128 + 1) / 2 * 2) * (size_t)tl.gstash_blocks * TC_BLOCK_BYTES;
+  // (+ 256 bytes at the end: the |upstream gradient| maximum of the call, grad_absmax_kernel)
+  return (size_t)(((n_samples + 127) / 128 + 1) / 2 * 2) * (size_t)tl.gstash_blocks * TC_BLOCK_BYTES + 256;
 }
 
 int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
@@ -813,16 +815,28 @@ int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // ---- 0. fp16 tier: largest |upstream gradient| of the call -> the power-of-two gradient scale (read on the device)
+  float* absmax = reinterpret_cast<float*>((uint8_t*)gstash + star_tc_gstash_bytes(tl, M) - 256);
+  if (fp16) {
+    cudaError_t e = cudaMemsetAsync(absmax, 0, 4, st);
+    if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
+    int64_t b = (M + 255) / 256;
+    if (b > 148 * 8) b = 148 * 8;
+    grad_absmax_kernel<<<(int)b, 256, 0, st>>>(d_raw_alpha, d_raw_rgb, S, M, ray_stride, absmax);
+    int rc = star_check_launch();
+    if (rc) return rc;
+  }
   // ---- 1. dX chain
   {
     const int grid = (int)(ntiles < sms ? ntiles : sms);
     const BwdSmem sl = bwd_smem_layout(tl.small_bytes);
-    auto kern = pose12 != nullptr ? mlp_bwd_tc_kernel<true> : mlp_bwd_tc_kernel<false>;
+    auto kern = pose12 != nullptr ? (fp16 ? mlp_bwd_tc_kernel<true, true> : mlp_bwd_tc_kernel<false, true>)
+                                  : (fp16 ? mlp_bwd_tc_kernel<true, false> : mlp_bwd_tc_kernel<false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
     if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
     kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
                                               d_raw_alpha, d_raw_rgb, ray_stride, (const uint8_t*)stash, (uint8_t*)gstash,
-                                              pose_acc, nullptr);
+                                              pose_acc, absmax, nullptr);
     int rc = star_check_launch();
     if (rc) return rc;
   }
@@ -858,8 +872,8 @@ int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed
     auto kern = fp16 ? dw_tc_kernel<true> : dw_tc_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
-    kern<<<n * splits, fp16 ? DW_THREADS_CVT : DW_THREADS, smem, st>>>(plan, tl.stash_blocks, tl.gstash_blocks, (const uint8_t*)stash,
-                                               (const uint8_t*)gstash, ntiles, grad_flat, nullptr);
+    kern<<<n * splits, DW_THREADS, smem, st>>>(plan, tl.stash_blocks, tl.gstash_blocks, (const uint8_t*)stash,
+                                               (const uint8_t*)gstash, ntiles, grad_flat, absmax, nullptr);
     int rc = star_check_launch();
     if (rc) return rc;
   }

@@ -167,7 +167,7 @@ def test_c4_reference_batch_training_step_against_the_oracle():
             assert_close(out[k], v, 1e-6, rtol=1e-4, msg=k)
         else:
             assert_close(out[k], v, 1e-4, rtol=1e-4 if k.startswith("disp") else 0.0, msg=k)
-    assert_close(loss, loss_ref, 1e-5, msg="loss")
+    assert_close(loss, loss_ref, 1e-5, rtol=1e-5, msg="loss")     # (the multi-field rgb is not bounded by 1: loss ~ 40)
     rel = lambda a, b: float((a.detach().cpu() - b).norm() / (b.norm() + 1e-30))
     # fp32 gradients through ReLU masks / 2^9-frequency encodings agree to ~1e-3 between two evaluation orders
     assert rel(pose_g.grad, pose_o.grad) < 2e-2, rel(pose_g.grad, pose_o.grad)
