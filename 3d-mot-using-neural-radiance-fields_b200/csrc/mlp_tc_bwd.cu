@@ -472,11 +472,8 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             for (int j = 0; j < 16; ++j) v[j] = 0.f;
           }
           // (the gstash copy of this block is a bulk store issued by the producer warp once the block is complete)
-          if (F16) {    // saturating conversion: a gradient that outgrows the headroom clamps to 65504 instead of inf
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fminf(fmaxf(v[j], -65504.f), 65504.f);
-          }
-          store_row16<F16, false>(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, v);
+          // (fp16: saturating conversion -- a gradient that outgrows the headroom clamps to 65504 instead of becoming inf)
+          store_row16<F16, false, true>(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, v);
           fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();

@@ -92,15 +92,15 @@ __device__ __forceinline__ void encode_slice(const float (&p)[3], const float* _
 // write 16 fp32 values as 16-bit operands into 16-byte chunks ch0, ch0+1 of row `row` of a SW128 K-block
 // `gblock` (nullable): the same two chunks also go to the 16 KB stash block at that global address (same
 // swizzled offsets), for the backward pass.  kblock_saddr == 0: global copy only.
-template <bool FP16, bool RELU>
+template <bool FP16, bool RELU, bool SAT = false>
 __device__ __forceinline__ void store_row16(uint32_t kblock_saddr, int row, int ch0, const float (&v)[16],
                                             uint8_t* gblock = nullptr) {
   const uint32_t x = (uint32_t)row & 7u;
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)(ch0 + c)) ^ x) << 4);
-    const uint32_t p0 = pack_16x2<FP16, RELU>(v[8 * c + 0], v[8 * c + 1]), p1 = pack_16x2<FP16, RELU>(v[8 * c + 2], v[8 * c + 3]),
-                   p2 = pack_16x2<FP16, RELU>(v[8 * c + 4], v[8 * c + 5]), p3 = pack_16x2<FP16, RELU>(v[8 * c + 6], v[8 * c + 7]);
+    const uint32_t p0 = pack_16x2<FP16, RELU, SAT>(v[8 * c + 0], v[8 * c + 1]), p1 = pack_16x2<FP16, RELU, SAT>(v[8 * c + 2], v[8 * c + 3]),
+                   p2 = pack_16x2<FP16, RELU, SAT>(v[8 * c + 4], v[8 * c + 5]), p3 = pack_16x2<FP16, RELU, SAT>(v[8 * c + 6], v[8 * c + 7]);
     if (kblock_saddr != 0u) st_shared_v4(kblock_saddr + off, p0, p1, p2, p3);
     if (gblock != nullptr) *reinterpret_cast<uint4*>(gblock + off) = make_uint4(p0, p1, p2, p3);
   }

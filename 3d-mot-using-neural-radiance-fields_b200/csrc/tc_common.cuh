@@ -264,10 +264,13 @@ __host__ __device__ __forceinline__ uint32_t sw128_off(int row, int k) {
 
 // two fp32 -> packed 16-bit pair (lo in the low half); FP16 selects IEEE half instead of bfloat16;
 // RELU fuses max(x, 0) into the conversion (cvt.rn.relu)
-template <bool FP16, bool RELU = false>
+// SAT (fp16 only): saturate to +-65504 instead of producing inf (F2FP.SATFINITE: no extra instruction)
+template <bool FP16, bool RELU = false, bool SAT = false>
 __device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {
   uint32_t r;
-  if (FP16) {
+  if (FP16 && SAT) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  } else if (FP16) {
     if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   } else {

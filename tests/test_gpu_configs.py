@@ -204,7 +204,11 @@ def test_c4_full_chunk_properties_on_the_tensor_core_tier():
             assert torch.equal(sub[k], out[k][idx]), k          # per-ray results do not depend on the batch they ran in
         net.set_precision("fp32")
         ref = R_.render_star_online(net, pts[idx], vd[idx], z[idx], ro[idx], rd[idx], Ni, pose)
-        assert float((sub["rgb0"] - ref["rgb0"]).abs().max()) <= 2e-3
+        # the multi-field colour sum_s T (a_s c_s + sum_v a_v c_v) is not bounded by 1 with random-init nets (per-field
+        # alphas under the TOTAL transmittance, rendering__.py:456-463; here up to ~6): the 2e-3 bound is taken relative
+        # to that range; weights are in [0, 1]
+        scale = max(1.0, float(ref["rgb0"].abs().max()))
+        assert float((sub["rgb0"] - ref["rgb0"]).abs().max()) <= 2e-3 * scale, (float((sub["rgb0"] - ref["rgb0"]).abs().max()), scale)
         assert float((sub["weights0"] - ref["weights0"]).abs().max()) <= 2e-3
 
 
