@@ -179,7 +179,12 @@ size_t star_mip_tc_packed_bytes();
 int star_mip_tc_pack(const float* master, const float* freqs, void* packed, int fp16, cudaStream_t st);
 int star_mip_tc_forward(const void* packed, const float* origins, const float* dirs, const float* pose12,
                         const float* bins, float radius, int R, int S, float* raw_sigma, float* raw_rgb,
-                        int64_t ray_stride, int fp16, cudaStream_t st);
+                        int64_t ray_stride, void* stash, int fp16, cudaStream_t st);
+size_t star_mip_tc_stash_bytes(int64_t n_samples);
+size_t star_mip_tc_gstash_bytes(int64_t n_samples);
+int star_mip_tc_backward(const void* packed, int R, int S, const float* d_raw_sigma, const float* d_raw_rgb,
+                         int64_t ray_stride, const void* stash, void* gstash, float* grad_flat, int fp16,
+                         cudaStream_t st);
 
 extern "C" size_t star_mip_param_count(void) {
   MipLayout lay;
@@ -211,14 +216,18 @@ extern "C" int star_mip_pack_weights(int precision, const float* flat_master, co
 extern "C" size_t star_mip_stash_bytes(int precision, int64_t n_samples) {
   MipLayout lay;
   star_make_mip_layout(&lay);
-  if (precision != STAR_PREC_F32 || n_samples < 0) return 0;
+  if (n_samples < 0) return 0;
+  if (precision == STAR_PREC_BF16 || precision == STAR_PREC_F16) return star_mip_tc_stash_bytes(n_samples);
+  if (precision != STAR_PREC_F32) return 0;
   return sizeof(float) * (size_t)lay.stash_cols * (size_t)n_samples;
 }
 
 extern "C" size_t star_mip_backward_workspace_bytes(int precision, int64_t n_samples) {
   MipLayout lay;
   star_make_mip_layout(&lay);
-  if (precision != STAR_PREC_F32 || n_samples < 0) return 0;
+  if (n_samples < 0) return 0;
+  if (precision == STAR_PREC_BF16 || precision == STAR_PREC_F16) return star_mip_tc_gstash_bytes(n_samples);
+  if (precision != STAR_PREC_F32) return 0;
   return sizeof(float) * (size_t)lay.g_cols * (size_t)n_samples;
 }
 
@@ -235,8 +244,7 @@ extern "C" int star_mip_field_forward(int precision, const void* packed, const f
     return star_mip_f32_forward(lay, packed, origins, dirs, pose12, bins, freqs, radius, R, S, raw_sigma, raw_rgb,
                                 ray_stride, stash, (cudaStream_t)stream);
   if (precision == STAR_PREC_BF16 || precision == STAR_PREC_F16) {
-    if (stash != nullptr) return STAR_E_UNSUPPORTED;   // tensor-core tier of the mip field: inference only
-    return star_mip_tc_forward(packed, origins, dirs, pose12, bins, radius, R, S, raw_sigma, raw_rgb, ray_stride,
+    return star_mip_tc_forward(packed, origins, dirs, pose12, bins, radius, R, S, raw_sigma, raw_rgb, ray_stride, stash,
                                precision == STAR_PREC_F16, (cudaStream_t)stream);
   }
   return STAR_E_UNSUPPORTED;
@@ -250,7 +258,7 @@ extern "C" int star_mip_field_backward(int precision, const void* packed, const 
   if (!packed || !origins || !dirs || !bins || !freqs || !d_raw_sigma || !d_raw_rgb || !stash || !workspace ||
       !grad_flat)
     return STAR_E_NULL;
-  if (pose12 && !pose_acc) return STAR_E_NULL;
+  if (pose12 && !pose_acc && precision == STAR_PREC_F32) return STAR_E_NULL;
   if (R < 0 || S < 1 || ray_stride < S) return STAR_E_BAD_SHAPE;
   if (R == 0) return STAR_OK;
   MipLayout lay;
@@ -258,5 +266,12 @@ extern "C" int star_mip_field_backward(int precision, const void* packed, const 
   if (precision == STAR_PREC_F32)
     return star_mip_f32_backward(lay, packed, origins, dirs, pose12, bins, freqs, radius, R, S, d_raw_sigma, d_raw_rgb,
                                  ray_stride, stash, workspace, grad_flat, pose_acc, (cudaStream_t)stream);
+  if (precision == STAR_PREC_BF16 || precision == STAR_PREC_F16) {
+    // tensor-core backward: gradients to the WEIGHTS only; a pass that needs the gradient of the ray (object pose)
+    // must run on the fp32 tier
+    if (pose_acc != nullptr) return STAR_E_UNSUPPORTED;
+    return star_mip_tc_backward(packed, R, S, d_raw_sigma, d_raw_rgb, ray_stride, stash, workspace, grad_flat,
+                                precision == STAR_PREC_F16, (cudaStream_t)stream);
+  }
   return STAR_E_UNSUPPORTED;
 }

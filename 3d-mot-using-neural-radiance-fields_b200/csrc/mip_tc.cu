@@ -13,56 +13,16 @@
 //   L5..L7 : A[0..3] N=256 ReLU; L7's epilogue also takes the density head (fp32 dot on the rectified base_out)
 //   H0 : A[0..3] + AD       N=128 ReLU -> A[0..1]              H1 : A[0..1] N=128 ReLU + rgb head (fp32 dot)
 // Biases are fp32 and added in the epilogue; the two heads run in fp32 on un-rounded activations (as in mlp_tc.cu).
-// Forward / inference only: training uses the fp32 tier (mip_f32.cu).
+// Training (STASH): every GEMM input of the tile (IPE blocks, encoded dirs, the rectified output of each layer) is also
+// written to the activation stash in the same swizzled 16 KB block image (mip_tc_layout.h) for the tensor-core backward
+// pass (mip_tc_bwd.cu: dX chain, dW through dw_tc_kernel, head gradients).
 #include "star_common.cuh"
 #include <cuda_fp16.h>
 #include "tc_common.cuh"
 #include "mip_layout.h"
 #include "mlp_tc_device.cuh"
 
-#define MIP_TC_NL 10
-#define BAR_X_DONE (2 * TC_MAX_NS + 14)
-
-enum MipTcKind { MK_HID = 0, MK_BASE_OUT = 1, MK_H0 = 2, MK_H1 = 3 };
-
-struct MipTcLayer {
-  int nkb;          // K-blocks issued before the (optional) mid-layer barrier
-  int nkb_extra;    // layer 4: 3 K-blocks of the re-encoded input; H0: 1 K-block of encoded dirs
-  int N, region, kind;
-  int bias_off;     // float offset in the small section
-  uint32_t w_off;   // byte offset of the first K-block in the weight stream
-};
-
-struct MipTcLayout {
-  MipTcLayer L[MIP_TC_NL];
-  int off_dw, off_db, off_rw, off_rb, off_freq;   // float offsets: density head, rgb head, frequency table
-  int small_floats;
-  uint32_t small_bytes, stream_bytes;
-};
-
-static inline void star_make_mip_tc_layout(MipTcLayout* o) {
-  int fo = 0;
-  uint32_t wo = 0;
-  auto add = [&](int i, int nkb, int extra, int N, int region, int kind) {
-    MipTcLayer& l = o->L[i];
-    l.nkb = nkb; l.nkb_extra = extra; l.N = N; l.region = region; l.kind = kind;
-    l.bias_off = fo; fo += MIP_W;
-    l.w_off = wo; wo += (uint32_t)(nkb + extra) * (uint32_t)N * 128u;
-  };
-  add(0, 3, 0, MIP_W, 0, MK_HID);
-  for (int l = 1; l < MIP_NBASE; ++l)
-    add(l, 4, l == MIP_SKIP ? 3 : 0, MIP_W, l & 1, l == MIP_NBASE - 1 ? MK_BASE_OUT : MK_HID);
-  add(8, 4, 1, MIP_WH, 0, MK_H0);
-  add(9, 2, 0, MIP_WH, 1, MK_H1);
-  o->off_dw = fo; fo += MIP_W;
-  o->off_db = fo; fo += 4;
-  o->off_rw = fo; fo += 3 * MIP_WH;
-  o->off_rb = fo; fo += 4;
-  o->off_freq = fo; fo += MIP_FREQ_FLOATS;
-  o->small_floats = fo;
-  o->small_bytes = ((uint32_t)fo * 4u + TC_SMALL_ALIGN - 1) / TC_SMALL_ALIGN * TC_SMALL_ALIGN;
-  o->stream_bytes = wo;
-}
+#include "mip_tc_layout.h"
 
 #define MIP_TWO_PI 6.2831854820251465f
 #define MIP_PIO2 1.5707963705062866f
@@ -118,16 +78,6 @@ __device__ __forceinline__ MipTcGeom mip_tc_geom(const float* __restrict__ origi
   return g;
 }
 
-// Kernel-internal K order of the integrated positional encoding (the packed weights are permuted to match,
-// mip_pack_tc_stream_kernel): column 2 p + t, p = c * 24 + k the (axis, frequency) pair, t = 0: e sin(a), t = 1:
-// e sin(a + pi/2); columns 144..146 the raw mean; zero padding up to 192.  A thread's 16 columns are 8 whole pairs, so
-// the damping factor and the range reduction are shared by the two features of a pair (the reference evaluates
-// sin(fl(a + pi/2)); cos of the reduced argument differs by < ulp(a)/2, far below the 16-bit operand resolution).
-__host__ __device__ __forceinline__ int ipe_master_col(int col) {   // kernel column -> reference feature index, -1 = padding
-  if (col < 6 * MIP_NF) return (col & 1) * 3 * MIP_NF + (col >> 1);
-  return col < MIP_KX ? col : -1;
-}
-
 __device__ __forceinline__ void ipe_pair(const MipTcGeom& g, const float* __restrict__ s_f, int p, float& f0, float& f1) {
   const int c = p / MIP_NF, k = p - c * MIP_NF;
   const float mc = c == 0 ? g.mean[0] : (c == 1 ? g.mean[1] : g.mean[2]);
@@ -153,16 +103,22 @@ __device__ __forceinline__ void pack_row16(const float (&v)[16], uint32_t (&w)[8
 #pragma unroll
   for (int i = 0; i < 8; ++i) w[i] = pack_16x2<FP16, false>(v[2 * i], v[2 * i + 1]);
 }
-__device__ __forceinline__ void store_words16(uint32_t kblock_saddr, int row, int ch0, const uint32_t (&w)[8]) {
+__device__ __forceinline__ void store_words16(uint32_t kblock_saddr, int row, int ch0, const uint32_t (&w)[8],
+                                              uint8_t* gblock = nullptr) {
   const uint32_t x = (uint32_t)row & 7u;
-  st_shared_v4(kblock_saddr + (uint32_t)row * 128u + ((((uint32_t)ch0) ^ x) << 4), w[0], w[1], w[2], w[3]);
-  st_shared_v4(kblock_saddr + (uint32_t)row * 128u + ((((uint32_t)(ch0 + 1)) ^ x) << 4), w[4], w[5], w[6], w[7]);
+  const uint32_t o0 = (uint32_t)row * 128u + ((((uint32_t)ch0) ^ x) << 4), o1 = (uint32_t)row * 128u + ((((uint32_t)(ch0 + 1)) ^ x) << 4);
+  st_shared_v4(kblock_saddr + o0, w[0], w[1], w[2], w[3]);
+  st_shared_v4(kblock_saddr + o1, w[4], w[5], w[6], w[7]);
+  if (gblock != nullptr) {     // training: the same chunks into the stash block at that global address
+    *reinterpret_cast<uint4*>(gblock + o0) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(gblock + o1) = make_uint4(w[4], w[5], w[6], w[7]);
+  }
 }
 
 // Encodes this thread's 3 x 16 columns, stores them into A[0..2] and keeps the packed words for the skip layer
 template <bool FP16>
 __device__ __forceinline__ void encode_ipe_blocks(const MipTcGeom& g, const float* __restrict__ s_f, uint32_t sA, int row,
-                                                  int cg, uint32_t (&cache)[3][8]) {
+                                                  int cg, uint32_t (&cache)[3][8], uint8_t* st_ipe) {
 #pragma unroll
   for (int kb = 0; kb < 3; ++kb) {
     float e[16];
@@ -183,7 +139,8 @@ __device__ __forceinline__ void encode_ipe_blocks(const MipTcGeom& g, const floa
       }
     }
     pack_row16<FP16>(e, cache[kb]);
-    store_words16(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, cache[kb]);
+    store_words16(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, cache[kb],
+                  st_ipe != nullptr ? st_ipe + (size_t)kb * TC_BLOCK_BYTES : nullptr);
   }
 }
 
@@ -192,6 +149,7 @@ struct MipEpi {
   uint32_t sA, a_ready0, tcol;
   const float* bias;
   const float* head_w;
+  uint8_t* stash_out;     // training: first stash block of this layer's rectified output, else NULL
   int row, cg, lane;
 };
 
@@ -232,8 +190,10 @@ __device__ __forceinline__ void mip_epilogue(const MipEpi& c, float (&h)[3]) {
         h[1] = fmaf(x, c.head_w[MIP_WH + col0 + j], h[1]);
         h[2] = fmaf(x, c.head_w[2 * MIP_WH + col0 + j], h[2]);
       }
+      if (c.stash_out != nullptr) store_row16<FP16, true>(0u, c.row, c.cg * 2, v, c.stash_out + (size_t)kb * TC_BLOCK_BYTES);
     } else {
-      store_row16<FP16, true>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v);
+      store_row16<FP16, true>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v,
+                              c.stash_out != nullptr ? c.stash_out + (size_t)kb * TC_BLOCK_BYTES : nullptr);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -243,12 +203,12 @@ __device__ __forceinline__ void mip_epilogue(const MipEpi& c, float (&h)[3]) {
 }
 
 // ============================================================================================ forward
-template <bool FP16>
+template <bool FP16, bool STASH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mip_fwd_tc_kernel(const MipTcLayout lay, const uint8_t* __restrict__ packed, const float* __restrict__ origins,
                   const float* __restrict__ dirs, const float* __restrict__ pose12, const float* __restrict__ bins,
                   float radius, int S, int64_t M, float* __restrict__ raw_sigma, float* __restrict__ raw_rgb,
-                  int64_t ray_stride, int* dbg) {
+                  int64_t ray_stride, uint8_t* __restrict__ stash, int* dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -371,7 +331,8 @@ mip_fwd_tc_kernel(const MipTcLayout lay, const uint8_t* __restrict__ packed, con
       }
       // ---- inputs: IPE -> A[0..2]; encoded dirs -> AD (columns 0..31: groups 0 and 1)
       uint32_t enc_cache[3][8];
-      encode_ipe_blocks<FP16>(g, s_f, sA, row, cg, enc_cache);
+      uint8_t* st_tile = STASH ? stash + (size_t)tile * MIP_STASH_BLOCKS * TC_BLOCK_BYTES : nullptr;
+      encode_ipe_blocks<FP16>(g, s_f, sA, row, cg, enc_cache, STASH ? st_tile + (size_t)MIP_S_IPE * TC_BLOCK_BYTES : nullptr);
       if (cg < 2) {
         float e[16];
 #pragma unroll
@@ -390,7 +351,10 @@ mip_fwd_tc_kernel(const MipTcLayout lay, const uint8_t* __restrict__ packed, con
           }
           e[j] = valid ? v : 0.f;
         }
-        store_row16<FP16, false>(sAD, row, cg * 2, e);
+        store_row16<FP16, false>(sAD, row, cg * 2, e, STASH ? st_tile + (size_t)MIP_S_DIRS * TC_BLOCK_BYTES : nullptr);
+      } else if (STASH) {      // columns 32..63 of the stashed dirs block: zeros (the dW GEMM reads the whole block)
+        const float z[16] = {0.f};
+        store_row16<FP16, false>(0u, row, cg * 2, z, st_tile + (size_t)MIP_S_DIRS * TC_BLOCK_BYTES);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -426,6 +390,8 @@ mip_fwd_tc_kernel(const MipTcLayout lay, const uint8_t* __restrict__ packed, con
         tc_fence_after();
         ctx.tcol = tmem_base + (((uint32_t)(q * 32)) << 16) + (L.region ? 256u : 0u) + (uint32_t)(cg * TC_CPT);
         ctx.bias = s_small + L.bias_off;
+        ctx.stash_out = STASH ? st_tile + (size_t)(l < MIP_NBASE ? MIP_S_OUT(l) : (l == 8 ? MIP_S_H0 : MIP_S_H1)) * TC_BLOCK_BYTES
+                              : nullptr;
         float h[3] = {0.f, 0.f, 0.f};
         if (L.kind == MK_HID) {
           mip_epilogue<MK_HID, FP16>(ctx, h);
@@ -526,10 +492,13 @@ __global__ void mip_pack_tc_stream_kernel(MipTcLayout tl, MipLayout ml, const fl
 }
 
 // ============================================================================================ host side
+int star_mip_tc_pack_tstream(const MipTcLayout& tl, const MipLayout& ml, const float* master, void* tstream, int fp16,
+                             cudaStream_t st);
+
 size_t star_mip_tc_packed_bytes() {
   MipTcLayout tl;
   star_make_mip_tc_layout(&tl);
-  return (size_t)tl.small_bytes + tl.stream_bytes;
+  return (size_t)tl.small_bytes + tl.stream_bytes + tl.tstream_bytes;
 }
 
 int star_mip_tc_pack(const float* master, const float* freqs, void* packed, int fp16, cudaStream_t st) {
@@ -541,12 +510,14 @@ int star_mip_tc_pack(const float* master, const float* freqs, void* packed, int 
   int rc = star_check_launch();
   if (rc) return rc;
   mip_pack_tc_stream_kernel<<<148 * 4, 256, 0, st>>>(tl, ml, master, (uint16_t*)((uint8_t*)packed + tl.small_bytes), fp16);
-  return star_check_launch();
+  rc = star_check_launch();
+  if (rc) return rc;
+  return star_mip_tc_pack_tstream(tl, ml, master, (uint8_t*)packed + tl.small_bytes + tl.stream_bytes, fp16, st);
 }
 
 int star_mip_tc_forward(const void* packed, const float* origins, const float* dirs, const float* pose12,
                         const float* bins, float radius, int R, int S, float* raw_sigma, float* raw_rgb,
-                        int64_t ray_stride, int fp16, cudaStream_t st) {
+                        int64_t ray_stride, void* stash, int fp16, cudaStream_t st) {
   MipTcLayout tl;
   star_make_mip_tc_layout(&tl);
   const int64_t M = (int64_t)R * S;
@@ -557,10 +528,11 @@ int star_mip_tc_forward(const void* packed, const float* origins, const float* d
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   const TcSmem sl = tc_smem_layout(tl.small_bytes);
   if (((uintptr_t)packed & 15) != 0) return STAR_E_ALIGN;
-  auto kern = fp16 ? mip_fwd_tc_kernel<true> : mip_fwd_tc_kernel<false>;
+  auto kern = stash != nullptr ? (fp16 ? mip_fwd_tc_kernel<true, true> : mip_fwd_tc_kernel<false, true>)
+                               : (fp16 ? mip_fwd_tc_kernel<true, false> : mip_fwd_tc_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
   if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
   kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, origins, dirs, pose12, bins, radius, S, M,
-                                            raw_sigma, raw_rgb, ray_stride, nullptr);
+                                            raw_sigma, raw_rgb, ray_stride, (uint8_t*)stash, nullptr);
   return star_check_launch();
 }

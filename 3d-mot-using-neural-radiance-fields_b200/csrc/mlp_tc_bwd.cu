@@ -14,6 +14,7 @@
 //   3. head_grad_tc_kernel -- alpha_linear / rgb_linear gradients on CUDA cores (tiny).
 #include <cuda_fp16.h>
 #include "mlp_tc_device.cuh"
+#include "mip_tc_layout.h"
 
 #define BK_PRE 0     // G_views from d_rgb, rgb_linear and the relu(h2) mask (no MMA before it)
 #define BK_FEAT 1    // G_feat = T                     (+ dirs part of the pose gradient)
@@ -511,6 +512,7 @@ struct DwItem {
   int g_blk, a_blk, n_a;     // first gradient-stash block (2 blocks), first stash block, number of stash blocks
   int64_t w_off, b_off;      // flat-gradient offsets of W[half*128][0] (+k0) and b[half*128] (-1: no bias here)
   int K, k0, k_valid;        // row length of W, first column written, valid columns of this item
+  int ipe_perm;              // mip field: operand column c holds master column ipe_master_col(c) (-1: padding)
 };
 #define DW_MAX_ITEMS 40
 struct DwPlan {
@@ -632,7 +634,12 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (c0 + j < it.k_valid) atomicAdd(wrow + c0 + j, __uint_as_float(r[j]) * unscale);
+          if (it.ipe_perm) {
+            const int mc = ipe_master_col(c0 + j);
+            if (mc >= 0) atomicAdd(wrow + mc, __uint_as_float(r[j]) * unscale);
+          } else if (c0 + j < it.k_valid) {
+            atomicAdd(wrow + c0 + j, __uint_as_float(r[j]) * unscale);
+          }
       }
       if (it.b_off >= 0) {
         uint32_t r[16];
@@ -668,13 +675,18 @@ __device__ __forceinline__ void unpack8(const uint4& v, bool fp16, float (&x)[8]
   }
 }
 
+struct HeadGradCfg {
+  int stash_blocks;          // blocks per tile of the activation stash
+  int blk_h, blk_h2;         // first block of the 256-wide input of the density head / of the 128-wide input of the rgb head
+  int64_t m_aw, m_ab, m_rw, m_rb;   // flat-gradient offsets: density head weight [256], bias; rgb head weight [3][128], bias [3]
+};
+
 __global__ void __launch_bounds__(256)
-head_grad_tc_kernel(const TcLayout lay, MlpLayout ml, const uint8_t* __restrict__ stash, const float* __restrict__ d_raw_alpha,
+head_grad_tc_kernel(const HeadGradCfg hc, const uint8_t* __restrict__ stash, const float* __restrict__ d_raw_alpha,
                     const float* __restrict__ d_raw_rgb, int64_t ray_stride, int S, int64_t M, int fp16,
                     float* __restrict__ grad_flat) {
   const int tid = threadIdx.x, rg = tid >> 5, ch = tid & 31;
   const int64_t ntiles = (M + 127) / 128;
-  const int F = lay.n_layers - 2, V = lay.n_layers - 1;
   float aw[8], rw[3][8], ab = 0.f, rb[3] = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int j = 0; j < 8; ++j) { aw[j] = 0.f; rw[0][j] = 0.f; rw[1][j] = 0.f; rw[2][j] = 0.f; }
@@ -692,9 +704,9 @@ head_grad_tc_kernel(const TcLayout lay, MlpLayout ml, const uint8_t* __restrict_
       s_d[tid][0] = a; s_d[tid][1] = c0; s_d[tid][2] = c1; s_d[tid][3] = c2;
     }
     __syncthreads();
-    const uint8_t* tile = stash + (size_t)t * lay.stash_blocks * TC_BLOCK_BYTES;
-    const uint8_t* hb = tile + (size_t)(lay.L[F].s_in + (ch >> 3)) * TC_BLOCK_BYTES;
-    const uint8_t* h2b = tile + (size_t)(lay.L[V].s_out + ((ch & 15) >> 3)) * TC_BLOCK_BYTES;
+    const uint8_t* tile = stash + (size_t)t * hc.stash_blocks * TC_BLOCK_BYTES;
+    const uint8_t* hb = tile + (size_t)(hc.blk_h + (ch >> 3)) * TC_BLOCK_BYTES;
+    const uint8_t* h2b = tile + (size_t)(hc.blk_h2 + ((ch & 15) >> 3)) * TC_BLOCK_BYTES;
     // all 16 (+16) 16-byte loads of the tile are issued before the first use: the kernel is a pure HBM reader
     uint4 qh[16], q2[16];
 #pragma unroll
@@ -739,13 +751,13 @@ head_grad_tc_kernel(const TcLayout lay, MlpLayout ml, const uint8_t* __restrict_
     float v = 0.f;
 #pragma unroll
     for (int g = 0; g < 8; ++g) v += s_red[g][c2][k];
-    if (k < 8) atomicAdd(&grad_flat[ml.m_alpha_w + c2 * 8 + k], v);
-    else if (c2 < 16) atomicAdd(&grad_flat[ml.m_rgb_w + ((k - 8) >> 3) * STAR_WV + c2 * 8 + ((k - 8) & 7)], v);
+    if (k < 8) atomicAdd(&grad_flat[hc.m_aw + c2 * 8 + k], v);
+    else if (c2 < 16) atomicAdd(&grad_flat[hc.m_rw + ((k - 8) >> 3) * STAR_WV + c2 * 8 + ((k - 8) & 7)], v);
   }
   if (tid == 0) {
     float v = 0.f;
     for (int g = 0; g < 8; ++g) v += s_red[g][31][32];
-    atomicAdd(&grad_flat[ml.m_alpha_b], v);
+    atomicAdd(&grad_flat[hc.m_ab], v);
   }
   // rgb bias: sum of d_rgb
   __syncthreads();
@@ -754,7 +766,7 @@ head_grad_tc_kernel(const TcLayout lay, MlpLayout ml, const uint8_t* __restrict_
   if (tid < 3) {
     float v = 0.f;
     for (int g = 0; g < 8; ++g) v += s_red[g][0][tid];
-    atomicAdd(&grad_flat[ml.m_rgb_b + tid], v);
+    atomicAdd(&grad_flat[hc.m_rb + tid], v);
   }
 }
 
@@ -853,6 +865,7 @@ int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed
         it.k_valid = K < 64 * it.n_a ? K : 64 * it.n_a;
         it.w_off = ml.L[l].m_w + (int64_t)h * 128 * K;
         it.b_off = ml.L[l].m_b + h * 128;
+        it.ipe_perm = 0;
         if (L.kind == LK_VIEWS) {          // encoded-dirs columns of the view layer: separate item, no bias
           DwItem& d2 = plan.it[n++];
           d2 = it;
@@ -877,8 +890,361 @@ int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed
   // ---- 3. heads
   {
     int blocks = (int)(ntiles < 4 * sms ? ntiles : 4 * sms);
-    head_grad_tc_kernel<<<blocks, 256, 0, st>>>(tl, ml, (const uint8_t*)stash, d_raw_alpha, d_raw_rgb, ray_stride, S, M,
-                                                fp16, grad_flat);
+    const HeadGradCfg hc{tl.stash_blocks, tl.L[tl.n_layers - 2].s_in, tl.L[tl.n_layers - 1].s_out, ml.m_alpha_w, ml.m_alpha_b,
+                         ml.m_rgb_w, ml.m_rgb_b};
+    head_grad_tc_kernel<<<blocks, 256, 0, st>>>(hc, (const uint8_t*)stash, d_raw_alpha, d_raw_rgb, ray_stride, S, M, fp16,
+                                                grad_flat);
+    return star_check_launch();
+  }
+}
+
+// ================================================================================================================
+// mip-NeRF field (models/mipnerf.py:53-100 -> nerfstudio NeRFField): tensor-core backward to the
+// WEIGHTS.  Same machine as the dX chain above (table-driven producer / issuer, bulk-stored gradient stash, the same
+// dw_tc_kernel and head-gradient kernel), with the mip layer program: no residual stream, ReLU after every layer (the
+// masks are read off the stashed rectified outputs: bits != 0), the density head on the rectified base output.
+// Gradients to the ray (pose of an object field: through the integrated positional encoding and its covariance) are NOT
+// produced here -- a pass that needs them runs on the fp32 tier (mip_f32.cu), which the host selects.
+#define MK_B_PRE 0     // G_h1 = (d_rgb . W_rgb) (.) mask(relu(h1))           (no MMA before it)
+#define MK_B_T 1       // G = acc (.) mask
+#define MK_B_BASE 2    // G_7 = (acc + d_sigma w_dens) (.) mask(relu(base_out))
+
+template <bool F16>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+mip_bwd_tc_kernel(const MipTcLayout lay, const uint8_t* __restrict__ packed, int S, int64_t M,
+                  const float* __restrict__ d_raw_sigma, const float* __restrict__ d_raw_rgb, int64_t ray_stride,
+                  const uint8_t* __restrict__ stash, uint8_t* __restrict__ gstash, const float* __restrict__ absmax,
+                  int* dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw_addr);
+  const BwdSmem sl = bwd_smem_layout(lay.small_bytes);
+  const uint32_t sA = base + sl.A, sW = base + sl.W, sBars = base + sl.bars;
+  float* s_small = reinterpret_cast<float*>(gbase + sl.small);
+  BwdStage* stages = reinterpret_cast<BwdStage*>(gbase + sl.tab);
+  BwdPhase* phases = reinterpret_cast<BwdPhase*>(gbase + sl.tab + BWD_MAX_STAGES * sizeof(BwdStage));
+  int* counts = reinterpret_cast<int*>(gbase + sl.tab + BWD_MAX_STAGES * sizeof(BwdStage) + BWD_MAX_PHASES * sizeof(BwdPhase));
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(gbase + sl.tmem_ptr);
+  auto bar = [&](int i) -> uint32_t { return sBars + 8u * (uint32_t)i; };
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (M + TC_M - 1) / TC_M;
+
+  // ---- the per-tile program: phase p's epilogue reads the accumulator of MMA group p - 1 (BwdPhase.mask_layer holds
+  // the TMEM column of that accumulator here) and writes the A operand of group p
+  if (tid == 0) {
+    int ns = 0, np = 0;
+    auto stage = [&](uint32_t w_off, uint32_t bytes, int a_kb, int N, int tcol, int accum, int last) {
+      BwdStage& s = stages[ns++];
+      s.w_off = lay.stream_bytes + w_off; s.bytes = bytes; s.a_kb = a_kb; s.N = N; s.tcol = tcol; s.accum = accum; s.nk = 4;
+      s.last = last;
+    };
+    auto phase = [&](int kind, int nch, int mask_blk, int g_blk, int tsrc) {
+      BwdPhase& p = phases[np++];
+      p.kind = kind; p.nch = nch; p.mask_blk = mask_blk; p.g_blk = g_blk; p.n_wait = nch; p.mask_layer = tsrc;
+    };
+    phase(MK_B_PRE, 2, MIP_S_H1, MIP_G_H1, 0);
+    for (int kb = 0; kb < 2; ++kb) stage(lay.wt_h1 + (uint32_t)kb * 16384u, 16384u, kb, 128, 256, kb > 0, kb == 1);
+    phase(MK_B_T, 2, MIP_S_H0, MIP_G_H0, 256);
+    for (int kb = 0; kb < 2; ++kb) stage(lay.wt_h0 + (uint32_t)kb * 32768u, 32768u, kb, 256, 0, kb > 0, kb == 1);
+    phase(MK_B_BASE, 4, MIP_S_OUT(MIP_NBASE - 1), MIP_G_OUT(MIP_NBASE - 1), 0);
+    int tcol = 256;
+    for (int l = MIP_NBASE - 1; l >= 1; --l) {
+      for (int kb = 0; kb < 4; ++kb) stage(lay.wt_off[l] + (uint32_t)kb * 32768u, 32768u, kb, 256, tcol, kb > 0, kb == 3);
+      phase(MK_B_T, 4, MIP_S_OUT(l - 1), MIP_G_OUT(l - 1), tcol);
+      tcol ^= 256;
+    }
+    counts[0] = ns; counts[1] = np;
+  }
+  if (warp == TC_EPI_WARPS && lane == 0) {
+    for (int i = 0; i < TC_NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), 1); mbar_init(bar(BAR_W_EMPTY(i)), 1); }
+    for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A_READY(i)), TC_EPI_WARPS);
+    mbar_init(bar(BAR_ACC_FULL), 1);
+    mbar_init(bar(BAR_STASH_DONE), 1);
+    fence_mbar_init();
+  }
+  if (warp == TC_EPI_WARPS + 1) tmem_alloc(base + sl.tmem_ptr, TC_TMEM_COLS);
+  for (int i = tid; i < lay.small_floats; i += TC_THREADS) s_small[i] = reinterpret_cast<const float*>(packed)[i];
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const int n_stages = counts[0], n_phases = counts[1];
+
+  if (warp == TC_EPI_WARPS) {
+    // ======================================================================== weight producer + gradient-stash writer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, s_par = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        uint8_t* gs_tile = gstash + (size_t)tile * MIP_GSTASH_BLOCKS * TC_BLOCK_BYTES;
+        auto stash_phase = [&](int g) {
+          const int nch = phases[g].nch, g_blk = phases[g].g_blk;
+          for (int kb = 0; kb < nch; ++kb) {
+            mbar_wait(bar(BAR_A_READY(kb)), (s_par >> kb) & 1u, dbg, 6);
+            s_par ^= 1u << kb;
+            bulk_s2g(gs_tile + (size_t)(g_blk + kb) * TC_BLOCK_BYTES, sA + (uint32_t)kb * TC_KB_BYTES, TC_KB_BYTES);
+            bulk_commit_group();
+          }
+          bulk_wait_group_read0();
+          mbar_arrive(bar(BAR_STASH_DONE));
+        };
+        int grp = 0;
+        bool group_start = true;
+        for (int i = 0; i < n_stages; ++i) {
+          const BwdStage& s = stages[i];
+          if (group_start && grp >= 1) stash_phase(grp - 1);
+          group_start = false;
+          mbar_wait(bar(BAR_W_EMPTY(stage)), phase ^ 1u, dbg, 1);
+          mbar_arrive_expect_tx(bar(BAR_W_FULL(stage)), s.bytes);
+          bulk_g2s(sW + stage * TC_STAGE_BYTES, packed + lay.small_bytes + s.w_off, s.bytes, bar(BAR_W_FULL(stage)));
+          if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
+          if (s.last) { ++grp; group_start = true; }
+        }
+        for (int g = grp - 1; g < n_phases; ++g) stash_phase(g);
+      }
+      bulk_wait_group0();
+    }
+  } else if (warp == TC_EPI_WARPS + 1) {
+    // ======================================================================== MMA issuer
+    uint32_t stage = 0, phase = 0, a_par = 0;
+    const uint64_t desc_a0 = umma_desc_sw128(sA), desc_w0 = umma_desc_sw128(sW);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int ph = 0;
+      bool group_start = true;
+      for (int i = 0; i < n_stages; ++i) {
+        const BwdStage s = stages[i];
+        if (group_start) {
+          for (int kb = 0; kb < phases[ph].n_wait; ++kb) {
+            mbar_wait(bar(BAR_A_READY(kb)), (a_par >> kb) & 1u, dbg, 2);
+            a_par ^= 1u << kb;
+          }
+          group_start = false;
+        }
+        mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_16(TC_M, s.N, F16 ? 0 : 1);
+        const uint64_t a0 = desc_a0 + (uint64_t)(s.a_kb * (TC_KB_BYTES >> 4));
+        const uint64_t b0 = desc_w0 + (uint64_t)(stage * (TC_STAGE_BYTES >> 4));
+        if (elect_one_sync()) {
+          tc_mma_kblock<4>(tmem_base + (uint32_t)s.tcol, a0, b0, idesc, s.accum ? 1u : 0u);
+          tc_commit(bar(BAR_W_EMPTY(stage)));
+          if (s.last) tc_commit(bar(BAR_ACC_FULL));
+        }
+        __syncwarp();
+        if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
+        if (s.last) { ++ph; group_start = true; }
+      }
+      // the tile's last phase (G_0) also arrives on a_ready[]: consume it to keep the parities in step across tiles
+      for (int kb = 0; ph < n_phases && kb < phases[ph].n_wait; ++kb) {
+        mbar_wait(bar(BAR_A_READY(kb)), (a_par >> kb) & 1u, dbg, 5);
+        a_par ^= 1u << kb;
+      }
+    }
+  } else {
+    // ======================================================================== epilogue warps
+    const int q = warp & 3, cg = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
+    uint32_t acc_par = 0, stash_par = 0;
+    const float gscale = F16 ? grad_scale_of(absmax) : 1.f;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t gi = tile * TC_M + row;
+      const bool valid = gi < M;
+      float ds = 0.f, dc0 = 0.f, dc1 = 0.f, dc2 = 0.f;
+      if (valid) {
+        const int64_t r = gi / S;
+        const int64_t o = r * ray_stride + (gi - r * S);
+        ds = d_raw_sigma[o] * gscale;
+        dc0 = d_raw_rgb[o * 3 + 0] * gscale; dc1 = d_raw_rgb[o * 3 + 1] * gscale; dc2 = d_raw_rgb[o * 3 + 2] * gscale;
+      }
+      const uint8_t* st_tile = stash + (size_t)tile * MIP_STASH_BLOCKS * TC_BLOCK_BYTES;
+      const uint32_t x_sw = (uint32_t)row & 7u;
+      for (int pi = 0; pi < n_phases; ++pi) {
+        const BwdPhase P = phases[pi];
+        // the masks of the whole phase (the stashed rectified outputs: > 0 <=> bits != 0) are fetched BEFORE the accumulator
+        // wait: their global-memory latency hides behind the MMAs
+        uint4 mq[4][2];
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          if (kb < P.nch) {
+            const uint8_t* mb = st_tile + (size_t)(P.mask_blk + kb) * TC_BLOCK_BYTES + (uint32_t)row * 128u;
+            mq[kb][0] = __ldg(reinterpret_cast<const uint4*>(mb + ((((uint32_t)(cg * 2)) ^ x_sw) << 4)));
+            mq[kb][1] = __ldg(reinterpret_cast<const uint4*>(mb + ((((uint32_t)(cg * 2 + 1)) ^ x_sw) << 4)));
+          }
+        }
+        if (P.kind != MK_B_PRE) {
+          mbar_wait(bar(BAR_ACC_FULL), acc_par, dbg, 4);
+          acc_par ^= 1u;
+          tc_fence_after();
+        }
+        if (!(pi == 0 && tile == (int64_t)blockIdx.x)) {   // the previous phase's A blocks have been copied to the gstash
+          mbar_wait(bar(BAR_STASH_DONE), stash_par, dbg, 7);
+          stash_par ^= 1u;
+        }
+        const uint32_t tsrc = tmem_base + lane_addr + (uint32_t)P.mask_layer + (uint32_t)(cg * TC_CPT);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          if (kb >= P.nch) break;
+          const int col0 = kb * 64 + cg * TC_CPT;
+          float v[16];
+          if (P.kind == MK_B_PRE) {
+            const float* rw = s_small + lay.off_rw + col0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = dc0 * rw[j] + dc1 * rw[MIP_WH + j] + dc2 * rw[2 * MIP_WH + j];
+          } else {
+            uint32_t r[16];
+            tmem_ld16(tsrc + 64u * (uint32_t)kb, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          }
+          if (P.kind == MK_B_BASE) {
+            const float* dw = s_small + lay.off_dw + col0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaf(ds, dw[j], v[j]);
+          }
+          const uint32_t mw[8] = {mq[kb][0].x, mq[kb][0].y, mq[kb][0].z, mq[kb][0].w,
+                                  mq[kb][1].x, mq[kb][1].y, mq[kb][1].z, mq[kb][1].w};
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t bits = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xffffu);
+            if (bits == 0u || !valid) v[j] = 0.f;
+          }
+          store_row16<F16, false, true>(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, v);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_A_READY(kb)));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_EPI_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// transposed weight stream of the mip field (layout: mip_tc_layout.h, wt_off / wt_h0 / wt_h1)
+__global__ void mip_pack_tc_tstream_kernel(MipTcLayout tl, MipLayout ml, const float* __restrict__ master,
+                                           uint16_t* __restrict__ tstream, int fp16) {
+  const uint32_t n_elems = tl.tstream_bytes / 2;
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_elems; e += gridDim.x * blockDim.x) {
+    const uint32_t byte = e * 2;
+    int ml_idx, rows, koff;
+    uint32_t off;
+    if (byte >= tl.wt_h1) { ml_idx = MIP_L_H1; rows = MIP_WH; koff = 0; off = byte - tl.wt_h1; }
+    else if (byte >= tl.wt_h0) { ml_idx = MIP_L_H0; rows = MIP_W; koff = MIP_KD; off = byte - tl.wt_h0; }
+    else {
+      int l = 1;
+      while (l + 1 < MIP_NBASE && byte >= tl.wt_off[l + 1]) ++l;
+      ml_idx = l; rows = MIP_W; koff = (l == MIP_SKIP) ? MIP_KX : 0; off = byte - tl.wt_off[l];
+    }
+    const uint32_t kb_bytes = (uint32_t)rows * 128u;
+    const int kb = (int)(off / kb_bytes);
+    const uint32_t rem = off % kb_bytes;
+    const int j = (int)(rem >> 7);                                   // input feature (B operand row)
+    const uint32_t inrow = rem & 127u;
+    const int chunk = (int)((inrow >> 4) ^ ((uint32_t)j & 7u));
+    const int nn = kb * 64 + chunk * 8 + (int)((inrow & 15u) >> 1);  // output feature
+    const int K = ml.K[ml_idx], N = ml.N[ml_idx];
+    const float v = (nn < N) ? master[ml.m_w[ml_idx] + (int64_t)nn * K + koff + j] : 0.f;
+    tstream[e] = fp16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  }
+}
+
+int star_mip_tc_pack_tstream(const MipTcLayout& tl, const MipLayout& ml, const float* master, void* tstream, int fp16,
+                             cudaStream_t st) {
+  mip_pack_tc_tstream_kernel<<<148 * 4, 256, 0, st>>>(tl, ml, master, (uint16_t*)tstream, fp16);
+  return star_check_launch();
+}
+
+size_t star_mip_tc_stash_bytes(int64_t n_samples) {
+  return (size_t)((n_samples + 127) / 128) * MIP_STASH_BLOCKS * TC_BLOCK_BYTES;
+}
+size_t star_mip_tc_gstash_bytes(int64_t n_samples) {
+  return (size_t)((n_samples + 127) / 128) * MIP_GSTASH_BLOCKS * TC_BLOCK_BYTES + 256;
+}
+
+int star_mip_tc_backward(const void* packed, int R, int S, const float* d_raw_sigma, const float* d_raw_rgb,
+                         int64_t ray_stride, const void* stash, void* gstash, float* grad_flat, int fp16,
+                         cudaStream_t st) {
+  MipTcLayout tl;
+  MipLayout ml;
+  star_make_mip_tc_layout(&tl);
+  star_make_mip_layout(&ml);
+  const int64_t M = (int64_t)R * S;
+  const int64_t ntiles = (M + TC_M - 1) / TC_M;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  float* absmax = reinterpret_cast<float*>((uint8_t*)gstash + star_mip_tc_gstash_bytes(M) - 256);
+  if (fp16) {
+    cudaError_t e = cudaMemsetAsync(absmax, 0, 4, st);
+    if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
+    int64_t b = (M + 255) / 256;
+    if (b > 148 * 8) b = 148 * 8;
+    grad_absmax_kernel<<<(int)b, 256, 0, st>>>(d_raw_sigma, d_raw_rgb, S, M, ray_stride, absmax);
+    int rc = star_check_launch();
+    if (rc) return rc;
+  }
+  {   // ---- 1. dX chain
+    const int grid = (int)(ntiles < sms ? ntiles : sms);
+    const BwdSmem sl = bwd_smem_layout(tl.small_bytes);
+    auto kern = fp16 ? mip_bwd_tc_kernel<true> : mip_bwd_tc_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
+    if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
+    kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, S, M, d_raw_sigma, d_raw_rgb, ray_stride,
+                                              (const uint8_t*)stash, (uint8_t*)gstash, absmax, nullptr);
+    int rc = star_check_launch();
+    if (rc) return rc;
+  }
+  {   // ---- 2. dW / db through the shared dW kernel
+    DwPlan plan;
+    int n = 0;
+    auto item = [&](int g_blk, int a_blk, int n_a, int ml_idx, int half, int k0, int k_valid, bool bias, int perm) {
+      DwItem& it = plan.it[n++];
+      it.g_blk = g_blk + 2 * half; it.a_blk = a_blk; it.n_a = n_a;
+      it.K = ml.K[ml_idx]; it.k0 = k0; it.k_valid = k_valid;
+      it.w_off = ml.m_w[ml_idx] + (int64_t)half * 128 * it.K;
+      it.b_off = bias ? ml.m_b[ml_idx] + half * 128 : -1;
+      it.ipe_perm = perm;
+    };
+    for (int h = 0; h < 2; ++h) {
+      item(MIP_G_OUT(0), MIP_S_IPE, 3, 0, h, 0, MIP_KX, true, 1);                       // layer 0: the encoding
+      for (int l = 1; l < MIP_NBASE; ++l) {
+        const int k0 = (l == MIP_SKIP) ? MIP_KX : 0;
+        item(MIP_G_OUT(l), MIP_S_OUT(l - 1), 4, l, h, k0, MIP_W, true, 0);              // x part
+        if (l == MIP_SKIP) item(MIP_G_OUT(l), MIP_S_IPE, 3, l, h, 0, MIP_KX, false, 1);  // re-concatenated encoding
+      }
+    }
+    item(MIP_G_H0, MIP_S_OUT(MIP_NBASE - 1), 4, MIP_L_H0, 0, MIP_KD, MIP_W, true, 0);   // head 0: base part
+    item(MIP_G_H0, MIP_S_DIRS, 1, MIP_L_H0, 0, 0, MIP_KD, false, 0);                     //         encoded dirs
+    item(MIP_G_H1, MIP_S_H0, 2, MIP_L_H1, 0, 0, MIP_WH, true, 0);                        // head 1
+    plan.n_items = n;
+    int splits = sms / n;
+    if (splits < 1) splits = 1;
+    if ((int64_t)splits > ntiles) splits = (int)ntiles;
+    plan.splits = splits;
+    const size_t smem = (size_t)(DW_NSTAGE * DW_STAGE_BLOCKS + 1) * TC_BLOCK_BYTES + 256 + 1024;
+    auto kern = fp16 ? dw_tc_kernel<true> : dw_tc_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
+    kern<<<n * splits, DW_THREADS, smem, st>>>(plan, MIP_STASH_BLOCKS, MIP_GSTASH_BLOCKS, (const uint8_t*)stash,
+                                               (const uint8_t*)gstash, ntiles, grad_flat, absmax, nullptr);
+    int rc = star_check_launch();
+    if (rc) return rc;
+  }
+  {   // ---- 3. density / rgb heads
+    int blocks = (int)(ntiles < 4 * sms ? ntiles : 4 * sms);
+    const HeadGradCfg hc{MIP_STASH_BLOCKS, MIP_S_OUT(MIP_NBASE - 1), MIP_S_H1, ml.m_w[MIP_L_DENS], ml.m_b[MIP_L_DENS],
+                         ml.m_w[MIP_L_RGB], ml.m_b[MIP_L_RGB]};
+    head_grad_tc_kernel<<<blocks, 256, 0, st>>>(hc, (const uint8_t*)stash, d_raw_sigma, d_raw_rgb, ray_stride, S, M, fp16,
+                                                grad_flat);
     return star_check_launch();
   }
 }

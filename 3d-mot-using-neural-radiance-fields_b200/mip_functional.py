@@ -131,7 +131,6 @@ class MipRuntime:
 
 
 _WARNED_FP32_TRAINING = False
-EFFECTIVE_TRAIN_PRECISION = "fp32"      # what a training pass of the mip field computes in, whatever tier is selected
 
 
 class MipFieldRaw(Function):
@@ -145,14 +144,17 @@ class MipFieldRaw(Function):
         R, S = bins.shape[0], bins.shape[1] - 1
         dev = origins.device
         need_grad = grad_mode and (any(ctx.needs_input_grad[7:]) or (pose12 is not None and ctx.needs_input_grad[6]))
-        if need_grad and precision != _capi.PREC_F32:
-            # the tensor-core tier of the mip field is forward-only: a training pass runs the fp32 kernels -- said out
-            # loud once, and visible to callers (bench.py reports it) through EFFECTIVE_TRAIN_PRECISION
+        want_pose_grad = pose12 is not None and ctx.needs_input_grad[6] and pose12.requires_grad
+        if need_grad and precision != _capi.PREC_F32 and want_pose_grad:
+            # the tensor-core backward of the mip field produces weight gradients only: a pass that must differentiate
+            # the ray (an object's pose, through the integrated positional encoding) runs the fp32 kernels -- said out
+            # loud once
             global _WARNED_FP32_TRAINING
             if not _WARNED_FP32_TRAINING:
                 import warnings
-                warnings.warn("star_b200 mip field: the 16-bit tensor-core tier has no backward pass; this training pass "
-                              "(and every later one) runs on the fp32 CUDA-core kernels", RuntimeWarning, stacklevel=2)
+                warnings.warn("star_b200 mip field: the 16-bit tensor-core tier has no pose gradient; object fields whose "
+                              "pose requires grad run this (and every later) training pass on the fp32 CUDA-core kernels",
+                              RuntimeWarning, stacklevel=2)
                 _WARNED_FP32_TRAINING = True
             precision = _capi.PREC_F32
         flat, packed = rt.refresh(precision)
@@ -197,7 +199,7 @@ class MipFieldRaw(Function):
         g_sigma = torch.zeros((R, S), device=dev) if g_sigma is None else _c(g_sigma)
         g_rgb = torch.zeros((R, S, 3), device=dev) if g_rgb is None else _c(g_rgb)
         grad_flat = torch.zeros_like(ctx.flat)
-        pose_acc = torch.zeros((32,), device=dev) if p12 is not None else None
+        pose_acc = torch.zeros((32,), device=dev) if (p12 is not None and precision == _capi.PREC_F32) else None
         for i, (a, b) in enumerate(ctx.chunks):
             n = (b - a) * S
             if ctx.stashes is not None:
@@ -230,7 +232,7 @@ class MipFieldRaw(Function):
             grads.append(grad_flat[off:off + n].view(shp))
             off += n
         g_pose = None
-        if p12 is not None and ctx.needs_input_grad[6]:
+        if pose_acc is not None and ctx.needs_input_grad[6]:
             # Euclidean gradient w.r.t. [R | t]:  dR = sum g o^T + sum h d^T,  dt = sum g
             g_pose = torch.cat([pose_acc[3:12] + pose_acc[15:24], pose_acc[0:3]])
         return (None, None, None, None, None, None, g_pose, *grads)

@@ -433,7 +433,7 @@ def build_workload(args, dev, rank, world):
     return net, ro_h, rd_h, step_device, params
 
 
-MIP_TIERS = ("fp32", "bf16", "fp16")      # precision tiers of the mip field (16-bit tiers: forward only)
+MIP_TIERS = ("fp32", "bf16", "fp16")      # precision tiers of the mip field (16-bit tiers: forward + weight gradients)
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -466,7 +466,8 @@ def run_b200(args):
         # the other configurations BASELINE.json names, as sub-records of the same line (weak scaling like the headline:
         # every rank its own rays): C4 = static + 5 objects with pose gradients, C5 = mip field
         for name, wk, mode, rays in (("c4_train", "c4", "train", 8192), ("c4_train_r1000", "c4", "train", 1000),
-                                     ("c4_render", "c4", "render", 65536), ("c5_render", "c5", "render", 16384)):
+                                     ("c4_render", "c4", "render", 65536), ("c5_render", "c5", "render", 16384),
+                                     ("c5_train", "c5", "train", 4096)):
             a3 = argparse.Namespace(**vars(args))
             a3.workload, a3.mode, a3.rays, a3.no_cpu_baseline, a3.opt_step = wk, mode, rays, True, False
             a3.steps, a3.warmup = min(args.steps, 5), 3
@@ -703,8 +704,7 @@ def measure(args):
             "metric": metric_name(args.mode), "value": total_rays / (ms * 1e-3), "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[
-                args.precision if (args.workload != "c5" or (args.precision in MIP_TIERS and not train)) else "fp32"],
+            "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision],
             "data": "synthetic", "config": workload_config(args, args.precision),
             "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 24 * R,
                     "d2h_bytes_per_step": (4 if train else 20 * R)},

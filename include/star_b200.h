@@ -291,8 +291,10 @@ int star_mip_pdf_sample(const float* spacing_bins, const float* weights, int64_t
  * [2**linspace(0,24,24) | its square | 2**linspace(0,4,4) | pad].  radius = sqrt(pixel_area)/sqrt(pi) (= 0.5642:
  * the reference passes pixel_area = 1, star_mipnerf.py:267).
  * Outputs are RAW (pre-softplus density, pre-sigmoid rgb), written with the strides of star_mlp_forward.
- * Precision tiers: STAR_PREC_F32 (CUDA cores, forward + backward) and STAR_PREC_BF16 / STAR_PREC_F16 (tcgen05
- * tensor cores, forward / inference only: stash must be NULL; the frequency table is baked into the packed image). */
+ * Precision tiers: STAR_PREC_F32 (CUDA cores, forward + backward incl. the pose accumulators) and STAR_PREC_BF16 /
+ * STAR_PREC_F16 (tcgen05 tensor cores; the frequency table is baked into the packed image): forward, and -- with a stash --
+ * a backward pass to the WEIGHTS (star_mip_field_backward with pose_acc == NULL; with pose_acc != NULL it returns
+ * STAR_E_UNSUPPORTED: the gradient of the ray through the integrated positional encoding exists on the fp32 tier only). */
 size_t star_mip_param_count(void);
 size_t star_mip_packed_bytes(int precision);
 int star_mip_pack_weights(int precision, const float* flat_master, const float* freqs, void* packed, void* stream);

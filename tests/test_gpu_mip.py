@@ -354,10 +354,56 @@ def psnr_shift(a, b):
     return float((pa - pb).abs())
 
 
-def test_mip_tc_training_falls_back_to_fp32_kernels_not_to_cpu():
-    """The 16-bit tiers of the mip field are forward-only: under autograd the fp32 CUDA kernels run (same gradients
-    as an fp32-tier module)."""
-    net, _ = make_net(0, 8, 8, 64, seed=11, training=True, gain=1.4)
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("R,S,with_pose", [(8, 32, False), (70, 33, False), (40, 48, True), (1250, 64, False)])
+def test_mip_tc_backward_matches_rounding_model_and_fp64(R, S, with_pose, prec):
+    """Tensor-core backward of the mip field (stash forward + dX chain + dW GEMMs + head gradients), weight gradients.
+    Two fp64 autograd references, as for the vanilla MLP: the oracle's operand-rounding model with straight-through
+    gradients (what remains is the 16-bit rounding of the back-propagated gradients) and the exact network (ReLU masks
+    flip under 16-bit operands).  with_pose: an object field whose pose does NOT require grad -- weights only."""
+    net, sd = make_net(1, 4, 4, 64, seed=3, training=True, gain=1.4)
+    net.set_precision(prec)
+    ro, vd, eu = _field_inputs(R, S, 10)
+    model = net.dynamic_nerfs[0] if with_pose else net.static_nerf
+    prefix = "dynamic_nerfs.0." if with_pose else "static_nerf."
+    pose7 = so.random_poses7(1, seed=4)[0]
+    ga = torch.randn(R, S, generator=gen(20))
+    gc = torch.randn(R, S, 3, generator=gen(21))
+    dt = torch.float64
+
+    def run_oracle(emulate):
+        p = {k: v.to(dt).clone().requires_grad_(True) for k, v in sd.items() if k.startswith(prefix)}
+        o, d = ro.to(dt), vd.to(dt)
+        if with_pose:
+            o, d = so.se3_act(pose7.to(dt), o), so.so3_act(pose7[3:].to(dt), d)
+        e = eu.to(dt)
+        a, c = mo.mip_field(p, prefix, o, d, e[:, :-1], e[:, 1:], emulate=emulate, return_raw=True)
+        ((a * ga.to(dt)).sum() + (c * gc.to(dt)).sum()).backward()
+        return p
+
+    p64, pm = run_oracle(False), run_oracle(prec)
+    p12 = star_b200.functional.pose_to_mat12(cu(pose7)) if with_pose else None     # no grad wanted for the pose
+    a, c = model.raw(cu(ro), cu(vd), cu(eu), p12)
+    ((a * cu(ga)).sum() + (c * cu(gc)).sum()).backward()
+    tol_model, tol_exact = (0.04, 0.25) if prec == "bf16" else (0.03, 0.12)
+
+    def rel(x, ref):
+        return float((x.cpu().double() - ref).norm() / (ref.norm() + 1e-30))
+
+    for k, v in model.named_parameters():
+        assert v.grad is not None, k
+        assert rel(v.grad, pm[prefix + k].grad) < tol_model, (k, rel(v.grad, pm[prefix + k].grad))
+        assert rel(v.grad, p64[prefix + k].grad) < tol_exact, (k, rel(v.grad, p64[prefix + k].grad))
+
+
+def test_mip_tc_training_with_pose_gradient_runs_the_fp32_kernels_loudly():
+    """The tensor-core backward of the mip field has no gradient of the ray: an object field whose pose requires grad
+    runs its training pass on the fp32 kernels (with a RuntimeWarning, once) -- same gradients as the fp32 tier; the
+    static field of the same model still trains on the tensor cores."""
+    import warnings
+    from star_b200 import mip_functional as MF_
+    MF_._WARNED_FP32_TRAINING = False
+    net, _ = make_net(1, 8, 8, 64, seed=11, training=True, gain=1.4)
     ro, vd = rays(8, 3)
     t = torch.rand(8, 9, generator=gen(1))
     u = torch.rand(8, 9, generator=gen(2))
@@ -365,7 +411,17 @@ def test_mip_tc_training_falls_back_to_fp32_kernels_not_to_cpu():
     for prec in ("fp32", "bf16"):
         net.set_precision(prec)
         net.zero_grad()
-        o = net(cu(ro), cu(vd), None, t_rand=cu(t), u_rand=cu(u))
-        o["rgb"].sum().backward()
-        outs[prec] = net.static_nerf.field.mlp_base.layers[0].weight.grad.clone()
-    assert torch.equal(outs["fp32"], outs["bf16"])
+        pose = cu(so.random_poses7(1, seed=8)).requires_grad_(True)
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            o = net(cu(ro), cu(vd), pose, t_rand=cu(t), u_rand=cu(u))
+            o["rgb"].sum().backward()
+        outs[prec] = (net.dynamic_nerfs[0].field.mlp_base.layers[0].weight.grad.clone(), pose.grad.clone(),
+                      net.static_nerf.field.mlp_base.layers[0].weight.grad.clone(),
+                      [x for x in w if issubclass(x.category, RuntimeWarning)])
+    assert len(outs["fp32"][3]) == 0 and len(outs["bf16"][3]) >= 1
+    # the object field ran the same fp32 kernels; its upstream gradients differ only through the static field's bf16 forward
+    for i in (0, 1):
+        a, b = outs["bf16"][i], outs["fp32"][i]
+        assert float((a - b).norm() / b.norm()) < 0.2
+    assert float(outs["bf16"][2].abs().max()) > 0
