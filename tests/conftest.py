@@ -10,6 +10,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # never test a stale library: rebuild libstar_b200.so when a source is newer (no-op otherwise; nvcc cross-compiles)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "_star_build", os.path.join(ROOT, "3d-mot-using-neural-radiance-fields_b200", "_build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build(force=False)
 
 
 def pytest_collection_modifyitems(config, items):
