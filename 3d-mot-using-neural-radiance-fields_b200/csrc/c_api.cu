@@ -14,7 +14,7 @@ int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, v
 int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                     const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
                     float* raw_rgb, int64_t ray_stride, void* stash, int* status, int fp16, int single_cta,
-                    cudaStream_t st);
+                    int stash_direct, cudaStream_t st);
 
 size_t star_tc_gstash_bytes(const TcLayout& tl, int64_t n_samples);
 int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
@@ -127,7 +127,8 @@ extern "C" int star_mlp_forward(const StarNetDesc* d, const void* packed, const 
     if (rc) return rc;
     return star_tc_forward(tl, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, raw_alpha, raw_rgb,
                            alpha_ray_stride, stash, status, star_prec(d) == STAR_PREC_F16,
-                           (d->precision & STAR_PREC_FLAG_CTA_PAIR) == 0, (cudaStream_t)stream);
+                           (d->precision & STAR_PREC_FLAG_CTA_PAIR) == 0,
+                           (d->precision & STAR_PREC_FLAG_STASH_DIRECT) != 0, (cudaStream_t)stream);
   }
   return STAR_E_UNSUPPORTED;
 }

@@ -45,6 +45,7 @@ struct EpiCtx {
   uint32_t stash_done0;        // smem address of barrier stash_done[0] of the A set this layer writes
   int set;                     // A set this layer writes (0 unless the training pair kernel alternates two sets)
   bool publishes;              // training: this layer's output blocks are bulk-stored to the stash afterwards
+  bool direct;                 // training, A/B variant: the epilogue threads write the stash themselves (no bulk stores)
   bool no_stash_wait;          // debug (timing experiments only)
   uint32_t w_full0;            // smem address of barrier w_full[0]
   uint32_t next_stage0;        // ring stage of the NEXT layer's K-block 0 (its K-block kb uses (next_stage0 + kb) % NS)
@@ -121,7 +122,8 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3], u
         }
         if (c.publishes) stash_pend |= bit;
       }
-      store_row16<FP16, RELU>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v);
+      store_row16<FP16, RELU>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v,
+                              (STASH && c.direct) ? c.stash_out + kb * TC_KB_BYTES : nullptr);
       if (STASH && RELU && !c.no_mask) {
         uint32_t b = 0u;
 #pragma unroll
@@ -134,7 +136,7 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3], u
       __syncwarp();
       if (c.lane == 0) {
         mbar_arrive(c.w_full0 + 8u * ((c.next_stage0 + (uint32_t)kb) & c.ns_mask));
-        if (STASH) mbar_arrive(c.a_ready0 + 8u * (uint32_t)kb);
+        if (STASH && !c.direct) mbar_arrive(c.a_ready0 + 8u * (uint32_t)kb);
       }
     }
   }
@@ -153,7 +155,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
                   const float* __restrict__ viewdirs, const float* __restrict__ pose12,
                   const float* __restrict__ sc_xyz, const float* __restrict__ sc_dir, int S, int64_t M,
                   float* __restrict__ raw_alpha, float* __restrict__ raw_rgb, int64_t ray_stride,
-                  uint8_t* __restrict__ stash, int* __restrict__ status, int* dbg, int dbg_mode_arg) {
+                  uint8_t* __restrict__ stash, int* __restrict__ status, int* dbg, int dbg_mode_arg, int stash_direct) {
   // status (nullable): word set to 1 when a raw output is not finite -- the range guard of the fp16-operand tier (an
   // activation beyond 65504 becomes +inf in the 16-bit operand and reaches the heads as inf / NaN) and, for any tier,
   // the sign of non-finite inputs or weights.
@@ -265,7 +267,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             mbar_arrive(bar(BAR_STASH_DONE_KB(4 * set + 3)));
           }
         };
-        if (STASH) {   // a_ready[0] also carries the encoder's arrival at the start of a tile: consume that phase
+        if (STASH && !stash_direct) {   // a_ready[0] also carries the encoder's arrival at the start of a tile: consume that phase
           mbar_wait(bar(BAR_A_READY(0)), s_par & 1u, dbg, 6);
           s_par ^= 1u;
         }
@@ -274,7 +276,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           const uint32_t kb_bytes = (uint32_t)lay.L[l].N * 128u;
           const uint32_t bytes = PAIR ? kb_bytes / 2 : kb_bytes;
           for (int kb = 0; kb < lay.L[l].nkb; ++kb) {
-            if (STASH && l >= 2 && kb < 4) stash_chunk(l - 2, kb);
+            if (STASH && !stash_direct && l >= 2 && kb < 4) stash_chunk(l - 2, kb);
             mbar_wait(bar(BAR_W_EMPTY(stage)), phase ^ 1u, dbg, 1);
             if (lay.L[l].kind == LK_VIEWS && kb == 4) mbar_arrive_n(bar(BAR_W_FULL(stage)), TC_EPI_WARPS);
             if (dbg_mode & 2) {
@@ -287,7 +289,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             if (++stage == NS) { stage = 0; phase ^= 1u; }
           }
         }
-        if (STASH)
+        if (STASH && !stash_direct)
           for (int kb = 0; kb < 4; ++kb) stash_chunk(lay.n_layers - 2, kb);   // feature_linear's output blocks
       }
       if (STASH) bulk_wait_group0();
@@ -388,6 +390,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     ctx.stash_done0 = bar(BAR_STASH_DONE_KB(0));
     ctx.set = 0;
     ctx.publishes = false;
+    ctx.direct = stash_direct != 0;
     ctx.ns_mask = NS - 1;
     ctx.no_stash_wait = (dbg_mode & 32) != 0;
     for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
@@ -440,7 +443,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(bar(BAR_W_FULL(kstage & (NS - 1))));   // operand of (layer 0, K-block 0)
-          if (STASH) mbar_arrive(bar(BAR_A_READY(0)));
+          if (STASH && !stash_direct) mbar_arrive(bar(BAR_A_READY(0)));
           mbar_arrive(bar(BAR_A_READY(4)));
         }
         TL_STAMP(tile == tl_tile && tid == 0, 9);
@@ -467,7 +470,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         ctx.set = (l + 1) & (NSETS - 1);
         ctx.sA = sA + (uint32_t)ctx.set * 4u * TC_KB_BYTES;
         ctx.stash_done0 = bar(BAR_STASH_DONE_KB(4 * ctx.set));
-        ctx.publishes = STASH && l + 1 < lay.n_layers;
+        ctx.publishes = STASH && !stash_direct && l + 1 < lay.n_layers;
         mbar_wait(bar(BAR_ACC_FULL), acc_par, dbg, 4);
         acc_par ^= 1u;
         tc_fence_after();
@@ -477,7 +480,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             fence_proxy_async_smem(); tc_fence_before(); __syncwarp();
             if (lane == 0) {
               mbar_arrive(bar(BAR_W_FULL((kstage + (uint32_t)kb) & (NS - 1))));
-              if (STASH) mbar_arrive(bar(BAR_A_READY(kb)));
+              if (STASH && !stash_direct) mbar_arrive(bar(BAR_A_READY(kb)));
             }
           }
         } else if (kind == LK_FC0 || kind == LK_FC1 || kind == LK_IN) {
@@ -615,7 +618,7 @@ int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, v
 int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                     const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
                     float* raw_rgb, int64_t ray_stride, void* stash, int* status, int fp16, int single_cta,
-                    cudaStream_t st) {
+                    int stash_direct, cudaStream_t st) {
   const int64_t M = (int64_t)R * S;
   const int64_t ntiles = (M + TC_M - 1) / TC_M;
   int dev = 0, sms = 148;
@@ -630,7 +633,7 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pt
   const int max_units = pair ? sms / 2 : sms;
   const int grid = (int)(units < max_units ? units : max_units) * (pair ? 2 : 1);
   using Kern = void (*)(const TcLayout, const uint8_t*, const StarPtsSrc, const float*, const float*, const float*,
-                        const float*, int, int64_t, float*, float*, int64_t, uint8_t*, int*, int*, int);
+                        const float*, int, int64_t, float*, float*, int64_t, uint8_t*, int*, int*, int, int);
   Kern kern;
   if (pair)
     kern = with_stash ? (fp16 ? mlp_fwd_tc_kernel<true, true, true> : mlp_fwd_tc_kernel<false, true, true>)
@@ -654,7 +657,7 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pt
   cfg.numAttrs = 1;
   auto launch = [&](int* dbg, int dbg_mode) -> int {
     cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
-                                        raw_alpha, raw_rgb, ray_stride, (uint8_t*)stash, status, dbg, dbg_mode);
+                                        raw_alpha, raw_rgb, ray_stride, (uint8_t*)stash, status, dbg, dbg_mode, stash_direct);
     if (le != cudaSuccess) { g_star_last_cuda_error = (int)le; return STAR_E_CUDA; }
     return STAR_OK;
   };

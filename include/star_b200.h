@@ -52,6 +52,9 @@ enum { STAR_PREC_F32 = 0, STAR_PREC_BF16 = 1, STAR_PREC_F16 = 2 };
  * profiles/r2b_*: the layer chain of a tile is latency-bound and the pair adds a cross-CTA hop to every operand hand-off),
  * so it is opt-in and kept for A/B measurements. */
 #define STAR_PREC_FLAG_CTA_PAIR 0x100
+/* training forward, A/B variant: the epilogue threads write the activation stash themselves (two 16-byte global stores per
+ * thread and chunk) instead of one bulk copy per completed operand block issued by the producer warp. */
+#define STAR_PREC_FLAG_STASH_DIRECT 0x200
 
 /* One NeRF radiance MLP (models/nerf.py:34-110, models/resnet.py:62-110).  W is fixed at 256,
  * the view branch at 128 (all 15 reference configs agree). */
