@@ -20,7 +20,7 @@ size_t star_tc_gstash_bytes(const TcLayout& tl, int64_t n_samples);
 int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                      const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, const float* d_raw_alpha,
                      const float* d_raw_rgb, int64_t ray_stride, const void* stash, void* gstash, float* grad_flat,
-                     float* pose_acc, int fp16, cudaStream_t st);
+                     float* pose_acc, int fp16, int serial_dx, cudaStream_t st);
 
 int star_f32_pack(const MlpLayout& lay, const float* master, void* packed, cudaStream_t st);
 int star_f32_forward(const MlpLayout& lay, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
@@ -161,7 +161,8 @@ extern "C" int star_mlp_backward(const StarNetDesc* d, const void* packed, const
     if (rc) return rc;
     return star_tc_backward(tl, lay, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, d_raw_alpha,
                             d_raw_rgb, alpha_ray_stride, stash, workspace, grad_flat, pose_acc,
-                            star_prec(d) == STAR_PREC_F16, (cudaStream_t)stream);
+                            star_prec(d) == STAR_PREC_F16, (d->precision & STAR_PREC_FLAG_DX_SERIAL) != 0,
+                            (cudaStream_t)stream);
   }
   return STAR_E_UNSUPPORTED;
 }

@@ -500,6 +500,447 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
   }
 }
 
+// ============================================================================================ dX chain, pipelined
+// Round 2.  In the kernel above every GEMM writes the same accumulator region T (the other one, X, holds the residual
+// gradient), so the MMAs of group g + 1 cannot start before the epilogue of group g has read ALL of T, and that epilogue
+// cannot start before ALL MMAs of group g are done: MMA (~2.8 k cycles) and epilogue (~3 k) of the 11 groups of a tile
+// alternate strictly, which is why the tensor pipe is active 29 % of the time.  Here every N = 256 GEMM is issued as two
+// N = 128 HALVES with their own completion barriers (half a -> T[0:128), half b -> T[128:256)); the epilogue consumes half a
+// (chunks 0, 1) while the tensor core still computes half b, and the next group's half a starts as soon as chunks 0 and 1
+// have been read (T[0:128) is free again) and the operand blocks it needs have been published -- K-block by K-block, like
+// the forward kernel.  Extra synchronisation this needs: an operand block may be overwritten by the next epilogue only
+// after the LAST MMA that reads it (half b of the same K-block: b_done[kb], a tcgen05.commit per K-block) and after its
+// copy to the gradient stash has left shared memory (stash_done[kb], per block).  The weight ring holds 8 stages of
+// 16 KB (one half K-block each).
+#define BWD2_MAX_STAGES 112
+#define BAR2_ACC_B (2 * TC_MAX_NS + 15)
+#define BAR2_B_DONE(kb) (2 * TC_MAX_NS + 16 + (kb))
+#define BWD2_NS 8
+#define BWD2_STAGE_BYTES 16384
+
+struct Bwd2Stage {
+  uint32_t w_off, bytes;
+  int a_kb, N, tcol, accum;
+  int wait0, wait1;      // a_ready barriers to wait for before this stage (-1: none)
+  int sig_acc;           // after this stage commit: 1 = accumulator half a complete, 2 = half b (or the whole group) complete
+  int sig_bdone;         // >= 0: this is the last stage of the group that reads A block sig_bdone
+};
+struct Bwd2Phase {
+  int kind, nch, mask_blk, g_blk, mask_layer;
+  int acc_a, acc_b;      // the preceding group signals half a / half b (phase waits for a before chunk 0, for b before chunk 2)
+  int reads_mask;        // A blocks the FOLLOWING group reads (bit kb): they carry a b_done commit
+};
+struct Bwd2Smem {
+  uint32_t A, W, small, tab, bars, tmem_ptr, total;
+};
+__host__ __device__ static inline Bwd2Smem bwd2_smem_layout(uint32_t small_bytes) {
+  Bwd2Smem s;
+  uint32_t o = 0;
+  s.A = o; o += 4 * TC_KB_BYTES;
+  s.W = o; o += BWD2_NS * BWD2_STAGE_BYTES;
+  s.small = o; o += small_bytes;
+  s.tab = o; o += BWD2_MAX_STAGES * sizeof(Bwd2Stage) + BWD_MAX_PHASES * sizeof(Bwd2Phase) + 16;
+  s.bars = o; o += 40 * 8;
+  s.tmem_ptr = o; o += 16;
+  s.total = o + 1024;
+  return s;
+}
+
+template <bool F16, bool POSE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+mlp_bwd2_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const StarPtsSrc pts,
+                   const float* __restrict__ viewdirs, const float* __restrict__ pose12,
+                   const float* __restrict__ sc_xyz, const float* __restrict__ sc_dir, int S, int64_t M,
+                   const float* __restrict__ d_raw_alpha, const float* __restrict__ d_raw_rgb, int64_t ray_stride,
+                   const uint8_t* __restrict__ stash, uint8_t* __restrict__ gstash, float* __restrict__ pose_acc,
+                   const float* __restrict__ absmax, int* dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw_addr);
+  const Bwd2Smem sl = bwd2_smem_layout(lay.small_bytes);
+  const uint32_t sA = base + sl.A, sW = base + sl.W, sBars = base + sl.bars;
+  float* s_small = reinterpret_cast<float*>(gbase + sl.small);
+  Bwd2Stage* stages = reinterpret_cast<Bwd2Stage*>(gbase + sl.tab);
+  Bwd2Phase* phases = reinterpret_cast<Bwd2Phase*>(gbase + sl.tab + BWD2_MAX_STAGES * sizeof(Bwd2Stage));
+  int* counts = reinterpret_cast<int*>(gbase + sl.tab + BWD2_MAX_STAGES * sizeof(Bwd2Stage) + BWD_MAX_PHASES * sizeof(Bwd2Phase));
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(gbase + sl.tmem_ptr);
+  auto bar = [&](int i) -> uint32_t { return sBars + 8u * (uint32_t)i; };
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (M + TC_M - 1) / TC_M;
+  constexpr bool has_pose = POSE;
+
+  // ---- the per-tile program: phase p (epilogue) writes the operand blocks that group p (MMAs) reads
+  if (tid == 0) {
+    const int nl = lay.n_layers, V = nl - 1, F = nl - 2, O = nl - 3;
+    int ns = 0, np = 0;
+    auto stage = [&](uint32_t w_off, uint32_t bytes, int a_kb, int N, int tcol, int accum, int wait0, int wait1, int sig_acc,
+                     int sig_bdone) {
+      Bwd2Stage& s = stages[ns++];
+      s.w_off = w_off; s.bytes = bytes; s.a_kb = a_kb; s.N = N; s.tcol = tcol; s.accum = accum;
+      s.wait0 = wait0; s.wait1 = wait1; s.sig_acc = sig_acc; s.sig_bdone = sig_bdone;
+    };
+    auto phase = [&](int kind, int nch, int mask_blk, int g_blk, int mask_layer, int acc_a, int acc_b) {
+      Bwd2Phase& p = phases[np++];
+      p.kind = kind; p.nch = nch; p.mask_blk = mask_blk; p.g_blk = g_blk; p.mask_layer = mask_layer;
+      p.acc_a = acc_a; p.acc_b = acc_b; p.reads_mask = 0;
+    };
+    // N = 256 GEMM of layer l over nkb operand blocks into [tcol, tcol + 256) as two N = 128 halves.  The B operand of a
+    // half = rows [128 h, 128 h + 128) of the transposed K-block = a contiguous 16 KB half of its 32 KB image.
+    // extra_b: more stages follow in the group (dirs rows of the view layer): they carry the "half b complete" commit.
+    auto gemm2 = [&](uint32_t wt_off, int nkb, int tcol, bool extra_b) {
+      for (int h = 0; h < 2; ++h)
+        for (int kb = 0; kb < nkb; ++kb) {
+          const bool last = kb == nkb - 1;
+          int w0 = -1, w1 = -1;
+          if (h == 0) {                       // operand block kb published; before the first MMA also: T[0:128) is free,
+            w0 = kb;                          // i.e. the previous epilogue has read its chunks 0 and 1
+            if (kb == 0 && nkb > 1) w1 = 1;
+          }
+          stage(lay.stream_bytes + wt_off + (uint32_t)kb * 32768u + (uint32_t)h * 16384u, 16384u, kb, 128, tcol + 128 * h,
+                kb > 0, w0, w1, last ? (h == 0 ? 1 : (extra_b ? 0 : 2)) : 0, (h == 1 && !extra_b) ? kb : -1);
+          phases[np - 1].reads_mask |= 1 << kb;
+        }
+    };
+    phase(BK_PRE, 2, lay.L[V].s_out, lay.L[V].g_out, -1, 0, 0);
+    gemm2(lay.L[V].wt_off, 2, 256, has_pose);      // views: T <- G_v Wv[:, :256]^T
+    if (has_pose)                                   // (+ X[0:32] <- G_v Wv[:, 256:288]^T for objects)
+      for (int kb = 0; kb < 2; ++kb)
+        stage(lay.stream_bytes + lay.wt_dirs_off + (uint32_t)kb * 8192u, 8192u, kb, 32, 0, kb > 0, -1, -1, kb == 1 ? 2 : 0, kb);   // (the last readers of blocks 0, 1)
+    phase(BK_FEAT, 4, -1, lay.L[F].g_out, -1, 1, 1);
+    gemm2(lay.L[F].wt_off, 4, 0, false);
+    phase(BK_OUT, 4, -1, lay.L[O].g_out, -1, 1, 1);
+    gemm2(lay.L[O].wt_off, 4, 256, false);
+    phase(BK_X0, 4, -1, lay.L[O - 1].g_out, O - 1, 1, 1);
+    for (int b = lay.n_blocks - 1; b >= 0; --b) {
+      const int l0 = 1 + 2 * b, l1 = 2 + 2 * b;
+      gemm2(lay.L[l1].wt_off, 4, 256, false);
+      phase(BK_FC1, 4, -1, lay.L[l0].g_out, l1 - 1, 1, 1);
+      gemm2(lay.L[l0].wt_off, 4, 256, false);
+      phase(BK_FC0, 4, -1, lay.L[l0 - 1].g_out, l0 - 1, 1, 1);
+    }
+    if (has_pose) {   // d enc_xyz = G_in W_in: N = 64, one "half"
+      for (int kb = 0; kb < 4; ++kb) {
+        stage(lay.stream_bytes + lay.L[0].wt_off + (uint32_t)kb * 8192u, 8192u, kb, 64, 256, kb > 0, kb, -1, kb == 3 ? 1 : 0, kb);
+        phases[np - 1].reads_mask |= 1 << kb;
+      }
+      phase(BK_IN, 0, -1, -1, -1, 1, 0);
+    }
+    counts[0] = ns; counts[1] = np;
+  }
+  if (warp == TC_EPI_WARPS && lane == 0) {
+    for (int i = 0; i < BWD2_NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), 1); mbar_init(bar(BAR_W_EMPTY(i)), 1); }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar(BAR_A_READY(i)), TC_EPI_WARPS);
+      mbar_init(bar(BAR_STASH_DONE_KB(i)), 1);
+      mbar_init(bar(BAR2_B_DONE(i)), 1);
+    }
+    mbar_init(bar(BAR_ACC_FULL), 1);
+    mbar_init(bar(BAR2_ACC_B), 1);
+    fence_mbar_init();
+  }
+  if (warp == TC_EPI_WARPS + 1) tmem_alloc(base + sl.tmem_ptr, TC_TMEM_COLS);
+  for (int i = tid; i < lay.small_floats; i += TC_THREADS) s_small[i] = reinterpret_cast<const float*>(packed)[i];
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const int n_stages = counts[0], n_phases = counts[1];
+
+  if (warp == TC_EPI_WARPS) {
+    // ======================================================================== weight producer + gradient-stash writer
+    // per group: request its weight stages (each waits for its ring slot, i.e. trails the MMAs of the previous group), then
+    // copy the operand blocks of the phase that feeds it to the gradient stash as they are published
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, s_par = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        uint8_t* gs_tile = gstash + (size_t)tile * (size_t)lay.gstash_blocks * TC_BLOCK_BYTES;
+        auto stash_phase = [&](int g) {
+          const int nch = phases[g].nch, g_blk = phases[g].g_blk;
+          if (nch == 0 || g_blk < 0) return;
+          for (int kb = 0; kb < nch; ++kb) {
+            mbar_wait(bar(BAR_A_READY(kb)), (s_par >> kb) & 1u, dbg, 6);
+            s_par ^= 1u << kb;
+            bulk_s2g(gs_tile + (size_t)(g_blk + kb) * TC_BLOCK_BYTES, sA + (uint32_t)kb * TC_KB_BYTES, TC_KB_BYTES);
+            bulk_commit_group();
+            if (kb >= 1) {                     // groups complete in order: block kb - 1 has been read
+              bulk_wait_group_read1();
+              mbar_arrive(bar(BAR_STASH_DONE_KB(kb - 1)));
+            }
+          }
+          bulk_wait_group_read0();
+          mbar_arrive(bar(BAR_STASH_DONE_KB(nch - 1)));
+        };
+        int i = 0;
+        for (int g = 0; g < n_phases; ++g) {
+          // the stages of group g: up to (and including) the one that signals "group complete" (sig_acc == 2, or == 1 for a
+          // single-half group followed by a phase without half b)
+          const bool has_group = i < n_stages;
+          if (has_group) {
+            const int want = phases[g + 1 < n_phases ? g + 1 : g].acc_b ? 2 : 1;
+            for (;;) {
+              const Bwd2Stage& s = stages[i++];
+              mbar_wait(bar(BAR_W_EMPTY(stage)), phase ^ 1u, dbg, 1);
+              mbar_arrive_expect_tx(bar(BAR_W_FULL(stage)), s.bytes);
+              bulk_g2s(sW + stage * BWD2_STAGE_BYTES, packed + lay.small_bytes + s.w_off, s.bytes, bar(BAR_W_FULL(stage)));
+              if (++stage == BWD2_NS) { stage = 0; phase ^= 1u; }
+              if (s.sig_acc == want) break;
+            }
+          }
+          stash_phase(g);
+        }
+      }
+      bulk_wait_group0();
+    }
+  } else if (warp == TC_EPI_WARPS + 1) {
+    // ======================================================================== MMA issuer
+    uint32_t stage = 0, phase = 0, a_par = 0;
+    const uint64_t desc_a0 = umma_desc_sw128(sA), desc_w0 = umma_desc_sw128(sW);
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int i = 0; i < n_stages; ++i) {
+        const Bwd2Stage s = stages[i];
+        if (s.wait0 >= 0) {
+          mbar_wait(bar(BAR_A_READY(s.wait0)), (a_par >> s.wait0) & 1u, dbg, 2);
+          a_par ^= 1u << s.wait0;
+        }
+        if (s.wait1 >= 0) {      // (waited for without consuming: its own stage consumes it)
+          mbar_wait(bar(BAR_A_READY(s.wait1)), (a_par >> s.wait1) & 1u, dbg, 2);
+        }
+        mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_16(TC_M, s.N, F16 ? 0 : 1);
+        const uint64_t a0 = desc_a0 + (uint64_t)(s.a_kb * (TC_KB_BYTES >> 4));
+        const uint64_t b0 = desc_w0 + (uint64_t)(stage * (BWD2_STAGE_BYTES >> 4));
+        if (elect_one_sync()) {
+          tc_mma_kblock<4>(tmem_base + (uint32_t)s.tcol, a0, b0, idesc, s.accum ? 1u : 0u);
+          tc_commit(bar(BAR_W_EMPTY(stage)));
+          if (s.sig_bdone >= 0) tc_commit(bar(BAR2_B_DONE(s.sig_bdone)));
+          if (s.sig_acc == 1) tc_commit(bar(BAR_ACC_FULL));
+          if (s.sig_acc == 2) tc_commit(bar(BAR2_ACC_B));
+        }
+        __syncwarp();
+        if (++stage == BWD2_NS) { stage = 0; phase ^= 1u; }
+      }
+      // the tile's last phase publishes operand blocks that no MMA reads (static nets: G of lin_in, for dW only): consume
+      // their a_ready phases to keep the parities in step across tiles
+      const Bwd2Phase& PL = phases[n_phases - 1];
+      if (PL.reads_mask == 0)
+        for (int kb = 0; kb < PL.nch; ++kb) {
+          mbar_wait(bar(BAR_A_READY(kb)), (a_par >> kb) & 1u, dbg, 5);
+          a_par ^= 1u << kb;
+        }
+    }
+  } else {
+    // ======================================================================== epilogue warps
+    const int q = warp & 3, cg = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
+    uint32_t acc_par = 0, accb_par = 0;
+    uint32_t st_par = 0, st_pend = 0;      // stash_done[kb]: parity of the next wait / a store of block kb is outstanding
+    uint32_t bd_par = 0, bd_pend = 0;      // b_done[kb]: the same for "the last MMA that reads block kb"
+    float pacc[POSE ? 27 : 1];
+#pragma unroll
+    for (int i = 0; i < (POSE ? 27 : 1); ++i) pacc[i] = 0.f;
+    const float gscale = F16 ? grad_scale_of(absmax) : 1.f;
+    // operand block kb is about to be overwritten: its last reader (MMA) and its copy to the gradient stash must be done
+    auto claim_block = [&](int kb) {
+      const uint32_t bit = 1u << kb;
+      if (bd_pend & bit) {
+        mbar_wait(bar(BAR2_B_DONE(kb)), (bd_par & bit) ? 1u : 0u, dbg, 8);
+        bd_par ^= bit; bd_pend &= ~bit;
+      }
+      if (st_pend & bit) {
+        mbar_wait(bar(BAR_STASH_DONE_KB(kb)), (st_par & bit) ? 1u : 0u, dbg, 7);
+        st_par ^= bit; st_pend &= ~bit;
+      }
+    };
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t gi = tile * TC_M + row;
+      const bool valid = gi < M;
+      float da = 0.f, dc0 = 0.f, dc1 = 0.f, dc2 = 0.f;
+      float pw[3] = {0.f, 0.f, 0.f}, po[3] = {0.f, 0.f, 0.f}, dw[3] = {0.f, 0.f, 0.f}, dob[3] = {0.f, 0.f, 0.f};
+      if (valid) {
+        const int64_t r = gi / S;
+        const int64_t o = r * ray_stride + (gi - r * S);
+        da = d_raw_alpha[o] * gscale;
+        dc0 = d_raw_rgb[o * 3 + 0] * gscale; dc1 = d_raw_rgb[o * 3 + 1] * gscale; dc2 = d_raw_rgb[o * 3 + 2] * gscale;
+        if (has_pose) {
+          star_load_pt(pts, gi, r, pw[0], pw[1], pw[2]);
+          dw[0] = viewdirs[r * 3 + 0]; dw[1] = viewdirs[r * 3 + 1]; dw[2] = viewdirs[r * 3 + 2];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            po[i] = pose12[i * 3 + 0] * pw[0] + pose12[i * 3 + 1] * pw[1] + pose12[i * 3 + 2] * pw[2] + pose12[9 + i];
+            dob[i] = pose12[i * 3 + 0] * dw[0] + pose12[i * 3 + 1] * dw[1] + pose12[i * 3 + 2] * dw[2];
+          }
+        }
+      }
+      const uint8_t* st_tile = stash + (size_t)tile * (size_t)lay.stash_blocks * TC_BLOCK_BYTES;
+      const uint32_t x_sw = (uint32_t)row & 7u;
+
+      for (int pi = 0; pi < n_phases; ++pi) {
+        const Bwd2Phase P = phases[pi];
+        // masks of the whole phase first (global-memory latency hides behind the MMAs)
+        uint4 mq[2][2];
+        uint2 mbits = make_uint2(~0u, ~0u);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          mq[kb][0] = make_uint4(~0u, ~0u, ~0u, ~0u);
+          mq[kb][1] = mq[kb][0];
+          if (P.mask_blk >= 0 && kb < P.nch) {
+            const uint8_t* mb = st_tile + (size_t)(P.mask_blk + kb) * TC_BLOCK_BYTES;
+            mq[kb][0] = __ldg(reinterpret_cast<const uint4*>(mb + (uint32_t)row * 128u + ((((uint32_t)(cg * 2)) ^ x_sw) << 4)));
+            mq[kb][1] = __ldg(reinterpret_cast<const uint4*>(mb + (uint32_t)row * 128u + ((((uint32_t)(cg * 2 + 1)) ^ x_sw) << 4)));
+          }
+        }
+        if (P.mask_layer >= 0)
+          mbits = __ldg(reinterpret_cast<const uint2*>(st_tile + (size_t)lay.mask_blk0 * TC_BLOCK_BYTES +
+                                                       (size_t)P.mask_layer * TC_MASK_BYTES) + (cg * TC_M + row));
+        if (P.acc_a) {
+          mbar_wait(bar(BAR_ACC_FULL), acc_par, dbg, 4);
+          acc_par ^= 1u;
+          tc_fence_after();
+        }
+        auto wait_half_b = [&]() {
+          mbar_wait(bar(BAR2_ACC_B), accb_par, dbg, 4);
+          accb_par ^= 1u;
+          tc_fence_after();
+        };
+        const uint32_t tX = tmem_base + lane_addr + (uint32_t)(cg * TC_CPT);
+        const uint32_t tT = tX + 256u;
+        bool half_b_seen = false;
+        if (P.kind == BK_FEAT && has_pose) {
+          // d enc_dir sits in X[0:32], written by the stages that also complete half b; the next group (feature_linear^T)
+          // writes X from its first MMA on, i.e. as soon as chunks 0 and 1 of THIS phase are published: read it first
+          wait_half_b();
+          half_b_seen = true;
+          if (cg < 2) {
+            uint32_t r[16];
+            tmem_ld16(tX, r);
+            tmem_wait_ld();
+            float h[3] = {0.f, 0.f, 0.f};
+            if (cg == 0) fold_jacobian<0, 27>(r, dob, sc_dir, h);
+            else fold_jacobian<16, 27>(r, dob, sc_dir, h);
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) pacc[15 + i * 3 + j] += h[i] * dw[j];
+              pacc[24] += dob[1] * h[2] - dob[2] * h[1];
+              pacc[25] += dob[2] * h[0] - dob[0] * h[2];
+              pacc[26] += dob[0] * h[1] - dob[1] * h[0];
+            }
+          }
+          tc_fence_before();
+        }
+        if (P.kind == BK_IN) {       // d enc_xyz in T[0:64]: 16 columns per thread
+          uint32_t r[16];
+          tmem_ld16(tT, r);
+          tmem_wait_ld();
+          float g[3] = {0.f, 0.f, 0.f};
+          if (cg == 0) fold_jacobian<0, 63>(r, po, sc_xyz, g);
+          else if (cg == 1) fold_jacobian<16, 63>(r, po, sc_xyz, g);
+          else if (cg == 2) fold_jacobian<32, 63>(r, po, sc_xyz, g);
+          else fold_jacobian<48, 63>(r, po, sc_xyz, g);
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              pacc[i] += g[i];
+#pragma unroll
+              for (int j = 0; j < 3; ++j) pacc[3 + i * 3 + j] += g[i] * pw[j];
+            }
+            pacc[12] += po[1] * g[2] - po[2] * g[1];
+            pacc[13] += po[2] * g[0] - po[0] * g[2];
+            pacc[14] += po[0] * g[1] - po[1] * g[0];
+          }
+          tc_fence_before();
+          continue;
+        }
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          if (kb >= P.nch) break;
+          if (kb == 2 && P.acc_b && !half_b_seen) wait_half_b();
+          const int col0 = kb * 64 + cg * TC_CPT;
+          const uint4 m0 = mq[kb & 1][0], m1 = mq[kb & 1][1];
+          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          const uint32_t mb16 = ((kb < 2 ? mbits.x : mbits.y) >> ((kb & 1) * 16)) & 0xffffu;
+          float v[16];
+          if (P.kind == BK_PRE) {
+            const float* rw = s_small + lay.off_rgb_w + col0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = dc0 * rw[j] + dc1 * rw[STAR_WV + j] + dc2 * rw[2 * STAR_WV + j];
+          } else {
+            uint32_t r[16];
+            tmem_ld16(((P.kind == BK_OUT) ? tX : tT) + 64u * (uint32_t)kb, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          }
+          if (P.kind == BK_OUT) {
+            const float* aw = s_small + lay.off_alpha_w + col0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaf(da, aw[j], v[j]);
+          }
+          if (P.mask_blk >= 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t bits = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xffffu);
+              if (bits == 0u) v[j] = 0.f;
+            }
+          }
+          if (P.mask_layer >= 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (!((mb16 >> j) & 1u)) v[j] = 0.f;
+          }
+          if (P.kind == BK_FC0) {      // dx += masked product
+            uint32_t rx[16];
+            tmem_ld16(tX + 64u * (uint32_t)kb, rx);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(rx[j]);
+          }
+          if (P.kind == BK_FC0 || P.kind == BK_X0) {
+            uint32_t rx[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rx[j] = __float_as_uint(v[j]);
+            tmem_st16(tX + 64u * (uint32_t)kb, rx);
+            tmem_wait_st();
+          }
+          if (!valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+          }
+          claim_block(kb);
+          store_row16<F16, false, true>(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, v);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_A_READY(kb)));
+          if (P.g_blk >= 0) st_pend |= 1u << kb;
+        }
+        if (P.acc_b && P.nch <= 2 && !half_b_seen) wait_half_b();           // (keep the half-b barrier in step)
+        bd_pend |= (uint32_t)P.reads_mask;                   // the following group commits b_done for the blocks it reads
+      }
+    }
+    if (has_pose) {
+      const float inv = 1.f / gscale;
+#pragma unroll
+      for (int i = 0; i < 27; ++i) {
+        const float s = warp_sum(pacc[i]);
+        if (lane == 0) atomicAdd(&pose_acc[i], s * inv);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_EPI_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
 // ============================================================================================ dW / db
 // One CTA = (layer l, 128-row half of its outputs, sample-tile range).  Per tile: 2 gradient blocks (A operand,
 // MN-major: M = output features) and up to 4 activation blocks (B operand, MN-major: N = input features), K = 128
@@ -818,7 +1259,7 @@ size_t star_tc_gstash_bytes(const TcLayout& tl, int64_t n_samples) {
 int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                      const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, const float* d_raw_alpha,
                      const float* d_raw_rgb, int64_t ray_stride, const void* stash, void* gstash, float* grad_flat,
-                     float* pose_acc, int fp16, cudaStream_t st) {
+                     float* pose_acc, int fp16, int serial_dx, cudaStream_t st) {
   const int64_t M = (int64_t)R * S;
   const int64_t ntiles = (M + TC_M - 1) / TC_M;
   int dev = 0, sms = 148;
@@ -835,8 +1276,20 @@ int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed
     int rc = star_check_launch();
     if (rc) return rc;
   }
-  // ---- 1. dX chain
-  {
+  // ---- 1. dX chain: the pipelined kernel (N = 128 halves), or the serial one (A/B flag)
+  if (!serial_dx) {
+    const int grid = (int)(ntiles < sms ? ntiles : sms);
+    const Bwd2Smem sl = bwd2_smem_layout(tl.small_bytes);
+    auto kern = pose12 != nullptr ? (fp16 ? mlp_bwd2_tc_kernel<true, true> : mlp_bwd2_tc_kernel<false, true>)
+                                  : (fp16 ? mlp_bwd2_tc_kernel<true, false> : mlp_bwd2_tc_kernel<false, false>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
+    if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
+    kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
+                                              d_raw_alpha, d_raw_rgb, ray_stride, (const uint8_t*)stash, (uint8_t*)gstash,
+                                              pose_acc, absmax, nullptr);
+    int rc = star_check_launch();
+    if (rc) return rc;
+  } else {
     const int grid = (int)(ntiles < sms ? ntiles : sms);
     const BwdSmem sl = bwd_smem_layout(tl.small_bytes);
     auto kern = pose12 != nullptr ? (fp16 ? mlp_bwd_tc_kernel<true, true> : mlp_bwd_tc_kernel<false, true>)
