@@ -15,7 +15,7 @@ ABI_VERSION = 2
 PREC_F32, PREC_BF16, PREC_F16 = 0, 1, 2
 PREC_FLAG_CTA_PAIR = 0x100
 PREC_FLAG_STASH_DIRECT = 0x200
-PREC_FLAG_DX_SERIAL = 0x400
+PREC_FLAG_DX_PIPELINED = 0x400
 PRECISIONS = {"fp32": PREC_F32, "bf16": PREC_BF16, "fp16": PREC_F16}
 
 c_f = C.c_void_p      # device pointers are passed as raw addresses

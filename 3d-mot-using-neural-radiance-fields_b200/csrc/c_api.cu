@@ -161,7 +161,7 @@ extern "C" int star_mlp_backward(const StarNetDesc* d, const void* packed, const
     if (rc) return rc;
     return star_tc_backward(tl, lay, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, d_raw_alpha,
                             d_raw_rgb, alpha_ray_stride, stash, workspace, grad_flat, pose_acc,
-                            star_prec(d) == STAR_PREC_F16, (d->precision & STAR_PREC_FLAG_DX_SERIAL) != 0,
+                            star_prec(d) == STAR_PREC_F16, (d->precision & STAR_PREC_FLAG_DX_PIPELINED) == 0,
                             (cudaStream_t)stream);
   }
   return STAR_E_UNSUPPORTED;

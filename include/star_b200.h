@@ -55,9 +55,11 @@ enum { STAR_PREC_F32 = 0, STAR_PREC_BF16 = 1, STAR_PREC_F16 = 2 };
 /* training forward, A/B variant: the epilogue threads write the activation stash themselves (two 16-byte global stores per
  * thread and chunk) instead of one bulk copy per completed operand block issued by the producer warp. */
 #define STAR_PREC_FLAG_STASH_DIRECT 0x200
-/* backward, A/B variant: the serial dX chain of round 1 (every GEMM one N = 256 group, MMA and epilogue alternate) instead
- * of the pipelined one (N = 128 halves; the epilogue of a group overlaps the MMAs of the next). */
-#define STAR_PREC_FLAG_DX_SERIAL 0x400
+/* backward, A/B variant: the pipelined dX chain (every N = 256 GEMM as two N = 128 halves with their own completion barriers,
+ * so that the epilogue of a group overlaps the MMAs of the next) instead of the serial one.  Same gradients; measured SLOWER
+ * (dX + dW + heads 5.09 against 4.79 ms per 4096-ray step: twice as many stages and N = 128 MMAs make the single issuing thread
+ * the bottleneck), so it is opt-in. */
+#define STAR_PREC_FLAG_DX_PIPELINED 0x400
 
 /* One NeRF radiance MLP (models/nerf.py:34-110, models/resnet.py:62-110).  W is fixed at 256,
  * the view branch at 128 (all 15 reference configs agree). */

@@ -316,3 +316,25 @@ def test_cta_pair_kernels_are_bit_identical_to_the_single_cta_kernels(prec, monk
         for x, y in zip(res[False][4], res[True][4]):
             assert float((x - y).norm()) <= 1e-4 * float(x.norm()) + 1e-12
     F_.check_range()
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_pipelined_dx_chain_gives_the_gradients_of_the_serial_one(prec, monkeypatch):
+    """The opt-in pipelined dX kernel (N = 128 halves, per-block b_done / stash_done barriers) against the default serial one:
+    the same GEMMs in the same K order -> the same gradient stash, hence equal weight and pose gradients up to the dW atomics."""
+    net, _ = make_star(1, 8, 4096, False, seed=21, training=True, precision=prec)
+    for R, S, dyn in ((301, 191, False), (129, 5, True), (640, 64, True)):
+        module = net.dynamic_coarse_nerfs[0] if dyn else net.static_coarse_nerf
+        ro, rd = so.carla_rays(R, seed=7)
+        vd = rd / rd.norm(dim=-1, keepdim=True)
+        pts, _ = so.sample_pts(ro, rd, 0.03, 0.8, S)
+        res = {}
+        for piped in (False, True):
+            monkeypatch.setattr(F_, "TC_DX_PIPELINED", piped)
+            module.zero_grad()
+            pose = cu(so.pose7_to_matrix(so.random_poses7(1, seed=9))[0]).requires_grad_(dyn)
+            a, c = module.raw(cu(pts), cu(vd), F_.pose_to_mat12(pose) if dyn else None)
+            ((a ** 2).mean() + (c ** 2).mean()).backward()
+            res[piped] = [p.grad.clone() for p in module.parameters()] + ([pose.grad.clone()] if dyn else [])
+        for x, y in zip(res[False], res[True]):
+            assert float((x - y).norm()) <= 1e-4 * float(x.norm()) + 1e-12
