@@ -97,17 +97,19 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3], u
       add_f32x2(v[4 * j4 + 0], v[4 * j4 + 1], bq[j4].x, bq[j4].y);
       add_f32x2(v[4 * j4 + 2], v[4 * j4 + 3], bq[j4].z, bq[j4].w);
     }
-    if (KIND == LK_OUT) {            // alpha head (nerf.py:151) on the fp32 h
+    if (KIND == LK_VIEWS) {          // rgb head (nerf.py:159) on the rectified fp32 h2: 4 independent partial sums per channel
 #pragma unroll
-      for (int j = 0; j < TC_CPT; ++j) h[0] = fmaf(v[j], c.head_w[col0 + j], h[0]);
-    }
-    if (KIND == LK_VIEWS) {          // rgb head (nerf.py:159) on the rectified fp32 h2
+      for (int ch = 0; ch < 3; ++ch) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < TC_CPT; ++j) {
-        const float x = fmaxf(v[j], 0.f);
-        h[0] = fmaf(x, c.head_w[col0 + j], h[0]);
-        h[1] = fmaf(x, c.head_w[STAR_WV + col0 + j], h[1]);
-        h[2] = fmaf(x, c.head_w[2 * STAR_WV + col0 + j], h[2]);
+        for (int j4 = 0; j4 < TC_CPT / 4; ++j4) {
+          const float4 w = *reinterpret_cast<const float4*>(c.head_w + ch * STAR_WV + col0 + 4 * j4);
+          a[0] = fmaf(fmaxf(v[4 * j4 + 0], 0.f), w.x, a[0]);
+          a[1] = fmaf(fmaxf(v[4 * j4 + 1], 0.f), w.y, a[1]);
+          a[2] = fmaf(fmaxf(v[4 * j4 + 2], 0.f), w.z, a[2]);
+          a[3] = fmaf(fmaxf(v[4 * j4 + 3], 0.f), w.w, a[3]);
+        }
+        h[ch] += (a[0] + a[1]) + (a[2] + a[3]);
       }
       if (STASH) store_row16<FP16, true>(0u, c.row, c.cg * 2, v, c.stash_out + kb * TC_KB_BYTES);
     } else {
@@ -137,6 +139,18 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3], u
       if (c.lane == 0) {
         mbar_arrive(c.w_full0 + 8u * ((c.next_stage0 + (uint32_t)kb) & c.ns_mask));
         if (STASH && !c.direct) mbar_arrive(c.a_ready0 + 8u * (uint32_t)kb);
+      }
+      if (KIND == LK_OUT) {          // alpha head (nerf.py:151) on the fp32 h -- AFTER the block is published: off the
+        float a[4] = {0.f, 0.f, 0.f, 0.f};   // path the next layer's MMAs wait on; 4 independent partial sums
+#pragma unroll
+        for (int j4 = 0; j4 < TC_CPT / 4; ++j4) {
+          const float4 w = *reinterpret_cast<const float4*>(c.head_w + col0 + 4 * j4);
+          a[0] = fmaf(v[4 * j4 + 0], w.x, a[0]);
+          a[1] = fmaf(v[4 * j4 + 1], w.y, a[1]);
+          a[2] = fmaf(v[4 * j4 + 2], w.z, a[2]);
+          a[3] = fmaf(v[4 * j4 + 3], w.w, a[3]);
+        }
+        h[0] += (a[0] + a[1]) + (a[2] + a[3]);
       }
     }
   }
@@ -205,6 +219,9 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
   long long* tl = (dbg != nullptr && blockIdx.x == 0) ? reinterpret_cast<long long*>(dbg) : nullptr;
   const int64_t tl_tile = tile_of(unit0 + unit_step);
 #define TL_STAMP(cond, slot) do { if (tl != nullptr && (cond)) tl[slot] = clock64(); } while (0)
+#ifndef TL_LAYER
+#define TL_LAYER 2             // the layer whose K-blocks the issuer stamps one by one
+#endif
 #else
 #define TL_STAMP(cond, slot) do { } while (0)
 #endif
@@ -278,7 +295,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           for (int kb = 0; kb < lay.L[l].nkb; ++kb) {
             if (STASH && !stash_direct && l >= 2 && kb < 4) stash_chunk(l - 2, kb);
             mbar_wait(bar(BAR_W_EMPTY(stage)), phase ^ 1u, dbg, 1);
-            if (lay.L[l].kind == LK_VIEWS && kb == 4) mbar_arrive_n(bar(BAR_W_FULL(stage)), TC_EPI_WARPS);
+            if (lay.L[l].kind == LK_VIEWS && kb == 0) mbar_arrive_n(bar(BAR_W_FULL(stage)), TC_EPI_WARPS);   // dirs block: a_ready[4]
             if (dbg_mode & 2) {
               mbar_arrive(bar(BAR_W_FULL(stage)));
             } else {
@@ -309,19 +326,23 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           const uint32_t d_tmem = tmem_base + (lay.L[l].region ? 256u : 0u);
           const uint32_t idesc = umma_idesc_16(PAIR ? 2 * TC_M : TC_M, lay.L[l].N, FP16 ? 0 : 1);
           const uint64_t desc_al = desc_a0 + (uint64_t)((l & (NSETS - 1)) * 4 * (TC_KB_BYTES >> 4));   // this layer's A set
+          // the view layer multiplies the encoded-dirs block FIRST (K-block 0; it has been in shared memory since the start of
+          // the tile, so its MMAs follow feature_linear's without a hand-off and the 5th K-block's weight stage is one that
+          // was released long ago), then the 4 feature blocks
+          const int kb_a0 = (kind == LK_VIEWS) ? 1 : 0;
           // one K-block: wait for its operand blocks, issue 4 (2 for the dirs block) MMAs, release the weight stage
-          auto kblock = [&](const int kb, const bool dirs) {
+          auto kblock = [&](const int kb, const int kb_a, const bool dirs) {
             if (dirs) {
               mbar_wait(bar(BAR_A_READY(4)), a_par & 1u, dbg, 2);
               a_par ^= 1u;
             }
             TL_STAMP(tile == tl_tile && lane == 0 && kb == 0, 16 + 4 * l);
-            TL_STAMP(tile == tl_tile && lane == 0 && l == 2, 240 + 3 * kb);
+            TL_STAMP(tile == tl_tile && lane == 0 && l == TL_LAYER && kb < 5, 240 + 3 * kb);
             if (PAIR) mbar_wait_cluster(bar(BAR_W_FULL(stage)), phase, dbg, 3);   // (acquires the peer's relay arrival)
             else mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
             tc_fence_after();
-            TL_STAMP(tile == tl_tile && lane == 0 && l == 2, 241 + 3 * kb);
-            const uint64_t a0 = dirs ? desc_ad : desc_al + (uint64_t)(kb * (TC_KB_BYTES >> 4));
+            TL_STAMP(tile == tl_tile && lane == 0 && l == TL_LAYER && kb < 5, 241 + 3 * kb);
+            const uint64_t a0 = dirs ? desc_ad : desc_al + (uint64_t)(kb_a * (TC_KB_BYTES >> 4));
             const uint64_t b0 = desc_w0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
             const uint32_t acc0 = (kind == LK_FC1 || kb > 0) ? 1u : 0u;
             if (elect_one_sync()) {
@@ -344,13 +365,17 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             }
             __syncwarp();
             TL_STAMP(tile == tl_tile && lane == 0 && kb == nkb - 1, 17 + 4 * l);
-            TL_STAMP(tile == tl_tile && lane == 0 && l == 2, 242 + 3 * kb);
+            TL_STAMP(tile == tl_tile && lane == 0 && l == TL_LAYER && kb < 5, 242 + 3 * kb);
             if (++stage == NS) { stage = 0; phase ^= 1u; }
           };
           if (nkb == 4) {            // the common case, unrolled: K-block indices become immediates
-            kblock(0, false); kblock(1, false); kblock(2, false); kblock(3, false);
+            kblock(0, 0, false); kblock(1, 1, false); kblock(2, 2, false); kblock(3, 3, false);
+          } else if (nkb == 1) {     // lin_in
+            kblock(0, 0, false);
+          } else if (kind == LK_VIEWS && nkb == 5) {
+            kblock(0, 0, true); kblock(1, 0, false); kblock(2, 1, false); kblock(3, 2, false); kblock(4, 3, false);
           } else {
-            for (int kb = 0; kb < nkb; ++kb) kblock(kb, kind == LK_VIEWS && kb == 4);
+            for (int kb = 0; kb < nkb; ++kb) kblock(kb, kb - kb_a0, kind == LK_VIEWS && kb == 0);
           }
         }
       }
@@ -362,7 +387,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         for (int l = 0; l < lay.n_layers; ++l) {
           const int nkb = lay.L[l].nkb;
           for (int kb = 0; kb < nkb; ++kb) {
-            if (lay.L[l].kind == LK_VIEWS && kb == 4) {
+            if (lay.L[l].kind == LK_VIEWS && kb == 0) {
               mbar_wait(bar(BAR_A_READY(4)), a_par & 1u, dbg, 2);
               a_par ^= 1u;
             }
@@ -432,6 +457,15 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         uint8_t* st_tile = STASH ? stash + (size_t)tile * (size_t)lay.stash_blocks * TC_BLOCK_BYTES : nullptr;
         uint8_t* st_dirs = STASH ? st_tile + (size_t)(lay.L[lay.n_layers - 1].s_in + 4) * TC_BLOCK_BYTES : nullptr;
         store_row16<FP16, false>(sA, row, cg * 2, e, STASH ? st_tile + (size_t)lay.L[0].s_in * TC_BLOCK_BYTES : nullptr);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar(BAR_W_FULL(kstage & (NS - 1))));   // operand of (layer 0, K-block 0)
+          if (STASH && !stash_direct) mbar_arrive(bar(BAR_A_READY(0)));
+        }
+        TL_STAMP(tile == tl_tile && tid == 0, 9);
+        // the dirs block is only read by the view layer: encoded AFTER lin_in's operand is out, while its MMAs run
         if (cg == 1) { encode_slice<0, 27>(dv, sc_dir, e); store_row16<FP16, false>(sAD, row, 0, e, st_dirs); }
         if (cg == 2) { encode_slice<16, 27>(dv, sc_dir, e); store_row16<FP16, false>(sAD, row, 2, e, st_dirs); }
         if (STASH && (cg == 0 || cg == 3)) {   // zero the unused half of the dirs block once per tile
@@ -441,12 +475,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(bar(BAR_W_FULL(kstage & (NS - 1))));   // operand of (layer 0, K-block 0)
-          if (STASH && !stash_direct) mbar_arrive(bar(BAR_A_READY(0)));
-          mbar_arrive(bar(BAR_A_READY(4)));
-        }
-        TL_STAMP(tile == tl_tile && tid == 0, 9);
+        if (lane == 0) mbar_arrive(bar(BAR_A_READY(4)));
       }
       // ---- layers
       for (int l = 0; l < lay.n_layers; ++l) {
@@ -464,7 +493,8 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         float h[3] = {0.f, 0.f, 0.f};
         TL_STAMP(tile == tl_tile && tid == 0, 80 + 8 * l);
         kstage = (kstage + (uint32_t)L.nkb) & (NS - 1);     // now the stage of the NEXT layer's K-block 0
-        ctx.next_stage0 = kstage;
+        // (the view layer's K-block 0 is the dirs block: feature block kb goes with its K-block kb + 1)
+        ctx.next_stage0 = (kstage + ((l + 1 < lay.n_layers && lay.L[l + 1].kind == LK_VIEWS) ? 1u : 0u)) & (NS - 1);
         // this layer's output = the next layer's operand: A set (l + 1) mod NSETS; bulk-stored to the stash afterwards
         // unless it is the view layer's (whose relu(h2) goes to the stash directly)
         ctx.set = (l + 1) & (NSETS - 1);
@@ -585,9 +615,9 @@ __global__ void pack_tc_stream_kernel(TcLayout tl, MlpLayout ml, const float* __
     const int kk = chunk * 8 + (int)((inrow & 15u) >> 1);
     const int K = ml.L[l].K;                                     // true input width (63, 256, 283)
     float v = 0.f;
-    if (L.kind == LK_VIEWS) {
-      const int k = (kb < 4) ? kb * 64 + kk : STAR_W + kk;
-      if (kb < 4 || kk < K - STAR_W) v = master[ml.L[l].m_w + (int64_t)n * K + k];
+    if (L.kind == LK_VIEWS) {          // K-block 0 = the encoded dirs, 1..4 = the feature blocks
+      const int k = (kb >= 1) ? (kb - 1) * 64 + kk : STAR_W + kk;
+      if (kb >= 1 || kk < K - STAR_W) v = master[ml.L[l].m_w + (int64_t)n * K + k];
     } else {
       const int k = kb * 64 + kk;
       if (k < K) v = master[ml.L[l].m_w + (int64_t)n * K + k];
@@ -692,8 +722,8 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pt
                 h[80 + 8 * l] - z, h[81 + 8 * l] - z, h[82 + 8 * l] - z);
       fprintf(stderr, "[star_tc]  L1 epilogue done per warp:");
       for (int w = 0; w < 16; ++w) fprintf(stderr, " %lld", h[200 + w] - z);
-      fprintf(stderr, "\n[star_tc]  L2 issuer per K-block (a_ready seen, w_full seen, issued):");
-      for (int kb = 0; kb < 4; ++kb) fprintf(stderr, "  kb%d %lld %lld %lld", kb, h[240 + 3 * kb] - z, h[241 + 3 * kb] - z, h[242 + 3 * kb] - z);
+      fprintf(stderr, "\n[star_tc]  L%d issuer per K-block (a_ready seen, w_full seen, issued):", TL_LAYER);
+      for (int kb = 0; kb < tl.L[TL_LAYER].nkb; ++kb) fprintf(stderr, "  kb%d %lld %lld %lld", kb, h[240 + 3 * kb] - z, h[241 + 3 * kb] - z, h[242 + 3 * kb] - z);
       fprintf(stderr, "\n");
       cudaMemset(d_dbg, 0, 4096);
     }

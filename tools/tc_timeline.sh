@@ -7,7 +7,7 @@ cd "$(dirname "$0")/.."
 P=3d-mot-using-neural-radiance-fields_b200
 cp $P/libstar_b200.so /tmp/libstar_b200.prod.so
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr \
-     -DSTAR_TC_DEBUG -DSTAR_TC_TIMELINE -c $P/csrc/mlp_tc.cu -o /tmp/mlp_tc_tl.o
+     -DSTAR_TC_DEBUG -DSTAR_TC_TIMELINE ${TL_LAYER:+-DTL_LAYER=$TL_LAYER} -c $P/csrc/mlp_tc.cu -o /tmp/mlp_tc_tl.o
 OBJS=$(ls $P/build/*.o | grep -v mlp_tc.o)
 nvcc -shared -o $P/libstar_b200.so $OBJS /tmp/mlp_tc_tl.o -gencode arch=compute_100a,code=sm_100a -lcudart
 STAR_TC_DEBUG_CYCLES=1 R=${R:-8192} python tools/tc_microbench.py 2>&1 | grep star_tc | head -20
