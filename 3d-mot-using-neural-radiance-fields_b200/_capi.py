@@ -13,8 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libstar_b200.so")
 
 ABI_VERSION = 2
 PREC_F32, PREC_BF16, PREC_F16 = 0, 1, 2
-PREC_FLAG_CTA_PAIR = 0x100
-PREC_FLAG_STASH_DIRECT = 0x200
+PREC_FLAG_RETIRED = 0x300      # round-2 A/B variants of the forward kernels (CTA pair, direct stash stores): rejected
 PREC_FLAG_DX_PIPELINED = 0x400
 PRECISIONS = {"fp32": PREC_F32, "bf16": PREC_BF16, "fp16": PREC_F16}
 
@@ -70,6 +69,7 @@ _SIGS = {
     "star_abi_version": (C.c_int, []),
     "star_error_string": (C.c_char_p, [C.c_int]),
     "star_last_cuda_error": (C.c_int, []),
+    "star_watchdog_word": (C.c_int, [C.c_int]),
     "star_net_param_count": (C.c_size_t, [C.POINTER(StarNetDesc)]),
     "star_packed_bytes": (C.c_size_t, [C.POINTER(StarNetDesc)]),
     "star_pack_weights": (C.c_int, [C.POINTER(StarNetDesc), c_f, c_f, c_f]),
@@ -197,7 +197,34 @@ def check(code, what):
         extra = ""
         if code == 6:
             extra = " (cudaError %d)" % L.star_last_cuda_error()
+            wd = watchdog_report()
+            if wd:
+                extra += " [kernel watchdog: %s]" % wd
         raise StarError("%s failed: %s%s" % (what, msg, extra))
+
+
+WATCHDOG_FAMILIES = ("mlp forward", "dX chain", "dW", "pipelined dX", "mip forward", "mip dX")
+
+
+def watchdog_report():
+    """Text for the tensor-core kernels' barrier watchdogs that fired ('' if none): after a CUDA launch failure this says
+    which kernel family hung on which wait (include/star_b200.h, star_watchdog_word)."""
+    L = lib()
+    out = []
+    for i, name in enumerate(WATCHDOG_FAMILIES):
+        w = L.star_watchdog_word(i)
+        if w:
+            out.append("%s: wait code %d in CTA %d" % (name, w >> 16, w & 0xffff))
+        b, e = L.star_watchdog_word(16 + i), L.star_watchdog_word(32 + i)
+        if b != e:
+            out.append("%s: launch %d started and did not finish (%d finished)" % (name, b, e))
+    return "; ".join(out)
+
+
+def launch_markers():
+    """(started, finished) launch counts per tensor-core kernel family (diagnostics)."""
+    L = lib()
+    return {name: (L.star_watchdog_word(16 + i), L.star_watchdog_word(32 + i)) for i, name in enumerate(WATCHDOG_FAMILIES)}
 
 
 def ptr(t):

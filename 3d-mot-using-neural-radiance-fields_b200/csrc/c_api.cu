@@ -1,10 +1,12 @@
 // extern "C" entry points of libstar_b200.so that are not kernel-file local (see include/star_b200.h).
 #include "star_common.cuh"
 #include "mlp_layout.h"
+#include <stdlib.h>
 #include "mlp_tc_layout.h"
 #include "mip_layout.h"
 
 int g_star_last_cuda_error = 0;
+int g_star_sync_launches = []() { const char* e = getenv("STAR_B200_SYNC_LAUNCHES"); return (e && e[0] == '1') ? 1 : 0; }();
 
 static inline int star_prec(const StarNetDesc* d) { return d->precision & 0xff; }   // (upper bits: STAR_PREC_FLAG_*)
 
@@ -13,8 +15,7 @@ int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, v
                  cudaStream_t st);
 int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                     const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
-                    float* raw_rgb, int64_t ray_stride, void* stash, int* status, int fp16, int single_cta,
-                    int stash_direct, cudaStream_t st);
+                    float* raw_rgb, int64_t ray_stride, void* stash, int* status, int fp16, cudaStream_t st);
 
 size_t star_tc_gstash_bytes(const TcLayout& tl, int64_t n_samples);
 int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
@@ -33,6 +34,22 @@ int star_f32_backward(const MlpLayout& lay, const void* packed, const StarPtsSrc
 
 extern "C" int star_abi_version(void) { return STAR_ABI_VERSION; }
 extern "C" int star_last_cuda_error(void) { return g_star_last_cuda_error; }
+
+// Watchdog words of the tensor-core kernels: mapped host memory (readable after the context died), one int per kernel family
+// (STAR_WD_*).  A barrier wait that exceeds STAR_TC_WATCHDOG_CYCLES stores (wait code << 16 | CTA) there and traps.
+static int* g_wd_host = nullptr;
+static int* g_wd_dev = nullptr;
+int* star_watchdog_dev(int family) {
+  if (g_wd_host == nullptr) {
+    if (cudaHostAlloc((void**)&g_wd_host, 256, cudaHostAllocMapped) != cudaSuccess) { g_wd_host = nullptr; return nullptr; }
+    for (int i = 0; i < 64; ++i) g_wd_host[i] = 0;
+    if (cudaHostGetDevicePointer((void**)&g_wd_dev, g_wd_host, 0) != cudaSuccess) return nullptr;
+  }
+  return g_wd_dev ? g_wd_dev + family : nullptr;
+}
+extern "C" int star_watchdog_word(int family) {
+  return (g_wd_host != nullptr && family >= 0 && family < 64) ? ((volatile int*)g_wd_host)[family] : 0;
+}
 
 extern "C" const char* star_error_string(int code) {
   switch (code) {
@@ -122,13 +139,12 @@ extern "C" int star_mlp_forward(const StarNetDesc* d, const void* packed, const 
     return star_f32_forward(lay, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, raw_alpha,
                             raw_rgb, alpha_ray_stride, stash, (cudaStream_t)stream);
   if (star_prec(d) == STAR_PREC_BF16 || star_prec(d) == STAR_PREC_F16) {
+    if (d->precision & STAR_PREC_FLAG_RETIRED) return STAR_E_UNSUPPORTED;
     TcLayout tl;
     rc = star_make_tc_layout(d, &tl);
     if (rc) return rc;
     return star_tc_forward(tl, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, raw_alpha, raw_rgb,
-                           alpha_ray_stride, stash, status, star_prec(d) == STAR_PREC_F16,
-                           (d->precision & STAR_PREC_FLAG_CTA_PAIR) == 0,
-                           (d->precision & STAR_PREC_FLAG_STASH_DIRECT) != 0, (cudaStream_t)stream);
+                           alpha_ray_stride, stash, status, star_prec(d) == STAR_PREC_F16, (cudaStream_t)stream);
   }
   return STAR_E_UNSUPPORTED;
 }

@@ -533,6 +533,6 @@ int star_mip_tc_forward(const void* packed, const float* origins, const float* d
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
   if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
   kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, origins, dirs, pose12, bins, radius, S, M,
-                                            raw_sigma, raw_rgb, ray_stride, (uint8_t*)stash, nullptr);
+                                            raw_sigma, raw_rgb, ray_stride, (uint8_t*)stash, star_watchdog_dev(STAR_WD_MIP_FWD));
   return star_check_launch();
 }

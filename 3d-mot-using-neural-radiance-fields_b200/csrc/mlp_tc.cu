@@ -23,6 +23,7 @@
 #include "star_common.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <string.h>
 #include <stdio.h>
 #include "tc_common.cuh"
 #include "mlp_tc_layout.h"
@@ -42,10 +43,8 @@ struct EpiCtx {
   uint8_t* stash_out;          // global: first stash block of this layer's epilogue output for this tile, or NULL
   uint8_t* mask_out;           // global: this layer's ReLU bit masks for this tile (training), or NULL
   bool no_mask;                // debug (timing experiments only)
-  uint32_t stash_done0;        // smem address of barrier stash_done[0] of the A set this layer writes
-  int set;                     // A set this layer writes (0 unless the training pair kernel alternates two sets)
+  uint32_t stash_done0;        // smem address of barrier stash_done[0]
   bool publishes;              // training: this layer's output blocks are bulk-stored to the stash afterwards
-  bool direct;                 // training, A/B variant: the epilogue threads write the stash themselves (no bulk stores)
   bool no_stash_wait;          // debug (timing experiments only)
   uint32_t w_full0;            // smem address of barrier w_full[0]
   uint32_t next_stage0;        // ring stage of the NEXT layer's K-block 0 (its K-block kb uses (next_stage0 + kb) % NS)
@@ -58,7 +57,7 @@ struct EpiCtx {
 // conversion) -> swizzled smem -> proxy fence -> one mbarrier arrival per warp.
 // KIND: LK_IN / LK_FC0 / LK_FC1 (ReLU), LK_OUT (affine + alpha head partial in h[0]), LK_FEAT (affine),
 // LK_VIEWS (ReLU, N = 128, rgb head partials in h[0..2], no A output).
-// Stash bookkeeping (training): bit (4 * set + kb) of `pend` = a bulk store that READS A block (set, kb) has been issued
+// Stash bookkeeping (training): bit kb of `pend` = a bulk store that READS A block kb has been issued
 // by the producer warp since this thread last waited for that block (every block strictly alternates "written and
 // published" -> "stored" -> "waited for" -> "overwritten"; the layer program is static, so the flag needs no
 // communication); `par` holds the parity of the next wait per block.
@@ -116,7 +115,7 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3], u
       // (training: the stash copy of this block is a bulk store issued by the producer warp once the block is complete;
       //  the previous layer's copy of block kb must have left shared memory before it is overwritten)
       if (STASH) {
-        const uint32_t bit = 1u << (4 * c.set + kb);
+        const uint32_t bit = 1u << kb;
         if (stash_pend & bit) {
           if (!c.no_stash_wait) mbar_wait(c.stash_done0 + 8u * (uint32_t)kb, (stash_par & bit) ? 1u : 0u, nullptr, 7);
           stash_par ^= bit;
@@ -124,8 +123,7 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3], u
         }
         if (c.publishes) stash_pend |= bit;
       }
-      store_row16<FP16, RELU>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v,
-                              (STASH && c.direct) ? c.stash_out + kb * TC_KB_BYTES : nullptr);
+      store_row16<FP16, RELU>(c.sA + (uint32_t)kb * TC_KB_BYTES, c.row, c.cg * 2, v);
       if (STASH && RELU && !c.no_mask) {
         uint32_t b = 0u;
 #pragma unroll
@@ -138,7 +136,7 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3], u
       __syncwarp();
       if (c.lane == 0) {
         mbar_arrive(c.w_full0 + 8u * ((c.next_stage0 + (uint32_t)kb) & c.ns_mask));
-        if (STASH && !c.direct) mbar_arrive(c.a_ready0 + 8u * (uint32_t)kb);
+        if (STASH) mbar_arrive(c.a_ready0 + 8u * (uint32_t)kb);
       }
       if (KIND == LK_OUT) {          // alpha head (nerf.py:151) on the fp32 h -- AFTER the block is published: off the
         float a[4] = {0.f, 0.f, 0.f, 0.f};   // path the next layer's MMAs wait on; 4 independent partial sums
@@ -158,18 +156,78 @@ __device__ __forceinline__ void epilogue_layer(const EpiCtx& c, float (&h)[3], u
     *reinterpret_cast<uint2*>(c.mask_out + ((uint32_t)(c.cg * TC_M + c.row) << 3)) = make_uint2(mlo, mhi);
 }
 
+// ---------------------------------------------------------------------------------------------- input encoders
+// Deliberately NOT inlined: each runs once per tile, and inlined into the layer loop their sincosf slow paths and the
+// registers they need made the compiler re-materialise addresses in every epilogue chunk (35 -> 55 instructions per chunk,
+// measured: 2.84 -> 2.73 M rays/s).  As calls they cost a few register saves per tile.
+struct TcSample { float p[3]; float dv[3]; };
+// pose transform of sample gi and of its ray direction (star__.py:160-199); zeros beyond the launch
+__device__ __noinline__ TcSample tc_load_sample(StarPtsSrc pts, const float* __restrict__ viewdirs,
+                                                const float* __restrict__ pose12, int64_t gi, int64_t M, int S) {
+  TcSample o;
+  o.p[0] = o.p[1] = o.p[2] = 0.f;
+  o.dv[0] = o.dv[1] = o.dv[2] = 0.f;
+  if (gi < M) {
+    const int64_t r = gi / S;
+    float px, py, pz;
+    star_load_pt(pts, gi, r, px, py, pz);
+    const float dx = viewdirs[r * 3 + 0], dy = viewdirs[r * 3 + 1], dz = viewdirs[r * 3 + 2];
+    if (pose12 != nullptr) {   // p' = R p + t, d' = R d
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        o.p[i] = pose12[i * 3 + 0] * px + pose12[i * 3 + 1] * py + pose12[i * 3 + 2] * pz + pose12[9 + i];
+        o.dv[i] = pose12[i * 3 + 0] * dx + pose12[i * 3 + 1] * dy + pose12[i * 3 + 2] * dz;
+      }
+    } else {
+      o.p[0] = px; o.p[1] = py; o.p[2] = pz;
+      o.dv[0] = dx; o.dv[1] = dy; o.dv[2] = dz;
+    }
+  }
+  return o;
+}
+// 16 columns [16 cg, 16 cg + 16) of the encoded xyz of one row -> chunks 2 cg, 2 cg + 1 of the row in the SW128 block at
+// shared address `dst` (and the same chunks of the stash block `gblock`, training)
+template <bool FP16>
+__device__ __noinline__ void tc_encode_xyz(float px, float py, float pz, const float* __restrict__ sc_xyz, int cg, int row,
+                                           uint32_t dst, uint8_t* gblock) {
+  const float p[3] = {px, py, pz};
+  float e[16];
+  if (cg == 0) encode_slice<0, 63>(p, sc_xyz, e);
+  else if (cg == 1) encode_slice<16, 63>(p, sc_xyz, e);
+  else if (cg == 2) encode_slice<32, 63>(p, sc_xyz, e);
+  else encode_slice<48, 63>(p, sc_xyz, e);
+  store_row16<FP16, false>(dst, row, cg * 2, e, gblock);
+}
+// the encoded ray direction of one row (27 columns: column groups 1 and 2 write 16 each) into the dirs block
+template <bool FP16, bool STASH>
+__device__ __noinline__ void tc_encode_dirs(float dx, float dy, float dz, const float* __restrict__ sc_dir, int cg, int row,
+                                            uint32_t dst, uint8_t* gblock) {
+  const float dv[3] = {dx, dy, dz};
+  float e[16];
+  if (cg == 1) { encode_slice<0, 27>(dv, sc_dir, e); store_row16<FP16, false>(dst, row, 0, e, gblock); }
+  if (cg == 2) { encode_slice<16, 27>(dv, sc_dir, e); store_row16<FP16, false>(dst, row, 2, e, gblock); }
+  if (STASH && (cg == 0 || cg == 3)) {   // zero the unused half of the stashed dirs block once per tile
+    const float z[16] = {0.f};
+    store_row16<FP16, false>(0u, row, cg == 0 ? 4 : 6, z, gblock);
+  }
+}
+
 // ============================================================================================ forward
-// PAIR: two CTAs (a cluster of 2 = two SMs of one TPC) walk PAIRS of tiles in lock step.  The leader's warp 17 issues
-// cta_group::2 MMAs (M = 256: both tiles at once; each CTA stages only its HALF of every weight K-block), the peer's warp 17
-// relays "my operand block + my weight half are ready" to the leader's w_full barrier, and tcgen05.commit multicasts
-// stage-free / accumulator-complete to both CTAs.  Everything else (producer, 16 epilogue warps, TMEM plan) is per CTA.
-template <bool FP16, bool STASH, bool PAIR>
+// Ring slots of one tile, in order (producer, issuer and epilogue warps all walk the same sequence):
+//   [S]  the tile's lin_in OPERAND (encoded xyz, 16 KB) -- written by the epilogue warps, not the producer
+//   [lin_in K-block 0] [fc_0 K-blocks 0..3] ... [view layer K-blocks 0..4]   weights (bulk copies by the producer)
+// Giving lin_in's operand a ring slot of its own (instead of A block 0, which still holds feature_linear's output while the
+// view layer runs) lets the epilogue warps encode tile t + 1 while tile t's view-layer MMAs run, and lets lin_in's MMAs
+// of tile t + 1 run while the view layer's epilogue of tile t (rgb head, raw outputs) is busy: the accumulator regions have
+// one completion barrier each (X: lin_in / fc_1 / feature_linear, T: fc_0 / lin_out / view layer), so lin_in (t + 1) -> X
+// can complete before the view layer's accumulator T has been read.
+template <bool FP16, bool STASH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const StarPtsSrc pts,
                   const float* __restrict__ viewdirs, const float* __restrict__ pose12,
                   const float* __restrict__ sc_xyz, const float* __restrict__ sc_dir, int S, int64_t M,
                   float* __restrict__ raw_alpha, float* __restrict__ raw_rgb, int64_t ray_stride,
-                  uint8_t* __restrict__ stash, int* __restrict__ status, int* dbg, int dbg_mode_arg, int stash_direct) {
+                  uint8_t* __restrict__ stash, int* __restrict__ status, int* dbg, int dbg_mode_arg) {
   // status (nullable): word set to 1 when a raw output is not finite -- the range guard of the fp16-operand tier (an
   // activation beyond 65504 becomes +inf in the 16-bit operand and reaches the heads as inf / NaN) and, for any tier,
   // the sign of non-finite inputs or weights.
@@ -184,16 +242,15 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
   // A store, bit 1 = no weight streaming (MMA reads whatever is in the ring), bit 2 = MMA issuer skips the MMAs,
   // training variant: bit 3 = no stash bulk stores, bit 4 = no ReLU bit masks, bit 5 = no stash_done waits
   extern __shared__ uint8_t smem_raw[];
+  tc_mark_begin(dbg);
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw_addr);
-  constexpr int NS = tc_ns(PAIR, STASH);
-  constexpr uint32_t STAGE_BYTES = tc_stage_bytes(PAIR);
-  constexpr int NSETS = tc_a_sets(PAIR, STASH);
-  const TcSmem sl = tc_smem_layout(lay.small_bytes, PAIR, STASH);
+  constexpr int NS = TC_NS;
+  constexpr uint32_t STAGE_BYTES = TC_STAGE_BYTES;
+  const TcSmem sl = tc_smem_layout(lay.small_bytes);
   const uint32_t sA = base + sl.A, sAD = base + sl.AD, sW = base + sl.W, sBars = base + sl.bars;
   float* s_small = reinterpret_cast<float*>(gbase + sl.small);
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   // partial head sums of column group g (1..3) of a row: 4 floats in 16-byte chunk (3 + g) of the row of the
   // dirs block (logical columns 32..63, which the MMA never reads: only 2 of its 4 K-steps are issued)
   auto part = [&](int r, int g) -> float* {
@@ -204,20 +261,16 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (M + TC_M - 1) / TC_M;
-  // work units: tiles, or pairs of tiles (this CTA takes tile 2 u + rank; a tile beyond the last one has no valid row,
-  // and the stash is allocated for an even number of tiles)
-  const int64_t n_units = PAIR ? (ntiles + 1) / 2 : ntiles;
-  const int64_t unit0 = PAIR ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
-  const int64_t unit_step = PAIR ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
-  auto tile_of = [&](int64_t u) -> int64_t { return PAIR ? 2 * u + (int64_t)rank : u; };
+  const int64_t tile0 = (int64_t)blockIdx.x, tile_step = (int64_t)gridDim.x;
+  const uint32_t slots_per_tile = 1u + (uint32_t)lay.n_stages;
   const long long t_start = clock64();
 #ifdef STAR_TC_TIMELINE
   // -DSTAR_TC_TIMELINE (debug build only, see tools/tc_timeline.sh): CTA 0 records clock64() stamps of its second tile
-  // into dbg[8..]:  issuer, slot 16 + 4 l: {a_ready[0] seen, last K-block issued + committed}; slots 240 + 3 kb: layer 2
-  // per K-block {a_ready seen, w_full seen, issued};  epilogue warp 0, slot 80 + 8 l: {wait start, accumulator seen,
-  // layer done}; slots 200 + w: layer-1 epilogue done per warp; slots 8 / 9: encode start / done
+  // into dbg[8..]:  issuer, slot 16 + 4 l: {a_ready[0] seen, last K-block issued + committed}; slots 240 + 3 kb: layer
+  // TL_LAYER per K-block {a_ready seen, w_full seen, issued};  epilogue warp 0, slot 80 + 8 l: {wait start, accumulator
+  // seen, layer done}; slots 200 + w: layer-1 epilogue done per warp; slots 8 / 9: encode (xyz) start / done
   long long* tl = (dbg != nullptr && blockIdx.x == 0) ? reinterpret_cast<long long*>(dbg) : nullptr;
-  const int64_t tl_tile = tile_of(unit0 + unit_step);
+  const int64_t tl_tile = tile0 + tile_step;
 #define TL_STAMP(cond, slot) do { if (tl != nullptr && (cond)) tl[slot] = clock64(); } while (0)
 #ifndef TL_LAYER
 #define TL_LAYER 2             // the layer whose K-blocks the issuer stamps one by one
@@ -228,19 +281,16 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
 
   // ---- one-time setup
   if (warp == TC_EPI_WARPS && lane == 0) {
-    // w_full: the producer (+ its bytes), the 16 epilogue warps and, in the leader of a pair, the peer's relay
-    const uint32_t full_count = 1 + TC_EPI_WARPS + ((PAIR && rank == 0) ? 1 : 0);
-    for (int i = 0; i < NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), full_count); mbar_init(bar(BAR_W_EMPTY(i)), 1); }
+    // w_full: the producer (+ its bytes) and the 16 epilogue warps (operand block of the same K-block)
+    for (int i = 0; i < NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), 1 + TC_EPI_WARPS); mbar_init(bar(BAR_W_EMPTY(i)), 1); }
     for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A_READY(i)), TC_EPI_WARPS);
     mbar_init(bar(BAR_ACC_FULL), 1);
-    for (int i = 0; i < 8; ++i) mbar_init(bar(BAR_STASH_DONE_KB(i)), 1);
+    mbar_init(bar(BAR_ACC_FULL_T), 1);
+    mbar_init(bar(BAR_S_READY), TC_EPI_WARPS);
+    for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_STASH_DONE_KB(i)), 1);
     fence_mbar_init();
   }
-  if (PAIR) cluster_sync_all();     // both CTAs' barriers exist before anything arrives on them from the other side
-  if (warp == TC_EPI_WARPS + 1) {
-    if (PAIR) tmem_alloc2(base + sl.tmem_ptr, TC_TMEM_COLS);
-    else tmem_alloc(base + sl.tmem_ptr, TC_TMEM_COLS);
-  }
+  if (warp == TC_EPI_WARPS + 1) tmem_alloc(base + sl.tmem_ptr, TC_TMEM_COLS);
   for (int i = tid; i < lay.small_floats; i += TC_THREADS) s_small[i] = reinterpret_cast<const float*>(packed)[i];
   for (int i = tid; i < TC_KB_BYTES / 16; i += TC_THREADS)
     reinterpret_cast<uint4*>(gbase + sl.AD)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -261,141 +311,117 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     if (lane == 0) {
       const uint8_t* wstream = packed + lay.small_bytes;
       uint32_t stage = 0, phase = 0, s_par = 0;
-      for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
-        const int64_t tile = tile_of(unit);
+      for (int64_t tile = tile0; tile < ntiles; tile += tile_step) {
         uint8_t* st_tile = STASH ? stash + (size_t)tile * (size_t)lay.stash_blocks * TC_BLOCK_BYTES : nullptr;
         auto stash_chunk = [&](int ls, int kb) {
-          const int set = (ls + 1) & (NSETS - 1);       // the A set that holds layer ls's output
           mbar_wait(bar(BAR_A_READY(kb)), (s_par >> kb) & 1u, dbg, 6);
           s_par ^= 1u << kb;
           if (!(dbg_mode & 8)) {
-            bulk_s2g(st_tile + (size_t)(lay.L[ls].s_out + kb) * TC_BLOCK_BYTES,
-                     sA + (uint32_t)(4 * set + kb) * TC_KB_BYTES, TC_KB_BYTES);
+            bulk_s2g(st_tile + (size_t)(lay.L[ls].s_out + kb) * TC_BLOCK_BYTES, sA + (uint32_t)kb * TC_KB_BYTES, TC_KB_BYTES);
             bulk_commit_group();
           }
           // block kb - 1 may be overwritten once its own store has read it (groups complete in order): the epilogue that
-          // next writes this set waits per block, so only the last block's store can still be in flight by then
+          // next writes it waits per block, so only the last block's store can still be in flight by then
           if (kb >= 1) {
             bulk_wait_group_read1();
-            mbar_arrive(bar(BAR_STASH_DONE_KB(4 * set + kb - 1)));
+            mbar_arrive(bar(BAR_STASH_DONE_KB(kb - 1)));
           }
           if (kb == 3) {
             bulk_wait_group_read0();
-            mbar_arrive(bar(BAR_STASH_DONE_KB(4 * set + 3)));
+            mbar_arrive(bar(BAR_STASH_DONE_KB(3)));
           }
         };
-        if (STASH && !stash_direct) {   // a_ready[0] also carries the encoder's arrival at the start of a tile: consume that phase
-          mbar_wait(bar(BAR_A_READY(0)), s_par & 1u, dbg, 6);
-          s_par ^= 1u;
-        }
+        // slot S belongs to the epilogue warps (they wait for the same w_empty phase before they write it and announce it
+        // on lin_in's w_full); the producer only keeps the slot's own barriers in step with the ring
+        mbar_wait(bar(BAR_W_EMPTY(stage)), phase ^ 1u, dbg, 1);
+        mbar_arrive_n(bar(BAR_W_FULL(stage)), 1 + TC_EPI_WARPS);
+        if (++stage == NS) { stage = 0; phase ^= 1u; }
         for (int l = 0; l < lay.n_layers; ++l) {
-          // (pair: this CTA's half of the K-block = rows [rank N/2, (rank + 1) N/2) = a contiguous half of its image)
           const uint32_t kb_bytes = (uint32_t)lay.L[l].N * 128u;
-          const uint32_t bytes = PAIR ? kb_bytes / 2 : kb_bytes;
           for (int kb = 0; kb < lay.L[l].nkb; ++kb) {
-            if (STASH && !stash_direct && l >= 2 && kb < 4) stash_chunk(l - 2, kb);
+            if (STASH && l >= 2 && kb < 4) stash_chunk(l - 2, kb);
             mbar_wait(bar(BAR_W_EMPTY(stage)), phase ^ 1u, dbg, 1);
-            if (lay.L[l].kind == LK_VIEWS && kb == 0) mbar_arrive_n(bar(BAR_W_FULL(stage)), TC_EPI_WARPS);   // dirs block: a_ready[4]
+            // operands with barriers of their own (the 16 epilogue warps do not arrive on w_full for them): the dirs block
+            // (a_ready[4]) and lin_in's operand in slot S (s_ready) -- both are written far ahead of their K-block's turn,
+            // when this stage's previous phase may still be open
+            if ((lay.L[l].kind == LK_VIEWS && kb == 4) || l == 0) mbar_arrive_n(bar(BAR_W_FULL(stage)), TC_EPI_WARPS);
             if (dbg_mode & 2) {
               mbar_arrive(bar(BAR_W_FULL(stage)));
             } else {
-              mbar_arrive_expect_tx(bar(BAR_W_FULL(stage)), bytes);
-              bulk_g2s(sW + stage * STAGE_BYTES, wstream + lay.L[l].w_off + (uint32_t)kb * kb_bytes + rank * bytes, bytes,
+              mbar_arrive_expect_tx(bar(BAR_W_FULL(stage)), kb_bytes);
+              bulk_g2s(sW + stage * STAGE_BYTES, wstream + lay.L[l].w_off + (uint32_t)kb * kb_bytes, kb_bytes,
                        bar(BAR_W_FULL(stage)));
             }
             if (++stage == NS) { stage = 0; phase ^= 1u; }
           }
         }
-        if (STASH && !stash_direct)
+        if (STASH)
           for (int kb = 0; kb < 4; ++kb) stash_chunk(lay.n_layers - 2, kb);   // feature_linear's output blocks
       }
       if (STASH) bulk_wait_group0();
     }
   } else if (warp == TC_EPI_WARPS + 1) {
-    // ======================================================================== MMA issuer (pair: leader) / relay (pair: peer)
+    // ======================================================================== MMA issuer
     // warp-uniform control flow (all lanes wait on the barriers), one elected lane issues the tcgen05 instructions
-    if (!PAIR || rank == 0) {
-      uint32_t stage = 0, phase = 0, a_par = 0;
-      const bool no_mma = (dbg_mode & 4) != 0;
-      const uint64_t desc_a0 = umma_desc_sw128(sA), desc_ad = umma_desc_sw128(sAD), desc_w0 = umma_desc_sw128(sW);
-      for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
-        const int64_t tile = tile_of(unit);
-        (void)tile;
-        for (int l = 0; l < lay.n_layers; ++l) {
-          const int kind = lay.L[l].kind, nkb = lay.L[l].nkb;
-          const uint32_t d_tmem = tmem_base + (lay.L[l].region ? 256u : 0u);
-          const uint32_t idesc = umma_idesc_16(PAIR ? 2 * TC_M : TC_M, lay.L[l].N, FP16 ? 0 : 1);
-          const uint64_t desc_al = desc_a0 + (uint64_t)((l & (NSETS - 1)) * 4 * (TC_KB_BYTES >> 4));   // this layer's A set
-          // the view layer multiplies the encoded-dirs block FIRST (K-block 0; it has been in shared memory since the start of
-          // the tile, so its MMAs follow feature_linear's without a hand-off and the 5th K-block's weight stage is one that
-          // was released long ago), then the 4 feature blocks
-          const int kb_a0 = (kind == LK_VIEWS) ? 1 : 0;
-          // one K-block: wait for its operand blocks, issue 4 (2 for the dirs block) MMAs, release the weight stage
-          auto kblock = [&](const int kb, const int kb_a, const bool dirs) {
-            if (dirs) {
-              mbar_wait(bar(BAR_A_READY(4)), a_par & 1u, dbg, 2);
-              a_par ^= 1u;
-            }
-            TL_STAMP(tile == tl_tile && lane == 0 && kb == 0, 16 + 4 * l);
-            TL_STAMP(tile == tl_tile && lane == 0 && l == TL_LAYER && kb < 5, 240 + 3 * kb);
-            if (PAIR) mbar_wait_cluster(bar(BAR_W_FULL(stage)), phase, dbg, 3);   // (acquires the peer's relay arrival)
-            else mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
-            tc_fence_after();
-            TL_STAMP(tile == tl_tile && lane == 0 && l == TL_LAYER && kb < 5, 241 + 3 * kb);
-            const uint64_t a0 = dirs ? desc_ad : desc_al + (uint64_t)(kb_a * (TC_KB_BYTES >> 4));
-            const uint64_t b0 = desc_w0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
-            const uint32_t acc0 = (kind == LK_FC1 || kb > 0) ? 1u : 0u;
-            if (elect_one_sync()) {
-              if (!no_mma) {
-                if (PAIR) {
-                  if (dirs) tc_mma2_kblock<2>(d_tmem, a0, b0, idesc, acc0);
-                  else tc_mma2_kblock<4>(d_tmem, a0, b0, idesc, acc0);
-                } else {
-                  if (dirs) tc_mma_kblock<2>(d_tmem, a0, b0, idesc, acc0);
-                  else tc_mma_kblock<4>(d_tmem, a0, b0, idesc, acc0);
-                }
-              }
-              if (PAIR) {
-                tc_commit2(bar(BAR_W_EMPTY(stage)));
-                if (kb == nkb - 1) tc_commit2(bar(BAR_ACC_FULL));
-              } else {
-                tc_commit(bar(BAR_W_EMPTY(stage)));
-                if (kb == nkb - 1) tc_commit(bar(BAR_ACC_FULL));
-              }
-            }
-            __syncwarp();
-            TL_STAMP(tile == tl_tile && lane == 0 && kb == nkb - 1, 17 + 4 * l);
-            TL_STAMP(tile == tl_tile && lane == 0 && l == TL_LAYER && kb < 5, 242 + 3 * kb);
-            if (++stage == NS) { stage = 0; phase ^= 1u; }
-          };
-          if (nkb == 4) {            // the common case, unrolled: K-block indices become immediates
-            kblock(0, 0, false); kblock(1, 1, false); kblock(2, 2, false); kblock(3, 3, false);
-          } else if (nkb == 1) {     // lin_in
-            kblock(0, 0, false);
-          } else if (kind == LK_VIEWS && nkb == 5) {
-            kblock(0, 0, true); kblock(1, 0, false); kblock(2, 1, false); kblock(3, 2, false); kblock(4, 3, false);
-          } else {
-            for (int kb = 0; kb < nkb; ++kb) kblock(kb, kb - kb_a0, kind == LK_VIEWS && kb == 0);
+    uint32_t stage = 0, phase = 0, a_par = 0;
+    const bool no_mma = (dbg_mode & 4) != 0;
+    const uint64_t desc_a0 = umma_desc_sw128(sA), desc_ad = umma_desc_sw128(sAD), desc_w0 = umma_desc_sw128(sW);
+    for (int64_t tile = tile0; tile < ntiles; tile += tile_step) {
+      const uint32_t stage_s = stage;             // slot S: lin_in's operand
+      if (++stage == NS) { stage = 0; phase ^= 1u; }
+      for (int l = 0; l < lay.n_layers; ++l) {
+        const int kind = lay.L[l].kind, nkb = lay.L[l].nkb;
+        const uint32_t d_tmem = tmem_base + (lay.L[l].region ? 256u : 0u);
+        const uint32_t acc_bar = bar(lay.L[l].region ? BAR_ACC_FULL_T : BAR_ACC_FULL);
+        const uint32_t idesc = umma_idesc_16(TC_M, lay.L[l].N, FP16 ? 0 : 1);
+        // The view layer multiplies the encoded-dirs block LAST (K-block 4).  It must be the dirs block that wraps around the
+        // 4-stage ring onto the stage of the layer's K-block 0: its w_full arrivals all come from the producer thread, in
+        // order behind K-block 0's.  A feature block in that position would have the 16 epilogue warps arrive on the barrier
+        // while K-block 0's phase can still be open (the producer lags behind when stash stores back up) -- a count
+        // underflow that the hardware answers with a launch failure (seen with the dirs block first, profiles/r2h_*).
+        // one K-block: wait for its operand block + weights, issue 4 (2 for the dirs block) MMAs, release the weight stage
+        // (SRC: 0 = A block kb_a, 1 = the dirs block, 2 = slot S)
+        auto kblock = [&](const int kb, const int kb_a, const int src) {
+          if (src == 1) {
+            mbar_wait(bar(BAR_A_READY(4)), a_par & 1u, dbg, 2);
+            a_par ^= 1u;
           }
-        }
-      }
-    } else {
-      // peer of a pair: the same walk over (tile pair, layer, K-block); once THIS CTA's operand block and weight half of a
-      // K-block are in shared memory (its own w_full: producer bytes + 16 epilogue warps), tell the leader's w_full
-      uint32_t stage = 0, phase = 0, a_par = 0;
-      for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
-        for (int l = 0; l < lay.n_layers; ++l) {
-          const int nkb = lay.L[l].nkb;
-          for (int kb = 0; kb < nkb; ++kb) {
-            if (lay.L[l].kind == LK_VIEWS && kb == 0) {
-              mbar_wait(bar(BAR_A_READY(4)), a_par & 1u, dbg, 2);
-              a_par ^= 1u;
-            }
-            mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 8);
-            if (lane == 0) mbar_arrive_remote(bar(BAR_W_FULL(stage)), 0u);
-            __syncwarp();
-            if (++stage == NS) { stage = 0; phase ^= 1u; }
+          if (src == 2) {
+            mbar_wait(bar(BAR_S_READY), (a_par >> 1) & 1u, dbg, 2);
+            a_par ^= 2u;
           }
+          TL_STAMP(tile == tl_tile && lane == 0 && kb == 0, 16 + 4 * l);
+          TL_STAMP(tile == tl_tile && lane == 0 && l == TL_LAYER && kb < 5, 240 + 3 * kb);
+          mbar_wait(bar(BAR_W_FULL(stage)), phase, dbg, 3);
+          tc_fence_after();
+          TL_STAMP(tile == tl_tile && lane == 0 && l == TL_LAYER && kb < 5, 241 + 3 * kb);
+          const uint64_t a0 = src == 1 ? desc_ad
+                            : src == 2 ? desc_w0 + (uint64_t)(stage_s * (STAGE_BYTES >> 4))
+                                       : desc_a0 + (uint64_t)(kb_a * (TC_KB_BYTES >> 4));
+          const uint64_t b0 = desc_w0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
+          const uint32_t acc0 = (kind == LK_FC1 || kb > 0) ? 1u : 0u;
+          if (elect_one_sync()) {
+            if (!no_mma) {
+              if (src == 1) tc_mma_kblock<2>(d_tmem, a0, b0, idesc, acc0);
+              else tc_mma_kblock<4>(d_tmem, a0, b0, idesc, acc0);
+            }
+            if (src == 2) tc_commit(bar(BAR_W_EMPTY(stage_s)));
+            tc_commit(bar(BAR_W_EMPTY(stage)));
+            if (kb == nkb - 1) tc_commit(acc_bar);
+          }
+          __syncwarp();
+          TL_STAMP(tile == tl_tile && lane == 0 && kb == nkb - 1, 17 + 4 * l);
+          TL_STAMP(tile == tl_tile && lane == 0 && l == TL_LAYER && kb < 5, 242 + 3 * kb);
+          if (++stage == NS) { stage = 0; phase ^= 1u; }
+        };
+        if (nkb == 4) {            // the common case, unrolled: K-block indices become immediates
+          kblock(0, 0, 0); kblock(1, 1, 0); kblock(2, 2, 0); kblock(3, 3, 0);
+        } else if (nkb == 1) {     // lin_in
+          kblock(0, 0, 2);
+        } else if (kind == LK_VIEWS && nkb == 5) {
+          kblock(0, 0, 0); kblock(1, 1, 0); kblock(2, 2, 0); kblock(3, 3, 0); kblock(4, 0, 1);
+        } else {
+          for (int kb = 0; kb < nkb; ++kb) kblock(kb, kb, (kind == LK_VIEWS && kb == 4) ? 1 : 0);
         }
       }
     }
@@ -405,7 +431,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     const int row = q * 32 + lane;
     uint32_t acc_par = 0, stash_par = 0, stash_pend = 0;
     bool nonfinite = false;
-    uint32_t kstage = 0;          // ring stage of the current layer's K-block 0 (same sequence as producer / issuer)
+    uint32_t kslot = 0;           // ring slot S of the current tile (same sequence as producer / issuer)
     EpiCtx ctx;
     ctx.sA = sA; ctx.a_ready0 = bar(BAR_A_READY(0)); ctx.w_full0 = bar(BAR_W_FULL(0));
     ctx.row = row; ctx.cg = cg; ctx.lane = lane;
@@ -413,70 +439,39 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     ctx.mask_out = nullptr;
     ctx.no_mask = (dbg_mode & 16) != 0;
     ctx.stash_done0 = bar(BAR_STASH_DONE_KB(0));
-    ctx.set = 0;
     ctx.publishes = false;
-    ctx.direct = stash_direct != 0;
     ctx.ns_mask = NS - 1;
     ctx.no_stash_wait = (dbg_mode & 32) != 0;
-    for (int64_t unit = unit0; unit < n_units; unit += unit_step) {
-      const int64_t tile = tile_of(unit);
+    // encoded xyz of tile `tile_n` (4 threads per row) -> ring slot `slot` (= that tile's slot S), announced on s_ready (NOT on
+    // the w_full barrier of lin_in's weights: this runs a whole layer before that stage's turn, while the barrier's phase of
+    // the stage's previous K-block can still be open); dv = the rotated ray direction of this thread's row
+    auto encode_xyz = [&](int64_t tile_n, uint32_t slot, float (&dv)[3]) {
+      TL_STAMP(tile_n == tl_tile && tid == 0, 8);
+      const TcSample sm = tc_load_sample(pts, viewdirs, pose12, tile_n * TC_M + row, M, S);
+      dv[0] = sm.dv[0]; dv[1] = sm.dv[1]; dv[2] = sm.dv[2];
+      const uint32_t st = slot & (NS - 1);
+      mbar_wait(bar(BAR_W_EMPTY(st)), ((slot / NS) & 1u) ^ 1u, dbg, 8);     // the MMAs that last read this stage are done
+      uint8_t* st_tile = STASH ? stash + (size_t)tile_n * (size_t)lay.stash_blocks * TC_BLOCK_BYTES : nullptr;
+      tc_encode_xyz<FP16>(sm.p[0], sm.p[1], sm.p[2], sc_xyz, cg, row, sW + st * STAGE_BYTES,
+                          STASH ? st_tile + (size_t)lay.L[0].s_in * TC_BLOCK_BYTES : nullptr);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(BAR_S_READY));
+      TL_STAMP(tile_n == tl_tile && tid == 0, 9);
+    };
+    float dv_next[3];
+    if (tile0 < ntiles) encode_xyz(tile0, 0u, dv_next);
+    for (int64_t tile = tile0; tile < ntiles; tile += tile_step) {
       const int64_t gi = tile * TC_M + row;
       const bool valid = gi < M;
       int64_t out_idx = 0;
-      if (STASH && (stash_pend & 1u)) {   // block 0 of set 0 (the encoder's) still feeds a stash store of the previous tile
-        if (!ctx.no_stash_wait) mbar_wait(bar(BAR_STASH_DONE_KB(0)), stash_par & 1u, dbg, 7);
-        stash_par ^= 1u;
-        stash_pend &= ~1u;
+      if (valid) {
+        const int64_t r = gi / S;
+        out_idx = r * ray_stride + (gi - r * S);
       }
-      TL_STAMP(tile == tl_tile && tid == 0, 8);
-      // ---- inputs: pose transform + encoding -> A K-block 0 (xyz, 4 threads per row) and the dirs block
-      {
-        float p[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 0.f};
-        if (valid) {
-          const int64_t r = gi / S;
-          out_idx = r * ray_stride + (gi - r * S);
-          float px, py, pz;
-          star_load_pt(pts, gi, r, px, py, pz);
-          const float dx = viewdirs[r * 3 + 0], dy = viewdirs[r * 3 + 1], dz = viewdirs[r * 3 + 2];
-          if (pose12 != nullptr) {   // p' = R p + t, d' = R d
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              p[i] = pose12[i * 3 + 0] * px + pose12[i * 3 + 1] * py + pose12[i * 3 + 2] * pz + pose12[9 + i];
-              dv[i] = pose12[i * 3 + 0] * dx + pose12[i * 3 + 1] * dy + pose12[i * 3 + 2] * dz;
-            }
-          } else {
-            p[0] = px; p[1] = py; p[2] = pz;
-            dv[0] = dx; dv[1] = dy; dv[2] = dz;
-          }
-        }
-        float e[16];
-        if (cg == 0) encode_slice<0, 63>(p, sc_xyz, e);
-        else if (cg == 1) encode_slice<16, 63>(p, sc_xyz, e);
-        else if (cg == 2) encode_slice<32, 63>(p, sc_xyz, e);
-        else encode_slice<48, 63>(p, sc_xyz, e);
-        uint8_t* st_tile = STASH ? stash + (size_t)tile * (size_t)lay.stash_blocks * TC_BLOCK_BYTES : nullptr;
-        uint8_t* st_dirs = STASH ? st_tile + (size_t)(lay.L[lay.n_layers - 1].s_in + 4) * TC_BLOCK_BYTES : nullptr;
-        store_row16<FP16, false>(sA, row, cg * 2, e, STASH ? st_tile + (size_t)lay.L[0].s_in * TC_BLOCK_BYTES : nullptr);
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(bar(BAR_W_FULL(kstage & (NS - 1))));   // operand of (layer 0, K-block 0)
-          if (STASH && !stash_direct) mbar_arrive(bar(BAR_A_READY(0)));
-        }
-        TL_STAMP(tile == tl_tile && tid == 0, 9);
-        // the dirs block is only read by the view layer: encoded AFTER lin_in's operand is out, while its MMAs run
-        if (cg == 1) { encode_slice<0, 27>(dv, sc_dir, e); store_row16<FP16, false>(sAD, row, 0, e, st_dirs); }
-        if (cg == 2) { encode_slice<16, 27>(dv, sc_dir, e); store_row16<FP16, false>(sAD, row, 2, e, st_dirs); }
-        if (STASH && (cg == 0 || cg == 3)) {   // zero the unused half of the dirs block once per tile
-          const float z[16] = {0.f};
-          store_row16<FP16, false>(0u, row, cg == 0 ? 4 : 6, z, st_dirs);
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(BAR_A_READY(4)));
-      }
+      float dv[3] = {dv_next[0], dv_next[1], dv_next[2]};
+      uint32_t kstage = (kslot + 1u) & (NS - 1);     // stage of the current layer's K-block 0
       // ---- layers
       for (int l = 0; l < lay.n_layers; ++l) {
         const TcLayer& L = lay.L[l];
@@ -491,26 +486,22 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
                          (size_t)l * TC_MASK_BYTES;
         }
         float h[3] = {0.f, 0.f, 0.f};
-        TL_STAMP(tile == tl_tile && tid == 0, 80 + 8 * l);
         kstage = (kstage + (uint32_t)L.nkb) & (NS - 1);     // now the stage of the NEXT layer's K-block 0
-        // (the view layer's K-block 0 is the dirs block: feature block kb goes with its K-block kb + 1)
-        ctx.next_stage0 = (kstage + ((l + 1 < lay.n_layers && lay.L[l + 1].kind == LK_VIEWS) ? 1u : 0u)) & (NS - 1);
-        // this layer's output = the next layer's operand: A set (l + 1) mod NSETS; bulk-stored to the stash afterwards
-        // unless it is the view layer's (whose relu(h2) goes to the stash directly)
-        ctx.set = (l + 1) & (NSETS - 1);
-        ctx.sA = sA + (uint32_t)ctx.set * 4u * TC_KB_BYTES;
-        ctx.stash_done0 = bar(BAR_STASH_DONE_KB(4 * ctx.set));
-        ctx.publishes = STASH && !stash_direct && l + 1 < lay.n_layers;
-        mbar_wait(bar(BAR_ACC_FULL), acc_par, dbg, 4);
-        acc_par ^= 1u;
+        ctx.next_stage0 = kstage;
+        ctx.publishes = STASH && l + 1 < lay.n_layers;
+        if (kind == LK_VIEWS && tile + tile_step < ntiles)   // while the view layer's MMAs run: the next tile's lin_in operand
+          encode_xyz(tile + tile_step, kslot + slots_per_tile, dv_next);
+        TL_STAMP(tile == tl_tile && tid == 0, 80 + 8 * l);
+        mbar_wait(bar(L.region ? BAR_ACC_FULL_T : BAR_ACC_FULL), (acc_par >> L.region) & 1u, dbg, 4);
+        acc_par ^= 1u << L.region;
         tc_fence_after();
         TL_STAMP(tile == tl_tile && tid == 0, 81 + 8 * l);
         if (dbg_mode & 1) {
           for (int kb = 0; kb < (L.N >> 6) && kind != LK_VIEWS; ++kb) {
             fence_proxy_async_smem(); tc_fence_before(); __syncwarp();
             if (lane == 0) {
-              mbar_arrive(bar(BAR_W_FULL((kstage + (uint32_t)kb) & (NS - 1))));
-              if (STASH && !stash_direct) mbar_arrive(bar(BAR_A_READY(kb)));
+              mbar_arrive(bar(BAR_W_FULL((ctx.next_stage0 + (uint32_t)kb) & (NS - 1))));
+              if (STASH) mbar_arrive(bar(BAR_A_READY(kb)));
             }
           }
         } else if (kind == LK_FC0 || kind == LK_FC1 || kind == LK_IN) {
@@ -550,22 +541,37 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         }
         TL_STAMP(tile == tl_tile && tid == 0, 82 + 8 * l);
         TL_STAMP(tile == tl_tile && lane == 0 && l == 1, 200 + warp);
+        if (l == 0) {
+          // the dirs block is only read by the view layer (and the previous tile's view layer is complete: its accumulator
+          // was read before lin_in's): encoded after lin_in's epilogue, while fc_0's MMAs run
+          uint8_t* st_tile = STASH ? stash + (size_t)tile * (size_t)lay.stash_blocks * TC_BLOCK_BYTES : nullptr;
+          uint8_t* st_dirs = STASH ? st_tile + (size_t)(lay.L[lay.n_layers - 1].s_in + 4) * TC_BLOCK_BYTES : nullptr;
+          tc_encode_dirs<FP16, STASH>(dv[0], dv[1], dv[2], sc_dir, cg, row, sAD, st_dirs);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_A_READY(4)));
+        }
       }
+      kslot += slots_per_tile;
     }
     if (status != nullptr && nonfinite) *reinterpret_cast<volatile int*>(status) = 1;
   }
 
-  // ---- teardown (pair: neither CTA may leave while the other's MMAs / commits can still touch its shared memory)
+  // ---- teardown
   tc_fence_before();
-  if (PAIR) cluster_sync_all();
-  else __syncthreads();
+  __syncthreads();
+  tc_mark_end(dbg);
+#ifdef STAR_TC_DEBUG
   if (dbg != nullptr && tid == 0 && blockIdx.x == 0) {   // debug only: cycles of CTA 0 (see star_tc_forward)
     reinterpret_cast<long long*>(dbg)[1] = clock64() - t_start;
   }
+#else
+  (void)t_start;
+#endif
   if (warp == TC_EPI_WARPS + 1) {
     tc_fence_after();
-    if (PAIR) tmem_dealloc2(tmem_base, TC_TMEM_COLS);
-    else tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
   }
 }
 
@@ -615,9 +621,9 @@ __global__ void pack_tc_stream_kernel(TcLayout tl, MlpLayout ml, const float* __
     const int kk = chunk * 8 + (int)((inrow & 15u) >> 1);
     const int K = ml.L[l].K;                                     // true input width (63, 256, 283)
     float v = 0.f;
-    if (L.kind == LK_VIEWS) {          // K-block 0 = the encoded dirs, 1..4 = the feature blocks
-      const int k = (kb >= 1) ? (kb - 1) * 64 + kk : STAR_W + kk;
-      if (kb >= 1 || kk < K - STAR_W) v = master[ml.L[l].m_w + (int64_t)n * K + k];
+    if (L.kind == LK_VIEWS) {          // K-blocks 0..3 = the feature blocks, 4 = the encoded dirs
+      const int k = (kb < 4) ? kb * 64 + kk : STAR_W + kk;
+      if (kb < 4 || kk < K - STAR_W) v = master[ml.L[l].m_w + (int64_t)n * K + k];
     } else {
       const int k = kb * 64 + kk;
       if (k < K) v = master[ml.L[l].m_w + (int64_t)n * K + k];
@@ -647,52 +653,29 @@ int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, v
 
 int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                     const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
-                    float* raw_rgb, int64_t ray_stride, void* stash, int* status, int fp16, int single_cta,
-                    int stash_direct, cudaStream_t st) {
+                    float* raw_rgb, int64_t ray_stride, void* stash, int* status, int fp16, cudaStream_t st) {
   const int64_t M = (int64_t)R * S;
   const int64_t ntiles = (M + TC_M - 1) / TC_M;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (((uintptr_t)packed & 15) != 0) return STAR_E_ALIGN;
-  const bool pair = !single_cta;
   const bool with_stash = stash != nullptr;
-  const TcSmem sl = tc_smem_layout(tl.small_bytes, pair, with_stash);
-  // grid: one CTA per SM over the tiles, or one CTA pair per two SMs over pairs of tiles
-  const int64_t units = pair ? (ntiles + 1) / 2 : ntiles;
-  const int max_units = pair ? sms / 2 : sms;
-  const int grid = (int)(units < max_units ? units : max_units) * (pair ? 2 : 1);
+  const TcSmem sl = tc_smem_layout(tl.small_bytes);
+  const int grid = (int)(ntiles < sms ? ntiles : sms);       // persistent: one CTA per SM over the tiles
   using Kern = void (*)(const TcLayout, const uint8_t*, const StarPtsSrc, const float*, const float*, const float*,
-                        const float*, int, int64_t, float*, float*, int64_t, uint8_t*, int*, int*, int, int);
-  Kern kern;
-  if (pair)
-    kern = with_stash ? (fp16 ? mlp_fwd_tc_kernel<true, true, true> : mlp_fwd_tc_kernel<false, true, true>)
-                      : (fp16 ? mlp_fwd_tc_kernel<true, false, true> : mlp_fwd_tc_kernel<false, false, true>);
-  else
-    kern = with_stash ? (fp16 ? mlp_fwd_tc_kernel<true, true, false> : mlp_fwd_tc_kernel<false, true, false>)
-                      : (fp16 ? mlp_fwd_tc_kernel<true, false, false> : mlp_fwd_tc_kernel<false, false, false>);
+                        const float*, int, int64_t, float*, float*, int64_t, uint8_t*, int*, int*, int);
+  Kern kern = with_stash ? (fp16 ? mlp_fwd_tc_kernel<true, true> : mlp_fwd_tc_kernel<false, true>)
+                         : (fp16 ? mlp_fwd_tc_kernel<true, false> : mlp_fwd_tc_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
   if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = sl.total;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = pair ? 2 : 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   auto launch = [&](int* dbg, int dbg_mode) -> int {
-    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
-                                        raw_alpha, raw_rgb, ray_stride, (uint8_t*)stash, status, dbg, dbg_mode, stash_direct);
-    if (le != cudaSuccess) { g_star_last_cuda_error = (int)le; return STAR_E_CUDA; }
+    kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
+                                             raw_alpha, raw_rgb, ray_stride, (uint8_t*)stash, status, dbg, dbg_mode);
     return STAR_OK;
   };
 #ifndef STAR_TC_DEBUG
-  { const int lrc = launch(nullptr, 0); if (lrc) return lrc; }
+  { const int lrc = launch(star_watchdog_dev(STAR_WD_FWD), 0); if (lrc) return lrc; }
 #else
   // -DSTAR_TC_DEBUG builds only (tools/tc_debug_modes.sh, tools/tc_timeline.sh): STAR_TC_DEBUG_MODE switches parts of the
   // kernel off (results are garbage), STAR_TC_DEBUG_CYCLES=1 makes the launch synchronous and prints CTA 0's cycles
@@ -710,7 +693,7 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pt
     static long long h[512];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, d_dbg, 4096, cudaMemcpyDeviceToHost);
-    const double t0 = (double)((units * (pair ? 2 : 1) + grid - 1) / grid);
+    const double t0 = (double)((ntiles + grid - 1) / grid);
     fprintf(stderr, "[star_tc] mode %d: CTA0 %.0f cycles/tile\n", dbg_mode, h[1] / t0);
 #ifdef STAR_TC_TIMELINE
     if (ntiles > 2 * (int64_t)grid && h[8] != 0) {

@@ -151,6 +151,7 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
                   const uint8_t* __restrict__ stash, uint8_t* __restrict__ gstash, float* __restrict__ pose_acc,
                   const float* __restrict__ absmax, int* dbg) {
   extern __shared__ uint8_t smem_raw[];
+  tc_mark_begin(dbg);
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw_addr);
@@ -494,6 +495,7 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
 
   tc_fence_before();
   __syncthreads();
+  tc_mark_end(dbg);
   if (warp == TC_EPI_WARPS + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TC_TMEM_COLS);
@@ -979,6 +981,7 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
              const uint8_t* __restrict__ gstash, int64_t ntiles, float* __restrict__ grad_flat,
              const float* __restrict__ absmax, int* dbg) {
   extern __shared__ uint8_t smem_raw[];
+  tc_mark_begin(dbg);
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw_addr);
@@ -1092,6 +1095,7 @@ dw_tc_kernel(const DwPlan plan, int stash_blocks, int gstash_blocks, const uint8
   }
   tc_fence_before();
   __syncthreads();
+  tc_mark_end(dbg);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -1286,7 +1290,7 @@ int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed
     if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
     kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
                                               d_raw_alpha, d_raw_rgb, ray_stride, (const uint8_t*)stash, (uint8_t*)gstash,
-                                              pose_acc, absmax, nullptr);
+                                              pose_acc, absmax, star_watchdog_dev(STAR_WD_DX2));
     int rc = star_check_launch();
     if (rc) return rc;
   } else {
@@ -1298,7 +1302,7 @@ int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed
     if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
     kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
                                               d_raw_alpha, d_raw_rgb, ray_stride, (const uint8_t*)stash, (uint8_t*)gstash,
-                                              pose_acc, absmax, nullptr);
+                                              pose_acc, absmax, star_watchdog_dev(STAR_WD_DX));
     int rc = star_check_launch();
     if (rc) return rc;
   }
@@ -1336,7 +1340,7 @@ int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
     kern<<<n * splits, DW_THREADS, smem, st>>>(plan, tl.stash_blocks, tl.gstash_blocks, (const uint8_t*)stash,
-                                               (const uint8_t*)gstash, ntiles, grad_flat, absmax, nullptr);
+                                               (const uint8_t*)gstash, ntiles, grad_flat, absmax, star_watchdog_dev(STAR_WD_DW));
     int rc = star_check_launch();
     if (rc) return rc;
   }
@@ -1652,7 +1656,7 @@ int star_mip_tc_backward(const void* packed, int R, int S, const float* d_raw_si
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
     if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
     kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, S, M, d_raw_sigma, d_raw_rgb, ray_stride,
-                                              (const uint8_t*)stash, (uint8_t*)gstash, absmax, nullptr);
+                                              (const uint8_t*)stash, (uint8_t*)gstash, absmax, star_watchdog_dev(STAR_WD_MIP_DX));
     int rc = star_check_launch();
     if (rc) return rc;
   }
@@ -1688,7 +1692,7 @@ int star_mip_tc_backward(const void* packed, int R, int S, const float* d_raw_si
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
     kern<<<n * splits, DW_THREADS, smem, st>>>(plan, MIP_STASH_BLOCKS, MIP_GSTASH_BLOCKS, (const uint8_t*)stash,
-                                               (const uint8_t*)gstash, ntiles, grad_flat, absmax, nullptr);
+                                               (const uint8_t*)gstash, ntiles, grad_flat, absmax, star_watchdog_dev(STAR_WD_DW));
     int rc = star_check_launch();
     if (rc) return rc;
   }

@@ -19,19 +19,13 @@ struct TcSmem {
   uint32_t A, AD, W, small, part, bars, tmem_ptr;   // byte offsets from the 1024-aligned base
   uint32_t total;
 };
-// CTA-pair variants (cta_group::2): a weight stage holds this CTA's HALF of a K-block (16 KB), which frees 64 KB: the
-// inference kernel spends them on a ring of 8 stages, the training kernel on a SECOND set of 4 A blocks, so that the bulk
-// stores of one layer's operand blocks to the stash overlap the next epilogue, which writes the other set.
-#define TC_MAX_NS 8
-__host__ __device__ constexpr int tc_ns(bool pair, bool stash) { return pair ? (stash ? 4 : 8) : TC_NS; }
-__host__ __device__ constexpr uint32_t tc_stage_bytes(bool pair) { return pair ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES; }
-__host__ __device__ constexpr int tc_a_sets(bool pair, bool stash) { return (pair && stash) ? 2 : 1; }
-__host__ __device__ static inline TcSmem tc_smem_layout(uint32_t small_bytes, bool pair = false, bool stash = false) {
+#define TC_MAX_NS 8                 // barrier index stride (the pipelined dX kernel runs a ring of 8 half-size stages)
+__host__ __device__ static inline TcSmem tc_smem_layout(uint32_t small_bytes) {
   TcSmem s;
   uint32_t o = 0;
-  s.A = o; o += (uint32_t)tc_a_sets(pair, stash) * 4 * TC_KB_BYTES;
+  s.A = o; o += 4 * TC_KB_BYTES;
   s.AD = o; o += TC_KB_BYTES;
-  s.W = o; o += (uint32_t)tc_ns(pair, stash) * tc_stage_bytes(pair);
+  s.W = o; o += (uint32_t)TC_NS * TC_STAGE_BYTES;
   s.small = o; o += small_bytes;
   s.part = s.AD;    // head partial sums live in the never-read half (columns 32..63) of the dirs block
   s.bars = o; o += 40 * 8;
@@ -46,7 +40,9 @@ __host__ __device__ static inline TcSmem tc_smem_layout(uint32_t small_bytes, bo
 #define BAR_A_READY(i) (2 * TC_MAX_NS + (i))      // 0..3: A K-blocks, 4: encoded-dirs block
 #define BAR_ACC_FULL (2 * TC_MAX_NS + 5)
 #define BAR_STASH_DONE (2 * TC_MAX_NS + 6)   // training: the bulk store of A block kb has read shared memory (one barrier per block)
-#define BAR_STASH_DONE_KB(kb) (BAR_STASH_DONE + (kb))       // kb + 4 * set: 8 barriers
+#define BAR_STASH_DONE_KB(kb) (BAR_STASH_DONE + (kb))
+#define BAR_S_READY (2 * TC_MAX_NS + 13)     // forward kernel: lin_in's operand (ring slot S) written by all 16 epilogue warps
+#define BAR_ACC_FULL_T (2 * TC_MAX_NS + 14)  // forward kernel: the T region's own completion barrier (BAR_ACC_FULL = X's)
 
 // ---------------------------------------------------------------------------------------------- encode
 // 16 consecutive columns [C0, C0+16) of the positional encoding [x, sin(2^k x), cos(2^k x)]_k (embedder.py:90-97;

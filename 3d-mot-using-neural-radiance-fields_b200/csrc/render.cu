@@ -9,8 +9,7 @@
 
 int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                     const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
-                    float* raw_rgb, int64_t ray_stride, void* stash, int* status, int fp16, int single_cta,
-                    int stash_direct, cudaStream_t st);
+                    float* raw_rgb, int64_t ray_stride, void* stash, int* status, int fp16, cudaStream_t st);
 int star_f32_forward(const MlpLayout& lay, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                      const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
                      float* raw_rgb, int64_t ray_stride, void* stash, cudaStream_t st);
@@ -62,11 +61,12 @@ int run_net(const StarRenderCfg& c, int n_blocks, const void* packed, const Star
     return star_f32_forward(lay, packed, pts, viewdirs, pose12, sc_xyz, sc_dir, c.R, S, raw_alpha, raw_rgb, ray_stride,
                             nullptr, st);
   if (prec == STAR_PREC_BF16 || prec == STAR_PREC_F16) {
+    if (c.precision & STAR_PREC_FLAG_RETIRED) return STAR_E_UNSUPPORTED;
     TcLayout tl;
     rc = star_make_tc_layout(&d, &tl);
     if (rc) return rc;
     return star_tc_forward(tl, packed, pts, viewdirs, pose12, sc_xyz, sc_dir, c.R, S, raw_alpha, raw_rgb, ray_stride,
-                           nullptr, status, prec == STAR_PREC_F16, (c.precision & STAR_PREC_FLAG_CTA_PAIR) == 0, 0, st);
+                           nullptr, status, prec == STAR_PREC_F16, st);
   }
   return STAR_E_UNSUPPORTED;
 }

@@ -9,9 +9,15 @@
 #define STAR_MAX_V 8                          // max dynamic objects handled by the compositing kernels
 
 extern int g_star_last_cuda_error;
+// device pointer of the watchdog word of a tensor-core kernel family (c_api.cu); NULL if mapped host memory is unavailable
+enum { STAR_WD_FWD = 0, STAR_WD_DX = 1, STAR_WD_DW = 2, STAR_WD_DX2 = 3, STAR_WD_MIP_FWD = 4, STAR_WD_MIP_DX = 5 };
+int* star_watchdog_dev(int family);
 
+extern int g_star_sync_launches;   // STAR_B200_SYNC_LAUNCHES=1 (diagnostics): every entry point waits for its kernels, so that
+                                   // an asynchronous fault is reported by the call that caused it
 static inline int star_check_launch() {
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && g_star_sync_launches) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     g_star_last_cuda_error = (int)e;
     return STAR_E_CUDA;

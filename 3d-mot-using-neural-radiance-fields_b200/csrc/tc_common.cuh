@@ -43,10 +43,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* db
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > STAR_TC_WATCHDOG_CYCLES) {
-      if (dbg != nullptr) atomicExch(dbg, (code << 16) | (int)(blockIdx.x & 0xffff));
+      if (dbg != nullptr) {      // (mapped host memory: make sure the word has landed before the context dies)
+        atomicExch(dbg, (code << 16) | (int)(blockIdx.x & 0xffff));
+        __threadfence_system();
+        if (*reinterpret_cast<volatile int*>(dbg) == 0) __threadfence_system();
+      }
       __trap();
     }
   }
+}
+
+// launch markers next to a family's watchdog word (mapped host memory): word + 16 counts kernel starts, word + 32 kernel ends
+// (CTA 0 only) -- after a CUDA fault, begin != end names the family that was running (star_watchdog_word(16 + f) / (32 + f))
+__device__ __forceinline__ void tc_mark_begin(int* dbg) {
+  if (dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(dbg + 16, 1);
+}
+__device__ __forceinline__ void tc_mark_end(int* dbg) {
+  if (dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(dbg + 32, 1);
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads, bulk copies)
@@ -173,7 +186,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity,
   const long long t0 = clock64();
   while (!mbar_try_wait_cluster(bar, parity)) {
     if (clock64() - t0 > STAR_TC_WATCHDOG_CYCLES) {
-      if (dbg != nullptr) atomicExch(dbg, (code << 16) | (int)(blockIdx.x & 0xffff));
+      if (dbg != nullptr) {      // (mapped host memory: make sure the word has landed before the context dies)
+        atomicExch(dbg, (code << 16) | (int)(blockIdx.x & 0xffff));
+        __threadfence_system();
+        if (*reinterpret_cast<volatile int*>(dbg) == 0) __threadfence_system();
+      }
       __trap();
     }
   }

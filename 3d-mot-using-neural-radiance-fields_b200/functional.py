@@ -19,8 +19,6 @@ STASH_BUDGET_BYTES = int(float(os.environ.get("STAR_B200_STASH_GB", "24")) * (1 
 
 # A/B switch: run the tensor-core forward on the CTA-pair (cta_group::2) kernels instead of the one-CTA-per-SM ones (same
 # results, measured slower: see include/star_b200.h)
-TC_CTA_PAIR = os.environ.get("STAR_B200_TC_PAIR", "0") == "1"
-TC_STASH_DIRECT = os.environ.get("STAR_B200_STASH_DIRECT", "0") == "1"
 TC_DX_PIPELINED = os.environ.get("STAR_B200_DX_PIPELINED", "0") == "1"
 
 # instrumentation for bench.py: number of kernel-launching C-ABI calls issued
@@ -334,10 +332,6 @@ class NetRuntime:
         return out
 
     def desc(self, precision):
-        if TC_CTA_PAIR and precision != _capi.PREC_F32:
-            precision = precision | _capi.PREC_FLAG_CTA_PAIR
-        if TC_STASH_DIRECT and precision != _capi.PREC_F32:
-            precision = precision | _capi.PREC_FLAG_STASH_DIRECT
         if TC_DX_PIPELINED and precision != _capi.PREC_F32:
             precision = precision | _capi.PREC_FLAG_DX_PIPELINED
         return _capi.net_desc(self.n_blocks, self.L_xyz, self.L_dir, precision)

@@ -637,7 +637,7 @@ def measure(args):
     t_wall = time.perf_counter()
     for i in range(args.steps):
         if flush is not None:
-            flush.fill_(i)
+            flush.fill_(i & 0xff)
         ev[2 * i].record()
         step_device(ro, rd)
         ev[2 * i + 1].record()
@@ -732,7 +732,17 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_b200(args)
+        try:
+            run_b200(args)
+        except Exception:
+            # a tensor-core kernel whose barrier watchdog fired says which wait hung (readable after the context died)
+            try:
+                import star_b200
+                rep = star_b200._capi.watchdog_report()
+                sys.stderr.write("[bench] kernel watchdog: %s | launch markers %s\n" % (rep or "-", star_b200._capi.launch_markers()))
+            except Exception:
+                pass
+            raise
 
 
 if __name__ == "__main__":

@@ -43,18 +43,17 @@ enum {
  *          2-3e-3 on its own), i.e. this tier does NOT meet the 2e-3 bound in the max norm.
  *   F16  : the same kernels with IEEE fp16 activations and weights (2^-12 operand rounding instead of 2^-9, same
  *          speed): max error < 1e-3, the tier that meets the bound and the default of the tensor-core path.  The
- *          back-propagated gradients stay bf16 (their range reaches 1e-8), multiplied with the fp16 weights /
- *          activations by mixed-format tcgen05.mma.  Range guard: activations beyond 65504 overflow to inf and surface
- *          as non-finite raw outputs, which star_mlp_forward reports through its `status` word. */
+ *          back-propagated gradients are fp16 too, scaled per launch by a power of two taken from the device-side
+ *          maximum of the incoming gradient and un-scaled in the dW / pose epilogues.  Range
+ *          guard: activations beyond 65504 overflow to inf and surface as non-finite raw outputs, which
+ *          star_mlp_forward reports through its `status` word. */
 enum { STAR_PREC_F32 = 0, STAR_PREC_BF16 = 1, STAR_PREC_F16 = 2 };
-/* OR-ed into StarNetDesc.precision (tensor-core tiers): run the forward on the CTA-pair (cta_group::2) kernels instead of
- * the one-CTA-per-SM kernels.  Same results bit for bit; measured SLOWER on B200 (C2 render 2.05 M against 2.66 M rays/s,
- * profiles/r2b_*: the layer chain of a tile is latency-bound and the pair adds a cross-CTA hop to every operand hand-off),
- * so it is opt-in and kept for A/B measurements. */
-#define STAR_PREC_FLAG_CTA_PAIR 0x100
-/* training forward, A/B variant: the epilogue threads write the activation stash themselves (two 16-byte global stores per
- * thread and chunk) instead of one bulk copy per completed operand block issued by the producer warp. */
-#define STAR_PREC_FLAG_STASH_DIRECT 0x200
+/* Bits 0x100 (CTA-pair / cta_group::2 forward) and 0x200 (activation stash written by the epilogue threads) selected two
+ * A/B variants of the forward kernels that were built, verified bit-identical and measured SLOWER in round 2 (C2 render 2.05 M
+ * against 2.66 M rays/s; stash forward 3.04 against 2.19 ms per step -- DESIGN.md section 7.0, profiles/r2b_*).  The variants
+ * were removed when the forward kernel was re-scheduled across tile boundaries; the bits are RETIRED: an entry point that
+ * receives one returns STAR_E_UNSUPPORTED. */
+#define STAR_PREC_FLAG_RETIRED 0x300
 /* backward, A/B variant: the pipelined dX chain (every N = 256 GEMM as two N = 128 halves with their own completion barriers,
  * so that the epilogue of a group overlaps the MMAs of the next) instead of the serial one.  Same gradients; measured SLOWER
  * (dX + dW + heads 5.09 against 4.79 ms per 4096-ray step: twice as many stages and N = 128 MMAs make the single issuing thread
@@ -73,6 +72,11 @@ typedef struct StarNetDesc {
 int star_abi_version(void);
 const char* star_error_string(int code);
 int star_last_cuda_error(void);
+/* Watchdog of the tensor-core kernels: every mbarrier wait is bounded (2 s of SM cycles); a wait that times out stores
+ * (wait code << 16 | CTA index) in a word of mapped host memory and traps, which surfaces as a CUDA launch failure.  The
+ * word survives the dead context: family 0 = MLP forward, 1 = dX chain, 2 = dW, 3 = pipelined dX, 4 = mip forward,
+ * 5 = mip dX.  0 = that family never timed out. */
+int star_watchdog_word(int family);
 
 /* Number of fp32 elements of the flat master parameter vector of one net, in this order
  * (each nn.Linear as weight [out,in] row-major then bias [out]):

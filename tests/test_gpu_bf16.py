@@ -290,32 +290,75 @@ def test_second_backward_through_a_retained_graph():
 
 
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
-def test_cta_pair_kernels_are_bit_identical_to_the_single_cta_kernels(prec, monkeypatch):
-    """The opt-in cta_group::2 forward (two CTAs, one M = 256 MMA, half the weight K-block per CTA; inference: 8-stage
-    ring, training: second A-block set) computes the same dot products in the same K order: raw outputs and stashes
-    (hence gradients, up to the dW atomics) must not differ from the one-CTA-per-SM kernels.  Odd tile counts exercise
-    the phantom last tile of a pair."""
+def test_forward_is_independent_of_the_tile_schedule(prec):
+    """The forward kernel overlaps tiles (lin_in's operand of tile t + 1 is encoded into a ring slot while the view layer
+    of tile t runs, the dirs block is rewritten after lin_in's epilogue): a sample's raw outputs must not depend on which
+    CTA / position in the CTA's tile sequence it lands on, nor on the kernel variant.  One launch with several tiles per
+    CTA (148 CTAs) against launches of the same rays in small groups (one or two tiles per CTA, other CTAs), inference
+    against training (stash) variant -- all bit-identical; gradients of the big launch equal the sum of the groups'."""
     net, _ = make_star(1, 8, 4096, False, seed=21, training=True, precision=prec)
-    for R, S, dyn in ((301, 191, False), (129, 5, True), (1, 1, False), (640, 64, True)):
+    for R, S, dyn in ((1150, 191, False), (1301, 67, True)):
         module = net.dynamic_coarse_nerfs[0] if dyn else net.static_coarse_nerf
         ro, rd = so.carla_rays(R, seed=7)
         vd = rd / rd.norm(dim=-1, keepdim=True)
         pts, _ = so.sample_pts(ro, rd, 0.03, 0.8, S)
         p12 = F_.pose_to_mat12(cu(so.pose7_to_matrix(so.random_poses7(1, seed=9))[0])) if dyn else None
-        res = {}
-        for pair in (False, True):
-            monkeypatch.setattr(F_, "TC_CTA_PAIR", pair)
+        pts_d, vd_d = cu(pts), cu(vd)
+        with torch.no_grad():
+            a0, c0 = module.raw(pts_d, vd_d, p12)                     # inference variant, ~8-11 tiles per CTA
+        module.zero_grad()
+        a, c = module.raw(pts_d, vd_d, p12)                           # training (stash) variant
+        ((a ** 2).mean() + (c ** 2).mean()).backward()
+        g_big = [p.grad.clone() for p in module.parameters()]
+        assert torch.equal(a0, a.detach()) and torch.equal(c0, c.detach()), (R, S)
+        module.zero_grad()
+        for lo in range(0, R, 97):                                    # 97 rays: 145 / 51 tiles, never the same alignment
+            hi = min(R, lo + 97)
             with torch.no_grad():
-                a0, c0 = module.raw(cu(pts), cu(vd), p12)             # inference variant
-            module.zero_grad()
-            a, c = module.raw(cu(pts), cu(vd), p12)                   # training (stash) variant
-            ((a ** 2).mean() + (c ** 2).mean()).backward()
-            res[pair] = (a0, c0, a.detach(), c.detach(), [p.grad.clone() for p in module.parameters()])
-        for i in range(4):
-            assert torch.equal(res[False][i], res[True][i]), (R, S, i)
-        for x, y in zip(res[False][4], res[True][4]):
-            assert float((x - y).norm()) <= 1e-4 * float(x.norm()) + 1e-12
+                a1, c1 = module.raw(pts_d[lo:hi].contiguous(), vd_d[lo:hi].contiguous(), p12)
+            assert torch.equal(a1, a0[lo:hi]) and torch.equal(c1, c0[lo:hi]), (R, S, lo)
+            a2, c2 = module.raw(pts_d[lo:hi].contiguous(), vd_d[lo:hi].contiguous(), p12)
+            (((a2 ** 2).sum() + 0.0) / a.numel() + (c2 ** 2).sum() / c.numel()).backward()
+        for x, y in zip(g_big, (p.grad for p in module.parameters())):
+            assert float((x - y).norm()) <= 2e-3 * float(x.norm()) + 1e-12
     F_.check_range()
+
+
+def test_stash_forward_back_to_back_launches_do_not_fault():
+    """Regression for a barrier race that only showed on some GPUs and only with kernels queued back to back: with the
+    dirs K-block FIRST in the view layer, the 16 epilogue warps announced feature block 3 on the w_full barrier of the ring
+    stage that K-block 0 (the dirs block) was still waiting on whenever the producer thread lagged behind its stash
+    stores -- an arrival-count underflow, reported as cudaErrorLaunchFailure after 0.5-20 s of training.  ~1500 training
+    forwards without a synchronisation in between (tools/stress_tc.py runs the long version)."""
+    net, _ = make_star(0, 8, 1 << 20, False, seed=3, training=True, precision="fp16")
+    m = net.static_fine_nerf
+    R, S = 4096, 192
+    ro, rd = so.carla_rays(R, seed=1)
+    vd = cu(rd / rd.norm(dim=-1, keepdim=True))
+    pts, _ = so.sample_pts(ro, rd, 2.0, 6.0, S)
+    pts = cu(pts).contiguous()
+    for _ in range(30):
+        for _ in range(25):
+            a, c = m.raw(pts, vd, None)
+            del a, c
+        torch.cuda.synchronize()
+    F_.check_range()
+
+
+def test_retired_variant_flags_are_rejected():
+    """Bits 0x100 / 0x200 of StarNetDesc.precision selected the CTA-pair and direct-stash A/B variants (removed): an entry
+    point must refuse them instead of silently running something else."""
+    import ctypes as C
+    lib = _capi.lib()
+    x = torch.zeros(128, 3, device="cuda")
+    out_a, out_c = torch.zeros(128, device="cuda"), torch.zeros(128, 3, device="cuda")
+    packed = torch.zeros(1 << 22, dtype=torch.uint8, device="cuda")
+    for flag in (0x100, 0x200):
+        d = _capi.net_desc(4, 10, 4, _capi.PREC_F16 | flag)
+        rc = lib.star_mlp_forward(C.byref(d), packed.data_ptr(), x.data_ptr(), None, None, None, x.data_ptr(), None, None,
+                                  None, 1, 128, out_a.data_ptr(), out_c.data_ptr(), 128, None, None, _capi.stream())
+        assert rc == 2, rc          # STAR_E_UNSUPPORTED
+    torch.cuda.synchronize()
 
 
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])

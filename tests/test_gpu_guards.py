@@ -34,16 +34,13 @@ class Arena:
 
 
 @pytest.mark.parametrize("prec", ["fp16", "bf16", "fp32"])
-@pytest.mark.parametrize("pair", [False, True])
-@pytest.mark.parametrize("R,S,dyn", [(129, 1, False), (77, 37, True), (3, 43, False)])
-def test_mlp_forward_backward_stay_inside_their_buffers(prec, pair, R, S, dyn):
-    if pair and prec == "fp32":
-        pytest.skip("no CTA-pair variant of the fp32 tier")
+@pytest.mark.parametrize("R,S,dyn", [(129, 1, False), (77, 37, True), (3, 43, False), (1031, 53, True)])
+def test_mlp_forward_backward_stay_inside_their_buffers(prec, R, S, dyn):
     net = star_b200.STaR(ref_harness.make_args(num_vehicles=1, N_importance=8, chunk=4096))
     net.load_state_dict(so.init_star_params(1, 8, seed=3, bias_std=0.02))
     net.to(DEV)
     m = net.dynamic_coarse_nerfs[0] if dyn else net.static_coarse_nerf
-    precision = _capi.PRECISIONS[prec] | (_capi.PREC_FLAG_CTA_PAIR if pair else 0)
+    precision = _capi.PRECISIONS[prec]
     flat, packed = m._rt.refresh(_capi.PRECISIONS[prec])
     d = _capi.net_desc(m._rt.n_blocks, 10, 4, precision)
     L = _capi.lib()

@@ -29,10 +29,7 @@ pose = torch.nn.Parameter(so.random_poses7(V, seed=3).to(dev))
 u = torch.rand(R, Ni, device=dev)
 target = torch.rand(R, 3, device=dev)
 for prec in ("fp32", "fp16", "bf16"):
-    for pair in (False, True):
-        if pair and prec == "fp32":
-            continue
-        F_.TC_CTA_PAIR = pair
+    for pair in (False,):
         net.set_precision(prec)
         net.train()
         net.zero_grad()
@@ -47,7 +44,6 @@ for prec in ("fp32", "fp16", "bf16"):
             o2 = R_.render_star_appinit(net, pts, vd, z, ro, rd, Ni)               # single-call entry, V = 0
         torch.cuda.synchronize()
         print(prec, "pair" if pair else "single", float(loss), float(o1["rgb"].mean()), float(o2["rgb"].mean()), flush=True)
-F_.TC_CTA_PAIR = False
 K = torch.tensor([[20.0, 0, 8.0], [0, 20.0, 6.0], [0, 0, 1.0]])
 c2w = torch.eye(4, device=dev)[:3]
 with torch.no_grad():
