@@ -1,15 +1,15 @@
-// bf16 tensor-core tier of the per-sample NeRF MLP (models/nerf.py:112-179, models/resnet.py:51-59,103-110)
-// for sm_100a: pose transform (star__.py:160-199) -> positional encoding (embedder.py:81-112) ->
-// ResNet-FC trunk -> heads as ONE persistent, warp-specialised kernel per launch.
+// 16-bit (bf16 / fp16 operands) tensor-core tiers of the per-sample NeRF MLP (models/nerf.py:112-179,
+// models/resnet.py:51-59,103-110) for sm_100a: pose transform (star__.py:160-199) -> positional encoding
+// (embedder.py:81-112) -> ResNet-FC trunk -> heads as ONE persistent, warp-specialised kernel per launch.
 //
 // One CTA per SM walks tiles of 128 samples.  Roles (576 threads):
-//   warps 0-15 "epilogue" warps: encode the tile's inputs to bf16 into the shared-memory A operand, and after
-//              every layer move the fp32 accumulator TMEM -> registers, add bias / ReLU, convert to bf16 and
-//              write the next layer's A operand (warp w owns TMEM lanes 32*(w%4).., 16 of every 64 columns:
-//              group w/4); alpha / rgb heads are fp32 dot products in these registers.
-//   warp 16    weight producer: streams the pre-swizzled bf16 weight K-blocks (32 KB each) from L2 into a
-//              4-stage shared-memory ring with 1-D bulk async copies (TMA engine) + mbarrier transaction counts.
-//   warp 17    MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16, bf16 -> fp32 in TMEM).
+//   warps 0-15 "epilogue" warps: encode the tile's inputs into shared memory, and after every layer move the fp32
+//              accumulator TMEM -> registers, add bias / ReLU, convert to 16 bits and write the next layer's A operand
+//              (warp w owns TMEM lanes 32*(w%4).., 16 of every 64 columns: group w/4); alpha / rgb heads are fp32
+//              dot products in these registers.
+//   warp 16    weight producer: streams the pre-swizzled weight K-blocks (32 KB each) from L2 into a 4-stage
+//              shared-memory ring with 1-D bulk async copies (TMA engine) + mbarrier transaction counts.
+//   warp 17    MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16, 16-bit operands -> fp32 in TMEM).
 //
 // TMEM (512 columns): X = columns 0..255 holds the residual stream x (fp32, biases kept separately),
 // T = columns 256..511 holds the other accumulator.  fc_1 ACCUMULATES onto X, which performs the residual
@@ -18,8 +18,15 @@
 // K-block by K-block).  An operand block of layer L+1 is announced on the SAME barrier as the weight K-block it will
 // be multiplied with: w_full[stage] expects 1 arrival + the copy's bytes from the producer and 16 arrivals from the
 // epilogue warps (count 17), so the issuer -- whose loop must stay under the 512 tensor cycles of a K-block -- waits
-// on one barrier per K-block instead of two.  (The encoded-dirs block is written a whole tile ahead of its use and
-// keeps its own a_ready[4]; training additionally arrives on a_ready[kb] for the stash writer.)
+// on one barrier per K-block instead of two.
+// RULE for that shared barrier: the epilogue warps may arrive on w_full[stage] only when the stage's previous phase is
+// certain to be complete, i.e. when the stage's previous user (4 ring slots earlier) belongs to a layer whose MMAs are
+// all done.  That holds for K-blocks 0..3 of a layer (an epilogue runs after its layer's accumulator is complete), NOT
+// for a 5th K-block (it wraps onto the stage of the same layer's K-block 0) and NOT for operands written ahead of time.
+// Those get barriers of their own and the producer thread supplies all 17 arrivals of their K-block's w_full, in program
+// order: the encoded-dirs block (a_ready[4]; the view layer's LAST K-block) and lin_in's operand of the next tile
+// (s_ready).  Breaking the rule is an arrival-count underflow = a launch failure on some GPUs (profiles/r2h_ring_race.md).
+// (Training additionally arrives on a_ready[kb] for the stash writer.)
 #include "star_common.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
