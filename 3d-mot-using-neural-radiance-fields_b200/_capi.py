@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstar_b200.so")
+# STAR_B200_LIB: another build of the same ABI (A/B measurements of kernel variants on one box)
+LIB_PATH = os.environ.get("STAR_B200_LIB") or os.path.join(_HERE, "libstar_b200.so")
 
 ABI_VERSION = 2
 PREC_F32, PREC_BF16, PREC_F16 = 0, 1, 2

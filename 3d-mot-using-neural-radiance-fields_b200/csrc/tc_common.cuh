@@ -27,8 +27,24 @@ __device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// TC_WAIT_HINT_NS > 0: try_wait carries a suspend-time hint (the thread sleeps until the phase completes or the hint
+// expires instead of returning after the implementation's default time limit): fewer polling instructions while the 16
+// epilogue warps wait for an accumulator.  Measured on the power-capped C2 render (tools/ab_bench.sh, one box, interleaved):
+// 1 us and 20 us hints are 0.5 % SLOWER than the default (2.777 / 2.778 M against 2.791 M rays/s, clock unchanged) -> off.
+#ifndef TC_WAIT_HINT_NS
+#define TC_WAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
+#if TC_WAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity), "r"((uint32_t)TC_WAIT_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -36,6 +52,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(done)
       : "r"(bar), "r"(parity)
       : "memory");
+#endif
   return done != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* dbg, int code) {
