@@ -142,6 +142,9 @@ __global__ void grad_absmax_kernel(const float* __restrict__ d_alpha, const floa
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(absmax), __float_as_uint(m));
 }
 
+#ifndef TC_DX_LD_DEPTH
+#define TC_DX_LD_DEPTH 2       // accumulator chunk loads in flight per epilogue thread of the dX chain (1 = load, wait, use)
+#endif
 template <bool F16, bool POSE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const StarPtsSrc pts,
@@ -419,36 +422,63 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             pacc[26] += dob[0] * h[1] - dob[1] * h[0];
           }
         }
+        // publish one 16-column chunk of this phase's output: zero rows beyond the launch, 16-bit conversion into A block kb
+        // (fp16: saturating -- a gradient that outgrows the headroom clamps to 65504 instead of becoming inf), proxy fence,
+        // arrival.  (The gstash copy of the block is a bulk store issued by the producer warp once the block is complete.)
+        auto publish = [&](const int kb, float (&v)[16]) {
+          if (!valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+          }
+          store_row16<F16, false, true>(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, v);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_A_READY(kb)));
+        };
+        if (P.kind == BK_PRE) {
+          // G of relu(h2) from d_rgb and the rgb head (2 chunks of the 128 view-layer features), masked by the stashed
+          // relu(h2) itself (> 0 <=> bits != 0 for a ReLU output)
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+            const int col0 = kb * 64 + cg * TC_CPT;
+            const uint4 m0 = mq[kb][0], m1 = mq[kb][1];
+            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            const float* rw = s_small + lay.off_rgb_w + col0;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              v[j] = dc0 * rw[j] + dc1 * rw[STAR_WV + j] + dc2 * rw[2 * STAR_WV + j];
+              const uint32_t bits = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xffffu);
+              if (bits == 0u) v[j] = 0.f;
+            }
+            publish(kb, v);
+          }
+          continue;
+        }
+        // TMEM loads are double buffered: the accumulator chunk of K-block kb + 1 is requested as soon as chunk kb has
+        // arrived, so its latency hides behind chunk kb's masking / conversion / stores (fc_0 also fetches the residual
+        // gradient's chunk kb then, and waits for both before the add)
+        const uint32_t t_acc = (P.kind == BK_OUT) ? tX : tT;
+        uint32_t racc[2][16];
+        if (TC_DX_LD_DEPTH >= 2) tmem_ld16(t_acc, racc[0]);
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
           if (kb >= P.nch) break;
           const int col0 = kb * 64 + cg * TC_CPT;
-          const uint4 m0 = mq[kb & 1][0], m1 = mq[kb & 1][1];      // (only the 2-chunk view phase has mask_blk >= 0)
-          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
           const uint32_t mb16 = ((kb < 2 ? mbits.x : mbits.y) >> ((kb & 1) * 16)) & 0xffffu;
+          if (TC_DX_LD_DEPTH < 2) tmem_ld16(t_acc + 64u * (uint32_t)kb, racc[kb & 1]);
+          tmem_wait_ld();            // (all of this thread's outstanding loads: chunk kb)
+          if (TC_DX_LD_DEPTH >= 2 && kb + 1 < P.nch) tmem_ld16(t_acc + 64u * (uint32_t)(kb + 1), racc[(kb + 1) & 1]);
+          uint32_t rx[16];
+          if (P.kind == BK_FC0) tmem_ld16(tX + 64u * (uint32_t)kb, rx);
           float v[16];
-          if (P.kind == BK_PRE) {
-            const float* rw = s_small + lay.off_rgb_w + col0;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = dc0 * rw[j] + dc1 * rw[STAR_WV + j] + dc2 * rw[2 * STAR_WV + j];
-          } else {
-            uint32_t r[16];
-            tmem_ld16(((P.kind == BK_OUT) ? tX : tT) + 64u * (uint32_t)kb, r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          }
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(racc[kb & 1][j]);
           if (P.kind == BK_OUT) {
             const float* aw = s_small + lay.off_alpha_w + col0;
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = fmaf(da, aw[j], v[j]);
-          }
-          if (P.mask_blk >= 0) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const uint32_t bits = (j & 1) ? (mw[j >> 1] >> 16) : (mw[j >> 1] & 0xffffu);
-              if (bits == 0u) v[j] = 0.f;
-            }
           }
           if (P.mask_layer >= 0) {
 #pragma unroll
@@ -456,30 +486,17 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
               if (!((mb16 >> j) & 1u)) v[j] = 0.f;
           }
           if (P.kind == BK_FC0) {      // dx += masked product
-            uint32_t rx[16];
-            tmem_ld16(tX + 64u * (uint32_t)kb, rx);
             tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(rx[j]);
           }
           if (P.kind == BK_FC0 || P.kind == BK_X0) {
-            uint32_t rx[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) rx[j] = __float_as_uint(v[j]);
             tmem_st16(tX + 64u * (uint32_t)kb, rx);
             tmem_wait_st();
           }
-          if (!valid) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0.f;
-          }
-          // (the gstash copy of this block is a bulk store issued by the producer warp once the block is complete)
-          // (fp16: saturating conversion -- a gradient that outgrows the headroom clamps to 65504 instead of becoming inf)
-          store_row16<F16, false, true>(sA + (uint32_t)kb * TC_KB_BYTES, row, cg * 2, v);
-          fence_proxy_async_smem();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(BAR_A_READY(kb)));
+          publish(kb, v);
         }
       }
     }
