@@ -29,6 +29,36 @@ def _free_port():
     return p
 
 
+def _run_ranks(worker, world=2, attempts=2):
+    """Spawn `world` gloo ranks and collect one result per rank.  The children import torch from a possibly cold page
+    cache (a minute on a fresh container), so the waits are generous, and a lost rendezvous (port taken between
+    _free_port and init_process_group) is retried once on a fresh port."""
+    import queue as _q
+    ctx = mp.get_context("spawn")
+    last = None
+    for _ in range(attempts):
+        port = _free_port()
+        q = ctx.Queue()
+        procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        try:
+            res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
+            for p in procs:
+                p.join(timeout=120)
+            if all(p.exitcode == 0 for p in procs):
+                return res
+            last = RuntimeError(f"rank exit codes {[p.exitcode for p in procs]}")
+        except _q.Empty as e:
+            last = e
+        finally:
+            for p in procs:
+                if p.is_alive():
+                    p.kill()
+                    p.join(timeout=30)
+    raise AssertionError(f"gloo ranks did not finish: {last!r}")
+
+
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -59,16 +89,7 @@ def _worker(rank, world, port, q):
 
 
 def test_two_rank_gloo_matches_single_process():
-    world, port = 2, _free_port()
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = _run_ranks(_worker)
     # single-process reference
     torch.manual_seed(0)
     w = torch.nn.Parameter(torch.randn(3, 3))
@@ -120,16 +141,7 @@ def _worker_flat(rank, world, port, q):
 
 
 def test_two_rank_gloo_flat_gradient_runs_are_reduced_in_place():
-    world, port = 2, _free_port()
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker_flat, args=(r, world, port, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = _run_ranks(_worker_flat)
     n = 15 + 5 + 15 + 3
     for rank, n_runs, gbuf, lone, g2 in res:
         assert n_runs == 2                                               # the flat run + the lone parameter
@@ -178,16 +190,7 @@ def _worker_sync(rank, world, port, q):
 
 
 def test_two_rank_gloo_gradsync_matches_single_process():
-    world, port = 2, _free_port()
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker_sync, args=(r, world, port, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = _run_ranks(_worker_sync)
     torch.manual_seed(0)
     net = _Toy()
     pose = torch.nn.Parameter(torch.randn(2, 7))
