@@ -99,6 +99,8 @@ _SIGS = {
     "star_invert_cdf": (C.c_int, [c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f]),
     "star_hierarchical": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f, c_f]),
     "star_merge_samples": (C.c_int, [c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, c_f, c_f, c_f, c_f]),
+    "star_composite_hier_forward": (C.c_int, [c_f, c_f, c_f, c_f, c_f, c_f, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                              c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f]),
     "star_render_workspace_bytes": (C.c_size_t, [C.POINTER(StarRenderCfg)]),
     "star_render_forward": (C.c_int, [C.POINTER(StarRenderCfg), C.POINTER(StarRenderIn), C.POINTER(StarRenderOut), c_f,
                                       C.c_size_t, c_f, c_f]),

@@ -4,39 +4,8 @@
 // transmittance product is a warp-shuffle prefix product with a running carry, the backward suffix
 // sums are warp-shuffle reverse scans.  HBM-bound: every input is read once (forward) or twice
 // (backward: forward recompute + reverse sweep, the second read hits L1/L2).
-#include "star_common.cuh"
+#include "ray_device.cuh"
 
-struct RayGeom {
-  float norm;  // ||rays_d||  (:325)
-};
-
-__device__ __forceinline__ float ray_norm(const float* __restrict__ rays_d, int r) {
-  const float x = rays_d[r * 3 + 0], y = rays_d[r * 3 + 1], z = rays_d[r * 3 + 2];
-  return sqrtf(x * x + y * y + z * z);
-}
-
-// dists (:318-325): z[s+1]-z[s], last = far_dist, times ||rays_d||
-__device__ __forceinline__ float sample_dist(const float* __restrict__ zr, int s, int S, float far_dist, float norm) {
-  const float d = (s == S - 1) ? far_dist : (zr[s + 1] - zr[s]);
-  return d * norm;
-}
-
-// alpha = 1 - exp(-softplus(raw) * dist)   (:301-303)
-__device__ __forceinline__ float alpha_of(float raw, float dist) { return 1.f - fexp(-softplus_f(raw) * dist); }
-// d alpha / d raw
-__device__ __forceinline__ float dalpha_draw(float raw, float dist) {
-  return dist * fexp(-softplus_f(raw) * dist) * softplus_grad_f(raw);
-}
-
-// exclusive prefix product of m over the warp given the running carry; updates carry
-__device__ __forceinline__ float excl_transmittance(float m, float& carry, int lane) {
-  const float incl = warp_scan_prod(m, lane);
-  float excl = __shfl_up_sync(STAR_FULL_MASK, incl, 1);
-  if (lane == 0) excl = 1.f;
-  const float T = carry * excl;
-  carry *= __shfl_sync(STAR_FULL_MASK, incl, 31);
-  return T;
-}
 
 // =========================================================================== single field forward
 __global__ void composite_single_fwd_kernel(const float* __restrict__ raw_alpha, const float* __restrict__ raw_rgb,
@@ -88,8 +57,7 @@ __global__ void composite_single_fwd_kernel(const float* __restrict__ raw_alpha,
   }
 }
 
-// Even S: every lane owns two consecutive samples (8-byte loads / stores, one transmittance scan and one trip of
-// the loop per 64 samples) and the five per-ray sums share 11 shuffles (warp_sum4).
+// Even S: every lane owns two consecutive samples (composite_single_ray_x2, ray_device.cuh).
 __global__ void composite_single_fwd_x2_kernel(const float* __restrict__ raw_alpha, const float* __restrict__ raw_rgb,
                                                const float* __restrict__ z_vals, const float* __restrict__ rays_d,
                                                int R, int S, float far_dist, int white_bkgd,
@@ -98,56 +66,8 @@ __global__ void composite_single_fwd_x2_kernel(const float* __restrict__ raw_alp
                                                float* __restrict__ weights_o, float* __restrict__ dists_o) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < R; r += gridDim.x * wpb) {
-    const float norm = ray_norm(rays_d, r);
-    const int64_t row = (int64_t)r * S;
-    const float* zr = z_vals + row;
-    float carry = 1.f, sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
-    for (int base = 0; base < S; base += 64) {
-      const int s0 = base + 2 * lane;
-      const bool ok = s0 < S;   // S even: both samples of the pair are valid together
-      float2 z = make_float2(0.f, 0.f), ra = make_float2(0.f, 0.f);
-      float2 c01 = make_float2(0.f, 0.f), c23 = c01, c45 = c01;
-      if (ok) {
-        z = *reinterpret_cast<const float2*>(zr + s0);
-        ra = *reinterpret_cast<const float2*>(raw_alpha + row + s0);
-        const float2* cp = reinterpret_cast<const float2*>(raw_rgb + (row + s0) * 3);
-        c01 = cp[0]; c23 = cp[1]; c45 = cp[2];
-      }
-      float znext = __shfl_down_sync(STAR_FULL_MASK, z.x, 1);
-      if (lane == 31 && base + 64 < S) znext = zr[base + 64];
-      float2 dist = make_float2(0.f, 0.f), alpha = make_float2(0.f, 0.f);
-      if (ok) {
-        dist.x = (z.y - z.x) * norm;
-        dist.y = ((s0 + 1 == S - 1) ? far_dist : (znext - z.y)) * norm;
-        alpha.x = alpha_of(ra.x, dist.x);
-        alpha.y = alpha_of(ra.y, dist.y);
-      }
-      const float m0 = 1.f - alpha.x + 1e-10f, m1 = 1.f - alpha.y + 1e-10f;   // (alpha = 0 -> m = 1 when !ok)
-      const float T0 = excl_transmittance(ok ? m0 * m1 : 1.f, carry, lane);
-      if (ok) {
-        const float w0 = alpha.x * T0, w1 = alpha.y * (T0 * m0);
-        *reinterpret_cast<float2*>(weights_o + row + s0) = make_float2(w0, w1);
-        if (dists_o) *reinterpret_cast<float2*>(dists_o + row + s0) = dist;
-        sr += w0 * sigmoid_f(c01.x) + w1 * sigmoid_f(c23.y);
-        sg += w0 * sigmoid_f(c01.y) + w1 * sigmoid_f(c45.x);
-        sb += w0 * sigmoid_f(c23.x) + w1 * sigmoid_f(c45.y);
-        sd += w0 * z.x + w1 * z.y;
-        sa += w0 + w1;
-      }
-    }
-    sa = warp_sum(sa);
-    const float v = warp_sum4(sr, sg, sb, sd, lane);   // lanes 0-7: r, 8-15: g, 16-23: b, 24-31: depth
-    const float bg = white_bkgd ? (1.f - sa) : 0.f;                   // :360-361
-    if ((lane & 7) == 0) {
-      if (lane < 24) {
-        rgb_o[r * 3 + (lane >> 3)] = v + bg;
-      } else {
-        const float wsum = (sa >= 0.f) ? sa : 1e-7f;                  // :353-354
-        disp_o[r] = 1.f / fmaxf(1e-10f, v / wsum);                    // :355-357
-        depth_o[r] = v;
-        acc_o[r] = sa;
-      }
-    }
+    composite_single_ray_x2(raw_alpha, raw_rgb, z_vals, rays_d, r, S, far_dist, white_bkgd, rgb_o, disp_o, acc_o, depth_o,
+                            weights_o, dists_o, nullptr, nullptr, lane);
   }
 }
 

@@ -155,11 +155,33 @@ extern "C" int star_render_forward(const StarRenderCfg* cfg, const StarRenderIn*
 
   // ---- coarse pass
   const StarPtsSrc src0{pts0, rays_o, rays_d, z0};
-  rc = run_pass(c, *in, true, src0, viewdirs, rays_d, z0, c.Nc, ws, sc, out->coarse, out->dists0, status, st);
-  if (rc || c.Ni <= 0) return rc;
+  // single field, fine samples drawn here: the coarse compositing and the hierarchical step are ONE kernel per ray
+  // (ray_fused.cu; weights and depths stay in shared memory between the two)
+  bool fused_tail = c.V == 0 && c.Ni > 0 && in->z_samples == nullptr && (c.Nc & 1) == 0 && c.Nc >= 4 &&
+                    out->z_samples != nullptr;
+  if (fused_tail) {
+    rc = run_net(c, c.n_blocks_static, in->packed_static_coarse, src0, viewdirs, nullptr, nullptr, nullptr, c.Nc,
+                 ws + sc.ra_s, ws + sc.rc_s, c.Nc, status, st);
+    if (rc) return rc;
+    const StarMultiOut& o = out->coarse;
+    rc = star_composite_hier_forward(ws + sc.ra_s, ws + sc.rc_s, z0, rays_d, in->u, in->u_det, c.R, c.Nc, c.Ni, c.far_dist,
+                                     c.white_bkgd, o.rgb, o.disp, o.acc, o.depth, o.weights, out->dists0, out->z_samples,
+                                     out->z_vals, out->z_std, st);
+    if (rc == STAR_E_UNSUPPORTED) {        // misaligned caller arrays: the two stand-alone kernels
+      fused_tail = false;
+      rc = star_composite_single_forward(ws + sc.ra_s, ws + sc.rc_s, z0, rays_d, c.R, c.Nc, c.far_dist, c.white_bkgd, o.rgb,
+                                         o.disp, o.acc, o.depth, o.weights, out->dists0, st);
+    }
+    if (rc) return rc;
+  } else {
+    rc = run_pass(c, *in, true, src0, viewdirs, rays_d, z0, c.Nc, ws, sc, out->coarse, out->dists0, status, st);
+    if (rc || c.Ni <= 0) return rc;
+  }
 
   // ---- hierarchical step: z_mid, sample_pdf(weights[1:-1]), sort(cat), std   (:128-144 / :271-296)
-  if (in->z_samples != nullptr) {
+  if (fused_tail) {
+    rc = STAR_OK;
+  } else if (in->z_samples != nullptr) {
     rc = star_merge_samples(z0, in->z_samples, nullptr, nullptr, c.R, c.Nc, c.Ni, out->z_vals, out->z_std, nullptr, st);
   } else {
     if (!out->z_samples) return STAR_E_NULL;

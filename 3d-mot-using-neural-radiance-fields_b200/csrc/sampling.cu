@@ -3,7 +3,7 @@
 // All arithmetic that feeds index decisions is written with explicit round-to-nearest intrinsics
 // (__fadd_rn / __fmul_rn / __fdiv_rn) so that nvcc cannot contract it into FMAs: every reference
 // op (one eager ATen kernel each) is rounded separately, and so is every op here.
-#include "star_common.cuh"
+#include "ray_device.cuh"
 
 // ------------------------------------------------------------------------------------------ a1
 // models/rendering__.py:87-110.  One thread per (ray, sample); pts written as 3 coalesced floats.
@@ -193,48 +193,7 @@ extern "C" int star_embed(const float* x, int M, int L, const float* scale, floa
 }
 
 // ------------------------------------------------------------------------------------------ a9
-// One warp per ray.  cdf / bins of the ray live in shared memory.
-// Defined arithmetic (DESIGN.md "sample_pdf arithmetic"):
-//   w   = weights + 1e-5f                                   (rendering__.py:722)
-//   s   = fp32( sum_k w_k accumulated in fp64 )             exactly rounded normaliser (:723)
-//   pdf = w / s                                             IEEE fp32 division
-//   cdf = fp32( prefix sums of pdf accumulated in fp64 )    == torch CPU cumsum (:733-734)
-// The fp64 sums of <= 2^10 fp32 values spanning <= 2^17 in magnitude are exact, so the warp-parallel
-// order gives the same bits as a sequential loop.
-__device__ __forceinline__ void build_cdf_warp(const float* __restrict__ w_row, int nw, float* cdf, int lane) {
-  double part = 0.0;
-  for (int k = lane; k < nw; k += 32) part += (double)__fadd_rn(w_row[k], 1e-5f);
-  const float s = (float)warp_sum_d(part);
-  double carry = 0.0;
-  if (lane == 0) cdf[0] = 0.f;
-  for (int base = 0; base < nw; base += 32) {
-    const int k = base + lane;
-    double p = 0.0;
-    if (k < nw) p = (double)__fdiv_rn(__fadd_rn(w_row[k], 1e-5f), s);
-    const double incl = warp_scan_sum_d(p, lane) + carry;
-    if (k < nw) cdf[k + 1] = (float)incl;
-    carry = __shfl_sync(STAR_FULL_MASK, incl, 31);
-  }
-}
-
-// searchsorted(cdf, u, right=True) (:745) + gather + lerp (:746-759)
-__device__ __forceinline__ float invert_one(const float* cdf, const float* bins, int nb, float u, int& inds,
-                                            int& below, int& above) {
-  int lo = 0, hi = nb;  // first index with cdf[idx] > u
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
-  }
-  inds = lo;
-  below = max(0, lo - 1);
-  above = min(nb - 1, lo);
-  const float c0 = cdf[below], c1 = cdf[above];
-  float denom = __fsub_rn(c1, c0);
-  if (denom < 1e-5f) denom = 1.f;
-  const float t = __fdiv_rn(__fsub_rn(u, c0), denom);
-  const float b0 = bins[below], b1 = bins[above];
-  return __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
-}
+// One warp per ray; cdf / bins of the ray live in shared memory (build_cdf_warp, invert_one: ray_device.cuh).
 
 template <bool HAVE_CDF>
 __global__ void sample_pdf_kernel(const float* __restrict__ bins, int64_t bins_stride,
@@ -318,30 +277,9 @@ extern "C" int star_invert_cdf(const float* bins, const float* cdf, const float*
 }
 
 // ------------------------------------------------------------------------------------------ a10
-// z_mid -> sample_pdf -> sort(cat(z_vals, z_samples)) -> z_std, pts.  One warp per ray.
-// smem per warp: see hier_smem_floats (P = next pow2 >= Ni; zs is padded with +inf up to P)
-// The concatenation is sorted as a MERGE: the coarse samples are sorted by construction, the fine samples are
-// sorted whenever u is (always in eval mode: inverse-CDF sampling is monotone); only otherwise (random u in
-// training) are the Ni fine samples bitonic-sorted first.  Every element then finds its output slot with one
-// binary search in the other list (coarse before fine on ties; torch.sort returns values only, :136,279).
+// z_mid -> sample_pdf -> sort(cat(z_vals, z_samples)) -> z_std, pts.  One warp per ray (hier_ray, ray_device.cuh).
 // GIVEN = true: the fine samples are supplied in z_samples (read, not written) and only the merge,
 // z_std and pts are computed (star_merge_samples).
-__device__ __forceinline__ int count_less(const float* a, int n, float x) {      // # a[i] <  x, a sorted
-  int lo = 0, hi = n;
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < x) lo = mid + 1; else hi = mid; }
-  return lo;
-}
-__device__ __forceinline__ int count_less_equal(const float* a, int n, float x) {  // # a[i] <= x, a sorted
-  int lo = 0, hi = n;
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] <= x) lo = mid + 1; else hi = mid; }
-  return lo;
-}
-
-// floats of shared memory per warp: zall[Nf, padded to 4] | zs[P] | zc[Nc] | cdf[nb] | bins[nb] | guess[Ni]
-__host__ __device__ __forceinline__ int hier_smem_floats(int Nc, int Ni, int P) {
-  return ((((Nc + Ni + 3) & ~3) + P + Nc + 2 * (Nc - 1) + Ni) + 3) & ~3;
-}
-
 template <bool GIVEN>
 __global__ void hierarchical_kernel(const float* __restrict__ z_vals, const float* __restrict__ weights,
                                     const float* __restrict__ u, const float* __restrict__ u_det,
@@ -360,106 +298,8 @@ __global__ void hierarchical_kernel(const float* __restrict__ z_vals, const floa
   int* gs = reinterpret_cast<int*>(sb + nb);   // per fine sample: below + 1 = first guess of its rank among zc
   const bool vec4 = ((Nf & 3) == 0) && (((uintptr_t)z_all | (uintptr_t)pts_fine) & 15) == 0;
   for (int r = blockIdx.x * wpb + warp; r < R; r += gridDim.x * wpb) {
-    const float* zr = z_vals + (int64_t)r * Nc;
-    if (!GIVEN) {
-      build_cdf_warp(weights + (int64_t)r * Nc + 1, Nc - 2, cdf, lane);  // weights[..., 1:-1]  (:131,274)
-      for (int k = lane; k < nb; k += 32) sb[k] = __fmul_rn(0.5f, __fadd_rn(zr[k + 1], zr[k]));  // z_mid (:128)
-    }
-    for (int k = lane; k < Nc; k += 32) zc[k] = zr[k];
-    for (int k = Ni + lane; k < P; k += 32) zs[k] = __int_as_float(0x7f800000);
-    __syncwarp();
-    float sum = 0.f;
-    for (int j = lane; j < Ni; j += 32) {
-      float s;
-      if (GIVEN) {
-        s = z_samples[(int64_t)r * Ni + j];
-      } else {
-        const float uu = (u != nullptr) ? u[(int64_t)r * Ni + j] : u_det[j];
-        int i0, b0, a0;
-        s = invert_one(cdf, sb, nb, uu, i0, b0, a0);
-        z_samples[(int64_t)r * Ni + j] = s;
-        gs[j] = b0 + 1;
-      }
-      zs[j] = s;
-      sum += s;
-    }
-    // z_std = std(z_samples, unbiased=False)   (:144,296)
-    const float mean = warp_sum(sum) / (float)Ni;
-    __syncwarp();
-    float var = 0.f;
-    bool sorted = true;
-    for (int j = lane; j < Ni; j += 32) {
-      const float d = zs[j] - mean;
-      var += d * d;
-      if (j + 1 < Ni && zs[j] > zs[j + 1]) sorted = false;
-    }
-    var = warp_sum(var) / (float)Ni;
-    if (lane == 0) z_std[r] = sqrtf(var);
-    const bool all_sorted = __all_sync(STAR_FULL_MASK, sorted);
-    if (!all_sorted) {
-      // bitonic sort of zs[0..P)
-      for (int k = 2; k <= P; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          __syncwarp();
-          for (int i = lane; i < P; i += 32) {
-            const int l = i ^ j;
-            if (l > i) {
-              const float a = zs[i], b = zs[l];
-              const bool up = ((i & k) == 0);
-              if ((a > b) == up) { zs[i] = b; zs[l] = a; }
-            }
-          }
-        }
-      }
-      __syncwarp();
-    }
-    // merge by rank
-    for (int i = lane; i < Nc; i += 32) {
-      const float v = zc[i];
-      za[i + count_less(zs, Ni, v)] = v;
-    }
-    for (int j = lane; j < Ni; j += 32) {
-      const float v = zs[j];
-      int k;
-      if (!GIVEN && all_sorted) {
-        // a sample drawn from bin [z_mid[b], z_mid[b+1]] has b+1 or b+2 coarse samples at or below it: start from
-        // the guess and walk (exact for any input, O(1) here)
-        k = gs[j];
-        while (k < Nc && zc[k] <= v) ++k;
-        while (k > 0 && zc[k - 1] > v) --k;
-      } else {
-        k = count_less_equal(zc, Nc, v);
-      }
-      za[j + k] = v;
-    }
-    __syncwarp();
-    const float ox = rays_o ? rays_o[r * 3 + 0] : 0.f, oy = rays_o ? rays_o[r * 3 + 1] : 0.f, oz = rays_o ? rays_o[r * 3 + 2] : 0.f;
-    const float dx = rays_d ? rays_d[r * 3 + 0] : 0.f, dy = rays_d ? rays_d[r * 3 + 1] : 0.f, dz = rays_d ? rays_d[r * 3 + 2] : 0.f;
-    if (vec4) {
-      for (int q = lane; q < (Nf >> 2); q += 32) {
-        const float4 z = *reinterpret_cast<const float4*>(za + 4 * q);
-        __stcs(reinterpret_cast<float4*>(z_all + (int64_t)r * Nf) + q, z);
-        if (pts_fine != nullptr) {
-          float4* po = reinterpret_cast<float4*>(pts_fine + ((int64_t)r * Nf + 4 * q) * 3);
-          __stcs(po + 0, make_float4(__fadd_rn(ox, __fmul_rn(dx, z.x)), __fadd_rn(oy, __fmul_rn(dy, z.x)),
-                                     __fadd_rn(oz, __fmul_rn(dz, z.x)), __fadd_rn(ox, __fmul_rn(dx, z.y))));
-          __stcs(po + 1, make_float4(__fadd_rn(oy, __fmul_rn(dy, z.y)), __fadd_rn(oz, __fmul_rn(dz, z.y)),
-                                     __fadd_rn(ox, __fmul_rn(dx, z.z)), __fadd_rn(oy, __fmul_rn(dy, z.z))));
-          __stcs(po + 2, make_float4(__fadd_rn(oz, __fmul_rn(dz, z.z)), __fadd_rn(ox, __fmul_rn(dx, z.w)),
-                                     __fadd_rn(oy, __fmul_rn(dy, z.w)), __fadd_rn(oz, __fmul_rn(dz, z.w))));
-        }
-      }
-    } else {
-      for (int k = lane; k < Nf; k += 32) z_all[(int64_t)r * Nf + k] = za[k];
-      if (pts_fine != nullptr) {
-        for (int i = lane; i < Nf * 3; i += 32) {
-          const int s = i / 3, c = i - s * 3;
-          const float o = c == 0 ? ox : (c == 1 ? oy : oz), d = c == 0 ? dx : (c == 1 ? dy : dz);
-          pts_fine[(int64_t)r * Nf * 3 + i] = __fadd_rn(o, __fmul_rn(d, za[s]));
-        }
-      }
-    }
-    __syncwarp();
+    hier_ray<GIVEN, false>(z_vals + (int64_t)r * Nc, GIVEN ? nullptr : weights + (int64_t)r * Nc, u, u_det, rays_o, rays_d, r,
+                           Nc, Ni, P, z_samples, z_all, z_std, pts_fine, za, zs, zc, cdf, sb, gs, vec4, lane);
   }
 }
 

@@ -222,6 +222,18 @@ int star_hierarchical(const float* z_vals, const float* weights, const float* u,
 int star_merge_samples(const float* z_vals, const float* z_samples, const float* rays_o, const float* rays_d,
                        int R, int Nc, int Ni, float* z_all, float* z_std, float* pts_fine, void* stream);
 
+/* ---- a6 + a9 + a10 fused (north-star bullet 1): models/rendering__.py:307-379 (raw2outputs of the coarse pass),
+ *      :719-761 (sample_pdf), :128-144 (z_mid, sort(cat), std) ---------------------------------------------------------
+ * One kernel, one warp per ray: compositing of the Nc coarse samples, the CDF of weights[1:-1], the inverse-CDF draw,
+ * z_std and the merge; weights and depths of the ray pass from the compositing part to the sampling part in shared
+ * memory.  Outputs = those of star_composite_single_forward (rgb[R,3], disp, acc, depth [R], weights, dists [R,Nc];
+ * the last two may be NULL) + those of star_hierarchical without pts (z_samples[R,Ni], z_all[R,Nc+Ni], z_std[R]), bit
+ * for bit.  Nc must be even and the [R,Nc] arrays 8-byte aligned: otherwise STAR_E_UNSUPPORTED (use the two entries). */
+int star_composite_hier_forward(const float* raw_alpha, const float* raw_rgb, const float* z_vals, const float* rays_d,
+                                const float* u, const float* u_det, int R, int Nc, int Ni, float far_dist,
+                                int white_bkgd, float* rgb, float* disp, float* acc, float* depth, float* weights,
+                                float* dists, float* z_samples, float* z_all, float* z_std, void* stream);
+
 /* ---- a10 + a11 in ONE call: models/rendering__.py:115-149 (render_star_appinit), :249-298 (render_star_online),
  *      models/star__.py:119-225 (STaR.forward_chunk) -----------------------------------------------------------
  * star_render_forward runs the whole coarse -> fine render of R rays on `stream` with no host round trip:
