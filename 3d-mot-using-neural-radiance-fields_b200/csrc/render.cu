@@ -156,8 +156,10 @@ extern "C" int star_render_forward(const StarRenderCfg* cfg, const StarRenderIn*
   // ---- coarse pass
   const StarPtsSrc src0{pts0, rays_o, rays_d, z0};
   // single field, fine samples drawn here: the coarse compositing and the hierarchical step are ONE kernel per ray
-  // (ray_fused.cu; weights and depths stay in shared memory between the two)
-  bool fused_tail = c.V == 0 && c.Ni > 0 && in->z_samples == nullptr && (c.Nc & 1) == 0 && c.Nc >= 4 &&
+  // (ray_fused.cu; weights and depths stay in shared memory between the two).  Measured (profiles/r2j_hbm_kernels.txt):
+  // 64 + 128 samples 0.336 ms against 0.421 ms for the two kernels (160 000 rays); 256 + 256: 0.285 against 0.275 ms (the
+  // larger per-warp shared memory costs occupancy) -- so only up to 128 coarse samples.
+  bool fused_tail = c.V == 0 && c.Ni > 0 && in->z_samples == nullptr && (c.Nc & 1) == 0 && c.Nc >= 4 && c.Nc <= 128 &&
                     out->z_samples != nullptr;
   if (fused_tail) {
     rc = run_net(c, c.n_blocks_static, in->packed_static_coarse, src0, viewdirs, nullptr, nullptr, nullptr, c.Nc,

@@ -289,6 +289,39 @@ def hierarchical(z_vals, weights, N_importance, det, rays_o, rays_d, u=None, wan
     return zs, z_all, z_std, pts
 
 
+def composite_hier(raw_alpha, raw_rgb, z_vals, rays_d, far_dist, white_bkgd, N_importance, det, u=None, want_weights=True):
+    """Coarse-pass tail of a single-field render in ONE kernel (star_composite_hier_forward, csrc/ray_fused.cu):
+    raw2outputs (models/rendering__.py:307-379) + z_mid / sample_pdf / sort(cat) / std (:128-144).  No autograd graph
+    (inference; the fine samples are detached in the reference anyway).  Returns the dict
+    rgb, disp, acc, depth, weights, dists, z_samples, z_vals, z_std; weights / dists are None when want_weights=False.
+    Needs an even Nc (the kernel's two-samples-per-lane form): StarError(STAR_E_UNSUPPORTED) otherwise."""
+    raw_alpha, raw_rgb, z_vals, rays_d = _c(raw_alpha.detach()), _c(raw_rgb.detach()), _c(z_vals.detach()), _c(rays_d)
+    R, Nc = raw_alpha.shape
+    dev = raw_alpha.device
+    u_det = None
+    if u is None:
+        if det:
+            u_det = _linspace01(N_importance, dev)
+        else:
+            u = torch.rand((R, N_importance), device=dev)
+    if u is not None:
+        u = _c(u)
+    rgb = torch.empty((R, 3), device=dev)
+    disp, acc, depth, z_std = (torch.empty((R,), device=dev) for _ in range(4))
+    weights = torch.empty((R, Nc), device=dev) if want_weights else None
+    dists = torch.empty((R, Nc), device=dev) if want_weights else None
+    zs = torch.empty((R, N_importance), device=dev)
+    z_all = torch.empty((R, Nc + N_importance), device=dev)
+    check(_capi.lib().star_composite_hier_forward(
+        f32(raw_alpha), f32(raw_rgb), f32(z_vals), f32(rays_d), f32(u) if u is not None else None,
+        f32(u_det) if u_det is not None else None, R, Nc, N_importance, float(far_dist), int(bool(white_bkgd)), f32(rgb),
+        f32(disp), f32(acc), f32(depth), ptr(weights), ptr(dists), f32(zs), f32(z_all), f32(z_std), stream()),
+        "star_composite_hier_forward")
+    _count()
+    return dict(rgb=rgb, disp=disp, acc=acc, depth=depth, weights=weights, dists=dists, z_samples=zs, z_vals=z_all,
+                z_std=z_std)
+
+
 # ------------------------------------------------------------------------------------------ a4 + K2
 def flat_master(params):
     """Flat fp32 master vector of a net: a zero-copy view when its parameters already sit back to back in one storage

@@ -501,6 +501,34 @@ def test_get_rays_kernel_bit_exact(H, W):
     assert_close(vd2, rd_ref[H // 3:H // 3 + H // 2] / rd_ref[H // 3:H // 3 + H // 2].norm(dim=-1, keepdim=True), 2e-7)
 
 
+# ------------------------------------------------------------------------------------------ a6 + a9 + a10 fused
+@pytest.mark.parametrize("R,Nc,Ni,det,white", [(257, 64, 128, True, True), (101, 256, 256, True, False),
+                                               (67, 64, 128, False, True), (33, 20, 24, False, False),
+                                               (19, 6, 5, True, True), (40, 1024, 512, True, False)])
+def test_fused_composite_hierarchical_kernel_equals_the_two_kernels(R, Nc, Ni, det, white):
+    """star_composite_hier_forward (compositing of the coarse samples, CDF, inverse-CDF draw, z_std and merge in one
+    kernel per ray, weights passed through shared memory) against star_composite_single_forward + star_hierarchical:
+    every output bit for bit (sorted u = the eval path, random u = the bitonic path); odd Nc is refused."""
+    g = torch.Generator().manual_seed(R + Nc)
+    raw_a = cu(torch.randn(R, Nc, generator=g) * 3)
+    raw_c = cu(torch.randn(R, Nc, 3, generator=g))
+    z = cu(torch.sort(torch.rand(R, Nc, generator=g) * 4 + 2, dim=-1).values)
+    rd = cu(torch.randn(R, 3, generator=g))
+    ro = torch.zeros_like(rd)
+    u = None if det else cu(torch.rand(R, Ni, generator=g))
+    rgb, disp, acc, depth, w, dists = F_.CompositeSingle.apply(raw_a, raw_c, z, rd, 1e10, white)
+    zs, z_all, z_std, _ = F_.hierarchical(z, w, Ni, det, ro, rd, u=u, want_pts=False)
+    f = F_.composite_hier(raw_a, raw_c, z, rd, 1e10, white, Ni, det, u=u)
+    for k, ref in dict(rgb=rgb, disp=disp, acc=acc, depth=depth, weights=w, dists=dists, z_samples=zs, z_vals=z_all,
+                       z_std=z_std).items():
+        assert torch.equal(f[k], ref), k
+    f2 = F_.composite_hier(raw_a, raw_c, z, rd, 1e10, white, Ni, det, u=u, want_weights=False)
+    assert f2["weights"] is None and torch.equal(f2["z_vals"], z_all) and torch.equal(f2["rgb"], rgb)
+    with pytest.raises(star_b200._capi.StarError):
+        F_.composite_hier(raw_a[:, :-1], raw_c[:, :-1], z[:, :-1], rd, 1e10, white, Ni, det,
+                          u=u)
+
+
 # ------------------------------------------------------------------------------------------ a10 + a11 in one C-ABI call
 @pytest.mark.parametrize("V,prec", [(0, "fp32"), (2, "fp32"), (0, "fp16"), (3, "fp16")])
 def test_single_call_render_equals_the_staged_path(V, prec, monkeypatch):

@@ -42,6 +42,17 @@ with torch.no_grad():
         u = torch.rand(Rr, Ni, device=dev, generator=g)
         ms = timeit(lambda: F_.hierarchical(z, w, Ni, False, o, d, u=u))
         report("hierarchical (random u) R=%d %d+%d" % (Rr, Nc, Ni), ms, Rr * (8 * Nc + 8 * Ni + 16 * (Nc + Ni)))
+        # coarse-pass tail of the single-call render (no positions): the two stand-alone kernels against the fused one
+        ra0 = torch.randn(Rr, Nc, device=dev, generator=g); rc0 = torch.randn(Rr, Nc, 3, device=dev, generator=g)
+        def pair():
+            ww = F_.CompositeSingle.apply(ra0, rc0, z, d, 1e10, True)[4]
+            F_.hierarchical(z, ww, Ni, True, o, d, want_pts=False)
+        ms = timeit(pair)
+        report("composite + hierarchical, 2 kernels R=%d %d+%d" % (Rr, Nc, Ni), ms, Rr * (28 * Nc + 8 * Nc + 4 * Ni + 4 * (Nc + Ni)))
+        ms = timeit(lambda: F_.composite_hier(ra0, rc0, z, d, 1e10, True, Ni, True))
+        report("composite_hier fused R=%d %d+%d" % (Rr, Nc, Ni), ms, Rr * (28 * Nc + 4 * Ni + 4 * (Nc + Ni)))
+        ms = timeit(lambda: F_.composite_hier(ra0, rc0, z, d, 1e10, True, Ni, True, want_weights=False))
+        report("composite_hier fused, no weights/dists out" , ms, Rr * (20 * Nc + 4 * Ni + 4 * (Nc + Ni)))
         zs, zall, zstd, ptsf = F_.hierarchical(z, w, Ni, True, o, d)
         S = Nc + Ni
         ra = torch.randn(Rr, S, device=dev, generator=g); rc = torch.randn(Rr, S, 3, device=dev, generator=g)
