@@ -9,7 +9,10 @@ from star_b200.models import rendering__ as R_
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 dev = "cuda"
 R = int(os.environ.get("R", 160000))
-flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+# The flush also hides the host: the timed call's Python wrapper (allocation + ctypes, 20-40 us) must be enqueued while the
+# flush still runs, or the gap lands inside the event pair -- 256 MB (39 us) was too short for that and inflated every kernel
+# under ~100 us (r1k / r2j figures of sample_pts and composite_single S=64); 2 GB = 0.3 ms.
+flush = torch.empty(int(os.environ.get("FLUSH_MB", 2048)) << 20, dtype=torch.uint8, device=dev)
 
 def timeit(fn, n=10):
     for _ in range(3): fn()
@@ -62,3 +65,12 @@ with torch.no_grad():
         rad = torch.randn(Rr, V, S, device=dev, generator=g); rcd = torch.randn(Rr, V, S, 3, device=dev, generator=g)
         ms = timeit(lambda: F_.CompositeStar.apply(ra, rc, rad, rcd, zall, d, 1e10, False, 8192, False))
         report("composite_multi_fwd V=5 R=%d S=%d" % (Rr, S), ms, Rr * S * ((1 + V) * 16 + 4 + 4))
+        with torch.enable_grad():
+            leaves = [t.clone().requires_grad_(True) for t in (ra, rc, rad, rcd)]
+            ws = F_.CompositeStar.apply(*leaves, zall, d, 1e10, False, 8192, False)
+            loss = ws[0].sum() + ws[4].sum() + ws[11].sum()      # rgb, weights, the five regularisers
+            def bwd():
+                for t in leaves: t.grad = None
+                loss.backward(retain_graph=True)
+            ms = timeit(bwd)
+        report("composite_multi_bwd (+ autograd glue) V=5 R=%d S=%d" % (Rr, S), ms, Rr * S * ((1 + V) * 32 + 4 + 4))
