@@ -8,7 +8,7 @@
 
 
 // =========================================================================== single field forward
-__global__ void composite_single_fwd_kernel(const float* __restrict__ raw_alpha, const float* __restrict__ raw_rgb,
+__global__ void __launch_bounds__(128, 16) composite_single_fwd_kernel(const float* __restrict__ raw_alpha, const float* __restrict__ raw_rgb,
                                             const float* __restrict__ z_vals, const float* __restrict__ rays_d,
                                             int R, int S, float far_dist, int white_bkgd, float* __restrict__ rgb_o,
                                             float* __restrict__ disp_o, float* __restrict__ acc_o,
@@ -58,7 +58,7 @@ __global__ void composite_single_fwd_kernel(const float* __restrict__ raw_alpha,
 }
 
 // Even S: every lane owns two consecutive samples (composite_single_ray_x2, ray_device.cuh).
-__global__ void composite_single_fwd_x2_kernel(const float* __restrict__ raw_alpha, const float* __restrict__ raw_rgb,
+__global__ void __launch_bounds__(128, 16) composite_single_fwd_x2_kernel(const float* __restrict__ raw_alpha, const float* __restrict__ raw_rgb,
                                                const float* __restrict__ z_vals, const float* __restrict__ rays_d,
                                                int R, int S, float far_dist, int white_bkgd,
                                                float* __restrict__ rgb_o, float* __restrict__ disp_o,
@@ -180,12 +180,16 @@ __device__ __forceinline__ float chunk_inv_count(int r, int R, int chunk) {
   return 1.f / (float)n;
 }
 
+#ifndef STAR_MULTI_FWD_MINBLOCKS
+#define STAR_MULTI_FWD_MINBLOCKS 4      // 128 registers: 16 warps per SM instead of 12 (V = 5: 36 bytes of spills)
+#endif
 template <int VT>
-__global__ void __launch_bounds__(128) composite_multi_fwd_kernel(const float* __restrict__ raw_alpha_s, const float* __restrict__ raw_rgb_s,
+__global__ void __launch_bounds__(128, STAR_MULTI_FWD_MINBLOCKS) composite_multi_fwd_kernel(const float* __restrict__ raw_alpha_s, const float* __restrict__ raw_rgb_s,
                                            const float* __restrict__ raw_alpha_d, const float* __restrict__ raw_rgb_d,
                                            const float* __restrict__ z_vals, const float* __restrict__ rays_d, int R,
-                                           int V, int S, float far_dist, int white_bkgd, int chunk, StarMultiOut out,
+                                           int /*V == VT*/, int S, float far_dist, int white_bkgd, int chunk, StarMultiOut out,
                                            float* __restrict__ reg_partial) {
+  constexpr int V = VT;     // one instantiation per object count: the per-object loops and the index arithmetic are static
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float reg_acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   for (int r = blockIdx.x * wpb + warp; r < R; r += gridDim.x * wpb) {

@@ -38,8 +38,9 @@ struct BwdPhase {
 #define BWD_MAX_PHASES 24
 
 struct BwdSmem {
-  uint32_t A, W, small, tab, bars, tmem_ptr, total;
+  uint32_t A, W, small, tab, bars, tmem_ptr, pacc, total;
 };
+#define BWD_PACC_FLOATS 32      // per epilogue warp: [0, 15) translation / rotation sums of the positions, [16, 28) of the directions
 __host__ __device__ static inline BwdSmem bwd_smem_layout(uint32_t small_bytes) {
   BwdSmem s;
   uint32_t o = 0;
@@ -49,8 +50,25 @@ __host__ __device__ static inline BwdSmem bwd_smem_layout(uint32_t small_bytes) 
   s.tab = o; o += BWD_MAX_STAGES * sizeof(BwdStage) + BWD_MAX_PHASES * sizeof(BwdPhase) + 16;
   s.bars = o; o += 40 * 8;
   s.tmem_ptr = o; o += 16;
+  s.pacc = o; o += TC_EPI_WARPS * BWD_PACC_FLOATS * sizeof(float);
   s.total = o + 1024;
   return s;
+}
+
+// Sums 16 per-lane values across the warp with 16 shuffles (each butterfly step halves the values a lane carries): the
+// lane pair (2 i, 2 i + 1) returns the total of v[i].
+__device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+  float a[8], b[4], c[2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = (h16 ? v[8 + i] : v[i]) + __shfl_xor_sync(STAR_FULL_MASK, h16 ? v[i] : v[8 + i], 16);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) b[i] = (h8 ? a[4 + i] : a[i]) + __shfl_xor_sync(STAR_FULL_MASK, h8 ? a[i] : a[4 + i], 8);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) c[i] = (h4 ? b[2 + i] : b[i]) + __shfl_xor_sync(STAR_FULL_MASK, h4 ? b[i] : b[2 + i], 4);
+  float d = (h2 ? c[1] : c[0]) + __shfl_xor_sync(STAR_FULL_MASK, h2 ? c[0] : c[1], 2);
+  d += __shfl_xor_sync(STAR_FULL_MASK, d, 1);
+  return d;
 }
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -169,6 +187,9 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (M + TC_M - 1) / TC_M;
   constexpr bool has_pose = POSE;   // object nets: pose accumulators and two extra GEMMs (compiled out for the static net)
+  // accumulator chunk loads in flight per epilogue thread: the second buffer (measured neutral on the static net) would push
+  // the object nets' epilogue past the 96 registers 576 threads leave, into spills inside the chunk loop
+  constexpr int LD_DEPTH = POSE ? 1 : TC_DX_LD_DEPTH;
 
   // ---- the per-tile program (identical for every tile): built once by one thread
   if (tid == 0) {
@@ -322,29 +343,21 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     const int row = q * 32 + lane;
     const uint32_t lane_addr = ((uint32_t)(q * 32)) << 16;
     uint32_t acc_par = 0, stash_par = 0;
-    float pacc[POSE ? 27 : 1];
-#pragma unroll
-    for (int i = 0; i < (POSE ? 27 : 1); ++i) pacc[i] = 0.f;
+    // Pose sums: reduced over the warp once per tile and kept per WARP in shared memory.  (27 per-thread running sums plus the
+    // transformed point / direction kept live across the tile cost this kernel 560 bytes of spills in its chunk loops, and an
+    // object net's dX chain -- 8 GEMM groups -- took as long as the static net's 12: profiles/r2m_c4_launches.md.)
+    float* s_pacc = reinterpret_cast<float*>(gbase + sl.pacc) + warp * BWD_PACC_FLOATS;
+    if (has_pose) s_pacc[lane] = 0.f;
     const float gscale = F16 ? grad_scale_of(absmax) : 1.f;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t gi = tile * TC_M + row;
       const bool valid = gi < M;
       float da = 0.f, dc0 = 0.f, dc1 = 0.f, dc2 = 0.f;
-      float pw[3] = {0.f, 0.f, 0.f}, po[3] = {0.f, 0.f, 0.f}, dw[3] = {0.f, 0.f, 0.f}, dob[3] = {0.f, 0.f, 0.f};
       if (valid) {
-        const int64_t r = gi / S;
-        const int64_t o = r * ray_stride + (gi - r * S);
+        const int64_t ray = gi / S;
+        const int64_t o = ray * ray_stride + (gi - ray * S);
         da = d_raw_alpha[o] * gscale;         // (exact: a power of two)
         dc0 = d_raw_rgb[o * 3 + 0] * gscale; dc1 = d_raw_rgb[o * 3 + 1] * gscale; dc2 = d_raw_rgb[o * 3 + 2] * gscale;
-        if (has_pose) {
-          star_load_pt(pts, gi, r, pw[0], pw[1], pw[2]);
-          dw[0] = viewdirs[r * 3 + 0]; dw[1] = viewdirs[r * 3 + 1]; dw[2] = viewdirs[r * 3 + 2];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            po[i] = pose12[i * 3 + 0] * pw[0] + pose12[i * 3 + 1] * pw[1] + pose12[i * 3 + 2] * pw[2] + pose12[9 + i];
-            dob[i] = pose12[i * 3 + 0] * dw[0] + pose12[i * 3 + 1] * dw[1] + pose12[i * 3 + 2] * dw[2];
-          }
-        }
       }
       const uint8_t* st_tile = stash + (size_t)tile * (size_t)lay.stash_blocks * TC_BLOCK_BYTES;
       uint8_t* gs_tile = gstash + (size_t)tile * (size_t)lay.gstash_blocks * TC_BLOCK_BYTES;
@@ -382,26 +395,37 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         }
         const uint32_t tX = tmem_base + lane_addr + (uint32_t)(cg * TC_CPT);
         const uint32_t tT = tX + 256u;
-        if (P.kind == BK_IN) {       // d enc_xyz in T[0:64]: 16 columns per thread
+        if (has_pose && P.kind == BK_IN) {       // d enc_xyz in T[0:64]: 16 columns per thread
           uint32_t r[16];
           tmem_ld16(tT, r);
           tmem_wait_ld();
+          // the sample's position and its image in the object frame are formed here, where they are used (not kept live
+          // across the tile's phases)
+          float pw[3] = {0.f, 0.f, 0.f}, po[3] = {0.f, 0.f, 0.f};
+          if (valid) {
+            star_load_pt(pts, gi, gi / S, pw[0], pw[1], pw[2]);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+              po[i] = pose12[i * 3 + 0] * pw[0] + pose12[i * 3 + 1] * pw[1] + pose12[i * 3 + 2] * pw[2] + pose12[9 + i];
+          }
           float g[3] = {0.f, 0.f, 0.f};
           if (cg == 0) fold_jacobian<0, 63>(r, po, sc_xyz, g);
           else if (cg == 1) fold_jacobian<16, 63>(r, po, sc_xyz, g);
           else if (cg == 2) fold_jacobian<32, 63>(r, po, sc_xyz, g);
           else fold_jacobian<48, 63>(r, po, sc_xyz, g);
-          if (valid) {
+          float c[16];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              pacc[i] += g[i];
+          for (int i = 0; i < 3; ++i) {
+            c[i] = valid ? g[i] : 0.f;
 #pragma unroll
-              for (int j = 0; j < 3; ++j) pacc[3 + i * 3 + j] += g[i] * pw[j];
-            }
-            pacc[12] += po[1] * g[2] - po[2] * g[1];
-            pacc[13] += po[2] * g[0] - po[0] * g[2];
-            pacc[14] += po[0] * g[1] - po[1] * g[0];
+            for (int j = 0; j < 3; ++j) c[3 + i * 3 + j] = valid ? g[i] * pw[j] : 0.f;
           }
+          c[12] = valid ? po[1] * g[2] - po[2] * g[1] : 0.f;
+          c[13] = valid ? po[2] * g[0] - po[0] * g[2] : 0.f;
+          c[14] = valid ? po[0] * g[1] - po[1] * g[0] : 0.f;
+          c[15] = 0.f;
+          const float tot = warp_reduce16(c, lane);
+          if ((lane & 1) == 0) s_pacc[lane >> 1] += tot;
           tc_fence_before();
           continue;
         }
@@ -409,18 +433,27 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           uint32_t r[16];
           tmem_ld16(tX, r);
           tmem_wait_ld();
+          float dw[3] = {0.f, 0.f, 0.f}, dob[3] = {0.f, 0.f, 0.f};
+          if (valid) {
+            const int64_t ray = gi / S;
+            dw[0] = viewdirs[ray * 3 + 0]; dw[1] = viewdirs[ray * 3 + 1]; dw[2] = viewdirs[ray * 3 + 2];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) dob[i] = pose12[i * 3 + 0] * dw[0] + pose12[i * 3 + 1] * dw[1] + pose12[i * 3 + 2] * dw[2];
+          }
           float h[3] = {0.f, 0.f, 0.f};
           if (cg == 0) fold_jacobian<0, 27>(r, dob, sc_dir, h);
           else fold_jacobian<16, 27>(r, dob, sc_dir, h);
-          if (valid) {
+          float c[16];
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
+          for (int i = 0; i < 3; ++i)
 #pragma unroll
-              for (int j = 0; j < 3; ++j) pacc[15 + i * 3 + j] += h[i] * dw[j];
-            pacc[24] += dob[1] * h[2] - dob[2] * h[1];
-            pacc[25] += dob[2] * h[0] - dob[0] * h[2];
-            pacc[26] += dob[0] * h[1] - dob[1] * h[0];
-          }
+            for (int j = 0; j < 3; ++j) c[i * 3 + j] = valid ? h[i] * dw[j] : 0.f;
+          c[9] = valid ? dob[1] * h[2] - dob[2] * h[1] : 0.f;
+          c[10] = valid ? dob[2] * h[0] - dob[0] * h[2] : 0.f;
+          c[11] = valid ? dob[0] * h[1] - dob[1] * h[0] : 0.f;
+          c[12] = c[13] = c[14] = c[15] = 0.f;
+          const float tot = warp_reduce16(c, lane);
+          if ((lane & 1) == 0) s_pacc[16 + (lane >> 1)] += tot;
         }
         // publish one 16-column chunk of this phase's output: zero rows beyond the launch, 16-bit conversion into A block kb
         // (fp16: saturating -- a gradient that outgrows the headroom clamps to 65504 instead of becoming inf), proxy fence,
@@ -461,15 +494,15 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         // gradient's chunk kb then, and waits for both before the add)
         const uint32_t t_acc = (P.kind == BK_OUT) ? tX : tT;
         uint32_t racc[2][16];
-        if (TC_DX_LD_DEPTH >= 2) tmem_ld16(t_acc, racc[0]);
+        if (LD_DEPTH >= 2) tmem_ld16(t_acc, racc[0]);
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
           if (kb >= P.nch) break;
           const int col0 = kb * 64 + cg * TC_CPT;
           const uint32_t mb16 = ((kb < 2 ? mbits.x : mbits.y) >> ((kb & 1) * 16)) & 0xffffu;
-          if (TC_DX_LD_DEPTH < 2) tmem_ld16(t_acc + 64u * (uint32_t)kb, racc[kb & 1]);
+          if (LD_DEPTH < 2) tmem_ld16(t_acc + 64u * (uint32_t)kb, racc[kb & 1]);
           tmem_wait_ld();            // (all of this thread's outstanding loads: chunk kb)
-          if (TC_DX_LD_DEPTH >= 2 && kb + 1 < P.nch) tmem_ld16(t_acc + 64u * (uint32_t)(kb + 1), racc[(kb + 1) & 1]);
+          if (LD_DEPTH >= 2 && kb + 1 < P.nch) tmem_ld16(t_acc + 64u * (uint32_t)(kb + 1), racc[(kb + 1) & 1]);
           uint32_t rx[16];
           if (P.kind == BK_FC0) tmem_ld16(tX + 64u * (uint32_t)kb, rx);
           float v[16];
@@ -502,11 +535,8 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     }
     if (has_pose) {
       const float inv = 1.f / gscale;
-#pragma unroll
-      for (int i = 0; i < 27; ++i) {
-        const float s = warp_sum(pacc[i]);
-        if (lane == 0) atomicAdd(&pose_acc[i], s * inv);
-      }
+      __syncwarp();
+      if (lane < 27) atomicAdd(&pose_acc[lane], s_pacc[lane < 15 ? lane : lane + 1] * inv);
     }
   }
 

@@ -106,18 +106,25 @@ __device__ __forceinline__ double warp_scan_sum_d(double v, int lane) {
 // expf/log1pf/IEEE division they are issue-bound at ~1/3 of it, so they use the SFU approximations (ex2.approx /
 // lg2.approx / rcp.approx: relative error <= ~2^-21 for the arguments that occur) -- two orders of magnitude inside
 // the 1e-4 absolute parity bar.  Nothing here feeds an index decision (sample_pdf has its own defined arithmetic).
-__device__ __forceinline__ float fexp(float x) { return __expf(x); }
-__device__ __forceinline__ float flog(float x) { return __logf(x); }
-__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+// The .ftz forms: without them every ex2 / lg2 / rcp carries a denormal fix-up (FSETP + two or three FMUL: 40 % of the
+// multi-field kernel's instructions, profiles/r2k_composite_multi.md).  Flushing only changes values below 2^-126: an
+// exp() that underflows gives 0 instead of a denormal (alpha = 1 - exp is the same float either way), a density below
+// 1e-38 counts as 0.
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fexp(float x) { return ex2_ftz(x * 1.4426950408889634f); }
+__device__ __forceinline__ float flog(float x) { return lg2_ftz(x) * 0.6931471805599453f; }
+__device__ __forceinline__ float fdiv(float a, float b) { return a * rcp_ftz(b); }
 // log(1 - c) for c in [eps, 1-eps]; lg2.approx has an ABSOLUTE error of ~2^-22 near 1, so small c takes the series
-__device__ __forceinline__ float flog1m(float c) { return c < 1e-3f ? -c * (1.f + 0.5f * c) : __logf(1.f - c); }
+__device__ __forceinline__ float flog1m(float c) { return c < 1e-3f ? -c * (1.f + 0.5f * c) : flog(1.f - c); }
 // torch.nn.functional.softplus (beta=1, threshold=20).  Below -8 the series e - e^2/2 keeps the RELATIVE accuracy of
 // tiny densities (they are multiplied by far_dist = 1e10 at the last sample, rendering__.py:321).
 __device__ __forceinline__ float softplus_f(float x) {
   if (x > 20.f) return x;
-  const float e = __expf(x);
-  return x < -8.f ? e * (1.f - 0.5f * e) : __logf(1.f + e);
+  const float e = fexp(x);
+  return x < -8.f ? e * (1.f - 0.5f * e) : flog(1.f + e);
 }
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_ftz(1.f + fexp(-x)); }
 // d softplus / dx with torch's threshold semantics
 __device__ __forceinline__ float softplus_grad_f(float x) { return x > 20.f ? 1.f : sigmoid_f(x); }
