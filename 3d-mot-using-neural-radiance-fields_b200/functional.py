@@ -687,8 +687,10 @@ def render_forward(static_nets, dynamic_nets, precision, rays_o, rays_d, viewdir
     n_samp = R * (Nc + (Nf if Ni > 0 else 0))
     _prof_end("render_forward", e0, n_samp, 2.0 * mac * n_samp)
     passes = 2 if Ni > 0 else 1
+    # single field, <= 128 (even) coarse samples, fine samples drawn by the call: compositing + hierarchical are one kernel
+    fused_tail = V == 0 and Ni > 0 and z_samples is None and Nc % 2 == 0 and 4 <= Nc <= 128
     _count(passes * (1 + V + (2 if V else 1)) + (1 if Ni > 0 else 0) + (1 if z_vals is None else 0)
-           + (1 if (camera is not None or viewdirs is None) else 0))
+           + (1 if (camera is not None or viewdirs is None) else 0) - (1 if fused_tail else 0))
     del keep
 
     def to_dict(o, z, dists, sfx):
