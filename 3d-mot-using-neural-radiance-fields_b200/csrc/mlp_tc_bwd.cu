@@ -160,6 +160,9 @@ __global__ void grad_absmax_kernel(const float* __restrict__ d_alpha, const floa
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(absmax), __float_as_uint(m));
 }
 
+#ifndef TC_DX_DEFER_WAIT_ST
+#define TC_DX_DEFER_WAIT_ST 0  // 1: one tcgen05.wait::st per phase instead of one per chunk (A/B: profiles/r2q)
+#endif
 #ifndef TC_DX_LD_DEPTH
 #define TC_DX_LD_DEPTH 2       // accumulator chunk loads in flight per epilogue thread of the dX chain (1 = load, wait, use)
 #endif
@@ -527,7 +530,9 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
 #pragma unroll
             for (int j = 0; j < 16; ++j) rx[j] = __float_as_uint(v[j]);
             tmem_st16(tX + 64u * (uint32_t)kb, rx);
-            tmem_wait_st();
+            // the residual gradient is next touched (by this thread, or by the next tile's MMAs after this phase's last
+            // arrival) after the phase: one wait for the phase's stores, before its last block is published
+            if (!TC_DX_DEFER_WAIT_ST || kb == P.nch - 1) tmem_wait_st();
           }
           publish(kb, v);
         }
