@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="render", choices=["render", "train"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2: lego vanilla NeRF (the headline, BASELINE.json configs[1]); c4: carla_star_online_multi "
                          "(static + 5 objects, 256+256 samples, 7-vector poses); c5: carla_star_app_init_mip (mip-NeRF "
                          "fields, 256+512 frustums).  c4 / c5 are extra measurements; the driver runs c2.")
@@ -292,6 +292,13 @@ def workload_config(args, precision):
                                      if args.mode == "train" else "eval render"))
         return {"workload": wl, "N_samples": 256, "N_importance": 256, "num_vehicles": 5, "mlp_precision": precision,
                 "parallelism": "ray-sharded x%d" % args.gpus, "l2": "L2 flushed between timed iterations (256 MB write)"}
+    if wk == "c3":
+        R = args.rays or (4096 if args.mode == "train" else 65536)
+        wl = ("C3 carla_star_app_init: static + 1 rigid object net, appearance initialisation (static nets on the path), "
+              "coarse+fine 256+256, ray chunk 5000, %d CARLA-shaped rays/step/GPU, %s" % (
+                  R, "training step (fwd+bwd, img2mse(rgb0) + img2mse(rgb))" if args.mode == "train" else "eval render"))
+        return {"workload": wl, "N_samples": 256, "N_importance": 256, "num_vehicles": 1, "mlp_precision": precision,
+                "parallelism": "ray-sharded x%d" % args.gpus, "l2": "L2 flushed between timed iterations (256 MB write)"}
     if wk == "c5":
         R = args.rays or 16384
         wl = ("C5 carla_star_app_init_mip: mip-NeRF field (IPE), 256+512 frustums, %d CARLA-shaped rays/step/GPU, %s" % (
@@ -356,6 +363,43 @@ def build_workload(args, dev, rank, world):
             with torch.no_grad():
                 pts, z = R_.sample_pts(ro, rd, NEAR, FAR, NC, perturb=0, is_train=False)
                 out = R_.render_star_appinit(net, pts, vd, z, ro, rd, NI)
+            return out
+        return net, ro_h, rd_h, step_device, params
+
+    if wk == "c3":
+        # configs/carla_star_app_init.txt: num_vehicles = 1, 256 + 256 samples, chunk = 5000; train_app_init__.py:60-77
+        Nc = Ni = 256
+        R = args.rays or (4096 if train else 65536)
+        ro_h, rd_h = so.carla_rays(R, seed=30 + rank)
+        g = torch.Generator().manual_seed(300 + rank)
+        target = torch.rand(R, 3, generator=g).to(dev)
+        net = star_b200.STaR(ref_harness.make_args(num_vehicles=1, N_importance=Ni, chunk=5000, white_bkgd=False))
+        net.load_state_dict(so.init_star_params(1, Ni, seed=0, bias_std=0.02))
+        net.to(dev)
+        net.set_precision(args.precision)
+        net.train(train)
+        params = [p for p in net.parameters()]
+        u = torch.rand(R, Ni, generator=g).to(dev) if train else None
+        sync = star_b200.parallel.GradSync(net) if (train and world > 1) else None
+
+        def step_device(ro, rd):
+            vd = rd / rd.norm(dim=-1, keepdim=True)
+            if train:
+                if sync is None:
+                    for p in params:
+                        p.grad = None
+                pts, z = R_.sample_pts(ro, rd, 0.03, 0.8, Nc, perturb=0, is_train=True)
+                out = R_.render_star_appinit(net, pts, vd, z, ro, rd, Ni, u=u)
+                loss = L_.photometric_loss(out["rgb0"], out["rgb"], target)[0]
+                if sync is not None:
+                    sync.scale_loss(loss).backward()
+                    sync.finish()
+                else:
+                    loss.backward()
+                return loss
+            with torch.no_grad():
+                pts, z = R_.sample_pts(ro, rd, 0.03, 0.8, Nc, perturb=0, is_train=False)
+                out = R_.render_star_appinit(net, pts, vd, z, ro, rd, Ni)
             return out
         return net, ro_h, rd_h, step_device, params
 
@@ -465,7 +509,8 @@ def run_b200(args):
     if args.mode == "render" and args.workload == "c2" and not args.no_extras and not args.no_train_extra:
         # the other configurations BASELINE.json names, as sub-records of the same line (weak scaling like the headline:
         # every rank its own rays): C4 = static + 5 objects with pose gradients, C5 = mip field
-        for name, wk, mode, rays in (("c4_train", "c4", "train", 8192), ("c4_train_r1000", "c4", "train", 1000),
+        for name, wk, mode, rays in (("c3_train", "c3", "train", 4096), ("c3_train_r1000", "c3", "train", 1000),
+                                     ("c4_train", "c4", "train", 8192), ("c4_train_r1000", "c4", "train", 1000),
                                      ("c4_render", "c4", "render", 65536), ("c5_render", "c5", "render", 16384),
                                      ("c5_train", "c5", "train", 4096)):
             a3 = argparse.Namespace(**vars(args))

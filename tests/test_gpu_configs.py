@@ -5,6 +5,10 @@ view against the CPU oracle (fp32 tier: coarse keys tight, fine keys through the
 C2 (configs[1]) at full size (800x800, the 16-bit tensor-core tier the bench reports): size-independent properties --
 finiteness and ranges, weights summing to acc, invariance to how the rays are split over launches, sortedness of the
 merged samples -- and 4096 rays of the view against the fp32 CPU oracle within the north star's 2e-3 / 0.05 dB.
+C3 (configs[2], carla_star_app_init: static + 1 rigid object, appearance initialisation) at the reference's batch
+size R = 1000, 256 + 256 samples, ray chunk 5000: the app-init training step (only the static nets are on the path,
+star__.py:142-152) against the oracle on both tiers, the object nets left without gradients as in the reference, and
+a 12 000-ray eval render (3 ray chunks) for the chunk-split invariance.
 C4 (configs[3], carla_star_online_multi: static + V = 5 objects, 256 + 256 samples, 7-vector poses) at the reference's
 batch size R = 1000: the training step against the oracle, teacher forced, with weight and pose gradients; and at
 R = 8192 (one chunk) the size-independent properties on the tensor-core tier.
@@ -105,6 +109,111 @@ def test_c2_full_size_render_fp16_tier_properties_and_oracle_parity():
     for k in ("rgb0", "rgb"):
         assert abs(psnr_db(forced[k].cpu(), target) - psnr_db(ref[k], target)) <= 0.05, k
     assert psnr_db(forced["rgb"].cpu(), ref["rgb"]) > 60.0
+
+
+# ------------------------------------------------------------------------------------------ C3
+def _c3_net(precision, training, seed=4):
+    V, Ni = 1, 256
+    net = star_b200.STaR(ref_harness.make_args(num_vehicles=V, N_importance=Ni, chunk=5000, white_bkgd=False))
+    sd = so.init_star_params(V, Ni, seed=seed, bias_std=0.02)
+    net.load_state_dict(sd)
+    net.to(DEV).train(training)
+    net.set_precision(precision)
+    return net, sd
+
+
+def test_c3_app_init_reference_batch_training_step_against_the_oracle():
+    """configs/carla_star_app_init.txt:13,24-25,29,44 (num_vehicles = 1, 256 + 256 samples, chunk 5000, N_rand = 1000) through
+    train_app_init__.py:70-77 (loss = img2mse(rgb0) + img2mse(rgb)): forward keys, loss and the gradients of the two static
+    nets against the oracle, fine pass on the oracle's own samples; the object nets are not on the app-init path
+    (star__.py:142-152) and must stay without gradients.  fp32 tier at 1e-4, then the benched fp16 tier at 2e-3 / 0.05 dB."""
+    V, Nc, Ni, R = 1, 256, 256, 1000
+    net, sd = _c3_net("fp32", True)
+    ro, rd = so.carla_rays(R, seed=21)
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    g = torch.Generator().manual_seed(6)
+    u, target = torch.rand(R, Ni, generator=g), torch.rand(R, 3, generator=g)
+
+    def total_loss(out):
+        t = target.to(out["rgb"].device)
+        return ((out["rgb0"] - t) ** 2).mean() + ((out["rgb"] - t) ** 2).mean()
+
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    cfg = so.StarConfig(V, Ni, 5000)
+    pts, z = so.sample_pts(ro, rd, 0.03, 0.8, Nc)
+    with torch.no_grad():
+        coarse = so.star_forward(p, cfg, pts, vd, z, rd, None, True, None, True)
+        mid = 0.5 * (z[..., 1:] + z[..., :-1])
+        zs = so.sample_pdf(mid, coarse["weights"][..., 1:-1], Ni, u=u, exact_sum=True)
+    ref = so.render_star(p, cfg, pts, vd, z, ro, rd, Ni, pose=None, training=True, u=u, z_samples=zs)
+    loss_ref = total_loss(ref)
+    loss_ref.backward()
+
+    c = lambda t: t.to(DEV)
+    rel = lambda a, b: float((a.detach().cpu() - b).norm() / (b.norm() + 1e-30))
+    for tier, tol, gtol in (("fp32", 1e-4, 2e-2), ("fp16", 2e-3, 5e-2)):
+        net.set_precision(tier)
+        for q in net.parameters():
+            q.grad = None
+        pts_g, z_g = R_.sample_pts(c(ro), c(rd), 0.03, 0.8, Nc)
+        assert torch.equal(z_g.cpu(), z)
+        out = R_.render_star_appinit(net, pts_g, c(vd), z_g, c(ro), c(rd), Ni, u=c(u), z_samples=c(zs))
+        loss = total_loss(out)
+        loss.backward()
+        F_.check_range()
+        assert set(k for k, v in ref.items() if v is not None) <= set(out.keys())
+        for k, v in ref.items():
+            if v is None:
+                continue
+            if k.startswith("disp"):       # 1 / depth: relative; the 16-bit tier's bound is stated for rgb / depth / weights
+                if tier == "fp32":
+                    assert_close(out[k], v, tol, rtol=tol, msg="%s %s" % (tier, k))
+            elif k.startswith("depth") or k == "z_std" or k.startswith("z_vals") or k.startswith("dists"):
+                assert_close(out[k], v, tol, rtol=1e-4, msg="%s %s" % (tier, k))
+            else:
+                assert_close(out[k], v, tol, msg="%s %s" % (tier, k))
+        assert_close(loss, loss_ref, tol, rtol=tol, msg=tier + " loss")
+        for k in ("rgb0", "rgb"):
+            assert abs(psnr_db(out[k].detach().cpu(), target) - psnr_db(ref[k].detach(), target)) <= 0.05, (tier, k)
+        seen = 0
+        for name, q in net.named_parameters():
+            gref = p[name].grad
+            if "dynamic" in name:
+                assert gref is None and q.grad is None, name       # the reference leaves them untouched; so does the port
+                continue
+            if gref is None or float(gref.norm()) == 0.0:
+                continue
+            seen += 1
+            assert rel(q.grad, gref) < gtol, (tier, name, rel(q.grad, gref))
+        assert seen >= 40, seen
+
+
+def test_c3_eval_render_over_three_ray_chunks_on_the_tensor_core_tier():
+    """12 000 rays with chunk = 5000 (configs/carla_star_app_init.txt:29): chunks of 5000 / 5000 / 2000 rays concatenated as
+    star__.py:100-117 does; per-ray results must not depend on the chunk a ray fell in."""
+    Nc, Ni, R = 256, 256, 12000
+    net, _ = _c3_net("fp16", False)
+    ro, rd = so.carla_rays(R, seed=22)
+    ro, rd = ro.to(DEV), rd.to(DEV)
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    with torch.no_grad():
+        pts, z = R_.sample_pts(ro, rd, 0.03, 0.8, Nc, is_train=False)
+        out = R_.render_star_appinit(net, pts, vd, z, ro, rd, Ni)
+        F_.check_range()
+        assert out["rgb"].shape == (R, 3) and out["weights"].shape == (R, Nc + Ni) and out["z_std"].shape == (R,)
+        for k, v in out.items():
+            if v is not None:
+                assert bool(torch.isfinite(v).all()), k
+        assert_close(out["weights"].sum(-1), out["acc"], 5e-5, msg="sum(weights) == acc")
+        assert bool((out["z_vals"][:, 1:] >= out["z_vals"][:, :-1]).all())
+        idx = torch.arange(4000, 11000, 7, device=DEV)             # straddles both chunk boundaries
+        sub = R_.render_star_appinit(net, pts[idx], vd[idx], z[idx], ro[idx], rd[idx], Ni)
+        for k in ("rgb", "depth", "weights", "rgb0", "z_vals"):
+            assert torch.equal(sub[k], out[k][idx]), k
+        net.set_precision("fp32")
+        ref = R_.render_star_appinit(net, pts[idx], vd[idx], z[idx], ro[idx], rd[idx], Ni)
+        assert float((sub["rgb0"] - ref["rgb0"]).abs().max()) <= 2e-3
+        assert float((sub["weights0"] - ref["weights0"]).abs().max()) <= 2e-3
 
 
 # ------------------------------------------------------------------------------------------ C4
