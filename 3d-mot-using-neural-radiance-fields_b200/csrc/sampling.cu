@@ -37,12 +37,18 @@ __global__ void sample_pts_kernel(const float* __restrict__ rays_o, const float*
   }
 }
 
-// Nc % 4 == 0: one thread per four consecutive samples of a ray -- 16-byte stores of z and of the 12 pts floats,
-// 32-bit index arithmetic.  Same per-element arithmetic as above.
-__global__ void sample_pts_x4_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+// Nc % 4 == 0: one thread per four consecutive samples of a ray (one quad per thread, the grid covers all quads), 32-bit
+// index arithmetic, same per-element arithmetic as above.  z leaves as one 16-byte store per thread.  The 12 position
+// floats of a quad are 48 contiguous bytes: stored straight from the thread, a warp's three store instructions each touch
+// 48 sectors half-way (16 of every 48 bytes) and the kernel ran at 0.53 of the HBM peak; staged through shared memory every
+// warp store covers 512 contiguous bytes: 0.82 (profiles/r2s_ab_sample_pts.txt).
+#define SP_THREADS 256
+__global__ void __launch_bounds__(SP_THREADS) sample_pts_x4_kernel(const float* __restrict__ rays_o,
+                                     const float* __restrict__ rays_d,
                                      const float* __restrict__ t_vals, const float* __restrict__ t_rand,
                                      float near_, float far_, int R, int Nc, int lindisp,
                                      float* __restrict__ pts, float* __restrict__ z_vals) {
+  __shared__ float4 stage[3 * SP_THREADS];
   const uint32_t Q = (uint32_t)Nc >> 2;
   const uint32_t total = (uint32_t)R * Q;
   auto zval = [&](int k) -> float {
@@ -52,7 +58,8 @@ __global__ void sample_pts_x4_kernel(const float* __restrict__ rays_o, const flo
     const float b = __fmul_rn(__fdiv_rn(1.f, far_), t);
     return __fdiv_rn(1.f, __fadd_rn(a, b));
   };
-  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+  const uint32_t q0 = blockIdx.x * SP_THREADS, q = q0 + threadIdx.x;
+  if (q < total) {
     const uint32_t r = q / Q, s0 = (q - r * Q) * 4u;
     float z[4];
 #pragma unroll
@@ -74,20 +81,29 @@ __global__ void sample_pts_x4_kernel(const float* __restrict__ rays_o, const flo
       for (int j = 0; j < 4; ++j) z[j] = zj[j];
     }
     __stcs(reinterpret_cast<float4*>(z_vals + (size_t)q * 4), make_float4(z[0], z[1], z[2], z[3]));
-    if (pts == nullptr) continue;      // depths only: the MLP kernels form the positions themselves (StarPtsSrc)
-    const float ox = rays_o[r * 3 + 0], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
-    const float dx = rays_d[r * 3 + 0], dy = rays_d[r * 3 + 1], dz = rays_d[r * 3 + 2];
-    float p[12];
+    if (pts != nullptr) {
+      const float ox = rays_o[r * 3 + 0], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
+      const float dx = rays_d[r * 3 + 0], dy = rays_d[r * 3 + 1], dz = rays_d[r * 3 + 2];
+      float p[12];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      p[3 * j + 0] = __fadd_rn(ox, __fmul_rn(dx, z[j]));
-      p[3 * j + 1] = __fadd_rn(oy, __fmul_rn(dy, z[j]));
-      p[3 * j + 2] = __fadd_rn(oz, __fmul_rn(dz, z[j]));
+      for (int j = 0; j < 4; ++j) {
+        p[3 * j + 0] = __fadd_rn(ox, __fmul_rn(dx, z[j]));
+        p[3 * j + 1] = __fadd_rn(oy, __fmul_rn(dy, z[j]));
+        p[3 * j + 2] = __fadd_rn(oz, __fmul_rn(dz, z[j]));
+      }
+      stage[3 * threadIdx.x + 0] = make_float4(p[0], p[1], p[2], p[3]);
+      stage[3 * threadIdx.x + 1] = make_float4(p[4], p[5], p[6], p[7]);
+      stage[3 * threadIdx.x + 2] = make_float4(p[8], p[9], p[10], p[11]);
     }
-    float4* po = reinterpret_cast<float4*>(pts + (size_t)q * 12);
-    __stcs(po + 0, make_float4(p[0], p[1], p[2], p[3]));
-    __stcs(po + 1, make_float4(p[4], p[5], p[6], p[7]));
-    __stcs(po + 2, make_float4(p[8], p[9], p[10], p[11]));
+  }
+  if (pts == nullptr) return;          // depths only: the MLP kernels form the positions themselves (StarPtsSrc)
+  __syncthreads();
+  const uint32_t nq = (total - q0 < (uint32_t)SP_THREADS) ? (total - q0) : (uint32_t)SP_THREADS;
+  float4* po = reinterpret_cast<float4*>(pts + (size_t)q0 * 12);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const uint32_t i = k * SP_THREADS + threadIdx.x;
+    if (i < 3 * nq) __stcs(po + i, stage[i]);
   }
 }
 
@@ -102,9 +118,8 @@ extern "C" int star_sample_pts(const float* rays_o, const float* rays_d, const f
   if ((Nc & 3) == 0 && total / 4 < (int64_t)0x7fffffff &&
       (((uintptr_t)pts | (uintptr_t)z_vals | (uintptr_t)t_rand) & 15) == 0) {
     const int64_t nq = total / 4;
-    const int blocks = (int)((nq + threads - 1) / threads < 148 * 8 ? (nq + threads - 1) / threads : 148 * 8);
-    sample_pts_x4_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(rays_o, rays_d, t_vals, t_rand, near_, far_,
-                                                                        R, Nc, lindisp, pts, z_vals);
+    sample_pts_x4_kernel<<<(unsigned)((nq + SP_THREADS - 1) / SP_THREADS), SP_THREADS, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, t_vals, t_rand, near_, far_, R, Nc, lindisp, pts, z_vals);
     return star_check_launch();
   }
   const int blocks = (int)((total + threads - 1) / threads < 148 * 16 ? (total + threads - 1) / threads : 148 * 16);

@@ -244,6 +244,61 @@ def gpu_eager_baseline(dev, n_rays=65536):
     return res
 
 
+def hbm_kernels(dev, R=160000):
+    """Achieved HBM GB/s of the sampling / compositing kernels of the C2 path (north star: ">= 60 % of HBM peak on the
+    sampling / compositing kernels"), each timed alone: CUDA events, inputs resident in HBM, a 2 GB fill between launches
+    (flushes the 126 MB L2 and keeps the device busy while the host enqueues the timed call).  Bytes = the kernel's
+    algorithmic reads + writes; peak = MEASURED_PEAKS.json hbm_gbs (copy bandwidth).  `R` rays = one
+    chunk of the C2 view."""
+    from star_b200 import functional as F_
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = json.load(open(pk))["hbm_gbs"] if os.path.isfile(pk) else 6650.0
+    flush = torch.empty(2048 << 20, dtype=torch.uint8, device=dev)
+
+    def timeit(fn, n=8):
+        for _ in range(3):
+            fn()
+        ms = 0.0
+        for i in range(n):
+            flush.fill_(i)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+        return ms / n
+
+    res = {"peak": peak, "unit": "GB/s", "peak_source": "MEASURED_PEAKS.json hbm_gbs" if os.path.isfile(pk) else "fallback",
+           "rays": R, "l2": "2 GB fill between launches"}
+
+    def rec(name, ms, nbytes):
+        gbs = nbytes / ms / 1e6
+        res[name] = {"ms": round(ms, 4), "achieved": round(gbs, 1), "frac": round(gbs / peak, 3), "bytes": nbytes}
+    try:
+        g = torch.Generator(device=dev).manual_seed(0)
+        ro = torch.randn(R, 3, device=dev, generator=g)
+        rd = torch.nn.functional.normalize(torch.randn(R, 3, device=dev, generator=g), dim=-1) * 1.1
+        with torch.no_grad():
+            rec("sample_pts_64", timeit(lambda: F_.sample_pts(ro, rd, NEAR, FAR, NC)), R * (24 + 16 * NC))
+            _pts, z = F_.sample_pts(ro, rd, NEAR, FAR, NC)
+            ra = torch.randn(R, NC, device=dev, generator=g)
+            rc = torch.randn(R, NC, 3, device=dev, generator=g)
+            rec("composite_single_fwd_64", timeit(lambda: F_.CompositeSingle.apply(ra, rc, z, rd, 1e10, True)), R * NC * 28)
+            rec("composite_hier_fused_64_128", timeit(lambda: F_.composite_hier(ra, rc, z, rd, 1e10, True, NI, True)),
+                R * (28 * NC + 4 * NI + 4 * (NC + NI)))
+            w = F_.CompositeSingle.apply(ra, rc, z, rd, 1e10, True)[4]
+            _zs, zall, _zstd, _p = F_.hierarchical(z, w, NI, True, ro, rd)
+            S = NC + NI
+            ra = torch.randn(R, S, device=dev, generator=g)
+            rc = torch.randn(R, S, 3, device=dev, generator=g)
+            rec("composite_single_fwd_192", timeit(lambda: F_.CompositeSingle.apply(ra, rc, zall, rd, 1e10, True)), R * S * 28)
+    except Exception as e:       # reported, never fatal
+        res["unavailable"] = "%s: %s" % (type(e).__name__, str(e)[:200])
+    del flush
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -528,6 +583,7 @@ def run_b200(args):
         if rank == 0:
             line["accuracy"] = accuracy_vs_oracle(args, torch.device("cuda", local))
             if world == 1:
+                line["hbm_kernels"] = hbm_kernels(torch.device("cuda", local))
                 line["gpu_eager_baseline"] = gpu_eager_baseline(torch.device("cuda", local))
     if rank == 0:
         print(json.dumps(line), flush=True)
