@@ -1178,6 +1178,120 @@ struct HeadGradCfg {
   int64_t m_aw, m_ab, m_rw, m_rb;   // flat-gradient offsets: density head weight [256], bias; rgb head weight [3][128], bias [3]
 };
 
+// Rows of a tile are taken in two halves of 64 (8 rows per thread and half: 8 + 4 sixteen-byte loads in flight), and the
+// 128-wide relu(h2) is split over BOTH half-warps -- lane ch owns chunk ch & 15 for the rows of parity ch >> 4 -- so that no
+// lane idles through the rgb part: 2 CTAs per SM (<= 128 registers) instead of one at 199 registers with half of every warp
+// masked off in 2/3 of its instructions.
+#ifndef HEAD_GRAD_OLD
+__global__ void __launch_bounds__(256, 2)
+head_grad_tc_kernel(const HeadGradCfg hc, const uint8_t* __restrict__ stash, const float* __restrict__ d_raw_alpha,
+                    const float* __restrict__ d_raw_rgb, int64_t ray_stride, int S, int64_t M, int fp16,
+                    float* __restrict__ grad_flat) {
+  const int tid = threadIdx.x, rg = tid >> 5, ch = tid & 31;
+  const int par = ch >> 4;
+  const int64_t ntiles = (M + 127) / 128;
+  float aw[8], rw[3][8], ab = 0.f, rb[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { aw[j] = 0.f; rw[0][j] = 0.f; rw[1][j] = 0.f; rw[2][j] = 0.f; }
+  __shared__ float s_d[128][4];
+  __shared__ float s_red[8][32][33];
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    __syncthreads();
+    if (tid < 128) {
+      const int64_t gi = t * 128 + tid;
+      float a = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+      if (gi < M) {
+        const int64_t r = gi / S, o = r * ray_stride + (gi - r * S);
+        a = d_raw_alpha[o]; c0 = d_raw_rgb[o * 3]; c1 = d_raw_rgb[o * 3 + 1]; c2 = d_raw_rgb[o * 3 + 2];
+      }
+      s_d[tid][0] = a; s_d[tid][1] = c0; s_d[tid][2] = c1; s_d[tid][3] = c2;
+    }
+    __syncthreads();
+    const uint8_t* tile = stash + (size_t)t * hc.stash_blocks * TC_BLOCK_BYTES;
+    const uint8_t* hb = tile + (size_t)(hc.blk_h + (ch >> 3)) * TC_BLOCK_BYTES;
+    const uint8_t* h2b = tile + (size_t)(hc.blk_h2 + ((ch & 15) >> 3)) * TC_BLOCK_BYTES;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int m0 = half * 64 + rg * 8;
+      uint4 qh[8], q2[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + i;
+        qh[i] = __ldg(reinterpret_cast<const uint4*>(hb + (uint32_t)m * 128u + ((((uint32_t)ch & 7u) ^ ((uint32_t)m & 7u)) << 4)));
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + 2 * i + par;
+        q2[i] = __ldg(reinterpret_cast<const uint4*>(h2b + (uint32_t)m * 128u + ((((uint32_t)ch & 7u) ^ ((uint32_t)m & 7u)) << 4)));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = s_d[m0 + i][0];
+        float x[8];
+        unpack8(qh[i], fp16 != 0, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) aw[j] = fmaf(d, x[j], aw[j]);
+        if (ch == 31) {
+          const float4 dd = *reinterpret_cast<const float4*>(&s_d[m0 + i][0]);
+          ab += dd.x; rb[0] += dd.y; rb[1] += dd.z; rb[2] += dd.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 d = *reinterpret_cast<const float4*>(&s_d[m0 + 2 * i + par][0]);
+        float x[8];
+        unpack8(q2[i], fp16 != 0, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          rw[0][j] = fmaf(d.y, x[j], rw[0][j]);
+          rw[1][j] = fmaf(d.z, x[j], rw[1][j]);
+          rw[2][j] = fmaf(d.w, x[j], rw[2][j]);
+        }
+      }
+    }
+  }
+  // reduce the 8 row groups (and, for the rgb head, the two row parities) through shared memory, then one atomic per
+  // output element and CTA
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s_red[rg][ch][j] = aw[j];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_red[rg][ch][8 + c * 8 + j] = rw[c][j];
+  s_red[rg][ch][32] = (ch == 31) ? ab : 0.f;
+  __syncthreads();
+  for (int e = tid; e < 32 * 32; e += 256) {
+    const int c2 = e >> 5, k = e & 31;     // chunk, slot
+    if (k < 8) {
+      float v = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) v += s_red[g][c2][k];
+      atomicAdd(&grad_flat[hc.m_aw + c2 * 8 + k], v);
+    } else if (c2 < 16) {
+      float v = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) v += s_red[g][c2][k] + s_red[g][c2 + 16][k];
+      atomicAdd(&grad_flat[hc.m_rw + ((k - 8) >> 3) * STAR_WV + c2 * 8 + ((k - 8) & 7)], v);
+    }
+  }
+  if (tid == 0) {
+    float v = 0.f;
+    for (int g = 0; g < 8; ++g) v += s_red[g][31][32];
+    atomicAdd(&grad_flat[hc.m_ab], v);
+  }
+  // rgb bias: sum of d_rgb
+  __syncthreads();
+  if (ch == 31) { s_red[rg][0][0] = rb[0]; s_red[rg][0][1] = rb[1]; s_red[rg][0][2] = rb[2]; }
+  __syncthreads();
+  if (tid < 3) {
+    float v = 0.f;
+    for (int g = 0; g < 8; ++g) v += s_red[g][0][tid];
+    atomicAdd(&grad_flat[hc.m_rb + tid], v);
+  }
+}
+#define HEAD_GRAD_CTAS_PER_SM 2
+#else
 __global__ void __launch_bounds__(256)
 head_grad_tc_kernel(const HeadGradCfg hc, const uint8_t* __restrict__ stash, const float* __restrict__ d_raw_alpha,
                     const float* __restrict__ d_raw_rgb, int64_t ray_stride, int S, int64_t M, int fp16,
@@ -1266,6 +1380,9 @@ head_grad_tc_kernel(const HeadGradCfg hc, const uint8_t* __restrict__ stash, con
     atomicAdd(&grad_flat[hc.m_rb + tid], v);
   }
 }
+
+#define HEAD_GRAD_CTAS_PER_SM 4
+#endif
 
 // ============================================================================================ transposed weight stream
 // dX GEMM of layer l: out[m][j] = sum_n G[m][n] W[n][j]: B operand rows j (input features, padded to 64 / 256),
@@ -1398,7 +1515,7 @@ int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed
   }
   // ---- 3. heads
   {
-    int blocks = (int)(ntiles < 4 * sms ? ntiles : 4 * sms);
+    int blocks = (int)(ntiles < HEAD_GRAD_CTAS_PER_SM * sms ? ntiles : HEAD_GRAD_CTAS_PER_SM * sms);
     const HeadGradCfg hc{tl.stash_blocks, tl.L[tl.n_layers - 2].s_in, tl.L[tl.n_layers - 1].s_out, ml.m_alpha_w, ml.m_alpha_b,
                          ml.m_rgb_w, ml.m_rgb_b};
     head_grad_tc_kernel<<<blocks, 256, 0, st>>>(hc, (const uint8_t*)stash, d_raw_alpha, d_raw_rgb, ray_stride, S, M, fp16,
@@ -1749,7 +1866,7 @@ int star_mip_tc_backward(const void* packed, int R, int S, const float* d_raw_si
     if (rc) return rc;
   }
   {   // ---- 3. density / rgb heads
-    int blocks = (int)(ntiles < 4 * sms ? ntiles : 4 * sms);
+    int blocks = (int)(ntiles < HEAD_GRAD_CTAS_PER_SM * sms ? ntiles : HEAD_GRAD_CTAS_PER_SM * sms);
     const HeadGradCfg hc{MIP_STASH_BLOCKS, MIP_S_OUT(MIP_NBASE - 1), MIP_S_H1, ml.m_w[MIP_L_DENS], ml.m_b[MIP_L_DENS],
                          ml.m_w[MIP_L_RGB], ml.m_b[MIP_L_RGB]};
     head_grad_tc_kernel<<<blocks, 256, 0, st>>>(hc, (const uint8_t*)stash, d_raw_sigma, d_raw_rgb, ray_stride, S, M, fp16,
