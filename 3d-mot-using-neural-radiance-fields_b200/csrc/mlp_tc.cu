@@ -37,6 +37,24 @@
 
 #include "mlp_tc_device.cuh"
 
+// Training (STASH) variant: who moves a finished A block to the activation stash?
+//   0 (default) the weight producer thread, with one bulk store (cp.async.bulk shared -> global) per block;
+//   1 a COPY WARP of its own (warp 18; the kernel then runs 19 warps): ld.shared.v4 / st.global.v4, 512 contiguous bytes per
+//     warp instruction, release of the block (stash_done) as soon as its loads have landed.
+// Measured (tools/bulk_store_rate.cu, profiles/r2v_bulk_store_rate.txt): the bulk-copy engine of an SM drains a 16 KB store at
+// ~25 B/clk (644 cycles per block even with ONE SM active; 148 SMs together = the 7.3 TB/s HBM write peak), 825 cycles per
+// block when the same engine also fetches a 32 KB weight K-block -- 4 x 825 cycles of engine time per layer, and weight loads
+// queue behind stores (no-stores debug mode: -6.4 k of 62.8 k cycles per tile).  The copy warp takes the stores off that engine
+// and is bit-identical (GPU suite), but SLOWER: 68.0 k cycles per tile (its copies cost 10 k: the loads / stores share the
+// LSU path with the 16 epilogue warps, the kernel's critical path), stash forward 2.14 against 2.09 ms per 4096-ray step
+// (profiles/r2w_ab_copy_warp.txt, r2w_stash_debug_modes.txt).  Kept as a compile-time A/B only.  Also measured: requesting the
+// weight K-block BEFORE the store of the same iteration (so that it cannot queue behind it in the engine): 62.8 k cycles per
+// tile either way (profiles/r2x_ab_store_after_load.txt) -- the order of the requests is not what the stores cost.
+#ifndef TC_STASH_COPY_WARP
+#define TC_STASH_COPY_WARP 0
+#endif
+#define TC_THREADS_STASH (TC_THREADS + (TC_STASH_COPY_WARP ? 32 : 0))
+
 #ifndef TC_LD_DEPTH
 #define TC_LD_DEPTH 2        // TMEM chunk loads in flight per epilogue thread (measured: 2 beats 1 and 4)
 #endif
@@ -229,7 +247,7 @@ __device__ __noinline__ void tc_encode_dirs(float dx, float dy, float dz, const 
 // one completion barrier each (X: lin_in / fc_1 / feature_linear, T: fc_0 / lin_out / view layer), so lin_in (t + 1) -> X
 // can complete before the view layer's accumulator T has been read.
 template <bool FP16, bool STASH>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(STASH ? TC_THREADS_STASH : TC_THREADS, 1)
 mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const StarPtsSrc pts,
                   const float* __restrict__ viewdirs, const float* __restrict__ pose12,
                   const float* __restrict__ sc_xyz, const float* __restrict__ sc_dir, int S, int64_t M,
@@ -298,8 +316,9 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     fence_mbar_init();
   }
   if (warp == TC_EPI_WARPS + 1) tmem_alloc(base + sl.tmem_ptr, TC_TMEM_COLS);
-  for (int i = tid; i < lay.small_floats; i += TC_THREADS) s_small[i] = reinterpret_cast<const float*>(packed)[i];
-  for (int i = tid; i < TC_KB_BYTES / 16; i += TC_THREADS)
+  constexpr int NTHREADS = STASH ? TC_THREADS_STASH : TC_THREADS;
+  for (int i = tid; i < lay.small_floats; i += NTHREADS) s_small[i] = reinterpret_cast<const float*>(packed)[i];
+  for (int i = tid; i < TC_KB_BYTES / 16; i += NTHREADS)
     reinterpret_cast<uint4*>(gbase + sl.AD)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_smem();
   tc_fence_before();
@@ -346,7 +365,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         for (int l = 0; l < lay.n_layers; ++l) {
           const uint32_t kb_bytes = (uint32_t)lay.L[l].N * 128u;
           for (int kb = 0; kb < lay.L[l].nkb; ++kb) {
-            if (STASH && l >= 2 && kb < 4) stash_chunk(l - 2, kb);
+            if (STASH && !TC_STASH_COPY_WARP && l >= 2 && kb < 4) stash_chunk(l - 2, kb);
             mbar_wait(bar(BAR_W_EMPTY(stage)), phase ^ 1u, dbg, 1);
             // operands with barriers of their own (the 16 epilogue warps do not arrive on w_full for them): the dirs block
             // (a_ready[4]) and lin_in's operand in slot S (s_ready) -- both are written far ahead of their K-block's turn,
@@ -362,10 +381,42 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
             if (++stage == NS) { stage = 0; phase ^= 1u; }
           }
         }
-        if (STASH)
+        if (STASH && !TC_STASH_COPY_WARP)
           for (int kb = 0; kb < 4; ++kb) stash_chunk(lay.n_layers - 2, kb);   // feature_linear's output blocks
       }
-      if (STASH) bulk_wait_group0();
+      if (STASH && !TC_STASH_COPY_WARP) bulk_wait_group0();
+    }
+  } else if (STASH && TC_STASH_COPY_WARP && warp == TC_EPI_WARPS + 2) {
+    // ======================================================================== stash copy warp (training)
+    // Output block kb of every layer but the last is at once the next layer's A operand and a 16 KB block of the activation
+    // stash (same swizzled image).  Once the 16 epilogue warps have published it (a_ready[kb]: their generic-proxy stores are
+    // visible to this warp's loads) the warp copies it, 8 x 512 bytes in flight, and releases it (stash_done[kb]) as soon as the
+    // loads have landed in registers -- the epilogue of the next layer waits for that before it overwrites the block.
+    uint32_t s_par = 0;
+    for (int64_t tile = tile0; tile < ntiles; tile += tile_step) {
+      uint8_t* st_tile = stash + (size_t)tile * (size_t)lay.stash_blocks * TC_BLOCK_BYTES;
+      for (int ls = 0; ls + 1 < lay.n_layers; ++ls) {
+        uint4* dst_l = reinterpret_cast<uint4*>(st_tile + (size_t)lay.L[ls].s_out * TC_BLOCK_BYTES) + lane;
+#pragma unroll 1
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(bar(BAR_A_READY(kb)), (s_par >> kb) & 1u, dbg, 6);
+          s_par ^= 1u << kb;
+          const uint4* src = reinterpret_cast<const uint4*>(gbase + sl.A + (uint32_t)kb * TC_KB_BYTES) + lane;
+          uint4* dst = dst_l + (size_t)kb * (TC_BLOCK_BYTES / 16);
+          if (!(dbg_mode & 8)) {
+#pragma unroll
+            for (int it = 0; it < 32; it += 8) {
+              uint4 v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = src[(it + j) * 32];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) __stcs(dst + (it + j) * 32, v[j]);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_STASH_DONE_KB(kb)));
+        }
+      }
     }
   } else if (warp == TC_EPI_WARPS + 1) {
     // ======================================================================== MMA issuer
@@ -432,7 +483,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
         }
       }
     }
-  } else {
+  } else if (warp < TC_EPI_WARPS) {
     // ======================================================================== epilogue warps
     const int q = warp & 3, cg = warp >> 2;
     const int row = q * 32 + lane;
@@ -677,7 +728,7 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pt
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
   if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
   auto launch = [&](int* dbg, int dbg_mode) -> int {
-    kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
+    kern<<<grid, with_stash ? TC_THREADS_STASH : TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
                                              raw_alpha, raw_rgb, ray_stride, (uint8_t*)stash, status, dbg, dbg_mode);
     return STAR_OK;
   };
