@@ -57,7 +57,10 @@ extern "C" int star_composite_hier_forward(const float* raw_alpha, const float* 
   if (per_warp * wpb > 200 * 1024) return STAR_E_BAD_SHAPE;
   const size_t smem = per_warp * wpb;
   int64_t blocks = ((int64_t)R + wpb - 1) / wpb;
-  if (blocks > 148 * 32) blocks = 148 * 32;
+#ifndef STAR_FUSED_GRID_CAP
+#define STAR_FUSED_GRID_CAP 0x3fffffff     // grid over all rays (profiles/r2y_ab_grid_cap.txt)
+#endif
+  if (blocks > STAR_FUSED_GRID_CAP) blocks = STAR_FUSED_GRID_CAP;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(composite_hier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   composite_hier_kernel<<<(int)blocks, wpb * 32, smem, (cudaStream_t)stream>>>(

@@ -253,7 +253,10 @@ static int launch_cfg_warp_per_ray(int R, size_t smem_per_warp, int& blocks, int
   threads = wpb * 32;
   smem = smem_per_warp * wpb;
   int64_t b = ((int64_t)R + wpb - 1) / wpb;
-  if (b > 148 * 32) b = 148 * 32;
+#ifndef STAR_FUSED_GRID_CAP
+#define STAR_FUSED_GRID_CAP 0x3fffffff     // grid over all rays (profiles/r2y_ab_grid_cap.txt)
+#endif
+  if (b > STAR_FUSED_GRID_CAP) b = STAR_FUSED_GRID_CAP;
   blocks = (int)b;
   return STAR_OK;
 }
