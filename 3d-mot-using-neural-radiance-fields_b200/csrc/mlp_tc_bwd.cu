@@ -161,7 +161,7 @@ __global__ void grad_absmax_kernel(const float* __restrict__ d_alpha, const floa
 }
 
 #ifndef TC_DX_DEFER_WAIT_ST
-#define TC_DX_DEFER_WAIT_ST 0  // 1: one tcgen05.wait::st per phase instead of one per chunk (A/B: profiles/r2q)
+#define TC_DX_DEFER_WAIT_ST 0  // 1: one tcgen05.wait::st per phase instead of one per chunk -- measured no gain (bwd 4.68 / 4.82 vs 4.65 / 4.70 ms, profiles/r2z_ab_defer_wait_st.txt)
 #endif
 #ifndef TC_DX_LD_DEPTH
 #define TC_DX_LD_DEPTH 2       // accumulator chunk loads in flight per epilogue thread of the dX chain (1 = load, wait, use)
