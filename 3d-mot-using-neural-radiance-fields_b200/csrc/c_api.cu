@@ -127,11 +127,11 @@ extern "C" int star_mlp_forward(const StarNetDesc* d, const void* packed, const 
                                 const float* pose12, const float* enc_scale_xyz, const float* enc_scale_dir, int R,
                                 int S, float* raw_alpha, float* raw_rgb, int64_t alpha_ray_stride, void* stash,
                                 int32_t* status, void* stream) {
+  if (R == 0) return STAR_OK;     /* an empty batch carries no pointers (torch: data_ptr() == 0 for numel() == 0) */
   if (!d || !packed || !viewdirs || !raw_alpha || !raw_rgb) return STAR_E_NULL;
   if (!pts_or_null && (!rays_o || !rays_d || !z_vals)) return STAR_E_NULL;
   const StarPtsSrc pts{pts_or_null, rays_o, rays_d, z_vals};
   if (R < 0 || S < 1 || alpha_ray_stride < S) return STAR_E_BAD_SHAPE;
-  if (R == 0) return STAR_OK;
   MlpLayout lay;
   int rc = star_make_layout(d, &lay);
   if (rc) return rc;
@@ -156,6 +156,7 @@ extern "C" int star_mlp_backward(const StarNetDesc* d, const void* packed, const
                                  const float* d_raw_alpha, const float* d_raw_rgb, int64_t alpha_ray_stride,
                                  const void* stash, void* workspace, float* grad_flat, float* pose_acc,
                                  void* stream) {
+  if (R == 0) return STAR_OK;     /* an empty batch carries no pointers (torch: data_ptr() == 0 for numel() == 0) */
   (void)flat_master;
   if (!d || !packed || !viewdirs || !d_raw_alpha || !d_raw_rgb || !stash || !workspace || !grad_flat)
     return STAR_E_NULL;
@@ -163,7 +164,6 @@ extern "C" int star_mlp_backward(const StarNetDesc* d, const void* packed, const
   const StarPtsSrc pts{pts_or_null, rays_o, rays_d, z_vals};
   if (pose12 && !pose_acc) return STAR_E_NULL;
   if (R < 0 || S < 1 || alpha_ray_stride < S) return STAR_E_BAD_SHAPE;
-  if (R == 0) return STAR_OK;
   MlpLayout lay;
   int rc = star_make_layout(d, &lay);
   if (rc) return rc;
@@ -253,9 +253,9 @@ extern "C" int star_mip_field_forward(int precision, const void* packed, const f
                                       const float* pose12, const float* bins, const float* freqs, float radius, int R,
                                       int S, float* raw_sigma, float* raw_rgb, int64_t ray_stride, void* stash,
                                       void* stream) {
+  if (R == 0) return STAR_OK;     /* an empty batch carries no pointers (torch: data_ptr() == 0 for numel() == 0) */
   if (!packed || !origins || !dirs || !bins || !freqs || !raw_sigma || !raw_rgb) return STAR_E_NULL;
   if (R < 0 || S < 1 || ray_stride < S) return STAR_E_BAD_SHAPE;
-  if (R == 0) return STAR_OK;
   MipLayout lay;
   star_make_mip_layout(&lay);
   if (precision == STAR_PREC_F32)
@@ -273,12 +273,12 @@ extern "C" int star_mip_field_backward(int precision, const void* packed, const 
                                        int S, const float* d_raw_sigma, const float* d_raw_rgb, int64_t ray_stride,
                                        const void* stash, void* workspace, float* grad_flat, float* pose_acc,
                                        void* stream) {
+  if (R == 0) return STAR_OK;     /* an empty batch carries no pointers (torch: data_ptr() == 0 for numel() == 0) */
   if (!packed || !origins || !dirs || !bins || !freqs || !d_raw_sigma || !d_raw_rgb || !stash || !workspace ||
       !grad_flat)
     return STAR_E_NULL;
   if (pose12 && !pose_acc && precision == STAR_PREC_F32) return STAR_E_NULL;
   if (R < 0 || S < 1 || ray_stride < S) return STAR_E_BAD_SHAPE;
-  if (R == 0) return STAR_OK;
   MipLayout lay;
   star_make_mip_layout(&lay);
   if (precision == STAR_PREC_F32)

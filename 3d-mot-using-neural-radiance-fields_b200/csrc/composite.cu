@@ -640,9 +640,9 @@ extern "C" int star_composite_single_forward(const float* raw_alpha, const float
                                              const float* rays_d, int R, int S, float far_dist, int white_bkgd,
                                              float* rgb, float* disp, float* acc, float* depth, float* weights,
                                              float* dists, void* stream) {
+  if (R == 0) return STAR_OK;     /* an empty batch carries no pointers (torch: data_ptr() == 0 for numel() == 0) */
   if (!raw_alpha || !raw_rgb || !z_vals || !rays_d || !rgb || !disp || !acc || !depth || !weights) return STAR_E_NULL;
   if (R < 0 || S < 1) return STAR_E_BAD_SHAPE;
-  if (R == 0) return STAR_OK;
   int blocks, threads;
   size_t smem;
   warp_per_ray_cfg(R, 0, blocks, threads, smem);
@@ -662,9 +662,9 @@ extern "C" int star_composite_single_backward(const float* raw_alpha, const floa
                                               const float* g_rgb, const float* g_disp, const float* g_acc,
                                               const float* g_depth, const float* g_weights, float* d_raw_alpha,
                                               float* d_raw_rgb, void* stream) {
+  if (R == 0) return STAR_OK;     /* an empty batch carries no pointers (torch: data_ptr() == 0 for numel() == 0) */
   if (!raw_alpha || !raw_rgb || !z_vals || !rays_d || !d_raw_alpha || !d_raw_rgb) return STAR_E_NULL;
   if (R < 0 || S < 1 || S > 16384) return STAR_E_BAD_SHAPE;
-  if (R == 0) return STAR_OK;
   int blocks, threads;
   size_t smem;
   warp_per_ray_cfg(R, sizeof(float) * 2 * S, blocks, threads, smem);

@@ -35,7 +35,7 @@ __global__ void iou2d_kernel(const float* __restrict__ dyn_t, const uint8_t* __r
 // pred (nullable) [V, R] bytes <- per-object masks, counts[2] <- {intersection, union} pixel counts (int64).
 extern "C" int star_iou2d(const float* dyn_t, const uint8_t* sem, int64_t R, int V, float thres, uint8_t* pred,
                           int64_t* counts, void* stream) {
-  if (!dyn_t || !sem || !counts) return STAR_E_NULL;
+  if (!counts || (R != 0 && (!dyn_t || !sem))) return STAR_E_NULL;     /* R == 0: empty arrays carry no pointers */
   if (R < 0 || V < 1 || V > STAR_MAX_V) return STAR_E_BAD_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
   const cudaError_t e = cudaMemsetAsync(counts, 0, 2 * sizeof(int64_t), st);

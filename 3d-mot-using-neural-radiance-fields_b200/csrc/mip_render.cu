@@ -40,9 +40,9 @@ __global__ void mip_uniform_bins_kernel(const float* __restrict__ lin, const flo
 
 extern "C" int star_mip_uniform_bins(const float* lin, const float* t_rand, float near_, float far_, int R, int Nc,
                                      float* spacing, float* euclid, void* stream) {
+  if (R == 0) return STAR_OK;     /* an empty batch carries no pointers (torch: data_ptr() == 0 for numel() == 0) */
   if (!lin || !spacing || !euclid) return STAR_E_NULL;
   if (R < 0 || Nc < 1) return STAR_E_BAD_SHAPE;
-  if (R == 0) return STAR_OK;
   const int64_t total = (int64_t)R * (Nc + 1);
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -113,9 +113,9 @@ extern "C" int star_mip_pdf_sample(const float* spacing_bins, const float* weigh
                                    const float* u_base, const float* u_rand, float near_, float far_, int R, int Nc,
                                    int Ni, float* spacing_out, float* euclid_out, int64_t* inds, float* cdf,
                                    void* stream) {
+  if (R == 0) return STAR_OK;     /* an empty batch carries no pointers (torch: data_ptr() == 0 for numel() == 0) */
   if (!spacing_bins || !weights || !u_base || !spacing_out || !euclid_out) return STAR_E_NULL;
   if (R < 0 || Nc < 1 || Ni < 1 || Nc > 8192) return STAR_E_BAD_SHAPE;
-  if (R == 0) return STAR_OK;
   const int wpb = 4;
   const size_t smem = sizeof(float) * 2 * (size_t)(Nc + 1) * wpb;
   int64_t blocks = ((int64_t)R + wpb - 1) / wpb;
@@ -571,9 +571,9 @@ static void mip_warp_per_ray_cfg(int R, size_t smem_per_warp, int& blocks, int& 
 extern "C" int star_mip_composite_single_forward(const float* raw_sigma, const float* raw_rgb, const float* bins, int R,
                                                  int S, float* rgb, float* acc, float* depth, float* weights,
                                                  void* stream) {
+  if (R == 0) return STAR_OK;     /* an empty batch carries no pointers (torch: data_ptr() == 0 for numel() == 0) */
   if (!raw_sigma || !raw_rgb || !bins || !rgb || !acc || !depth || !weights) return STAR_E_NULL;
   if (R < 0 || S < 1) return STAR_E_BAD_SHAPE;
-  if (R == 0) return STAR_OK;
   int blocks, threads;
   size_t smem;
   mip_warp_per_ray_cfg(R, 0, blocks, threads, smem);
@@ -585,9 +585,9 @@ extern "C" int star_mip_composite_single_forward(const float* raw_sigma, const f
 extern "C" int star_mip_composite_single_backward(const float* raw_sigma, const float* raw_rgb, const float* bins, int R,
                                                   int S, const float* g_rgb, const float* g_acc, const float* g_weights,
                                                   float* d_raw_sigma, float* d_raw_rgb, void* stream) {
+  if (R == 0) return STAR_OK;     /* an empty batch carries no pointers (torch: data_ptr() == 0 for numel() == 0) */
   if (!raw_sigma || !raw_rgb || !bins || !d_raw_sigma || !d_raw_rgb) return STAR_E_NULL;
   if (R < 0 || S < 1 || S > 12288) return STAR_E_BAD_SHAPE;
-  if (R == 0) return STAR_OK;
   int blocks, threads;
   size_t smem;
   mip_warp_per_ray_cfg(R, sizeof(float) * S, blocks, threads, smem);

@@ -41,6 +41,7 @@ extern "C" int star_composite_hier_forward(const float* raw_alpha, const float* 
                                            float far_dist, int white_bkgd, float* rgb, float* disp, float* acc, float* depth,
                                            float* weights, float* dists, float* z_samples, float* z_all, float* z_std,
                                            void* stream) {
+  if (R == 0) return STAR_OK;     /* an empty batch carries no pointers (torch: data_ptr() == 0 for numel() == 0) */
   if (!raw_alpha || !raw_rgb || !z_vals || !rays_d || !rgb || !disp || !acc || !depth || !z_samples || !z_all || !z_std ||
       (!u && !u_det))
     return STAR_E_NULL;
@@ -48,7 +49,6 @@ extern "C" int star_composite_hier_forward(const float* raw_alpha, const float* 
   if ((Nc & 1) != 0 || Nc < 4) return STAR_E_UNSUPPORTED;
   if ((((uintptr_t)raw_alpha | (uintptr_t)raw_rgb | (uintptr_t)z_vals | (uintptr_t)weights | (uintptr_t)dists) & 7) != 0)
     return STAR_E_UNSUPPORTED;
-  if (R == 0) return STAR_OK;
   int P = 2;
   while (P < Ni) P <<= 1;
   const size_t per_warp = sizeof(float) * ((size_t)hier_smem_floats(Nc, Ni, P) + ((Nc + 3) & ~3));

@@ -101,11 +101,12 @@ extern "C" size_t star_render_workspace_bytes(const StarRenderCfg* cfg) {
 
 extern "C" int star_render_forward(const StarRenderCfg* cfg, const StarRenderIn* in, const StarRenderOut* out,
                                    void* workspace, size_t workspace_bytes, int32_t* status, void* stream) {
-  if (!cfg || !in || !out || !workspace) return STAR_E_NULL;
+  if (!cfg) return STAR_E_NULL;
+  if (cfg->R == 0) return STAR_OK;     /* an empty batch carries no pointers (and needs no workspace) */
+  if (!in || !out || !workspace) return STAR_E_NULL;
   const StarRenderCfg& c = *cfg;
   if (c.R < 0 || c.Nc < 1 || c.V < 0 || c.V > STAR_MAX_V || c.chunk < 1) return STAR_E_BAD_SHAPE;
   if (c.Ni > 0 && c.Nc < 3) return STAR_E_BAD_SHAPE;
-  if (c.R == 0) return STAR_OK;
   if (!in->packed_static_coarse || (c.Ni > 0 && !in->packed_static_fine)) return STAR_E_NULL;
   if (c.V > 0 && (!in->pose12 || !in->packed_dynamic_coarse || (c.Ni > 0 && !in->packed_dynamic_fine))) return STAR_E_NULL;
   if (c.Ni > 0 && !in->u && !in->u_det && !in->z_samples) return STAR_E_NULL;

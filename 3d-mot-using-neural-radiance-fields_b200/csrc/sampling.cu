@@ -110,9 +110,9 @@ __global__ void __launch_bounds__(SP_THREADS) sample_pts_x4_kernel(const float* 
 extern "C" int star_sample_pts(const float* rays_o, const float* rays_d, const float* t_vals,
                                const float* t_rand, float near_, float far_, int R, int Nc, int lindisp,
                                float* pts, float* z_vals, void* stream) {
+  if (R == 0) return STAR_OK;     /* an empty batch carries no pointers (torch: data_ptr() == 0 for numel() == 0) */
   if (!t_vals || !z_vals || (pts && (!rays_o || !rays_d))) return STAR_E_NULL;     // pts == NULL: depths only
   if (R < 0 || Nc < 1) return STAR_E_BAD_SHAPE;
-  if (R == 0) return STAR_OK;
   const int64_t total = (int64_t)R * Nc;
   const int threads = 256;
   if ((Nc & 3) == 0 && total / 4 < (int64_t)0x7fffffff &&
@@ -264,9 +264,9 @@ static int launch_cfg_warp_per_ray(int R, size_t smem_per_warp, int& blocks, int
 extern "C" int star_sample_pdf(const float* bins, int64_t bins_stride, const float* weights, int64_t w_stride,
                                const float* u, const float* u_det, int R, int nb, int Ni, float* samples,
                                int64_t* inds, int64_t* below, int64_t* above, float* cdf, void* stream) {
+  if (R == 0) return STAR_OK;     /* an empty batch carries no pointers (torch: data_ptr() == 0 for numel() == 0) */
   if (!bins || !weights || !samples || (!u && !u_det)) return STAR_E_NULL;
   if (R < 0 || nb < 2 || Ni < 1) return STAR_E_BAD_SHAPE;
-  if (R == 0) return STAR_OK;
   int blocks, threads;
   size_t smem;
   int rc = launch_cfg_warp_per_ray(R, sizeof(float) * 2 * nb, blocks, threads, smem);
@@ -280,9 +280,9 @@ extern "C" int star_sample_pdf(const float* bins, int64_t bins_stride, const flo
 
 extern "C" int star_invert_cdf(const float* bins, const float* cdf, const float* u, int R, int nb, int Ni,
                                float* samples, int64_t* inds, int64_t* below, int64_t* above, void* stream) {
+  if (R == 0) return STAR_OK;     /* an empty batch carries no pointers (torch: data_ptr() == 0 for numel() == 0) */
   if (!bins || !cdf || !u || !samples) return STAR_E_NULL;
   if (R < 0 || nb < 1 || Ni < 1) return STAR_E_BAD_SHAPE;
-  if (R == 0) return STAR_OK;
   int blocks, threads;
   size_t smem;
   int rc = launch_cfg_warp_per_ray(R, sizeof(float) * 2 * nb, blocks, threads, smem);
@@ -324,10 +324,10 @@ __global__ void hierarchical_kernel(const float* __restrict__ z_vals, const floa
 extern "C" int star_hierarchical(const float* z_vals, const float* weights, const float* u, const float* u_det,
                                  const float* rays_o, const float* rays_d, int R, int Nc, int Ni,
                                  float* z_samples, float* z_all, float* z_std, float* pts_fine, void* stream) {
+  if (R == 0) return STAR_OK;     /* an empty batch carries no pointers (torch: data_ptr() == 0 for numel() == 0) */
   if (!z_vals || !weights || !z_samples || !z_all || !z_std || (!u && !u_det)) return STAR_E_NULL;
   if (pts_fine && (!rays_o || !rays_d)) return STAR_E_NULL;
   if (R < 0 || Nc < 3 || Ni < 1 || Nc + Ni > 8192) return STAR_E_BAD_SHAPE;
-  if (R == 0) return STAR_OK;
   int P = 2;
   while (P < Ni) P <<= 1;
   int blocks, threads;
@@ -344,10 +344,10 @@ extern "C" int star_hierarchical(const float* z_vals, const float* weights, cons
 extern "C" int star_merge_samples(const float* z_vals, const float* z_samples, const float* rays_o,
                                   const float* rays_d, int R, int Nc, int Ni, float* z_all, float* z_std,
                                   float* pts_fine, void* stream) {
+  if (R == 0) return STAR_OK;     /* an empty batch carries no pointers (torch: data_ptr() == 0 for numel() == 0) */
   if (!z_vals || !z_samples || !z_all || !z_std) return STAR_E_NULL;
   if (pts_fine && (!rays_o || !rays_d)) return STAR_E_NULL;
   if (R < 0 || Nc < 1 || Ni < 1 || Nc + Ni > 8192) return STAR_E_BAD_SHAPE;
-  if (R == 0) return STAR_OK;
   int P = 2;
   while (P < Ni) P <<= 1;
   int blocks, threads;

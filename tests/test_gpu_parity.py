@@ -452,6 +452,26 @@ def test_error_paths():
         net(pts, cu(rd), z, cu(rd), pose=torch.zeros(7, device=DEV))
 
 
+def test_empty_ray_batch_gives_empty_outputs():
+    """R = 0 (a rank whose shard of a view is empty, a filtered batch): the reference's eager ops return empty tensors of
+    the right shapes; so must the kernels' entry points -- no launch with a zero-sized grid, no error."""
+    net, _ = make_star(0, 24, 4096, True, seed=1, training=False)
+    ro = torch.zeros(0, 3, device=DEV)
+    rd = torch.zeros(0, 3, device=DEV)
+    pts, z = R_.sample_pts(ro, rd, 2.0, 6.0, 16, is_train=False)
+    assert pts.shape == (0, 16, 3) and z.shape == (0, 16)
+    with torch.no_grad():
+        out = R_.render_star_appinit(net, pts, rd, z, ro, rd, 24)          # the single-call entry
+    assert out["rgb"].shape == (0, 3) and out["weights"].shape == (0, 40) and out["z_std"].shape == (0,)
+    assert out["rgb0"].shape == (0, 3) and out["weights0"].shape == (0, 16)
+    ra, rc = torch.zeros(0, 16, device=DEV), torch.zeros(0, 16, 3, device=DEV)
+    res = F_.CompositeSingle.apply(ra, rc, z, rd, 1e10, True)
+    assert res[0].shape == (0, 3) and res[4].shape == (0, 16)
+    zs, zall, zstd, ptsf = F_.hierarchical(z, res[4], 24, True, ro, rd)
+    assert zs.shape == (0, 24) and zall.shape == (0, 40) and zstd.shape == (0,) and ptsf.shape == (0, 40, 3)
+    torch.cuda.synchronize()
+
+
 # ------------------------------------------------------------------------------------------ properties
 def test_rays_are_independent_and_chunking_is_invisible():
     """callbacks/check_batch_grad.py idea: per-ray outputs must not depend on the other rays in the
