@@ -472,6 +472,58 @@ def test_empty_ray_batch_gives_empty_outputs():
     torch.cuda.synchronize()
 
 
+def test_strided_ray_views_are_accepted():
+    """The reference's datasets hand out rays as slices of one [R, 6+] tensor (datasets/carla_star_online__.py): views with a
+    row stride must give the bits of their contiguous copies."""
+    net, _ = make_star(0, 24, 4096, True, seed=2, training=False)
+    ro, rd = so.lego_rays(20, 20)
+    rays = torch.cat([ro.reshape(-1, 3), rd.reshape(-1, 3), torch.zeros(400, 2)], -1).to(DEV)      # [R, 8]
+    ro_v, rd_v = rays[:, :3], rays[:, 3:6]
+    assert not ro_v.is_contiguous()
+    vd_v = torch.cat([rd_v / rd_v.norm(dim=-1, keepdim=True), torch.zeros(400, 1, device=DEV)], -1)[:, :3]
+    assert not vd_v.is_contiguous()
+    with torch.no_grad():
+        pts, z = R_.sample_pts(ro_v, rd_v, 2.0, 6.0, 16, is_train=False)
+        pts_c, z_c = R_.sample_pts(ro_v.contiguous(), rd_v.contiguous(), 2.0, 6.0, 16, is_train=False)
+        assert torch.equal(pts, pts_c) and torch.equal(z, z_c)
+        a = R_.render_star_appinit(net, pts, vd_v, z, ro_v, rd_v, 24)
+        b = R_.render_star_appinit(net, pts_c, vd_v.contiguous(), z_c, ro_v.contiguous(), rd_v.contiguous(), 24)
+        # a strided view of the sample depths (every second ray of a larger batch)
+        c = R_.render_star_appinit(net, pts_c[::2], vd_v[::2], z_c[::2], ro_v[::2], rd_v[::2], 24)
+    for k in ("rgb", "depth", "weights", "rgb0", "z_vals"):
+        assert torch.equal(a[k], b[k]), k
+        assert torch.equal(c[k], b[k][::2]), k
+
+
+def test_tensors_beyond_2_to_31_elements():
+    """Maximum sizes: [R, S, 3] arrays with more than 2^31 elements (2.9 M rays x 256 samples: a 9 GB position array) -- every
+    index that reaches them must be 64-bit.  sample_pts against the eager formula on the last rows, single-field compositing
+    against its own small-batch result on the first and the last rows (rays are independent)."""
+    R, S = 2_900_000, 256
+    assert R * S * 3 > 2 ** 31
+    g = torch.Generator(device=DEV).manual_seed(3)
+    ro = torch.randn(R, 3, device=DEV, generator=g)
+    rd = torch.randn(R, 3, device=DEV, generator=g)
+    pts, z = F_.sample_pts(ro, rd, 2.0, 6.0, S)
+    for sl in (slice(0, 1000), slice(R - 1000, R), slice(R // 2 + 12345, R // 2 + 13345)):
+        ref = ro[sl, None, :] + rd[sl, None, :] * z[sl, :, None]
+        assert torch.equal(pts[sl], ref)
+    t = torch.linspace(0.0, 1.0, S).to(DEV)          # (the CPU's linspace, as rendering__.py:90 computes it)
+    assert torch.equal(z[R - 1], 2.0 * (1.0 - t) + 6.0 * t)
+    del pts
+    ra = torch.randn(R, S, device=DEV, generator=g)
+    rc = torch.randn(R, S, 3, device=DEV, generator=g)
+    with torch.no_grad():
+        big = F_.CompositeSingle.apply(ra, rc, z, rd, 1e10, False)
+        for sl in (slice(0, 777), slice(R - 777, R)):
+            small = F_.CompositeSingle.apply(ra[sl].contiguous(), rc[sl].contiguous(), z[sl].contiguous(), rd[sl].contiguous(),
+                                             1e10, False)
+            for i in (0, 1, 2, 3, 4):
+                assert torch.equal(big[i][sl], small[i]), i
+        assert bool(torch.isfinite(big[0]).all())
+        assert_close(big[4][R - 5000:].sum(-1), big[2][R - 5000:], 5e-5, msg="sum(weights) == acc")
+
+
 # ------------------------------------------------------------------------------------------ properties
 def test_rays_are_independent_and_chunking_is_invisible():
     """callbacks/check_batch_grad.py idea: per-ray outputs must not depend on the other rays in the
