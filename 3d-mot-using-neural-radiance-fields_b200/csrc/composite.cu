@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128, 16) composite_single_fwd_kernel(const flo
     sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sd = warp_sum(sd); sa = warp_sum(sa);
     if (lane == 0) {
       const float wsum = (sa >= 0.f) ? sa : 1e-7f;                  // :353-354
-      disp_o[r] = 1.f / fmaxf(1e-10f, sd / wsum);                   // :355-357
+      disp_o[r] = 1.f / max_nan_f(1e-10f, sd / wsum);                   // :355-357
       acc_o[r] = sa;
       depth_o[r] = sd;
       const float bg = white_bkgd ? (1.f - sa) : 0.f;               // :360-361
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(128, STAR_MULTI_FWD_MINBLOCKS) composite_multi
     }
     if (lane == 0) {
       const float wsum = (s_acc >= 0.f) ? s_acc : STAR_EPS_F32;        // :509-511
-      out.disp[r] = 1.f / fmaxf(1e-10f, s_depth / wsum);
+      out.disp[r] = 1.f / max_nan_f(1e-10f, s_depth / wsum);
       out.acc[r] = s_acc;
       out.depth[r] = s_depth;
       const float bg = white_bkgd ? (1.f - s_acc) : 0.f;

@@ -94,7 +94,7 @@ __device__ __forceinline__ void composite_single_ray_x2(const float* __restrict_
         rgb_o[r * 3 + (lane >> 3)] = v + bg;
       } else {
         const float wsum = (sa >= 0.f) ? sa : 1e-7f;                  // :353-354
-        disp_o[r] = 1.f / fmaxf(1e-10f, v / wsum);                    // :355-357
+        disp_o[r] = 1.f / max_nan_f(1e-10f, v / wsum);                    // :355-357
         depth_o[r] = v;
         acc_o[r] = sa;
       }

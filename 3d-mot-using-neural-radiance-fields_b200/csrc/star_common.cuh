@@ -128,3 +128,7 @@ __device__ __forceinline__ float softplus_f(float x) {
 __device__ __forceinline__ float sigmoid_f(float x) { return rcp_ftz(1.f + fexp(-x)); }
 // d softplus / dx with torch's threshold semantics
 __device__ __forceinline__ float softplus_grad_f(float x) { return x > 20.f ? 1.f : sigmoid_f(x); }
+
+// torch.max(a, b) element-wise propagates NaN (fmaxf drops it): disp = 1 / max(1e-10, depth / acc) of a ray whose weights
+// are all exactly 0 is 0 / 0 = NaN in the reference (models/rendering__.py:353-357) and must be NaN here
+__device__ __forceinline__ float max_nan_f(float a, float b) { return (b != b) ? b : fmaxf(a, b); }

@@ -249,6 +249,51 @@ def test_sample_pdf_edge_and_large_sizes(R, Nc, Ni):
     assert torch.equal(d["inds"].cpu(), d_ref["inds"]) and torch.equal(s.cpu(), s_ref)
 
 
+def test_degenerate_distributions_and_depths_vs_oracle():
+    """The cases the reference's arithmetic meets on real scenes: all the mass of a ray in ONE bin (every other cdf step is
+    below the 1e-5 `denom` guard, rendering__.py:753-755), u exactly 0 and exactly 1 (searchsorted(right=True) runs off the
+    end, :745-748), repeated bin edges (zero-width bins), and -- for compositing -- repeated depths (dist = 0 -> alpha = 0),
+    saturated densities (raw = +-80) and a ray that is opaque at its first sample."""
+    gen = torch.Generator().manual_seed(11)
+    R, Nc, Ni = 12, 64, 128
+    w = torch.zeros(R, Nc - 2)
+    w[torch.arange(R), torch.randint(0, Nc - 2, (R,), generator=gen)] = 1.0      # a delta
+    w[1] = 1e-30
+    w[2, :] = 1.0
+    bins, _ = torch.sort(torch.rand(R, Nc - 1, generator=gen) * 4 + 2, -1)
+    bins[3, 10:20] = bins[3, 10:11]                                              # zero-width bins
+    bins[4] = 3.0                                                                # every edge the same
+    u = torch.rand(R, Ni, generator=gen)
+    u[:, 0], u[:, 1], u[:, -1] = 0.0, 1.0, 1.0
+    for det, uu in ((True, None), (False, u)):
+        s_ref, d_ref = so.sample_pdf(bins, w, Ni, det=det, u=uu, exact_sum=True, return_details=True)
+        s, d = F_.sample_pdf(cu(bins), cu(w), Ni, det=det, u=cu(uu) if uu is not None else None, return_details=True)
+        assert bool(torch.isfinite(s).all())
+        assert torch.equal(d["cdf"].cpu(), d_ref["cdf"])
+        for k in ("inds", "below", "above"):
+            assert torch.equal(d[k].cpu(), d_ref[k]), (det, k)
+        assert torch.equal(s.cpu(), s_ref), det
+    # compositing
+    S = 48
+    ro, rd = so.carla_rays(R, seed=6)
+    _, z = so.sample_pts(ro, rd, 0.03, 0.8, S)
+    z = z.clone()
+    z[0, 5:15] = z[0, 5:6]                  # repeated depths
+    z[1] = z[1, :1]                         # a ray of ONE depth
+    ra = torch.randn(R, S, generator=gen) * 3
+    ra[2], ra[3], ra[4, 0] = 80.0, -80.0, 1e4
+    rc = torch.randn(R, S, 3, generator=gen) * 4
+    rc[5] = 60.0
+    rc[6] = -60.0
+    for white in (False, True):
+        ref = so.raw2outputs(ra, rc, z, rd, 0.0, white, 1e10)
+        out = R_.raw2outputs(cu(ra), cu(rc), cu(z), cu(rd), 0.0, white, 1e10)
+        for k in ("rgb", "acc", "depth", "weights"):
+            assert bool(torch.isfinite(out[k]).all()), k
+            assert_close(out[k], ref[k], 2e-6, rtol=1e-5, msg="%s white=%s" % (k, white))
+        assert_close(out["disp"], ref["disp"], 1e-5, rtol=1e-4, msg="disp")
+
+
 def test_sample_pdf_accepts_strided_weights_view():
     gen = torch.Generator().manual_seed(3)
     w_full = torch.rand(11, 66, generator=gen)
