@@ -179,6 +179,41 @@ def test_raw2outputs_star_forward_backward_vs_oracle(R, V, S, chunk):
         assert_close(a.grad, b.grad, 3e-5, 2e-4, name)
 
 
+def test_raw2outputs_star_degenerate_rays_forward_vs_oracle():
+    """Multi-field compositing where the clamps of the regularisers bite (rendering__.py:612-711): rays on which every field
+    is transparent (all alphas below EPS: tot < EPS, p clamps), a ray one object makes opaque at its first sample, saturated
+    densities of both signs, repeated depths (alpha = 0 exactly) -- forward keys and the five regularisers against the oracle;
+    a non-finite value may only appear where the reference produces the same one (disp of a weightless ray)."""
+    gen = torch.Generator().manual_seed(21)
+    R, V, S = 16, 3, 40
+    ras = torch.randn(R, S, generator=gen) * 3 - 1
+    rcs = torch.randn(R, S, 3, generator=gen) * 2
+    rad = torch.randn(R, V, S, generator=gen) * 3 - 2
+    rcd = torch.randn(R, V, S, 3, generator=gen) * 2
+    ras[0], rad[0] = -80.0, -80.0                 # nothing on the ray
+    ras[1], rad[1] = -80.0, -30.0
+    rad[2, 1, 0] = 1e4                            # object 1 opaque at the first sample
+    ras[3] = 80.0                                 # static field saturated
+    rad[4] = 80.0                                 # every object saturated
+    ras[5], rad[5] = 0.0, 0.0
+    ro, rd = so.carla_rays(R, seed=8)
+    _, z = so.sample_pts(ro, rd, 0.03, 0.8, S)
+    z = z.clone()
+    z[6, 3:30] = z[6, 3:4]                        # repeated depths
+    z[7] = z[7, :1]
+    for chunk in (R, 5):
+        outs = [so.raw2outputs_star(ras[i:i + chunk], rcs[i:i + chunk], rad[i:i + chunk], rcd[i:i + chunk],
+                                    z[i:i + chunk], rd[i:i + chunk], False, 1e10, test=True) for i in range(0, R, chunk)]
+        o_ref = {k: (sum(o[k] for o in outs) if outs[0][k].dim() == 0 else torch.cat([o[k] for o in outs], 0))
+                 for k in outs[0]}
+        o = R_.raw2outputs_star(cu(ras), cu(rcs), cu(rad), cu(rcd), cu(z), cu(rd), 0, False, 1e10, test=True, chunk=chunk)
+        for k, v in o.items():
+            tol = 2e-5 if k == "disp" else 4e-6
+            assert_close(v, o_ref[k], tol, 2e-5, "%s (chunk %d)" % (k, chunk))
+        for k in REGS:
+            assert bool(torch.isfinite(o[k]).all()) == bool(torch.isfinite(o_ref[k]).all()), k
+
+
 def test_star_static_products_equal_single_field():
     """The per-field static products of raw2outputs_star (:482,:500) are the single-field composite of the
     static raws; and with transparent objects (raw_d << 0) the composite colour degenerates to
