@@ -214,6 +214,22 @@ def test_raw2outputs_star_degenerate_rays_forward_vs_oracle():
             assert bool(torch.isfinite(o[k]).all()) == bool(torch.isfinite(o_ref[k]).all()), k
 
 
+def test_degenerate_rays_vs_reference_fixture():
+    """The kernels against the UNMODIFIED reference on tests/golden/degenerate.npz: weightless rays (disp = NaN there and here),
+    saturated densities and colours, repeated depths, an object opaque at its first sample."""
+    g = load_golden("degenerate")
+    for tag, white in (("white.", True), ("black.", False)):
+        o = R_.raw2outputs(cu(g["raw_alpha_s"]), cu(g["raw_rgb_s"]), cu(g["z_vals"]), cu(g["rays_d"]), 0.0, white, 1e10)
+        for k in ("rgb", "disp", "acc", "weights", "depth", "dists"):
+            assert_close(o[k], g[tag + k], 2e-6, 2e-5 if k == "disp" else 1e-5, tag + k)
+        assert bool(torch.isnan(o["disp"][:2]).all()) and bool(torch.isfinite(o["disp"][2:]).all())
+    o = R_.raw2outputs_star(cu(g["raw_alpha_s"]), cu(g["raw_rgb_s"]), cu(g["raw_alpha_d"]), cu(g["raw_rgb_d"]),
+                            cu(g["z_vals"]), cu(g["rays_d"]), 0, False, 1e10, test=True)
+    for k, v in o.items():
+        if v is not None and ("star." + k) in g:
+            assert_close(v, g["star." + k], 2e-5 if k == "disp" else 4e-6, 2e-5, "star." + k)
+
+
 def test_star_static_products_equal_single_field():
     """The per-field static products of raw2outputs_star (:482,:500) are the single-field composite of the
     static raws; and with transparent objects (raw_d << 0) the composite colour degenerates to

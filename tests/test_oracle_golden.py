@@ -64,6 +64,22 @@ def test_raw2outputs_star(test):
         assert_close(v, g[tag + k], 1e-7, 2e-6, tag + k)
 
 
+def test_degenerate_rays_fixture():
+    """tests/golden/degenerate.npz (tools/make_golden.py --only-degenerate): the unmodified reference on rays without any
+    weight, saturated densities / colours, repeated depths.  Pins in particular disp = NaN where acc == 0 (torch.max
+    propagates the 0 / 0 of rendering__.py:353-357)."""
+    g = load_golden("degenerate")
+    assert bool(torch.isnan(g["white.disp"][:2]).all()) and bool(torch.isfinite(g["white.disp"][2:]).all())
+    for tag, white in (("white.", True), ("black.", False)):
+        o = so.raw2outputs(g["raw_alpha_s"], g["raw_rgb_s"], g["z_vals"], g["rays_d"], 0.0, white, 1e10)
+        for k, v in o.items():
+            assert_close(v, g[tag + k], 1e-7, 1e-6, tag + k)
+    o = so.raw2outputs_star(g["raw_alpha_s"], g["raw_rgb_s"], g["raw_alpha_d"], g["raw_rgb_d"], g["z_vals"], g["rays_d"],
+                            white_bkgd=False, far_dist=1e10, test=True)
+    for k, v in o.items():
+        assert_close(v, g["star." + k], 1e-7, 2e-6, "star." + k)
+
+
 def test_sample_pdf_reference_ops():
     g = load_golden("sample_pdf")
     s, d = so.sample_pdf(g["bins"], g["weights"], 64, det=True, return_details=True)

@@ -67,8 +67,47 @@ def rays_fixture(ref):
     npz("get_rays", H=H, W=W, K=K, c2w=c2w, rays_o=ro, rays_d=rd, rays_o_np=np.ascontiguousarray(ro_np), rays_d_np=rd_np)
 
 
+def degenerate_inputs():
+    """Rays on which the reference's clamps and guards bite (shared with tests/test_gpu_parity.py through the fixture):
+    nothing on the ray (all alphas 0 -> disp = 1 / max(1e-10, 0 / 0)), transparent static + faint objects, an object opaque at
+    its first sample, saturated densities, repeated depths, a ray of one depth, saturated colours."""
+    gen = torch.Generator().manual_seed(21)
+    R, V, S = 16, 3, 40
+    ras = torch.randn(R, S, generator=gen) * 3 - 1
+    rcs = torch.randn(R, S, 3, generator=gen) * 2
+    rad = torch.randn(R, V, S, generator=gen) * 3 - 2
+    rcd = torch.randn(R, V, S, 3, generator=gen) * 2
+    ras[0], rad[0] = -80.0, -80.0
+    ras[1], rad[1] = -80.0, -30.0
+    rad[2, 1, 0] = 1e4
+    ras[3] = 80.0
+    rad[4] = 80.0
+    ras[5], rad[5] = 0.0, 0.0
+    rcs[8], rcs[9] = 60.0, -60.0
+    ro, rd = so.carla_rays(R, seed=8)
+    _, z = so.sample_pts(ro, rd, 0.03, 0.8, S)
+    z = z.clone()
+    z[6, 3:30] = z[6, 3:4]
+    z[7] = z[7, :1]
+    return ras, rcs, rad, rcd, z.contiguous(), rd
+
+
+def degenerate_fixture(ref):
+    """raw2outputs (white / black) and raw2outputs_star (test=True) of the UNMODIFIED reference on degenerate_inputs()."""
+    R_ = ref.rendering
+    ras, rcs, rad, rcd, z, rd = degenerate_inputs()
+    o_w = R_.raw2outputs(ras, rcs, z, rd, 0.0, True, 1e10)
+    o_b = R_.raw2outputs(ras, rcs, z, rd, 0.0, False, 1e10)
+    s_te = R_.raw2outputs_star(ras, rcs, rad, rcd, z, rd, 0, False, 1e10, test=True)
+    npz("degenerate", raw_alpha_s=ras, raw_rgb_s=rcs, raw_alpha_d=rad, raw_rgb_d=rcd, z_vals=z, rays_d=rd,
+        **flat_outputs("white.", o_w), **flat_outputs("black.", o_b), **flat_outputs("star.", s_te))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--only-degenerate" in sys.argv:   # added after the other fixtures were committed: leaves them untouched
+        degenerate_fixture(ref_harness.load_reference())
+        return
     if "--only-rays" in sys.argv:      # added after the other fixtures were committed: leaves them untouched
         rays_fixture(ref_harness.load_reference())
         return
