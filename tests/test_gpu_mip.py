@@ -291,6 +291,19 @@ def test_mip_star_training_step_gradients_reach_weights_and_pose():
     assert float(pose_g.grad[:, 6].abs().max()) == 0.0
 
 
+def test_mip_empty_ray_batch_gives_empty_outputs():
+    """R = 0 through the mip variant's forward (app-init branch, both tiers): empty outputs of the right shapes, no launch."""
+    net, _ = make_net(0, 16, 24, 4096, seed=3, training=False)
+    ro = torch.zeros(0, 3, device=DEV)
+    for prec in ("fp32", "fp16"):
+        net.set_precision(prec)
+        with torch.no_grad():
+            out = net(ro, ro, None)
+        assert out["rgb"].shape == (0, 3) and out["rgb0"].shape == (0, 3)
+        assert out["weights"].shape[0] == 0 and out["acc"].shape[0] == 0
+    torch.cuda.synchronize()
+
+
 def test_mip_error_paths():
     net, _ = make_net(1, 4, 4, 64, seed=1, training=False)
     ro, vd = rays(3, 1)
