@@ -567,10 +567,11 @@ def run_b200(args):
         for name, wk, mode, rays in (("c3_train", "c3", "train", 4096), ("c3_train_r1000", "c3", "train", 1000),
                                      ("c4_train", "c4", "train", 8192), ("c4_train_r1000", "c4", "train", 1000),
                                      ("c4_render", "c4", "render", 65536), ("c5_render", "c5", "render", 16384),
+                                     ("c5_frame_render", "c5", "render", 1280 * 720),      # one whole frame of configs[4]
                                      ("c5_train", "c5", "train", 4096)):
             a3 = argparse.Namespace(**vars(args))
             a3.workload, a3.mode, a3.rays, a3.no_cpu_baseline, a3.opt_step = wk, mode, rays, True, False
-            a3.steps, a3.warmup = min(args.steps, 5), 3
+            a3.steps, a3.warmup = min(args.steps, 2 if rays > 500000 else 5), 3
             t = measure(a3)
             if rank == 0:
                 line[name] = {k: t[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline", "gpu_launches",
