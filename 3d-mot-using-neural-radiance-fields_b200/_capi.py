@@ -16,6 +16,7 @@ ABI_VERSION = 2
 PREC_F32, PREC_BF16, PREC_F16 = 0, 1, 2
 PREC_FLAG_RETIRED = 0x300      # round-2 A/B variants of the forward kernels (CTA pair, direct stash stores): rejected
 PREC_FLAG_DX_PIPELINED = 0x400
+PREC_FLAG_NO_WSHARE = 0x800     # inference forward: every CTA streams its own weights (default: cluster of 2 shares them)
 PRECISIONS = {"fp32": PREC_F32, "bf16": PREC_BF16, "fp16": PREC_F16}
 
 c_f = C.c_void_p      # device pointers are passed as raw addresses

@@ -144,7 +144,9 @@ extern "C" int star_mlp_forward(const StarNetDesc* d, const void* packed, const 
     rc = star_make_tc_layout(d, &tl);
     if (rc) return rc;
     return star_tc_forward(tl, packed, pts, viewdirs, pose12, enc_scale_xyz, enc_scale_dir, R, S, raw_alpha, raw_rgb,
-                           alpha_ray_stride, stash, status, star_prec(d) == STAR_PREC_F16, (cudaStream_t)stream);
+                           alpha_ray_stride, stash, status,
+                           (star_prec(d) == STAR_PREC_F16 ? 1 : 0) | ((d->precision & STAR_PREC_FLAG_NO_WSHARE) ? 2 : 0),
+                           (cudaStream_t)stream);
   }
   return STAR_E_UNSUPPORTED;
 }

@@ -53,6 +53,19 @@
 #ifndef TC_STASH_COPY_WARP
 #define TC_STASH_COPY_WARP 0
 #endif
+// Inference variant: two CTAs of a cluster SHARE the weight stream (TC_WSHARE = 1): each fetches half of every weight K-block
+// from L2 and multicasts it into both CTAs' ring stage, so the L2 -> SM weight traffic (1.6 MB per tile and SM, 9.4 TB/s over
+// the chip) halves.  Everything else stays per CTA (own tiles, own MMAs / TMEM / epilogue -- no cta_group::2, no cross-CTA
+// hand-off on the layer chain): the only coupling is the ring itself -- a stage is refilled when BOTH CTAs' MMAs have released
+// it (w_empty counts 2: every issuer's commit is multicast to both CTAs).
+#ifndef TC_WSHARE
+#define TC_WSHARE 1      // A/B on one box (profiles/r2zz_ab_wshare.txt): C2 render 2.808 -> 2.880 M rays/s, 1668 -> 1684 MHz under the power cap
+#endif
+// the same for the training (stash) forward -- A/B switch (the stash is sized for an even number of tiles, star_stash_bytes, so a
+// ghost tile's blocks land in the spare one)
+#ifndef TC_WSHARE_STASH
+#define TC_WSHARE_STASH 1      // A/B (profiles/r2zz_ab_wshare_stash.txt): stash forward 2.085 -> 2.027 ms per 4096-ray step
+#endif
 #define TC_THREADS_STASH (TC_THREADS + (TC_STASH_COPY_WARP ? 32 : 0))
 
 #ifndef TC_LD_DEPTH
@@ -246,7 +259,7 @@ __device__ __noinline__ void tc_encode_dirs(float dx, float dy, float dz, const 
 // of tile t + 1 run while the view layer's epilogue of tile t (rgb head, raw outputs) is busy: the accumulator regions have
 // one completion barrier each (X: lin_in / fc_1 / feature_linear, T: fc_0 / lin_out / view layer), so lin_in (t + 1) -> X
 // can complete before the view layer's accumulator T has been read.
-template <bool FP16, bool STASH>
+template <bool FP16, bool STASH, bool WSHARE = false>
 __global__ void __launch_bounds__(STASH ? TC_THREADS_STASH : TC_THREADS, 1)
 mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const StarPtsSrc pts,
                   const float* __restrict__ viewdirs, const float* __restrict__ pose12,
@@ -285,8 +298,11 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
   auto bar = [&](int i) -> uint32_t { return sBars + 8u * (uint32_t)i; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t ntiles = (M + TC_M - 1) / TC_M;
+  // (WSHARE: the two CTAs of a cluster walk the ring in lock step and must make the same number of trips: the tile count is
+  //  rounded up to even -- the grid is even -- and a tile beyond the launch is a ghost: zero inputs, no outputs)
+  const int64_t ntiles = WSHARE ? (((M + TC_M - 1) / TC_M + 1) & ~(int64_t)1) : (M + TC_M - 1) / TC_M;
   const int64_t tile0 = (int64_t)blockIdx.x, tile_step = (int64_t)gridDim.x;
+  const uint32_t crank = WSHARE ? cluster_ctarank() : 0u;
   const uint32_t slots_per_tile = 1u + (uint32_t)lay.n_stages;
   const long long t_start = clock64();
 #ifdef STAR_TC_TIMELINE
@@ -307,7 +323,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
   // ---- one-time setup
   if (warp == TC_EPI_WARPS && lane == 0) {
     // w_full: the producer (+ its bytes) and the 16 epilogue warps (operand block of the same K-block)
-    for (int i = 0; i < NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), 1 + TC_EPI_WARPS); mbar_init(bar(BAR_W_EMPTY(i)), 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), 1 + TC_EPI_WARPS); mbar_init(bar(BAR_W_EMPTY(i)), WSHARE ? 2 : 1); }
     for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A_READY(i)), TC_EPI_WARPS);
     mbar_init(bar(BAR_ACC_FULL), 1);
     mbar_init(bar(BAR_ACC_FULL_T), 1);
@@ -323,6 +339,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (WSHARE) cluster_sync_all();      // the peer's barriers are initialised before anything of this CTA reaches them
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
@@ -375,8 +392,15 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
               mbar_arrive(bar(BAR_W_FULL(stage)));
             } else {
               mbar_arrive_expect_tx(bar(BAR_W_FULL(stage)), kb_bytes);
-              bulk_g2s(sW + stage * STAGE_BYTES, wstream + lay.L[l].w_off + (uint32_t)kb * kb_bytes, kb_bytes,
-                       bar(BAR_W_FULL(stage)));
+              if (WSHARE) {      // this CTA's half of the K-block, into both CTAs' stage (each half signals both w_full barriers)
+                const uint32_t half = kb_bytes >> 1;
+                bulk_g2s_mcast(sW + stage * STAGE_BYTES + crank * half,
+                               wstream + lay.L[l].w_off + (uint32_t)kb * kb_bytes + crank * half, half,
+                               bar(BAR_W_FULL(stage)), (uint16_t)3);
+              } else {
+                bulk_g2s(sW + stage * STAGE_BYTES, wstream + lay.L[l].w_off + (uint32_t)kb * kb_bytes, kb_bytes,
+                         bar(BAR_W_FULL(stage)));
+              }
             }
             if (++stage == NS) { stage = 0; phase ^= 1u; }
           }
@@ -463,8 +487,13 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
               if (src == 1) tc_mma_kblock<2>(d_tmem, a0, b0, idesc, acc0);
               else tc_mma_kblock<4>(d_tmem, a0, b0, idesc, acc0);
             }
-            if (src == 2) tc_commit(bar(BAR_W_EMPTY(stage_s)));
-            tc_commit(bar(BAR_W_EMPTY(stage)));
+            if (WSHARE) {        // a stage is free when BOTH CTAs' MMAs have read it
+              if (src == 2) tc_commit_mcast(bar(BAR_W_EMPTY(stage_s)), (uint16_t)3);
+              tc_commit_mcast(bar(BAR_W_EMPTY(stage)), (uint16_t)3);
+            } else {
+              if (src == 2) tc_commit(bar(BAR_W_EMPTY(stage_s)));
+              tc_commit(bar(BAR_W_EMPTY(stage)));
+            }
             if (kb == nkb - 1) tc_commit(acc_bar);
           }
           __syncwarp();
@@ -619,6 +648,7 @@ mlp_fwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
   // ---- teardown
   tc_fence_before();
   __syncthreads();
+  if (WSHARE) cluster_sync_all();      // no CTA leaves while its peer's commits / copies can still land in it
   tc_mark_end(dbg);
 #ifdef STAR_TC_DEBUG
   if (dbg != nullptr && tid == 0 && blockIdx.x == 0) {   // debug only: cycles of CTA 0 (see star_tc_forward)
@@ -711,7 +741,8 @@ int star_tc_pack(const TcLayout& tl, const MlpLayout& ml, const float* master, v
 
 int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pts, const float* viewdirs,
                     const float* pose12, const float* sc_xyz, const float* sc_dir, int R, int S, float* raw_alpha,
-                    float* raw_rgb, int64_t ray_stride, void* stash, int* status, int fp16, cudaStream_t st) {
+                    float* raw_rgb, int64_t ray_stride, void* stash, int* status, int fp16_flags, cudaStream_t st) {
+  const bool fp16 = (fp16_flags & 1) != 0, no_wshare = (fp16_flags & 2) != 0;   // bit 1: STAR_PREC_FLAG_NO_WSHARE
   const int64_t M = (int64_t)R * S;
   const int64_t ntiles = (M + TC_M - 1) / TC_M;
   int dev = 0, sms = 148;
@@ -723,11 +754,30 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pt
   const int grid = (int)(ntiles < sms ? ntiles : sms);       // persistent: one CTA per SM over the tiles
   using Kern = void (*)(const TcLayout, const uint8_t*, const StarPtsSrc, const float*, const float*, const float*,
                         const float*, int, int64_t, float*, float*, int64_t, uint8_t*, int*, int*, int);
-  Kern kern = with_stash ? (fp16 ? mlp_fwd_tc_kernel<true, true> : mlp_fwd_tc_kernel<false, true>)
+  const bool wshare = TC_WSHARE && !no_wshare && (!with_stash || TC_WSHARE_STASH) && ntiles >= 2 * (int64_t)sms;
+  Kern kern = with_stash ? (wshare && TC_WSHARE_STASH ? (fp16 ? mlp_fwd_tc_kernel<true, true, TC_WSHARE_STASH != 0>
+                                                              : mlp_fwd_tc_kernel<false, true, TC_WSHARE_STASH != 0>)
+                                                      : (fp16 ? mlp_fwd_tc_kernel<true, true> : mlp_fwd_tc_kernel<false, true>))
+              : wshare   ? (fp16 ? mlp_fwd_tc_kernel<true, false, true> : mlp_fwd_tc_kernel<false, false, true>)
                          : (fp16 ? mlp_fwd_tc_kernel<true, false> : mlp_fwd_tc_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
   if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
   auto launch = [&](int* dbg, int dbg_mode) -> int {
+    if (wshare) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(grid & ~1), 1, 1);
+      cfg.blockDim = dim3(with_stash ? TC_THREADS_STASH : TC_THREADS, 1, 1);
+      cfg.dynamicSmemBytes = sl.total;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
+                                                raw_alpha, raw_rgb, ray_stride, (uint8_t*)stash, status, dbg, dbg_mode);
+      if (le != cudaSuccess) { g_star_last_cuda_error = (int)le; return STAR_E_CUDA; }
+      return STAR_OK;
+    }
     kern<<<grid, with_stash ? TC_THREADS_STASH : TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
                                              raw_alpha, raw_rgb, ray_stride, (uint8_t*)stash, status, dbg, dbg_mode);
     return STAR_OK;

@@ -66,7 +66,7 @@ int run_net(const StarRenderCfg& c, int n_blocks, const void* packed, const Star
     rc = star_make_tc_layout(&d, &tl);
     if (rc) return rc;
     return star_tc_forward(tl, packed, pts, viewdirs, pose12, sc_xyz, sc_dir, c.R, S, raw_alpha, raw_rgb, ray_stride,
-                           nullptr, status, prec == STAR_PREC_F16, st);
+                           nullptr, status, (prec == STAR_PREC_F16 ? 1 : 0) | ((c.precision & STAR_PREC_FLAG_NO_WSHARE) ? 2 : 0), st);
   }
   return STAR_E_UNSUPPORTED;
 }

@@ -20,6 +20,7 @@ STASH_BUDGET_BYTES = int(float(os.environ.get("STAR_B200_STASH_GB", "24")) * (1 
 # A/B switch: run the tensor-core forward on the CTA-pair (cta_group::2) kernels instead of the one-CTA-per-SM ones (same
 # results, measured slower: see include/star_b200.h)
 TC_DX_PIPELINED = os.environ.get("STAR_B200_DX_PIPELINED", "0") == "1"
+TC_NO_WSHARE = os.environ.get("STAR_B200_NO_WSHARE", "0") == "1"      # A/B: opt out of the weight-sharing cluster launch
 
 # instrumentation for bench.py: number of kernel-launching C-ABI calls issued
 LAUNCH_COUNTER = {"calls": 0}
@@ -367,6 +368,8 @@ class NetRuntime:
     def desc(self, precision):
         if TC_DX_PIPELINED and precision != _capi.PREC_F32:
             precision = precision | _capi.PREC_FLAG_DX_PIPELINED
+        if TC_NO_WSHARE and precision != _capi.PREC_F32:
+            precision = precision | _capi.PREC_FLAG_NO_WSHARE
         return _capi.net_desc(self.n_blocks, self.L_xyz, self.L_dir, precision)
 
     def refresh(self, precision):
@@ -624,7 +627,7 @@ def render_forward(static_nets, dynamic_nets, precision, rays_o, rays_d, viewdir
     else:
         Nc = int(N_samples)
     Nf = Nc + Ni
-    cfg = _capi.StarRenderCfg(R, Nc, Ni, V, int(precision), sc_net._rt.n_blocks, dyn_c[0]._rt.n_blocks if V else 2,
+    cfg = _capi.StarRenderCfg(R, Nc, Ni, V, int(precision) | (_capi.PREC_FLAG_NO_WSHARE if TC_NO_WSHARE and int(precision) != _capi.PREC_F32 else 0), sc_net._rt.n_blocks, dyn_c[0]._rt.n_blocks if V else 2,
                               sc_net._rt.L_xyz, sc_net._rt.L_dir, int(bool(white_bkgd)), int(bool(lindisp)),
                               int(bool(test)), int(chunk or max(R, 1)), float(near or 0.0), float(far or 0.0),
                               float(far_dist))

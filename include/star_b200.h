@@ -59,6 +59,12 @@ enum { STAR_PREC_F32 = 0, STAR_PREC_BF16 = 1, STAR_PREC_F16 = 2 };
  * (dX + dW + heads 5.09 against 4.79 ms per 4096-ray step: twice as many stages and N = 128 MMAs make the single issuing thread
  * the bottleneck), so it is opt-in. */
 #define STAR_PREC_FLAG_DX_PIPELINED 0x400
+/* inference forward, opt-OUT of the weight-sharing cluster launch: by default (launches of at least two tiles per SM) the two
+ * CTAs of a cluster of 2 each fetch half of every weight K-block from L2 and multicast it into both CTAs' shared-memory ring,
+ * which halves the L2 -> SM weight traffic (1.6 MB per tile and SM); with this bit every CTA streams its own weights.  Same
+ * arithmetic, bit-identical outputs (tests/test_gpu_bf16.py); measured 2.81 -> 2.88 M rays/s on the C2 render
+ * (profiles/r2zz_ab_wshare.txt). */
+#define STAR_PREC_FLAG_NO_WSHARE 0x800
 
 /* One NeRF radiance MLP (models/nerf.py:34-110, models/resnet.py:62-110).  W is fixed at 256,
  * the view branch at 128 (all 15 reference configs agree). */

@@ -362,6 +362,39 @@ def test_retired_variant_flags_are_rejected():
 
 
 @pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_weight_sharing_cluster_launch_is_bit_identical(prec, monkeypatch):
+    """Inference launches of at least two tiles per SM run as clusters of 2 whose CTAs each fetch half of every weight K-block
+    and multicast it to both (STAR_PREC_FLAG_NO_WSHARE opts out): same arithmetic -> the same bits, for even and odd tile
+    counts (the odd one rounds up to a ghost tile), static and object nets, through star_mlp_forward and star_render_forward."""
+    net, _ = make_star(1, 24, 4096, False, seed=23, training=False, precision=prec)
+    for R, S, dyn in ((700, 64, False), (673, 67, False), (673, 67, True), (2051, 19, True)):
+        assert R * S >= 2 * 148 * 128
+        module = net.dynamic_coarse_nerfs[0] if dyn else net.static_coarse_nerf
+        ro, rd = so.carla_rays(R, seed=8)
+        vd = rd / rd.norm(dim=-1, keepdim=True)
+        pts, _ = so.sample_pts(ro, rd, 0.03, 0.8, S)
+        pose = cu(so.pose7_to_matrix(so.random_poses7(1, seed=9))[0])
+        res = {}
+        for off in (False, True):
+            monkeypatch.setattr(F_, "TC_NO_WSHARE", off)
+            with torch.no_grad():
+                res[off] = module.raw(cu(pts), cu(vd), F_.pose_to_mat12(pose) if dyn else None)
+        assert torch.equal(res[False][0], res[True][0]) and torch.equal(res[False][1], res[True][1]), (R, S, dyn)
+    ro, rd = so.carla_rays(1500, seed=9)
+    ro, rd = cu(ro), cu(rd)
+    vd = rd / rd.norm(dim=-1, keepdim=True)
+    pose = cu(so.random_poses7(1, seed=3))
+    outs = {}
+    for off in (False, True):
+        monkeypatch.setattr(F_, "TC_NO_WSHARE", off)
+        with torch.no_grad():
+            pts, z = R_.sample_pts(ro, rd, 0.03, 0.8, 32, is_train=False)
+            outs[off] = R_.render_star_online(net, pts, vd, z, ro, rd, 24, pose)
+    for k in ("rgb", "rgb0", "weights", "depth", "rgb_dynamic"):
+        assert torch.equal(outs[False][k], outs[True][k]), k
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
 def test_pipelined_dx_chain_gives_the_gradients_of_the_serial_one(prec, monkeypatch):
     """The opt-in pipelined dX kernel (N = 128 halves, per-block b_done / stash_done barriers) against the default serial one:
     the same GEMMs in the same K order -> the same gradient stash, hence equal weight and pose gradients up to the dW atomics."""
