@@ -160,13 +160,19 @@ __global__ void grad_absmax_kernel(const float* __restrict__ d_alpha, const floa
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(absmax), __float_as_uint(m));
 }
 
+#ifndef TC_WSHARE_DX
+// 1: the dX chain's (transposed) weight stream shared by the two CTAs of a cluster, as in the forward kernels.  Built, GPU
+// tests green with it, measured NEUTRAL (dX + dW + heads 4.73-4.76 against 4.74 ms per 4096-ray step,
+// profiles/r2zz_ab_wshare_dx.txt): the serial MMA / epilogue alternation of this kernel does not wait for weights.
+#define TC_WSHARE_DX 0
+#endif
 #ifndef TC_DX_DEFER_WAIT_ST
 #define TC_DX_DEFER_WAIT_ST 0  // 1: one tcgen05.wait::st per phase instead of one per chunk -- measured no gain (bwd 4.68 / 4.82 vs 4.65 / 4.70 ms, profiles/r2z_ab_defer_wait_st.txt)
 #endif
 #ifndef TC_DX_LD_DEPTH
 #define TC_DX_LD_DEPTH 2       // accumulator chunk loads in flight per epilogue thread of the dX chain (1 = load, wait, use)
 #endif
-template <bool F16, bool POSE>
+template <bool F16, bool POSE, bool WSHARE = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const StarPtsSrc pts,
                   const float* __restrict__ viewdirs, const float* __restrict__ pose12,
@@ -188,7 +194,10 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(gbase + sl.tmem_ptr);
   auto bar = [&](int i) -> uint32_t { return sBars + 8u * (uint32_t)i; };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t ntiles = (M + TC_M - 1) / TC_M;
+  // WSHARE (mlp_tc.cu: the two CTAs of a cluster share the weight stream): an even number of trips per cluster; a tile beyond
+  // the launch is a ghost (zero gradients, its blocks land in the spare tile of the even-sized stashes)
+  const int64_t ntiles = WSHARE ? (((M + TC_M - 1) / TC_M + 1) & ~(int64_t)1) : (M + TC_M - 1) / TC_M;
+  const uint32_t crank = WSHARE ? cluster_ctarank() : 0u;
   constexpr bool has_pose = POSE;   // object nets: pose accumulators and two extra GEMMs (compiled out for the static net)
   // accumulator chunk loads in flight per epilogue thread: the second buffer (measured neutral on the static net) would push
   // the object nets' epilogue past the 96 registers 576 threads leave, into spills inside the chunk loop
@@ -240,7 +249,7 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
     counts[0] = ns; counts[1] = np;
   }
   if (warp == TC_EPI_WARPS && lane == 0) {
-    for (int i = 0; i < TC_NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), 1); mbar_init(bar(BAR_W_EMPTY(i)), 1); }
+    for (int i = 0; i < TC_NS; ++i) { mbar_init(bar(BAR_W_FULL(i)), 1); mbar_init(bar(BAR_W_EMPTY(i)), WSHARE ? 2 : 1); }
     for (int i = 0; i < 5; ++i) mbar_init(bar(BAR_A_READY(i)), TC_EPI_WARPS);
     mbar_init(bar(BAR_ACC_FULL), 1);
     mbar_init(bar(BAR_STASH_DONE), 1);
@@ -251,6 +260,7 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (WSHARE) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   const int n_stages = counts[0], n_phases = counts[1];
@@ -288,7 +298,13 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           group_start = false;
           mbar_wait(bar(BAR_W_EMPTY(stage)), phase ^ 1u, dbg, 1);
           mbar_arrive_expect_tx(bar(BAR_W_FULL(stage)), s.bytes);
-          bulk_g2s(sW + stage * TC_STAGE_BYTES, packed + lay.small_bytes + s.w_off, s.bytes, bar(BAR_W_FULL(stage)));
+          if (WSHARE) {
+            const uint32_t half = s.bytes >> 1;
+            bulk_g2s_mcast(sW + stage * TC_STAGE_BYTES + crank * half, packed + lay.small_bytes + s.w_off + crank * half, half,
+                           bar(BAR_W_FULL(stage)), (uint16_t)3);
+          } else {
+            bulk_g2s(sW + stage * TC_STAGE_BYTES, packed + lay.small_bytes + s.w_off, s.bytes, bar(BAR_W_FULL(stage)));
+          }
           if (++stage == TC_NS) { stage = 0; phase ^= 1u; }
           if (s.last) { ++grp; group_start = true; }
         }
@@ -322,7 +338,8 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
           const uint64_t b0 = desc_w0 + (uint64_t)(stage * (TC_STAGE_BYTES >> 4));
           if (elect_one_sync()) {
             tc_mma_kblock<4>(tmem_base + (uint32_t)s.tcol, a0, b0, idesc, s.accum ? 1u : 0u);   // every stage has 4 K-steps
-            tc_commit(bar(BAR_W_EMPTY(stage)));
+            if (WSHARE) tc_commit_mcast(bar(BAR_W_EMPTY(stage)), (uint16_t)3);
+            else tc_commit(bar(BAR_W_EMPTY(stage)));
             if (s.last) tc_commit(bar(BAR_ACC_FULL));
           }
           __syncwarp();
@@ -547,6 +564,7 @@ mlp_bwd_tc_kernel(const TcLayout lay, const uint8_t* __restrict__ packed, const 
 
   tc_fence_before();
   __syncthreads();
+  if (WSHARE) cluster_sync_all();      // no CTA leaves while its peer's commits / copies can still land in it
   tc_mark_end(dbg);
   if (warp == TC_EPI_WARPS + 1) {
     tc_fence_after();
@@ -1465,13 +1483,36 @@ int star_tc_backward(const TcLayout& tl, const MlpLayout& ml, const void* packed
   } else {
     const int grid = (int)(ntiles < sms ? ntiles : sms);
     const BwdSmem sl = bwd_smem_layout(tl.small_bytes);
-    auto kern = pose12 != nullptr ? (fp16 ? mlp_bwd_tc_kernel<true, true> : mlp_bwd_tc_kernel<false, true>)
-                                  : (fp16 ? mlp_bwd_tc_kernel<true, false> : mlp_bwd_tc_kernel<false, false>);
+    // TC_WSHARE_DX: clusters of 2 share the (transposed) weight stream as in the forward kernels (mlp_tc.cu)
+    const bool wshare = TC_WSHARE_DX && ntiles >= 2 * (int64_t)sms;
+    using KernDx = void (*)(const TcLayout, const uint8_t*, const StarPtsSrc, const float*, const float*, const float*,
+                            const float*, int, int64_t, const float*, const float*, int64_t, const uint8_t*, uint8_t*, float*,
+                            const float*, int*);
+    KernDx kern = wshare ? (pose12 != nullptr ? (fp16 ? mlp_bwd_tc_kernel<true, true, TC_WSHARE_DX != 0> : mlp_bwd_tc_kernel<false, true, TC_WSHARE_DX != 0>)
+                                              : (fp16 ? mlp_bwd_tc_kernel<true, false, TC_WSHARE_DX != 0> : mlp_bwd_tc_kernel<false, false, TC_WSHARE_DX != 0>))
+                         : (pose12 != nullptr ? (fp16 ? mlp_bwd_tc_kernel<true, true> : mlp_bwd_tc_kernel<false, true>)
+                                              : (fp16 ? mlp_bwd_tc_kernel<true, false> : mlp_bwd_tc_kernel<false, false>));
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
     if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
-    kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
-                                              d_raw_alpha, d_raw_rgb, ray_stride, (const uint8_t*)stash, (uint8_t*)gstash,
-                                              pose_acc, absmax, star_watchdog_dev(STAR_WD_DX));
+    if (wshare) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(grid & ~1), 1, 1);
+      cfg.blockDim = dim3(TC_THREADS, 1, 1);
+      cfg.dynamicSmemBytes = sl.total;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
+                                                d_raw_alpha, d_raw_rgb, ray_stride, (const uint8_t*)stash, (uint8_t*)gstash,
+                                                pose_acc, (const float*)absmax, star_watchdog_dev(STAR_WD_DX));
+      if (le != cudaSuccess) { g_star_last_cuda_error = (int)le; return STAR_E_CUDA; }
+    } else {
+      kern<<<grid, TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
+                                                d_raw_alpha, d_raw_rgb, ray_stride, (const uint8_t*)stash, (uint8_t*)gstash,
+                                                pose_acc, absmax, star_watchdog_dev(STAR_WD_DX));
+    }
     int rc = star_check_launch();
     if (rc) return rc;
   }
