@@ -58,6 +58,19 @@
 // the chip) halves.  Everything else stays per CTA (own tiles, own MMAs / TMEM / epilogue -- no cta_group::2, no cross-CTA
 // hand-off on the layer chain): the only coupling is the ring itself -- a stage is refilled when BOTH CTAs' MMAs have released
 // it (w_empty counts 2: every issuer's commit is multicast to both CTAs).
+// Why the shared ring is race-free (the argument the barrier counts rest on):
+//  * A stage use n of CTA A is loaded only after A's w_empty[stage] saw BOTH commits of use n - 1.  The peer's commit follows
+//    the peer's MMAs of use n - 1, which waited for the peer's w_full[stage] phase n - 1: so when A's half of use n lands in the
+//    peer (bytes + complete_tx on the peer's w_full[stage]) the peer's phase n - 1 is complete and the bytes count into phase n
+//    -- possibly before the peer's own expect_tx of phase n (a negative transaction count is legal; the phase cannot complete
+//    before the peer's producer arrival), and the peer's MMAs of use n - 1 no longer read the stage.  The same holds for the
+//    uses whose w_full arrivals all come from the producer (slot S, the dirs K-block): the producer posts them, in program
+//    order, before it requests the next weights, so a later commit of the peer implies they have been posted.
+//  * w_empty[stage] receives exactly two commits per use (both CTAs run the same layer program over the same number of
+//    tiles); use n + 1 cannot be committed by either CTA before BOTH producers have observed phase n (its weights are
+//    requested after that observation), so no waiter -- the producer, or the epilogue warps that own slot S -- can miss a phase.
+//  * Cluster barriers after the mbarrier initialisation and before exit keep the peer's copies / commits inside the lifetime
+//    of the shared memory they target.
 #ifndef TC_WSHARE
 #define TC_WSHARE 1      // A/B on one box (profiles/r2zz_ab_wshare.txt): C2 render 2.808 -> 2.880 M rays/s, 1668 -> 1684 MHz under the power cap
 #endif
