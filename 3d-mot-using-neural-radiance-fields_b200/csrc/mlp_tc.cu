@@ -767,7 +767,13 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pt
   const int grid = (int)(ntiles < sms ? ntiles : sms);       // persistent: one CTA per SM over the tiles
   using Kern = void (*)(const TcLayout, const uint8_t*, const StarPtsSrc, const float*, const float*, const float*,
                         const float*, int, int64_t, float*, float*, int64_t, uint8_t*, int*, int*, int);
-  const bool wshare = TC_WSHARE && !no_wshare && (!with_stash || TC_WSHARE_STASH) && ntiles >= 2 * (int64_t)sms;
+  // (a device / partition that refuses the cluster launch -- a synchronous launch error, nothing has run -- gets the plain
+  //  launch of the same kernel family from then on, with one line on stderr: a launch shape, not a numerical fallback)
+  static bool s_cluster_refused = false;
+  const bool wshare = TC_WSHARE && !no_wshare && !s_cluster_refused && (!with_stash || TC_WSHARE_STASH) &&
+                      ntiles >= 2 * (int64_t)sms;
+  Kern kern_plain = with_stash ? (fp16 ? mlp_fwd_tc_kernel<true, true> : mlp_fwd_tc_kernel<false, true>)
+                               : (fp16 ? mlp_fwd_tc_kernel<true, false> : mlp_fwd_tc_kernel<false, false>);
   Kern kern = with_stash ? (wshare && TC_WSHARE_STASH ? (fp16 ? mlp_fwd_tc_kernel<true, true, TC_WSHARE_STASH != 0>
                                                               : mlp_fwd_tc_kernel<false, true, TC_WSHARE_STASH != 0>)
                                                       : (fp16 ? mlp_fwd_tc_kernel<true, true> : mlp_fwd_tc_kernel<false, true>))
@@ -775,6 +781,10 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pt
                          : (fp16 ? mlp_fwd_tc_kernel<true, false> : mlp_fwd_tc_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
   if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
+  if (kern_plain != kern) {
+    e = cudaFuncSetAttribute(kern_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
+    if (e != cudaSuccess) { g_star_last_cuda_error = (int)e; return STAR_E_CUDA; }
+  }
   auto launch = [&](int* dbg, int dbg_mode) -> int {
     if (wshare) {
       cudaLaunchConfig_t cfg = {};
@@ -788,10 +798,13 @@ int star_tc_forward(const TcLayout& tl, const void* packed, const StarPtsSrc& pt
       cfg.attrs = at; cfg.numAttrs = 1;
       const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
                                                 raw_alpha, raw_rgb, ray_stride, (uint8_t*)stash, status, dbg, dbg_mode);
-      if (le != cudaSuccess) { g_star_last_cuda_error = (int)le; return STAR_E_CUDA; }
-      return STAR_OK;
+      if (le == cudaSuccess) return STAR_OK;
+      (void)cudaGetLastError();      // the refused launch leaves a (non-sticky) error behind
+      s_cluster_refused = true;
+      fprintf(stderr, "[star_b200] cluster launch of the MLP forward refused (%s): one CTA per SM streams its own weights\n",
+              cudaGetErrorString(le));
     }
-    kern<<<grid, with_stash ? TC_THREADS_STASH : TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
+    kern_plain<<<grid, with_stash ? TC_THREADS_STASH : TC_THREADS, sl.total, st>>>(tl, (const uint8_t*)packed, pts, viewdirs, pose12, sc_xyz, sc_dir, S, M,
                                              raw_alpha, raw_rgb, ray_stride, (uint8_t*)stash, status, dbg, dbg_mode);
     return STAR_OK;
   };
