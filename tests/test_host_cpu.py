@@ -28,6 +28,22 @@ def test_library_exports_every_declared_symbol():
     assert lib.star_abi_version() == _capi.ABI_VERSION
 
 
+def test_python_constants_match_the_header():
+    """The precision tiers and flag bits of include/star_b200.h and the status codes the binding names must be the same
+    numbers in _capi.py (the C ABI is the contract; ctypes passes plain ints)."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "star_b200.h")).read()
+    defs = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+(STAR_\w+)\s+(0x[0-9a-fA-F]+|\d+)\b", hdr)}
+    enum = re.search(r"enum\s*\{\s*STAR_PREC_F32\s*=\s*(\d+),\s*STAR_PREC_BF16\s*=\s*(\d+),\s*STAR_PREC_F16\s*=\s*(\d+)", hdr)
+    assert enum and tuple(int(x) for x in enum.groups()) == (_capi.PREC_F32, _capi.PREC_BF16, _capi.PREC_F16)
+    assert defs["STAR_PREC_FLAG_RETIRED"] == _capi.PREC_FLAG_RETIRED
+    assert defs["STAR_PREC_FLAG_DX_PIPELINED"] == _capi.PREC_FLAG_DX_PIPELINED
+    assert defs["STAR_PREC_FLAG_NO_WSHARE"] == _capi.PREC_FLAG_NO_WSHARE
+    flags = [_capi.PREC_FLAG_RETIRED, _capi.PREC_FLAG_DX_PIPELINED, _capi.PREC_FLAG_NO_WSHARE]
+    assert all(f & 0xff == 0 for f in flags) and len(set(flags)) == 3          # the low byte is the tier
+    assert (_capi.PREC_FLAG_DX_PIPELINED & _capi.PREC_FLAG_NO_WSHARE) == 0
+
+
 def test_param_counts_and_packed_sizes():
     import ctypes as C
     lib = _capi.lib()
