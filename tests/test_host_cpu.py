@@ -204,6 +204,25 @@ def test_c_abi_argument_checks_need_no_gpu():
     assert lib.star_mlp_forward(C.byref(d), None, None, None, None, None, None, None, None, None, 4, 8, None, None, 8, None, None, None) == 3
 
 
+def test_c_abi_empty_batches_return_ok_without_touching_pointers():
+    """R = 0: an empty batch carries no pointers (torch's data_ptr() of an empty tensor is 0), so every per-ray entry returns
+    STAR_OK before its NULL checks -- and before any CUDA call, which is why this runs without a GPU."""
+    import ctypes as C
+    lib = _capi.lib()
+    assert lib.star_sample_pts(None, None, None, None, 0.0, 1.0, 0, 8, 0, None, None, None) == 0
+    assert lib.star_sample_pts(None, None, None, None, 0.0, 1.0, -1, 8, 0, None, None, None) != 0
+    assert lib.star_mip_uniform_bins(None, None, 0.0, 1.0, 0, 8, None, None, None) == 0
+    assert lib.star_mip_pdf_sample(None, None, 0, None, None, 0.0, 1.0, 0, 8, 8, None, None, None, None, None) == 0
+    assert lib.star_mip_field_forward(0, None, None, None, None, None, None, 0.5, 0, 8, None, None, 8, None, None) == 0
+    assert lib.star_mip_composite_single_forward(None, None, None, 0, 8, None, None, None, None, None) == 0
+    d = _capi.net_desc(4, 10, 4, _capi.PREC_F32)
+    assert lib.star_mlp_forward(C.byref(d), None, None, None, None, None, None, None, None, None, 0, 8, None, None, 8, None,
+                                None, None) == 0
+    for prec in (_capi.PREC_F32, _capi.PREC_F16, _capi.PREC_F16 | _capi.PREC_FLAG_NO_WSHARE):
+        cfg = _capi.StarRenderCfg(0, 64, 128, 0, prec, 4, 2, 10, 4, 1, 0, 1, 8192, 2.0, 6.0, 1e10)
+        assert lib.star_render_forward(C.byref(cfg), None, None, None, 0, None, None) == 0
+
+
 def test_train_step_abi_argument_checks_and_host_logic():
     """status codes of the loss / optimiser entry points without a GPU, the run-merging and
     parameter re-homing logic of optim.py (pure host code), and the no-fallback rule."""
