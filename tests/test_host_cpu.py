@@ -204,6 +204,40 @@ def test_c_abi_argument_checks_need_no_gpu():
     assert lib.star_mlp_forward(C.byref(d), None, None, None, None, None, None, None, None, None, 4, 8, None, None, 8, None, None, None) == 3
 
 
+def test_sass_of_the_mlp_kernels_is_tcgen05_tmem_and_bulk_copies():
+    """What the built library executes on the hot path, read from its SASS (cuobjdump, no GPU): the MLP kernels issue
+    tcgen05.mma (UTCHMMA) with accumulators in TMEM (LDTM), fetch weights with bulk async copies (UBLKCP) -- the inference
+    kernel of the weight-sharing launch with the MULTICAST form and multicast commits (UTCBAR.MULTICAST) inside a cluster
+    (UCGABAR) -- and contain no warp-level HMMA (mma.sync / wmma), the recompiled-baseline path."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    lib = os.path.join(ROOT, "3d-mot-using-neural-radiance-fields_b200", "libstar_b200.so")
+    names = subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True).stdout
+    funs = re.findall(r"Function (\S+):", names)
+
+    def sass(pred):
+        f = [n for n in funs if pred(n)]
+        assert f, "kernel not found in the library"
+        out = subprocess.run(["cuobjdump", "-sass", "-fun", f[0], lib], capture_output=True, text=True).stdout
+        return [m.group(1) for m in re.finditer(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\w+\s+)?([A-Z][\w.]*)", out, re.M)]
+
+    fwd_shared = sass(lambda n: n.startswith("_Z17mlp_fwd_tc_kernelILb1ELb0ELb1E"))       # fp16, inference, weight sharing
+    fwd_plain = sass(lambda n: n.startswith("_Z17mlp_fwd_tc_kernelILb1ELb0ELb0E"))
+    dx = sass(lambda n: n.startswith("_Z17mlp_bwd_tc_kernelILb1ELb0ELb0E"))
+    dw = sass(lambda n: n.startswith("_Z12dw_tc_kernelILb1E"))
+    for name, ops in (("forward (shared weights)", fwd_shared), ("forward", fwd_plain), ("dX chain", dx), ("dW", dw)):
+        assert any(o.startswith("UTCHMMA") for o in ops), name + ": no tcgen05.mma"
+        assert any(o.startswith("LDTM") for o in ops), name + ": no TMEM loads"
+        assert any(o.startswith("UBLKCP") for o in ops), name + ": no bulk async copies"
+        assert not any(o.startswith("HMMA") for o in ops), name + ": warp-level HMMA found"
+    assert any(o.startswith("UBLKCP") and "MULTICAST" in o for o in fwd_shared)
+    assert any(o.startswith("UTCBAR") and "MULTICAST" in o for o in fwd_shared)
+    assert any(o.startswith("UCGABAR") for o in fwd_shared)
+    assert not any("MULTICAST" in o for o in fwd_plain)
+
+
 def test_c_abi_empty_batches_return_ok_without_touching_pointers():
     """R = 0: an empty batch carries no pointers (torch's data_ptr() of an empty tensor is 0), so every per-ray entry returns
     STAR_OK before its NULL checks -- and before any CUDA call, which is why this runs without a GPU."""
