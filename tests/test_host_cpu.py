@@ -238,6 +238,26 @@ def test_sass_of_the_mlp_kernels_is_tcgen05_tmem_and_bulk_copies():
     assert not any("MULTICAST" in o for o in fwd_plain)
 
 
+def test_register_budget_of_the_576_thread_kernels():
+    """The persistent tensor-core kernels run 576 (608 with the optional stash copy warp) threads per CTA: more than 96
+    registers per thread and the launch fails at run time (warps are allocated in fours: 20 x 32 x 96 = 61 440 of 65 536).
+    Read from the built library, no GPU."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    lib = os.path.join(ROOT, "3d-mot-using-neural-radiance-fields_b200", "libstar_b200.so")
+    out = subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True).stdout
+    usage = dict(re.findall(r"Function (\S+):\s*\n\s*REG:(\d+)", out))
+    big = {k: int(v) for k, v in usage.items()
+           if re.match(r"_Z1[78]m(lp|ip)_(fwd|bwd|bwd2)_tc_kernel", k)}
+    assert len(big) >= 20, sorted(big)
+    for k, r in big.items():
+        assert r <= 96, (k, r)
+    hg = [int(v) for k, v in usage.items() if k.startswith("_Z19head_grad_tc_kernel")]
+    assert hg and hg[0] <= 128          # two CTAs of 256 threads per SM
+
+
 def test_c_abi_empty_batches_return_ok_without_touching_pointers():
     """R = 0: an empty batch carries no pointers (torch's data_ptr() of an empty tensor is 0), so every per-ray entry returns
     STAR_OK before its NULL checks -- and before any CUDA call, which is why this runs without a GPU."""
